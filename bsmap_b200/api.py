@@ -1,0 +1,251 @@
+"""Python mirror of the reference's RefSeq / SingleAlign / PairAlign seam over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _l
+from .lib import PAIR_REC, REC, BsxError, IndexInfo, Params, Stats, check, load, strs
+
+
+def make_params(s=16, I=4, v=2, w=1000, r=1, m=28, x=500, n=0, pairend=0, S=0, f=5, L=144,
+                out_sam=1, u=0, R=0, D=None, A=()) -> Params:
+    """Param defaults (param.cpp:6-83) + the side effects of mGetOptions (main.cpp:234-289):
+    -D forces seed 12 / interval 1 whatever -s / -I say (App. B Q17)."""
+    p = Params()
+    p.seed_size, p.index_interval, p.max_snp_num, p.max_num_hits = s, I, v, w
+    p.report_repeat_hits, p.min_insert, p.max_insert, p.chains = r, m, x, n
+    p.pairend, p.randseed, p.max_ns, p.max_readlen = pairend, S, f, L
+    p.out_sam, p.out_unmap, p.out_ref = out_sam, u, R
+    if D:
+        if "-" not in D:
+            raise ValueError("Digestion position not marked, use '-' to mark. example: 'C-CGG'")
+        p.digest_pos = D.index("-")
+        p.digest_site = D.replace("-", "").encode()
+        p.rrbs, p.index_interval, p.seed_size = 1, 1, 12
+    if len(A) > 10:
+        raise ValueError("at most 10 adapters")
+    p.n_adapter = len(A)
+    for i, a in enumerate(A):
+        p.adapter[i].value = a.encode()[:63]
+    return p
+
+
+def pack_reads(seqs, stride=None):
+    """list of bytes -> (uint8[n, stride] zero padded, uint16 lens); stride is a multiple of 16"""
+    n = len(seqs)
+    lens = np.array([min(len(s), 65535) for s in seqs], dtype=np.uint16)
+    need = int(lens.max()) if n else 16
+    stride = stride or max(16, (min(need, 160) + 15) // 16 * 16)
+    buf = np.zeros((n, stride), dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        k = min(len(s), stride)
+        buf[i, :k] = np.frombuffer(s[:k], dtype=np.uint8)
+    return buf, lens
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Index:
+    """RefSeq: 2-bit packed Watson/Crick strands + bisulfite seed table, resident on one GPU."""
+
+    def __init__(self, params: Params, names, seqs, device: int = 0, _handle=None):
+        self.p = params
+        self.device = device
+        if _handle is not None:
+            self.h = _handle
+            return
+        L = load()
+        self._keep = [s if isinstance(s, bytes) else (s.tobytes() if isinstance(s, np.ndarray) else bytes(s)) for s in seqs]
+        lens = np.array([len(s) for s in self._keep], dtype=np.uint32)
+        h = C.c_void_p()
+        check(L.bsx_index_create(C.byref(params), len(names), strs(names), strs(self._keep), lens.ctypes.data, device, C.byref(h)))
+        self.h = h
+        self._keep = None
+
+    @classmethod
+    def from_fasta(cls, params: Params, path: str, device: int = 0):
+        h = C.c_void_p()
+        check(load().bsx_index_create_from_fasta(C.byref(params), path.encode(), device, C.byref(h)))
+        return cls(params, None, None, device, _handle=h)
+
+    @classmethod
+    def from_pointers(cls, params: Params, names, ptrs, lens, device: int = 0):
+        """sequences already in host memory at raw addresses (bench: pinned torch tensors)"""
+        arr = (C.c_char_p * len(names))()
+        for i, a in enumerate(ptrs):
+            arr[i] = C.cast(C.c_void_p(int(a)), C.c_char_p)
+        ln = np.asarray(lens, dtype=np.uint32)
+        h = C.c_void_p()
+        check(load().bsx_index_create(C.byref(params), len(names), strs(names), arr, ln.ctypes.data, device, C.byref(h)))
+        return cls(params, None, None, device, _handle=h)
+
+    @classmethod
+    def text_only(cls, params: Params, names, seqs):
+        """host-only index for the text layer (format_*); cannot map"""
+        keep = [s if isinstance(s, bytes) else bytes(s) for s in seqs]
+        lens = np.array([len(s) for s in keep], dtype=np.uint32)
+        h = C.c_void_p()
+        check(load().bsx_index_create_text_only(C.byref(params), len(names), strs(names), strs(keep), lens.ctypes.data, C.byref(h)))
+        return cls(params, None, None, -1, _handle=h)
+
+    def replicate(self, device: int) -> "Index":
+        """full replica on another GPU over NVLink (cudaMemcpyPeer): the one-time index broadcast"""
+        h = C.c_void_p()
+        check(load().bsx_index_replicate(self.h, device, C.byref(h)))
+        return Index(self.p, None, None, device, _handle=h)
+
+    def meta(self) -> bytes:
+        n = load().bsx_index_meta_size(self.h)
+        b = C.create_string_buffer(n)
+        check(load().bsx_index_meta_export(self.h, b, n))
+        return b.raw
+
+    @classmethod
+    def shell(cls, params: Params, meta: bytes, device: int) -> "Index":
+        h = C.c_void_p()
+        check(load().bsx_index_create_shell(meta, len(meta), device, C.byref(h)))
+        return cls(params, None, None, device, _handle=h)
+
+    def device_buffers(self):
+        ptrs = (C.c_void_p * 5)()
+        sizes = (C.c_size_t * 5)()
+        n = load().bsx_index_device_buffers(self.h, ptrs, sizes, 5)
+        return [(int(ptrs[i] or 0), int(sizes[i])) for i in range(n)]
+
+    @property
+    def info(self) -> IndexInfo:
+        i = IndexInfo()
+        check(load().bsx_index_get_info(self.h, C.byref(i)))
+        return i
+
+    def names(self):
+        return [load().bsx_index_seq_name(self.h, k).decode() for k in range(self.info.n_seq)]
+
+    def download(self, what: str) -> np.ndarray:
+        i = self.info
+        which = {"refcat": (0, i.n_words), "crefcat": (1, i.n_words), "anchor": (2, i.n_seq + 1),
+                 "tab": (3, 2 * i.n_keys + 1), "pos": (4, i.n_entries), "tag": (5, i.n_entries)}[what]
+        out = np.empty(int(which[1]), dtype=np.uint32)
+        check(load().bsx_index_download(self.h, which[0], out.ctypes.data, out.nbytes))
+        return out
+
+    def header(self) -> bytes:
+        n = load().bsx_format_header(self.h, None, 0)
+        b = C.create_string_buffer(n + 1)
+        load().bsx_format_header(self.h, b, n + 1)
+        return b.raw[:n]
+
+    def close(self):
+        if getattr(self, "h", None) and _l._lib is not None:
+            _l._lib.bsx_index_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mapper:
+    """SingleAlign / PairAlign: ImportBatchReads + Do_Batch on the device."""
+
+    def __init__(self, index: Index, params: Params = None, max_batch: int = 1 << 20, stride: int = 160):
+        self.index = index
+        self.p = params or index.p
+        self.max_batch, self.stride = max_batch, stride
+        h = C.c_void_p()
+        check(load().bsx_mapper_create(index.h, C.byref(self.p), max_batch, stride, C.byref(h)))
+        self.h = h
+
+    # --- Do_Batch with host buffers (end to end) ---
+    def map_se(self, buf: np.ndarray, lens: np.ndarray, first_index=0, readset=0, want_counts=True):
+        n = len(lens)
+        assert buf.shape[1] == self.stride and buf.dtype == np.uint8 and buf.flags.c_contiguous
+        out = np.zeros(n, dtype=REC)
+        counts = np.zeros((n, 16), dtype=np.uint16) if want_counts else None
+        check(load().bsx_map_se(self.h, n, buf.ctypes.data, lens.ctypes.data, first_index, readset, out.ctypes.data, _ptr(counts)))
+        return out, counts
+
+    def map_se_ptr(self, n, seq_ptr, len_ptr, out_ptr, counts_ptr=None, first_index=0, readset=0):
+        """raw-address form (pinned host buffers owned by the caller)"""
+        check(load().bsx_map_se(self.h, n, seq_ptr, len_ptr, first_index, readset, out_ptr, counts_ptr))
+
+    def map_pe(self, buf_a, lens_a, buf_b, lens_b, first_index=0):
+        n = len(lens_a)
+        assert buf_a.shape[1] == self.stride and buf_b.shape[1] == self.stride
+        pr = np.zeros(n, dtype=PAIR_REC)
+        ra, rb = np.zeros(n, dtype=REC), np.zeros(n, dtype=REC)
+        ca, cb = np.zeros((n, 16), dtype=np.uint16), np.zeros((n, 16), dtype=np.uint16)
+        check(load().bsx_map_pe(self.h, n, buf_a.ctypes.data, lens_a.ctypes.data, buf_b.ctypes.data, lens_b.ctypes.data,
+                                first_index, pr.ctypes.data, ra.ctypes.data, rb.ctypes.data, ca.ctypes.data, cb.ctypes.data))
+        return pr, ra, rb, ca, cb
+
+    # --- staged form: inputs resident in HBM ---
+    def upload(self, n, seq_ptr, len_ptr, seq_b_ptr=None, len_b_ptr=None, stream=None):
+        check(load().bsx_batch_upload(self.h, n, seq_ptr, len_ptr, seq_b_ptr, len_b_ptr, stream))
+
+    def run_se(self, n, first_index=0, readset=0, stream=None):
+        check(load().bsx_batch_run_se(self.h, n, first_index, readset, stream))
+
+    def run_pe(self, n, first_index=0, stream=None):
+        check(load().bsx_batch_run_pe(self.h, n, first_index, stream))
+
+    def download_se(self, n, want_counts=False, stream=None):
+        out = np.zeros(n, dtype=REC)
+        counts = np.zeros((n, 16), dtype=np.uint16) if want_counts else None
+        check(load().bsx_batch_download_se(self.h, n, out.ctypes.data, _ptr(counts), stream))
+        return out, counts
+
+    def sync(self):
+        check(load().bsx_mapper_sync(self.h))
+
+    def stats(self, reset=False) -> dict:
+        s = Stats()
+        check(load().bsx_mapper_stats(self.h, C.byref(s), 1 if reset else 0))
+        return s.as_dict()
+
+    @property
+    def launches(self) -> int:
+        return int(load().bsx_mapper_launches(self.h))
+
+    def debug_seeds(self, n):
+        out = np.zeros((n, 40), dtype=np.uint32)
+        check(load().bsx_mapper_debug_seeds(self.h, n, out.ctypes.data))
+        return out
+
+    # --- text (s_OutHit & co) ---
+    def format_se(self, names, seqs, quals, recs, counts=None, readset=0):
+        n = len(names)
+        args = (self.index.h, C.byref(self.p), n, strs(names), strs(seqs), strs(quals), readset, recs.ctypes.data, _ptr(counts))
+        na = C.c_uint32(0)
+        need = load().bsx_format_se(*args, None, 0, C.byref(na))
+        b = C.create_string_buffer(need + 1)
+        load().bsx_format_se(*args, b, need + 1, C.byref(na))
+        return b.raw[:need], na.value
+
+    def format_pe(self, names_a, seqs_a, quals_a, names_b, seqs_b, quals_b, pr, ra, rb, ca=None, cb=None):
+        n = len(names_a)
+        args = (self.index.h, C.byref(self.p), n, strs(names_a), strs(seqs_a), strs(quals_a), strs(names_b), strs(seqs_b),
+                strs(quals_b), pr.ctypes.data, ra.ctypes.data, rb.ctypes.data, _ptr(ca), _ptr(cb))
+        nu = C.c_size_t(0)
+        st = (C.c_uint32 * 3)()
+        need = load().bsx_format_pe(*args, None, 0, None, 0, C.byref(nu), st)
+        b, bu = C.create_string_buffer(need + 1), C.create_string_buffer(nu.value + 1)
+        load().bsx_format_pe(*args, b, need + 1, bu, nu.value + 1, C.byref(nu), st)
+        return b.raw[:need], bu.raw[:nu.value], tuple(st)
+
+    def close(self):
+        if getattr(self, "h", None) and _l._lib is not None:
+            _l._lib.bsx_mapper_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

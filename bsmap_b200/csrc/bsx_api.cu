@@ -1,0 +1,518 @@
+// bsx_api.cu -- the C ABI (include/bsmap_b200.h): handles, batch plumbing, stream pipeline.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "bsx_common.cuh"
+#include "bsx_internal.h"
+#include "bsx_map.cuh"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void bsx_set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+extern "C" const char *bsx_last_error(void) { return g_err; }
+
+extern "C" int bsx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int require_device(int device) {
+    int n = bsx_device_count();
+    if (n <= 0) { bsx_set_error("no CUDA device available: bsmap_b200 has no CPU fallback"); return BSX_ERR_CUDA; }
+    if (device < 0 || device >= n) { bsx_set_error("device %d out of range (have %d)", device, n); return BSX_ERR_ARG; }
+    return BSX_OK;
+}
+
+// Param::Param (param.cpp:6-83)
+extern "C" void bsx_params_default(bsx_params *p) {
+    memset(p, 0, sizeof *p);
+    p->seed_size = 16; p->index_interval = 4; p->max_snp_num = 2; p->max_num_hits = BSX_MAXHITS;
+    p->report_repeat_hits = 1; p->min_insert = 28; p->max_insert = 500; p->max_ns = 5;
+    p->max_readlen = BSX_MAX_READLEN;
+}
+
+static int check_params(const bsx_params *p) {
+    if (p->seed_size < 8 || p->seed_size > 16) { bsx_set_error("seed size must be 8..16 (got %d)", p->seed_size); return BSX_ERR_ARG; }
+    if (p->index_interval < 1 || p->index_interval > 16) { bsx_set_error("index interval must be 1..16"); return BSX_ERR_ARG; }
+    if (p->max_snp_num < 0 || p->max_snp_num > BSX_MAXSNPS) { bsx_set_error("max mismatches must be 0..%d", BSX_MAXSNPS); return BSX_ERR_ARG; }
+    if (p->max_num_hits < 1 || p->max_num_hits > BSX_MAXHITS) { bsx_set_error("max multi-hits must be 1..%d", BSX_MAXHITS); return BSX_ERR_ARG; }
+    if (p->n_adapter < 0 || p->n_adapter > BSX_MAX_ADAPTERS) { bsx_set_error("at most %d adapters", BSX_MAX_ADAPTERS); return BSX_ERR_ARG; }
+    if (p->rrbs && (p->seed_size != 12 || p->index_interval != 1)) { bsx_set_error("RRBS mode forces seed 12 / interval 1 (param.cpp:95-106)"); return BSX_ERR_ARG; }
+    return BSX_OK;
+}
+
+// ------------------------------------------------------------------------------------ index
+extern "C" int bsx_index_create(const bsx_params *p, int n_seq, const char *const *names,
+                                const char *const *seqs, const uint32_t *lens, int device, bsx_index **out) {
+    if (!p || !out || n_seq <= 0 || !names || !seqs || !lens) { bsx_set_error("bsx_index_create: bad argument"); return BSX_ERR_ARG; }
+    int rc = check_params(p); if (rc) return rc;
+    rc = require_device(device); if (rc) return rc;
+    bsx_index *ix = new bsx_index();
+    ix->device = device; ix->par = *p; ix->n_seq = (uint32_t)n_seq;
+    for (int k = 0; k < n_seq; k++) { ix->names.emplace_back(names[k]); ix->size.push_back(lens[k]); }
+    rc = bsx_index_build_device(ix, seqs);
+    if (rc) { bsx_index_free_device(ix); delete ix; return rc; }
+    *out = ix;
+    return BSX_OK;
+}
+
+// Host-only index for the text layer: names, sizes, anchors, the packed Watson strand (XR:Z / BSP
+// refseq column) and RRBS digestion sites.  It cannot map (device = -1); it exists so that records
+// produced on a GPU node can be formatted elsewhere, and so the formatter is testable without a GPU.
+extern "C" int bsx_index_create_text_only(const bsx_params *p, int n_seq, const char *const *names,
+                                          const char *const *seqs, const uint32_t *lens, bsx_index **out) {
+    if (!p || !out || n_seq <= 0 || !names || !seqs || !lens) { bsx_set_error("bsx_index_create_text_only: bad argument"); return BSX_ERR_ARG; }
+    bsx_index *ix = new bsx_index();
+    ix->device = -1; ix->par = *p; ix->n_seq = (uint32_t)n_seq;
+    uint64_t tot = 0;
+    ix->anchor.resize(n_seq + 1);
+    for (int k = 0; k < n_seq; k++) {
+        ix->names.emplace_back(names[k]); ix->size.push_back(lens[k]);
+        ix->nwords.push_back((lens[k] + BSX_SEGLEN - 1) / BSX_SEGLEN + 2);
+        ix->rc_offset.push_back(ix->nwords[k] * BSX_SEGLEN);
+        ix->anchor[k] = (uint32_t)((tot + BSX_REF_MARGIN) * BSX_SEGLEN);
+        tot += ix->nwords[k];
+    }
+    ix->anchor[n_seq] = (uint32_t)((tot + BSX_REF_MARGIN) * BSX_SEGLEN);
+    ix->n_words = tot + 2 * BSX_REF_MARGIN;
+    ix->h_refcat.assign(ix->n_words, 0);
+    ix->sites.assign(n_seq, {});
+    const int sl = (int)strnlen(p->digest_site, sizeof p->digest_site);
+    for (int k = 0; k < n_seq; k++) {
+        uint32_t *w = ix->h_refcat.data() + (ix->anchor[k] >> 4);
+        const uint8_t *sq = (const uint8_t *)seqs[k];
+        for (uint32_t i = 0; i < lens[k]; i++) w[i >> 4] |= bsx_code_fwd(sq[i]) << (30 - 2 * (i & 15));
+        if (p->rrbs)
+            for (uint32_t q = 0; q + sl <= lens[k]; q++) {
+                bool ok = true;
+                for (int t = 0; t < sl; t++) { uint8_t c = sq[q + t]; if (c >= 'a' && c <= 'z') c -= 32; if (c != (uint8_t)p->digest_site[t]) { ok = false; break; } }
+                if (ok) ix->sites[k].push_back(q + p->digest_pos);
+            }
+    }
+    *out = ix;
+    return BSX_OK;
+}
+
+// RefSeq::LoadNextSeq (dbseq.cpp:18-54): name = first token after '>', sequence = whitespace-free
+// concatenation of the following tokens up to the next '>'
+extern "C" int bsx_index_create_from_fasta(const bsx_params *p, const char *path, int device, bsx_index **out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { bsx_set_error("fatal error: failed to open ref file %s", path); return BSX_ERR_IO; }
+    std::vector<std::string> names, seqs;
+    std::vector<char> buf(1 << 22);
+    bool in_header = false, header_name_done = false, at_line_start = true;
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        for (size_t i = 0; i < got; i++) {
+            const char c = buf[i];
+            if (in_header) {
+                if (c == '\n') { in_header = false; at_line_start = true; }
+                else if (!header_name_done) { if (c == ' ' || c == '\t' || c == '\r') { if (!names.back().empty()) header_name_done = true; } else names.back().push_back(c); }
+                continue;
+            }
+            if (c == '>' && (at_line_start || true)) { names.emplace_back(); seqs.emplace_back(); in_header = true; header_name_done = false; continue; }
+            if (c == '\n') { at_line_start = true; continue; }
+            at_line_start = false;
+            if (c == ' ' || c == '\t' || c == '\r') continue;
+            if (!seqs.empty()) seqs.back().push_back(c);
+        }
+    }
+    fclose(f);
+    if (seqs.empty()) { bsx_set_error("no sequences in %s", path); return BSX_ERR_IO; }
+    std::vector<const char *> np, sp; std::vector<uint32_t> ln;
+    for (size_t k = 0; k < seqs.size(); k++) { np.push_back(names[k].c_str()); sp.push_back(seqs[k].data()); ln.push_back((uint32_t)seqs[k].size()); }
+    return bsx_index_create(p, (int)seqs.size(), np.data(), sp.data(), ln.data(), device, out);
+}
+
+extern "C" int bsx_index_destroy(bsx_index *ix) {
+    if (!ix) return BSX_OK;
+    bsx_index_free_device(ix);
+    delete ix;
+    return BSX_OK;
+}
+
+extern "C" int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info) {
+    if (!ix || !info) return BSX_ERR_ARG;
+    info->n_words = ix->n_words; info->n_keys = ix->n_keys; info->n_entries = ix->n_entries;
+    info->n_seq = ix->n_seq; info->device = ix->device; info->build_seconds = ix->build_seconds;
+    return BSX_OK;
+}
+extern "C" const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k) { return (ix && k < ix->n_seq) ? ix->names[k].c_str() : ""; }
+extern "C" uint32_t bsx_index_seq_size(const bsx_index *ix, uint32_t k) { return (ix && k < ix->n_seq) ? ix->size[k] : 0; }
+
+extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size_t bytes) {
+    if (!ix || !dst) return BSX_ERR_ARG;
+    if (ix->device < 0) { bsx_set_error("text-only index has no device arrays"); return BSX_ERR_ARG; }
+    BSX_CUDA_CHECK(cudaSetDevice(ix->device));
+    const void *src = nullptr; size_t have = 0;
+    switch (what) {
+        case 0: src = ix->d_refcat; have = ix->n_words * 4; break;
+        case 1: src = ix->d_crefcat; have = ix->n_words * 4; break;
+        case 2: src = ix->d_seqinfo; have = ((size_t)ix->n_seq + 1) * 4; break;
+        case 3: src = ix->d_tab; have = (2 * ix->n_keys + 1) * 4; break;
+        case 4: src = ix->d_pos; have = ix->n_entries * 4; break;
+        case 5: src = ix->d_tag; have = ix->d_tag ? ix->n_entries * 4 : 0; break;
+        default: bsx_set_error("bsx_index_download: unknown array %d", what); return BSX_ERR_ARG;
+    }
+    if (bytes > have) { bsx_set_error("bsx_index_download: asked %zu bytes, array has %zu", bytes, have); return BSX_ERR_ARG; }
+    if (bytes) BSX_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return BSX_OK;
+}
+
+extern "C" int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap) {
+    if (!ix || cap < 5) return 0;
+    ptrs[0] = ix->d_refcat; bytes[0] = ix->n_words * 4;
+    ptrs[1] = ix->d_crefcat; bytes[1] = ix->n_words * 4;
+    ptrs[2] = ix->d_tab; bytes[2] = (2 * ix->n_keys + 1) * 4;
+    ptrs[3] = ix->d_pos; bytes[3] = ix->n_entries * 4;
+    ptrs[4] = ix->d_tag; bytes[4] = ix->d_tag ? ix->n_entries * 4 : 0;
+    return 5;
+}
+
+// metadata blob: everything a replica needs besides the big device arrays
+static void put(std::vector<uint8_t> &b, const void *p, size_t n) { const uint8_t *q = (const uint8_t *)p; b.insert(b.end(), q, q + n); }
+static std::vector<uint8_t> meta_blob(const bsx_index *ix) {
+    std::vector<uint8_t> b;
+    const uint64_t magic = 0x3130585342ULL;  // "BSX01"
+    put(b, &magic, 8); put(b, &ix->par, sizeof ix->par);
+    put(b, &ix->n_seq, 4); put(b, &ix->n_words, 8); put(b, &ix->n_keys, 8); put(b, &ix->n_entries, 8);
+    for (uint32_t k = 0; k < ix->n_seq; k++) {
+        uint32_t l = (uint32_t)ix->names[k].size(); put(b, &l, 4); put(b, ix->names[k].data(), l);
+        put(b, &ix->size[k], 4); put(b, &ix->rc_offset[k], 4); put(b, &ix->nwords[k], 4); put(b, &ix->anchor[k], 4);
+        uint32_t ns = ix->par.rrbs ? (uint32_t)ix->sites[k].size() : 0; put(b, &ns, 4);
+        if (ns) put(b, ix->sites[k].data(), (size_t)ns * 4);
+    }
+    put(b, &ix->anchor[ix->n_seq], 4);
+    return b;
+}
+extern "C" size_t bsx_index_meta_size(const bsx_index *ix) { return ix ? meta_blob(ix).size() : 0; }
+extern "C" int bsx_index_meta_export(const bsx_index *ix, void *dst, size_t bytes) {
+    if (!ix || !dst) return BSX_ERR_ARG;
+    std::vector<uint8_t> b = meta_blob(ix);
+    if (bytes < b.size()) { bsx_set_error("meta buffer too small"); return BSX_ERR_ARG; }
+    memcpy(dst, b.data(), b.size());
+    return BSX_OK;
+}
+extern "C" int bsx_index_create_shell(const void *meta, size_t bytes, int device, bsx_index **out) {
+    if (!meta || !out) return BSX_ERR_ARG;
+    int rc = require_device(device); if (rc) return rc;
+    const uint8_t *q = (const uint8_t *)meta, *end = q + bytes;
+    auto get = [&](void *p, size_t n) { if (q + n > end) return false; memcpy(p, q, n); q += n; return true; };
+    uint64_t magic = 0;
+    bsx_index *ix = new bsx_index();
+    bool ok = get(&magic, 8) && magic == 0x3130585342ULL && get(&ix->par, sizeof ix->par) && get(&ix->n_seq, 4) &&
+              get(&ix->n_words, 8) && get(&ix->n_keys, 8) && get(&ix->n_entries, 8);
+    if (ok) {
+        ix->size.resize(ix->n_seq); ix->rc_offset.resize(ix->n_seq); ix->nwords.resize(ix->n_seq); ix->anchor.resize(ix->n_seq + 1);
+        ix->names.resize(ix->n_seq); ix->sites.resize(ix->n_seq);
+        for (uint32_t k = 0; ok && k < ix->n_seq; k++) {
+            uint32_t l = 0, ns = 0;
+            ok = get(&l, 4); if (!ok) break;
+            ix->names[k].resize(l); ok = get(&ix->names[k][0], l) && get(&ix->size[k], 4) && get(&ix->rc_offset[k], 4) &&
+                                         get(&ix->nwords[k], 4) && get(&ix->anchor[k], 4) && get(&ns, 4);
+            if (ok && ns) { ix->sites[k].resize(ns); ok = get(ix->sites[k].data(), (size_t)ns * 4); }
+        }
+        ok = ok && get(&ix->anchor[ix->n_seq], 4);
+    }
+    if (!ok) { delete ix; bsx_set_error("bsx_index_create_shell: corrupt metadata"); return BSX_ERR_ARG; }
+    ix->device = device;
+    rc = bsx_index_alloc_device(ix);
+    if (rc) { bsx_index_free_device(ix); delete ix; return rc; }
+    *out = ix;
+    return BSX_OK;
+}
+
+// one-time replica over NVLink (peer copy); the only inter-GPU traffic of the whole design
+extern "C" int bsx_index_replicate(const bsx_index *src, int device, bsx_index **out) {
+    if (!src || !out) return BSX_ERR_ARG;
+    std::vector<uint8_t> b = meta_blob(src);
+    int rc = bsx_index_create_shell(b.data(), b.size(), device, out);
+    if (rc) return rc;
+    void *sp[5], *dp[5]; size_t sb[5], db[5];
+    bsx_index_device_buffers(src, sp, sb, 5); bsx_index_device_buffers(*out, dp, db, 5);
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, device, src->device);
+    if (can) { cudaSetDevice(device); cudaDeviceEnablePeerAccess(src->device, 0); cudaGetLastError(); }
+    for (int i = 0; i < 5; i++)
+        if (sb[i] && sp[i]) BSX_CUDA_CHECK(cudaMemcpyPeer(dp[i], device, sp[i], src->device, sb[i]));
+    BSX_CUDA_CHECK(cudaDeviceSynchronize());
+    return BSX_OK;
+}
+
+// ------------------------------------------------------------------------------------ mapper
+struct bsx_slot {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_seq_a = nullptr, *d_seq_b = nullptr;
+    uint16_t *d_len_a = nullptr, *d_len_b = nullptr;
+    bsx_rec *d_out_a = nullptr, *d_out_b = nullptr;
+    bsx_pair_rec *d_out_pair = nullptr;
+    uint16_t *d_cnt_a = nullptr, *d_cnt_b = nullptr;
+    uint32_t *d_counter = nullptr;
+    uint2 *d_hits = nullptr; uint32_t *d_dd = nullptr; uint4 *d_pairs = nullptr;
+};
+
+struct bsx_mapper {
+    const bsx_index *ix = nullptr;
+    bsx_params par{};
+    uint32_t max_batch = 0, stride = 0;
+    int n_ctas_se = 0, n_ctas_pe = 0, plan_cap = 0;
+    uint32_t hit_stride = 0, dd_stride = 0, pair_stride = 0;
+    bool pe_ready = false;
+    bsx_slot slot[2];
+    unsigned long long *d_stats = nullptr;
+    uint32_t *d_debug = nullptr;
+    uint64_t launches = 0;
+    MapArgs base{};
+};
+
+int bsx_map_occupancy(int pe, size_t smem);   // bsx_map.cu
+
+static void slot_free(bsx_slot &s) {
+    cudaFree(s.d_seq_a); cudaFree(s.d_seq_b); cudaFree(s.d_len_a); cudaFree(s.d_len_b); cudaFree(s.d_out_a); cudaFree(s.d_out_b);
+    cudaFree(s.d_out_pair); cudaFree(s.d_cnt_a); cudaFree(s.d_cnt_b); cudaFree(s.d_counter); cudaFree(s.d_hits); cudaFree(s.d_dd); cudaFree(s.d_pairs);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = bsx_slot();
+}
+
+extern "C" int bsx_mapper_destroy(bsx_mapper *m) {
+    if (!m) return BSX_OK;
+    cudaSetDevice(m->ix->device);
+    cudaDeviceSynchronize();
+    slot_free(m->slot[0]); slot_free(m->slot[1]);
+    cudaFree(m->d_stats); cudaFree(m->d_debug);
+    delete m;
+    return BSX_OK;
+}
+
+static int alloc_pe(bsx_mapper *m) {
+    // second mate + pair buckets: allocated on first paired-end use
+    if (m->pe_ready) return BSX_OK;
+    const size_t warps = (size_t)m->n_ctas_pe * BSX_WARPS_PER_CTA;
+    const uint32_t W1 = (uint32_t)m->par.max_num_hits + 1, lv = (uint32_t)m->par.max_snp_num + 1;
+    for (int i = 0; i < 2; i++) {
+        bsx_slot &s = m->slot[i];
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_seq_b, (size_t)m->max_batch * m->stride));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_len_b, (size_t)m->max_batch * 2));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_out_b, (size_t)m->max_batch * sizeof(bsx_rec)));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_cnt_b, (size_t)m->max_batch * 32));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_out_pair, (size_t)m->max_batch * sizeof(bsx_pair_rec)));
+        // all-level hit storage for both mates replaces the SE scratch
+        cudaFree(s.d_hits); cudaFree(s.d_dd); s.d_hits = nullptr; s.d_dd = nullptr;
+        const size_t se_warps = (size_t)m->n_ctas_se * BSX_WARPS_PER_CTA;
+        const size_t hit_elems = std::max(warps * 2 * (size_t)(lv * 2 * W1), se_warps * (size_t)(2 * W1));
+        const size_t dd_elems = std::max(warps * 2, se_warps) * (size_t)m->dd_stride;
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_hits, hit_elems * sizeof(uint2)));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_dd, dd_elems * 4));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_pairs, warps * (size_t)m->pair_stride * sizeof(uint4)));
+    }
+    m->pe_ready = true;
+    return BSX_OK;
+}
+
+extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint32_t max_batch, uint32_t stride, bsx_mapper **out) {
+    if (!ix || !p || !out || max_batch == 0) { bsx_set_error("bsx_mapper_create: bad argument"); return BSX_ERR_ARG; }
+    if (ix->device < 0) { bsx_set_error("text-only index cannot map: build it with bsx_index_create on a CUDA device"); return BSX_ERR_CUDA; }
+    int rc = check_params(p); if (rc) return rc;
+    if (stride % 16 != 0 || stride < 16) { bsx_set_error("read stride must be a positive multiple of 16 (got %u)", stride); return BSX_ERR_ARG; }
+    if (p->seed_size != ix->par.seed_size || p->index_interval != ix->par.index_interval || p->rrbs != ix->par.rrbs) {
+        bsx_set_error("mapper parameters (-s/-I/-D) differ from the index they were built with"); return BSX_ERR_ARG; }
+    if (p->rrbs && (p->pairend || p->chains) != (ix->par.pairend || ix->par.chains)) {
+        bsx_set_error("RRBS index was built for a different strand set (-b/-n)"); return BSX_ERR_ARG; }
+    rc = require_device(ix->device); if (rc) return rc;
+    BSX_CUDA_CHECK(cudaSetDevice(ix->device));
+    bsx_mapper *m = new bsx_mapper();
+    m->ix = ix; m->par = *p; m->max_batch = max_batch; m->stride = stride;
+    int readlen = std::min(p->max_readlen, BSX_MAX_READLEN);
+    int maxseg = std::min((readlen - p->index_interval + 1) / p->seed_size, p->max_snp_num + 1);
+    if (maxseg < 1) maxseg = 1;
+    m->plan_cap = maxseg * (p->rrbs ? 1 : p->index_interval);
+    int sms = 0;
+    BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
+    int occ_se = bsx_map_occupancy(0, bsx_warp_smem_bytes(1, m->plan_cap) * BSX_WARPS_PER_CTA);
+    int occ_pe = bsx_map_occupancy(1, bsx_warp_smem_bytes(2, m->plan_cap) * BSX_WARPS_PER_CTA);
+    if (occ_se < 1 || occ_pe < 1) { delete m; bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
+    m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
+    const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;
+    m->hit_stride = 2 * W1;                        // SE: only the best level is kept
+    m->dd_stride = lv * (uint32_t)p->max_num_hits + 32;
+    m->pair_stride = (2 * (uint32_t)p->max_snp_num + 1) * W1 * 2;   // uint4 units (32-byte PairHit)
+    const size_t se_warps = (size_t)m->n_ctas_se * BSX_WARPS_PER_CTA;
+    for (int i = 0; i < 2; i++) {
+        bsx_slot &s = m->slot[i];
+        BSX_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_seq_a, (size_t)max_batch * stride));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_len_a, (size_t)max_batch * 2));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_out_a, (size_t)max_batch * sizeof(bsx_rec)));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_cnt_a, (size_t)max_batch * 32));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_counter, 64));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_hits, se_warps * (size_t)m->hit_stride * sizeof(uint2)));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_dd, se_warps * (size_t)m->dd_stride * 4));
+    }
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_stats, 8 * sizeof(unsigned long long)));
+    BSX_CUDA_CHECK(cudaMemset(m->d_stats, 0, 8 * sizeof(unsigned long long)));
+    if (getenv("BSX_DEBUG_SEEDS")) {
+        BSX_CUDA_CHECK(cudaMalloc(&m->d_debug, (size_t)max_batch * 40 * 4));
+        BSX_CUDA_CHECK(cudaMemset(m->d_debug, 0, (size_t)max_batch * 40 * 4));
+    }
+    MapArgs &a = m->base;
+    memset(&a, 0, sizeof a);
+    a.refcat = ix->d_refcat; a.crefcat = ix->d_crefcat; a.tab = ix->d_tab; a.pos = ix->d_pos; a.tag = ix->d_tag;
+    a.seqinfo = ix->d_seqinfo; a.sites = ix->d_sites; a.site_off = ix->d_site_off; a.n_seq = ix->n_seq;
+    a.s = p->seed_size; a.I = p->index_interval; a.v = p->max_snp_num; a.W = p->max_num_hits; a.r = p->report_repeat_hits;
+    a.min_insert = p->min_insert; a.max_insert = p->max_insert; a.chains = p->chains; a.pairend = p->pairend; a.rrbs = p->rrbs;
+    a.randseed = p->randseed; a.max_ns = p->max_ns; a.max_readlen = p->max_readlen; a.n_adapter = p->n_adapter;
+    a.site_len = (int)strnlen(p->digest_site, sizeof p->digest_site); a.digest_pos = p->digest_pos;
+    a.seed_bits = (p->seed_size == 16) ? 0xffffffffu : ((1u << (2 * p->seed_size)) - 1);
+    a.plan_cap = m->plan_cap;
+    for (int i = 0; i < p->n_adapter; i++) { a.adapter_len[i] = (int)strnlen(p->adapter[i], 63); memcpy(a.adapter[i], p->adapter[i], 64); }
+    memcpy(a.digest_site, p->digest_site, sizeof a.digest_site);
+    a.stride = stride; a.stats = m->d_stats; a.debug = m->d_debug;
+    a.hit_stride = m->hit_stride; a.dd_stride = m->dd_stride; a.pair_stride = m->pair_stride;
+    *out = m;
+    return BSX_OK;
+}
+
+static cudaStream_t pick_stream(bsx_mapper *m, int slot, void *stream) { return stream ? (cudaStream_t)stream : m->slot[slot].stream; }
+
+static int upload_slot(bsx_mapper *m, int si, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb, cudaStream_t st) {
+    bsx_slot &s = m->slot[si];
+    if (n > m->max_batch) { bsx_set_error("batch of %u reads exceeds max_batch %u", n, m->max_batch); return BSX_ERR_ARG; }
+    BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_seq_a, sa, (size_t)n * m->stride, cudaMemcpyHostToDevice, st));
+    BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_len_a, la, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    if (sb) {
+        int rc = alloc_pe(m); if (rc) return rc;
+        BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_seq_b, sb, (size_t)n * m->stride, cudaMemcpyHostToDevice, st));
+        BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_len_b, lb, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    }
+    return BSX_OK;
+}
+
+static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int readset, bool pe, cudaStream_t st) {
+    bsx_slot &s = m->slot[si];
+    if (n == 0) return BSX_OK;
+    if (pe) { int rc = alloc_pe(m); if (rc) return rc; }
+    MapArgs a = m->base;
+    a.seq_a = s.d_seq_a; a.len_a = s.d_len_a; a.seq_b = s.d_seq_b; a.len_b = s.d_len_b;
+    a.n = n; a.first_index = first_index; a.readset = readset;
+    a.out_a = s.d_out_a; a.out_b = s.d_out_b; a.out_pair = s.d_out_pair; a.cnt_a = s.d_cnt_a; a.cnt_b = s.d_cnt_b;
+    a.work_counter = s.d_counter; a.hit_scratch = s.d_hits; a.dd_scratch = s.d_dd; a.pair_scratch = s.d_pairs;
+    if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
+    BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
+    m->launches++;
+    return pe ? bsx_launch_map_pe(a, m->n_ctas_pe, st) : bsx_launch_map_se(a, m->n_ctas_se, st);
+}
+
+static int download_slot(bsx_mapper *m, int si, uint32_t n, bool pe, bsx_pair_rec *op, bsx_rec *oa, bsx_rec *ob,
+                         uint16_t *ca, uint16_t *cb, cudaStream_t st) {
+    bsx_slot &s = m->slot[si];
+    if (n == 0) return BSX_OK;
+    if (oa) BSX_CUDA_CHECK(cudaMemcpyAsync(oa, s.d_out_a, (size_t)n * sizeof(bsx_rec), cudaMemcpyDeviceToHost, st));
+    if (ca) BSX_CUDA_CHECK(cudaMemcpyAsync(ca, s.d_cnt_a, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    if (pe) {
+        if (op) BSX_CUDA_CHECK(cudaMemcpyAsync(op, s.d_out_pair, (size_t)n * sizeof(bsx_pair_rec), cudaMemcpyDeviceToHost, st));
+        if (ob) BSX_CUDA_CHECK(cudaMemcpyAsync(ob, s.d_out_b, (size_t)n * sizeof(bsx_rec), cudaMemcpyDeviceToHost, st));
+        if (cb) BSX_CUDA_CHECK(cudaMemcpyAsync(cb, s.d_cnt_b, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    }
+    return BSX_OK;
+}
+
+extern "C" int bsx_batch_upload(bsx_mapper *m, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb, void *stream) {
+    if (!m || !sa || !la) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    return upload_slot(m, 0, n, sa, la, sb, lb, pick_stream(m, 0, stream));
+}
+extern "C" int bsx_batch_run_se(bsx_mapper *m, uint32_t n, uint32_t first_index, int readset, void *stream) {
+    if (!m) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    return run_slot(m, 0, n, first_index, readset, false, pick_stream(m, 0, stream));
+}
+extern "C" int bsx_batch_run_pe(bsx_mapper *m, uint32_t n, uint32_t first_index, void *stream) {
+    if (!m) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    return run_slot(m, 0, n, first_index, 0, true, pick_stream(m, 0, stream));
+}
+extern "C" int bsx_batch_download_se(bsx_mapper *m, uint32_t n, bsx_rec *out, uint16_t *counts, void *stream) {
+    if (!m) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    cudaStream_t st = pick_stream(m, 0, stream);
+    int rc = download_slot(m, 0, n, false, nullptr, out, nullptr, counts, nullptr, st); if (rc) return rc;
+    BSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return BSX_OK;
+}
+extern "C" int bsx_batch_download_pe(bsx_mapper *m, uint32_t n, bsx_pair_rec *out, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb, void *stream) {
+    if (!m) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    cudaStream_t st = pick_stream(m, 0, stream);
+    int rc = download_slot(m, 0, n, true, out, oa, ob, ca, cb, st); if (rc) return rc;
+    BSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return BSX_OK;
+}
+extern "C" int bsx_mapper_sync(bsx_mapper *m) {
+    if (!m) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaStreamSynchronize(m->slot[0].stream));
+    BSX_CUDA_CHECK(cudaStreamSynchronize(m->slot[1].stream));
+    return BSX_OK;
+}
+
+// Do_Batch with host buffers: sub-batches alternate between two slots/streams so the H2D copy of
+// batch k+1 and the D2H copy of batch k-1 overlap the kernel of batch k (host buffers should be
+// pinned for the overlap to be real).
+static int map_host(bsx_mapper *m, bool pe, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb,
+                    uint32_t first_index, int readset, bsx_pair_rec *op, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb) {
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    uint32_t done = 0; int k = 0;
+    while (done < n) {
+        const int si = k & 1;
+        cudaStream_t st = m->slot[si].stream;
+        const uint32_t nb = std::min(m->max_batch, n - done);
+        BSX_CUDA_CHECK(cudaStreamSynchronize(st));    // slot free again
+        int rc = upload_slot(m, si, nb, sa + (size_t)done * m->stride, la + done, sb ? sb + (size_t)done * m->stride : nullptr,
+                             lb ? lb + done : nullptr, st);
+        if (rc) return rc;
+        rc = run_slot(m, si, nb, first_index + done, readset, pe, st); if (rc) return rc;
+        rc = download_slot(m, si, nb, pe, op ? op + done : nullptr, oa ? oa + done : nullptr, ob ? ob + done : nullptr,
+                           ca ? ca + (size_t)done * 16 : nullptr, cb ? cb + (size_t)done * 16 : nullptr, st);
+        if (rc) return rc;
+        done += nb; k++;
+    }
+    BSX_CUDA_CHECK(cudaStreamSynchronize(m->slot[0].stream));
+    BSX_CUDA_CHECK(cudaStreamSynchronize(m->slot[1].stream));
+    return BSX_OK;
+}
+
+extern "C" int bsx_map_se(bsx_mapper *m, uint32_t n, const char *seqs, const uint16_t *lens, uint32_t first_index, int readset,
+                          bsx_rec *out, uint16_t *counts) {
+    if (m && n == 0) return BSX_OK;
+    if (!m || !seqs || !lens || !out) { bsx_set_error("bsx_map_se: bad argument"); return BSX_ERR_ARG; }
+    return map_host(m, false, n, seqs, lens, nullptr, nullptr, first_index, readset, nullptr, out, nullptr, counts, nullptr);
+}
+extern "C" int bsx_map_pe(bsx_mapper *m, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb,
+                          uint32_t first_index, bsx_pair_rec *out, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb) {
+    if (m && n == 0) return BSX_OK;
+    if (!m || !sa || !la || !sb || !lb || !out || !oa || !ob) { bsx_set_error("bsx_map_pe: bad argument"); return BSX_ERR_ARG; }
+    return map_host(m, true, n, sa, la, sb, lb, first_index, 0, out, oa, ob, ca, cb);
+}
+
+extern "C" int bsx_mapper_stats(bsx_mapper *m, bsx_stats *out, int reset) {
+    if (!m || !out) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaDeviceSynchronize());
+    BSX_CUDA_CHECK(cudaMemcpy(out, m->d_stats, sizeof(bsx_stats), cudaMemcpyDeviceToHost));
+    if (reset) BSX_CUDA_CHECK(cudaMemset(m->d_stats, 0, sizeof(bsx_stats)));
+    return BSX_OK;
+}
+extern "C" uint64_t bsx_mapper_launches(const bsx_mapper *m) { return m ? m->launches : 0; }
+
+// test hook: seed-selection state of the last SE batch (BSX_DEBUG_SEEDS=1), 40 u32 per read
+extern "C" int bsx_mapper_debug_seeds(bsx_mapper *m, uint32_t n, uint32_t *dst) {
+    if (!m || !m->d_debug) { bsx_set_error("debug buffer not enabled (set BSX_DEBUG_SEEDS=1 before bsx_mapper_create)"); return BSX_ERR_ARG; }
+    BSX_CUDA_CHECK(cudaMemcpy(dst, m->d_debug, (size_t)n * 40 * 4, cudaMemcpyDeviceToHost));
+    return BSX_OK;
+}

@@ -1,0 +1,265 @@
+// bsx_format.cpp -- host text layer: s_OutHit (align.cpp:631-765), s_OutHitPair / s_OutHitUnpair
+// (pairs.cpp:288-498), FixPairReadName (pairs.cpp:535-555), the SAM header (main.cpp:405-413).
+// Pure host code: it turns the device's fixed-size records into the bytes the reference writes.
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "bsx_internal.h"
+
+namespace {
+
+const char kNt[] = "ACGTacgt";   // useful_nt after SetAlign('T','C') (param.cpp:220-221)
+
+struct Out {
+    char *p; size_t cap, n;
+    void put(const char *s, size_t len) { if (n + len <= cap && p) memcpy(p + n, s, len); n += len; }
+    void put(const std::string &s) { put(s.data(), s.size()); }
+    void puts(const char *s) { put(s, strlen(s)); }
+    void putc(char c) { put(&c, 1); }
+    void putu(unsigned long long v) { char b[24]; int l = snprintf(b, sizeof b, "%llu", v); put(b, (size_t)l); }
+    void puti(long long v) { char b[24]; int l = snprintf(b, sizeof b, "%lld", v); put(b, (size_t)l); }
+};
+
+char comp(char c) {   // rev_char[] (param.cpp:166-177)
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return 'N';
+    }
+}
+void revcomp(std::string &s) { std::string r(s.rbegin(), s.rend()); for (char &c : r) c = comp(c); s.swap(r); }
+void reverse(std::string &s) { std::string r(s.rbegin(), s.rend()); s.swap(r); }
+
+const std::vector<uint32_t> &watson(const bsx_index *ix) {
+    bsx_index *m = const_cast<bsx_index *>(ix);
+    if (m->h_refcat.empty()) {
+        m->h_refcat.resize(ix->n_words);
+        if (bsx_index_download(ix, 0, m->h_refcat.data(), ix->n_words * 4) != BSX_OK) m->h_refcat.assign(ix->n_words, 0);
+    }
+    return m->h_refcat;
+}
+
+// reference bases around a hit: 2 upstream (lower case) + len + 2 downstream (lower case)
+std::string mapseq(const bsx_index *ix, uint32_t chr, uint32_t loc, int len) {
+    const std::vector<uint32_t> &ref = watson(ix);
+    const uint32_t *m = ref.data() + (ix->anchor[chr >> 1] >> 4);
+    std::string s;
+    for (uint32_t ii = 2; ii > 0; ii--) {
+        if (loc < ii) continue;                      // App. B Q12
+        uint32_t q = loc - ii;
+        s.push_back((char)(kNt[(m[q >> 4] >> (30 - 2 * (q & 15))) & 3] + 32));
+    }
+    for (int ii = 0; ii < len + 2; ii++) {
+        uint32_t q = loc + (uint32_t)ii;
+        s.push_back(kNt[(m[q >> 4] >> (30 - 2 * (q & 15))) & 3]);
+    }
+    s[s.size() - 1] += 32; s[s.size() - 2] += 32;
+    return s;
+}
+
+// RefSeq::CCGG_seglen (dbseq.cpp:541-567)
+void seglen(const bsx_index *ix, uint32_t chr, uint32_t pos, int readlen, uint32_t *first, int *second) {
+    const std::vector<uint32_t> &st = ix->sites[chr >> 1];
+    const int n = (int)st.size();
+    if (n == 0) { *first = 0; *second = 0; return; }
+    int left = 0, right = n - 1;
+    while (left < right - 1) {
+        int mid = (left + right) / 2;
+        if (st[mid] == pos) { left = mid; right = mid + 1; break; }
+        else if (st[mid] < pos) left = mid; else right = mid;
+    }
+    const uint32_t add = (uint32_t)(strlen(ix->par.digest_site) - 2 * ix->par.digest_pos);
+    uint32_t seg_end;
+    for (;;) {
+        int rr = right < n ? right : n - 1;          // App. B Q20: clamp
+        seg_end = st[rr] + add;
+        if (seg_end < pos + (uint32_t)readlen && right < n) right++; else break;
+    }
+    *first = st[left] + 1; *second = (int)(seg_end - st[left]);
+}
+
+struct Read { std::string name, seq, qual; int raw; };
+
+int clip(const bsx_params *p, size_t l) { int v = (int)l; if (v > p->max_readlen) v = p->max_readlen; if (v > BSX_MAX_READLEN) v = BSX_MAX_READLEN; return v; }
+int rmsn(const bsx_params *p, int len, int raw) { return raw > 0 ? (int)((size_t)(p->max_snp_num + 1) * (size_t)(len - 1) / (size_t)raw) : 0; }
+
+Read make_read(const bsx_params *p, const char *name, const char *seq, const char *qual, int len) {
+    Read r;
+    r.name = name;
+    size_t sl = strlen(seq), ql = strlen(qual);
+    r.raw = clip(p, sl);
+    r.seq.assign(seq, std::min<size_t>(sl, (size_t)len));
+    r.qual.assign(qual, std::min<size_t>(ql, (size_t)len));
+    return r;
+}
+
+// s_OutHit.  n: -1 filtered (QC), 0 no hit (NM), >0 hits.
+void out_hit(const bsx_index *ix, const bsx_params *p, Out &o, Read &rd, int readset, int chain, int n, int nsnps,
+             uint32_t chr, uint32_t loc, int insert_size, const uint16_t *counts, int max_snp, uint32_t *n_aligned) {
+    const int len = (int)rd.seq.size();
+    const bool rev = (chain ^ (int)(chr & 1)) != 0;
+    if (p->out_sam) {
+        int flag = 0x40 * readset;
+        if (n <= 0 || (n > 1 && p->report_repeat_hits == 0)) {
+            if (!p->out_unmap) return;
+            flag |= (n < 0) ? 0x204 : (n == 0 ? 0x4 : 0x104);
+            o.put(rd.name); o.putc('\t'); o.puti(flag); o.puts("\t*\t0\t0\t*\t*\t0\t0\t"); o.put(rd.seq); o.putc('\t'); o.put(rd.qual); o.putc('\n');
+            return;
+        }
+        ++*n_aligned;
+        if (n > 1) flag |= 0x100;
+        if (rev) { flag |= 0x10; revcomp(rd.seq); reverse(rd.qual); }
+        o.put(rd.name); o.putc('\t'); o.puti(flag); o.putc('\t'); o.put(ix->names[chr >> 1]); o.putc('\t'); o.putu(loc + 1u);
+        o.puts("\t255\t"); o.puti(len); o.puts("M\t*\t0\t0\t"); o.put(rd.seq); o.putc('\t'); o.put(rd.qual); o.puts("\tNM:i:"); o.puti(nsnps);
+        if (p->out_ref) { o.puts("\tXR:Z:"); o.put(mapseq(ix, chr, loc, len)); }
+        if (p->rrbs) { uint32_t f; int sl; seglen(ix, chr, loc, len, &f, &sl); o.puts("\tZP:i:"); o.puti((int)f); o.puts("\tZL:i:"); o.puti(sl); }
+        o.puts("\tZS:Z:"); o.putc("+-"[chr & 1]); o.putc("+-"[chain]); o.putc('\n');
+        return;
+    }
+    // BSP
+    if (!p->out_unmap && (n <= 0 || (n > 1 && p->report_repeat_hits == 0))) return;
+    o.put(rd.name); o.putc('\t');
+    if (rev && n) { revcomp(rd.seq); reverse(rd.qual); }
+    o.put(rd.seq); o.putc('\t'); o.put(rd.qual); o.putc('\t');
+    o.put(n < 0 ? "QC" : n == 0 ? "NM" : n == 1 ? "UM" : n >= p->max_num_hits ? "OF" : "MA", 2);
+    if ((n > 0 && p->report_repeat_hits == 1) || (n == 1 && p->report_repeat_hits == 0)) {
+        ++*n_aligned;
+        o.putc('\t'); o.put(ix->names[chr >> 1]); o.putc('\t'); o.putu(loc + 1u); o.putc('\t'); o.putc("+-"[chr & 1]); o.putc("+-"[chain]);
+        o.putc('\t'); o.puti(insert_size); o.putc('\t'); o.put(mapseq(ix, chr, loc, len)); o.putc('\t'); o.puti(nsnps); o.putc('\t');
+        for (int ii = 0; ii < max_snp; ii++) { o.puti(counts ? counts[ii] : 0); o.putc(':'); }
+        o.puti(counts ? counts[max_snp] : 0);
+    }
+    o.putc('\n');
+}
+
+// s_OutHitUnpair, SAM branch
+void out_unpair_sam(const bsx_index *ix, const bsx_params *p, Out &o, Read &rd, int readset, int chain_a, int chain_b,
+                    int ma, int na, uint32_t a_chr, uint32_t a_loc, int mb, uint32_t b_chr, uint32_t b_loc, uint32_t *n_al) {
+    int flag = 1 | (0x40 * readset);
+    const bool mate_un = (mb <= 0 || (mb > 1 && p->report_repeat_hits == 0));
+    if (ma <= 0 || (ma > 1 && p->report_repeat_hits == 0)) {
+        if (!p->out_unmap) return;
+        if (ma < 0) flag |= 0x204;
+        if (ma == 0) flag |= 0x004;
+        if (ma > 1) flag |= 0x104;
+        if (mate_un) {
+            flag |= 0x008;
+            o.put(rd.name); o.putc('\t'); o.puti(flag); o.puts("\t*\t0\t0\t*\t*\t0\t0\t");
+        } else {
+            if (chain_b ^ (int)(b_chr & 1)) flag |= 0x020;
+            o.put(rd.name); o.putc('\t'); o.puti(flag); o.puts("\t*\t0\t0\t*\t"); o.put(ix->names[b_chr >> 1]); o.putc('\t'); o.putu(b_loc + 1u); o.puts("\t0\t");
+        }
+        o.put(rd.seq); o.putc('\t'); o.put(rd.qual); o.putc('\n');
+        return;
+    }
+    ++*n_al;
+    if (ma > 1) flag |= 0x100;
+    if (chain_a ^ (int)(a_chr & 1)) { flag |= 0x010; revcomp(rd.seq); reverse(rd.qual); }
+    const int len = (int)rd.seq.size();
+    if (mate_un) flag |= 0x008; else if (chain_b ^ (int)(b_chr & 1)) flag |= 0x020;
+    o.put(rd.name); o.putc('\t'); o.puti(flag); o.putc('\t'); o.put(ix->names[a_chr >> 1]); o.putc('\t'); o.putu(a_loc + 1u);
+    o.puts("\t255\t"); o.puti(len); o.puts("M\t");
+    if (mate_un) o.puts("*\t0\t0\t");
+    else { o.put(ix->names[b_chr >> 1]); o.putc('\t'); o.putu(b_loc + 1u); o.puts("\t0\t"); }
+    o.put(rd.seq); o.putc('\t'); o.put(rd.qual); o.puts("\tNM:i:"); o.puti(na);
+    if (p->out_ref) { o.puts("\tXR:Z:"); o.put(mapseq(ix, a_chr, a_loc, len)); }
+    if (p->rrbs) { uint32_t f; int sl; seglen(ix, a_chr, a_loc, len, &f, &sl); o.puts("\tZP:i:"); o.puti((int)f); o.puts("\tZL:i:"); o.puti(sl); }
+    o.puts("\tZS:Z:"); o.putc("+-"[a_chr & 1]); o.putc("+-"[chain_a]); o.putc('\n');
+}
+
+}  // namespace
+
+extern "C" size_t bsx_format_header(const bsx_index *ix, char *out, size_t cap) {
+    Out o{out, cap, 0};
+    o.puts("@HD\tVN:1.0\n");
+    for (uint32_t k = 0; k < ix->n_seq; k++) { o.puts("@SQ\tSN:"); o.put(ix->names[k]); o.puts("\tLN:"); o.putu(ix->size[k]); o.putc('\n'); }
+    o.puts("@PG\tID:BSMAP_2.6\n");
+    return o.n;
+}
+
+extern "C" size_t bsx_format_se(const bsx_index *ix, const bsx_params *p, uint32_t n, const char *const *names,
+                                const char *const *seqs, const char *const *quals, int readset,
+                                const bsx_rec *recs, const uint16_t *counts, char *out, size_t cap, uint32_t *n_aligned) {
+    Out o{out, cap, 0};
+    uint32_t na = 0;
+    for (uint32_t t = 0; t < n; t++) {
+        const bsx_rec &rc = recs[t];
+        Read rd = make_read(p, names[t], seqs[t], quals[t], rc.len);
+        if (rc.status == 1) {   // Do_Batch (align.cpp:598-600): filtered reads are printed only when -r != 0
+            if (p->report_repeat_hits) out_hit(ix, p, o, rd, readset, 0, -1, 0, 0, 0, 0, nullptr, 0, &na);
+            continue;
+        }
+        out_hit(ix, p, o, rd, readset, rc.chain, (int)rc.nhits, rc.nm, rc.chr, rc.loc, 0, counts ? counts + (size_t)t * 16 : nullptr,
+                rmsn(p, rc.len, rd.raw), &na);
+    }
+    if (n_aligned) *n_aligned = na;
+    return o.n;
+}
+
+extern "C" size_t bsx_format_pe(const bsx_index *ix, const bsx_params *p, uint32_t n,
+                                const char *const *names_a, const char *const *seqs_a, const char *const *quals_a,
+                                const char *const *names_b, const char *const *seqs_b, const char *const *quals_b,
+                                const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb,
+                                const uint16_t *counts_a, const uint16_t *counts_b,
+                                char *out, size_t cap, char *out_unpair, size_t cap_unpair, size_t *n_unpair, uint32_t *n_stats) {
+    Out o{out, cap, 0}, ou{out_unpair, cap_unpair, 0};
+    uint32_t n_pairs = 0, n_a = 0, n_b = 0, dummy = 0;
+    for (uint32_t t = 0; t < n; t++) {
+        Read A = make_read(p, names_a[t], seqs_a[t], quals_a[t], ra[t].len);
+        Read B = make_read(p, names_b[t], seqs_b[t], quals_b[t], rb[t].len);
+        if (p->out_sam && A.name != B.name) {
+            // FixPairReadName: cut both names after the last digit of their common prefix
+            size_t i = 0, i0 = std::min(A.name.size(), B.name.size()); long d = -1;
+            for (; i < i0; i++) { if (A.name[i] != B.name[i]) break; else if (isdigit((unsigned char)A.name[i])) d = (long)i; }
+            if (i > 0) { if (d < 0) d = (long)i - 1; if (A.name.size() > (size_t)d + 1) A.name.erase((size_t)d + 1); if (B.name.size() > (size_t)d + 1) B.name.erase((size_t)d + 1); }
+        }
+        const uint16_t *ca = counts_a ? counts_a + (size_t)t * 16 : nullptr, *cb = counts_b ? counts_b + (size_t)t * 16 : nullptr;
+        const bsx_pair_rec &pp = pr[t];
+        if (pp.paired) {
+            n_pairs++;
+            uint32_t a_loc = pp.a_loc, b_loc = pp.b_loc;
+            const int ins = pp.insert, chain = pp.chain;
+            const int lena0 = (int)A.seq.size(), lenb0 = (int)B.seq.size();
+            // fragment shorter than the read: drop the adapter part (pairs.cpp:296-306)
+            if (ins < lena0) { if (chain ^ (int)(pp.a_chr & 1)) a_loc += (uint32_t)(lena0 - ins); A.seq.erase((size_t)ins); if (A.qual.size() > (size_t)ins) A.qual.erase((size_t)ins); }
+            if (ins < lenb0) { if ((!chain) ^ (int)(pp.b_chr & 1)) b_loc += (uint32_t)(lenb0 - ins); B.seq.erase((size_t)ins); if (B.qual.size() > (size_t)ins) B.qual.erase((size_t)ins); }
+            const int np = (int)pp.npairs;
+            if (p->out_sam) {
+                for (int mate = 0; mate < 2; mate++) {
+                    Read &rd = mate ? B : A;
+                    const uint32_t chr = mate ? pp.b_chr : pp.a_chr, loc = mate ? b_loc : a_loc, mloc = mate ? a_loc : b_loc;
+                    const int ch = mate ? !chain : chain, len = (int)rd.seq.size();
+                    int flag = 0x3, tlen; uint32_t seg_start;
+                    if (np > 1) flag |= 0x100;
+                    if (ch ^ (int)(chr & 1)) { flag |= 0x10; seg_start = mloc + 1; tlen = -ins; revcomp(rd.seq); reverse(rd.qual); }
+                    else { flag |= 0x20; seg_start = loc + 1; tlen = ins; }
+                    flag |= 0x40 * (mate ? 2 : 1);
+                    o.put(rd.name); o.putc('\t'); o.puti(flag); o.putc('\t'); o.put(ix->names[chr >> 1]); o.putc('\t'); o.putu(loc + 1u);
+                    o.puts("\t255\t"); o.puti(len); o.puts("M\t=\t"); o.putu(mloc + 1u); o.putc('\t'); o.puti(tlen); o.putc('\t');
+                    o.put(rd.seq); o.putc('\t'); o.put(rd.qual); o.puts("\tNM:i:"); o.puti(mate ? pp.nb : pp.na);
+                    if (p->out_ref) { o.puts("\tXR:Z:"); o.put(mapseq(ix, chr, loc, len)); }
+                    if (p->rrbs) { o.puts("\tZP:i:"); o.puti((int)seg_start); o.puts("\tZL:i:"); o.puti(ins); }
+                    o.puts("\tZS:Z:"); o.putc("+-"[chr & 1]); o.putc("+-"[ch]); o.putc('\n');
+                }
+            } else {
+                out_hit(ix, p, o, A, 1, chain, np, pp.na, pp.a_chr, a_loc, ins, ca, rmsn(p, ra[t].len, A.raw), &dummy);
+                out_hit(ix, p, o, B, 2, !chain, np, pp.nb, pp.b_chr, b_loc, ins, cb, rmsn(p, rb[t].len, B.raw), &dummy);
+            }
+            continue;
+        }
+        // StringAlignUnpair
+        const int ma = ra[t].status ? -1 : (int)ra[t].nhits, mb = rb[t].status ? -1 : (int)rb[t].nhits;
+        if (p->out_sam) {
+            out_unpair_sam(ix, p, o, A, 1, ra[t].chain, rb[t].chain, ma, ra[t].nm, ra[t].chr, ra[t].loc, mb, rb[t].chr, rb[t].loc, &n_a);
+            out_unpair_sam(ix, p, o, B, 2, rb[t].chain, ra[t].chain, mb, rb[t].nm, rb[t].chr, rb[t].loc, ma, ra[t].chr, ra[t].loc, &n_b);
+        } else {
+            out_hit(ix, p, ou, A, 1, ra[t].chain, ma, ra[t].nm, ra[t].chr, ra[t].loc, 0, ca, ra[t].status ? 0 : rmsn(p, ra[t].len, A.raw), &dummy);
+            out_hit(ix, p, ou, B, 2, rb[t].chain, mb, rb[t].nm, rb[t].chr, rb[t].loc, 0, cb, rb[t].status ? 0 : rmsn(p, rb[t].len, B.raw), &dummy);
+        }
+    }
+    if (n_unpair) *n_unpair = ou.n;
+    if (n_stats) { n_stats[0] = n_pairs; n_stats[1] = n_a; n_stats[2] = n_b; }
+    return o.n;
+}

@@ -1,0 +1,770 @@
+// bsx_map.cu -- SingleAlign / PairAlign on the device (align.cpp, align.h, pairs.cpp).
+//
+// One warp owns one read (SE) or one read pair (PE) from ASCII to result record; warps are
+// persistent and fetch work with an atomic counter, so heavy-tailed candidate lists balance.
+//
+//   K2  load / trim / filter / pack   TrimAdapter, FilterReads, ConvertBinaySeq (align.cpp:371-425,
+//                                     579-589, 90-162): ASCII staged in shared memory, 2-bit words
+//                                     and the N mask built by lanes 0..9, all seed keys by XT.
+//   K3  seed selection                ReorderSeed / AdjustSeedStartArray / CountSeeds
+//                                     (align.cpp:454-577): every DISTINCT read offset that can carry
+//                                     a seed is probed once (coalesced across lanes into 8-byte table
+//                                     loads), then lane 0 replays the reference's argmin / sort logic
+//                                     from shared memory.
+//   K4  probe + extend + commit       SnpAlign + CountMismatch (align.cpp:253-346, align.h:167-200):
+//                                     32 list entries per step, coalesced 128-B list loads; each lane
+//                                     extends one candidate.  Extension is two-phase: first ONE aligned
+//                                     16-byte gather (3 read words = 48 bases away from the seed),
+//                                     XOR + asymmetric C/T mask + popcount; only survivors load the rest
+//                                     of the window.  The partial count is a lower bound, so accept /
+//                                     reject decisions are identical to the reference.  Survivors are
+//                                     committed in lane order (ballot + serial loop) so dedupe, bucket
+//                                     counts, -w threshold lowering and the -r 0 exits fire at exactly
+//                                     the candidate the sequential reference would stop at.
+//   K5  selection                     StringAlign (align.cpp:610-627) + myrand.
+//   K6  pairing                       PairAlign::RunAlign / GetPairs (pairs.cpp:34-190).
+//
+// Integer, HBM-latency/bandwidth bound: no tensor cores.
+#include <cstdio>
+#include "bsx_map.cuh"
+
+namespace {
+
+struct RS {                // per-read state, warp-uniform registers
+    int len, raw, rmsn, seedseg, nw;
+    uint32_t thres;
+    int fc, cc;            // flag_chain / cflag_chain
+    uint32_t index;
+    int readset;
+    uint32_t dn;           // dedupe entries
+    int best;              // SE: level whose hits are stored
+    int filtered;
+};
+
+struct Ctr { unsigned long long cand, probe, over, full, commit, list; };
+
+__device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
+    return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
+}
+
+// ------------------------------------------------------------------ K2: load, trim, filter, pack
+__device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, RS &S, const uint8_t *seqs,
+                                          const uint16_t *lens, uint32_t r, int readset, int lane) {
+    int len = lens[r];
+    if (len > A.max_readlen) len = A.max_readlen;          // reads.cpp:115-117
+    if (len > BSX_MAX_READLEN) len = BSX_MAX_READLEN;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(seqs + (size_t)r * A.stride);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(R->ascii);
+    for (int t = lane; t < 40; t += 32) dst[t] = (t * 4 < (int)A.stride) ? __ldg(src + t) : 0u;
+    __syncwarp();
+    S.len = len; S.raw = len; S.readset = readset; S.index = A.first_index + r;
+}
+
+// TrimAdapter (align.cpp:371-425): adapters in -A order, positions ascending, first success wins
+__device__ __forceinline__ void trim_adapter(const MapArgs &A, ReadSm *R, RS &S, int lane) {
+    S.raw = S.len;
+    const int len = S.len, s = A.s;
+    const uint8_t *sq = R->ascii;
+    const int tail = A.rrbs ? 5 : 4;
+    for (int a = 0; a < A.n_adapter; a++) {
+        const int al = A.adapter_len[a];
+        for (int pos0 = s; pos0 < len - tail; pos0 += 32) {
+            const int pos = pos0 + lane;
+            bool ok = false;
+            if (pos < len - tail) {
+                int m0 = 0, k = 0;
+                for (; k < al && k < 15 && pos + k < len; k++) {
+                    m0 += (A.adapter[a][k] != (char)sq[pos + k]);
+                    if (m0 > 4) break;
+                }
+                if (!A.rrbs) ok = (k >= m0 * 5 && k > 3);
+                else if (k >= m0 * 5) {
+                    // digestion-site remnant just before the adapter (align.cpp:383-404)
+                    const int sl = A.site_len, dp = A.digest_pos;
+                    int m = m0, m2 = m0;
+                    for (int t = 0; t < sl - dp; t++) {
+                        char x = A.digest_site[t], y = (char)sq[pos - sl + dp + t];
+                        m += (x != y) && (x != 'C' || y != 'T');
+                        m2 += (x != y) && (x != 'G' || y != 'A');
+                    }
+                    ok = (k >= m * 5) || (A.pairend && k >= m2 * 5);
+                }
+            }
+            unsigned b = __ballot_sync(BSX_FULL, ok);
+            if (b) { S.len = pos0 + __ffs(b) - 1; return; }
+        }
+    }
+}
+
+// FilterReads (align.cpp:579-589); returns 1 when the read is rejected
+__device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, int lane) {
+    trim_adapter(A, R, S, lane);
+    if (S.len < A.s) return 1;
+    int n = 0;
+    for (int i = lane; i < S.len; i += 32) n += !bsx_is_acgt(R->ascii[i]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(BSX_FULL, n, d);
+    if (n > A.max_ns) return 1;
+    S.rmsn = (int)((unsigned)(A.v + 1) * (unsigned)(S.len - 1) / (unsigned)S.raw);
+    return 0;
+}
+
+// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + mask, then every seed key
+__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, SelSm *X, const RS &S, int chain, int lane) {
+    const int len = S.len;
+    if (lane < BSX_FIXWORDS) {
+        uint32_t w = 0, m = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int i = lane * 16 + k;
+            uint32_t code = 0, valid = 0;
+            if (i < len) {
+                uint8_t ch = chain ? R->ascii[len - 1 - i] : R->ascii[i];
+                code = chain ? bsx_code_rev(ch) : bsx_code_fwd(ch);
+                valid = bsx_is_acgt(ch);
+            }
+            w = (w << 2) | code;
+            m = (m << 2) | valid;
+        }
+        R->rw[chain][lane] = w;
+        R->m5[chain][lane] = m;
+    }
+    __syncwarp();
+    const int s = A.s;
+    for (int p = lane; p + s <= len; p += 32) {
+        int j = p >> 4, sh = (p & 15) * 2;
+        uint32_t hi = R->rw[chain][j], lo = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u;
+        uint32_t v = __funnelshift_l(lo, hi, sh) >> (32 - 2 * s);
+        X->keys[p] = bsx_xt(v & A.seed_bits, s);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ K3: probe + choose seeds
+__device__ __forceinline__ uint32_t list_size(const SelSm *X, int p, int rrbs) {
+    uint32_t n = X->en[p] - X->st[p];       // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
+    return rrbs ? n : (n ? n + 2 : 0u);
+}
+
+__device__ void select_seeds(const MapArgs &A, ReadSm *R, SelSm *X, const RS &S, int chain, int lane, Ctr &C) {
+    const int s = A.s, I = A.I, len = S.len, seg = S.seedseg;
+    const int mo = A.rrbs ? 0 : (len - I + 1) % s;                 // max_offset
+    const int cso = (A.rrbs && chain) ? (len % s) : 0;             // cseed_offset (RRBS rc chain)
+    for (int t = lane; t < 160; t += 32) X->need[t] = 0;
+    __syncwarp();
+    const int combos = seg * I * (mo + 1);
+    for (int c = lane; c < combos; c += 32) {
+        int o = c % (mo + 1), t = c / (mo + 1), i = t % I, n = t / I;
+        int p = bsx_profile_a(s, I, n, i) - i + o + cso;
+        if (p >= 0 && p + s <= len) X->need[p] = 1;
+    }
+    __syncwarp();
+    int np = 0;
+    for (int p = lane; p < BSX_MAX_KEYS; p += 32) {
+        if (X->need[p]) {
+            const uint32_t key = X->keys[p];
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
+            const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
+            X->st[p] = a.x; X->md[p] = a.y; X->en[p] = e;
+            np++;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
+    C.probe += np;
+    __syncwarp();
+    uint4 *plan = plan_of(R, chain, A.plan_cap);
+    if (lane == 0) {
+        // ReorderSeed (align.cpp:454-504): global offset = first minimum of the total list size
+        int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
+        if (!A.rrbs) {
+            uint32_t total = 0xffffffffu;
+            for (int i = 0; i < mo; i++) {
+                uint32_t tt = 0;
+                for (int n = 0; n < seg; n++)
+                    for (int k = 0; k < I; k++) tt += list_size(X, bsx_profile_a(s, I, n, k) + i - k, 0);
+                if (tt < total) { total = tt; og = i; }
+            }
+        }
+        // AdjustSeedStartArray (align.cpp:506-528)
+        for (int n = 0; n < seg; n++) X->arr[n] = og;
+        if (!A.rrbs) {
+            for (int i = 0; i < seg; i++) {
+                const int ptr = (i % 2 == 0) ? i / 2 : seg - 1 - i / 2;
+                uint32_t total = 0xffffffffu;
+                const int start = (ptr == 0) ? 0 : X->arr[ptr - 1];
+                const int end = (ptr == seg - 1) ? mo : X->arr[ptr + 1];
+                X->arr[ptr] = start;
+                for (int ii = start; ii <= end; ii++) {
+                    uint32_t tt = 0;
+                    for (int k = 0; k < I; k++) tt += list_size(X, bsx_profile_a(s, I, ptr, k) + ii - k, 0);
+                    if (tt < total) { total = tt; X->arr[ptr] = ii; }
+                }
+            }
+        }
+        // seedindex: (sum of list sizes, segment), ascending (align.cpp:474-485)
+        for (int n = 0; n < seg; n++) {
+            uint32_t sum = 0;
+            if (A.rrbs) sum = list_size(X, bsx_profile_a(s, I, n, 0) + X->arr[n] + cso, 1);
+            else for (int k = 0; k < I; k++) sum += list_size(X, bsx_profile_a(s, I, n, k) + X->arr[n] - k, 0);
+            int key0 = (int)sum, j = n;               // insertion sort on (sum, n); n ascends, so ties keep order
+            while (j > 0 && X->sidx[j - 1][0] > key0) { X->sidx[j][0] = X->sidx[j - 1][0]; X->sidx[j][1] = X->sidx[j - 1][1]; j--; }
+            X->sidx[j][0] = key0; X->sidx[j][1] = n;
+        }
+        const int per = A.rrbs ? 1 : I;
+        for (int m = 0; m < seg; m++) {
+            const int sg = X->sidx[m][1];
+            for (int k = 0; k < per; k++) {
+                const int p = A.rrbs ? (bsx_profile_a(s, I, sg, 0) + X->arr[sg] + cso)
+                                     : (bsx_profile_a(s, I, sg, k) + X->arr[sg] - k);
+                plan[m * per + k] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ K4: extension
+// which 16-byte chunk of the window to gather first: for every residue o = (word index & 3) pick
+// delta in {0,1,2} maximising the number of valid read bases outside the seed that the chunk's
+// three fully covered read words hold.  Returns delta for o = 0..3 packed 2 bits each.
+__device__ __forceinline__ uint32_t chunk_table(const ReadSm *R, int chain, int nw, int p, int s, int lane) {
+    const int o = (lane / 3) & 3, dl = lane % 3;
+    int score = 0;
+    if (lane < 12) {
+        const int jlo = 4 * dl - o;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int j = jlo + t;
+            if (j >= 0 && j < nw) {
+                int lo = max(p, 16 * j) - 16 * j, hi = min(p + s, 16 * j + 16) - 16 * j;
+                uint32_t seedm = 0;
+                if (lo < hi) {
+                    uint32_t a = 0xffffffffu >> (2 * lo);
+                    uint32_t b = (hi >= 16) ? 0u : (0xffffffffu >> (2 * hi));
+                    seedm = a & ~b;
+                }
+                score += __popc(R->m5[chain][j] & ~seedm);
+            }
+        }
+    }
+    const int oo = lane & 3;
+    const int a0 = __shfl_sync(BSX_FULL, score, 3 * oo), a1 = __shfl_sync(BSX_FULL, score, 3 * oo + 1),
+              a2 = __shfl_sync(BSX_FULL, score, 3 * oo + 2);
+    int best = 0, bs = a0;
+    if (a1 > bs) { best = 1; bs = a1; }
+    if (a2 > bs) { best = 2; }
+    uint32_t tb = (uint32_t)best << (2 * oo);
+    return __shfl_sync(BSX_FULL, tb, 0) | __shfl_sync(BSX_FULL, tb, 1) | __shfl_sync(BSX_FULL, tb, 2) | __shfl_sync(BSX_FULL, tb, 3);
+}
+
+__device__ __forceinline__ uint32_t partial_mismatch(const ReadSm *R, int chain, int nw, const uint32_t *__restrict__ refbase,
+                                                     uint32_t loc, uint32_t tbl) {
+    const uint32_t wi = loc >> 4, sh2 = (loc & 15u) * 2u, o = wi & 3u;
+    const uint32_t dl = (tbl >> (2 * o)) & 3u;
+    const int jlo = 4 * (int)dl - (int)o;
+    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(refbase) + (wi >> 2) + dl);
+    uint32_t w = 0;
+    int j = jlo;
+    if (j >= 0 && j < nw) w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(c.y, c.x, sh2)));
+    j++;
+    if (j >= 0 && j < nw) w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(c.z, c.y, sh2)));
+    j++;
+    if (j >= 0 && j < nw) w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(c.w, c.z, sh2)));
+    return w;
+}
+
+// CountMismatch (align.h:167-200) over the whole read; stops early once above the threshold
+__device__ __forceinline__ uint32_t full_mismatch(const ReadSm *R, int chain, int nw, const uint32_t *__restrict__ refbase,
+                                                  uint32_t loc, uint32_t thres) {
+    const uint32_t *rp = refbase + (loc >> 4);
+    const uint32_t sh2 = (loc & 15u) * 2u;
+    uint32_t w = 0, prev = __ldg(rp);
+    for (int j = 0; j < nw; j++) {
+        const uint32_t next = __ldg(rp + j + 1);
+        w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(next, prev, sh2)));
+        prev = next;
+        if (w > thres) break;
+    }
+    return w;
+}
+
+// RefSeq::CCGG_seglen (dbseq.cpp:541-567), clamped at the last site (App. B Q20)
+__device__ int ccgg_seglen(const MapArgs &A, uint32_t chr, uint32_t pos, int readlen) {
+    const uint32_t *st = A.sites + A.site_off[chr >> 1];
+    const int n = (int)(A.site_off[(chr >> 1) + 1] - A.site_off[chr >> 1]);
+    int left = 0, right = n - 1;
+    while (left < right - 1) {
+        int mid = (left + right) / 2;
+        uint32_t mv = st[mid];
+        if (mv == pos) { left = mid; right = mid + 1; break; }
+        else if (mv < pos) left = mid; else right = mid;
+    }
+    const uint32_t seg_start = st[left], add = (uint32_t)(A.site_len - 2 * A.digest_pos);
+    uint32_t seg_end;
+    for (;;) {
+        int rr = right < n ? right : n - 1;
+        seg_end = st[rr] + add;
+        if (seg_end < pos + (uint32_t)readlen && right < n) right++; else break;
+    }
+    return (int)(seg_end - seg_start);
+}
+
+// One accepted candidate, executed warp-uniformly: int2hit, bounds, dedupe, bucket append, exits
+// (align.cpp:270-278 and its three twins).  Returns 1 when SnpAlign must return.
+__device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all, int chain,
+                          uint32_t chr, uint32_t loc, uint32_t w, int mode, int frag_filter, int lane, Ctr &C) {
+    const uint32_t *anchor = A.seqinfo, *size = A.seqinfo + A.n_seq + 1, *rcoff = A.seqinfo + 2 * A.n_seq + 1;
+    const uint32_t k = chr >> 1;
+    if (chr & 1u) loc = rcoff[k] - (uint32_t)S.len - loc;
+    if (loc + (uint32_t)S.len > size[k]) return 0;                      // overflow the end of refseq
+    const uint32_t key = anchor[k] + loc;                               // == (chr>>1, loc), see DESIGN.md
+    bool found = false;
+    for (uint32_t t = lane; t < S.dn; t += 32) found |= (dd[t] == key);
+    if (__any_sync(BSX_FULL, found)) return 0;                          // hit already exists
+    if (S.dn < A.dd_stride) {                                           // capacity guard (RRBS fragment-filtered hits are uncounted)
+        if (lane == 0) dd[S.dn] = key;
+        S.dn++;
+    }
+    if (frag_filter) {
+        const int sl = ccgg_seglen(A, chr, loc, S.len);
+        if (sl > A.max_insert || sl < A.min_insert) { __syncwarp(); return 0; }
+    }
+    const uint32_t cnt = chain ? R->nc[w] : R->nh[w];
+    if (!store_all && (int)w < S.best) S.best = (int)w;
+    if (lane == 0) {
+        if (store_all) hits[((size_t)w * 2 + chain) * (A.W + 1) + cnt] = make_uint2(chr, loc);
+        else if ((int)w == S.best) hits[(size_t)chain * (A.W + 1) + cnt] = make_uint2(chr, loc);
+        if (chain) R->nc[w] = (uint16_t)(cnt + 1); else R->nh[w] = (uint16_t)(cnt + 1);
+    }
+    __syncwarp();
+    C.commit++;
+    const int tot = (int)R->nh[w] + (int)R->nc[w];
+    if ((int)w == mode && !A.pairend && A.r == 0 && tot > 1) return 1;
+    if (tot >= A.W) { if (w == 0) return 1; S.thres = w - 1; }
+    return 0;
+}
+
+// SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early
+__device__ int snp_align(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr &C) {
+    const uint32_t *anchor = A.seqinfo;
+    const int per = A.rrbs ? 1 : A.I;
+    for (int chain = 0; chain < 2; chain++) {
+        if (chain == 0 ? !S.fc : !S.cc) continue;
+        const uint4 *plan = plan_of(R, chain, A.plan_cap);
+        for (int i = 0; i < per; i++) {
+            const uint4 e = plan[mode * per + i];
+            if (e.x == e.z) continue;                                    // index2[_seed] == NULL
+            const int p = (int)(e.w & 0xffffu), sg = (int)(e.w >> 16);
+            const uint32_t tbl = chunk_table(R, chain, S.nw, p, A.s, lane);
+            const uint32_t h = (uint32_t)(-p);                          // -profile.a + i - seed_start_array
+            const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
+            uint32_t nxt = (e.x + lane < e.z) ? __ldg(A.pos + e.x + lane) : 0u;
+            for (uint32_t j0 = e.x; j0 < e.z; j0 += 32) {
+                const uint32_t idx = j0 + lane;
+                bool valid = idx < e.z;
+                const uint32_t entry = nxt;
+                if (idx + 32 < e.z) nxt = __ldg(A.pos + idx + 32);
+                uint32_t strand, chr = 0, loc;
+                const uint32_t *refbase;
+                if (!A.rrbs) {
+                    strand = idx >= e.y;
+                    refbase = strand ? A.crefcat : A.refcat;
+                    loc = entry + h;
+                } else {
+                    // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
+                    const uint32_t tag = valid ? __ldg(A.tag + idx) : 0u;
+                    chr = tag & 0xffffu; strand = chr & 1u;
+                    if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
+                    if (entry < (uint32_t)p) valid = false;
+                    refbase = strand ? A.crefcat : A.refcat;
+                    loc = valid ? (entry - (uint32_t)p + anchor[chr >> 1]) : anchor[0];
+                }
+                uint32_t w = 0xffffu;
+                bool pass = false;
+                if (valid) {
+                    w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
+                    pass = w <= S.thres;
+                }
+                unsigned pm1 = __ballot_sync(BSX_FULL, pass);
+                if (pass) {
+                    w = full_mismatch(R, chain, S.nw, refbase, loc, S.thres);
+                    pass = w <= S.thres;
+                }
+                unsigned pm = __ballot_sync(BSX_FULL, pass);
+                const unsigned vm = __ballot_sync(BSX_FULL, valid);
+                C.full += __popc(pm1);
+                C.list += min(32u, e.z - j0);
+                int ret = 0, last = 31;
+                while (pm) {
+                    const int src = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const uint32_t w_s = __shfl_sync(BSX_FULL, w, src);
+                    if (w_s > S.thres) continue;                         // threshold lowered by an earlier commit
+                    uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
+                    const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
+                    uint32_t chr_s;
+                    if (!A.rrbs) {
+                        // RefSeq::int2hit (dbseq.cpp:585-595)
+                        int left = 0, right = (int)A.n_seq;
+                        while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
+                        chr_s = (uint32_t)left * 2u + strand_s;
+                        loc_s -= anchor[left];
+                    } else {
+                        chr_s = __shfl_sync(BSX_FULL, chr, src);
+                        loc_s -= anchor[chr_s >> 1];
+                    }
+                    ret = commit_hit(A, R, S, hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
+                                     A.rrbs && chain == 0 && !A.pairend, lane, C);
+                    if (ret) { last = src; break; }
+                }
+                // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted)
+                const unsigned upto = (last == 31) ? 0xffffffffu : ((2u << last) - 1u);
+                C.cand += __popc(vm & upto);
+                C.over += __popc(vm & ~upto);
+                if (ret) return 1;
+            }
+        }
+    }
+    return 0;
+}
+
+// everything RunAlign does before the mode loop (align.cpp:435-444)
+__device__ void prepare_read(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, int lane, Ctr &C, uint32_t *dbg) {
+    S.seedseg = min((S.len - A.I + 1) / A.s, S.rmsn + 1);
+    if (S.seedseg < 0) S.seedseg = 0;
+    S.fc = A.chains || (S.readset < 2);
+    S.cc = A.chains || (S.readset == 2);
+    S.thres = (uint32_t)S.rmsn;
+    S.nw = (S.len + 15) >> 4;
+    S.dn = 0; S.best = 99;
+    if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
+    __syncwarp();
+    for (int chain = 0; chain < 2; chain++) {
+        if (chain == 0 ? !S.fc : !S.cc) continue;
+        pack_chain(A, R, X, S, chain, lane);
+        select_seeds(A, R, X, S, chain, lane, C);
+        if (dbg && lane == 0) {
+            dbg[chain * 20 + 0] = (uint32_t)S.seedseg;
+            for (int n = 0; n < S.seedseg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)X->arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)X->sidx[n][1]; }
+        }
+        __syncwarp();
+    }
+}
+
+// SingleAlign::RunAlign (align.cpp:435-452)
+__device__ void run_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr &C, uint32_t *dbg) {
+    prepare_read(A, R, X, S, lane, C, dbg);
+    for (int m = 0; m < S.seedseg; m++) {
+        snp_align(A, R, S, hits, dd, store_all, m, lane, C);
+        if (!A.rrbs) {
+            bool any = false;
+            for (int ii = 0; ii <= m; ii++) any |= (R->nh[ii] || R->nc[ii]);
+            if (any) return;
+        }
+    }
+}
+
+// StringAlign (align.cpp:610-627) -> record
+__device__ void write_record(const MapArgs &A, const ReadSm *R, const RS &S, const uint2 *hits, int store_all,
+                             bsx_rec *out, uint16_t *cnt, int lane) {
+    if (cnt && lane < 16) cnt[lane] = (!S.filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
+    if (lane != 0) return;
+    bsx_rec o;
+    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)S.filtered; o.len = (uint8_t)S.len;
+    if (!S.filtered) {
+        int ii, sum = 0;
+        for (ii = 0; ii <= S.rmsn; ii++) if ((sum = R->nh[ii] + R->nc[ii]) > 0) break;
+        o.nm = (uint8_t)ii;
+        if (sum > 0) {
+            const int j = (int)(bsx_myrand(S.index, A.randseed) % (uint32_t)sum);
+            const int nh = R->nh[ii];
+            const int chain = j >= nh;
+            const size_t lvl = store_all ? (size_t)ii * 2 : 0;
+            const uint2 h = hits[(lvl + chain) * (A.W + 1) + (chain ? j - nh : j)];
+            o.chr = h.x; o.loc = h.y; o.nhits = (uint32_t)sum; o.chain = (uint8_t)chain;
+        }
+    }
+    *out = o;
+}
+
+__device__ __forceinline__ void flush_counters(const MapArgs &A, const Ctr &C, unsigned long long mapped, int lane) {
+    if (lane == 0) {
+        atomicAdd(A.stats + 0, C.cand); atomicAdd(A.stats + 1, C.probe); atomicAdd(A.stats + 2, C.over);
+        atomicAdd(A.stats + 3, C.full); atomicAdd(A.stats + 4, C.commit); atomicAdd(A.stats + 5, mapped);
+        atomicAdd(A.stats + 6, C.list);
+    }
+}
+
+// ------------------------------------------------------------------ SE kernel
+__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 4)
+bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4) + sizeof(SelSm);
+    uint8_t *base = smem + per_warp * wid;
+    ReadSm *R = reinterpret_cast<ReadSm *>(base);
+    SelSm *X = reinterpret_cast<SelSm *>(base + sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4));
+    const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
+    uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
+    uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
+    Ctr C = {0, 0, 0, 0, 0, 0};
+    unsigned long long mapped = 0;
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(A.work_counter, 1u);
+        r = __shfl_sync(BSX_FULL, r, 0);
+        if (r >= A.n) break;
+        RS S;
+        S.rmsn = 0; S.seedseg = 0; S.nw = 0; S.thres = 0; S.fc = S.cc = 0; S.dn = 0; S.best = 99;
+        load_read(A, R, S, A.seq_a, A.len_a, r, A.readset, lane);
+        S.filtered = filter_read(A, R, S, lane);
+        uint32_t *dbg = A.debug ? A.debug + (size_t)r * 40 : nullptr;
+        if (!S.filtered) run_align(A, R, X, S, hits, dd, 0, lane, C, dbg);
+        else if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
+        __syncwarp();
+        write_record(A, R, S, hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
+        if (!S.filtered) { bool any = false; for (int ii = 0; ii <= S.rmsn; ii++) any |= (R->nh[ii] || R->nc[ii]); mapped += any; }
+        __syncwarp();
+    }
+    flush_counters(A, C, mapped, lane);
+}
+
+// ------------------------------------------------------------------ PE kernel (pairs.cpp)
+// pair buckets: pairhits[na+nb][..] as uint4 {a.chr, a.loc, b.chr, b.loc}; insert / chain / na / nb
+// in a parallel uint4.  One warp per pair; GetPairs runs on lane 0 (its loops are short and strictly
+// ordered), the two mates' SnpAlign calls are the warp-parallel part.
+struct PairHitDev { uint32_t a_chr, a_loc, b_chr, b_loc; int32_t insert; uint32_t meta; /* chain | na<<8 | nb<<16 */ uint32_t pad0, pad1; };
+
+__device__ void sort_hits(uint2 *h, int n, int lane) {
+    // SortHits4PE (align.cpp:363-368) with HitComp (utilities.cpp:53): ascending (chr, loc).  Bucket
+    // elements are distinct (dedupe), so any correct sort agrees with std::sort.  Warp-parallel
+    // odd-even transposition in place; buckets are almost always 0-2 entries.
+    if (n < 2) return;
+    bool dirty = true;
+    while (dirty) {
+        bool sw = false;
+        for (int phase = 0; phase < 2; phase++) {
+            for (int i = phase + 2 * lane; i + 1 < n; i += 64) {
+                const uint2 a = h[i], b = h[i + 1];
+                if (a.x > b.x || (a.x == b.x && a.y > b.y)) { h[i] = b; h[i + 1] = a; sw = true; }
+            }
+            __syncwarp();
+        }
+        dirty = __any_sync(BSX_FULL, sw);
+    }
+}
+
+// GetPairs (pairs.cpp:34-135), lane 0 only
+__device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb, const RS &Sa, const RS &Sb,
+                         const uint2 *ha_all, const uint2 *hb_all, PairHitDev *pairs, uint16_t *npairs, int na, int nb) {
+    if (na > Sa.rmsn || nb > Sb.rmsn) return 0;
+    const size_t W1 = (size_t)A.W + 1;
+    uint16_t &cnt = npairs[na + nb];
+    PairHitDev *bucket = pairs + (size_t)(na + nb) * W1;
+    for (int dir = 0; dir < 2; dir++) {
+        const uint2 *ha = ha_all + ((size_t)na * 2 + dir) * W1;           // dir 0: a.hits  x b.chits
+        const uint2 *hb = hb_all + ((size_t)nb * 2 + (1 - dir)) * W1;     // dir 1: a.chits x b.hits
+        const int cnt_a = dir ? Ra->nc[na] : Ra->nh[na];
+        const int cnt_b = dir ? Rb->nh[nb] : Rb->nc[nb];
+        uint32_t chra = 0xffffffffu; int bstart = 0, bend = 0;
+        for (int i = 0; i < cnt_a; i++) {
+            const uint2 x = ha[i];
+            if (chra != x.x) {
+                chra = x.x;
+                for (bstart = bend; bstart < cnt_b; bstart++) if (hb[bstart].x >= chra) break;
+                for (bend = bstart; bend < cnt_b; bend++) if (hb[bend].x > chra) break;
+            }
+            for (int j = bstart; j < bend; j++) {
+                const uint2 y = hb[j];
+                const bool a_first = dir ? ((chra & 1u) != 0) : ((chra & 1u) == 0);
+                uint32_t seg_start, seg_end;
+                if (!a_first) { seg_start = y.y; seg_end = x.y + (uint32_t)Sa.len; }
+                else { seg_start = x.y; seg_end = y.y + (uint32_t)Sb.len; }
+                const int ins = (int)(seg_end - seg_start);
+                if (ins >= A.min_insert && ins <= A.max_insert) {
+                    PairHitDev ph;
+                    ph.a_chr = x.x; ph.a_loc = x.y; ph.b_chr = y.x; ph.b_loc = y.y; ph.insert = ins;
+                    ph.meta = (uint32_t)dir | ((uint32_t)na << 8) | ((uint32_t)nb << 16); ph.pad0 = ph.pad1 = 0;
+                    bucket[cnt++] = ph;
+                    if ((int)cnt >= A.W) return 1;
+                }
+            }
+        }
+    }
+    return cnt > 0;
+}
+
+// the selection half of StringAlignUnpair (pairs.cpp:244-286) for one mate -> record
+__device__ void write_unpaired(const MapArgs &A, const ReadSm *R, const RS &S, const uint2 *hits, bsx_rec *out, uint16_t *cnt, int lane) {
+    if (cnt && lane < 16) cnt[lane] = (!S.filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
+    if (lane != 0) return;
+    bsx_rec o;
+    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)S.filtered; o.len = (uint8_t)S.len;
+    if (!S.filtered) {
+        int na, ma = 0, ra = 0;
+        for (na = 0; na <= S.rmsn; na++) if ((ma = R->nh[na] + R->nc[na]) > 0) break;
+        uint2 h = make_uint2(0, 0);
+        if (ma) {
+            if (ma > 1) ra = (int)(bsx_myrand(S.index, A.randseed) % (uint32_t)ma);
+            const int nh = R->nh[na];
+            h = (ra < nh) ? hits[((size_t)na * 2) * (A.W + 1) + ra] : hits[((size_t)na * 2 + 1) * (A.W + 1) + (ra - nh)];
+        }
+        na %= (S.rmsn + 1);
+        o.chr = h.x; o.loc = h.y; o.nhits = (uint32_t)ma; o.nm = (uint8_t)na;
+        o.chain = (uint8_t)(ra >= (int)R->nh[na]);
+    }
+    *out = o;
+}
+
+// Fix_Unpaired_Short_Fragment (align.cpp:768-791), lane 0
+__device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, const RS &S, uint2 *hits) {
+    if (S.len >= A.min_insert) return;
+    const size_t W1 = (size_t)A.W + 1;
+    for (int ii = 0; ii <= S.rmsn; ii++) {
+        for (int pass = 0; pass < 2; pass++) {
+            uint2 *h = hits + ((size_t)ii * 2 + pass) * W1;
+            int cnt = pass ? R->nc[ii] : R->nh[ii];
+            for (int j = 0; j < cnt; j++) {
+                const int sl = ccgg_seglen(A, h[j].x, h[j].y, S.len);
+                if (sl < A.min_insert || sl > A.max_insert) { cnt--; for (int k = j; k < cnt; k++) h[k] = h[k + 1]; j--; }
+            }
+            if (pass) R->nc[ii] = (uint16_t)cnt; else R->nh[ii] = (uint16_t)cnt;
+        }
+        if (R->nh[ii] + R->nc[ii] > 0) break;
+    }
+}
+
+__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 2)
+bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t read_sm = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4);
+    const size_t per_warp = 2 * read_sm + sizeof(SelSm);
+    uint8_t *base = smem + per_warp * wid;
+    ReadSm *Ra = reinterpret_cast<ReadSm *>(base);
+    ReadSm *Rb = reinterpret_cast<ReadSm *>(base + read_sm);
+    SelSm *X = reinterpret_cast<SelSm *>(base + 2 * read_sm);
+    const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
+    uint2 *hits_a = A.hit_scratch + (size_t)gw * 2 * A.hit_stride, *hits_b = hits_a + A.hit_stride;
+    uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride, *dd_b = dd_a + A.dd_stride;
+    PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
+    uint16_t *npairs = reinterpret_cast<uint16_t *>(X->need);     // 2*MAXSNPS+1 counters; `need` is dead after selection
+    Ctr C = {0, 0, 0, 0, 0, 0};
+    unsigned long long mapped = 0;
+    const size_t W1 = (size_t)A.W + 1;
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(A.work_counter, 1u);
+        r = __shfl_sync(BSX_FULL, r, 0);
+        if (r >= A.n) break;
+        RS Sa, Sb;
+        Sa.rmsn = Sb.rmsn = 0; Sa.seedseg = Sb.seedseg = 0; Sa.dn = Sb.dn = 0; Sa.best = Sb.best = 99;
+        Sa.nw = Sb.nw = 0; Sa.thres = Sb.thres = 0; Sa.fc = Sa.cc = Sb.fc = Sb.cc = 0;
+        load_read(A, Ra, Sa, A.seq_a, A.len_a, r, 1, lane);
+        load_read(A, Rb, Sb, A.seq_b, A.len_b, r, 2, lane);
+        Sa.filtered = filter_read(A, Ra, Sa, lane);
+        Sb.filtered = filter_read(A, Rb, Sb, lane);
+        if (lane < 16) { Ra->nh[lane] = Ra->nc[lane] = 0; Rb->nh[lane] = Rb->nc[lane] = 0; }
+        __syncwarp();
+        int paired = 0;
+        bsx_pair_rec po;
+        po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
+        if (!Sa.filtered && !Sb.filtered) {
+            // PairAlign::RunAlign (pairs.cpp:137-190)
+            prepare_read(A, Ra, X, Sa, lane, C, nullptr);
+            prepare_read(A, Rb, X, Sb, lane, C, nullptr);
+            if (lane < 31) npairs[lane] = 0;
+            __syncwarp();
+            const int maxi = max(Sa.rmsn, Sb.rmsn);
+            for (int i = 0; i <= maxi && !paired; i++) {
+                if (i < Sa.seedseg) snp_align(A, Ra, Sa, hits_a, dd_a, 1, i, lane, C);
+                if (i < Sb.seedseg) snp_align(A, Rb, Sb, hits_b, dd_b, 1, i, lane, C);
+                if (i <= Sa.rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
+                if (i <= Sb.rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
+                __syncwarp();
+                int n = 0;
+                if (lane == 0) {
+                    n = get_pairs(A, Ra, Rb, Sa, Sb, hits_a, hits_b, pairs, npairs, i, i);
+                    for (int j = 0; j < i; j++) { n += get_pairs(A, Ra, Rb, Sa, Sb, hits_a, hits_b, pairs, npairs, i, j);
+                                                  n += get_pairs(A, Ra, Rb, Sa, Sb, hits_a, hits_b, pairs, npairs, j, i); }
+                }
+                n = __shfl_sync(BSX_FULL, n, 0);
+                if (n > 0) paired = i + 1;
+            }
+            __syncwarp();
+            if (paired && lane == 0) {
+                // StringAlignPair (pairs.cpp:222-242)
+                for (int i = 0; i <= A.v * 2; i++) {
+                    const int np = npairs[i];
+                    if (!np) continue;
+                    int j = -1;
+                    if (np == 1) j = 0;
+                    else if (A.r == 1) j = (int)(bsx_myrand(Sa.index, A.randseed) % (uint32_t)np);
+                    if (j >= 0) {
+                        const PairHitDev ph = pairs[(size_t)i * W1 + j];
+                        po.a_chr = ph.a_chr; po.a_loc = ph.a_loc; po.b_chr = ph.b_chr; po.b_loc = ph.b_loc; po.insert = ph.insert;
+                        po.npairs = (uint32_t)np; po.chain = (uint8_t)(ph.meta & 0xff); po.na = (uint8_t)((ph.meta >> 8) & 0xff);
+                        po.nb = (uint8_t)((ph.meta >> 16) & 0xff); po.paired = 1;
+                    }
+                    break;
+                }
+            }
+        } else {
+            if (!Sa.filtered) run_align(A, Ra, X, Sa, hits_a, dd_a, 1, lane, C, nullptr);
+            if (!Sb.filtered) run_align(A, Rb, X, Sb, hits_b, dd_b, 1, lane, C, nullptr);
+        }
+        const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
+        if (!out_paired && A.rrbs) {
+            if (lane == 0) { if (!Sa.filtered) fix_unpaired_short(A, Ra, Sa, hits_a); if (!Sb.filtered) fix_unpaired_short(A, Rb, Sb, hits_b); }
+            __syncwarp();
+        }
+        if (lane == 0) A.out_pair[r] = po;
+        write_unpaired(A, Ra, Sa, hits_a, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
+        write_unpaired(A, Rb, Sb, hits_b, A.out_b + r, A.cnt_b ? A.cnt_b + (size_t)r * 16 : nullptr, lane);
+        mapped += out_paired ? 1 : 0;
+        __syncwarp();
+    }
+    flush_counters(A, C, mapped, lane);
+}
+
+}  // namespace
+
+// resident CTAs per SM for the persistent grid (0 when the kernel cannot launch with `smem`)
+int bsx_map_occupancy(int pe, size_t smem) {
+    int occ = 0;
+    cudaError_t e;
+    if (pe) {
+        e = cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_pe_kernel, BSX_WARPS_PER_CTA * 32, smem);
+    } else {
+        e = cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_se_kernel, BSX_WARPS_PER_CTA * 32, smem);
+    }
+    if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
+    return occ;
+}
+
+int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st) {
+    const size_t smem = bsx_warp_smem_bytes(1, a.plan_cap) * BSX_WARPS_PER_CTA;
+    static size_t configured = 0;
+    if (smem > configured) {
+        BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    bsx_map_se_kernel<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
+    BSX_CUDA_CHECK(cudaGetLastError());
+    return BSX_OK;
+}
+
+int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
+    const size_t smem = bsx_warp_smem_bytes(2, a.plan_cap) * BSX_WARPS_PER_CTA;
+    static size_t configured = 0;
+    if (smem > configured) {
+        BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    bsx_map_pe_kernel<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
+    BSX_CUDA_CHECK(cudaGetLastError());
+    return BSX_OK;
+}

@@ -1,0 +1,63 @@
+// bsx_map.cuh -- kernel argument block and shared-memory layout of the mapping kernels.
+#pragma once
+#include "bsx_common.cuh"
+#include "../../include/bsmap_b200.h"
+
+#define BSX_MAX_KEYS 144          // seed_array[144] (align.h:84)
+#define BSX_WARPS_PER_CTA 8
+
+struct MapArgs {
+    // RefSeq
+    const uint32_t *refcat, *crefcat, *tab, *pos, *tag, *seqinfo;   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
+    const uint32_t *sites, *site_off;
+    uint32_t n_seq;
+    // Param
+    int s, I, v, W, r, min_insert, max_insert, chains, pairend, rrbs, randseed, max_ns, max_readlen;
+    int n_adapter, site_len, digest_pos;
+    uint32_t seed_bits;
+    int plan_cap;                 // plan entries per chain = max segments * I
+    int adapter_len[BSX_MAX_ADAPTERS];
+    char adapter[BSX_MAX_ADAPTERS][64];
+    char digest_site[32];
+    // batch
+    const uint8_t *seq_a, *seq_b;
+    const uint16_t *len_a, *len_b;
+    uint32_t stride, n, first_index;
+    int readset;
+    bsx_rec *out_a, *out_b;
+    bsx_pair_rec *out_pair;
+    uint16_t *cnt_a, *cnt_b;
+    // scratch (global)
+    uint32_t *work_counter;
+    unsigned long long *stats;    // bsx_stats as 8 x u64
+    uint2 *hit_scratch;           // per warp: reads_per_warp * hit_stride Hit{chr, loc}
+    uint32_t *dd_scratch;         // per warp: reads_per_warp * dd_stride dedupe keys
+    uint4 *pair_scratch;          // per warp: PE pair buckets
+    uint32_t hit_stride, dd_stride, pair_stride;
+    uint32_t *debug;              // optional: per read 40 u32 of seed-selection state (tests)
+};
+
+// shared memory, per read handled by a warp (SE: 1, PE: 2)
+struct ReadSm {
+    uint32_t rw[2][BSX_FIXWORDS];     // 2-bit read, chain 0 = as is, 1 = reverse complement (bseq/cbseq)
+    uint32_t m5[2][BSX_FIXWORDS];     // 01 per ACGT base (reg/creg & 0x5555...)
+    uint16_t nh[16], nc[16];          // _cur_n_hit / _cur_n_chit
+    uint8_t ascii[160];
+    // followed by uint4 plan[2][plan_cap]: {list start, rc start, list end, read offset of the seed}
+};
+
+// transient per-warp scratch used while choosing seeds
+struct SelSm {
+    uint32_t keys[BSX_MAX_KEYS];      // seed_array / cseed_array
+    uint32_t st[BSX_MAX_KEYS], md[BSX_MAX_KEYS], en[BSX_MAX_KEYS];
+    uint8_t need[160];
+    int arr[16];                      // seed_start_array
+    int sidx[16][2];                  // seedindex (sum, segment)
+};
+
+static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap) {
+    return (size_t)reads_per_warp * (sizeof(ReadSm) + 2u * (size_t)plan_cap * sizeof(uint4)) + sizeof(SelSm);
+}
+
+int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st);
+int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st);

@@ -1,0 +1,185 @@
+/* bsmap_b200.h -- C ABI of the B200-native BSMAP hot path (libbsmap_b200.so).
+ *
+ * The reference (BSMAP 2.6) has no plugin/FFI interface; the seam this ABI slots into is the three
+ * calls a reference worker thread makes (main.cpp:49-114):
+ *
+ *     RefSeq::Run_ConvertBinseq + RefSeq::CreateIndex      (dbseq.cpp:215, 516)   -> bsx_index_create
+ *     SingleAlign::ImportBatchReads + SingleAlign::Do_Batch (align.cpp:42, 591)   -> bsx_map_se (+ bsx_format_se)
+ *     PairAlign::ImportBatchReads + PairAlign::Do_Batch     (pairs.cpp:27, 192)   -> bsx_map_pe (+ bsx_format_pe)
+ *
+ * Everything is `extern "C"`, plain pointers and sizes, opaque handles, int status codes
+ * (0 = ok, non-zero = error; text via bsx_last_error()).  There is no CPU fallback: every compute
+ * entry point fails with BSX_ERR_CUDA when no CUDA device is usable.
+ *
+ * Data layout
+ *   reads   : ASCII, one read per `stride` bytes (stride % 16 == 0, stride >= longest read), plus
+ *             uint16 lengths.  Reads longer than max_readlen are truncated (reads.cpp:115-117).
+ *   records : fixed-size bsx_rec / bsx_pair_rec, the decision StringAlign / StringAlignPair makes
+ *             before any text is produced; text formatting (s_OutHit & co) is host code in the same
+ *             library (bsx_format_*), so names and qualities never travel to the device.
+ */
+#ifndef BSMAP_B200_H
+#define BSMAP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSX_MAXSNPS 15        /* param.h:27  MAXSNPS              */
+#define BSX_MAXHITS 1000      /* makefile:4  -DMAXHITS=1000       */
+#define BSX_MAX_READLEN 144   /* param.h:23-25, param.cpp:80 (READ_144) */
+#define BSX_MAX_ADAPTERS 10   /* param.h:99 */
+
+enum { BSX_OK = 0, BSX_ERR_ARG = 1, BSX_ERR_CUDA = 2, BSX_ERR_NOMEM = 3, BSX_ERR_UNSUPPORTED = 4, BSX_ERR_IO = 5 };
+
+/* Mirror of the option fields of class Param (param.h:54-121) that reach the hot path. */
+typedef struct bsx_params {
+    int32_t seed_size;          /* -s */
+    int32_t index_interval;     /* -I */
+    int32_t max_snp_num;        /* -v */
+    int32_t max_num_hits;       /* -w */
+    int32_t report_repeat_hits; /* -r */
+    int32_t min_insert;         /* -m */
+    int32_t max_insert;         /* -x */
+    int32_t chains;             /* -n */
+    int32_t pairend;            /* -b given */
+    int32_t rrbs;               /* -D given */
+    int32_t randseed;           /* -S */
+    int32_t max_ns;             /* -f */
+    int32_t max_readlen;        /* -L */
+    int32_t out_sam;            /* -o *.sam */
+    int32_t out_unmap;          /* -u */
+    int32_t out_ref;            /* -R */
+    int32_t digest_pos;         /* -D: index of '-' */
+    int32_t n_adapter;          /* -A (repeatable) */
+    char    digest_site[32];    /* -D with '-' removed */
+    char    adapter[BSX_MAX_ADAPTERS][64];
+} bsx_params;
+
+/* Param::Param defaults (param.cpp:6-83) */
+void bsx_params_default(bsx_params *p);
+
+/* One record per read: what SingleAlign::StringAlign (align.cpp:610-627) decides. */
+typedef struct bsx_rec {
+    uint32_t loc;     /* Hit.loc, 0-based on the Watson strand            */
+    uint32_t chr;     /* Hit.chr = 2*sequence + strand                     */
+    uint32_t nhits;   /* hits in the lowest non-empty mismatch bucket      */
+    uint8_t  nm;      /* that bucket's mismatch count                      */
+    uint8_t  chain;   /* 0: read as is, 1: reverse-complemented read       */
+    uint8_t  status;  /* 0: alignment attempted, 1: rejected by FilterReads */
+    uint8_t  len;     /* read length after adapter trimming                */
+} bsx_rec;
+
+/* One record per pair: PairAlign::StringAlignPair (pairs.cpp:222-242). */
+typedef struct bsx_pair_rec {
+    uint32_t a_loc, a_chr, b_loc, b_chr;
+    int32_t  insert;
+    uint32_t npairs;
+    uint8_t  na, nb, chain;
+    uint8_t  paired;  /* 1: s_OutHitPair path; 0: the two bsx_rec of the mates apply (StringAlignUnpair) */
+} bsx_pair_rec;
+
+typedef struct bsx_index_info {
+    uint64_t n_words;    /* u32 words per strand array incl. 2*400 margin words (dbseq.h:15) */
+    uint64_t n_keys;     /* 3^seed_size (dbseq.cpp:314)                                      */
+    uint64_t n_entries;  /* seed-table entries, both strands                                 */
+    uint32_t n_seq;
+    int32_t  device;
+    double   build_seconds;   /* device time of pack + key + sort + table kernels */
+} bsx_index_info;
+
+/* work counters accumulated by the mapping kernels */
+typedef struct bsx_stats {
+    uint64_t candidates;      /* C: CountMismatch calls the reference semantics make      */
+    uint64_t probes;          /* P: distinct seed-table headers read                      */
+    uint64_t overfetch;       /* candidates evaluated speculatively past an exit point    */
+    uint64_t full_extensions; /* candidates that needed more than the first 16-byte chunk */
+    uint64_t commits;         /* accepted hits                                            */
+    uint64_t mapped;          /* reads / pairs with a reported location                   */
+    uint64_t list_entries;    /* position-list entries loaded                             */
+    uint64_t reserved;
+} bsx_stats;
+
+typedef struct bsx_index bsx_index;     /* device-resident 2-bit reference + seed table (RefSeq) */
+typedef struct bsx_mapper bsx_mapper;   /* per-device working set: batch buffers, scratch, streams */
+
+const char *bsx_last_error(void);
+int bsx_device_count(void);
+
+/* --- RefSeq::Run_ConvertBinseq + CreateIndex (dbseq.cpp:215-282, 516-523) ------------------- */
+int bsx_index_create(const bsx_params *p, int n_seq, const char *const *names,
+                     const char *const *seqs, const uint32_t *lens, int device, bsx_index **out);
+int bsx_index_create_from_fasta(const bsx_params *p, const char *fasta_path, int device, bsx_index **out);
+/* host-only index for the text layer (bsx_format_*): no device arrays, cannot map */
+int bsx_index_create_text_only(const bsx_params *p, int n_seq, const char *const *names,
+                               const char *const *seqs, const uint32_t *lens, bsx_index **out);
+int bsx_index_destroy(bsx_index *ix);
+int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info);
+/* name/size of sequence k (RefTitle, dbseq.h:24-30) */
+const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k);
+uint32_t bsx_index_seq_size(const bsx_index *ix, uint32_t k);
+/* copy a device array to the host (parity tests): what = 0 refcat, 1 crefcat, 2 anchors (n_seq+1),
+ * 3 tab (2*n_keys+1), 4 pos (n_entries), 5 RRBS tags (n_entries) */
+int bsx_index_download(const bsx_index *ix, int what, void *dst, size_t bytes);
+/* device pointers + byte sizes of the arrays a replica needs (one-time NVLink broadcast):
+ * order refcat, crefcat, tab, pos, tag(may be NULL/0).  Returns the count written. */
+int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap);
+/* replica on another device: allocates there and copies over NVLink with cudaMemcpyPeer */
+int bsx_index_replicate(const bsx_index *src, int device, bsx_index **out);
+/* replica shell on `device` from the source's serialised metadata; the caller then fills the device
+ * buffers (bsx_index_device_buffers) with its own broadcast (NCCL) */
+size_t bsx_index_meta_size(const bsx_index *ix);
+int bsx_index_meta_export(const bsx_index *ix, void *dst, size_t bytes);
+int bsx_index_create_shell(const void *meta, size_t bytes, int device, bsx_index **out);
+
+/* --- SingleAlign / PairAlign ----------------------------------------------------------------- */
+int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint32_t max_batch, uint32_t stride,
+                      bsx_mapper **out);
+int bsx_mapper_destroy(bsx_mapper *m);
+
+/* Do_Batch with HOST buffers (end to end: H2D, kernels, D2H; returns when `out` is valid).
+ * n may exceed max_batch: the call pipelines sub-batches over two streams.
+ * counts: optional n*16 uint16 per-level hit counts (BSP output), may be NULL. */
+int bsx_map_se(bsx_mapper *m, uint32_t n, const char *seqs, const uint16_t *lens,
+               uint32_t first_index, int readset, bsx_rec *out, uint16_t *counts);
+int bsx_map_pe(bsx_mapper *m, uint32_t n, const char *seqs_a, const uint16_t *lens_a,
+               const char *seqs_b, const uint16_t *lens_b, uint32_t first_index,
+               bsx_pair_rec *out, bsx_rec *out_a, bsx_rec *out_b, uint16_t *counts_a, uint16_t *counts_b);
+
+/* Staged form (inputs resident in HBM; used for kernel-only timing and by pipelined callers).
+ * n <= max_batch.  `stream` is a cudaStream_t (NULL = the mapper's own stream). */
+int bsx_batch_upload(bsx_mapper *m, uint32_t n, const char *seqs_a, const uint16_t *lens_a,
+                     const char *seqs_b, const uint16_t *lens_b, void *stream);
+int bsx_batch_run_se(bsx_mapper *m, uint32_t n, uint32_t first_index, int readset, void *stream);
+int bsx_batch_run_pe(bsx_mapper *m, uint32_t n, uint32_t first_index, void *stream);
+int bsx_batch_download_se(bsx_mapper *m, uint32_t n, bsx_rec *out, uint16_t *counts, void *stream);
+int bsx_batch_download_pe(bsx_mapper *m, uint32_t n, bsx_pair_rec *out, bsx_rec *out_a, bsx_rec *out_b,
+                          uint16_t *counts_a, uint16_t *counts_b, void *stream);
+int bsx_mapper_sync(bsx_mapper *m);
+/* counters since the last reset; number of kernel launches issued by this mapper */
+int bsx_mapper_stats(bsx_mapper *m, bsx_stats *out, int reset);
+uint64_t bsx_mapper_launches(const bsx_mapper *m);
+
+/* --- text: s_OutHit / s_OutHitPair / s_OutHitUnpair (align.cpp:631-765, pairs.cpp:288-498) ---- */
+/* return bytes needed (excluding NUL); if <= cap the text is in `out`. */
+size_t bsx_format_header(const bsx_index *ix, char *out, size_t cap);            /* main.cpp:405-413 */
+size_t bsx_format_se(const bsx_index *ix, const bsx_params *p, uint32_t n, const char *const *names,
+                     const char *const *seqs, const char *const *quals, int readset,
+                     const bsx_rec *recs, const uint16_t *counts, char *out, size_t cap, uint32_t *n_aligned);
+size_t bsx_format_pe(const bsx_index *ix, const bsx_params *p, uint32_t n,
+                     const char *const *names_a, const char *const *seqs_a, const char *const *quals_a,
+                     const char *const *names_b, const char *const *seqs_b, const char *const *quals_b,
+                     const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb,
+                     const uint16_t *counts_a, const uint16_t *counts_b,
+                     char *out, size_t cap, char *out_unpair, size_t cap_unpair, size_t *n_unpair,
+                     uint32_t *n_stats /* pairs, single a, single b */);
+
+/* --- the bsmap command line (main.cpp:441-476): same options, same output files -------------- */
+int bsx_cli_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
