@@ -50,6 +50,7 @@ struct bso_ref {
     /* RRBS */
     uint32_t **sites; uint32_t *n_sites;
     int rrbs; int seed_size; int site_len; int digest_pos;
+    int borrowed;          /* arrays belong to the caller (bso_ref_import) */
 };
 
 /* ---------------------------------------------------------------- tables (param.cpp:139-231) */
@@ -289,8 +290,33 @@ bso_ref *bso_ref_create(const bso_params *p, int n_seq, const char *const *names
     return r;
 }
 
+bso_ref *bso_ref_import(const bso_params *p, int n_seq, const char *const *names, const uint32_t *lens,
+                        const uint32_t *refcat, const uint32_t *crefcat, const uint32_t *tab, const uint32_t *pos,
+                        uint64_t n_entries) {
+    init_tables();
+    if (p->rrbs) return NULL;
+    bso_ref *r = calloc(1, sizeof *r);
+    r->n_seq = n_seq; r->rrbs = 0; r->seed_size = p->seed_size; r->borrowed = 1;
+    r->name = calloc(n_seq, sizeof(char *));
+    r->size = calloc(n_seq, 4); r->rc_offset = calloc(n_seq, 4); r->nwords = calloc(n_seq, 4);
+    r->anchor = calloc(n_seq + 1, 4);
+    uint64_t tot = 0;
+    for (int k = 0; k < n_seq; k++) {
+        r->name[k] = strdup(names[k]); r->size[k] = lens[k];
+        r->nwords[k] = (lens[k] + SEGLEN - 1) / SEGLEN + 2; r->rc_offset[k] = r->nwords[k] * SEGLEN;
+        r->anchor[k] = (uint32_t)((tot + REF_MARGIN) * SEGLEN); tot += r->nwords[k];
+    }
+    r->anchor[n_seq] = (uint32_t)((tot + REF_MARGIN) * SEGLEN);
+    r->n_words = tot + 2 * REF_MARGIN;
+    r->refcat = (uint32_t *)refcat; r->crefcat = (uint32_t *)crefcat; r->tab = (uint32_t *)tab; r->pos = (uint32_t *)pos;
+    r->n_keys = 1; for (int i = 0; i < p->seed_size; i++) r->n_keys *= 3;
+    r->n_entries = n_entries;
+    return r;
+}
+
 void bso_ref_destroy(bso_ref *r) {
     if (!r) return;
+    if (r->borrowed) { r->refcat = r->crefcat = r->tab = r->pos = NULL; }
     for (int k = 0; k < r->n_seq; k++) { free(r->name[k]); if (r->sites) free(r->sites[k]); }
     free(r->name); free(r->size); free(r->rc_offset); free(r->nwords); free(r->anchor);
     free(r->refcat); free(r->crefcat); free(r->blocks); free(r->tab); free(r->pos); free(r->tag);

@@ -64,6 +64,13 @@ typedef struct bso_ref bso_ref;
 
 bso_ref *bso_ref_create(const bso_params *p, int n_seq, const char *const *names,
                         const char *const *seqs, const uint32_t *lens);
+/* CPU-baseline helper: adopt an already built index (arrays are borrowed, not copied; the caller keeps
+ * them alive).  Used by bench.py so the CPU leg times MAPPING on the full-size workload without the
+ * reference's 250-300 s single-threaded table build; tests prove the imported arrays are bit-identical
+ * to what bso_ref_create builds (tests/test_gpu_parity.py::test_index_matches_oracle). */
+bso_ref *bso_ref_import(const bso_params *p, int n_seq, const char *const *names, const uint32_t *lens,
+                        const uint32_t *refcat, const uint32_t *crefcat, const uint32_t *tab, const uint32_t *pos,
+                        uint64_t n_entries);
 void bso_ref_destroy(bso_ref *r);
 
 /* introspection for index parity tests */

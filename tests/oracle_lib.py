@@ -66,6 +66,9 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.bso_ref_create.restype = C.c_void_p
         L.bso_ref_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p]
+        L.bso_ref_import.restype = C.c_void_p
+        L.bso_ref_import.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_uint64]
         L.bso_ref_destroy.argtypes = [C.c_void_p]
         for f in ("n_words", "n_keys", "n_entries"):
             getattr(L, "bso_ref_" + f).restype = C.c_uint64
@@ -122,6 +125,19 @@ class OracleRef:
         self.h = lib().bso_ref_create(C.byref(params), len(names), _strs(names), _strs(self._seqs),
                                       lens.ctypes.data)
         self.n_seq = len(names)
+
+    @classmethod
+    def imported(cls, params, names, lens, refcat, crefcat, tab, pos):
+        """adopt index arrays built elsewhere (numpy uint32 arrays, kept alive by this object)"""
+        self = cls.__new__(cls)
+        self.p, self.n_seq = params, len(names)
+        self._keep = (refcat, crefcat, tab, pos)
+        ln = np.asarray(lens, dtype=np.uint32)
+        self.h = lib().bso_ref_import(C.byref(params), len(names), _strs(names), ln.ctypes.data, refcat.ctypes.data,
+                                      crefcat.ctypes.data, tab.ctypes.data, pos.ctypes.data, len(pos))
+        if not self.h:
+            raise RuntimeError("bso_ref_import failed")
+        return self
 
     def close(self):
         if getattr(self, "h", None) and _lib is not None:
