@@ -244,7 +244,11 @@ def main():
 
     # =====================================================================================
     mp = B.Mapper(ix, p, max_batch=n, stride=STRIDE)
-    stream = torch.cuda.current_stream().cuda_stream
+    # the kernel is launched on this (non-default) torch stream, so torch.cuda.Event brackets it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     mp.upload(n, seq_host.data_ptr(), len_host.data_ptr(), stream=stream)
     torch.cuda.synchronize()
 
@@ -262,10 +266,10 @@ def main():
     clocks = ClockSampler(local); clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    e0.record(tstream)
     for _ in range(a.steps):
         mp.run_se(n, first_index=first_index, stream=stream)
-    e1.record()
+    e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
     st = mp.stats(reset=True)

@@ -47,6 +47,13 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
     return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
 }
 
+// per-CTA tables: seed profile and p -> (segment, remainder), so per-read code never divides
+__device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) K->profA[t] = (uint8_t)bsx_profile_a(A.s, A.I, t >> 4, t & 15);
+    for (int t = threadIdx.x; t < 160; t += blockDim.x) { K->segof[t] = (uint8_t)(t / A.s); K->remof[t] = (uint8_t)(t % A.s); }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ K2: load, trim, filter, pack
 __device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, RS &S, const uint8_t *seqs,
                                           const uint16_t *lens, uint32_t r, int readset, int lane) {
@@ -109,8 +116,8 @@ __device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, i
     return 0;
 }
 
-// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + mask, then every seed key
-__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, SelSm *X, const RS &S, int chain, int lane) {
+// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask
+__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, const RS &S, int chain, int lane) {
     const int len = S.len;
     if (lane < BSX_FIXWORDS) {
         uint32_t w = 0, m = 0;
@@ -130,14 +137,14 @@ __device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, SelSm *X
         R->m5[chain][lane] = m;
     }
     __syncwarp();
-    const int s = A.s;
-    for (int p = lane; p + s <= len; p += 32) {
-        int j = p >> 4, sh = (p & 15) * 2;
-        uint32_t hi = R->rw[chain][j], lo = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u;
-        uint32_t v = __funnelshift_l(lo, hi, sh) >> (32 - 2 * s);
-        X->keys[p] = bsx_xt(v & A.seed_bits, s);
-    }
-    __syncwarp();
+}
+
+// seed_array[p] (align.cpp:101-105): 3-letter key of the seed starting at read offset p
+__device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const ReadSm *R, int chain, int p) {
+    const int j = p >> 4, sh = (p & 15) * 2;
+    const uint32_t hi = R->rw[chain][j], lo = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u;
+    const uint32_t v = __funnelshift_l(lo, hi, sh) >> (32 - 2 * A.s);
+    return bsx_xt(v & A.seed_bits, A.s);
 }
 
 // ------------------------------------------------------------------ K3: probe + choose seeds
@@ -146,23 +153,26 @@ __device__ __forceinline__ uint32_t list_size(const SelSm *X, int p, int rrbs) {
     return rrbs ? n : (n ? n + 2 : 0u);
 }
 
-__device__ void select_seeds(const MapArgs &A, ReadSm *R, SelSm *X, const RS &S, int chain, int lane, Ctr &C) {
+__device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, const RS &S, int chain, int lane, Ctr &C) {
     const int s = A.s, I = A.I, len = S.len, seg = S.seedseg;
-    const int mo = A.rrbs ? 0 : (len - I + 1) % s;                 // max_offset
-    const int cso = (A.rrbs && chain) ? (len % s) : 0;             // cseed_offset (RRBS rc chain)
-    for (int t = lane; t < 160; t += 32) X->need[t] = 0;
-    __syncwarp();
-    const int combos = seg * I * (mo + 1);
-    for (int c = lane; c < combos; c += 32) {
-        int o = c % (mo + 1), t = c / (mo + 1), i = t % I, n = t / I;
-        int p = bsx_profile_a(s, I, n, i) - i + o + cso;
-        if (p >= 0 && p + s <= len) X->need[p] = 1;
-    }
-    __syncwarp();
+    const int mo = (A.rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
+    const int cso = (A.rrbs && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
+    const int lim = I - 1 + mo;
+    // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset]
+    //    (profile.a - i lies in [n*s, n*s+I-1]); its list header is read ONCE, coalesced across lanes
     int np = 0;
-    for (int p = lane; p < BSX_MAX_KEYS; p += 32) {
-        if (X->need[p]) {
-            const uint32_t key = X->keys[p];
+    for (int p = lane; p + s <= len; p += 32) {
+        bool nd;
+        if (!A.rrbs) {
+            const int n = K->segof[p], r = K->remof[p];
+            nd = false;
+#pragma unroll
+            for (int d = 0; d < 4; d++) nd |= (n - d >= 0 && n - d < seg && r + d * s <= lim);
+        } else {
+            nd = p >= cso && K->remof[p - cso] == 0 && (int)K->segof[p - cso] < seg;
+        }
+        if (nd) {
+            const uint32_t key = seed_key(A, R, chain, p);
             const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
             const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
             X->st[p] = a.x; X->md[p] = a.y; X->en[p] = e;
@@ -173,52 +183,65 @@ __device__ void select_seeds(const MapArgs &A, ReadSm *R, SelSm *X, const RS &S,
     for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
     C.probe += np;
     __syncwarp();
-    uint4 *plan = plan_of(R, chain, A.plan_cap);
-    if (lane == 0) {
-        // ReorderSeed (align.cpp:454-504): global offset = first minimum of the total list size
-        int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
-        if (!A.rrbs) {
-            uint32_t total = 0xffffffffu;
-            for (int i = 0; i < mo; i++) {
+    // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset, in parallel
+    if (!A.rrbs) {
+        for (int idx = lane; idx < seg * 16; idx += 32) {
+            const int n = idx >> 4, o = idx & 15;
+            if (o <= mo) {
                 uint32_t tt = 0;
-                for (int n = 0; n < seg; n++)
-                    for (int k = 0; k < I; k++) tt += list_size(X, bsx_profile_a(s, I, n, k) + i - k, 0);
-                if (tt < total) { total = tt; og = i; }
+                for (int k = 0; k < I; k++) tt += list_size(X, (int)K->profA[n * 16 + k] + o - k, 0);
+                X->T[idx] = tt;
             }
         }
+        __syncwarp();
+    }
+    // 3. ReorderSeed (align.cpp:454-468): global offset = FIRST minimum of GetTotalSeedLoc over [0, max_offset)
+    int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
+    if (!A.rrbs && mo > 0) {
+        unsigned long long best = ~0ull;
+        if (lane < mo) {
+            uint32_t tt = 0;
+            for (int n = 0; n < seg; n++) tt += X->T[n * 16 + lane];
+            best = ((unsigned long long)tt << 8) | (unsigned)lane;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { unsigned long long o2 = __shfl_xor_sync(BSX_FULL, best, d); best = o2 < best ? o2 : best; }
+        og = (int)(best & 0xff);
+    }
+    uint4 *plan = plan_of(R, chain, A.plan_cap);
+    if (lane == 0) {
         // AdjustSeedStartArray (align.cpp:506-528)
         for (int n = 0; n < seg; n++) X->arr[n] = og;
         if (!A.rrbs) {
             for (int i = 0; i < seg; i++) {
-                const int ptr = (i % 2 == 0) ? i / 2 : seg - 1 - i / 2;
+                const int ptr = (i & 1) == 0 ? i / 2 : seg - 1 - i / 2;
                 uint32_t total = 0xffffffffu;
                 const int start = (ptr == 0) ? 0 : X->arr[ptr - 1];
                 const int end = (ptr == seg - 1) ? mo : X->arr[ptr + 1];
-                X->arr[ptr] = start;
+                int bi = start;
                 for (int ii = start; ii <= end; ii++) {
-                    uint32_t tt = 0;
-                    for (int k = 0; k < I; k++) tt += list_size(X, bsx_profile_a(s, I, ptr, k) + ii - k, 0);
-                    if (tt < total) { total = tt; X->arr[ptr] = ii; }
+                    const uint32_t tt = X->T[ptr * 16 + ii];
+                    if (tt < total) { total = tt; bi = ii; }
                 }
+                X->arr[ptr] = bi;
             }
         }
         // seedindex: (sum of list sizes, segment), ascending (align.cpp:474-485)
         for (int n = 0; n < seg; n++) {
-            uint32_t sum = 0;
-            if (A.rrbs) sum = list_size(X, bsx_profile_a(s, I, n, 0) + X->arr[n] + cso, 1);
-            else for (int k = 0; k < I; k++) sum += list_size(X, bsx_profile_a(s, I, n, k) + X->arr[n] - k, 0);
+            const uint32_t sum = A.rrbs ? list_size(X, n * s + cso, 1) : X->T[n * 16 + X->arr[n]];
             int key0 = (int)sum, j = n;               // insertion sort on (sum, n); n ascends, so ties keep order
             while (j > 0 && X->sidx[j - 1][0] > key0) { X->sidx[j][0] = X->sidx[j - 1][0]; X->sidx[j][1] = X->sidx[j - 1][1]; j--; }
             X->sidx[j][0] = key0; X->sidx[j][1] = n;
         }
-        const int per = A.rrbs ? 1 : I;
-        for (int m = 0; m < seg; m++) {
-            const int sg = X->sidx[m][1];
-            for (int k = 0; k < per; k++) {
-                const int p = A.rrbs ? (bsx_profile_a(s, I, sg, 0) + X->arr[sg] + cso)
-                                     : (bsx_profile_a(s, I, sg, k) + X->arr[sg] - k);
-                plan[m * per + k] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
-            }
+    }
+    __syncwarp();
+    // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
+    const int per = A.rrbs ? 1 : I;
+    for (int m = 0; m < seg; m++) {
+        const int sg = X->sidx[m][1];
+        if (lane < per) {
+            const int p = A.rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + lane] + X->arr[sg] - lane);
+            plan[m * per + lane] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
         }
     }
     __syncwarp();
@@ -430,7 +453,7 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32
 }
 
 // everything RunAlign does before the mode loop (align.cpp:435-444)
-__device__ void prepare_read(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, int lane, Ctr &C, uint32_t *dbg) {
+__device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, int lane, Ctr &C, uint32_t *dbg) {
     S.seedseg = min((S.len - A.I + 1) / A.s, S.rmsn + 1);
     if (S.seedseg < 0) S.seedseg = 0;
     S.fc = A.chains || (S.readset < 2);
@@ -442,8 +465,8 @@ __device__ void prepare_read(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, int l
     __syncwarp();
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !S.fc : !S.cc) continue;
-        pack_chain(A, R, X, S, chain, lane);
-        select_seeds(A, R, X, S, chain, lane, C);
+        pack_chain(A, R, S, chain, lane);
+        select_seeds(A, K, R, X, S, chain, lane, C);
         if (dbg && lane == 0) {
             dbg[chain * 20 + 0] = (uint32_t)S.seedseg;
             for (int n = 0; n < S.seedseg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)X->arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)X->sidx[n][1]; }
@@ -453,8 +476,8 @@ __device__ void prepare_read(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, int l
 }
 
 // SingleAlign::RunAlign (align.cpp:435-452)
-__device__ void run_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr &C, uint32_t *dbg) {
-    prepare_read(A, R, X, S, lane, C, dbg);
+__device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr &C, uint32_t *dbg) {
+    prepare_read(A, K, R, X, S, lane, C, dbg);
     for (int m = 0; m < S.seedseg; m++) {
         snp_align(A, R, S, hits, dd, store_all, m, lane, C);
         if (!A.rrbs) {
@@ -502,7 +525,9 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t per_warp = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4) + sizeof(SelSm);
-    uint8_t *base = smem + per_warp * wid;
+    CtaSm *K = reinterpret_cast<CtaSm *>(smem);
+    init_cta_tables(A, K);
+    uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
     ReadSm *R = reinterpret_cast<ReadSm *>(base);
     SelSm *X = reinterpret_cast<SelSm *>(base + sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4));
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
@@ -520,7 +545,7 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
         load_read(A, R, S, A.seq_a, A.len_a, r, A.readset, lane);
         S.filtered = filter_read(A, R, S, lane);
         uint32_t *dbg = A.debug ? A.debug + (size_t)r * 40 : nullptr;
-        if (!S.filtered) run_align(A, R, X, S, hits, dd, 0, lane, C, dbg);
+        if (!S.filtered) run_align(A, K, R, X, S, hits, dd, 0, lane, C, dbg);
         else if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
         __syncwarp();
         write_record(A, R, S, hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
@@ -641,7 +666,9 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t read_sm = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4);
     const size_t per_warp = 2 * read_sm + sizeof(SelSm);
-    uint8_t *base = smem + per_warp * wid;
+    CtaSm *K = reinterpret_cast<CtaSm *>(smem);
+    init_cta_tables(A, K);
+    uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
     ReadSm *Ra = reinterpret_cast<ReadSm *>(base);
     ReadSm *Rb = reinterpret_cast<ReadSm *>(base + read_sm);
     SelSm *X = reinterpret_cast<SelSm *>(base + 2 * read_sm);
@@ -649,7 +676,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     uint2 *hits_a = A.hit_scratch + (size_t)gw * 2 * A.hit_stride, *hits_b = hits_a + A.hit_stride;
     uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride, *dd_b = dd_a + A.dd_stride;
     PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
-    uint16_t *npairs = reinterpret_cast<uint16_t *>(X->need);     // 2*MAXSNPS+1 counters; `need` is dead after selection
+    uint16_t *npairs = X->npairs;
     Ctr C = {0, 0, 0, 0, 0, 0};
     unsigned long long mapped = 0;
     const size_t W1 = (size_t)A.W + 1;
@@ -672,8 +699,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
         po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
         if (!Sa.filtered && !Sb.filtered) {
             // PairAlign::RunAlign (pairs.cpp:137-190)
-            prepare_read(A, Ra, X, Sa, lane, C, nullptr);
-            prepare_read(A, Rb, X, Sb, lane, C, nullptr);
+            prepare_read(A, K, Ra, X, Sa, lane, C, nullptr);
+            prepare_read(A, K, Rb, X, Sb, lane, C, nullptr);
             if (lane < 31) npairs[lane] = 0;
             __syncwarp();
             const int maxi = max(Sa.rmsn, Sb.rmsn);
@@ -711,8 +738,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                 }
             }
         } else {
-            if (!Sa.filtered) run_align(A, Ra, X, Sa, hits_a, dd_a, 1, lane, C, nullptr);
-            if (!Sb.filtered) run_align(A, Rb, X, Sb, hits_b, dd_b, 1, lane, C, nullptr);
+            if (!Sa.filtered) run_align(A, K, Ra, X, Sa, hits_a, dd_a, 1, lane, C, nullptr);
+            if (!Sb.filtered) run_align(A, K, Rb, X, Sb, hits_b, dd_b, 1, lane, C, nullptr);
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
         if (!out_paired && A.rrbs) {
@@ -746,7 +773,7 @@ int bsx_map_occupancy(int pe, size_t smem) {
 }
 
 int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_warp_smem_bytes(1, a.plan_cap) * BSX_WARPS_PER_CTA;
+    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap);
     static size_t configured = 0;
     if (smem > configured) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -758,7 +785,7 @@ int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st) {
 }
 
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_warp_smem_bytes(2, a.plan_cap) * BSX_WARPS_PER_CTA;
+    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap);
     static size_t configured = 0;
     if (smem > configured) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

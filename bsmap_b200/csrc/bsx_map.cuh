@@ -48,15 +48,24 @@ struct ReadSm {
 
 // transient per-warp scratch used while choosing seeds
 struct SelSm {
-    uint32_t keys[BSX_MAX_KEYS];      // seed_array / cseed_array
-    uint32_t st[BSX_MAX_KEYS], md[BSX_MAX_KEYS], en[BSX_MAX_KEYS];
-    uint8_t need[160];
+    uint32_t st[BSX_MAX_KEYS], md[BSX_MAX_KEYS], en[BSX_MAX_KEYS];   // list bounds per read offset
+    uint32_t T[16 * 16];              // T[n][o] = CountSeeds(segment n, start offset o)
     int arr[16];                      // seed_start_array
     int sidx[16][2];                  // seedindex (sum, segment)
+    uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
+};
+
+// per-CTA constant tables (no integer division in the per-read code)
+struct CtaSm {
+    uint8_t profA[16 * 16];           // Param::InitMapping profile[n][i].a (param.cpp:85-93)
+    uint8_t segof[160], remof[160];   // p / seed_size, p % seed_size
 };
 
 static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap) {
     return (size_t)reads_per_warp * (sizeof(ReadSm) + 2u * (size_t)plan_cap * sizeof(uint4)) + sizeof(SelSm);
+}
+static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap) {
+    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap) * BSX_WARPS_PER_CTA;
 }
 
 int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st);
