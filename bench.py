@@ -147,7 +147,7 @@ def main():
     import torch
     import torch.distributed as dist
     import bsmap_b200 as B
-    from bsmap_b200 import synth
+    from bsmap_b200 import shard, synth
     from bsmap_b200.lib import REC
 
     if not torch.cuda.is_available():
@@ -168,7 +168,7 @@ def main():
     # ---- synthetic genome on the GPU; host copy only where the index is built
     genome = synth.make_genome(2, lens, device=dev)
     p = B.make_params(**OPTS)
-    build_s = None
+    build_s, bcast_s = None, None
     if rank == 0 or not multi:
         host_g = [torch.empty(ln, dtype=torch.uint8, pin_memory=True) for ln in lens]
         for h, g in zip(host_g, genome):
@@ -179,14 +179,13 @@ def main():
         del host_g
     if multi:
         # one-time index broadcast over NVLink: metadata by object broadcast, arrays by NCCL broadcast
-        meta = [ix.meta() if rank == 0 else None]
-        dist.broadcast_object_list(meta, src=0)
+        meta = shard.broadcast_blob(ix.meta() if rank == 0 else None, src=0, device=dev)
         if rank != 0:
-            ix = B.Index.shell(p, meta[0], local)
-        for ptr, nbytes in ix.device_buffers():
-            if nbytes:
-                dist.broadcast(torch.as_tensor(_DevBuf(ptr, nbytes), device=dev), src=0)
+            ix = B.Index.shell(p, meta, local)
+        t_b = time.perf_counter()
+        shard.broadcast_buffers([torch.as_tensor(_DevBuf(ptr, nbytes), device=dev) for ptr, nbytes in ix.device_buffers() if nbytes], src=0)
         torch.cuda.synchronize()
+        bcast_s = time.perf_counter() - t_b
 
     # ---- simulated reads for this rank (distinct per rank), generated in HBM
     first_index = rank * n
@@ -294,16 +293,9 @@ def main():
     same = bool(np.array_equal(e2e_recs, recs_dev))
 
     # max over ranks
-    if multi:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
-        agg = torch.tensor([st["candidates"], st["probes"], st["overfetch"], st["full_extensions"], st["list_entries"]],
-                           dtype=torch.float64, device=dev)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        tot_c, tot_p, tot_over, tot_full, tot_list = [float(x) for x in agg]
-    else:
-        tot_c, tot_p, tot_over, tot_full, tot_list = (float(st[k]) for k in ("candidates", "probes", "overfetch", "full_extensions", "list_entries"))
+    ms, e2e_s = shard.reduce_max([ms, e2e_s], device=dev)
+    tot_c, tot_p, tot_over, tot_full, tot_list = shard.reduce_sum(
+        [st[k] for k in ("candidates", "probes", "overfetch", "full_extensions", "list_entries")], device=dev)
     reads_total = n * world * a.steps
     value = reads_total / (ms * 1e-3)
     e2e_val = reads_total / e2e_s
@@ -359,7 +351,8 @@ def main():
                         "ms_per_step": 1e3 * e2e_s / a.steps, "records_identical_to_resident_run": same},
                 "gpu_launches": int(launches_value + launches_e2e),
                 "roofline": roof, "cpu_baseline": cpu,
-                "mapped_fraction": mapped_frac, "index_build_seconds": build_s, "setup_seconds": setup_s}
+                "mapped_fraction": mapped_frac, "index_build_seconds": build_s, "index_broadcast_seconds": bcast_s,
+                "setup_seconds": setup_s}
         print(json.dumps(line))
     mp.close(); small.close()
     if multi:
