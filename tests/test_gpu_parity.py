@@ -212,3 +212,42 @@ def test_index_replica_over_nvlink_or_same_device():
     exp = R.oracle_run(case)
     assert _rec_diff("rec", recs, exp["recs"]) is None
     mp.close(); rep.close(); ix.close()
+
+
+CLI_CASES = ["se_cfg1", "se_mixed_A", "se_mixed_fa", "se_cfg2_bsp", "se_L60", "pe_sam", "pe_bsp_r0", "rrbs_se_A", "rrbs_pe"]
+
+
+@pytest.mark.parametrize("name", CLI_CASES)
+def test_cli_writes_the_reference_files(name, tmp_path):
+    """the `bsmap` drop-in executable: same options, FASTA/FASTQ files in, SAM/BSP files out,
+    byte-identical to what the unmodified reference wrote (-p 1)"""
+    import subprocess
+    case = CS.BY_NAME[name]
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    assert os.path.exists(exe), "bsmap CLI not built (python -m bsmap_b200.build)"
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    o = str(tmp_path / ("out." + case.out_ext))
+    o2 = str(tmp_path / "out_unpair.bsp") if (case.paired and case.out_ext != "sam") else None
+    r = subprocess.run([exe] + case.cli(a, b, fa, o, o2) + ["-p", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    exp_main, exp_un = R.golden_load(case)
+    got = open(o, "rb").read()
+    assert got == exp_main, R.first_diff(got, exp_main)
+    if o2:
+        got_un = open(o2, "rb").read()
+        assert got_un == exp_un, R.first_diff(got_un, exp_un)
+    assert "Total number of aligned reads" in r.stdout
+
+
+def test_cli_option_grammar(tmp_path):
+    """-x=val form, unknown option exit code = argv index (main.cpp:452-455)"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    case = CS.BY_NAME["se_cfg1"]
+    fa, a, _ = CS.write_inputs(case, str(tmp_path))
+    o = str(tmp_path / "o.sam")
+    r = subprocess.run([exe, f"-a={a}", f"-d={fa}", f"-o={o}", "-s=16", "-v=2", "-I=4", "-S=7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert open(o, "rb").read() == R.golden_load(case)[0]
+    r = subprocess.run([exe, "-a", a, "-Q", "3"], capture_output=True, text=True)
+    assert r.returncode == 3 and "unknown option: -Q" in r.stdout
