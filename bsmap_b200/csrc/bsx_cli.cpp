@@ -122,6 +122,7 @@ int get_options(int argc, char **argv, Opts &o) {
         const char c = argv[i][1];
         const char *val = nullptr;
         const bool flag = (c == 'R' || c == 'u' || c == 'h');
+        if (c == 0 || !strchr("abdo2smxnrIvwqfzpARuBEDMLSh", c)) return i;   // default: return i (main.cpp:283)
         if (!flag) {
             if (argv[i][2] == 0) { if (i + 1 >= argc) return i; val = argv[++i]; }
             else if (argv[i][2] == '=') val = argv[i] + 3;

@@ -36,16 +36,16 @@ BSX_HD uint32_t bsx_is_acgt(uint8_t c) {
     return (c == 'a' || c == 'c' || c == 'g' || c == 't') ? 1u : 0u;
 }
 
-// Param::XT: collapse T(11)->C(01), then read `nbases` 2-bit fields (already right-aligned in v) as
-// base-3 digits, first base most significant.
-BSX_HD uint32_t bsx_xt(uint32_t v, int nbases) {
+// Param::XT: collapse T(11)->C(01), then read the 2-bit fields of v (right-aligned, leading fields zero)
+// as base-3 digits, first base most significant.  Pairwise reduction: 2-bit digits -> 4-bit (x3) ->
+// 8-bit (x9) -> 16-bit (x81) -> 32-bit (x6561), i.e. the reference's two 8-base table lookups
+// (_T[lo16] + 6561*_T[hi16], param.h:123) without the table.
+BSX_HD uint32_t bsx_xt(uint32_t v, int /*nbases*/) {
     v &= ~((v & (v << 1)) & 0xAAAAAAAAu);   // clear the high bit where both bits are set
-    uint32_t key = 0;
-#pragma unroll
-    for (int j = 15; j >= 0; j--) {
-        if (j < nbases) key = key * 3u + ((v >> (2 * j)) & 3u);
-    }
-    return key;
+    v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u) * 3u;
+    v = (v & 0x0F0F0F0Fu) + ((v >> 4) & 0x0F0F0F0Fu) * 9u;
+    v = (v & 0x00FF00FFu) + ((v >> 8) & 0x00FF00FFu) * 81u;
+    return (v & 0xFFFFu) + (v >> 16) * 6561u;
 }
 
 // mismatches of one 16-base word: q = read word, m5 = valid-base mask (01 per valid base),

@@ -41,7 +41,7 @@ struct RS {                // per-read state, warp-uniform registers
     int filtered;
 };
 
-struct Ctr { unsigned long long cand, probe, over, full, commit, list; };
+struct Ctr { uint32_t cand, probe, over, full, commit, list; };
 
 __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
     return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
@@ -51,6 +51,8 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
 __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
     for (int t = threadIdx.x; t < 256; t += blockDim.x) K->profA[t] = (uint8_t)bsx_profile_a(A.s, A.I, t >> 4, t & 15);
     for (int t = threadIdx.x; t < 160; t += blockDim.x) { K->segof[t] = (uint8_t)(t / A.s); K->remof[t] = (uint8_t)(t % A.s); }
+    const int per = A.rrbs ? 1 : A.I;
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) { K->divI[t] = (uint8_t)(t / per); K->modI[t] = (uint8_t)(t % per); }
     __syncthreads();
 }
 
@@ -116,25 +118,55 @@ __device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, i
     return 0;
 }
 
-// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask
+// four ASCII bases in a u32 (first base in the low byte) -> their 2-bit codes and validity, byte-wise
+__device__ __forceinline__ void codes4(uint32_t w, int rev, uint32_t &code, uint32_t &valid) {
+    const uint32_t v = w | 0x20202020u;
+    valid = __vcmpeq4(v, 0x61616161u) | __vcmpeq4(v, 0x63636363u) | __vcmpeq4(v, 0x67676767u) | __vcmpeq4(v, 0x74747474u);
+    uint32_t c = (w >> 1) & 0x03030303u;          // A 0, C 1, G 3, T 2
+    c ^= (c >> 1) & 0x01010101u;                   // A 0, C 1, G 2, T 3
+    c &= valid;                                    // everything else -> 0 (alphabet[], param.cpp:210)
+    if (rev) c = (~c) & 0x03030303u;               // complement; everything else -> 3 (rev_alphabet[], param.cpp:215)
+    code = c;
+    valid &= 0x01010101u;
+}
+// byte-wise 2-bit fields (first base in the low byte) -> 8 bits, first base most significant
+__device__ __forceinline__ uint32_t squeeze4(uint32_t c) {
+    return ((c & 0x3u) << 6) | ((c >> 4) & 0x30u) | ((c >> 14) & 0xCu) | (c >> 24);
+}
+
+// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask.
+// Lane t < 20 converts bases [8t, 8t+8) with byte-SIMD ops; lane pairs are merged by shuffle.
 __device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, const RS &S, int chain, int lane) {
     const int len = S.len;
-    if (lane < BSX_FIXWORDS) {
-        uint32_t w = 0, m = 0;
+    uint32_t half = 0, mhalf = 0;
+    if (lane < 2 * BSX_FIXWORDS) {
+        uint32_t w0, w1;
+        if (!chain) {
+            const uint32_t *a32 = reinterpret_cast<const uint32_t *>(R->ascii);
+            w0 = a32[2 * lane]; w1 = a32[2 * lane + 1];
+        } else {                                    // reversed read: base i is ascii[len-1-i]
+            w0 = 0; w1 = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            int i = lane * 16 + k;
-            uint32_t code = 0, valid = 0;
-            if (i < len) {
-                uint8_t ch = chain ? R->ascii[len - 1 - i] : R->ascii[i];
-                code = chain ? bsx_code_rev(ch) : bsx_code_fwd(ch);
-                valid = bsx_is_acgt(ch);
+            for (int k = 0; k < 4; k++) {
+                const int i0 = len - 1 - (8 * lane + k), i1 = i0 - 4;
+                w0 |= (i0 >= 0 ? (uint32_t)R->ascii[i0] : 0u) << (8 * k);
+                w1 |= (i1 >= 0 ? (uint32_t)R->ascii[i1] : 0u) << (8 * k);
             }
-            w = (w << 2) | code;
-            m = (m << 2) | valid;
         }
-        R->rw[chain][lane] = w;
-        R->m5[chain][lane] = m;
+        // bases beyond the read count as invalid code 0
+        const int rem = len - 8 * lane;             // valid bases in this lane's 8
+        uint32_t keep0 = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : (0xffffffffu >> (8 * (4 - rem))));
+        uint32_t keep1 = rem >= 8 ? 0xffffffffu : (rem <= 4 ? 0u : (0xffffffffu >> (8 * (8 - rem))));
+        uint32_t c0, v0, c1, v1;
+        codes4(w0, chain, c0, v0); codes4(w1, chain, c1, v1);
+        c0 &= keep0; v0 &= keep0; c1 &= keep1; v1 &= keep1;
+        half = (squeeze4(c0) << 8) | squeeze4(c1);
+        mhalf = (squeeze4(v0) << 8) | squeeze4(v1);
+    }
+    const uint32_t ohalf = __shfl_down_sync(BSX_FULL, half, 1), omhalf = __shfl_down_sync(BSX_FULL, mhalf, 1);
+    if (lane < 2 * BSX_FIXWORDS && !(lane & 1)) {
+        R->rw[chain][lane >> 1] = (half << 16) | ohalf;
+        R->m5[chain][lane >> 1] = (mhalf << 16) | omhalf;
     }
     __syncwarp();
 }
@@ -226,23 +258,26 @@ __device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
                 X->arr[ptr] = bi;
             }
         }
-        // seedindex: (sum of list sizes, segment), ascending (align.cpp:474-485)
-        for (int n = 0; n < seg; n++) {
-            const uint32_t sum = A.rrbs ? list_size(X, n * s + cso, 1) : X->T[n * 16 + X->arr[n]];
-            int key0 = (int)sum, j = n;               // insertion sort on (sum, n); n ascends, so ties keep order
-            while (j > 0 && X->sidx[j - 1][0] > key0) { X->sidx[j][0] = X->sidx[j - 1][0]; X->sidx[j][1] = X->sidx[j - 1][1]; j--; }
-            X->sidx[j][0] = key0; X->sidx[j][1] = n;
+    }
+    __syncwarp();
+    // seedindex: (sum of list sizes, segment) ascending (align.cpp:474-485): rank sort, one segment per lane
+    if (lane < seg) {
+        const int mine = (int)(A.rrbs ? list_size(X, lane * s + cso, 1) : X->T[lane * 16 + X->arr[lane]]);
+        int rank = 0;
+        for (int m = 0; m < seg; m++) {
+            const int other = (int)(A.rrbs ? list_size(X, m * s + cso, 1) : X->T[m * 16 + X->arr[m]]);
+            rank += (other < mine) || (other == mine && m < lane);
         }
+        X->sidx[rank][0] = mine; X->sidx[rank][1] = lane;
     }
     __syncwarp();
     // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
     const int per = A.rrbs ? 1 : I;
-    for (int m = 0; m < seg; m++) {
+    for (int t = lane; t < seg * per; t += 32) {
+        const int m = K->divI[t], k = K->modI[t];
         const int sg = X->sidx[m][1];
-        if (lane < per) {
-            const int p = A.rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + lane] + X->arr[sg] - lane);
-            plan[m * per + lane] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
-        }
+        const int p = A.rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + X->arr[sg] - k);
+        plan[t] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
     }
     __syncwarp();
 }
@@ -251,7 +286,7 @@ __device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
 // which 16-byte chunk of the window to gather first: for every residue o = (word index & 3) pick
 // delta in {0,1,2} maximising the number of valid read bases outside the seed that the chunk's
 // three fully covered read words hold.  Returns delta for o = 0..3 packed 2 bits each.
-__device__ __forceinline__ uint32_t chunk_table(const ReadSm *R, int chain, int nw, int p, int s, int lane) {
+__device__ __forceinline__ uint32_t chunk_table(const ReadSm *R, int chain, int nw, int zlo, int zhi, int lane) {
     const int o = (lane / 3) & 3, dl = lane % 3;
     int score = 0;
     if (lane < 12) {
@@ -260,7 +295,7 @@ __device__ __forceinline__ uint32_t chunk_table(const ReadSm *R, int chain, int 
         for (int t = 0; t < 3; t++) {
             const int j = jlo + t;
             if (j >= 0 && j < nw) {
-                int lo = max(p, 16 * j) - 16 * j, hi = min(p + s, 16 * j + 16) - 16 * j;
+                int lo = max(zlo, 16 * j) - 16 * j, hi = min(zhi, 16 * j + 16) - 16 * j;
                 uint32_t seedm = 0;
                 if (lo < hi) {
                     uint32_t a = 0xffffffffu >> (2 * lo);
@@ -374,85 +409,116 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint3
     return 0;
 }
 
-// SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early
-__device__ int snp_align(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr &C) {
+// SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
+// The I position lists of the mode are walked as ONE concatenated stream (sub-seed 0's forward
+// entries, its rc entries, sub-seed 1's ...: exactly the reference's visiting order), 32 candidates per
+// step, so steps stay full even when the individual lists are short.
+__device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr &C) {
     const uint32_t *anchor = A.seqinfo;
     const int per = A.rrbs ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !S.fc : !S.cc) continue;
-        const uint4 *plan = plan_of(R, chain, A.plan_cap);
-        for (int i = 0; i < per; i++) {
-            const uint4 e = plan[mode * per + i];
-            if (e.x == e.z) continue;                                    // index2[_seed] == NULL
-            const int p = (int)(e.w & 0xffffu), sg = (int)(e.w >> 16);
-            const uint32_t tbl = chunk_table(R, chain, S.nw, p, A.s, lane);
-            const uint32_t h = (uint32_t)(-p);                          // -profile.a + i - seed_start_array
-            const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
-            uint32_t nxt = (e.x + lane < e.z) ? __ldg(A.pos + e.x + lane) : 0u;
-            for (uint32_t j0 = e.x; j0 < e.z; j0 += 32) {
-                const uint32_t idx = j0 + lane;
-                bool valid = idx < e.z;
-                const uint32_t entry = nxt;
-                if (idx + 32 < e.z) nxt = __ldg(A.pos + idx + 32);
-                uint32_t strand, chr = 0, loc;
-                const uint32_t *refbase;
-                if (!A.rrbs) {
-                    strand = idx >= e.y;
-                    refbase = strand ? A.crefcat : A.refcat;
-                    loc = entry + h;
-                } else {
-                    // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
-                    const uint32_t tag = valid ? __ldg(A.tag + idx) : 0u;
-                    chr = tag & 0xffffu; strand = chr & 1u;
-                    if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
-                    if (entry < (uint32_t)p) valid = false;
-                    refbase = strand ? A.crefcat : A.refcat;
-                    loc = valid ? (entry - (uint32_t)p + anchor[chr >> 1]) : anchor[0];
-                }
-                uint32_t w = 0xffffu;
-                bool pass = false;
-                if (valid) {
-                    w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
-                    pass = w <= S.thres;
-                }
-                unsigned pm1 = __ballot_sync(BSX_FULL, pass);
+        const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
+        // prefix of list lengths (lanes < per), seed zone of the mode
+        uint32_t n_i = 0; int p_i = 0;
+        if (lane < per) { const uint4 e = plan[lane]; n_i = e.z - e.x; p_i = (int)(e.w & 0xffffu); }
+        uint32_t incl = n_i;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { const uint32_t y = __shfl_up_sync(BSX_FULL, incl, d); if (lane >= d) incl += y; }
+        if (lane < per) X->cum[lane + 1] = incl;
+        if (lane == 0) X->cum[0] = 0;
+        const uint32_t tot = __shfl_sync(BSX_FULL, incl, per - 1);
+        int zlo = lane < per ? p_i : 1000, zhi = lane < per ? p_i : -1;
+#pragma unroll
+        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+        __syncwarp();
+        if (tot == 0) continue;                                          // every index2[_seed] == NULL
+        const int sg = (int)(plan[0].w >> 16);
+        const uint32_t tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
+        const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
+        // software pipeline: the list entry of step k+1 is loaded while step k is extended
+        uint32_t n_idx = 0, n_entry = 0, n_md = 0; int n_p = 0; bool n_valid;
+        {
+            const uint32_t g = lane;
+            n_valid = g < tot;
+            int i = 0;
+            for (int t = 1; t < per; t++) i += (g >= X->cum[t]);
+            const uint4 e = plan[i];
+            n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu);
+            if (n_valid) n_entry = __ldg(A.pos + n_idx);
+        }
+        for (uint32_t c0 = 0; c0 < tot; c0 += 32) {
+            const uint32_t idx = n_idx, entry = n_entry, md = n_md; const int p = n_p; bool valid = n_valid;
+            if (c0 + 32 < tot) {
+                const uint32_t g = c0 + 32 + lane;
+                n_valid = g < tot;
+                int i = 0;
+                for (int t = 1; t < per; t++) i += (g >= X->cum[t]);
+                const uint4 e = plan[i];
+                n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu);
+                if (n_valid) n_entry = __ldg(A.pos + n_idx);
+            }
+            uint32_t strand, chr = 0, loc;
+            const uint32_t *refbase;
+            if (!A.rrbs) {
+                strand = idx >= md;
+                refbase = strand ? A.crefcat : A.refcat;
+                loc = entry - (uint32_t)p;                               // h = -profile.a + i - seed_start_array
+            } else {
+                // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
+                const uint32_t tag = valid ? __ldg(A.tag + idx) : 0u;
+                chr = tag & 0xffffu; strand = chr & 1u;
+                if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
+                if (entry < (uint32_t)p) valid = false;
+                refbase = strand ? A.crefcat : A.refcat;
+                loc = valid ? (entry - (uint32_t)p + anchor[chr >> 1]) : anchor[0];
+            }
+            uint32_t w = 0xffffu;
+            bool pass = false;
+            if (valid) {
+                w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
+                pass = w <= S.thres;
+            }
+            const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
+            const unsigned vm = __ballot_sync(BSX_FULL, valid);
+            unsigned pm = 0;
+            if (pm1) {
                 if (pass) {
                     w = full_mismatch(R, chain, S.nw, refbase, loc, S.thres);
                     pass = w <= S.thres;
                 }
-                unsigned pm = __ballot_sync(BSX_FULL, pass);
-                const unsigned vm = __ballot_sync(BSX_FULL, valid);
+                pm = __ballot_sync(BSX_FULL, pass);
                 C.full += __popc(pm1);
-                C.list += min(32u, e.z - j0);
-                int ret = 0, last = 31;
-                while (pm) {
-                    const int src = __ffs(pm) - 1;
-                    pm &= pm - 1;
-                    const uint32_t w_s = __shfl_sync(BSX_FULL, w, src);
-                    if (w_s > S.thres) continue;                         // threshold lowered by an earlier commit
-                    uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
-                    const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
-                    uint32_t chr_s;
-                    if (!A.rrbs) {
-                        // RefSeq::int2hit (dbseq.cpp:585-595)
-                        int left = 0, right = (int)A.n_seq;
-                        while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
-                        chr_s = (uint32_t)left * 2u + strand_s;
-                        loc_s -= anchor[left];
-                    } else {
-                        chr_s = __shfl_sync(BSX_FULL, chr, src);
-                        loc_s -= anchor[chr_s >> 1];
-                    }
-                    ret = commit_hit(A, R, S, hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
-                                     A.rrbs && chain == 0 && !A.pairend, lane, C);
-                    if (ret) { last = src; break; }
-                }
-                // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted)
-                const unsigned upto = (last == 31) ? 0xffffffffu : ((2u << last) - 1u);
-                C.cand += __popc(vm & upto);
-                C.over += __popc(vm & ~upto);
-                if (ret) return 1;
             }
+            C.list += min(32u, tot - c0);
+            int ret = 0, last = 31;
+            while (pm) {
+                const int src = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t w_s = __shfl_sync(BSX_FULL, w, src);
+                if (w_s > S.thres) continue;                             // threshold lowered by an earlier commit
+                uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
+                const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
+                uint32_t chr_s;
+                if (!A.rrbs) {
+                    // RefSeq::int2hit (dbseq.cpp:585-595)
+                    int left = 0, right = (int)A.n_seq;
+                    while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
+                    chr_s = (uint32_t)left * 2u + strand_s;
+                    loc_s -= anchor[left];
+                } else {
+                    chr_s = __shfl_sync(BSX_FULL, chr, src);
+                    loc_s -= anchor[chr_s >> 1];
+                }
+                ret = commit_hit(A, R, S, hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
+                                 A.rrbs && chain == 0 && !A.pairend, lane, C);
+                if (ret) { last = src; break; }
+            }
+            // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted)
+            if (last == 31) C.cand += __popc(vm);
+            else { const unsigned upto = (2u << last) - 1u; C.cand += __popc(vm & upto); C.over += __popc(vm & ~upto); }
+            if (ret) return 1;
         }
     }
     return 0;
@@ -485,7 +551,7 @@ __device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
 __device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr &C, uint32_t *dbg) {
     prepare_read(A, K, R, X, S, lane, C, dbg);
     for (int m = 0; m < S.seedseg; m++) {
-        snp_align(A, R, S, hits, dd, store_all, m, lane, C);
+        snp_align(A, R, X, S, hits, dd, store_all, m, lane, C);
         if (!A.rrbs) {
             bool any = false;
             for (int ii = 0; ii <= m; ii++) any |= (R->nh[ii] || R->nc[ii]);
@@ -517,12 +583,14 @@ __device__ void write_record(const MapArgs &A, const ReadSm *R, const RS &S, con
     *out = o;
 }
 
-__device__ __forceinline__ void flush_counters(const MapArgs &A, const Ctr &C, unsigned long long mapped, int lane) {
+__device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr &C, uint32_t &mapped, int lane) {
     if (lane == 0) {
-        atomicAdd(A.stats + 0, C.cand); atomicAdd(A.stats + 1, C.probe); atomicAdd(A.stats + 2, C.over);
-        atomicAdd(A.stats + 3, C.full); atomicAdd(A.stats + 4, C.commit); atomicAdd(A.stats + 5, mapped);
-        atomicAdd(A.stats + 6, C.list);
+        atomicAdd(A.stats + 0, (unsigned long long)C.cand); atomicAdd(A.stats + 1, (unsigned long long)C.probe);
+        atomicAdd(A.stats + 2, (unsigned long long)C.over); atomicAdd(A.stats + 3, (unsigned long long)C.full);
+        atomicAdd(A.stats + 4, (unsigned long long)C.commit); atomicAdd(A.stats + 5, (unsigned long long)mapped);
+        atomicAdd(A.stats + 6, (unsigned long long)C.list);
     }
+    C.cand = C.probe = C.over = C.full = C.commit = C.list = 0; mapped = 0;
 }
 
 // ------------------------------------------------------------------ SE kernel
@@ -540,12 +608,13 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
     Ctr C = {0, 0, 0, 0, 0, 0};
-    unsigned long long mapped = 0;
+    uint32_t mapped = 0;
     for (;;) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1u);
         r = __shfl_sync(BSX_FULL, r, 0);
         if (r >= A.n) break;
+        if ((C.cand | C.list) & 0x80000000u) flush_counters(A, C, mapped, lane);
         RS S;
         S.rmsn = 0; S.seedseg = 0; S.nw = 0; S.thres = 0; S.fc = S.cc = 0; S.dn = 0; S.best = 99;
         load_read(A, R, S, A.seq_a, A.len_a, r, A.readset, lane);
@@ -684,13 +753,14 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
     uint16_t *npairs = X->npairs;
     Ctr C = {0, 0, 0, 0, 0, 0};
-    unsigned long long mapped = 0;
+    uint32_t mapped = 0;
     const size_t W1 = (size_t)A.W + 1;
     for (;;) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1u);
         r = __shfl_sync(BSX_FULL, r, 0);
         if (r >= A.n) break;
+        if ((C.cand | C.list) & 0x80000000u) flush_counters(A, C, mapped, lane);
         RS Sa, Sb;
         Sa.rmsn = Sb.rmsn = 0; Sa.seedseg = Sb.seedseg = 0; Sa.dn = Sb.dn = 0; Sa.best = Sb.best = 99;
         Sa.nw = Sb.nw = 0; Sa.thres = Sb.thres = 0; Sa.fc = Sa.cc = Sb.fc = Sb.cc = 0;
@@ -711,8 +781,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             __syncwarp();
             const int maxi = max(Sa.rmsn, Sb.rmsn);
             for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Sa.seedseg) snp_align(A, Ra, Sa, hits_a, dd_a, 1, i, lane, C);
-                if (i < Sb.seedseg) snp_align(A, Rb, Sb, hits_b, dd_b, 1, i, lane, C);
+                if (i < Sa.seedseg) snp_align(A, Ra, X, Sa, hits_a, dd_a, 1, i, lane, C);
+                if (i < Sb.seedseg) snp_align(A, Rb, X, Sb, hits_b, dd_b, 1, i, lane, C);
                 if (i <= Sa.rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
                 if (i <= Sb.rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
                 __syncwarp();

@@ -53,12 +53,14 @@ struct SelSm {
     int arr[16];                      // seed_start_array
     int sidx[16][2];                  // seedindex (sum, segment)
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
+    uint32_t cum[20];                 // SnpAlign: prefix of the I list lengths of the current mode
 };
 
 // per-CTA constant tables (no integer division in the per-read code)
 struct CtaSm {
     uint8_t profA[16 * 16];           // Param::InitMapping profile[n][i].a (param.cpp:85-93)
     uint8_t segof[160], remof[160];   // p / seed_size, p % seed_size
+    uint8_t divI[256], modI[256];     // t / per, t % per  (per = sub-seeds per segment)
 };
 
 static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap) {
