@@ -208,7 +208,7 @@ def main():
     setup_s = time.perf_counter() - t_setup
 
     cfg = {"workload": f"cfg2: {a.chroms}x{a.chrom_mb:g}Mb synthetic genome, {n} x {L_READ}nt SE reads per GPU per step, -s 16 -v 5 -I 4",
-           "l2_policy": "working set larger than L2 (index 8.5 GB + 2.2 GB reads per step vs 126 MB L2)",
+           "l2_policy": "working set larger than L2 (index 21 GB + 2.2 GB reads per step vs 126 MB L2)",
            "reads_per_gpu_per_step": n, "genome_bp": sum(lens)}
 
     # =====================================================================================
@@ -294,8 +294,8 @@ def main():
 
     # max over ranks
     ms, e2e_s = shard.reduce_max([ms, e2e_s], device=dev)
-    tot_c, tot_p, tot_over, tot_full, tot_list = shard.reduce_sum(
-        [st[k] for k in ("candidates", "probes", "overfetch", "full_extensions", "list_entries")], device=dev)
+    tot_c, tot_p, tot_over, tot_full, tot_list, tot_gather = shard.reduce_sum(
+        [st[k] for k in ("candidates", "probes", "overfetch", "full_extensions", "list_entries", "gathers")], device=dev)
     reads_total = n * world * a.steps
     value = reads_total / (ms * 1e-3)
     e2e_val = reads_total / e2e_s
@@ -317,7 +317,8 @@ def main():
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": peak_src, "kernel": "bsx_map_se_kernel", "algorithmic_bytes_per_read": bytes_per_read,
             "candidates_per_read": c_per_read, "headers_per_read": p_per_read,
-            "overfetch_per_read": tot_over / reads_total, "full_extensions_per_read": tot_full / reads_total}
+            "overfetch_per_read": tot_over / reads_total, "full_extensions_per_read": tot_full / reads_total,
+            "hbm_gathers_per_read": tot_gather / reads_total}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roof["traffic"] = prof.get("dram_bytes_per_read", 0) * n or None

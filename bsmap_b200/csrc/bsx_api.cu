@@ -158,6 +158,7 @@ extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size
         case 3: src = ix->d_tab; have = (2 * ix->n_keys + 1) * 4; break;
         case 4: src = ix->d_pos; have = ix->n_entries * 4; break;
         case 5: src = ix->d_tag; have = ix->d_tag ? ix->n_entries * 4 : 0; break;
+        case 6: src = ix->d_ctx; have = ix->d_ctx ? ix->n_entries * 8 : 0; break;
         default: bsx_set_error("bsx_index_download: unknown array %d", what); return BSX_ERR_ARG;
     }
     if (bytes > have) { bsx_set_error("bsx_index_download: asked %zu bytes, array has %zu", bytes, have); return BSX_ERR_ARG; }
@@ -166,13 +167,14 @@ extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size
 }
 
 extern "C" int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap) {
-    if (!ix || cap < 5) return 0;
+    if (!ix || cap < 6) return 0;
     ptrs[0] = ix->d_refcat; bytes[0] = ix->n_words * 4;
     ptrs[1] = ix->d_crefcat; bytes[1] = ix->n_words * 4;
     ptrs[2] = ix->d_tab; bytes[2] = (2 * ix->n_keys + 1) * 4;
     ptrs[3] = ix->d_pos; bytes[3] = ix->n_entries * 4;
     ptrs[4] = ix->d_tag; bytes[4] = ix->d_tag ? ix->n_entries * 4 : 0;
-    return 5;
+    ptrs[5] = ix->d_ctx; bytes[5] = ix->d_ctx ? ix->n_entries * 8 : 0;
+    return 6;
 }
 
 // metadata blob: everything a replica needs besides the big device arrays
@@ -234,12 +236,12 @@ extern "C" int bsx_index_replicate(const bsx_index *src, int device, bsx_index *
     std::vector<uint8_t> b = meta_blob(src);
     int rc = bsx_index_create_shell(b.data(), b.size(), device, out);
     if (rc) return rc;
-    void *sp[5], *dp[5]; size_t sb[5], db[5];
-    bsx_index_device_buffers(src, sp, sb, 5); bsx_index_device_buffers(*out, dp, db, 5);
+    void *sp[6], *dp[6]; size_t sb[6], db[6];
+    bsx_index_device_buffers(src, sp, sb, 6); bsx_index_device_buffers(*out, dp, db, 6);
     int can = 0;
     cudaDeviceCanAccessPeer(&can, device, src->device);
     if (can) { cudaSetDevice(device); cudaDeviceEnablePeerAccess(src->device, 0); cudaGetLastError(); }
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < 6; i++)
         if (sb[i] && sp[i]) BSX_CUDA_CHECK(cudaMemcpyPeer(dp[i], device, sp[i], src->device, sb[i]));
     BSX_CUDA_CHECK(cudaDeviceSynchronize());
     return BSX_OK;
@@ -362,7 +364,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     }
     MapArgs &a = m->base;
     memset(&a, 0, sizeof a);
-    a.refcat = ix->d_refcat; a.crefcat = ix->d_crefcat; a.tab = ix->d_tab; a.pos = ix->d_pos; a.tag = ix->d_tag;
+    a.refcat = ix->d_refcat; a.crefcat = ix->d_crefcat; a.tab = ix->d_tab; a.pos = ix->d_pos; a.tag = ix->d_tag; a.ctx = ix->d_ctx;
     a.seqinfo = ix->d_seqinfo; a.sites = ix->d_sites; a.site_off = ix->d_site_off; a.n_seq = ix->n_seq;
     a.s = p->seed_size; a.I = p->index_interval; a.v = p->max_snp_num; a.W = p->max_num_hits; a.r = p->report_repeat_hits;
     a.min_insert = p->min_insert; a.max_insert = p->max_insert; a.chains = p->chains; a.pairend = p->pairend; a.rrbs = p->rrbs;

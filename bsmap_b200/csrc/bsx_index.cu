@@ -67,7 +67,8 @@ __global__ void seed_items_kernel(const uint32_t *__restrict__ refcat, const uin
     uint32_t p = b.i0 + (uint32_t)(e - prefix[lo]) * (uint32_t)I;
     const uint32_t *m = (b.strand ? crefcat : refcat) + b.word_base;
     uint32_t key = seed_key_at(m, p, s, seed_bits);
-    items[e] = ((uint64_t)key << 32) | (uint64_t)(b.anchor + p);     // hit2int (dbseq.cpp:570)
+    // hit2int (dbseq.cpp:570); the strand rides along in bit 63, above every radix digit
+    items[e] = ((uint64_t)b.strand << 63) | ((uint64_t)key << 32) | (uint64_t)(b.anchor + p);
     atomicAdd(&hist[2 * key + b.strand], 1u);
 }
 
@@ -240,7 +241,51 @@ radix_scatter_kernel(const uint64_t *__restrict__ in, uint64_t n, int shift, int
     }
 }
 
-static int radix_sort_items(uint64_t *d_a, uint64_t *d_b, uint64_t n, int key_bits, uint32_t *d_out32, cudaStream_t st) {
+// Last pass for the WGBS table: besides the position it stores, next to every entry, the 16 reference
+// bases that precede the seed and the 16 that follow it on the entry's strand ("inline context").
+// The mapping kernel rejects >98 % of candidates from these 8 bytes, which arrive with the coalesced
+// list stream, instead of paying one random HBM access per candidate.
+__global__ void __launch_bounds__(RS_WARPS * 32)
+radix_scatter_ctx_kernel(const uint64_t *__restrict__ in, uint64_t n, int shift, int bits, uint32_t n_sub,
+                         const uint32_t *__restrict__ offs, const uint32_t *__restrict__ refcat,
+                         const uint32_t *__restrict__ crefcat, int seed_size, uint32_t *__restrict__ out_pos,
+                         uint2 *__restrict__ out_ctx) {
+    __shared__ uint32_t sh[RS_WARPS][1 << RS_MAX_BITS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t sub = blockIdx.x * RS_WARPS + wid;
+    const uint32_t nd = 1u << bits;
+    if (sub >= n_sub) return;
+    for (uint32_t d = lane; d < nd; d += 32) sh[wid][d] = offs[(uint64_t)d * n_sub + sub];
+    __syncwarp();
+    uint64_t b = (uint64_t)sub * RS_SUB_ITEMS, e = b + RS_SUB_ITEMS < n ? b + RS_SUB_ITEMS : n;
+    for (uint64_t i0 = b; i0 < e; i0 += 32) {
+        uint64_t i = i0 + lane;
+        const bool act = i < e;
+        uint64_t it = act ? in[i] : 0;
+        uint32_t d = act ? ((uint32_t)(it >> (32 + shift)) & (nd - 1)) : 0xffffffffu;
+        unsigned peers = __match_any_sync(BSX_FULL, d);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t dst = 0;
+        if (act) dst = sh[wid][d] + rank;
+        __syncwarp();
+        if (act && rank == 0) sh[wid][d] += __popc(peers);
+        __syncwarp();
+        if (act) {
+            const uint32_t c = (uint32_t)it;
+            const uint32_t *m = (it >> 63) ? crefcat : refcat;
+            const uint32_t bb = c - 16u, aa = c + (uint32_t)seed_size;
+            const uint32_t before = __funnelshift_l(m[(bb >> 4) + 1], m[bb >> 4], (bb & 15u) * 2u);
+            const uint32_t after = __funnelshift_l(m[(aa >> 4) + 1], m[aa >> 4], (aa & 15u) * 2u);
+            out_pos[dst] = c;
+            out_ctx[dst] = make_uint2(before, after);
+        }
+    }
+}
+
+struct bsx_ctx_out { const uint32_t *refcat, *crefcat; int seed_size; uint2 *ctx; };
+
+static int radix_sort_items(uint64_t *d_a, uint64_t *d_b, uint64_t n, int key_bits, uint32_t *d_out32, cudaStream_t st,
+                            const bsx_ctx_out *cx = nullptr) {
     // sorts by the key held in the high word; final pass writes the low word to d_out32
     int passes = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
     if (passes < 1) passes = 1;
@@ -258,7 +303,10 @@ static int radix_sort_items(uint64_t *d_a, uint64_t *d_b, uint64_t n, int key_bi
         BSX_CUDA_CHECK(cudaGetLastError());
         int rc = exclusive_scan_u32(d_hist, d_hist, n_hist, st);
         if (rc) { cudaFree(d_hist); return rc; }
-        if (p == passes - 1)
+        if (p == passes - 1 && cx)
+            radix_scatter_ctx_kernel<<<grid, RS_WARPS * 32, 0, st>>>(src, n, shift, bits, n_sub, d_hist, cx->refcat, cx->crefcat,
+                                                                      cx->seed_size, d_out32, cx->ctx);
+        else if (p == passes - 1)
             radix_scatter_kernel<uint32_t><<<grid, RS_WARPS * 32, 0, st>>>(src, n, shift, bits, n_sub, d_hist, d_out32);
         else
             radix_scatter_kernel<uint64_t><<<grid, RS_WARPS * 32, 0, st>>>(src, n, shift, bits, n_sub, d_hist, dst);
@@ -305,8 +353,9 @@ static void unmask_region(const char *seq, uint32_t len, uint32_t id, uint32_t T
 void bsx_index_free_device(bsx_index *ix) {
     if (ix->device >= 0) cudaSetDevice(ix->device);
     cudaFree(ix->d_refcat); cudaFree(ix->d_crefcat); cudaFree(ix->d_tab); cudaFree(ix->d_pos);
-    cudaFree(ix->d_tag); cudaFree(ix->d_seqinfo); cudaFree(ix->d_sites); cudaFree(ix->d_site_off);
+    cudaFree(ix->d_tag); cudaFree(ix->d_seqinfo); cudaFree(ix->d_sites); cudaFree(ix->d_site_off); cudaFree(ix->d_ctx);
     ix->d_refcat = ix->d_crefcat = ix->d_tab = ix->d_pos = ix->d_tag = ix->d_seqinfo = ix->d_sites = ix->d_site_off = nullptr;
+    ix->d_ctx = nullptr;
 }
 
 static int upload_seqinfo(bsx_index *ix) {
@@ -334,6 +383,7 @@ int bsx_index_alloc_device(bsx_index *ix) {
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_tab, (2 * ix->n_keys + 1) * 4));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_pos, (ix->n_entries + 64) * 4));
     if (ix->par.rrbs) BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, (ix->n_entries + 64) * 4));
+    else BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (ix->n_entries + 64) * sizeof(uint2)));
     return upload_seqinfo(ix);
 }
 
@@ -481,7 +531,10 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs) {
         if (rc) return rc;
         int key_bits = 1; while ((1ull << key_bits) < ix->n_keys) key_bits++;
         if (!p.rrbs) {
-            rc = radix_sort_items(d_a, d_b, n_items, key_bits, ix->d_pos, st);
+            BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (n_items + 64) * sizeof(uint2)));
+            BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, (n_items + 64) * sizeof(uint2), st));
+            bsx_ctx_out cx = {ix->d_refcat, ix->d_crefcat, s, ix->d_ctx};
+            rc = radix_sort_items(d_a, d_b, n_items, key_bits, ix->d_pos, st, &cx);
             if (rc) return rc;
         } else {
             uint32_t *d_order = nullptr;
@@ -498,6 +551,8 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs) {
         cudaFree(d_a); cudaFree(d_b);
     } else if (p.rrbs) {
         BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, 64 * 4));
+    } else {
+        BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, 64 * sizeof(uint2)));
     }
     cudaEventRecord(ev1, st);
     BSX_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <cuda_runtime.h>
 #include "../../include/bsmap_b200.h"
 
 struct bsx_block { uint32_t id, begin, end; };   // Block (dbseq.h:31-36)
@@ -23,6 +24,7 @@ struct bsx_index {
     uint32_t *d_refcat = nullptr, *d_crefcat = nullptr;   // 2-bit packed strands, margins zeroed
     uint32_t *d_tab = nullptr;      // 2*n_keys+1: [2k] list start, [2k+1] start of rc part, [2k+2] end
     uint32_t *d_pos = nullptr;      // n_entries positions (ref_anchor + p), lists fwd-ascending then rc-ascending
+    uint2 *d_ctx = nullptr;         // WGBS: per entry the 16 reference bases before the seed (.x) and the 16 after it (.y)
     uint32_t *d_tag = nullptr;      // RRBS: Hit.chr tag per entry
     uint32_t *d_seqinfo = nullptr;  // anchor[n_seq+1] | size[n_seq] | rc_offset[n_seq]
     uint32_t *d_sites = nullptr;    // RRBS: all digestion sites, concatenated

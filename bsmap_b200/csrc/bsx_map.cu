@@ -41,7 +41,7 @@ struct RS {                // per-read state, warp-uniform registers
     int filtered;
 };
 
-struct Ctr { uint32_t cand, probe, over, full, commit, list; };
+struct Ctr { uint32_t cand, probe, over, full, commit, list, gather; };
 
 __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
     return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
@@ -432,32 +432,54 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
 #pragma unroll
         for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
         zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+        if (!A.rrbs && lane < per) {
+            // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
+            const int xb = p_i - 16, xa = p_i + A.s;
+            uint32_t rb, mb, ra, ma;
+            if (xb >= 0) {
+                const int j = xb >> 4, sh = (xb & 15) * 2;
+                rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);      // j + 1 <= 9 because p <= 144
+                mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
+            } else {                                                                 // fewer than 16 bases before the seed
+                rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
+                if (xb <= -16) { rb = 0; mb = 0; }
+            }
+            {
+                const int j = xa >> 4, sh = (xa & 15) * 2;
+                const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
+                const uint32_t r0 = (j < BSX_FIXWORDS) ? R->rw[chain][j] : 0u, m0 = (j < BSX_FIXWORDS) ? R->m5[chain][j] : 0u;
+                ra = __funnelshift_l(r1, r0, sh); ma = __funnelshift_l(m1, m0, sh);
+            }
+            X->flank[lane] = make_uint4(rb, mb, ra, ma);
+        }
         __syncwarp();
         if (tot == 0) continue;                                          // every index2[_seed] == NULL
         const int sg = (int)(plan[0].w >> 16);
         const uint32_t tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
         const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
         // software pipeline: the list entry of step k+1 is loaded while step k is extended
-        uint32_t n_idx = 0, n_entry = 0, n_md = 0; int n_p = 0; bool n_valid;
+        uint32_t n_idx = 0, n_entry = 0, n_md = 0; int n_p = 0, n_li = 0; bool n_valid;
+        uint2 n_ctx = make_uint2(0, 0);
         {
             const uint32_t g = lane;
             n_valid = g < tot;
             int i = 0;
             for (int t = 1; t < per; t++) i += (g >= X->cum[t]);
             const uint4 e = plan[i];
-            n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu);
-            if (n_valid) n_entry = __ldg(A.pos + n_idx);
+            n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu); n_li = i;
+            if (n_valid) { n_entry = __ldg(A.pos + n_idx); if (!A.rrbs) n_ctx = __ldg(A.ctx + n_idx); }
         }
         for (uint32_t c0 = 0; c0 < tot; c0 += 32) {
-            const uint32_t idx = n_idx, entry = n_entry, md = n_md; const int p = n_p; bool valid = n_valid;
+            const uint32_t idx = n_idx, entry = n_entry, md = n_md; const int p = n_p, li = n_li; bool valid = n_valid;
+            const uint2 cx = n_ctx;
             if (c0 + 32 < tot) {
                 const uint32_t g = c0 + 32 + lane;
                 n_valid = g < tot;
                 int i = 0;
                 for (int t = 1; t < per; t++) i += (g >= X->cum[t]);
                 const uint4 e = plan[i];
-                n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu);
-                if (n_valid) n_entry = __ldg(A.pos + n_idx);
+                n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu); n_li = i;
+                if (n_valid) { n_entry = __ldg(A.pos + n_idx); if (!A.rrbs) n_ctx = __ldg(A.ctx + n_idx); }
             }
             uint32_t strand, chr = 0, loc;
             const uint32_t *refbase;
@@ -475,13 +497,23 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
                 loc = valid ? (entry - (uint32_t)p + anchor[chr >> 1]) : anchor[0];
             }
             uint32_t w = 0xffffu;
-            bool pass = false;
-            if (valid) {
+            bool pass = valid;
+            if (!A.rrbs && valid) {
+                // phase 0: mismatches among the <= 32 read bases that face the entry's inline context
+                // (a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the reference);
+                // no memory access beyond the list stream itself
+                const uint4 f = X->flank[li];
+                w = __popc(bsx_mm_word_bits(f.x, f.y, cx.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx.y));
+                pass = w <= S.thres;
+            }
+            const unsigned vm = __ballot_sync(BSX_FULL, valid);
+            C.gather += __popc(__ballot_sync(BSX_FULL, pass));
+            if (pass) {
+                // phase 1: one aligned 16-byte gather (48 bases away from the seed)
                 w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
                 pass = w <= S.thres;
             }
             const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
-            const unsigned vm = __ballot_sync(BSX_FULL, valid);
             unsigned pm = 0;
             if (pm1) {
                 if (pass) {
@@ -588,9 +620,9 @@ __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr &C, uint32_
         atomicAdd(A.stats + 0, (unsigned long long)C.cand); atomicAdd(A.stats + 1, (unsigned long long)C.probe);
         atomicAdd(A.stats + 2, (unsigned long long)C.over); atomicAdd(A.stats + 3, (unsigned long long)C.full);
         atomicAdd(A.stats + 4, (unsigned long long)C.commit); atomicAdd(A.stats + 5, (unsigned long long)mapped);
-        atomicAdd(A.stats + 6, (unsigned long long)C.list);
+        atomicAdd(A.stats + 6, (unsigned long long)C.list); atomicAdd(A.stats + 7, (unsigned long long)C.gather);
     }
-    C.cand = C.probe = C.over = C.full = C.commit = C.list = 0; mapped = 0;
+    C.cand = C.probe = C.over = C.full = C.commit = C.list = C.gather = 0; mapped = 0;
 }
 
 // ------------------------------------------------------------------ SE kernel
@@ -607,7 +639,7 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
-    Ctr C = {0, 0, 0, 0, 0, 0};
+    Ctr C = {0, 0, 0, 0, 0, 0, 0};
     uint32_t mapped = 0;
     for (;;) {
         uint32_t r = 0;
@@ -752,7 +784,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride, *dd_b = dd_a + A.dd_stride;
     PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
     uint16_t *npairs = X->npairs;
-    Ctr C = {0, 0, 0, 0, 0, 0};
+    Ctr C = {0, 0, 0, 0, 0, 0, 0};
     uint32_t mapped = 0;
     const size_t W1 = (size_t)A.W + 1;
     for (;;) {

@@ -8,7 +8,8 @@
 
 struct MapArgs {
     // RefSeq
-    const uint32_t *refcat, *crefcat, *tab, *pos, *tag, *seqinfo;   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
+    const uint32_t *refcat, *crefcat, *tab, *pos, *tag, *seqinfo;
+    const uint2 *ctx;             // WGBS inline context per entry: 16 bases before / after the seed   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
     const uint32_t *sites, *site_off;
     uint32_t n_seq;
     // Param
@@ -54,6 +55,7 @@ struct SelSm {
     int sidx[16][2];                  // seedindex (sum, segment)
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
     uint32_t cum[20];                 // SnpAlign: prefix of the I list lengths of the current mode
+    uint4 flank[16];                  // per sub-seed list: read bases / mask before (x,y) and after (z,w) the seed
 };
 
 // per-CTA constant tables (no integer division in the per-read code)

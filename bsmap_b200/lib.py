@@ -36,10 +36,10 @@ class IndexInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("candidates", "probes", "overfetch", "full_extensions", "commits",
-                                          "mapped", "list_entries", "reserved")]
+                                          "mapped", "list_entries", "gathers")]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 REC = np.dtype([("loc", "<u4"), ("chr", "<u4"), ("nhits", "<u4"), ("nm", "u1"), ("chain", "u1"),

@@ -95,11 +95,11 @@ typedef struct bsx_stats {
     uint64_t candidates;      /* C: CountMismatch calls the reference semantics make      */
     uint64_t probes;          /* P: distinct seed-table headers read                      */
     uint64_t overfetch;       /* candidates evaluated speculatively past an exit point    */
-    uint64_t full_extensions; /* candidates that needed more than the first 16-byte chunk */
+    uint64_t full_extensions; /* candidates whose whole window was loaded (exact CountMismatch)  */
     uint64_t commits;         /* accepted hits                                            */
     uint64_t mapped;          /* reads / pairs with a reported location                   */
     uint64_t list_entries;    /* position-list entries loaded                             */
-    uint64_t reserved;
+    uint64_t gathers;         /* candidates that survived the inline-context filter (one 16-byte HBM gather each) */
 } bsx_stats;
 
 typedef struct bsx_index bsx_index;     /* device-resident 2-bit reference + seed table (RefSeq) */
@@ -121,10 +121,11 @@ int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info);
 const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k);
 uint32_t bsx_index_seq_size(const bsx_index *ix, uint32_t k);
 /* copy a device array to the host (parity tests): what = 0 refcat, 1 crefcat, 2 anchors (n_seq+1),
- * 3 tab (2*n_keys+1), 4 pos (n_entries), 5 RRBS tags (n_entries) */
+ * 3 tab (2*n_keys+1), 4 pos (n_entries), 5 RRBS tags (n_entries), 6 WGBS inline context (n_entries x 2 u32:
+ * the 16 reference bases before and the 16 after each entry's seed) */
 int bsx_index_download(const bsx_index *ix, int what, void *dst, size_t bytes);
 /* device pointers + byte sizes of the arrays a replica needs (one-time NVLink broadcast):
- * order refcat, crefcat, tab, pos, tag(may be NULL/0).  Returns the count written. */
+ * order refcat, crefcat, tab, pos, tag, ctx (NULL/0 when absent).  Returns the count written (cap >= 6). */
 int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap);
 /* replica on another device: allocates there and copies over NVLink with cudaMemcpyPeer */
 int bsx_index_replicate(const bsx_index *src, int device, bsx_index **out);

@@ -59,6 +59,27 @@ def test_index_matches_oracle(name):
     if kw.get("D"):
         msg = _diff_arrays("tag", ix.download("tag"), np.array(oref.pos_tag))
         assert msg is None, msg
+    else:
+        # inline context: the 16 reference bases before / after every entry's seed, on the entry's strand
+        tab, pos = np.array(oref.tab).astype(np.int64), np.array(oref.pos).astype(np.int64)
+        ctx = ix.download("ctx").reshape(-1, 2)
+        strand = np.zeros(len(pos), dtype=bool)
+        starts, mids, ends = tab[0:-1:2], tab[1::2], tab[2::2]
+        nz = np.nonzero(ends > mids)[0]
+        for k in nz[:200000]:
+            strand[mids[k]:ends[k]] = True
+        if len(nz) > 200000:   # vectorised fallback for big tables
+            strand = np.zeros(len(pos) + 1, dtype=np.int64); np.add.at(strand, mids, 1); np.add.at(strand, ends, -1)
+            strand = np.cumsum(strand)[:-1] > 0
+        f, c = np.array(oref.refcat).astype(np.uint64), np.array(oref.crefcat).astype(np.uint64)
+        def window(coord):
+            w, sh = coord >> 4, ((coord & 15) * 2).astype(np.uint64)
+            lo_f, hi_f = f[w + 1], f[w]; lo_c, hi_c = c[w + 1], c[w]
+            hi, lo = np.where(strand, hi_c, hi_f), np.where(strand, lo_c, lo_f)
+            return ((((hi << np.uint64(32)) | lo) << sh) >> np.uint64(32)) & np.uint64(0xffffffff)
+        s_ = kw.get("s", 16)
+        assert np.array_equal(ctx[:, 0].astype(np.uint64), window(pos - 16)), "ctx.before differs"
+        assert np.array_equal(ctx[:, 1].astype(np.uint64), window(pos + s_)), "ctx.after differs"
     ix.close(); oref.close()
 
 
