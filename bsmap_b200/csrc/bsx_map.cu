@@ -105,15 +105,21 @@ __device__ __forceinline__ void trim_adapter(const MapArgs &A, ReadSm *R, RS &S,
     }
 }
 
-// FilterReads (align.cpp:579-589); returns 1 when the read is rejected
+// FilterReads (align.cpp:579-589); returns 1 when the read is rejected.  The chains the read will be
+// aligned with are packed here (ConvertBinaySeq), because the valid-base mask also gives CountNs.
+__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, const RS &S, int chain, int lane);
 __device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, int lane) {
     trim_adapter(A, R, S, lane);
+    S.fc = A.chains || (S.readset < 2);             // flag_chain / cflag_chain (align.cpp:93-94)
+    S.cc = A.chains || (S.readset == 2);
     if (S.len < A.s) return 1;
-    int n = 0;
-    for (int i = lane; i < S.len; i += 32) n += !bsx_is_acgt(R->ascii[i]);
+    if (S.fc) pack_chain(A, R, S, 0, lane);
+    if (S.cc) pack_chain(A, R, S, 1, lane);
+    int nv = lane < BSX_FIXWORDS ? __popc(R->m5[S.fc ? 0 : 1][lane]) : 0;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(BSX_FULL, n, d);
-    if (n > A.max_ns) return 1;
+    for (int d = 8; d; d >>= 1) nv += __shfl_xor_sync(BSX_FULL, nv, d);
+    nv = __shfl_sync(BSX_FULL, nv, 0);
+    if (S.len - nv > A.max_ns) return 1;            // CountNs (align.cpp:48-55)
     S.rmsn = (int)((unsigned)(A.v + 1) * (unsigned)(S.len - 1) / (unsigned)S.raw);
     return 0;
 }
@@ -395,7 +401,7 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint3
         if (sl > A.max_insert || sl < A.min_insert) { __syncwarp(); return 0; }
     }
     const uint32_t cnt = chain ? R->nc[w] : R->nh[w];
-    if (!store_all && (int)w < S.best) S.best = (int)w;
+    if ((int)w < S.best) S.best = (int)w;            // lowest level that holds a hit
     if (lane == 0) {
         if (store_all) hits[((size_t)w * 2 + chain) * (A.W + 1) + cnt] = make_uint2(chr, loc);
         else if ((int)w == S.best) hits[(size_t)chain * (A.W + 1) + cnt] = make_uint2(chr, loc);
@@ -409,29 +415,81 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint3
     return 0;
 }
 
+// 32 candidates that survived phase 0: phase 1 (one aligned 16-byte gather), phase 2 (whole window, exact
+// CountMismatch) and the ordered commit.  Returns 1 when SnpAlign must return; `last` = exiting lane.
+__device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all,
+                                                 int chain, int mode, bool pass, uint32_t entry, uint32_t idx, uint32_t md, int p,
+                                                 uint32_t chr, uint32_t tbl, int lane, Ctr &C, int &last) {
+    const uint32_t *anchor = A.seqinfo;
+    uint32_t strand, loc;
+    if (!A.rrbs) { strand = idx >= md; loc = entry - (uint32_t)p; }      // h = -profile.a + i - seed_start_array
+    else { strand = chr & 1u; loc = entry - (uint32_t)p + anchor[chr >> 1]; }
+    const uint32_t *refbase = strand ? A.crefcat : A.refcat;
+    uint32_t w = 0xffffu;
+    C.gather += __popc(__ballot_sync(BSX_FULL, pass));
+    if (pass) {
+        w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
+        pass = w <= S.thres;
+    }
+    const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
+    unsigned pm = 0;
+    if (pm1) {
+        if (pass) {
+            w = full_mismatch(R, chain, S.nw, refbase, loc, S.thres);
+            pass = w <= S.thres;
+        }
+        pm = __ballot_sync(BSX_FULL, pass);
+        C.full += __popc(pm1);
+    }
+    int ret = 0;
+    last = 31;
+    while (pm) {
+        const int src = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const uint32_t w_s = __shfl_sync(BSX_FULL, w, src);
+        if (w_s > S.thres) continue;                                     // threshold lowered by an earlier commit
+        uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
+        const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
+        uint32_t chr_s;
+        if (!A.rrbs) {
+            // RefSeq::int2hit (dbseq.cpp:585-595)
+            int left = 0, right = (int)A.n_seq;
+            while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
+            chr_s = (uint32_t)left * 2u + strand_s;
+            loc_s -= anchor[left];
+        } else {
+            chr_s = __shfl_sync(BSX_FULL, chr, src);
+            loc_s -= anchor[chr_s >> 1];
+        }
+        ret = commit_hit(A, R, S, hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
+                         A.rrbs && chain == 0 && !A.pairend, lane, C);
+        if (ret) { last = src; break; }
+    }
+    return ret;
+}
+
 // SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
 // The I position lists of the mode are walked as ONE concatenated stream (sub-seed 0's forward
-// entries, its rc entries, sub-seed 1's ...: exactly the reference's visiting order), 32 candidates per
-// step, so steps stay full even when the individual lists are short.
+// entries, its rc entries, sub-seed 1's ...: exactly the reference's visiting order), 64 candidates per
+// step (two per lane), so steps stay full even when the individual lists are short.
 __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr &C) {
-    const uint32_t *anchor = A.seqinfo;
     const int per = A.rrbs ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !S.fc : !S.cc) continue;
         const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
-        // prefix of list lengths (lanes < per), seed zone of the mode
+        // prefix of the list lengths (lanes < per)
         uint32_t n_i = 0; int p_i = 0;
         if (lane < per) { const uint4 e = plan[lane]; n_i = e.z - e.x; p_i = (int)(e.w & 0xffffu); }
         uint32_t incl = n_i;
 #pragma unroll
         for (int d = 1; d < 16; d <<= 1) { const uint32_t y = __shfl_up_sync(BSX_FULL, incl, d); if (lane >= d) incl += y; }
+        const uint32_t tot = __shfl_sync(BSX_FULL, incl, per - 1);
+        if (tot == 0) continue;                                          // every index2[_seed] == NULL
         if (lane < per) X->cum[lane + 1] = incl;
         if (lane == 0) X->cum[0] = 0;
-        const uint32_t tot = __shfl_sync(BSX_FULL, incl, per - 1);
-        int zlo = lane < per ? p_i : 1000, zhi = lane < per ? p_i : -1;
-#pragma unroll
-        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+        const uint32_t c1 = per > 1 ? __shfl_sync(BSX_FULL, incl, 0) : 0xffffffffu;
+        const uint32_t c2 = per > 2 ? __shfl_sync(BSX_FULL, incl, 1) : 0xffffffffu;
+        const uint32_t c3 = per > 3 ? __shfl_sync(BSX_FULL, incl, 2) : 0xffffffffu;
         if (!A.rrbs && lane < per) {
             // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
             const int xb = p_i - 16, xa = p_i + A.s;
@@ -440,10 +498,9 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
                 const int j = xb >> 4, sh = (xb & 15) * 2;
                 rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);      // j + 1 <= 9 because p <= 144
                 mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
-            } else {                                                                 // fewer than 16 bases before the seed
+            } else if (xb > -16) {                                                   // fewer than 16 bases before the seed
                 rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
-                if (xb <= -16) { rb = 0; mb = 0; }
-            }
+            } else { rb = 0; mb = 0; }
             {
                 const int j = xa >> 4, sh = (xa & 15) * 2;
                 const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
@@ -453,104 +510,77 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
             X->flank[lane] = make_uint4(rb, mb, ra, ma);
         }
         __syncwarp();
-        if (tot == 0) continue;                                          // every index2[_seed] == NULL
         const int sg = (int)(plan[0].w >> 16);
-        const uint32_t tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
         const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
-        // software pipeline: the list entry of step k+1 is loaded while step k is extended
-        uint32_t n_idx = 0, n_entry = 0, n_md = 0; int n_p = 0, n_li = 0; bool n_valid;
-        uint2 n_ctx = make_uint2(0, 0);
-        {
-            const uint32_t g = lane;
-            n_valid = g < tot;
-            int i = 0;
-            for (int t = 1; t < per; t++) i += (g >= X->cum[t]);
-            const uint4 e = plan[i];
-            n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu); n_li = i;
-            if (n_valid) { n_entry = __ldg(A.pos + n_idx); if (!A.rrbs) n_ctx = __ldg(A.ctx + n_idx); }
-        }
-        for (uint32_t c0 = 0; c0 < tot; c0 += 32) {
-            const uint32_t idx = n_idx, entry = n_entry, md = n_md; const int p = n_p, li = n_li; bool valid = n_valid;
-            const uint2 cx = n_ctx;
-            if (c0 + 32 < tot) {
-                const uint32_t g = c0 + 32 + lane;
-                n_valid = g < tot;
-                int i = 0;
-                for (int t = 1; t < per; t++) i += (g >= X->cum[t]);
+        uint32_t tbl = 0; bool have_tbl = false;
+        for (uint32_t c0 = 0; c0 < tot; c0 += 64) {
+            uint32_t entry[2], idx[2], md[2], chr[2]; int p[2]; bool pass[2];
+            unsigned vm[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t g = c0 + 32 * h + lane;
+                bool valid = g < tot;
+                int i;
+                if (per <= 4) i = (int)(g >= c1) + (int)(g >= c2) + (int)(g >= c3);
+                else { i = 0; for (int t = 1; t < per; t++) i += (g >= X->cum[t]); }
                 const uint4 e = plan[i];
-                n_idx = e.x + (g - X->cum[i]); n_md = e.y; n_p = (int)(e.w & 0xffffu); n_li = i;
-                if (n_valid) { n_entry = __ldg(A.pos + n_idx); if (!A.rrbs) n_ctx = __ldg(A.ctx + n_idx); }
-            }
-            uint32_t strand, chr = 0, loc;
-            const uint32_t *refbase;
-            if (!A.rrbs) {
-                strand = idx >= md;
-                refbase = strand ? A.crefcat : A.refcat;
-                loc = entry - (uint32_t)p;                               // h = -profile.a + i - seed_start_array
-            } else {
-                // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
-                const uint32_t tag = valid ? __ldg(A.tag + idx) : 0u;
-                chr = tag & 0xffffu; strand = chr & 1u;
-                if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
-                if (entry < (uint32_t)p) valid = false;
-                refbase = strand ? A.crefcat : A.refcat;
-                loc = valid ? (entry - (uint32_t)p + anchor[chr >> 1]) : anchor[0];
-            }
-            uint32_t w = 0xffffu;
-            bool pass = valid;
-            if (!A.rrbs && valid) {
-                // phase 0: mismatches among the <= 32 read bases that face the entry's inline context
-                // (a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the reference);
-                // no memory access beyond the list stream itself
-                const uint4 f = X->flank[li];
-                w = __popc(bsx_mm_word_bits(f.x, f.y, cx.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx.y));
-                pass = w <= S.thres;
-            }
-            const unsigned vm = __ballot_sync(BSX_FULL, valid);
-            C.gather += __popc(__ballot_sync(BSX_FULL, pass));
-            if (pass) {
-                // phase 1: one aligned 16-byte gather (48 bases away from the seed)
-                w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
-                pass = w <= S.thres;
-            }
-            const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
-            unsigned pm = 0;
-            if (pm1) {
-                if (pass) {
-                    w = full_mismatch(R, chain, S.nw, refbase, loc, S.thres);
-                    pass = w <= S.thres;
-                }
-                pm = __ballot_sync(BSX_FULL, pass);
-                C.full += __popc(pm1);
-            }
-            C.list += min(32u, tot - c0);
-            int ret = 0, last = 31;
-            while (pm) {
-                const int src = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t w_s = __shfl_sync(BSX_FULL, w, src);
-                if (w_s > S.thres) continue;                             // threshold lowered by an earlier commit
-                uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
-                const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
-                uint32_t chr_s;
+                idx[h] = e.x + (g - X->cum[i]); md[h] = e.y; p[h] = (int)(e.w & 0xffffu);
+                entry[h] = 0; chr[h] = 0; pass[h] = false;
                 if (!A.rrbs) {
-                    // RefSeq::int2hit (dbseq.cpp:585-595)
-                    int left = 0, right = (int)A.n_seq;
-                    while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
-                    chr_s = (uint32_t)left * 2u + strand_s;
-                    loc_s -= anchor[left];
+                    if (valid) {
+                        entry[h] = __ldg(A.pos + idx[h]);
+                        const uint2 cx = __ldg(A.ctx + idx[h]);
+                        // phase 0: mismatches among the <= 32 read bases that face the entry's inline context
+                        // (a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the reference);
+                        // no memory access beyond the list stream itself
+                        const uint4 f = X->flank[i];
+                        const uint32_t w0 = __popc(bsx_mm_word_bits(f.x, f.y, cx.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx.y));
+                        pass[h] = w0 <= S.thres;
+                    }
+                    const uint32_t nv = tot - c0 > 32u * h ? tot - c0 - 32u * h : 0u;
+                    vm[h] = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
                 } else {
-                    chr_s = __shfl_sync(BSX_FULL, chr, src);
-                    loc_s -= anchor[chr_s >> 1];
+                    // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
+                    if (valid) {
+                        entry[h] = __ldg(A.pos + idx[h]);
+                        const uint32_t tag = __ldg(A.tag + idx[h]);
+                        chr[h] = tag & 0xffffu;
+                        if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
+                        if (entry[h] < (uint32_t)p[h]) valid = false;
+                    }
+                    pass[h] = valid;
+                    vm[h] = __ballot_sync(BSX_FULL, valid);
                 }
-                ret = commit_hit(A, R, S, hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
-                                 A.rrbs && chain == 0 && !A.pairend, lane, C);
-                if (ret) { last = src; break; }
+            }
+            const unsigned pm0 = __ballot_sync(BSX_FULL, pass[0]), pm1 = __ballot_sync(BSX_FULL, pass[1]);
+            C.list += min(64u, tot - c0);
+            int ret = 0, last = 31, half = 2;
+            if (pm0 | pm1) {
+                if (!have_tbl) {
+                    int zlo = lane < per ? p_i : 1000, zhi = lane < per ? p_i : -1;
+#pragma unroll
+                    for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+                    zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+                    tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
+                    have_tbl = true;
+                }
+                if (pm0) {
+                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass[0], entry[0], idx[0], md[0], p[0], chr[0], tbl, lane, C, last);
+                    if (ret) half = 0;
+                }
+                if (!ret && pm1) {
+                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass[1], entry[1], idx[1], md[1], p[1], chr[1], tbl, lane, C, last);
+                    if (ret) half = 1;
+                }
             }
             // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted)
-            if (last == 31) C.cand += __popc(vm);
-            else { const unsigned upto = (2u << last) - 1u; C.cand += __popc(vm & upto); C.over += __popc(vm & ~upto); }
-            if (ret) return 1;
+            if (!ret) C.cand += __popc(vm[0]) + __popc(vm[1]);
+            else {
+                const unsigned upto = (2u << last) - 1u;
+                if (half == 0) { C.cand += __popc(vm[0] & upto); C.over += __popc(vm[0] & ~upto) + __popc(vm[1]); }
+                else { C.cand += __popc(vm[0]) + __popc(vm[1] & upto); C.over += __popc(vm[1] & ~upto); }
+                return 1;
+            }
         }
     }
     return 0;
@@ -560,8 +590,6 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
 __device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, int lane, Ctr &C, uint32_t *dbg) {
     S.seedseg = min((S.len - A.I + 1) / A.s, S.rmsn + 1);
     if (S.seedseg < 0) S.seedseg = 0;
-    S.fc = A.chains || (S.readset < 2);
-    S.cc = A.chains || (S.readset == 2);
     S.thres = (uint32_t)S.rmsn;
     S.nw = (S.len + 15) >> 4;
     S.dn = 0; S.best = 99;
@@ -569,7 +597,6 @@ __device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
     __syncwarp();
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !S.fc : !S.cc) continue;
-        pack_chain(A, R, S, chain, lane);
         select_seeds(A, K, R, X, S, chain, lane, C);
         if (dbg && lane == 0) {
             dbg[chain * 20 + 0] = (uint32_t)S.seedseg;
@@ -584,11 +611,7 @@ __device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X,
     prepare_read(A, K, R, X, S, lane, C, dbg);
     for (int m = 0; m < S.seedseg; m++) {
         snp_align(A, R, X, S, hits, dd, store_all, m, lane, C);
-        if (!A.rrbs) {
-            bool any = false;
-            for (int ii = 0; ii <= m; ii++) any |= (R->nh[ii] || R->nc[ii]);
-            if (any) return;
-        }
+        if (!A.rrbs && S.best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
     }
 }
 
@@ -600,8 +623,8 @@ __device__ void write_record(const MapArgs &A, const ReadSm *R, const RS &S, con
     bsx_rec o;
     o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)S.filtered; o.len = (uint8_t)S.len;
     if (!S.filtered) {
-        int ii, sum = 0;
-        for (ii = 0; ii <= S.rmsn; ii++) if ((sum = R->nh[ii] + R->nc[ii]) > 0) break;
+        const int ii = S.best <= S.rmsn ? S.best : S.rmsn + 1;     // lowest non-empty bucket
+        const int sum = ii <= S.rmsn ? R->nh[ii] + R->nc[ii] : 0;
         o.nm = (uint8_t)ii;
         if (sum > 0) {
             const int j = (int)(bsx_myrand(S.index, A.randseed) % (uint32_t)sum);
@@ -656,7 +679,7 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
         else if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
         __syncwarp();
         write_record(A, R, S, hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
-        if (!S.filtered) { bool any = false; for (int ii = 0; ii <= S.rmsn; ii++) any |= (R->nh[ii] || R->nc[ii]); mapped += any; }
+        if (!S.filtered && S.best <= S.rmsn) mapped++;
         __syncwarp();
     }
     flush_counters(A, C, mapped, lane);
