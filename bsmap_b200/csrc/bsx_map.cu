@@ -28,6 +28,11 @@
 #include <cstdio>
 #include "bsx_map.cuh"
 
+#define BSX_READ_BLOCK 4        // consecutive reads a warp takes per work-counter atomic
+#ifndef BSX_SE_MIN_CTAS
+#define BSX_SE_MIN_CTAS 4
+#endif
+
 namespace {
 
 struct RS {                // per-read state, warp-uniform registers
@@ -344,18 +349,21 @@ __device__ __forceinline__ uint32_t partial_mismatch(const ReadSm *R, int chain,
     return w;
 }
 
-// CountMismatch (align.h:167-200) over the whole read; stops early once above the threshold
+// CountMismatch (align.h:167-200) over the whole read.  All window words are requested before the
+// first one is used (one memory latency instead of a chain of nw+1); a count above the threshold is only
+// ever compared with it, so summing every word is equivalent to the reference's early returns.
 __device__ __forceinline__ uint32_t full_mismatch(const ReadSm *R, int chain, int nw, const uint32_t *__restrict__ refbase,
                                                   uint32_t loc, uint32_t thres) {
     const uint32_t *rp = refbase + (loc >> 4);
     const uint32_t sh2 = (loc & 15u) * 2u;
-    uint32_t w = 0, prev = __ldg(rp);
-    for (int j = 0; j < nw; j++) {
-        const uint32_t next = __ldg(rp + j + 1);
-        w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(next, prev, sh2)));
-        prev = next;
-        if (w > thres) break;
-    }
+    uint32_t win[BSX_FIXWORDS];
+#pragma unroll
+    for (int j = 0; j < BSX_FIXWORDS; j++) win[j] = (j <= nw) ? __ldg(rp + j) : 0u;
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < BSX_FIXWORDS - 1; j++)
+        if (j < nw) w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(win[j + 1], win[j], sh2)));
+    (void)thres;
     return w;
 }
 
@@ -513,35 +521,61 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
         const int sg = (int)(plan[0].w >> 16);
         const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
         uint32_t tbl = 0; bool have_tbl = false;
+        // list lookup of stream element g: which sub-seed list, and its position in the seed table
+        auto locate = [&](uint32_t g, int &i, uint32_t &ix) {
+            if (per <= 4) i = (int)(g >= c1) + (int)(g >= c2) + (int)(g >= c3);
+            else { i = 0; for (int t = 1; t < per; t++) i += (g >= X->cum[t]); }
+            ix = plan[i].x + (g - X->cum[i]);
+        };
+        // WGBS fast path is software-pipelined: the inline context of step k+1 is in flight while step k
+        // is filtered.  Only survivors ever touch pos[] or the reference.
+        uint2 n_cx[2]; int n_li[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            n_cx[h] = make_uint2(0, 0); n_li[h] = 0;
+            const uint32_t g = 32 * h + lane;
+            if (!A.rrbs && g < tot) { uint32_t ix; locate(g, n_li[h], ix); n_cx[h] = __ldg(A.ctx + ix); }
+        }
         for (uint32_t c0 = 0; c0 < tot; c0 += 64) {
             uint32_t entry[2], idx[2], md[2], chr[2]; int p[2]; bool pass[2];
             unsigned vm[2];
+            uint2 cx[2]; int li[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) { cx[h] = n_cx[h]; li[h] = n_li[h]; }
+            if (!A.rrbs && c0 + 64 < tot) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t g = c0 + 64 + 32 * h + lane;
+                    if (g < tot) { uint32_t ix; locate(g, n_li[h], ix); n_cx[h] = __ldg(A.ctx + ix); }
+                }
+            }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t g = c0 + 32 * h + lane;
                 bool valid = g < tot;
-                int i;
-                if (per <= 4) i = (int)(g >= c1) + (int)(g >= c2) + (int)(g >= c3);
-                else { i = 0; for (int t = 1; t < per; t++) i += (g >= X->cum[t]); }
-                const uint4 e = plan[i];
-                idx[h] = e.x + (g - X->cum[i]); md[h] = e.y; p[h] = (int)(e.w & 0xffffu);
-                entry[h] = 0; chr[h] = 0; pass[h] = false;
+                entry[h] = 0; chr[h] = 0; pass[h] = false; idx[h] = 0; md[h] = 0; p[h] = 0;
                 if (!A.rrbs) {
                     if (valid) {
-                        entry[h] = __ldg(A.pos + idx[h]);
-                        const uint2 cx = __ldg(A.ctx + idx[h]);
                         // phase 0: mismatches among the <= 32 read bases that face the entry's inline context
                         // (a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the reference);
                         // no memory access beyond the list stream itself
-                        const uint4 f = X->flank[i];
-                        const uint32_t w0 = __popc(bsx_mm_word_bits(f.x, f.y, cx.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx.y));
+                        const uint4 f = X->flank[li[h]];
+                        const uint32_t w0 = __popc(bsx_mm_word_bits(f.x, f.y, cx[h].x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx[h].y));
                         pass[h] = w0 <= S.thres;
+                        if (pass[h]) {                                   // survivor: fetch its table entry
+                            const uint4 e = plan[li[h]];
+                            idx[h] = e.x + (g - X->cum[li[h]]); md[h] = e.y; p[h] = (int)(e.w & 0xffffu);
+                            entry[h] = __ldg(A.pos + idx[h]);
+                        }
                     }
                     const uint32_t nv = tot - c0 > 32u * h ? tot - c0 - 32u * h : 0u;
                     vm[h] = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
                 } else {
                     // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
                     if (valid) {
+                        int i; locate(g, i, idx[h]);
+                        const uint4 e = plan[i];
+                        md[h] = e.y; p[h] = (int)(e.w & 0xffffu);
                         entry[h] = __ldg(A.pos + idx[h]);
                         const uint32_t tag = __ldg(A.tag + idx[h]);
                         chr[h] = tag & 0xffffu;
@@ -649,7 +683,7 @@ __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr &C, uint32_
 }
 
 // ------------------------------------------------------------------ SE kernel
-__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_SE_MIN_CTAS)
 bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -664,11 +698,14 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
     Ctr C = {0, 0, 0, 0, 0, 0, 0};
     uint32_t mapped = 0;
+    uint32_t r = 0, r_end = 0;
     for (;;) {
-        uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(A.work_counter, 1u);
-        r = __shfl_sync(BSX_FULL, r, 0);
-        if (r >= A.n) break;
+        if (r == r_end) {                       // one atomic hands this warp BSX_READ_BLOCK consecutive reads
+            if (lane == 0) r = atomicAdd(A.work_counter, (uint32_t)BSX_READ_BLOCK);
+            r = __shfl_sync(BSX_FULL, r, 0);
+            if (r >= A.n) break;
+            r_end = min(r + (uint32_t)BSX_READ_BLOCK, A.n);
+        }
         if ((C.cand | C.list) & 0x80000000u) flush_counters(A, C, mapped, lane);
         RS S;
         S.rmsn = 0; S.seedseg = 0; S.nw = 0; S.thres = 0; S.fc = S.cc = 0; S.dn = 0; S.best = 99;
@@ -681,6 +718,7 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
         write_record(A, R, S, hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
         if (!S.filtered && S.best <= S.rmsn) mapped++;
         __syncwarp();
+        r++;
     }
     flush_counters(A, C, mapped, lane);
 }
