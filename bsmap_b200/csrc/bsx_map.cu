@@ -28,25 +28,30 @@
 #include <cstdio>
 #include "bsx_map.cuh"
 
+#ifndef BSX_READ_BLOCK
 #define BSX_READ_BLOCK 4        // consecutive reads a warp takes per work-counter atomic
+#endif
+#ifndef BSX_PIPE
+#define BSX_PIPE 1              // software-pipeline the inline-context loads one step ahead
+#endif
 #ifndef BSX_SE_MIN_CTAS
 #define BSX_SE_MIN_CTAS 4
 #endif
 
 namespace {
 
-struct RS {                // per-read state, warp-uniform registers
-    int len, raw, rmsn, seedseg, nw;
+struct RS {                // hot per-read state, warp-uniform registers (the rest lives in ReadSm)
+    int len, rmsn, nw;
     uint32_t thres;
     int fc, cc;            // flag_chain / cflag_chain
-    uint32_t index;
-    int readset;
     uint32_t dn;           // dedupe entries
-    int best;              // SE: level whose hits are stored
-    int filtered;
+    int best;              // lowest mismatch level that holds a hit
 };
 
-struct Ctr { uint32_t cand, probe, over, full, commit, list, gather; };
+// work counters live in shared memory (SelSm::ctr, bsx_stats order); lane 0 updates them
+enum { CT_CAND = 0, CT_PROBE, CT_OVER, CT_FULL, CT_COMMIT, CT_MAPPED, CT_LIST, CT_GATHER };
+typedef uint32_t Ctr;
+#define CTR_ADD(C, k, v) do { if (lane == 0) (C)[k] += (uint32_t)(v); } while (0)
 
 __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
     return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
@@ -71,12 +76,12 @@ __device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, RS &S, co
     uint32_t *dst = reinterpret_cast<uint32_t *>(R->ascii);
     for (int t = lane; t < 40; t += 32) dst[t] = (t * 4 < (int)A.stride) ? __ldg(src + t) : 0u;
     __syncwarp();
-    S.len = len; S.raw = len; S.readset = readset; S.index = A.first_index + r;
+    S.len = len; R->raw = len; R->readset = readset; R->index = A.first_index + r;
 }
 
 // TrimAdapter (align.cpp:371-425): adapters in -A order, positions ascending, first success wins
 __device__ __forceinline__ void trim_adapter(const MapArgs &A, ReadSm *R, RS &S, int lane) {
-    S.raw = S.len;
+    R->raw = S.len;
     const int len = S.len, s = A.s;
     const uint8_t *sq = R->ascii;
     const int tail = A.rrbs ? 5 : 4;
@@ -115,8 +120,8 @@ __device__ __forceinline__ void trim_adapter(const MapArgs &A, ReadSm *R, RS &S,
 __device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, const RS &S, int chain, int lane);
 __device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, int lane) {
     trim_adapter(A, R, S, lane);
-    S.fc = A.chains || (S.readset < 2);             // flag_chain / cflag_chain (align.cpp:93-94)
-    S.cc = A.chains || (S.readset == 2);
+    S.fc = A.chains || (R->readset < 2);             // flag_chain / cflag_chain (align.cpp:93-94)
+    S.cc = A.chains || (R->readset == 2);
     if (S.len < A.s) return 1;
     if (S.fc) pack_chain(A, R, S, 0, lane);
     if (S.cc) pack_chain(A, R, S, 1, lane);
@@ -125,7 +130,7 @@ __device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, i
     for (int d = 8; d; d >>= 1) nv += __shfl_xor_sync(BSX_FULL, nv, d);
     nv = __shfl_sync(BSX_FULL, nv, 0);
     if (S.len - nv > A.max_ns) return 1;            // CountNs (align.cpp:48-55)
-    S.rmsn = (int)((unsigned)(A.v + 1) * (unsigned)(S.len - 1) / (unsigned)S.raw);
+    S.rmsn = (int)((unsigned)(A.v + 1) * (unsigned)(S.len - 1) / (unsigned)R->raw);
     return 0;
 }
 
@@ -196,8 +201,8 @@ __device__ __forceinline__ uint32_t list_size(const SelSm *X, int p, int rrbs) {
     return rrbs ? n : (n ? n + 2 : 0u);
 }
 
-__device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, const RS &S, int chain, int lane, Ctr &C) {
-    const int s = A.s, I = A.I, len = S.len, seg = S.seedseg;
+__device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, const RS &S, int chain, int lane, Ctr *C) {
+    const int s = A.s, I = A.I, len = S.len, seg = R->seedseg;
     const int mo = (A.rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
     const int cso = (A.rrbs && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
     const int lim = I - 1 + mo;
@@ -224,7 +229,7 @@ __device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
-    C.probe += np;
+    CTR_ADD(C, CT_PROBE, np);
     __syncwarp();
     // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset, in parallel
     if (!A.rrbs) {
@@ -391,7 +396,7 @@ __device__ int ccgg_seglen(const MapArgs &A, uint32_t chr, uint32_t pos, int rea
 // One accepted candidate, executed warp-uniformly: int2hit, bounds, dedupe, bucket append, exits
 // (align.cpp:270-278 and its three twins).  Returns 1 when SnpAlign must return.
 __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all, int chain,
-                          uint32_t chr, uint32_t loc, uint32_t w, int mode, int frag_filter, int lane, Ctr &C) {
+                          uint32_t chr, uint32_t loc, uint32_t w, int mode, int frag_filter, int lane, Ctr *C) {
     const uint32_t *anchor = A.seqinfo, *size = A.seqinfo + A.n_seq + 1, *rcoff = A.seqinfo + 2 * A.n_seq + 1;
     const uint32_t k = chr >> 1;
     if (chr & 1u) loc = rcoff[k] - (uint32_t)S.len - loc;
@@ -416,25 +421,43 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint3
         if (chain) R->nc[w] = (uint16_t)(cnt + 1); else R->nh[w] = (uint16_t)(cnt + 1);
     }
     __syncwarp();
-    C.commit++;
+    CTR_ADD(C, CT_COMMIT, 1);
     const int tot = (int)R->nh[w] + (int)R->nc[w];
     if ((int)w == mode && !A.pairend && A.r == 0 && tot > 1) return 1;
     if (tot >= A.W) { if (w == 0) return 1; S.thres = w - 1; }
     return 0;
 }
 
-// 32 candidates that survived phase 0: phase 1 (one aligned 16-byte gather), phase 2 (whole window, exact
-// CountMismatch) and the ordered commit.  Returns 1 when SnpAlign must return; `last` = exiting lane.
-__device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all,
-                                                 int chain, int mode, bool pass, uint32_t entry, uint32_t idx, uint32_t md, int p,
-                                                 uint32_t chr, uint32_t tbl, int lane, Ctr &C, int &last) {
+// Stream geometry of one (mode, chain): which list holds stream element g and where it sits in pos[]
+struct Stream { const uint4 *plan; const SelSm *X; int per; uint32_t c1, c2, c3; };
+__device__ __forceinline__ int stream_list(const Stream &T, uint32_t g) {
+    if (T.per <= 4) return (int)(g >= T.c1) + (int)(g >= T.c2) + (int)(g >= T.c3);
+    int i = 0;
+    for (int t = 1; t < T.per; t++) i += (g >= T.X->cum[t]);
+    return i;
+}
+
+// 32 candidates that survived phase 0 (stream elements g0 + lane): phase 1 (one aligned 16-byte gather),
+// phase 2 (whole window, exact CountMismatch) and the ordered commit.  Everything a survivor needs
+// (table entry, strand, read offset) is re-derived here, so the filter loop carries no state for it.
+// Returns 1 when SnpAlign must return; `last` = exiting lane.
+__device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS &S, const Stream &T, uint2 *hits, uint32_t *dd,
+                                                 int store_all, int chain, int mode, bool pass, uint32_t g0, uint32_t tbl,
+                                                 int lane, Ctr *C, int &last) {
     const uint32_t *anchor = A.seqinfo;
-    uint32_t strand, loc;
-    if (!A.rrbs) { strand = idx >= md; loc = entry - (uint32_t)p; }      // h = -profile.a + i - seed_start_array
-    else { strand = chr & 1u; loc = entry - (uint32_t)p + anchor[chr >> 1]; }
+    uint32_t strand = 0, loc = anchor[0], chr = 0;
+    if (pass) {
+        const uint32_t g = g0 + lane;
+        const int i = stream_list(T, g);
+        const uint4 e = T.plan[i];
+        const uint32_t idx = e.x + (g - T.X->cum[i]);
+        const uint32_t entry = __ldg(A.pos + idx), p = e.w & 0xffffu;
+        if (!A.rrbs) { strand = idx >= e.y; loc = entry - p; }           // h = -profile.a + i - seed_start_array
+        else { chr = __ldg(A.tag + idx) & 0xffffu; strand = chr & 1u; loc = entry - p + anchor[chr >> 1]; }
+    }
     const uint32_t *refbase = strand ? A.crefcat : A.refcat;
     uint32_t w = 0xffffu;
-    C.gather += __popc(__ballot_sync(BSX_FULL, pass));
+    CTR_ADD(C, CT_GATHER, __popc(__ballot_sync(BSX_FULL, pass)));
     if (pass) {
         w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
         pass = w <= S.thres;
@@ -447,7 +470,7 @@ __device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS
             pass = w <= S.thres;
         }
         pm = __ballot_sync(BSX_FULL, pass);
-        C.full += __popc(pm1);
+        CTR_ADD(C, CT_FULL, __popc(pm1));
     }
     int ret = 0;
     last = 31;
@@ -480,14 +503,15 @@ __device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS
 // The I position lists of the mode are walked as ONE concatenated stream (sub-seed 0's forward
 // entries, its rc entries, sub-seed 1's ...: exactly the reference's visiting order), 64 candidates per
 // step (two per lane), so steps stay full even when the individual lists are short.
-__device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr &C) {
+__device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
     const int per = A.rrbs ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !S.fc : !S.cc) continue;
-        const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
+        Stream T;
+        T.plan = plan_of(R, chain, A.plan_cap) + mode * per; T.X = X; T.per = per;
         // prefix of the list lengths (lanes < per)
         uint32_t n_i = 0; int p_i = 0;
-        if (lane < per) { const uint4 e = plan[lane]; n_i = e.z - e.x; p_i = (int)(e.w & 0xffffu); }
+        if (lane < per) { const uint4 e = T.plan[lane]; n_i = e.z - e.x; p_i = (int)(e.w & 0xffffu); }
         uint32_t incl = n_i;
 #pragma unroll
         for (int d = 1; d < 16; d <<= 1) { const uint32_t y = __shfl_up_sync(BSX_FULL, incl, d); if (lane >= d) incl += y; }
@@ -495,9 +519,9 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
         if (tot == 0) continue;                                          // every index2[_seed] == NULL
         if (lane < per) X->cum[lane + 1] = incl;
         if (lane == 0) X->cum[0] = 0;
-        const uint32_t c1 = per > 1 ? __shfl_sync(BSX_FULL, incl, 0) : 0xffffffffu;
-        const uint32_t c2 = per > 2 ? __shfl_sync(BSX_FULL, incl, 1) : 0xffffffffu;
-        const uint32_t c3 = per > 3 ? __shfl_sync(BSX_FULL, incl, 2) : 0xffffffffu;
+        T.c1 = per > 1 ? __shfl_sync(BSX_FULL, incl, 0) : 0xffffffffu;
+        T.c2 = per > 2 ? __shfl_sync(BSX_FULL, incl, 1) : 0xffffffffu;
+        T.c3 = per > 3 ? __shfl_sync(BSX_FULL, incl, 2) : 0xffffffffu;
         if (!A.rrbs && lane < per) {
             // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
             const int xb = p_i - 16, xa = p_i + A.s;
@@ -518,112 +542,89 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
             X->flank[lane] = make_uint4(rb, mb, ra, ma);
         }
         __syncwarp();
-        const int sg = (int)(plan[0].w >> 16);
-        const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;   // RRBS segment tag
         uint32_t tbl = 0; bool have_tbl = false;
-        // list lookup of stream element g: which sub-seed list, and its position in the seed table
-        auto locate = [&](uint32_t g, int &i, uint32_t &ix) {
-            if (per <= 4) i = (int)(g >= c1) + (int)(g >= c2) + (int)(g >= c3);
-            else { i = 0; for (int t = 1; t < per; t++) i += (g >= X->cum[t]); }
-            ix = plan[i].x + (g - X->cum[i]);
-        };
-        // WGBS fast path is software-pipelined: the inline context of step k+1 is in flight while step k
-        // is filtered.  Only survivors ever touch pos[] or the reference.
-        uint2 n_cx[2]; int n_li[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            n_cx[h] = make_uint2(0, 0); n_li[h] = 0;
-            const uint32_t g = 32 * h + lane;
-            if (!A.rrbs && g < tot) { uint32_t ix; locate(g, n_li[h], ix); n_cx[h] = __ldg(A.ctx + ix); }
-        }
-        for (uint32_t c0 = 0; c0 < tot; c0 += 64) {
-            uint32_t entry[2], idx[2], md[2], chr[2]; int p[2]; bool pass[2];
-            unsigned vm[2];
-            uint2 cx[2]; int li[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) { cx[h] = n_cx[h]; li[h] = n_li[h]; }
-            if (!A.rrbs && c0 + 64 < tot) {
+        uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
+        int ret = 0;
+        for (uint32_t c0 = 0; c0 < tot && !ret; c0 += 64) {
+            bool pass0 = false, pass1 = false;
+            unsigned vm0, vm1;
+            if (!A.rrbs) {
+                // phase 0: mismatches among the <= 32 read bases that face the entry's inline context (8 bytes that
+                // arrive with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres` rejects
+                // exactly like the reference; pos[] and the reference are only touched by survivors.
+                const uint32_t g0 = c0 + lane, g1 = g0 + 32;
+                uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0); int l0 = 0, l1 = 0;
+                if (g0 < tot) { l0 = stream_list(T, g0); cx0 = __ldg(A.ctx + T.plan[l0].x + (g0 - X->cum[l0])); }
+                if (g1 < tot) { l1 = stream_list(T, g1); cx1 = __ldg(A.ctx + T.plan[l1].x + (g1 - X->cum[l1])); }
+                if (g0 < tot) {
+                    const uint4 f = X->flank[l0];
+                    pass0 = __popc(bsx_mm_word_bits(f.x, f.y, cx0.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx0.y)) <= S.thres;
+                }
+                if (g1 < tot) {
+                    const uint4 f = X->flank[l1];
+                    pass1 = __popc(bsx_mm_word_bits(f.x, f.y, cx1.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx1.y)) <= S.thres;
+                }
+                const uint32_t left = tot - c0;
+                vm0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+                vm1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
+            } else {
+                // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
+                const int sg = (int)(T.plan[0].w >> 16);
+                const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;
+                const uint32_t p = T.plan[0].w & 0xffffu;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const uint32_t g = c0 + 64 + 32 * h + lane;
-                    if (g < tot) { uint32_t ix; locate(g, n_li[h], ix); n_cx[h] = __ldg(A.ctx + ix); }
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t g = c0 + 32 * h + lane;
-                bool valid = g < tot;
-                entry[h] = 0; chr[h] = 0; pass[h] = false; idx[h] = 0; md[h] = 0; p[h] = 0;
-                if (!A.rrbs) {
+                    const uint32_t g = c0 + 32 * h + lane;
+                    bool valid = g < tot;
                     if (valid) {
-                        // phase 0: mismatches among the <= 32 read bases that face the entry's inline context
-                        // (a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the reference);
-                        // no memory access beyond the list stream itself
-                        const uint4 f = X->flank[li[h]];
-                        const uint32_t w0 = __popc(bsx_mm_word_bits(f.x, f.y, cx[h].x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx[h].y));
-                        pass[h] = w0 <= S.thres;
-                        if (pass[h]) {                                   // survivor: fetch its table entry
-                            const uint4 e = plan[li[h]];
-                            idx[h] = e.x + (g - X->cum[li[h]]); md[h] = e.y; p[h] = (int)(e.w & 0xffffu);
-                            entry[h] = __ldg(A.pos + idx[h]);
-                        }
-                    }
-                    const uint32_t nv = tot - c0 > 32u * h ? tot - c0 - 32u * h : 0u;
-                    vm[h] = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
-                } else {
-                    // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
-                    if (valid) {
-                        int i; locate(g, i, idx[h]);
-                        const uint4 e = plan[i];
-                        md[h] = e.y; p[h] = (int)(e.w & 0xffffu);
-                        entry[h] = __ldg(A.pos + idx[h]);
-                        const uint32_t tag = __ldg(A.tag + idx[h]);
-                        chr[h] = tag & 0xffffu;
+                        const uint32_t idx = T.plan[0].x + g;
+                        const uint32_t tag = __ldg(A.tag + idx);
                         if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
-                        if (entry[h] < (uint32_t)p[h]) valid = false;
+                        if (__ldg(A.pos + idx) < p) valid = false;
                     }
-                    pass[h] = valid;
-                    vm[h] = __ballot_sync(BSX_FULL, valid);
+                    if (h == 0) { pass0 = valid; vm0 = __ballot_sync(BSX_FULL, valid); }
+                    else { pass1 = valid; vm1 = __ballot_sync(BSX_FULL, valid); }
                 }
             }
-            const unsigned pm0 = __ballot_sync(BSX_FULL, pass[0]), pm1 = __ballot_sync(BSX_FULL, pass[1]);
-            C.list += min(64u, tot - c0);
-            int ret = 0, last = 31, half = 2;
-            if (pm0 | pm1) {
-                if (!have_tbl) {
-                    int zlo = lane < per ? p_i : 1000, zhi = lane < per ? p_i : -1;
+            const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+            visited += min(64u, tot - c0);
+            if ((pm0 | pm1) == 0) { counted += __popc(vm0) + __popc(vm1); continue; }
+            if (!have_tbl) {
+                int zlo = lane < per ? p_i : 1000, zhi = lane < per ? p_i : -1;
 #pragma unroll
-                    for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-                    zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                    tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
-                    have_tbl = true;
-                }
-                if (pm0) {
-                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass[0], entry[0], idx[0], md[0], p[0], chr[0], tbl, lane, C, last);
-                    if (ret) half = 0;
-                }
-                if (!ret && pm1) {
-                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass[1], entry[1], idx[1], md[1], p[1], chr[1], tbl, lane, C, last);
-                    if (ret) half = 1;
-                }
+                for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+                zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+                tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
+                have_tbl = true;
             }
-            // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted)
-            if (!ret) C.cand += __popc(vm[0]) + __popc(vm[1]);
-            else {
-                const unsigned upto = (2u << last) - 1u;
-                if (half == 0) { C.cand += __popc(vm[0] & upto); C.over += __popc(vm[0] & ~upto) + __popc(vm[1]); }
-                else { C.cand += __popc(vm[0]) + __popc(vm[1] & upto); C.over += __popc(vm[1] & ~upto); }
-                return 1;
+            int last = 31;
+            if (pm0) {
+                ret = extend_and_commit(A, R, S, T, hits, dd, store_all, chain, mode, pass0, c0, tbl, lane, C, last);
+                if (ret) { counted += __popc(vm0 & ((2u << last) - 1u)); break; }
             }
+            counted += __popc(vm0);
+            if (pm1) {
+                ret = extend_and_commit(A, R, S, T, hits, dd, store_all, chain, mode, pass1, c0 + 32, tbl, lane, C, last);
+                if (ret) { counted += __popc(vm1 & ((2u << last) - 1u)); break; }
+            }
+            counted += __popc(vm1);
         }
+        // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
+        // entries evaluated past an exit point count as over-fetch
+        if (lane == 0) {
+            C[CT_LIST] += visited;
+            C[CT_CAND] += counted;
+            if (ret) C[CT_OVER] += (A.rrbs ? 0u : visited - counted);
+        }
+        if (ret) return 1;
     }
     return 0;
 }
 
 // everything RunAlign does before the mode loop (align.cpp:435-444)
-__device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, int lane, Ctr &C, uint32_t *dbg) {
-    S.seedseg = min((S.len - A.I + 1) / A.s, S.rmsn + 1);
-    if (S.seedseg < 0) S.seedseg = 0;
+__device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, int lane, Ctr *C, uint32_t *dbg) {
+    R->seedseg = min((S.len - A.I + 1) / A.s, S.rmsn + 1);
+    if (R->seedseg < 0) R->seedseg = 0;
     S.thres = (uint32_t)S.rmsn;
     S.nw = (S.len + 15) >> 4;
     S.dn = 0; S.best = 99;
@@ -633,17 +634,17 @@ __device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
         if (chain == 0 ? !S.fc : !S.cc) continue;
         select_seeds(A, K, R, X, S, chain, lane, C);
         if (dbg && lane == 0) {
-            dbg[chain * 20 + 0] = (uint32_t)S.seedseg;
-            for (int n = 0; n < S.seedseg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)X->arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)X->sidx[n][1]; }
+            dbg[chain * 20 + 0] = (uint32_t)R->seedseg;
+            for (int n = 0; n < R->seedseg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)X->arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)X->sidx[n][1]; }
         }
         __syncwarp();
     }
 }
 
 // SingleAlign::RunAlign (align.cpp:435-452)
-__device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr &C, uint32_t *dbg) {
+__device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint32_t *dbg) {
     prepare_read(A, K, R, X, S, lane, C, dbg);
-    for (int m = 0; m < S.seedseg; m++) {
+    for (int m = 0; m < R->seedseg; m++) {
         snp_align(A, R, X, S, hits, dd, store_all, m, lane, C);
         if (!A.rrbs && S.best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
     }
@@ -652,16 +653,16 @@ __device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X,
 // StringAlign (align.cpp:610-627) -> record
 __device__ void write_record(const MapArgs &A, const ReadSm *R, const RS &S, const uint2 *hits, int store_all,
                              bsx_rec *out, uint16_t *cnt, int lane) {
-    if (cnt && lane < 16) cnt[lane] = (!S.filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
+    if (cnt && lane < 16) cnt[lane] = (!R->filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
     if (lane != 0) return;
     bsx_rec o;
-    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)S.filtered; o.len = (uint8_t)S.len;
-    if (!S.filtered) {
+    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)R->filtered; o.len = (uint8_t)S.len;
+    if (!R->filtered) {
         const int ii = S.best <= S.rmsn ? S.best : S.rmsn + 1;     // lowest non-empty bucket
         const int sum = ii <= S.rmsn ? R->nh[ii] + R->nc[ii] : 0;
         o.nm = (uint8_t)ii;
         if (sum > 0) {
-            const int j = (int)(bsx_myrand(S.index, A.randseed) % (uint32_t)sum);
+            const int j = (int)(bsx_myrand(R->index, A.randseed) % (uint32_t)sum);
             const int nh = R->nh[ii];
             const int chain = j >= nh;
             const size_t lvl = store_all ? (size_t)ii * 2 : 0;
@@ -672,14 +673,10 @@ __device__ void write_record(const MapArgs &A, const ReadSm *R, const RS &S, con
     *out = o;
 }
 
-__device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr &C, uint32_t &mapped, int lane) {
-    if (lane == 0) {
-        atomicAdd(A.stats + 0, (unsigned long long)C.cand); atomicAdd(A.stats + 1, (unsigned long long)C.probe);
-        atomicAdd(A.stats + 2, (unsigned long long)C.over); atomicAdd(A.stats + 3, (unsigned long long)C.full);
-        atomicAdd(A.stats + 4, (unsigned long long)C.commit); atomicAdd(A.stats + 5, (unsigned long long)mapped);
-        atomicAdd(A.stats + 6, (unsigned long long)C.list); atomicAdd(A.stats + 7, (unsigned long long)C.gather);
-    }
-    C.cand = C.probe = C.over = C.full = C.commit = C.list = C.gather = 0; mapped = 0;
+__device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr *C, int lane) {
+    __syncwarp();
+    if (lane < 8) { atomicAdd(A.stats + lane, (unsigned long long)C[lane]); C[lane] = 0; }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ SE kernel
@@ -696,8 +693,9 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
-    Ctr C = {0, 0, 0, 0, 0, 0, 0};
-    uint32_t mapped = 0;
+    Ctr *C = X->ctr;
+    if (lane < 8) C[lane] = 0;
+    __syncwarp();
     uint32_t r = 0, r_end = 0;
     for (;;) {
         if (r == r_end) {                       // one atomic hands this warp BSX_READ_BLOCK consecutive reads
@@ -706,21 +704,21 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
             if (r >= A.n) break;
             r_end = min(r + (uint32_t)BSX_READ_BLOCK, A.n);
         }
-        if ((C.cand | C.list) & 0x80000000u) flush_counters(A, C, mapped, lane);
+        if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
         RS S;
-        S.rmsn = 0; S.seedseg = 0; S.nw = 0; S.thres = 0; S.fc = S.cc = 0; S.dn = 0; S.best = 99;
+        S.rmsn = 0; R->seedseg = 0; S.nw = 0; S.thres = 0; S.fc = S.cc = 0; S.dn = 0; S.best = 99;
         load_read(A, R, S, A.seq_a, A.len_a, r, A.readset, lane);
-        S.filtered = filter_read(A, R, S, lane);
+        R->filtered = filter_read(A, R, S, lane);
         uint32_t *dbg = A.debug ? A.debug + (size_t)r * 40 : nullptr;
-        if (!S.filtered) run_align(A, K, R, X, S, hits, dd, 0, lane, C, dbg);
+        if (!R->filtered) run_align(A, K, R, X, S, hits, dd, 0, lane, C, dbg);
         else if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
         __syncwarp();
         write_record(A, R, S, hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
-        if (!S.filtered && S.best <= S.rmsn) mapped++;
+        if (!R->filtered && S.best <= S.rmsn) CTR_ADD(C, CT_MAPPED, 1);
         __syncwarp();
         r++;
     }
-    flush_counters(A, C, mapped, lane);
+    flush_counters(A, C, lane);
 }
 
 // ------------------------------------------------------------------ PE kernel (pairs.cpp)
@@ -790,16 +788,16 @@ __device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb, c
 
 // the selection half of StringAlignUnpair (pairs.cpp:244-286) for one mate -> record
 __device__ void write_unpaired(const MapArgs &A, const ReadSm *R, const RS &S, const uint2 *hits, bsx_rec *out, uint16_t *cnt, int lane) {
-    if (cnt && lane < 16) cnt[lane] = (!S.filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
+    if (cnt && lane < 16) cnt[lane] = (!R->filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
     if (lane != 0) return;
     bsx_rec o;
-    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)S.filtered; o.len = (uint8_t)S.len;
-    if (!S.filtered) {
+    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)R->filtered; o.len = (uint8_t)S.len;
+    if (!R->filtered) {
         int na, ma = 0, ra = 0;
         for (na = 0; na <= S.rmsn; na++) if ((ma = R->nh[na] + R->nc[na]) > 0) break;
         uint2 h = make_uint2(0, 0);
         if (ma) {
-            if (ma > 1) ra = (int)(bsx_myrand(S.index, A.randseed) % (uint32_t)ma);
+            if (ma > 1) ra = (int)(bsx_myrand(R->index, A.randseed) % (uint32_t)ma);
             const int nh = R->nh[na];
             h = (ra < nh) ? hits[((size_t)na * 2) * (A.W + 1) + ra] : hits[((size_t)na * 2 + 1) * (A.W + 1) + (ra - nh)];
         }
@@ -845,28 +843,29 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride, *dd_b = dd_a + A.dd_stride;
     PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
     uint16_t *npairs = X->npairs;
-    Ctr C = {0, 0, 0, 0, 0, 0, 0};
-    uint32_t mapped = 0;
+    Ctr *C = X->ctr;
+    if (lane < 8) C[lane] = 0;
+    __syncwarp();
     const size_t W1 = (size_t)A.W + 1;
     for (;;) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1u);
         r = __shfl_sync(BSX_FULL, r, 0);
         if (r >= A.n) break;
-        if ((C.cand | C.list) & 0x80000000u) flush_counters(A, C, mapped, lane);
+        if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
         RS Sa, Sb;
-        Sa.rmsn = Sb.rmsn = 0; Sa.seedseg = Sb.seedseg = 0; Sa.dn = Sb.dn = 0; Sa.best = Sb.best = 99;
+        Sa.rmsn = Sb.rmsn = 0; Ra->seedseg = Rb->seedseg = 0; Sa.dn = Sb.dn = 0; Sa.best = Sb.best = 99;
         Sa.nw = Sb.nw = 0; Sa.thres = Sb.thres = 0; Sa.fc = Sa.cc = Sb.fc = Sb.cc = 0;
         load_read(A, Ra, Sa, A.seq_a, A.len_a, r, 1, lane);
         load_read(A, Rb, Sb, A.seq_b, A.len_b, r, 2, lane);
-        Sa.filtered = filter_read(A, Ra, Sa, lane);
-        Sb.filtered = filter_read(A, Rb, Sb, lane);
+        Ra->filtered = filter_read(A, Ra, Sa, lane);
+        Rb->filtered = filter_read(A, Rb, Sb, lane);
         if (lane < 16) { Ra->nh[lane] = Ra->nc[lane] = 0; Rb->nh[lane] = Rb->nc[lane] = 0; }
         __syncwarp();
         int paired = 0;
         bsx_pair_rec po;
         po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
-        if (!Sa.filtered && !Sb.filtered) {
+        if (!Ra->filtered && !Rb->filtered) {
             // PairAlign::RunAlign (pairs.cpp:137-190)
             prepare_read(A, K, Ra, X, Sa, lane, C, nullptr);
             prepare_read(A, K, Rb, X, Sb, lane, C, nullptr);
@@ -874,8 +873,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             __syncwarp();
             const int maxi = max(Sa.rmsn, Sb.rmsn);
             for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Sa.seedseg) snp_align(A, Ra, X, Sa, hits_a, dd_a, 1, i, lane, C);
-                if (i < Sb.seedseg) snp_align(A, Rb, X, Sb, hits_b, dd_b, 1, i, lane, C);
+                if (i < Ra->seedseg) snp_align(A, Ra, X, Sa, hits_a, dd_a, 1, i, lane, C);
+                if (i < Rb->seedseg) snp_align(A, Rb, X, Sb, hits_b, dd_b, 1, i, lane, C);
                 if (i <= Sa.rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
                 if (i <= Sb.rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
                 __syncwarp();
@@ -896,7 +895,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                     if (!np) continue;
                     int j = -1;
                     if (np == 1) j = 0;
-                    else if (A.r == 1) j = (int)(bsx_myrand(Sa.index, A.randseed) % (uint32_t)np);
+                    else if (A.r == 1) j = (int)(bsx_myrand(Ra->index, A.randseed) % (uint32_t)np);
                     if (j >= 0) {
                         const PairHitDev ph = pairs[(size_t)i * W1 + j];
                         po.a_chr = ph.a_chr; po.a_loc = ph.a_loc; po.b_chr = ph.b_chr; po.b_loc = ph.b_loc; po.insert = ph.insert;
@@ -907,21 +906,21 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                 }
             }
         } else {
-            if (!Sa.filtered) run_align(A, K, Ra, X, Sa, hits_a, dd_a, 1, lane, C, nullptr);
-            if (!Sb.filtered) run_align(A, K, Rb, X, Sb, hits_b, dd_b, 1, lane, C, nullptr);
+            if (!Ra->filtered) run_align(A, K, Ra, X, Sa, hits_a, dd_a, 1, lane, C, nullptr);
+            if (!Rb->filtered) run_align(A, K, Rb, X, Sb, hits_b, dd_b, 1, lane, C, nullptr);
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
         if (!out_paired && A.rrbs) {
-            if (lane == 0) { if (!Sa.filtered) fix_unpaired_short(A, Ra, Sa, hits_a); if (!Sb.filtered) fix_unpaired_short(A, Rb, Sb, hits_b); }
+            if (lane == 0) { if (!Ra->filtered) fix_unpaired_short(A, Ra, Sa, hits_a); if (!Rb->filtered) fix_unpaired_short(A, Rb, Sb, hits_b); }
             __syncwarp();
         }
         if (lane == 0) A.out_pair[r] = po;
         write_unpaired(A, Ra, Sa, hits_a, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
         write_unpaired(A, Rb, Sb, hits_b, A.out_b + r, A.cnt_b ? A.cnt_b + (size_t)r * 16 : nullptr, lane);
-        mapped += out_paired ? 1 : 0;
+        if (out_paired) CTR_ADD(C, CT_MAPPED, 1);
         __syncwarp();
     }
-    flush_counters(A, C, mapped, lane);
+    flush_counters(A, C, lane);
 }
 
 }  // namespace

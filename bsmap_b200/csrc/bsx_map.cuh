@@ -43,6 +43,10 @@ struct ReadSm {
     uint32_t rw[2][BSX_FIXWORDS];     // 2-bit read, chain 0 = as is, 1 = reverse complement (bseq/cbseq)
     uint32_t m5[2][BSX_FIXWORDS];     // 01 per ACGT base (reg/creg & 0x5555...)
     uint16_t nh[16], nc[16];          // _cur_n_hit / _cur_n_chit
+    // rarely-read per-read state (kept out of registers)
+    int raw, seedseg, readset, filtered;
+    uint32_t index;
+    uint32_t pad_[3];
     uint8_t ascii[160];
     // followed by uint4 plan[2][plan_cap]: {list start, rc start, list end, read offset of the seed}
 };
@@ -56,6 +60,7 @@ struct SelSm {
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
     uint32_t cum[20];                 // SnpAlign: prefix of the I list lengths of the current mode
     uint4 flank[16];                  // per sub-seed list: read bases / mask before (x,y) and after (z,w) the seed
+    uint32_t ctr[8];                  // work counters of this warp (bsx_stats order), flushed to global rarely
 };
 
 // per-CTA constant tables (no integer division in the per-read code)

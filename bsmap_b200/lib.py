@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbsmap_b200.so")
+LIB_PATH = os.environ.get("BSMAP_B200_LIB") or os.path.join(HERE, "libbsmap_b200.so")   # override: kernel A/B experiments
 
 MAXSNPS, MAXHITS, MAX_READLEN = 15, 1000, 144
 
