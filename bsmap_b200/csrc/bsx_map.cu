@@ -51,7 +51,7 @@ struct RS {                // hot per-read state, warp-uniform registers (the re
 // work counters live in shared memory (SelSm::ctr, bsx_stats order); lane 0 updates them
 enum { CT_CAND = 0, CT_PROBE, CT_OVER, CT_FULL, CT_COMMIT, CT_MAPPED, CT_LIST, CT_GATHER };
 typedef uint32_t Ctr;
-#define CTR_ADD(C, k, v) do { if (lane == 0) (C)[k] += (uint32_t)(v); } while (0)
+#define CTR_ADD(C, k, v) do { const uint32_t v_ = (uint32_t)(v); if (lane == 0) (C)[k] += v_; } while (0)   // v may hold warp collectives
 
 __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
     return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
