@@ -354,21 +354,20 @@ __device__ __forceinline__ uint32_t partial_mismatch(const ReadSm *R, int chain,
     return w;
 }
 
-// CountMismatch (align.h:167-200) over the whole read.  All window words are requested before the
-// first one is used (one memory latency instead of a chain of nw+1); a count above the threshold is only
-// ever compared with it, so summing every word is equivalent to the reference's early returns.
+// CountMismatch (align.h:167-200) over the whole read; stops early once above the threshold
+// (measured: requesting all window words up front is 10 % slower on config 2 -- most phase-1 survivors
+// are rejected within the first two words)
 __device__ __forceinline__ uint32_t full_mismatch(const ReadSm *R, int chain, int nw, const uint32_t *__restrict__ refbase,
                                                   uint32_t loc, uint32_t thres) {
     const uint32_t *rp = refbase + (loc >> 4);
     const uint32_t sh2 = (loc & 15u) * 2u;
-    uint32_t win[BSX_FIXWORDS];
-#pragma unroll
-    for (int j = 0; j < BSX_FIXWORDS; j++) win[j] = (j <= nw) ? __ldg(rp + j) : 0u;
-    uint32_t w = 0;
-#pragma unroll
-    for (int j = 0; j < BSX_FIXWORDS - 1; j++)
-        if (j < nw) w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(win[j + 1], win[j], sh2)));
-    (void)thres;
+    uint32_t w = 0, prev = __ldg(rp);
+    for (int j = 0; j < nw; j++) {
+        const uint32_t next = __ldg(rp + j + 1);
+        w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(next, prev, sh2)));
+        prev = next;
+        if (w > thres) break;
+    }
     return w;
 }
 
