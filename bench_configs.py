@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--configs", default="cfg1,cfg3,cfg4,cfg5")
     ap.add_argument("--genome-mb", type=float, default=3100.0)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=4_000_000)
     a = ap.parse_args()
     import torch
     import bsmap_b200 as B
@@ -124,7 +125,7 @@ def main():
             g, names, lens = big_genome(2)
             p = B.make_params(s=16, v=2, I=4, m=28, x=500, S=7, pairend=1)
             ix, tb = build_index(p, g, names, lens)
-            n = 4_000_000
+            n = a.pairs
             s1 = torch.zeros((n, 112), dtype=torch.uint8, device=dev); s2 = torch.zeros((n, 112), dtype=torch.uint8, device=dev)
             CH = 1 << 20
             for s0 in range(0, n, CH):

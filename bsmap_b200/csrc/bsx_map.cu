@@ -427,31 +427,19 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint3
     return 0;
 }
 
-// Stream geometry of one (mode, chain): which list holds stream element g and where it sits in pos[]
-struct Stream { const uint4 *plan; const SelSm *X; int per; uint32_t c1, c2, c3; };
-__device__ __forceinline__ int stream_list(const Stream &T, uint32_t g) {
-    if (T.per <= 4) return (int)(g >= T.c1) + (int)(g >= T.c2) + (int)(g >= T.c3);
-    int i = 0;
-    for (int t = 1; t < T.per; t++) i += (g >= T.X->cum[t]);
-    return i;
-}
-
-// 32 candidates that survived phase 0 (stream elements g0 + lane): phase 1 (one aligned 16-byte gather),
-// phase 2 (whole window, exact CountMismatch) and the ordered commit.  Everything a survivor needs
-// (table entry, strand, read offset) is re-derived here, so the filter loop carries no state for it.
+// 32 candidates that survived phase 0 (table entries idx0 + lane of one list): phase 1 (one aligned 16-byte
+// gather), phase 2 (whole window, exact CountMismatch) and the ordered commit.  Everything a survivor
+// needs is re-derived here from its table index, so the filter loop carries no state for it.
 // Returns 1 when SnpAlign must return; `last` = exiting lane.
-__device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS &S, const Stream &T, uint2 *hits, uint32_t *dd,
-                                                 int store_all, int chain, int mode, bool pass, uint32_t g0, uint32_t tbl,
-                                                 int lane, Ctr *C, int &last) {
+__device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd,
+                                                 int store_all, int chain, int mode, bool pass, uint32_t idx0, uint32_t md,
+                                                 uint32_t p, uint32_t tbl, int lane, Ctr *C, int &last) {
     const uint32_t *anchor = A.seqinfo;
     uint32_t strand = 0, loc = anchor[0], chr = 0;
     if (pass) {
-        const uint32_t g = g0 + lane;
-        const int i = stream_list(T, g);
-        const uint4 e = T.plan[i];
-        const uint32_t idx = e.x + (g - T.X->cum[i]);
-        const uint32_t entry = __ldg(A.pos + idx), p = e.w & 0xffffu;
-        if (!A.rrbs) { strand = idx >= e.y; loc = entry - p; }           // h = -profile.a + i - seed_start_array
+        const uint32_t idx = idx0 + lane;
+        const uint32_t entry = __ldg(A.pos + idx);
+        if (!A.rrbs) { strand = idx >= md; loc = entry - p; }           // h = -profile.a + i - seed_start_array
         else { chr = __ldg(A.tag + idx) & 0xffffu; strand = chr & 1u; loc = entry - p + anchor[chr >> 1]; }
     }
     const uint32_t *refbase = strand ? A.crefcat : A.refcat;
@@ -499,114 +487,97 @@ __device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS
 }
 
 // SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
-// The I position lists of the mode are walked as ONE concatenated stream (sub-seed 0's forward
-// entries, its rc entries, sub-seed 1's ...: exactly the reference's visiting order), 64 candidates per
-// step (two per lane), so steps stay full even when the individual lists are short.
+// The I position lists of the mode are walked in the reference's order (sub-seed 0's forward entries, its
+// rc entries, sub-seed 1's, ...), 64 table entries per step (two per lane).  Everything that depends on
+// the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
+// work is one 8-byte load, two masked XOR/popcount words and a compare.
 __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
     const int per = A.rrbs ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !S.fc : !S.cc) continue;
-        Stream T;
-        T.plan = plan_of(R, chain, A.plan_cap) + mode * per; T.X = X; T.per = per;
-        // prefix of the list lengths (lanes < per)
-        uint32_t n_i = 0; int p_i = 0;
-        if (lane < per) { const uint4 e = T.plan[lane]; n_i = e.z - e.x; p_i = (int)(e.w & 0xffffu); }
-        uint32_t incl = n_i;
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) { const uint32_t y = __shfl_up_sync(BSX_FULL, incl, d); if (lane >= d) incl += y; }
-        const uint32_t tot = __shfl_sync(BSX_FULL, incl, per - 1);
-        if (tot == 0) continue;                                          // every index2[_seed] == NULL
-        if (lane < per) X->cum[lane + 1] = incl;
-        if (lane == 0) X->cum[0] = 0;
-        T.c1 = per > 1 ? __shfl_sync(BSX_FULL, incl, 0) : 0xffffffffu;
-        T.c2 = per > 2 ? __shfl_sync(BSX_FULL, incl, 1) : 0xffffffffu;
-        T.c3 = per > 3 ? __shfl_sync(BSX_FULL, incl, 2) : 0xffffffffu;
-        if (!A.rrbs && lane < per) {
-            // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
-            const int xb = p_i - 16, xa = p_i + A.s;
-            uint32_t rb, mb, ra, ma;
-            if (xb >= 0) {
-                const int j = xb >> 4, sh = (xb & 15) * 2;
-                rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);      // j + 1 <= 9 because p <= 144
-                mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
-            } else if (xb > -16) {                                                   // fewer than 16 bases before the seed
-                rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
-            } else { rb = 0; mb = 0; }
-            {
+        const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
+        uint32_t tbl = 0; bool have_tbl = false;
+        uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
+        int ret = 0;
+        for (int i = 0; i < per && !ret; i++) {
+            const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
+            if (e.x == e.z) continue;                                    // index2[_seed] == NULL
+            const uint32_t p = e.w & 0xffffu;
+            uint32_t rb = 0, mb = 0, ra = 0, ma = 0, want = 0;
+            if (!A.rrbs) {
+                // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
+                const int xb = (int)p - 16, xa = (int)p + A.s;
+                if (xb >= 0) {
+                    const int j = xb >> 4, sh = (xb & 15) * 2;
+                    rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);  // j + 1 <= 9 because p <= 144
+                    mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
+                } else if (xb > -16) {                                               // fewer than 16 bases before the seed
+                    rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
+                }
                 const int j = xa >> 4, sh = (xa & 15) * 2;
                 const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
                 const uint32_t r0 = (j < BSX_FIXWORDS) ? R->rw[chain][j] : 0u, m0 = (j < BSX_FIXWORDS) ? R->m5[chain][j] : 0u;
                 ra = __funnelshift_l(r1, r0, sh); ma = __funnelshift_l(m1, m0, sh);
-            }
-            X->flank[lane] = make_uint4(rb, mb, ra, ma);
-        }
-        __syncwarp();
-        uint32_t tbl = 0; bool have_tbl = false;
-        uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
-        int ret = 0;
-        for (uint32_t c0 = 0; c0 < tot && !ret; c0 += 64) {
-            bool pass0 = false, pass1 = false;
-            unsigned vm0, vm1;
-            if (!A.rrbs) {
-                // phase 0: mismatches among the <= 32 read bases that face the entry's inline context (8 bytes that
-                // arrive with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres` rejects
-                // exactly like the reference; pos[] and the reference are only touched by survivors.
-                const uint32_t g0 = c0 + lane, g1 = g0 + 32;
-                uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0); int l0 = 0, l1 = 0;
-                if (g0 < tot) { l0 = stream_list(T, g0); cx0 = __ldg(A.ctx + T.plan[l0].x + (g0 - X->cum[l0])); }
-                if (g1 < tot) { l1 = stream_list(T, g1); cx1 = __ldg(A.ctx + T.plan[l1].x + (g1 - X->cum[l1])); }
-                if (g0 < tot) {
-                    const uint4 f = X->flank[l0];
-                    pass0 = __popc(bsx_mm_word_bits(f.x, f.y, cx0.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx0.y)) <= S.thres;
-                }
-                if (g1 < tot) {
-                    const uint4 f = X->flank[l1];
-                    pass1 = __popc(bsx_mm_word_bits(f.x, f.y, cx1.x)) + __popc(bsx_mm_word_bits(f.z, f.w, cx1.y)) <= S.thres;
-                }
-                const uint32_t left = tot - c0;
-                vm0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-                vm1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
             } else {
-                // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
-                const int sg = (int)(T.plan[0].w >> 16);
-                const uint32_t want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;
-                const uint32_t p = T.plan[0].w & 0xffffu;
+                const int sg = (int)(e.w >> 16);
+                want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;      // RRBS segment tag
+            }
+            for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
+                const uint32_t i0 = c0 + lane, i1 = i0 + 32;
+                bool pass0 = false, pass1 = false;
+                unsigned vm0, vm1;
+                if (!A.rrbs) {
+                    // phase 0: mismatches among the <= 32 read bases that face the entry's inline context (8 bytes
+                    // that arrive with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres`
+                    // rejects exactly like the reference; pos[] and the reference are only touched by survivors.
+                    uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0);
+                    if (i0 < e.z) cx0 = __ldg(A.ctx + i0);
+                    if (i1 < e.z) cx1 = __ldg(A.ctx + i1);
+                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= S.thres;
+                    if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= S.thres;
+                    const uint32_t left = e.z - c0;
+                    vm0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+                    vm1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
+                } else {
+                    // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t g = c0 + 32 * h + lane;
-                    bool valid = g < tot;
-                    if (valid) {
-                        const uint32_t idx = T.plan[0].x + g;
-                        const uint32_t tag = __ldg(A.tag + idx);
-                        if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
-                        if (__ldg(A.pos + idx) < p) valid = false;
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t idx = h ? i1 : i0;
+                        bool valid = idx < e.z;
+                        if (valid) {
+                            const uint32_t tag = __ldg(A.tag + idx);
+                            if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
+                            if (__ldg(A.pos + idx) < p) valid = false;
+                        }
+                        if (h == 0) { pass0 = valid; vm0 = __ballot_sync(BSX_FULL, valid); }
+                        else { pass1 = valid; vm1 = __ballot_sync(BSX_FULL, valid); }
                     }
-                    if (h == 0) { pass0 = valid; vm0 = __ballot_sync(BSX_FULL, valid); }
-                    else { pass1 = valid; vm1 = __ballot_sync(BSX_FULL, valid); }
                 }
-            }
-            const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
-            visited += min(64u, tot - c0);
-            if ((pm0 | pm1) == 0) { counted += __popc(vm0) + __popc(vm1); continue; }
-            if (!have_tbl) {
-                int zlo = lane < per ? p_i : 1000, zhi = lane < per ? p_i : -1;
+                const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+                visited += min(64u, e.z - c0);
+                if ((pm0 | pm1) == 0) { counted += __popc(vm0) + __popc(vm1); continue; }
+                if (!have_tbl) {
+                    // phase-1 chunk choice: keep away from the seed zone of this mode (all sub-seeds)
+                    int zlo = 1000, zhi = -1;
+                    if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
 #pragma unroll
-                for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-                zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
-                have_tbl = true;
+                    for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+                    zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+                    tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
+                    have_tbl = true;
+                }
+                int last = 31;
+                if (pm0) {
+                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass0, c0, e.y, p, tbl, lane, C, last);
+                    if (ret) { counted += __popc(vm0 & ((2u << last) - 1u)); break; }
+                }
+                counted += __popc(vm0);
+                if (pm1) {
+                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass1, c0 + 32, e.y, p, tbl, lane, C, last);
+                    if (ret) { counted += __popc(vm1 & ((2u << last) - 1u)); break; }
+                }
+                counted += __popc(vm1);
             }
-            int last = 31;
-            if (pm0) {
-                ret = extend_and_commit(A, R, S, T, hits, dd, store_all, chain, mode, pass0, c0, tbl, lane, C, last);
-                if (ret) { counted += __popc(vm0 & ((2u << last) - 1u)); break; }
-            }
-            counted += __popc(vm0);
-            if (pm1) {
-                ret = extend_and_commit(A, R, S, T, hits, dd, store_all, chain, mode, pass1, c0 + 32, tbl, lane, C, last);
-                if (ret) { counted += __popc(vm1 & ((2u << last) - 1u)); break; }
-            }
-            counted += __popc(vm1);
         }
         // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
         // entries evaluated past an exit point count as over-fetch
@@ -825,7 +796,7 @@ __device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, const RS &S, uin
     }
 }
 
-__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 2)
+__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 4)
 bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
