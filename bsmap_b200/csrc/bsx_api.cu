@@ -273,7 +273,8 @@ struct bsx_mapper {
     MapArgs base{};
 };
 
-int bsx_map_occupancy(int pe, size_t smem);   // bsx_map.cu
+int bsx_map_occupancy_se(size_t smem);   // bsx_map_se.cu
+int bsx_map_occupancy_pe(size_t smem);   // bsx_map_pe.cu
 
 static void slot_free(bsx_slot &s) {
     cudaFree(s.d_seq_a); cudaFree(s.d_seq_b); cudaFree(s.d_len_a); cudaFree(s.d_len_b); cudaFree(s.d_out_a); cudaFree(s.d_out_b);
@@ -336,8 +337,8 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     m->plan_cap = maxseg * (p->rrbs ? 1 : p->index_interval);
     int sms = 0;
     BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    int occ_se = bsx_map_occupancy(0, bsx_cta_smem_bytes(1, m->plan_cap));
-    int occ_pe = bsx_map_occupancy(1, bsx_cta_smem_bytes(2, m->plan_cap));
+    int occ_se = bsx_map_occupancy_se(bsx_cta_smem_bytes(1, m->plan_cap));
+    int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap));
     if (occ_se < 1 || occ_pe < 1) { delete m; bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
     const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;

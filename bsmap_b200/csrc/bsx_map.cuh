@@ -43,9 +43,15 @@ struct ReadSm {
     uint32_t rw[2][BSX_FIXWORDS];     // 2-bit read, chain 0 = as is, 1 = reverse complement (bseq/cbseq)
     uint32_t m5[2][BSX_FIXWORDS];     // 01 per ACGT base (reg/creg & 0x5555...)
     uint16_t nh[16], nc[16];          // _cur_n_hit / _cur_n_chit
-    // rarely-read per-read state (kept out of registers)
+    // per-read state (SingleAlign members), warp-uniform; kept in shared memory so the big device functions can be
+    // real calls (one copy of the code: the kernels used to be I-cache bound) instead of inlined register structs
     int raw, seedseg, readset, filtered;
     uint32_t index;
+    int len, rmsn, nw;                // read length after trimming, read_max_snp_num, packed words
+    uint32_t thres;                   // snp_thres
+    int fc, cc;                       // flag_chain / cflag_chain
+    uint32_t dn;                      // dedupe entries
+    int best;                         // lowest mismatch level that holds a hit
     uint32_t pad_[3];
     uint8_t ascii[160];
     // followed by uint4 plan[2][plan_cap]: {list start, rc start, list end, read offset of the seed}

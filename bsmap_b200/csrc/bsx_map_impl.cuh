@@ -1,4 +1,7 @@
-// bsx_map.cu -- SingleAlign / PairAlign on the device (align.cpp, align.h, pairs.cpp).
+// bsx_map_impl.cuh -- SingleAlign / PairAlign on the device (align.cpp, align.h, pairs.cpp).
+// Included by bsx_map_se.cu (everything inlined: fastest for the single-end kernel) and by bsx_map_pe.cu
+// (big device functions are real calls: the paired-end kernel shrinks from 321 KB to 134 KB of SASS and gains
+// 30 %, it was instruction-cache bound).
 //
 // One warp owns one read (SE) or one read pair (PE) from ASCII to result record; warps are
 // persistent and fetch work with an atomic counter, so heavy-tailed candidate lists balance.
@@ -31,6 +34,14 @@
 #ifndef BSX_READ_BLOCK
 #define BSX_READ_BLOCK 4        // consecutive reads a warp takes per work-counter atomic
 #endif
+#ifndef BSX_CALLS
+#define BSX_CALLS 1             // 1: big device functions are real calls (small binary), 0: everything inlined
+#endif
+#if BSX_CALLS
+#define BSX_FN __noinline__
+#else
+#define BSX_FN __forceinline__
+#endif
 #ifndef BSX_PIPE
 #define BSX_PIPE 1              // software-pipeline the inline-context loads one step ahead
 #endif
@@ -40,17 +51,11 @@
 
 namespace {
 
-struct RS {                // hot per-read state, warp-uniform registers (the rest lives in ReadSm)
-    int len, rmsn, nw;
-    uint32_t thres;
-    int fc, cc;            // flag_chain / cflag_chain
-    uint32_t dn;           // dedupe entries
-    int best;              // lowest mismatch level that holds a hit
-};
-
 // work counters live in shared memory (SelSm::ctr, bsx_stats order); lane 0 updates them
 enum { CT_CAND = 0, CT_PROBE, CT_OVER, CT_FULL, CT_COMMIT, CT_MAPPED, CT_LIST, CT_GATHER };
 typedef uint32_t Ctr;
+// warp-uniform state in shared memory is written by lane 0 only, fenced on both sides
+#define WSET(lhs, rhs) do { const auto v_ = (rhs); __syncwarp(); if (lane == 0) (lhs) = v_; __syncwarp(); } while (0)
 #define CTR_ADD(C, k, v) do { const uint32_t v_ = (uint32_t)(v); if (lane == 0) (C)[k] += v_; } while (0)   // v may hold warp collectives
 
 __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
@@ -67,7 +72,7 @@ __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
 }
 
 // ------------------------------------------------------------------ K2: load, trim, filter, pack
-__device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, RS &S, const uint8_t *seqs,
+__device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, const uint8_t *seqs,
                                           const uint16_t *lens, uint32_t r, int readset, int lane) {
     int len = lens[r];
     if (len > A.max_readlen) len = A.max_readlen;          // reads.cpp:115-117
@@ -76,13 +81,15 @@ __device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, RS &S, co
     uint32_t *dst = reinterpret_cast<uint32_t *>(R->ascii);
     for (int t = lane; t < 40; t += 32) dst[t] = (t * 4 < (int)A.stride) ? __ldg(src + t) : 0u;
     __syncwarp();
-    S.len = len; R->raw = len; R->readset = readset; R->index = A.first_index + r;
+    __syncwarp();
+    if (lane == 0) { R->len = len; R->raw = len; R->readset = readset; R->index = A.first_index + r; }
+    __syncwarp();
 }
 
 // TrimAdapter (align.cpp:371-425): adapters in -A order, positions ascending, first success wins
-__device__ __forceinline__ void trim_adapter(const MapArgs &A, ReadSm *R, RS &S, int lane) {
-    R->raw = S.len;
-    const int len = S.len, s = A.s;
+__device__ BSX_FN void trim_adapter(const MapArgs &A, ReadSm *R, int lane) {
+    WSET(R->raw, R->len);
+    const int len = R->len, s = A.s;
     const uint8_t *sq = R->ascii;
     const int tail = A.rrbs ? 5 : 4;
     for (int a = 0; a < A.n_adapter; a++) {
@@ -110,27 +117,31 @@ __device__ __forceinline__ void trim_adapter(const MapArgs &A, ReadSm *R, RS &S,
                 }
             }
             unsigned b = __ballot_sync(BSX_FULL, ok);
-            if (b) { S.len = pos0 + __ffs(b) - 1; return; }
+            if (b) { WSET(R->len, pos0 + __ffs(b) - 1); return; }
         }
     }
 }
 
 // FilterReads (align.cpp:579-589); returns 1 when the read is rejected.  The chains the read will be
 // aligned with are packed here (ConvertBinaySeq), because the valid-base mask also gives CountNs.
-__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, const RS &S, int chain, int lane);
-__device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, RS &S, int lane) {
-    trim_adapter(A, R, S, lane);
-    S.fc = A.chains || (R->readset < 2);             // flag_chain / cflag_chain (align.cpp:93-94)
-    S.cc = A.chains || (R->readset == 2);
-    if (S.len < A.s) return 1;
-    if (S.fc) pack_chain(A, R, S, 0, lane);
-    if (S.cc) pack_chain(A, R, S, 1, lane);
-    int nv = lane < BSX_FIXWORDS ? __popc(R->m5[S.fc ? 0 : 1][lane]) : 0;
+__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, int chain, int lane);
+__device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, int lane) {
+    trim_adapter(A, R,  lane);
+    {   // flag_chain / cflag_chain (align.cpp:93-94)
+        const int fc = A.chains || (R->readset < 2), cc = A.chains || (R->readset == 2);
+        __syncwarp();
+        if (lane == 0) { R->fc = fc; R->cc = cc; }
+        __syncwarp();
+    }
+    if (R->len < A.s) return 1;
+    if (R->fc) pack_chain(A, R,  0, lane);
+    if (R->cc) pack_chain(A, R,  1, lane);
+    int nv = lane < BSX_FIXWORDS ? __popc(R->m5[R->fc ? 0 : 1][lane]) : 0;
 #pragma unroll
     for (int d = 8; d; d >>= 1) nv += __shfl_xor_sync(BSX_FULL, nv, d);
     nv = __shfl_sync(BSX_FULL, nv, 0);
-    if (S.len - nv > A.max_ns) return 1;            // CountNs (align.cpp:48-55)
-    S.rmsn = (int)((unsigned)(A.v + 1) * (unsigned)(S.len - 1) / (unsigned)R->raw);
+    if (R->len - nv > A.max_ns) return 1;            // CountNs (align.cpp:48-55)
+    WSET(R->rmsn, (int)((unsigned)(A.v + 1) * (unsigned)(R->len - 1) / (unsigned)R->raw));
     return 0;
 }
 
@@ -152,8 +163,8 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t c) {
 
 // ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask.
 // Lane t < 20 converts bases [8t, 8t+8) with byte-SIMD ops; lane pairs are merged by shuffle.
-__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, const RS &S, int chain, int lane) {
-    const int len = S.len;
+__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, int chain, int lane) {
+    const int len = R->len;
     uint32_t half = 0, mhalf = 0;
     if (lane < 2 * BSX_FIXWORDS) {
         uint32_t w0, w1;
@@ -201,8 +212,8 @@ __device__ __forceinline__ uint32_t list_size(const SelSm *X, int p, int rrbs) {
     return rrbs ? n : (n ? n + 2 : 0u);
 }
 
-__device__ void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, const RS &S, int chain, int lane, Ctr *C) {
-    const int s = A.s, I = A.I, len = S.len, seg = R->seedseg;
+__device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int chain, int lane, Ctr *C) {
+    const int s = A.s, I = A.I, len = R->len, seg = R->seedseg;
     const int mo = (A.rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
     const int cso = (A.rrbs && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
     const int lim = I - 1 + mo;
@@ -394,36 +405,38 @@ __device__ int ccgg_seglen(const MapArgs &A, uint32_t chr, uint32_t pos, int rea
 
 // One accepted candidate, executed warp-uniformly: int2hit, bounds, dedupe, bucket append, exits
 // (align.cpp:270-278 and its three twins).  Returns 1 when SnpAlign must return.
-__device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd, int store_all, int chain,
+__device__ int commit_hit(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int chain,
                           uint32_t chr, uint32_t loc, uint32_t w, int mode, int frag_filter, int lane, Ctr *C) {
     const uint32_t *anchor = A.seqinfo, *size = A.seqinfo + A.n_seq + 1, *rcoff = A.seqinfo + 2 * A.n_seq + 1;
     const uint32_t k = chr >> 1;
-    if (chr & 1u) loc = rcoff[k] - (uint32_t)S.len - loc;
-    if (loc + (uint32_t)S.len > size[k]) return 0;                      // overflow the end of refseq
+    if (chr & 1u) loc = rcoff[k] - (uint32_t)R->len - loc;
+    if (loc + (uint32_t)R->len > size[k]) return 0;                      // overflow the end of refseq
     const uint32_t key = anchor[k] + loc;                               // == (chr>>1, loc), see DESIGN.md
     bool found = false;
-    for (uint32_t t = lane; t < S.dn; t += 32) found |= (dd[t] == key);
+    const uint32_t dn = R->dn;
+    for (uint32_t t = lane; t < dn; t += 32) found |= (dd[t] == key);
     if (__any_sync(BSX_FULL, found)) return 0;                          // hit already exists
-    if (S.dn < A.dd_stride) {                                           // capacity guard (RRBS fragment-filtered hits are uncounted)
-        if (lane == 0) dd[S.dn] = key;
-        S.dn++;
+    if (dn < A.dd_stride) {                                              // capacity guard (RRBS fragment-filtered hits are uncounted)
+        __syncwarp();
+        if (lane == 0) { dd[dn] = key; R->dn = dn + 1; }
+        __syncwarp();
     }
     if (frag_filter) {
-        const int sl = ccgg_seglen(A, chr, loc, S.len);
+        const int sl = ccgg_seglen(A, chr, loc, R->len);
         if (sl > A.max_insert || sl < A.min_insert) { __syncwarp(); return 0; }
     }
     const uint32_t cnt = chain ? R->nc[w] : R->nh[w];
-    if ((int)w < S.best) S.best = (int)w;            // lowest level that holds a hit
+    if ((int)w < R->best) WSET(R->best, (int)w);       // lowest level that holds a hit
     if (lane == 0) {
         if (store_all) hits[((size_t)w * 2 + chain) * (A.W + 1) + cnt] = make_uint2(chr, loc);
-        else if ((int)w == S.best) hits[(size_t)chain * (A.W + 1) + cnt] = make_uint2(chr, loc);
+        else if ((int)w == R->best) hits[(size_t)chain * (A.W + 1) + cnt] = make_uint2(chr, loc);
         if (chain) R->nc[w] = (uint16_t)(cnt + 1); else R->nh[w] = (uint16_t)(cnt + 1);
     }
     __syncwarp();
     CTR_ADD(C, CT_COMMIT, 1);
     const int tot = (int)R->nh[w] + (int)R->nc[w];
     if ((int)w == mode && !A.pairend && A.r == 0 && tot > 1) return 1;
-    if (tot >= A.W) { if (w == 0) return 1; S.thres = w - 1; }
+    if (tot >= A.W) { if (w == 0) return 1; WSET(R->thres, w - 1); }
     return 0;
 }
 
@@ -431,9 +444,9 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint3
 // gather), phase 2 (whole window, exact CountMismatch) and the ordered commit.  Everything a survivor
 // needs is re-derived here from its table index, so the filter loop carries no state for it.
 // Returns 1 when SnpAlign must return; `last` = exiting lane.
-__device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS &S, uint2 *hits, uint32_t *dd,
-                                                 int store_all, int chain, int mode, bool pass, uint32_t idx0, uint32_t md,
-                                                 uint32_t p, uint32_t tbl, int lane, Ctr *C, int &last) {
+__device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd,
+                                              int store_all, int chain, int mode, bool pass, uint32_t idx0, uint32_t md,
+                                              uint32_t p, uint32_t tbl, int lane, Ctr *C) {
     const uint32_t *anchor = A.seqinfo;
     uint32_t strand = 0, loc = anchor[0], chr = 0;
     if (pass) {
@@ -446,26 +459,25 @@ __device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS
     uint32_t w = 0xffffu;
     CTR_ADD(C, CT_GATHER, __popc(__ballot_sync(BSX_FULL, pass)));
     if (pass) {
-        w = partial_mismatch(R, chain, S.nw, refbase, loc, tbl);
-        pass = w <= S.thres;
+        w = partial_mismatch(R, chain, R->nw, refbase, loc, tbl);
+        pass = w <= R->thres;
     }
     const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
     unsigned pm = 0;
     if (pm1) {
         if (pass) {
-            w = full_mismatch(R, chain, S.nw, refbase, loc, S.thres);
-            pass = w <= S.thres;
+            w = full_mismatch(R, chain, R->nw, refbase, loc, R->thres);
+            pass = w <= R->thres;
         }
         pm = __ballot_sync(BSX_FULL, pass);
         CTR_ADD(C, CT_FULL, __popc(pm1));
     }
-    int ret = 0;
-    last = 31;
+    int ret = 0, last = 31;
     while (pm) {
         const int src = __ffs(pm) - 1;
         pm &= pm - 1;
         const uint32_t w_s = __shfl_sync(BSX_FULL, w, src);
-        if (w_s > S.thres) continue;                                     // threshold lowered by an earlier commit
+        if (w_s > R->thres) continue;                                     // threshold lowered by an earlier commit
         uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
         const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
         uint32_t chr_s;
@@ -479,11 +491,11 @@ __device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS
             chr_s = __shfl_sync(BSX_FULL, chr, src);
             loc_s -= anchor[chr_s >> 1];
         }
-        ret = commit_hit(A, R, S, hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
+        ret = commit_hit(A, R,  hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
                          A.rrbs && chain == 0 && !A.pairend, lane, C);
         if (ret) { last = src; break; }
     }
-    return ret;
+    return ret | (last << 8);        // bit 0: SnpAlign returns; bits 8..: exiting lane
 }
 
 // SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
@@ -491,10 +503,10 @@ __device__ __forceinline__ int extend_and_commit(const MapArgs &A, ReadSm *R, RS
 // rc entries, sub-seed 1's, ...), 64 table entries per step (two per lane).  Everything that depends on
 // the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
 // work is one 8-byte load, two masked XOR/popcount words and a compare.
-__device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
+__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
     const int per = A.rrbs ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
-        if (chain == 0 ? !S.fc : !S.cc) continue;
+        if (chain == 0 ? !R->fc : !R->cc) continue;
         const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
         uint32_t tbl = 0; bool have_tbl = false;
         uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
@@ -520,7 +532,7 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
                 ra = __funnelshift_l(r1, r0, sh); ma = __funnelshift_l(m1, m0, sh);
             } else {
                 const int sg = (int)(e.w >> 16);
-                want = chain ? (uint32_t)(S.len / A.s - 1 - sg) : (uint32_t)sg;      // RRBS segment tag
+                want = chain ? (uint32_t)(R->len / A.s - 1 - sg) : (uint32_t)sg;      // RRBS segment tag
             }
             for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
                 const uint32_t i0 = c0 + lane, i1 = i0 + 32;
@@ -533,8 +545,8 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
                     uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0);
                     if (i0 < e.z) cx0 = __ldg(A.ctx + i0);
                     if (i1 < e.z) cx1 = __ldg(A.ctx + i1);
-                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= S.thres;
-                    if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= S.thres;
+                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= R->thres;
+                    if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= R->thres;
                     const uint32_t left = e.z - c0;
                     vm0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
                     vm1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
@@ -563,20 +575,19 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
 #pragma unroll
                     for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
                     zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                    tbl = chunk_table(R, chain, S.nw, zlo, zhi, lane);
+                    tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
                     have_tbl = true;
                 }
-                int last = 31;
-                if (pm0) {
-                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass0, c0, e.y, p, tbl, lane, C, last);
-                    if (ret) { counted += __popc(vm0 & ((2u << last) - 1u)); break; }
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {                            // one call site: the slow path exists once in the binary
+                    const unsigned pmh = h ? pm1 : pm0, vmh = h ? vm1 : vm0;
+                    if (pmh) {
+                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, lane, C);
+                        if (rc & 1) { ret = 1; counted += __popc(vmh & ((2u << (rc >> 8)) - 1u)); break; }
+                    }
+                    counted += __popc(vmh);
                 }
-                counted += __popc(vm0);
-                if (pm1) {
-                    ret = extend_and_commit(A, R, S, hits, dd, store_all, chain, mode, pass1, c0 + 32, e.y, p, tbl, lane, C, last);
-                    if (ret) { counted += __popc(vm1 & ((2u << last) - 1u)); break; }
-                }
-                counted += __popc(vm1);
+                if (ret) break;
             }
         }
         // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
@@ -592,17 +603,20 @@ __device__ int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, RS &S, uint2 *hi
 }
 
 // everything RunAlign does before the mode loop (align.cpp:435-444)
-__device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, int lane, Ctr *C, uint32_t *dbg) {
-    R->seedseg = min((S.len - A.I + 1) / A.s, S.rmsn + 1);
-    if (R->seedseg < 0) R->seedseg = 0;
-    S.thres = (uint32_t)S.rmsn;
-    S.nw = (S.len + 15) >> 4;
-    S.dn = 0; S.best = 99;
+__device__ BSX_FN void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int lane, Ctr *C, uint32_t *dbg) {
+    {
+        int seg = min((R->len - A.I + 1) / A.s, R->rmsn + 1);
+        if (seg < 0) seg = 0;
+        const int rmsn = R->rmsn, nw = (R->len + 15) >> 4;
+        __syncwarp();
+        if (lane == 0) { R->seedseg = seg; R->thres = (uint32_t)rmsn; R->nw = nw; R->dn = 0; R->best = 99; }
+        __syncwarp();
+    }
     if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
     __syncwarp();
     for (int chain = 0; chain < 2; chain++) {
-        if (chain == 0 ? !S.fc : !S.cc) continue;
-        select_seeds(A, K, R, X, S, chain, lane, C);
+        if (chain == 0 ? !R->fc : !R->cc) continue;
+        select_seeds(A, K, R, X,  chain, lane, C);
         if (dbg && lane == 0) {
             dbg[chain * 20 + 0] = (uint32_t)R->seedseg;
             for (int n = 0; n < R->seedseg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)X->arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)X->sidx[n][1]; }
@@ -612,24 +626,24 @@ __device__ void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm 
 }
 
 // SingleAlign::RunAlign (align.cpp:435-452)
-__device__ void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, RS &S, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint32_t *dbg) {
-    prepare_read(A, K, R, X, S, lane, C, dbg);
+__device__ BSX_FN void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint32_t *dbg) {
+    prepare_read(A, K, R, X,  lane, C, dbg);
     for (int m = 0; m < R->seedseg; m++) {
-        snp_align(A, R, X, S, hits, dd, store_all, m, lane, C);
-        if (!A.rrbs && S.best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
+        snp_align(A, R, X,  hits, dd, store_all, m, lane, C);
+        if (!A.rrbs && R->best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
     }
 }
 
 // StringAlign (align.cpp:610-627) -> record
-__device__ void write_record(const MapArgs &A, const ReadSm *R, const RS &S, const uint2 *hits, int store_all,
+__device__ void write_record(const MapArgs &A, const ReadSm *R, const uint2 *hits, int store_all,
                              bsx_rec *out, uint16_t *cnt, int lane) {
-    if (cnt && lane < 16) cnt[lane] = (!R->filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
+    if (cnt && lane < 16) cnt[lane] = (!R->filtered && lane <= R->rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
     if (lane != 0) return;
     bsx_rec o;
-    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)R->filtered; o.len = (uint8_t)S.len;
+    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)R->filtered; o.len = (uint8_t)R->len;
     if (!R->filtered) {
-        const int ii = S.best <= S.rmsn ? S.best : S.rmsn + 1;     // lowest non-empty bucket
-        const int sum = ii <= S.rmsn ? R->nh[ii] + R->nc[ii] : 0;
+        const int ii = R->best <= R->rmsn ? R->best : R->rmsn + 1;     // lowest non-empty bucket
+        const int sum = ii <= R->rmsn ? R->nh[ii] + R->nc[ii] : 0;
         o.nm = (uint8_t)ii;
         if (sum > 0) {
             const int j = (int)(bsx_myrand(R->index, A.randseed) % (uint32_t)sum);
@@ -649,6 +663,7 @@ __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr *C, int lan
     __syncwarp();
 }
 
+#ifdef BSX_BUILD_SE
 // ------------------------------------------------------------------ SE kernel
 __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_SE_MIN_CTAS)
 bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
@@ -675,22 +690,26 @@ bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
             r_end = min(r + (uint32_t)BSX_READ_BLOCK, A.n);
         }
         if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
-        RS S;
-        S.rmsn = 0; R->seedseg = 0; S.nw = 0; S.thres = 0; S.fc = S.cc = 0; S.dn = 0; S.best = 99;
-        load_read(A, R, S, A.seq_a, A.len_a, r, A.readset, lane);
-        R->filtered = filter_read(A, R, S, lane);
+        __syncwarp();
+        if (lane == 0) { R->rmsn = 0; R->seedseg = 0; R->nw = 0; R->thres = 0; R->fc = R->cc = 0; R->dn = 0; R->best = 99; }
+        __syncwarp();
+        load_read(A, R,  A.seq_a, A.len_a, r, A.readset, lane);
+        WSET(R->filtered, filter_read(A, R, lane));
         uint32_t *dbg = A.debug ? A.debug + (size_t)r * 40 : nullptr;
-        if (!R->filtered) run_align(A, K, R, X, S, hits, dd, 0, lane, C, dbg);
+        if (!R->filtered) run_align(A, K, R, X,  hits, dd, 0, lane, C, dbg);
         else if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
         __syncwarp();
-        write_record(A, R, S, hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
-        if (!R->filtered && S.best <= S.rmsn) CTR_ADD(C, CT_MAPPED, 1);
+        write_record(A, R,  hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
+        if (!R->filtered && R->best <= R->rmsn) CTR_ADD(C, CT_MAPPED, 1);
         __syncwarp();
         r++;
     }
     flush_counters(A, C, lane);
 }
 
+#endif  // BSX_BUILD_SE
+
+#ifdef BSX_BUILD_PE
 // ------------------------------------------------------------------ PE kernel (pairs.cpp)
 // pair buckets: pairhits[na+nb][..] as uint4 {a.chr, a.loc, b.chr, b.loc}; insert / chain / na / nb
 // in a parallel uint4.  One warp per pair; GetPairs runs on lane 0 (its loops are short and strictly
@@ -717,9 +736,9 @@ __device__ void sort_hits(uint2 *h, int n, int lane) {
 }
 
 // GetPairs (pairs.cpp:34-135), lane 0 only
-__device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb, const RS &Sa, const RS &Sb,
+__device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb,
                          const uint2 *ha_all, const uint2 *hb_all, PairHitDev *pairs, uint16_t *npairs, int na, int nb) {
-    if (na > Sa.rmsn || nb > Sb.rmsn) return 0;
+    if (na > Ra->rmsn || nb > Rb->rmsn) return 0;
     const size_t W1 = (size_t)A.W + 1;
     uint16_t &cnt = npairs[na + nb];
     PairHitDev *bucket = pairs + (size_t)(na + nb) * W1;
@@ -740,8 +759,8 @@ __device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb, c
                 const uint2 y = hb[j];
                 const bool a_first = dir ? ((chra & 1u) != 0) : ((chra & 1u) == 0);
                 uint32_t seg_start, seg_end;
-                if (!a_first) { seg_start = y.y; seg_end = x.y + (uint32_t)Sa.len; }
-                else { seg_start = x.y; seg_end = y.y + (uint32_t)Sb.len; }
+                if (!a_first) { seg_start = y.y; seg_end = x.y + (uint32_t)Ra->len; }
+                else { seg_start = x.y; seg_end = y.y + (uint32_t)Rb->len; }
                 const int ins = (int)(seg_end - seg_start);
                 if (ins >= A.min_insert && ins <= A.max_insert) {
                     PairHitDev ph;
@@ -757,21 +776,21 @@ __device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb, c
 }
 
 // the selection half of StringAlignUnpair (pairs.cpp:244-286) for one mate -> record
-__device__ void write_unpaired(const MapArgs &A, const ReadSm *R, const RS &S, const uint2 *hits, bsx_rec *out, uint16_t *cnt, int lane) {
-    if (cnt && lane < 16) cnt[lane] = (!R->filtered && lane <= S.rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
+__device__ void write_unpaired(const MapArgs &A, const ReadSm *R, const uint2 *hits, bsx_rec *out, uint16_t *cnt, int lane) {
+    if (cnt && lane < 16) cnt[lane] = (!R->filtered && lane <= R->rmsn) ? (uint16_t)(R->nh[lane] + R->nc[lane]) : (uint16_t)0;
     if (lane != 0) return;
     bsx_rec o;
-    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)R->filtered; o.len = (uint8_t)S.len;
+    o.loc = 0; o.chr = 0; o.nhits = 0; o.nm = 0; o.chain = 0; o.status = (uint8_t)R->filtered; o.len = (uint8_t)R->len;
     if (!R->filtered) {
         int na, ma = 0, ra = 0;
-        for (na = 0; na <= S.rmsn; na++) if ((ma = R->nh[na] + R->nc[na]) > 0) break;
+        for (na = 0; na <= R->rmsn; na++) if ((ma = R->nh[na] + R->nc[na]) > 0) break;
         uint2 h = make_uint2(0, 0);
         if (ma) {
             if (ma > 1) ra = (int)(bsx_myrand(R->index, A.randseed) % (uint32_t)ma);
             const int nh = R->nh[na];
             h = (ra < nh) ? hits[((size_t)na * 2) * (A.W + 1) + ra] : hits[((size_t)na * 2 + 1) * (A.W + 1) + (ra - nh)];
         }
-        na %= (S.rmsn + 1);
+        na %= (R->rmsn + 1);
         o.chr = h.x; o.loc = h.y; o.nhits = (uint32_t)ma; o.nm = (uint8_t)na;
         o.chain = (uint8_t)(ra >= (int)R->nh[na]);
     }
@@ -779,15 +798,15 @@ __device__ void write_unpaired(const MapArgs &A, const ReadSm *R, const RS &S, c
 }
 
 // Fix_Unpaired_Short_Fragment (align.cpp:768-791), lane 0
-__device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, const RS &S, uint2 *hits) {
-    if (S.len >= A.min_insert) return;
+__device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, uint2 *hits) {
+    if (R->len >= A.min_insert) return;
     const size_t W1 = (size_t)A.W + 1;
-    for (int ii = 0; ii <= S.rmsn; ii++) {
+    for (int ii = 0; ii <= R->rmsn; ii++) {
         for (int pass = 0; pass < 2; pass++) {
             uint2 *h = hits + ((size_t)ii * 2 + pass) * W1;
             int cnt = pass ? R->nc[ii] : R->nh[ii];
             for (int j = 0; j < cnt; j++) {
-                const int sl = ccgg_seglen(A, h[j].x, h[j].y, S.len);
+                const int sl = ccgg_seglen(A, h[j].x, h[j].y, R->len);
                 if (sl < A.min_insert || sl > A.max_insert) { cnt--; for (int k = j; k < cnt; k++) h[k] = h[k + 1]; j--; }
             }
             if (pass) R->nc[ii] = (uint16_t)cnt; else R->nh[ii] = (uint16_t)cnt;
@@ -823,13 +842,16 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
         r = __shfl_sync(BSX_FULL, r, 0);
         if (r >= A.n) break;
         if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
-        RS Sa, Sb;
-        Sa.rmsn = Sb.rmsn = 0; Ra->seedseg = Rb->seedseg = 0; Sa.dn = Sb.dn = 0; Sa.best = Sb.best = 99;
-        Sa.nw = Sb.nw = 0; Sa.thres = Sb.thres = 0; Sa.fc = Sa.cc = Sb.fc = Sb.cc = 0;
-        load_read(A, Ra, Sa, A.seq_a, A.len_a, r, 1, lane);
-        load_read(A, Rb, Sb, A.seq_b, A.len_b, r, 2, lane);
-        Ra->filtered = filter_read(A, Ra, Sa, lane);
-        Rb->filtered = filter_read(A, Rb, Sb, lane);
+        __syncwarp();
+        if (lane == 0) {
+            Ra->rmsn = Rb->rmsn = 0; Ra->seedseg = Rb->seedseg = 0; Ra->dn = Rb->dn = 0; Ra->best = Rb->best = 99;
+            Ra->nw = Rb->nw = 0; Ra->thres = Rb->thres = 0; Ra->fc = Ra->cc = Rb->fc = Rb->cc = 0;
+        }
+        __syncwarp();
+        load_read(A, Ra,  A.seq_a, A.len_a, r, 1, lane);
+        load_read(A, Rb,  A.seq_b, A.len_b, r, 2, lane);
+        WSET(Ra->filtered, filter_read(A, Ra, lane));
+        WSET(Rb->filtered, filter_read(A, Rb, lane));
         if (lane < 16) { Ra->nh[lane] = Ra->nc[lane] = 0; Rb->nh[lane] = Rb->nc[lane] = 0; }
         __syncwarp();
         int paired = 0;
@@ -837,22 +859,22 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
         po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
         if (!Ra->filtered && !Rb->filtered) {
             // PairAlign::RunAlign (pairs.cpp:137-190)
-            prepare_read(A, K, Ra, X, Sa, lane, C, nullptr);
-            prepare_read(A, K, Rb, X, Sb, lane, C, nullptr);
+            prepare_read(A, K, Ra, X,  lane, C, nullptr);
+            prepare_read(A, K, Rb, X,  lane, C, nullptr);
             if (lane < 31) npairs[lane] = 0;
             __syncwarp();
-            const int maxi = max(Sa.rmsn, Sb.rmsn);
+            const int maxi = max(Ra->rmsn, Rb->rmsn);
             for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Ra->seedseg) snp_align(A, Ra, X, Sa, hits_a, dd_a, 1, i, lane, C);
-                if (i < Rb->seedseg) snp_align(A, Rb, X, Sb, hits_b, dd_b, 1, i, lane, C);
-                if (i <= Sa.rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
-                if (i <= Sb.rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
+                if (i < Ra->seedseg) snp_align(A, Ra, X,  hits_a, dd_a, 1, i, lane, C);
+                if (i < Rb->seedseg) snp_align(A, Rb, X,  hits_b, dd_b, 1, i, lane, C);
+                if (i <= Ra->rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
+                if (i <= Rb->rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
                 __syncwarp();
                 int n = 0;
                 if (lane == 0) {
-                    n = get_pairs(A, Ra, Rb, Sa, Sb, hits_a, hits_b, pairs, npairs, i, i);
-                    for (int j = 0; j < i; j++) { n += get_pairs(A, Ra, Rb, Sa, Sb, hits_a, hits_b, pairs, npairs, i, j);
-                                                  n += get_pairs(A, Ra, Rb, Sa, Sb, hits_a, hits_b, pairs, npairs, j, i); }
+                    n = get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, i, i);
+                    for (int j = 0; j < i; j++) { n += get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, i, j);
+                                                  n += get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, j, i); }
                 }
                 n = __shfl_sync(BSX_FULL, n, 0);
                 if (n > 0) paired = i + 1;
@@ -876,40 +898,36 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                 }
             }
         } else {
-            if (!Ra->filtered) run_align(A, K, Ra, X, Sa, hits_a, dd_a, 1, lane, C, nullptr);
-            if (!Rb->filtered) run_align(A, K, Rb, X, Sb, hits_b, dd_b, 1, lane, C, nullptr);
+            if (!Ra->filtered) run_align(A, K, Ra, X,  hits_a, dd_a, 1, lane, C, nullptr);
+            if (!Rb->filtered) run_align(A, K, Rb, X,  hits_b, dd_b, 1, lane, C, nullptr);
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
         if (!out_paired && A.rrbs) {
-            if (lane == 0) { if (!Ra->filtered) fix_unpaired_short(A, Ra, Sa, hits_a); if (!Rb->filtered) fix_unpaired_short(A, Rb, Sb, hits_b); }
+            if (lane == 0) { if (!Ra->filtered) fix_unpaired_short(A, Ra,  hits_a); if (!Rb->filtered) fix_unpaired_short(A, Rb,  hits_b); }
             __syncwarp();
         }
         if (lane == 0) A.out_pair[r] = po;
-        write_unpaired(A, Ra, Sa, hits_a, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
-        write_unpaired(A, Rb, Sb, hits_b, A.out_b + r, A.cnt_b ? A.cnt_b + (size_t)r * 16 : nullptr, lane);
+        write_unpaired(A, Ra,  hits_a, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
+        write_unpaired(A, Rb,  hits_b, A.out_b + r, A.cnt_b ? A.cnt_b + (size_t)r * 16 : nullptr, lane);
         if (out_paired) CTR_ADD(C, CT_MAPPED, 1);
         __syncwarp();
     }
     flush_counters(A, C, lane);
 }
 
+#endif  // BSX_BUILD_PE
+
 }  // namespace
 
-// resident CTAs per SM for the persistent grid (0 when the kernel cannot launch with `smem`)
-int bsx_map_occupancy(int pe, size_t smem) {
+// resident CTAs per SM for the persistent grid (0 when the kernel cannot launch with `smem`), and the launchers
+#ifdef BSX_BUILD_SE
+int bsx_map_occupancy_se(size_t smem) {
     int occ = 0;
-    cudaError_t e;
-    if (pe) {
-        e = cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_pe_kernel, BSX_WARPS_PER_CTA * 32, smem);
-    } else {
-        e = cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_se_kernel, BSX_WARPS_PER_CTA * 32, smem);
-    }
+    cudaError_t e = cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_se_kernel, BSX_WARPS_PER_CTA * 32, smem);
     if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
     return occ;
 }
-
 int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st) {
     const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap);
     static size_t configured = 0;
@@ -921,7 +939,16 @@ int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st) {
     BSX_CUDA_CHECK(cudaGetLastError());
     return BSX_OK;
 }
+#endif
 
+#ifdef BSX_BUILD_PE
+int bsx_map_occupancy_pe(size_t smem) {
+    int occ = 0;
+    cudaError_t e = cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_pe_kernel, BSX_WARPS_PER_CTA * 32, smem);
+    if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
+    return occ;
+}
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
     const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap);
     static size_t configured = 0;
@@ -933,3 +960,4 @@ int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
     BSX_CUDA_CHECK(cudaGetLastError());
     return BSX_OK;
 }
+#endif
