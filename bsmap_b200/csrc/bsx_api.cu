@@ -273,7 +273,10 @@ struct bsx_mapper {
     MapArgs base{};
 };
 
-int bsx_map_occupancy_se(size_t smem);   // bsx_map_se.cu
+int bsx_map_occupancy_se_wgbs(size_t smem);   // bsx_map_se.cu
+int bsx_map_occupancy_se_rrbs(size_t smem);   // bsx_map_se_rrbs.cu
+int bsx_launch_map_se_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
+int bsx_launch_map_se_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_map_occupancy_pe(size_t smem);   // bsx_map_pe.cu
 
 static void slot_free(bsx_slot &s) {
@@ -337,7 +340,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     m->plan_cap = maxseg * (p->rrbs ? 1 : p->index_interval);
     int sms = 0;
     BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    int occ_se = bsx_map_occupancy_se(bsx_cta_smem_bytes(1, m->plan_cap));
+    int occ_se = (p->rrbs ? bsx_map_occupancy_se_rrbs(bsx_cta_smem_bytes(1, m->plan_cap)) : bsx_map_occupancy_se_wgbs(bsx_cta_smem_bytes(1, m->plan_cap)));
     int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap));
     if (occ_se < 1 || occ_pe < 1) { delete m; bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
@@ -408,7 +411,8 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;
-    return pe ? bsx_launch_map_pe(a, m->n_ctas_pe, st) : bsx_launch_map_se(a, m->n_ctas_se, st);
+    if (pe) return bsx_launch_map_pe(a, m->n_ctas_pe, st);
+    return a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st);
 }
 
 static int download_slot(bsx_mapper *m, int si, uint32_t n, bool pe, bsx_pair_rec *op, bsx_rec *oa, bsx_rec *ob,

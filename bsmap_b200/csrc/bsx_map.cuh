@@ -83,5 +83,4 @@ static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap) {
     return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap) * BSX_WARPS_PER_CTA;
 }
 
-int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st);

@@ -34,6 +34,15 @@
 #ifndef BSX_READ_BLOCK
 #define BSX_READ_BLOCK 4        // consecutive reads a warp takes per work-counter atomic
 #endif
+// RRBS mode (-D) as a compile-time constant where a translation unit fixes it (dead code leaves the binary)
+#ifndef BSX_RRBS
+#define BSX_RRBS(A) ((A).rrbs)
+#endif
+#ifndef BSX_SE_KERNEL
+#define BSX_SE_KERNEL bsx_map_se_kernel
+#define BSX_SE_OCC bsx_map_occupancy_se
+#define BSX_SE_LAUNCH bsx_launch_map_se
+#endif
 #ifndef BSX_CALLS
 #define BSX_CALLS 1             // 1: big device functions are real calls (small binary), 0: everything inlined
 #endif
@@ -66,7 +75,7 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
 __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
     for (int t = threadIdx.x; t < 256; t += blockDim.x) K->profA[t] = (uint8_t)bsx_profile_a(A.s, A.I, t >> 4, t & 15);
     for (int t = threadIdx.x; t < 160; t += blockDim.x) { K->segof[t] = (uint8_t)(t / A.s); K->remof[t] = (uint8_t)(t % A.s); }
-    const int per = A.rrbs ? 1 : A.I;
+    const int per = BSX_RRBS(A) ? 1 : A.I;
     for (int t = threadIdx.x; t < 256; t += blockDim.x) { K->divI[t] = (uint8_t)(t / per); K->modI[t] = (uint8_t)(t % per); }
     __syncthreads();
 }
@@ -91,7 +100,7 @@ __device__ BSX_FN void trim_adapter(const MapArgs &A, ReadSm *R, int lane) {
     WSET(R->raw, R->len);
     const int len = R->len, s = A.s;
     const uint8_t *sq = R->ascii;
-    const int tail = A.rrbs ? 5 : 4;
+    const int tail = BSX_RRBS(A) ? 5 : 4;
     for (int a = 0; a < A.n_adapter; a++) {
         const int al = A.adapter_len[a];
         for (int pos0 = s; pos0 < len - tail; pos0 += 32) {
@@ -103,7 +112,7 @@ __device__ BSX_FN void trim_adapter(const MapArgs &A, ReadSm *R, int lane) {
                     m0 += (A.adapter[a][k] != (char)sq[pos + k]);
                     if (m0 > 4) break;
                 }
-                if (!A.rrbs) ok = (k >= m0 * 5 && k > 3);
+                if (!BSX_RRBS(A)) ok = (k >= m0 * 5 && k > 3);
                 else if (k >= m0 * 5) {
                     // digestion-site remnant just before the adapter (align.cpp:383-404)
                     const int sl = A.site_len, dp = A.digest_pos;
@@ -214,15 +223,15 @@ __device__ __forceinline__ uint32_t list_size(const SelSm *X, int p, int rrbs) {
 
 __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int chain, int lane, Ctr *C) {
     const int s = A.s, I = A.I, len = R->len, seg = R->seedseg;
-    const int mo = (A.rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
-    const int cso = (A.rrbs && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
+    const int mo = (BSX_RRBS(A) || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
+    const int cso = (BSX_RRBS(A) && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
     const int lim = I - 1 + mo;
     // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset]
     //    (profile.a - i lies in [n*s, n*s+I-1]); its list header is read ONCE, coalesced across lanes
     int np = 0;
     for (int p = lane; p + s <= len; p += 32) {
         bool nd;
-        if (!A.rrbs) {
+        if (!BSX_RRBS(A)) {
             const int n = K->segof[p], r = K->remof[p];
             nd = false;
 #pragma unroll
@@ -243,7 +252,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     CTR_ADD(C, CT_PROBE, np);
     __syncwarp();
     // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset, in parallel
-    if (!A.rrbs) {
+    if (!BSX_RRBS(A)) {
         for (int idx = lane; idx < seg * 16; idx += 32) {
             const int n = idx >> 4, o = idx & 15;
             if (o <= mo) {
@@ -256,7 +265,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     }
     // 3. ReorderSeed (align.cpp:454-468): global offset = FIRST minimum of GetTotalSeedLoc over [0, max_offset)
     int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
-    if (!A.rrbs && mo > 0) {
+    if (!BSX_RRBS(A) && mo > 0) {
         unsigned long long best = ~0ull;
         if (lane < mo) {
             uint32_t tt = 0;
@@ -271,7 +280,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     if (lane == 0) {
         // AdjustSeedStartArray (align.cpp:506-528)
         for (int n = 0; n < seg; n++) X->arr[n] = og;
-        if (!A.rrbs) {
+        if (!BSX_RRBS(A)) {
             for (int i = 0; i < seg; i++) {
                 const int ptr = (i & 1) == 0 ? i / 2 : seg - 1 - i / 2;
                 uint32_t total = 0xffffffffu;
@@ -289,21 +298,21 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     __syncwarp();
     // seedindex: (sum of list sizes, segment) ascending (align.cpp:474-485): rank sort, one segment per lane
     if (lane < seg) {
-        const int mine = (int)(A.rrbs ? list_size(X, lane * s + cso, 1) : X->T[lane * 16 + X->arr[lane]]);
+        const int mine = (int)(BSX_RRBS(A) ? list_size(X, lane * s + cso, 1) : X->T[lane * 16 + X->arr[lane]]);
         int rank = 0;
         for (int m = 0; m < seg; m++) {
-            const int other = (int)(A.rrbs ? list_size(X, m * s + cso, 1) : X->T[m * 16 + X->arr[m]]);
+            const int other = (int)(BSX_RRBS(A) ? list_size(X, m * s + cso, 1) : X->T[m * 16 + X->arr[m]]);
             rank += (other < mine) || (other == mine && m < lane);
         }
         X->sidx[rank][0] = mine; X->sidx[rank][1] = lane;
     }
     __syncwarp();
     // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
-    const int per = A.rrbs ? 1 : I;
+    const int per = BSX_RRBS(A) ? 1 : I;
     for (int t = lane; t < seg * per; t += 32) {
         const int m = K->divI[t], k = K->modI[t];
         const int sg = X->sidx[m][1];
-        const int p = A.rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + X->arr[sg] - k);
+        const int p = BSX_RRBS(A) ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + X->arr[sg] - k);
         plan[t] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
     }
     __syncwarp();
@@ -452,7 +461,7 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
     if (pass) {
         const uint32_t idx = idx0 + lane;
         const uint32_t entry = __ldg(A.pos + idx);
-        if (!A.rrbs) { strand = idx >= md; loc = entry - p; }           // h = -profile.a + i - seed_start_array
+        if (!BSX_RRBS(A)) { strand = idx >= md; loc = entry - p; }           // h = -profile.a + i - seed_start_array
         else { chr = __ldg(A.tag + idx) & 0xffffu; strand = chr & 1u; loc = entry - p + anchor[chr >> 1]; }
     }
     const uint32_t *refbase = strand ? A.crefcat : A.refcat;
@@ -481,7 +490,7 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
         uint32_t loc_s = __shfl_sync(BSX_FULL, loc, src);
         const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
         uint32_t chr_s;
-        if (!A.rrbs) {
+        if (!BSX_RRBS(A)) {
             // RefSeq::int2hit (dbseq.cpp:585-595)
             int left = 0, right = (int)A.n_seq;
             while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
@@ -492,7 +501,7 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
             loc_s -= anchor[chr_s >> 1];
         }
         ret = commit_hit(A, R,  hits, dd, store_all, chain, chr_s, loc_s, w_s, mode,
-                         A.rrbs && chain == 0 && !A.pairend, lane, C);
+                         BSX_RRBS(A) && chain == 0 && !A.pairend, lane, C);
         if (ret) { last = src; break; }
     }
     return ret | (last << 8);        // bit 0: SnpAlign returns; bits 8..: exiting lane
@@ -504,7 +513,7 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
 // the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
 // work is one 8-byte load, two masked XOR/popcount words and a compare.
 __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
-    const int per = A.rrbs ? 1 : A.I;
+    const int per = BSX_RRBS(A) ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
         const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
@@ -516,7 +525,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
             const uint32_t p = e.w & 0xffffu;
             uint32_t rb = 0, mb = 0, ra = 0, ma = 0, want = 0;
-            if (!A.rrbs) {
+            if (!BSX_RRBS(A)) {
                 // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
                 const int xb = (int)p - 16, xa = (int)p + A.s;
                 if (xb >= 0) {
@@ -538,7 +547,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
                 const uint32_t i0 = c0 + lane, i1 = i0 + 32;
                 bool pass0 = false, pass1 = false;
                 unsigned vm0, vm1;
-                if (!A.rrbs) {
+                if (!BSX_RRBS(A)) {
                     // phase 0: mismatches among the <= 32 read bases that face the entry's inline context (8 bytes
                     // that arrive with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres`
                     // rejects exactly like the reference; pos[] and the reference are only touched by survivors.
@@ -595,7 +604,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
         if (lane == 0) {
             C[CT_LIST] += visited;
             C[CT_CAND] += counted;
-            if (ret) C[CT_OVER] += (A.rrbs ? 0u : visited - counted);
+            if (ret) C[CT_OVER] += (BSX_RRBS(A) ? 0u : visited - counted);
         }
         if (ret) return 1;
     }
@@ -630,7 +639,7 @@ __device__ BSX_FN void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, Se
     prepare_read(A, K, R, X,  lane, C, dbg);
     for (int m = 0; m < R->seedseg; m++) {
         snp_align(A, R, X,  hits, dd, store_all, m, lane, C);
-        if (!A.rrbs && R->best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
+        if (!BSX_RRBS(A) && R->best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
     }
 }
 
@@ -666,7 +675,7 @@ __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr *C, int lan
 #ifdef BSX_BUILD_SE
 // ------------------------------------------------------------------ SE kernel
 __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_SE_MIN_CTAS)
-bsx_map_se_kernel(const __grid_constant__ MapArgs A) {
+BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t per_warp = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4) + sizeof(SelSm);
@@ -902,7 +911,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             if (!Rb->filtered) run_align(A, K, Rb, X,  hits_b, dd_b, 1, lane, C, nullptr);
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
-        if (!out_paired && A.rrbs) {
+        if (!out_paired && BSX_RRBS(A)) {
             if (lane == 0) { if (!Ra->filtered) fix_unpaired_short(A, Ra,  hits_a); if (!Rb->filtered) fix_unpaired_short(A, Rb,  hits_b); }
             __syncwarp();
         }
@@ -921,21 +930,21 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
 
 // resident CTAs per SM for the persistent grid (0 when the kernel cannot launch with `smem`), and the launchers
 #ifdef BSX_BUILD_SE
-int bsx_map_occupancy_se(size_t smem) {
+int BSX_SE_OCC(size_t smem) {
     int occ = 0;
-    cudaError_t e = cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_se_kernel, BSX_WARPS_PER_CTA * 32, smem);
+    cudaError_t e = cudaFuncSetAttribute(BSX_SE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, BSX_SE_KERNEL, BSX_WARPS_PER_CTA * 32, smem);
     if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
     return occ;
 }
-int bsx_launch_map_se(const MapArgs &a, int n_ctas, cudaStream_t st) {
+int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
     const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap);
     static size_t configured = 0;
     if (smem > configured) {
-        BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BSX_CUDA_CHECK(cudaFuncSetAttribute(BSX_SE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    bsx_map_se_kernel<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
+    BSX_SE_KERNEL<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
     BSX_CUDA_CHECK(cudaGetLastError());
     return BSX_OK;
 }
