@@ -73,9 +73,12 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
 
 // per-CTA tables: seed profile and p -> (segment, remainder), so per-read code never divides
 __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
+    #pragma unroll 1
     for (int t = threadIdx.x; t < 256; t += blockDim.x) K->profA[t] = (uint8_t)bsx_profile_a(A.s, A.I, t >> 4, t & 15);
+    #pragma unroll 1
     for (int t = threadIdx.x; t < 160; t += blockDim.x) { K->segof[t] = (uint8_t)(t / A.s); K->remof[t] = (uint8_t)(t % A.s); }
     const int per = BSX_RRBS(A) ? 1 : A.I;
+    #pragma unroll 1
     for (int t = threadIdx.x; t < 256; t += blockDim.x) { K->divI[t] = (uint8_t)(t / per); K->modI[t] = (uint8_t)(t % per); }
     __syncthreads();
 }
@@ -88,6 +91,7 @@ __device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, const uin
     if (len > BSX_MAX_READLEN) len = BSX_MAX_READLEN;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(seqs + (size_t)r * A.stride);
     uint32_t *dst = reinterpret_cast<uint32_t *>(R->ascii);
+    #pragma unroll 1
     for (int t = lane; t < 40; t += 32) dst[t] = (t * 4 < (int)A.stride) ? __ldg(src + t) : 0u;
     __syncwarp();
     __syncwarp();
@@ -101,13 +105,16 @@ __device__ BSX_FN void trim_adapter(const MapArgs &A, ReadSm *R, int lane) {
     const int len = R->len, s = A.s;
     const uint8_t *sq = R->ascii;
     const int tail = BSX_RRBS(A) ? 5 : 4;
+    #pragma unroll 1
     for (int a = 0; a < A.n_adapter; a++) {
         const int al = A.adapter_len[a];
+        #pragma unroll 1
         for (int pos0 = s; pos0 < len - tail; pos0 += 32) {
             const int pos = pos0 + lane;
             bool ok = false;
             if (pos < len - tail) {
                 int m0 = 0, k = 0;
+                #pragma unroll 1
                 for (; k < al && k < 15 && pos + k < len; k++) {
                     m0 += (A.adapter[a][k] != (char)sq[pos + k]);
                     if (m0 > 4) break;
@@ -117,6 +124,7 @@ __device__ BSX_FN void trim_adapter(const MapArgs &A, ReadSm *R, int lane) {
                     // digestion-site remnant just before the adapter (align.cpp:383-404)
                     const int sl = A.site_len, dp = A.digest_pos;
                     int m = m0, m2 = m0;
+                    #pragma unroll 1
                     for (int t = 0; t < sl - dp; t++) {
                         char x = A.digest_site[t], y = (char)sq[pos - sl + dp + t];
                         m += (x != y) && (x != 'C' || y != 'T');
@@ -229,6 +237,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset]
     //    (profile.a - i lies in [n*s, n*s+I-1]); its list header is read ONCE, coalesced across lanes
     int np = 0;
+    #pragma unroll 1
     for (int p = lane; p + s <= len; p += 32) {
         bool nd;
         if (!BSX_RRBS(A)) {
@@ -253,10 +262,12 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     __syncwarp();
     // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset, in parallel
     if (!BSX_RRBS(A)) {
+        #pragma unroll 1
         for (int idx = lane; idx < seg * 16; idx += 32) {
             const int n = idx >> 4, o = idx & 15;
             if (o <= mo) {
                 uint32_t tt = 0;
+                #pragma unroll 1
                 for (int k = 0; k < I; k++) tt += list_size(X, (int)K->profA[n * 16 + k] + o - k, 0);
                 X->T[idx] = tt;
             }
@@ -269,6 +280,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
         unsigned long long best = ~0ull;
         if (lane < mo) {
             uint32_t tt = 0;
+            #pragma unroll 1
             for (int n = 0; n < seg; n++) tt += X->T[n * 16 + lane];
             best = ((unsigned long long)tt << 8) | (unsigned)lane;
         }
@@ -279,14 +291,17 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     uint4 *plan = plan_of(R, chain, A.plan_cap);
     if (lane == 0) {
         // AdjustSeedStartArray (align.cpp:506-528)
+        #pragma unroll 1
         for (int n = 0; n < seg; n++) X->arr[n] = og;
         if (!BSX_RRBS(A)) {
+            #pragma unroll 1
             for (int i = 0; i < seg; i++) {
                 const int ptr = (i & 1) == 0 ? i / 2 : seg - 1 - i / 2;
                 uint32_t total = 0xffffffffu;
                 const int start = (ptr == 0) ? 0 : X->arr[ptr - 1];
                 const int end = (ptr == seg - 1) ? mo : X->arr[ptr + 1];
                 int bi = start;
+                #pragma unroll 1
                 for (int ii = start; ii <= end; ii++) {
                     const uint32_t tt = X->T[ptr * 16 + ii];
                     if (tt < total) { total = tt; bi = ii; }
@@ -300,6 +315,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     if (lane < seg) {
         const int mine = (int)(BSX_RRBS(A) ? list_size(X, lane * s + cso, 1) : X->T[lane * 16 + X->arr[lane]]);
         int rank = 0;
+        #pragma unroll 1
         for (int m = 0; m < seg; m++) {
             const int other = (int)(BSX_RRBS(A) ? list_size(X, m * s + cso, 1) : X->T[m * 16 + X->arr[m]]);
             rank += (other < mine) || (other == mine && m < lane);
@@ -309,6 +325,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     __syncwarp();
     // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
     const int per = BSX_RRBS(A) ? 1 : I;
+    #pragma unroll 1
     for (int t = lane; t < seg * per; t += 32) {
         const int m = K->divI[t], k = K->modI[t];
         const int sg = X->sidx[m][1];
@@ -382,6 +399,7 @@ __device__ __forceinline__ uint32_t full_mismatch(const ReadSm *R, int chain, in
     const uint32_t *rp = refbase + (loc >> 4);
     const uint32_t sh2 = (loc & 15u) * 2u;
     uint32_t w = 0, prev = __ldg(rp);
+    #pragma unroll 1
     for (int j = 0; j < nw; j++) {
         const uint32_t next = __ldg(rp + j + 1);
         w += __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(next, prev, sh2)));
@@ -423,6 +441,7 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd
     const uint32_t key = anchor[k] + loc;                               // == (chr>>1, loc), see DESIGN.md
     bool found = false;
     const uint32_t dn = R->dn;
+    #pragma unroll 1
     for (uint32_t t = lane; t < dn; t += 32) found |= (dd[t] == key);
     if (__any_sync(BSX_FULL, found)) return 0;                          // hit already exists
     if (dn < A.dd_stride) {                                              // capacity guard (RRBS fragment-filtered hits are uncounted)
@@ -520,6 +539,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
         uint32_t tbl = 0; bool have_tbl = false;
         uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
         int ret = 0;
+        #pragma unroll 1
         for (int i = 0; i < per && !ret; i++) {
             const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
@@ -543,6 +563,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
                 const int sg = (int)(e.w >> 16);
                 want = chain ? (uint32_t)(R->len / A.s - 1 - sg) : (uint32_t)sg;      // RRBS segment tag
             }
+            #pragma unroll 1
             for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
                 const uint32_t i0 = c0 + lane, i1 = i0 + 32;
                 bool pass0 = false, pass1 = false;
@@ -637,6 +658,7 @@ __device__ BSX_FN void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R,
 // SingleAlign::RunAlign (align.cpp:435-452)
 __device__ BSX_FN void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint32_t *dbg) {
     prepare_read(A, K, R, X,  lane, C, dbg);
+    #pragma unroll 1
     for (int m = 0; m < R->seedseg; m++) {
         snp_align(A, R, X,  hits, dd, store_all, m, lane, C);
         if (!BSX_RRBS(A) && R->best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
@@ -733,7 +755,9 @@ __device__ void sort_hits(uint2 *h, int n, int lane) {
     bool dirty = true;
     while (dirty) {
         bool sw = false;
+        #pragma unroll 1
         for (int phase = 0; phase < 2; phase++) {
+            #pragma unroll 1
             for (int i = phase + 2 * lane; i + 1 < n; i += 64) {
                 const uint2 a = h[i], b = h[i + 1];
                 if (a.x > b.x || (a.x == b.x && a.y > b.y)) { h[i] = b; h[i + 1] = a; sw = true; }
@@ -757,6 +781,7 @@ __device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb,
         const int cnt_a = dir ? Ra->nc[na] : Ra->nh[na];
         const int cnt_b = dir ? Rb->nh[nb] : Rb->nc[nb];
         uint32_t chra = 0xffffffffu; int bstart = 0, bend = 0;
+        #pragma unroll 1
         for (int i = 0; i < cnt_a; i++) {
             const uint2 x = ha[i];
             if (chra != x.x) {
@@ -764,6 +789,7 @@ __device__ int get_pairs(const MapArgs &A, const ReadSm *Ra, const ReadSm *Rb,
                 for (bstart = bend; bstart < cnt_b; bstart++) if (hb[bstart].x >= chra) break;
                 for (bend = bstart; bend < cnt_b; bend++) if (hb[bend].x > chra) break;
             }
+            #pragma unroll 1
             for (int j = bstart; j < bend; j++) {
                 const uint2 y = hb[j];
                 const bool a_first = dir ? ((chra & 1u) != 0) : ((chra & 1u) == 0);
@@ -810,10 +836,12 @@ __device__ void write_unpaired(const MapArgs &A, const ReadSm *R, const uint2 *h
 __device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, uint2 *hits) {
     if (R->len >= A.min_insert) return;
     const size_t W1 = (size_t)A.W + 1;
+    #pragma unroll 1
     for (int ii = 0; ii <= R->rmsn; ii++) {
         for (int pass = 0; pass < 2; pass++) {
             uint2 *h = hits + ((size_t)ii * 2 + pass) * W1;
             int cnt = pass ? R->nc[ii] : R->nh[ii];
+            #pragma unroll 1
             for (int j = 0; j < cnt; j++) {
                 const int sl = ccgg_seglen(A, h[j].x, h[j].y, R->len);
                 if (sl < A.min_insert || sl > A.max_insert) { cnt--; for (int k = j; k < cnt; k++) h[k] = h[k + 1]; j--; }
@@ -873,6 +901,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             if (lane < 31) npairs[lane] = 0;
             __syncwarp();
             const int maxi = max(Ra->rmsn, Rb->rmsn);
+            #pragma unroll 1
             for (int i = 0; i <= maxi && !paired; i++) {
                 if (i < Ra->seedseg) snp_align(A, Ra, X,  hits_a, dd_a, 1, i, lane, C);
                 if (i < Rb->seedseg) snp_align(A, Rb, X,  hits_b, dd_b, 1, i, lane, C);
@@ -891,6 +920,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             __syncwarp();
             if (paired && lane == 0) {
                 // StringAlignPair (pairs.cpp:222-242)
+                #pragma unroll 1
                 for (int i = 0; i <= A.v * 2; i++) {
                     const int np = npairs[i];
                     if (!np) continue;
