@@ -64,8 +64,6 @@ struct SelSm {
     int arr[16];                      // seed_start_array
     int sidx[16][2];                  // seedindex (sum, segment)
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
-    uint32_t cum[20];                 // SnpAlign: prefix of the I list lengths of the current mode
-    uint4 flank[16];                  // per sub-seed list: read bases / mask before (x,y) and after (z,w) the seed
     uint32_t ctr[8];                  // work counters of this warp (bsx_stats order), flushed to global rarely
 };
 

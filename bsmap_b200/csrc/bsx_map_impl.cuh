@@ -55,7 +55,7 @@
 #define BSX_PIPE 1              // software-pipeline the inline-context loads one step ahead
 #endif
 #ifndef BSX_SE_MIN_CTAS
-#define BSX_SE_MIN_CTAS 4
+#define BSX_SE_MIN_CTAS 6
 #endif
 
 namespace {

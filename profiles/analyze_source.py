@@ -6,7 +6,7 @@ rep, reads = sys.argv[1], float(sys.argv[2]); top = int(sys.argv[3]) if len(sys.
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = open(os.path.join(root, "bsmap_b200/csrc/bsx_map.cu")).read().splitlines()
+src = open(os.path.join(root, "bsmap_b200/csrc/bsx_map_impl.cuh")).read().splitlines()
 funcs, cur = [], "?"
 for l in src:
     m = re.match(r'^(?:__device__|__global__).*?\b(\w+)\s*\(', l)
@@ -21,7 +21,7 @@ for r in rows:
         try: s = int(r[4]); inst = int(r[7])
         except ValueError: continue
         ln = int(r[0])
-        key = funcs[ln - 1] if curf == 'bsx_map.cu' and ln <= len(funcs) else curf
+        key = funcs[ln - 1] if curf == 'bsx_map_impl.cuh' and ln <= len(funcs) else curf
         a = agg.setdefault(key, [0, 0]); a[0] += s; a[1] += inst; tot += inst
         lines.append((inst, s, curf, ln, r[1].strip()[:90]))
 ts = sum(a[0] for a in agg.values())
