@@ -263,7 +263,7 @@ struct bsx_mapper {
     const bsx_index *ix = nullptr;
     bsx_params par{};
     uint32_t max_batch = 0, stride = 0;
-    int n_ctas_se = 0, n_ctas_pe = 0, plan_cap = 0;
+    int n_ctas_se = 0, n_ctas_pe = 0, plan_cap = 0, nslot = 1;
     uint32_t hit_stride = 0, dd_stride = 0, pair_stride = 0;
     bool pe_ready = false;
     bsx_slot slot[2];
@@ -338,10 +338,11 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     int maxseg = std::min((readlen - p->index_interval + 1) / p->seed_size, p->max_snp_num + 1);
     if (maxseg < 1) maxseg = 1;
     m->plan_cap = maxseg * (p->rrbs ? 1 : p->index_interval);
+    m->nslot = p->chains ? 2 : 1;
     int sms = 0;
     BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    int occ_se = (p->rrbs ? bsx_map_occupancy_se_rrbs(bsx_cta_smem_bytes(1, m->plan_cap)) : bsx_map_occupancy_se_wgbs(bsx_cta_smem_bytes(1, m->plan_cap)));
-    int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap));
+    int occ_se = (p->rrbs ? bsx_map_occupancy_se_rrbs(bsx_cta_smem_bytes(1, m->plan_cap, m->nslot)) : bsx_map_occupancy_se_wgbs(bsx_cta_smem_bytes(1, m->plan_cap, m->nslot)));
+    int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap, m->nslot));
     if (occ_se < 1 || occ_pe < 1) { delete m; bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
     const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;
@@ -375,7 +376,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     a.randseed = p->randseed; a.max_ns = p->max_ns; a.max_readlen = p->max_readlen; a.n_adapter = p->n_adapter;
     a.site_len = (int)strnlen(p->digest_site, sizeof p->digest_site); a.digest_pos = p->digest_pos;
     a.seed_bits = (p->seed_size == 16) ? 0xffffffffu : ((1u << (2 * p->seed_size)) - 1);
-    a.plan_cap = m->plan_cap;
+    a.plan_cap = m->plan_cap; a.nslot = m->nslot;
     for (int i = 0; i < p->n_adapter; i++) { a.adapter_len[i] = (int)strnlen(p->adapter[i], 63); memcpy(a.adapter[i], p->adapter[i], 64); }
     memcpy(a.digest_site, p->digest_site, sizeof a.digest_site);
     a.stride = stride; a.stats = m->d_stats; a.debug = m->d_debug;

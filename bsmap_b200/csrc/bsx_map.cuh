@@ -17,6 +17,7 @@ struct MapArgs {
     int n_adapter, site_len, digest_pos;
     uint32_t seed_bits;
     int plan_cap;                 // plan entries per chain = max segments * I
+    int nslot;                    // chains a read can use at once: 2 with -n 1, else 1 (plan storage per read)
     int adapter_len[BSX_MAX_ADAPTERS];
     char adapter[BSX_MAX_ADAPTERS][64];
     char digest_site[32];
@@ -54,7 +55,8 @@ struct ReadSm {
     int best;                         // lowest mismatch level that holds a hit
     uint32_t pad_[3];
     uint8_t ascii[160];
-    // followed by uint4 plan[2][plan_cap]: {list start, rc start, list end, read offset of the seed}
+    // followed by uint4 plan[nslot][plan_cap]: {list start, rc start, list end, read offset | segment << 16}
+    // and uint4 flank[nslot][plan_cap]: read bases / mask facing the inline context before (x,y) and after (z,w) the seed
 };
 
 // transient per-warp scratch used while choosing seeds
@@ -74,11 +76,14 @@ struct CtaSm {
     uint8_t divI[256], modI[256];     // t / per, t % per  (per = sub-seeds per segment)
 };
 
-static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap) {
-    return (size_t)reads_per_warp * (sizeof(ReadSm) + 2u * (size_t)plan_cap * sizeof(uint4)) + sizeof(SelSm);
+static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int nslot) {
+    return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * 2u * sizeof(uint4);
 }
-static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap) {
-    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap) * BSX_WARPS_PER_CTA;
+static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
+    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot) + sizeof(SelSm);
+}
+static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
+    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot) * BSX_WARPS_PER_CTA;
 }
 
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st);

@@ -67,8 +67,11 @@ typedef uint32_t Ctr;
 #define WSET(lhs, rhs) do { const auto v_ = (rhs); __syncwarp(); if (lane == 0) (lhs) = v_; __syncwarp(); } while (0)
 #define CTR_ADD(C, k, v) do { const uint32_t v_ = (uint32_t)(v); if (lane == 0) (C)[k] += v_; } while (0)   // v may hold warp collectives
 
-__device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, int plan_cap) {
-    return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * plan_cap;
+__device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, const MapArgs &A) {
+    return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + (A.nslot == 2 ? chain : 0) * A.plan_cap;
+}
+__device__ __forceinline__ uint4 *flank_of(ReadSm *R, int chain, const MapArgs &A) {
+    return plan_of(R, chain, A) + A.nslot * A.plan_cap;
 }
 
 // per-CTA tables: seed profile and p -> (segment, remainder), so per-read code never divides
@@ -288,7 +291,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
         for (int d = 16; d; d >>= 1) { unsigned long long o2 = __shfl_xor_sync(BSX_FULL, best, d); best = o2 < best ? o2 : best; }
         og = (int)(best & 0xff);
     }
-    uint4 *plan = plan_of(R, chain, A.plan_cap);
+    uint4 *plan = plan_of(R, chain, A), *flank = flank_of(R, chain, A);
     if (lane == 0) {
         // AdjustSeedStartArray (align.cpp:506-528)
         #pragma unroll 1
@@ -331,6 +334,22 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
         const int sg = X->sidx[m][1];
         const int p = BSX_RRBS(A) ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + X->arr[sg] - k);
         plan[t] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
+        if (!BSX_RRBS(A)) {
+            // read bases / valid mask facing an entry's inline context: [p-16, p) and [p+s, p+s+16)
+            const int xb = p - 16, xa = p + s;
+            uint32_t rb = 0, mb = 0;
+            if (xb >= 0) {
+                const int j = xb >> 4, sh = (xb & 15) * 2;
+                rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);      // j + 1 <= 9 because p <= 144
+                mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
+            } else if (xb > -16) {                                                   // fewer than 16 bases before the seed
+                rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
+            }
+            const int j = xa >> 4, sh = (xa & 15) * 2;
+            const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
+            const uint32_t r0 = (j < BSX_FIXWORDS) ? R->rw[chain][j] : 0u, m0 = (j < BSX_FIXWORDS) ? R->m5[chain][j] : 0u;
+            flank[t] = make_uint4(rb, mb, __funnelshift_l(r1, r0, sh), __funnelshift_l(m1, m0, sh));
+        }
     }
     __syncwarp();
 }
@@ -474,7 +493,7 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd
 // Returns 1 when SnpAlign must return; `last` = exiting lane.
 __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd,
                                               int store_all, int chain, int mode, bool pass, uint32_t idx0, uint32_t md,
-                                              uint32_t p, uint32_t tbl, int lane, Ctr *C) {
+                                              uint32_t p, uint32_t tbl, int use_p1, int lane, Ctr *C) {
     const uint32_t *anchor = A.seqinfo;
     uint32_t strand = 0, loc = anchor[0], chr = 0;
     if (pass) {
@@ -485,10 +504,12 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
     }
     const uint32_t *refbase = strand ? A.crefcat : A.refcat;
     uint32_t w = 0xffffu;
-    CTR_ADD(C, CT_GATHER, __popc(__ballot_sync(BSX_FULL, pass)));
-    if (pass) {
-        w = partial_mismatch(R, chain, R->nw, refbase, loc, tbl);
-        pass = w <= R->thres;
+    if (use_p1) {                                                        // many survivors: one 16-byte gather filters first
+        CTR_ADD(C, CT_GATHER, __popc(__ballot_sync(BSX_FULL, pass)));
+        if (pass) {
+            w = partial_mismatch(R, chain, R->nw, refbase, loc, tbl);
+            pass = w <= R->thres;
+        }
     }
     const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
     unsigned pm = 0;
@@ -535,7 +556,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
     const int per = BSX_RRBS(A) ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
-        const uint4 *plan = plan_of(R, chain, A.plan_cap) + mode * per;
+        const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per;
         uint32_t tbl = 0; bool have_tbl = false;
         uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
         int ret = 0;
@@ -546,24 +567,12 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
             const uint32_t p = e.w & 0xffffu;
             uint32_t rb = 0, mb = 0, ra = 0, ma = 0, want = 0;
             if (!BSX_RRBS(A)) {
-                // read bases / valid mask facing the entry's inline context: [p-16, p) and [p+s, p+s+16)
-                const int xb = (int)p - 16, xa = (int)p + A.s;
-                if (xb >= 0) {
-                    const int j = xb >> 4, sh = (xb & 15) * 2;
-                    rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);  // j + 1 <= 9 because p <= 144
-                    mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
-                } else if (xb > -16) {                                               // fewer than 16 bases before the seed
-                    rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
-                }
-                const int j = xa >> 4, sh = (xa & 15) * 2;
-                const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
-                const uint32_t r0 = (j < BSX_FIXWORDS) ? R->rw[chain][j] : 0u, m0 = (j < BSX_FIXWORDS) ? R->m5[chain][j] : 0u;
-                ra = __funnelshift_l(r1, r0, sh); ma = __funnelshift_l(m1, m0, sh);
+                const uint4 f = flank[i];                                // prepared with the plan (select_seeds)
+                rb = f.x; mb = f.y; ra = f.z; ma = f.w;
             } else {
                 const int sg = (int)(e.w >> 16);
-                want = chain ? (uint32_t)(R->len / A.s - 1 - sg) : (uint32_t)sg;      // RRBS segment tag
+                want = chain ? (uint32_t)(R->len / A.s - 1 - sg) : (uint32_t)sg;     // RRBS segment tag
             }
-            #pragma unroll 1
             for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
                 const uint32_t i0 = c0 + lane, i1 = i0 + 32;
                 bool pass0 = false, pass1 = false;
@@ -598,7 +607,10 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
                 const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
                 visited += min(64u, e.z - c0);
                 if ((pm0 | pm1) == 0) { counted += __popc(vm0) + __popc(vm1); continue; }
-                if (!have_tbl) {
+                // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
+                // (high -v); otherwise survivors go straight to the exact count
+                const int use_p1 = BSX_RRBS(A) || (__popc(pm0) + __popc(pm1) > 2);
+                if (use_p1 && !have_tbl) {
                     // phase-1 chunk choice: keep away from the seed zone of this mode (all sub-seeds)
                     int zlo = 1000, zhi = -1;
                     if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
@@ -612,7 +624,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
                 for (int h = 0; h < 2; h++) {                            // one call site: the slow path exists once in the binary
                     const unsigned pmh = h ? pm1 : pm0, vmh = h ? vm1 : vm0;
                     if (pmh) {
-                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, lane, C);
+                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, use_p1, lane, C);
                         if (rc & 1) { ret = 1; counted += __popc(vmh & ((2u << (rc >> 8)) - 1u)); break; }
                     }
                     counted += __popc(vmh);
@@ -700,12 +712,12 @@ __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_SE_MIN_CTAS)
 BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4) + sizeof(SelSm);
+    const size_t per_warp = bsx_read_smem_bytes(A.plan_cap, A.nslot) + sizeof(SelSm);
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
     uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
     ReadSm *R = reinterpret_cast<ReadSm *>(base);
-    SelSm *X = reinterpret_cast<SelSm *>(base + sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4));
+    SelSm *X = reinterpret_cast<SelSm *>(base + bsx_read_smem_bytes(A.plan_cap, A.nslot));
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
@@ -856,7 +868,7 @@ __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 4)
 bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t read_sm = sizeof(ReadSm) + 2u * (size_t)A.plan_cap * sizeof(uint4);
+    const size_t read_sm = bsx_read_smem_bytes(A.plan_cap, A.nslot);
     const size_t per_warp = 2 * read_sm + sizeof(SelSm);
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
@@ -968,7 +980,7 @@ int BSX_SE_OCC(size_t smem) {
     return occ;
 }
 int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap);
+    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot);
     static size_t configured = 0;
     if (smem > configured) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(BSX_SE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -989,7 +1001,7 @@ int bsx_map_occupancy_pe(size_t smem) {
     return occ;
 }
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap);
+    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot);
     static size_t configured = 0;
     if (smem > configured) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
