@@ -161,7 +161,8 @@ __device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, int lane
     for (int d = 8; d; d >>= 1) nv += __shfl_xor_sync(BSX_FULL, nv, d);
     nv = __shfl_sync(BSX_FULL, nv, 0);
     if (R->len - nv > A.max_ns) return 1;            // CountNs (align.cpp:48-55)
-    WSET(R->rmsn, (int)((unsigned)(A.v + 1) * (unsigned)(R->len - 1) / (unsigned)R->raw));
+    // read_max_snp_num = (v+1)*(len-1)/raw_readlen (align.cpp:586); equals v for an untrimmed read longer than v
+    WSET(R->rmsn, (R->len == R->raw && A.v + 1 <= R->len) ? A.v : (int)((unsigned)(A.v + 1) * (unsigned)(R->len - 1) / (unsigned)R->raw));
     return 0;
 }
 
@@ -573,24 +574,54 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
                 const int sg = (int)(e.w >> 16);
                 want = chain ? (uint32_t)(R->len / A.s - 1 - sg) : (uint32_t)sg;     // RRBS segment tag
             }
-            for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
-                const uint32_t i0 = c0 + lane, i1 = i0 + 32;
-                bool pass0 = false, pass1 = false;
-                unsigned vm0, vm1;
-                if (!BSX_RRBS(A)) {
-                    // phase 0: mismatches among the <= 32 read bases that face the entry's inline context (8 bytes
-                    // that arrive with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres`
-                    // rejects exactly like the reference; pos[] and the reference are only touched by survivors.
+            if (!BSX_RRBS(A)) {
+                // ---- WGBS: phase 0 = mismatches among the <= 32 read bases that face the entry's inline context
+                // (8 bytes that arrive with the list stream).  It is a lower bound of CountMismatch, so
+                // `> snp_thres` rejects exactly like the reference; pos[] and the reference are only touched by
+                // survivors.  Every entry of the list is a candidate, so the counters need no per-step work.
+                uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
+                for (; c0 < e.z; c0 += 64) {
+                    const uint32_t i0 = c0 + lane, i1 = i0 + 32;
+                    bool pass0 = false, pass1 = false;
                     uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0);
                     if (i0 < e.z) cx0 = __ldg(A.ctx + i0);
                     if (i1 < e.z) cx1 = __ldg(A.ctx + i1);
-                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= R->thres;
-                    if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= R->thres;
-                    const uint32_t left = e.z - c0;
-                    vm0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-                    vm1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
-                } else {
-                    // tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194, 229-236)
+                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
+                    if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
+                    if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
+                    const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+                    // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
+                    // (high -v); otherwise survivors go straight to the exact count
+                    const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
+                    if (use_p1 && !have_tbl) {
+                        // phase-1 chunk choice: keep away from the seed zone of this mode (all sub-seeds)
+                        int zlo = 1000, zhi = -1;
+                        if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
+#pragma unroll
+                        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+                        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+                        tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
+                        have_tbl = true;
+                    }
+#pragma unroll 1
+                    for (int h = 0; h < 2; h++) {                        // one call site: the slow path exists once in the binary
+                        if (h ? pm1 : pm0) {
+                            const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, use_p1, lane, C);
+                            if (rc & 1) { ret = 1; exit_pos = (c0 - e.x) + 32u * h + (uint32_t)(rc >> 8) + 1u; break; }
+                        }
+                    }
+                    if (ret) break;
+                    thres = R->thres;
+                }
+                if (!ret) { visited += e.z - e.x; counted += e.z - e.x; }
+                else { visited += min(c0 + 64u, e.z) - e.x; counted += exit_pos; }
+            } else {
+                // ---- RRBS: tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194,
+                // 229-236); survivors of the filter are the reference's candidates
+                for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
+                    const uint32_t i0 = c0 + lane, i1 = i0 + 32;
+                    bool pass0 = false, pass1 = false;
+                    unsigned vm0 = 0, vm1 = 0;
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const uint32_t idx = h ? i1 : i0;
@@ -603,33 +634,28 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
                         if (h == 0) { pass0 = valid; vm0 = __ballot_sync(BSX_FULL, valid); }
                         else { pass1 = valid; vm1 = __ballot_sync(BSX_FULL, valid); }
                     }
-                }
-                const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
-                visited += min(64u, e.z - c0);
-                if ((pm0 | pm1) == 0) { counted += __popc(vm0) + __popc(vm1); continue; }
-                // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
-                // (high -v); otherwise survivors go straight to the exact count
-                const int use_p1 = BSX_RRBS(A) || (__popc(pm0) + __popc(pm1) > 2);
-                if (use_p1 && !have_tbl) {
-                    // phase-1 chunk choice: keep away from the seed zone of this mode (all sub-seeds)
-                    int zlo = 1000, zhi = -1;
-                    if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
+                    visited += min(64u, e.z - c0);
+                    if ((vm0 | vm1) == 0) continue;
+                    if (!have_tbl) {
+                        int zlo = 1000, zhi = -1;
+                        if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
 #pragma unroll
-                    for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-                    zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                    tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
-                    have_tbl = true;
-                }
-#pragma unroll 1
-                for (int h = 0; h < 2; h++) {                            // one call site: the slow path exists once in the binary
-                    const unsigned pmh = h ? pm1 : pm0, vmh = h ? vm1 : vm0;
-                    if (pmh) {
-                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, use_p1, lane, C);
-                        if (rc & 1) { ret = 1; counted += __popc(vmh & ((2u << (rc >> 8)) - 1u)); break; }
+                        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+                        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+                        tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
+                        have_tbl = true;
                     }
-                    counted += __popc(vmh);
+#pragma unroll 1
+                    for (int h = 0; h < 2; h++) {
+                        const unsigned vmh = h ? vm1 : vm0;
+                        if (vmh) {
+                            const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, 1, lane, C);
+                            if (rc & 1) { ret = 1; counted += __popc(vmh & ((2u << (rc >> 8)) - 1u)); break; }
+                        }
+                        counted += __popc(vmh);
+                    }
+                    if (ret) break;
                 }
-                if (ret) break;
             }
         }
         // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
@@ -647,8 +673,8 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
 // everything RunAlign does before the mode loop (align.cpp:435-444)
 __device__ BSX_FN void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int lane, Ctr *C, uint32_t *dbg) {
     {
-        int seg = min((R->len - A.I + 1) / A.s, R->rmsn + 1);
-        if (seg < 0) seg = 0;
+        const int q = R->len - A.I + 1;
+        int seg = q > 0 ? min((int)K->segof[q], R->rmsn + 1) : 0;
         const int rmsn = R->rmsn, nw = (R->len + 15) >> 4;
         __syncwarp();
         if (lane == 0) { R->seedseg = seg; R->thres = (uint32_t)rmsn; R->nw = nw; R->dn = 0; R->best = 99; }
