@@ -61,7 +61,7 @@ struct ReadSm {
 
 // transient per-warp scratch used while choosing seeds
 struct SelSm {
-    uint32_t st[BSX_MAX_KEYS], md[BSX_MAX_KEYS], en[BSX_MAX_KEYS];   // list bounds per read offset
+    uint32_t st[BSX_MAX_KEYS], md[BSX_MAX_KEYS], sz[BSX_MAX_KEYS];   // per read offset: list start, rc start, list "size" (index2[key][0])
     uint32_t T[16 * 16];              // T[n][o] = CountSeeds(segment n, start offset o)
     int arr[16];                      // seed_start_array
     int sidx[16][2];                  // seedindex (sum, segment)

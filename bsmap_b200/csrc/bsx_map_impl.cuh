@@ -228,11 +228,6 @@ __device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const ReadSm *R, 
 }
 
 // ------------------------------------------------------------------ K3: probe + choose seeds
-__device__ __forceinline__ uint32_t list_size(const SelSm *X, int p, int rrbs) {
-    uint32_t n = X->en[p] - X->st[p];       // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
-    return rrbs ? n : (n ? n + 2 : 0u);
-}
-
 __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int chain, int lane, Ctr *C) {
     const int s = A.s, I = A.I, len = R->len, seg = R->seedseg;
     const int mo = (BSX_RRBS(A) || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
@@ -256,7 +251,9 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
             const uint32_t key = seed_key(A, R, chain, p);
             const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
             const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
-            X->st[p] = a.x; X->md[p] = a.y; X->en[p] = e;
+            const uint32_t n = e - a.x;
+            X->st[p] = a.x; X->md[p] = a.y;
+            X->sz[p] = BSX_RRBS(A) ? n : (n ? n + 2 : 0u);    // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
             np++;
         }
     }
@@ -272,7 +269,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
             if (o <= mo) {
                 uint32_t tt = 0;
                 #pragma unroll 1
-                for (int k = 0; k < I; k++) tt += list_size(X, (int)K->profA[n * 16 + k] + o - k, 0);
+                for (int k = 0; k < I; k++) tt += X->sz[(int)K->profA[n * 16 + k] + o - k];
                 X->T[idx] = tt;
             }
         }
@@ -280,7 +277,7 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     }
     // 3. ReorderSeed (align.cpp:454-468): global offset = FIRST minimum of GetTotalSeedLoc over [0, max_offset)
     int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
-    if (!BSX_RRBS(A) && mo > 0) {
+    if (!BSX_RRBS(A) && mo > 1) {                 // with a single candidate (max_offset == 1) the answer is 0
         unsigned long long best = ~0ull;
         if (lane < mo) {
             uint32_t tt = 0;
@@ -316,16 +313,22 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     }
     __syncwarp();
     // seedindex: (sum of list sizes, segment) ascending (align.cpp:474-485): rank sort, one segment per lane
+    int mine = 0;
     if (lane < seg) {
-        const int mine = (int)(BSX_RRBS(A) ? list_size(X, lane * s + cso, 1) : X->T[lane * 16 + X->arr[lane]]);
-        int rank = 0;
+        mine = (int)(BSX_RRBS(A) ? X->sz[lane * s + cso] : X->T[lane * 16 + X->arr[lane]]);
+        X->sidx[lane][0] = mine;
+    }
+    __syncwarp();
+    int rank = 0;
+    if (lane < seg) {
         #pragma unroll 1
         for (int m = 0; m < seg; m++) {
-            const int other = (int)(BSX_RRBS(A) ? list_size(X, m * s + cso, 1) : X->T[m * 16 + X->arr[m]]);
+            const int other = X->sidx[m][0];
             rank += (other < mine) || (other == mine && m < lane);
         }
-        X->sidx[rank][0] = mine; X->sidx[rank][1] = lane;
     }
+    __syncwarp();
+    if (lane < seg) X->sidx[rank][1] = lane;
     __syncwarp();
     // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
     const int per = BSX_RRBS(A) ? 1 : I;
@@ -334,7 +337,9 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
         const int m = K->divI[t], k = K->modI[t];
         const int sg = X->sidx[m][1];
         const int p = BSX_RRBS(A) ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + X->arr[sg] - k);
-        plan[t] = make_uint4(X->st[p], X->md[p], X->en[p], (uint32_t)p | ((uint32_t)sg << 16));
+        const uint32_t st0 = X->st[p], sz0 = X->sz[p];
+        const uint32_t en0 = st0 + (BSX_RRBS(A) ? sz0 : (sz0 ? sz0 - 2u : 0u));
+        plan[t] = make_uint4(st0, X->md[p], en0, (uint32_t)p | ((uint32_t)sg << 16));
         if (!BSX_RRBS(A)) {
             // read bases / valid mask facing an entry's inline context: [p-16, p) and [p+s, p+s+16)
             const int xb = p - 16, xa = p + s;
