@@ -315,7 +315,7 @@ def main():
     kernel_s = (ms * 1e-3) / a.steps
     achieved = per_launch_bytes / kernel_s / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": peak_src, "kernel": "bsx_map_se_kernel", "algorithmic_bytes_per_read": bytes_per_read,
+            "peak_source": peak_src, "kernel": "bsx_map_se_wgbs_kernel", "algorithmic_bytes_per_read": bytes_per_read,
             "candidates_per_read": c_per_read, "headers_per_read": p_per_read,
             "overfetch_per_read": tot_over / reads_total, "full_extensions_per_read": tot_full / reads_total,
             "hbm_gathers_per_read": tot_gather / reads_total}
