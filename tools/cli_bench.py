@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""End-to-end command-line comparison on BASELINE config 1 (the reference's own CPU-runnable case):
+the unmodified reference binary (oracle/_ref/bsmap -p <cores>) vs the bsmap_b200 drop-in CLI, same FASTA /
+FASTQ files, wall clock of the whole process, outputs compared byte for byte (reference at -p 1 for order).
+
+    python tools/cli_bench.py [--reads 2000000] [--len 50] [--genome-mb 5]
+"""
+import argparse, hashlib, json, os, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bsmap_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reads", type=int, default=2_000_000)
+ap.add_argument("--len", type=int, default=50)
+ap.add_argument("--genome-mb", type=float, default=5.0)
+ap.add_argument("--opts", default="-s 16 -v 2 -I 4 -S 7")
+ap.add_argument("--skip-ref", action="store_true")
+a = ap.parse_args()
+dev = "cuda" if torch.cuda.is_available() else "cpu"
+td = tempfile.mkdtemp(prefix="bsx_cli_")
+n_chr = 5
+g = synth.make_genome(1, [int(a.genome_mb * 1e6 / n_chr)] * n_chr, device=dev)
+sim = synth.simulate_reads(g, a.reads, a.len, seed=11, subs="cfg1" if a.len <= 50 else "cfg2")
+fa, fq = os.path.join(td, "ref.fa"), os.path.join(td, "reads.fq")
+synth.write_fasta(fa, [x.cpu() for x in g])
+synth.write_fastq(fq, sim["seq"].cpu(), synth.read_names({k: v.cpu() for k, v in sim.items() if k != "seq"}))
+res = {"reads": a.reads, "read_len": a.len, "genome_mb": a.genome_mb, "opts": a.opts, "host_cores": os.cpu_count()}
+def run(exe, out, extra):
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "-a", fq, "-d", fa, "-o", out] + a.opts.split() + extra, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    return dt, hashlib.md5(open(out, "rb").read()).hexdigest()
+ours = os.path.join(ROOT, "bsmap_b200", "bsmap")
+dt, md5 = run(ours, os.path.join(td, "ours.sam"), [])
+res["ours_seconds"], res["ours_reads_per_s"], res["ours_md5"] = dt, a.reads / dt, md5
+refbin = os.path.join(ROOT, "oracle", "_ref", "bsmap")
+if os.path.exists(refbin) and not a.skip_ref:
+    p = min(os.cpu_count() or 1, 8)
+    dt, _ = run(refbin, os.path.join(td, "ref_pN.sam"), ["-p", str(p)])
+    res["reference_threads"], res["reference_seconds"], res["reference_reads_per_s"] = p, dt, a.reads / dt
+    dt1, md5r = run(refbin, os.path.join(td, "ref_p1.sam"), ["-p", "1"])
+    res["reference_p1_seconds"], res["identical_to_reference_p1"] = dt1, md5r == md5
+print(json.dumps(res))
