@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -90,6 +91,12 @@ class Index:
         lens = np.array([len(s) for s in keep], dtype=np.uint32)
         h = C.c_void_p()
         check(load().bsx_index_create_text_only(C.byref(params), len(names), strs(names), strs(keep), lens.ctypes.data, C.byref(h)))
+        return cls(params, None, None, -1, _handle=h)
+
+    @classmethod
+    def text_only_from_fasta(cls, params: Params, path: str):
+        h = C.c_void_p()
+        check(load().bsx_index_create_text_only_from_fasta(C.byref(params), os.fsencode(path), C.byref(h)))
         return cls(params, None, None, -1, _handle=h)
 
     def replicate(self, device: int) -> "Index":
@@ -250,3 +257,61 @@ class Mapper:
             self.close()
         except Exception:
             pass
+
+
+class Reads:
+    """One FASTA / FASTQ read file: ReadClass::CheckFile + LoadBatchReads (reads.cpp:13-119)."""
+
+    def __init__(self, path: str, zero_qual: int = ord("!"), max_readlen: int = 144):
+        h = C.c_void_p()
+        check(load().bsx_reads_open(os.fsencode(path), zero_qual, max_readlen, C.byref(h)))
+        self.h = h
+
+    @property
+    def kind(self) -> str:
+        return ("fastq", "fasta")[load().bsx_reads_kind(self.h)]
+
+    def skip(self, n_reads: int):
+        load().bsx_reads_skip(self.h, n_reads)
+
+    def force_token_reader(self, on: bool = True):
+        load().bsx_reads_force_token_reader(self.h, int(on))
+
+    def next(self, want: int, stride: int = 160, threads: int = 0):
+        """load up to `want` reads -> (n, bases[n, stride] u8 zero padded, lens[n] u16)"""
+        buf = np.empty((want, stride), dtype=np.uint8)
+        lens = np.empty(want, dtype=np.uint16)
+        n = load().bsx_reads_next(self.h, want, stride, buf.ctypes.data, lens.ctypes.data, threads)
+        return n, buf[:n], lens[:n]
+
+    def get(self, i: int):
+        """(name, bases, qualities) of read i of the current batch"""
+        ptr = [C.c_void_p() for _ in range(3)]
+        ln = [C.c_uint32() for _ in range(3)]
+        check(load().bsx_reads_get(self.h, i, C.byref(ptr[0]), C.byref(ln[0]), C.byref(ptr[1]), C.byref(ln[1]), C.byref(ptr[2]), C.byref(ln[2])))
+        return tuple(C.string_at(q.value, l.value) if l.value else b"" for q, l in zip(ptr, ln))
+
+    def close(self):
+        if getattr(self, "h", None) and _l._lib is not None:
+            _l._lib.bsx_reads_close(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def emit_se(index: Index, params: Params, reads: Reads, n: int, recs, counts, fd: int, readset=0, threads=0):
+    """format the current batch of `reads` on `threads` host threads and write it to fd -> (bytes, n_aligned)"""
+    na = C.c_uint32(0)
+    w = load().bsx_emit_se(index.h, C.byref(params), reads.h, n, readset, recs.ctypes.data, _ptr(counts), threads, fd, C.byref(na))
+    return w, na.value
+
+
+def emit_pe(index: Index, params: Params, a: Reads, b: Reads, n: int, pr, ra, rb, ca, cb, fd: int, fd_unpair: int = -1, threads=0):
+    st = (C.c_uint32 * 3)()
+    w = load().bsx_emit_pe(index.h, C.byref(params), a.h, b.h, n, pr.ctypes.data, ra.ctypes.data, rb.ctypes.data, _ptr(ca), _ptr(cb),
+                           threads, fd, fd_unpair, st)
+    return w, tuple(st)

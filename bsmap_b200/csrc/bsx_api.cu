@@ -100,34 +100,23 @@ extern "C" int bsx_index_create_text_only(const bsx_params *p, int n_seq, const 
 }
 
 // RefSeq::LoadNextSeq (dbseq.cpp:18-54): name = first token after '>', sequence = whitespace-free
-// concatenation of the following tokens up to the next '>'
+// concatenation of the following tokens up to the next '>' (bsx_load_fasta, bsx_reads.cpp)
 extern "C" int bsx_index_create_from_fasta(const bsx_params *p, const char *path, int device, bsx_index **out) {
-    FILE *f = fopen(path, "rb");
-    if (!f) { bsx_set_error("fatal error: failed to open ref file %s", path); return BSX_ERR_IO; }
     std::vector<std::string> names, seqs;
-    std::vector<char> buf(1 << 22);
-    bool in_header = false, header_name_done = false, at_line_start = true;
-    size_t got;
-    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
-        for (size_t i = 0; i < got; i++) {
-            const char c = buf[i];
-            if (in_header) {
-                if (c == '\n') { in_header = false; at_line_start = true; }
-                else if (!header_name_done) { if (c == ' ' || c == '\t' || c == '\r') { if (!names.back().empty()) header_name_done = true; } else names.back().push_back(c); }
-                continue;
-            }
-            if (c == '>' && (at_line_start || true)) { names.emplace_back(); seqs.emplace_back(); in_header = true; header_name_done = false; continue; }
-            if (c == '\n') { at_line_start = true; continue; }
-            at_line_start = false;
-            if (c == ' ' || c == '\t' || c == '\r') continue;
-            if (!seqs.empty()) seqs.back().push_back(c);
-        }
-    }
-    fclose(f);
-    if (seqs.empty()) { bsx_set_error("no sequences in %s", path); return BSX_ERR_IO; }
+    const int rc = bsx_load_fasta(path, names, seqs);
+    if (rc != BSX_OK) return rc;
     std::vector<const char *> np, sp; std::vector<uint32_t> ln;
     for (size_t k = 0; k < seqs.size(); k++) { np.push_back(names[k].c_str()); sp.push_back(seqs[k].data()); ln.push_back((uint32_t)seqs[k].size()); }
     return bsx_index_create(p, (int)seqs.size(), np.data(), sp.data(), ln.data(), device, out);
+}
+
+extern "C" int bsx_index_create_text_only_from_fasta(const bsx_params *p, const char *path, bsx_index **out) {
+    std::vector<std::string> names, seqs;
+    const int rc = bsx_load_fasta(path, names, seqs);
+    if (rc != BSX_OK) return rc;
+    std::vector<const char *> np, sp; std::vector<uint32_t> ln;
+    for (size_t k = 0; k < seqs.size(); k++) { np.push_back(names[k].c_str()); sp.push_back(seqs[k].data()); ln.push_back((uint32_t)seqs[k].size()); }
+    return bsx_index_create_text_only(p, (int)seqs.size(), np.data(), sp.data(), ln.data(), out);
 }
 
 extern "C" int bsx_index_destroy(bsx_index *ix) {
@@ -148,7 +137,11 @@ extern "C" uint32_t bsx_index_seq_size(const bsx_index *ix, uint32_t k) { return
 
 extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size_t bytes) {
     if (!ix || !dst) return BSX_ERR_ARG;
-    if (ix->device < 0) { bsx_set_error("text-only index has no device arrays"); return BSX_ERR_ARG; }
+    if (ix->device < 0) {   // text-only index: the packed Watson strand is all it has
+        if (what != 0 || bytes > ix->h_refcat.size() * 4) { bsx_set_error("text-only index has no device arrays"); return BSX_ERR_ARG; }
+        memcpy(dst, ix->h_refcat.data(), bytes);
+        return BSX_OK;
+    }
     BSX_CUDA_CHECK(cudaSetDevice(ix->device));
     const void *src = nullptr; size_t have = 0;
     switch (what) {

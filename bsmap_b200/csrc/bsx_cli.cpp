@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "bsx_internal.h"
@@ -19,58 +22,9 @@ struct Opts {
     bsx_params p;
     std::string a, b, d, o, o2;
     unsigned read_start = 1, read_end = ~0u;
-    int num_procs = 8, zero_qual = '!', qual_threshold = 0;
-    unsigned batch = 1u << 20;
+    int num_procs = 0, zero_qual = '!', qual_threshold = 0;   // -p: host threads (0 = all cores)
+    unsigned batch = 1u << 17;   // reads per GPU batch: small enough to keep the three host stages overlapped
 };
-
-// token reader with ifstream `>>` / getline semantics
-struct Reader {
-    FILE *f = nullptr; std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
-    bool open(const char *path) { f = fopen(path, "rb"); buf.resize(1 << 22); return f != nullptr; }
-    void close() { if (f) fclose(f); f = nullptr; }
-    int get() { if (pos == len) { if (eof) return -1; len = fread(buf.data(), 1, buf.size(), f); pos = 0; if (len == 0) { eof = true; return -1; } } return (unsigned char)buf[pos++]; }
-    void unget() { if (pos > 0) pos--; }
-    static bool ws(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
-    bool token(std::string &s) { s.clear(); int c; while ((c = get()) >= 0 && ws(c)) {} if (c < 0) return false; do { s.push_back((char)c); c = get(); } while (c >= 0 && !ws(c)); if (c >= 0) unget(); return true; }
-    int nonws() { int c; while ((c = get()) >= 0 && ws(c)) {} return c; }
-    void skipline() { int c; while ((c = get()) >= 0 && c != '\n') {} }
-};
-
-struct Batch {
-    std::vector<std::string> name, seq, qual;
-    void clear() { name.clear(); seq.clear(); qual.clear(); }
-};
-
-// ReadClass::LoadBatchReads (reads.cpp:83-119) for FASTA / FASTQ
-unsigned load_batch(Reader &r, int fmt, const Opts &o, unsigned &index, unsigned want, Batch &b) {
-    b.clear();
-    std::string tok;
-    while (b.name.size() < want && index < o.read_end) {
-        int c = r.nonws();
-        if (c < 0) break;
-        std::string nm, sq, ql;
-        if (!r.token(nm)) break;
-        r.skipline();
-        if (!r.token(sq)) sq.clear();
-        if (fmt == 0) { r.token(tok); r.skipline(); r.token(ql); }
-        else ql.assign(sq.size(), (char)(o.zero_qual + 40));          // zero_qual + default_qual (reads.cpp:108)
-        if ((int)sq.size() > o.p.max_readlen) { sq.erase(o.p.max_readlen); if ((int)ql.size() > o.p.max_readlen) ql.erase(o.p.max_readlen); }
-        b.name.push_back(nm); b.seq.push_back(sq); b.qual.push_back(ql);
-        index++;
-    }
-    return (unsigned)b.name.size();
-}
-
-int sniff(const char *path) {   // CheckFile (reads.cpp:13-54): 1 = FASTA, 0 = FASTQ, -1 = unsupported
-    FILE *f = fopen(path, "rb"); if (!f) return -2;
-    int c; while ((c = fgetc(f)) >= 0 && Reader::ws(c)) {}
-    fclose(f);
-    return c == '>' ? 1 : c == '@' ? 0 : -1;
-}
-
-void skip_reads(Reader &r, int fmt, unsigned n) {   // -B (reads.cpp:56-66): 4 (fq) or 2 (fa) lines per read
-    for (unsigned long long i = 0; i < (unsigned long long)n * (fmt == 0 ? 4 : 2); i++) { if (r.eof) break; r.skipline(); }
-}
 
 void usage() {
     printf("Usage:\tbsmap [options]\n"
@@ -84,7 +38,7 @@ void usage() {
            "       -B  <int>   start from the Nth read or read pair, default: 1\n"
            "       -E  <int>   end at the Nth read or read pair, default: 4,294,967,295\n"
            "       -I  <int>   index interval, default=4\n"
-           "       -p  <int>   accepted for compatibility (the GPU path ignores it)\n"
+           "       -p  <int>   number of host threads for parsing/formatting, default: all cores\n"
            "       -D  <str>   activating RRBS mapping mode and set restriction enzyme digestion sites, example: -D C-CGG\n"
            "       -S  <int>   seed for random number generation used in selecting multiple hits\n"
            "       -n  [0,1]   set mapping strand information. default: -n 0\n"
@@ -163,25 +117,34 @@ int get_options(int argc, char **argv, Opts &o) {
     return 0;
 }
 
-struct Cbuf {   // arrays of C strings for the ABI
-    std::vector<const char *> v;
-    const char *const *set(const std::vector<std::string> &s) { v.resize(s.size()); for (size_t i = 0; i < s.size(); i++) v[i] = s[i].c_str(); return v.data(); }
+// bounded hand-off between pipeline stages
+template <class T> struct Chan {
+    std::mutex m; std::condition_variable cv; std::vector<T> q; size_t cap; bool closed = false;
+    explicit Chan(size_t c) : cap(c) {}
+    void push(T &&v) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return q.size() < cap; }); q.push_back(std::move(v)); cv.notify_all(); }
+    bool pop(T &v) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return false; v = std::move(q.front()); q.erase(q.begin()); cv.notify_all(); return true; }
+    void close() { std::unique_lock<std::mutex> l(m); closed = true; cv.notify_all(); }
 };
 
-void pack(const Batch &b, unsigned stride, std::vector<char> &buf, std::vector<uint16_t> &lens) {
-    const size_t n = b.seq.size();
-    buf.assign(n * stride, 0); lens.resize(n);
-    for (size_t i = 0; i < n; i++) {
-        size_t l = b.seq[i].size(); if (l > stride) l = stride;
-        memcpy(&buf[i * stride], b.seq[i].data(), l);
-        lens[i] = (uint16_t)l;
-    }
+struct Views { std::vector<bsx_view> name, seq, qual; std::vector<std::string> store; };
+void take_views(bsx_reads *r, Views &v) { v.name.swap(r->name); v.seq.swap(r->seq); v.qual.swap(r->qual); v.store.swap(r->slow_store); }
+
+struct Job { uint32_t n = 0; int slot = 0; unsigned done_index = 0; Views a, b; };
+struct Text { std::vector<std::string> main, unpair; unsigned done_index = 0; };
+
+template <class T> T *pinned(size_t count) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, count * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { fprintf(stderr, "cudaHostAlloc of %zu bytes failed\n", count * sizeof(T)); exit(1); }
+    return (T *)p;
 }
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 }  // namespace
 
 extern "C" int bsx_cli_main(int argc, char **argv) {
     const time_t t0 = time(nullptr);
+    const double t_start = now();
     printf("\nBSMAP v2.6 (bsmap_b200: B200-native hot path)\n");
     if (argc == 1) usage();
     { time_t t = time(nullptr); printf("Start at:  %s\n", ctime(&t)); }
@@ -192,8 +155,21 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         if (o.o.compare(o.o.size() - 4, 4, ".sam") == 0) o.p.out_sam = 1;
         else if (o.o.compare(o.o.size() - 4, 4, ".bam") == 0) { fprintf(stderr, ".bam output is not supported; write .sam and convert\n"); return 1; }
     }
+    // the CUDA context comes up on its own thread while this one parses the reference FASTA
     bsx_index *ix = nullptr;
-    if (bsx_index_create_from_fasta(&o.p, o.d.c_str(), 0, &ix) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    std::thread ctx_thread([] { cudaFree(nullptr); });
+    std::vector<std::string> ref_names, ref_seqs;
+    const int lrc = bsx_load_fasta(o.d.c_str(), ref_names, ref_seqs);
+    const double t_fa = now();
+    ctx_thread.join();
+    const double t_ctx = now();
+    if (lrc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    {
+        std::vector<const char *> np, sp; std::vector<uint32_t> ln;
+        for (size_t k = 0; k < ref_seqs.size(); k++) { np.push_back(ref_names[k].c_str()); sp.push_back(ref_seqs[k].data()); ln.push_back((uint32_t)ref_seqs[k].size()); }
+        if (bsx_index_create(&o.p, (int)ref_seqs.size(), np.data(), sp.data(), ln.data(), 0, &ix) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    }
+    std::vector<std::string>().swap(ref_seqs);
     bsx_index_info info; bsx_index_get_info(ix, &info);
     unsigned long long sum_len = 0; for (uint32_t k = 0; k < info.n_seq; k++) sum_len += bsx_index_seq_size(ix, k);
     printf("Load in %u db seqs, total size %llu bp. %ld secs passed\n", info.n_seq, sum_len, (long)(time(nullptr) - t0));
@@ -214,63 +190,108 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
 
     const bool pe = !o.a.empty() && !o.b.empty();
     if (o.a.empty()) { fprintf(stderr, "missing query file(s)\n"); return 1; }
-    Reader ra, rb;
-    const int fa = sniff(o.a.c_str()), fb = pe ? sniff(o.b.c_str()) : 0;
-    if (fa == -2 || !ra.open(o.a.c_str())) { fprintf(stderr, "failed to open read file%s (check -a option): %s\n", pe ? " #1" : "", o.a.c_str()); return 1; }
-    if (pe && (fb == -2 || !rb.open(o.b.c_str()))) { fprintf(stderr, "failed to open read file #2 (check -b option): %s\n", o.b.c_str()); return 1; }
-    if (fa < 0 || fb < 0) { fprintf(stderr, "fatal error: unrecognizable format of reads file (FASTA/FASTQ only; SAM/BAM input is not supported).\n"); return 1; }
+    const bool timing = getenv("BSX_CLI_TIMING") != nullptr;
+    const double t_idx = now();
+    bsx_reads *ra = nullptr, *rb = nullptr;
+    int rc = bsx_reads_open(o.a.c_str(), o.zero_qual, p.max_readlen, &ra);
+    if (rc == BSX_ERR_IO) { fprintf(stderr, "failed to open read file%s (check -a option): %s\n", pe ? " #1" : "", o.a.c_str()); return 1; }
+    if (rc == BSX_OK && pe) {
+        rc = bsx_reads_open(o.b.c_str(), o.zero_qual, p.max_readlen, &rb);
+        if (rc == BSX_ERR_IO) { fprintf(stderr, "failed to open read file #2 (check -b option): %s\n", o.b.c_str()); return 1; }
+    }
+    if (rc != BSX_OK) { fprintf(stderr, "fatal error: unrecognizable format of reads file (FASTA/FASTQ only; SAM/BAM input is not supported).\n"); return 1; }
     if (pe) printf("Pair-end alignment(GPU)\nQuery: %s  %s  Reference: %s  Output: %s  %s\n", o.a.c_str(), o.b.c_str(), o.d.c_str(), o.o.c_str(), o.o2.c_str());
     else printf("Single read alignment(GPU)\nQuery: %s  Reference: %s  Output: %s\n", o.a.c_str(), o.d.c_str(), o.o.c_str());
     FILE *fout = fopen(o.o.c_str(), "wb");
     if (!fout) { fprintf(stderr, "failed to open output file (check -o option): %s\n", o.o.c_str()); return 1; }
     FILE *fun = nullptr;
     if (pe && !p.out_sam) { fun = fopen(o.o2.c_str(), "wb"); if (!fun) { fprintf(stderr, "failed to open output file for unpaired hits (check -2 option): %s\n", o.o2.c_str()); return 1; } }
-    std::vector<char> text, text2;
-    if (p.out_sam) { size_t n = bsx_format_header(ix, nullptr, 0); text.resize(n + 1); bsx_format_header(ix, text.data(), n + 1); fwrite(text.data(), 1, n, fout); }
+    if (p.out_sam) { std::vector<char> text; size_t n = bsx_format_header(ix, nullptr, 0); text.resize(n + 1); bsx_format_header(ix, text.data(), n + 1); fwrite(text.data(), 1, n, fout); fflush(fout); }
 
     const unsigned stride = 160;
+    const int threads = bsx_host_threads(o.num_procs);
+    if (const char *e = getenv("BSX_CLI_BATCH")) { const int v = atoi(e); if (v > 0) o.batch = (unsigned)v; }
     bsx_mapper *mp = nullptr;
     if (bsx_mapper_create(ix, &p, o.batch, stride, &mp) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
-    skip_reads(ra, fa, o.read_start - 1); if (pe) skip_reads(rb, fb, o.read_start - 1);
-    unsigned index_a = o.read_start - 1, index_b = o.read_start - 1;
-    Batch ba, bb; Cbuf ca1, ca2, ca3, cb1, cb2, cb3;
-    std::vector<char> sa, sb; std::vector<uint16_t> la, lb;
-    std::vector<bsx_rec> reca, recb; std::vector<bsx_pair_rec> recp; std::vector<uint16_t> cnta, cntb;
-    unsigned long long n_aligned = 0, n_pairs = 0, n_a = 0, n_b = 0;
-    for (;;) {
-        const unsigned first = index_a;
-        const unsigned n1 = load_batch(ra, fa, o, index_a, o.batch, ba);
-        const unsigned n2 = pe ? load_batch(rb, fb, o, index_b, o.batch, bb) : n1;
-        if (!n1 || n1 != n2) break;
-        pack(ba, stride, sa, la);
-        reca.resize(n1); cnta.resize((size_t)n1 * 16);
-        size_t need, need2 = 0;
-        if (!pe) {
-            if (bsx_map_se(mp, n1, sa.data(), la.data(), first, 0, reca.data(), cnta.data()) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
-            uint32_t na = 0;
-            need = bsx_format_se(ix, &p, n1, ca1.set(ba.name), ca2.set(ba.seq), ca3.set(ba.qual), 0, reca.data(), cnta.data(), nullptr, 0, &na);
-            text.resize(need + 1);
-            bsx_format_se(ix, &p, n1, ca1.v.data(), ca2.v.data(), ca3.v.data(), 0, reca.data(), cnta.data(), text.data(), need + 1, &na);
-            n_aligned += na;
-        } else {
-            pack(bb, stride, sb, lb);
-            recb.resize(n1); recp.resize(n1); cntb.resize((size_t)n1 * 16);
-            if (bsx_map_pe(mp, n1, sa.data(), la.data(), sb.data(), lb.data(), first, recp.data(), reca.data(), recb.data(), cnta.data(), cntb.data()) != BSX_OK) {
-                fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
-            uint32_t st[3] = {0, 0, 0};
-            need = bsx_format_pe(ix, &p, n1, ca1.set(ba.name), ca2.set(ba.seq), ca3.set(ba.qual), cb1.set(bb.name), cb2.set(bb.seq), cb3.set(bb.qual),
-                                 recp.data(), reca.data(), recb.data(), cnta.data(), cntb.data(), nullptr, 0, nullptr, 0, &need2, st);
-            text.resize(need + 1); text2.resize(need2 + 1);
-            bsx_format_pe(ix, &p, n1, ca1.v.data(), ca2.v.data(), ca3.v.data(), cb1.v.data(), cb2.v.data(), cb3.v.data(),
-                          recp.data(), reca.data(), recb.data(), cnta.data(), cntb.data(), text.data(), need + 1, text2.data(), need2 + 1, &need2, st);
-            n_pairs += st[0]; n_a += st[1]; n_b += st[2];
-        }
-        fwrite(text.data(), 1, need, fout);
-        if (fun && need2) fwrite(text2.data(), 1, need2, fun);
-        printf("%u reads finished. %ld secs passed\n", index_a - o.read_start + 1, (long)(time(nullptr) - t0));
+    bsx_reads_skip(ra, o.read_start - 1); if (pe) bsx_reads_skip(rb, o.read_start - 1);
+    unsigned index_a = o.read_start - 1;
+    // pinned staging: one upload buffer per mate (the map call returns after its copies), three result slots
+    // (slot k is read by the formatter while k+1 waits in the channel and k+2 is being mapped)
+    const int NSLOT = 3;
+    char *sa = pinned<char>((size_t)o.batch * stride), *sb = pe ? pinned<char>((size_t)o.batch * stride) : nullptr;
+    uint16_t *la = pinned<uint16_t>(o.batch), *lb = pe ? pinned<uint16_t>(o.batch) : nullptr;
+    bsx_rec *reca[NSLOT], *recb[NSLOT]; bsx_pair_rec *recp[NSLOT]; uint16_t *cnta[NSLOT], *cntb[NSLOT];
+    const bool want_counts = !p.out_sam;   // per-level hit counts are a BSP column
+    for (int k = 0; k < NSLOT; k++) {
+        reca[k] = pinned<bsx_rec>(o.batch); cnta[k] = want_counts ? pinned<uint16_t>((size_t)o.batch * 16) : nullptr;
+        recb[k] = pe ? pinned<bsx_rec>(o.batch) : nullptr; recp[k] = pe ? pinned<bsx_pair_rec>(o.batch) : nullptr;
+        cntb[k] = pe && want_counts ? pinned<uint16_t>((size_t)o.batch * 16) : nullptr;
     }
+    unsigned long long n_aligned = 0, n_pairs = 0, n_a = 0, n_b = 0;
+    double t_parse = 0, t_map = 0, t_fmt = 0, t_write = 0;
+    Chan<Job> jobs(1); Chan<Text> texts(2);
+    const double t_alloc = now();
+    std::thread formatter([&] {
+        Job j;
+        while (jobs.pop(j)) {
+            const double t = now();
+            Text tx; tx.done_index = j.done_index;
+            if (!pe) {
+                uint32_t na = 0;
+                bsx_format_se_chunks(ix, &p, j.n, j.a.name.data(), j.a.seq.data(), j.a.qual.data(), 0, reca[j.slot], cnta[j.slot], threads, tx.main, &na);
+                n_aligned += na;
+            } else {
+                uint32_t st[3] = {0, 0, 0};
+                bsx_format_pe_chunks(ix, &p, j.n, j.a.name.data(), j.a.seq.data(), j.a.qual.data(), j.b.name.data(), j.b.seq.data(), j.b.qual.data(),
+                                     recp[j.slot], reca[j.slot], recb[j.slot], cnta[j.slot], cntb[j.slot], threads, tx.main, tx.unpair, st);
+                n_pairs += st[0]; n_a += st[1]; n_b += st[2];
+            }
+            t_fmt += now() - t;
+            texts.push(std::move(tx));
+        }
+        texts.close();
+    });
+    std::thread writer([&] {
+        Text tx;
+        while (texts.pop(tx)) {
+            const double t = now();
+            for (const std::string &c : tx.main) fwrite(c.data(), 1, c.size(), fout);
+            if (fun) for (const std::string &c : tx.unpair) fwrite(c.data(), 1, c.size(), fun);
+            t_write += now() - t;
+            printf("%u reads finished. %ld secs passed\n", tx.done_index, (long)(time(nullptr) - t0));
+        }
+    });
+    int fail = 0;
+    for (unsigned k = 0;; k++) {
+        const unsigned first = index_a;
+        const unsigned want = (unsigned)std::min<unsigned long long>(o.batch, index_a < o.read_end ? (unsigned long long)o.read_end - index_a : 0);
+        if (!want) break;
+        double t = now();
+        const unsigned n1 = bsx_reads_next(ra, want, stride, sa, la, threads);
+        const unsigned n2 = pe ? bsx_reads_next(rb, want, stride, sb, lb, threads) : n1;
+        t_parse += now() - t;
+        if (!n1 || n1 != n2) break;
+        index_a += n1;
+        const int slot = (int)(k % NSLOT);
+        t = now();
+        if (!pe) rc = bsx_map_se(mp, n1, sa, la, first, 0, reca[slot], cnta[slot]);
+        else rc = bsx_map_pe(mp, n1, sa, la, sb, lb, first, recp[slot], reca[slot], recb[slot], cnta[slot], cntb[slot]);
+        t_map += now() - t;
+        if (rc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); fail = 1; break; }
+        Job j; j.n = n1; j.slot = slot; j.done_index = index_a - o.read_start + 1;
+        take_views(ra, j.a); if (pe) take_views(rb, j.b);
+        jobs.push(std::move(j));
+    }
+    const double t_loop = now();
+    jobs.close();
+    formatter.join(); writer.join();
     fclose(fout); if (fun) fclose(fun);
-    ra.close(); rb.close();
+    const double t_drain = now();
+    if (timing) fprintf(stderr, "[bsx timing] wall: reference FASTA %.3f s || CUDA context (ready at %.3f s), index %.3f s, buffers+mapper %.3f s, map loop %.3f s, drain %.3f s | stage busy time: cut %.3f s, map %.3f s, format %.3f s, write %.3f s | reads cut by line %llu, by token reader %llu | %d host threads\n",
+                        t_fa - t_start, t_ctx - t_start, t_idx - t_ctx, t_alloc - t_idx, t_loop - t_alloc, t_drain - t_loop, t_parse, t_map, t_fmt, t_write, (unsigned long long)(ra->n_fast + (rb ? rb->n_fast : 0)),
+                        (unsigned long long)(ra->n_slow + (rb ? rb->n_slow : 0)), threads);
+    bsx_reads_close(ra); bsx_reads_close(rb);
+    if (fail) return 1;
     const double tot = (double)(index_a - o.read_start + 1);
     if (pe) printf("Total number of aligned reads: \npairs:       %llu (%.2g%%)\nsingle a:    %llu (%.2g%%)\nsingle b:    %llu (%.2g%%)\n",
                    n_pairs, 100.0 * n_pairs / tot, n_a, 100.0 * n_a / tot, n_b, 100.0 * n_b / tot);
@@ -278,6 +299,8 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     printf("Done.\n");
     { time_t t = time(nullptr); printf("Finished at %s", ctime(&t)); }
     printf("Total time consumed:  %ld secs\n", (long)(time(nullptr) - t0));
+    const double t_fin = now();
     bsx_mapper_destroy(mp); bsx_index_destroy(ix);
+    if (timing) fprintf(stderr, "[bsx timing] teardown %.3f s, total in main %.3f s\n", now() - t_fin, now() - t_start);
     return 0;
 }

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <thread>
 #include <cuda_runtime.h>
 #include "../../include/bsmap_b200.h"
 
@@ -36,7 +37,55 @@ struct bsx_index {
 
 struct bsx_mapper;
 
+// ---- host ingest / emit (bsx_reads.cpp, bsx_format.cpp) ----
+struct bsx_view { const char *p; uint32_t n; };
+
+// ReadClass (reads.h:26-48) over a memory-mapped FASTA / FASTQ file
+struct bsx_reads {
+    int fd = -1;
+    const char *p = nullptr; size_t n = 0; bool mapped = false;
+    std::vector<char> owned;               // non-mappable inputs (pipes) are slurped
+    size_t pos = 0;
+    int kind = 0;                          // _file_format: 0 FASTQ, 1 FASTA
+    int zero_qual = '!', max_readlen = BSX_MAX_READLEN;
+    bool force_slow = false;
+    std::vector<bsx_view> name, seq, qual; // the current batch
+    std::vector<std::string> slow_store;   // backing store of records that took the token reader
+    std::string qual_fill;                 // FASTA reads: zero_qual + default_qual (reads.cpp:108)
+    std::vector<uint64_t> lines;
+    double rec_bytes = 0;                  // running bytes per record: sizes the next scan window
+    uint64_t n_fast = 0, n_slow = 0;
+};
+
+// run f(tid, begin, end) over [0, n) on `threads` host threads (contiguous ranges)
+template <class F> inline void bsx_parallel(int threads, size_t n, F f);
+
+// formatter cores over (pointer, length) views; text is appended to one string per contiguous chunk
+void bsx_format_se_chunks(const bsx_index *ix, const bsx_params *p, uint32_t n, const bsx_view *names, const bsx_view *seqs,
+                          const bsx_view *quals, int readset, const bsx_rec *recs, const uint16_t *counts, int threads,
+                          std::vector<std::string> &chunks, uint32_t *n_aligned);
+void bsx_format_pe_chunks(const bsx_index *ix, const bsx_params *p, uint32_t n, const bsx_view *names_a, const bsx_view *seqs_a,
+                          const bsx_view *quals_a, const bsx_view *names_b, const bsx_view *seqs_b, const bsx_view *quals_b,
+                          const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb, const uint16_t *counts_a,
+                          const uint16_t *counts_b, int threads, std::vector<std::string> &chunks,
+                          std::vector<std::string> &chunks_unpair, uint32_t *n_stats);
+int bsx_load_fasta(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs);   // bsx_reads.cpp
+int bsx_host_threads(int requested);   // 0 = BSX_THREADS env or hardware concurrency (capped at 32)
+
 int bsx_index_build_device(bsx_index *ix, const char *const *seqs);   // bsx_index.cu
 int bsx_index_alloc_device(bsx_index *ix);                            // shell: allocate device arrays
 void bsx_index_free_device(bsx_index *ix);
 void bsx_set_error(const char *fmt, ...);
+
+template <class F> inline void bsx_parallel(int threads, size_t n, F f) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    if (threads == 1) { f(0, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(threads);
+    for (int t = 0; t < threads; t++) {
+        const size_t b = n * (size_t)t / threads, e = n * (size_t)(t + 1) / threads;
+        th.emplace_back([=]() { f(t, b, e); });
+    }
+    for (auto &x : th) x.join();
+}

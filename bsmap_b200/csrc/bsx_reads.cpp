@@ -1,0 +1,344 @@
+// bsx_reads.cpp -- host ingest: ReadClass::CheckFile / LoadBatchReads (reads.cpp:13-119) for FASTA / FASTQ.
+//
+// The reference pulls reads through ifstream `>>` / getline one token at a time under a mutex.  Here the
+// file is memory-mapped and a batch is cut in two steps: one memchr pass finds the line starts, then
+// `threads` host threads validate and slice their share of records straight into the batch buffers the
+// GPU upload reads from.  A record is taken by the line cutter only when the token reader would load
+// exactly the same thing (header char in column 0, one token per line, nothing but blanks after it);
+// anything else -- blank lines, indented headers, wrapped sequences, trailing junk -- is handed to a
+// token reader that restates the reference's stream semantics, record by record, until the input is
+// regular again.  No copies are made of names / bases / qualities: the batch holds views into the map.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "bsx_internal.h"
+
+namespace {
+
+inline bool ws(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
+
+// token reader with ifstream `>>` / getline semantics over the mapped bytes
+struct Tok {
+    const char *p; size_t n, pos;
+    int get() { return pos < n ? (unsigned char)p[pos++] : -1; }
+    int nonws() { int c; while ((c = get()) >= 0 && ws(c)) {} return c; }
+    bool token(std::string &s) {
+        s.clear();
+        int c = nonws();
+        if (c < 0) return false;
+        do { s.push_back((char)c); c = get(); } while (c >= 0 && !ws(c));
+        if (c >= 0) pos--;
+        return true;
+    }
+    void skipline() { const void *q = pos < n ? memchr(p + pos, '\n', n - pos) : nullptr; pos = q ? (size_t)((const char *)q - p) + 1 : n; }
+};
+
+// one record by the reference's rules (reads.cpp:93-113); false at end of input
+bool slow_record(bsx_reads *r, std::string &nm, std::string &sq, std::string &ql) {
+    Tok t{r->p, r->n, r->pos};
+    std::string tok;
+    const int c = t.nonws();
+    if (c < 0) { r->pos = t.pos; return false; }
+    if (!t.token(nm)) { r->pos = t.pos; return false; }
+    t.skipline();
+    if (!t.token(sq)) sq.clear();
+    if (r->kind == 0) { t.token(tok); t.skipline(); if (!t.token(ql)) ql.clear(); }
+    else ql.assign(sq.size(), (char)(r->zero_qual + 40));   // zero_qual + default_qual (reads.cpp:108)
+    if ((int)sq.size() > r->max_readlen) { sq.erase(r->max_readlen); if ((int)ql.size() > r->max_readlen) ql.erase(r->max_readlen); }
+    r->pos = t.pos;
+    return true;
+}
+
+// [b, e) holds exactly one token starting in column 0, followed by blanks only
+inline bool one_token(const char *b, const char *e, uint32_t *len) {
+    if (b == e || ws((unsigned char)*b)) return false;
+    const char *q = b + 1;
+    while (q < e && !ws((unsigned char)*q)) q++;
+    *len = (uint32_t)(q - b);
+    while (q < e) { if (!ws((unsigned char)*q)) return false; q++; }
+    return true;
+}
+
+inline void put_seq(char *seqs, uint16_t *lens, uint32_t stride, size_t slot, const char *s, uint32_t l) {
+    if (!seqs) return;
+    const uint32_t m = l < stride ? l : stride;
+    char *d = seqs + slot * (size_t)stride;
+    memcpy(d, s, m);
+    memset(d + m, 0, stride - m);
+    lens[slot] = (uint16_t)m;
+}
+
+// Line starts of a window of the file, found by `threads` memchr scanners.  ln = starts of the lines
+// in [pos, wend) plus one sentinel (one past the last complete line's '\n'; n + 1 when the file's last
+// line has none), so line i is [ln[i], ln[i+1] - 1).
+void scan_lines(bsx_reads *r, size_t wend, int threads) {
+    std::vector<uint64_t> &ln = r->lines;
+    ln.clear();
+    const char *p = r->p;
+    const size_t pos = r->pos, span = wend - pos;
+    if ((size_t)threads > span / 65536 + 1) threads = (int)(span / 65536 + 1);
+    std::vector<std::vector<uint64_t>> part((size_t)threads);
+    bsx_parallel(threads, span, [&, p, pos](int t, size_t b, size_t e) {
+        std::vector<uint64_t> &v = part[t];
+        v.reserve((e - b) / 24 + 16);
+        for (size_t q = pos + b; q < pos + e;) {
+            const void *h = memchr(p + q, '\n', pos + e - q);
+            if (!h) break;
+            q = (size_t)((const char *)h - p) + 1;
+            v.push_back(q);
+        }
+    });
+    size_t tot = 2; for (auto &v : part) tot += v.size();
+    ln.reserve(tot);
+    ln.push_back(pos);
+    for (auto &v : part) ln.insert(ln.end(), v.begin(), v.end());
+    if (wend == r->n && ln.back() != r->n) ln.push_back(r->n + 1);   // last line without '\n'
+}
+
+// Cut up to `want` regular records starting at r->pos (which must be a line start); returns how many
+// were taken.  *bad = stopped in front of a record the token reader has to look at (or at the end of
+// the input); otherwise the scan window was merely short and the caller comes back for more.
+uint32_t fast_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, uint16_t *lens, size_t base, int threads, bool *bad) {
+    const int lpr = r->kind == 0 ? 4 : 2;
+    const char hdr = r->kind == 0 ? '@' : '>';
+    *bad = true;
+    if (r->pos >= r->n) return 0;
+    if (r->rec_bytes <= 0) {   // size the first window from the first record
+        size_t q = r->pos; int k = 0;
+        while (k < lpr && q < r->n) { const void *h = memchr(r->p + q, '\n', r->n - q); q = h ? (size_t)((const char *)h - r->p) + 1 : r->n; k++; }
+        r->rec_bytes = (double)(q - r->pos) + 1;
+    }
+    const double wbytes = (double)want * r->rec_bytes * 1.03 + 4096;
+    const size_t wend = wbytes >= (double)(r->n - r->pos) ? r->n : r->pos + (size_t)wbytes;
+    scan_lines(r, wend, threads);
+    std::vector<uint64_t> &ln = r->lines;
+    const bool short_window = wend < r->n && (ln.size() - 1) / lpr < want;
+    if (ln.size() - 1 > (size_t)want * lpr) ln.resize((size_t)want * lpr + 1);
+    const size_t nrec = (ln.size() - 1) / lpr;
+    if (nrec == 0) { *bad = !short_window; if (short_window) r->rec_bytes *= 2; return 0; }
+    std::atomic<size_t> first_bad(nrec);
+    const char *p = r->p;
+    const int mrl = r->max_readlen;
+    bsx_view *vn = r->name.data() + base, *vs = r->seq.data() + base, *vq = r->qual.data() + base;
+    const char *qfill = r->qual_fill.data();
+    bsx_parallel(threads, nrec, [&, p, hdr, lpr, mrl, stride, seqs, lens, base, vn, vs, vq, qfill](int, size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            if (i >= first_bad.load(std::memory_order_relaxed)) return;
+            const uint64_t *L = &ln[i * lpr];
+            const char *h0 = p + L[0], *h1 = p + L[1] - 1;          // header line without its '\n'
+            bool ok = h1 - h0 >= 2 && h0[0] == hdr && !ws((unsigned char)h0[1]);
+            uint32_t nl = 0, sl = 0, ql = 0;
+            if (ok) { const char *t = h0 + 1; while (t < h1 && !ws((unsigned char)*t)) t++; nl = (uint32_t)(t - h0 - 1); }
+            ok = ok && one_token(p + L[1], p + L[2] - 1, &sl);
+            if (ok && lpr == 4) {
+                const char *c0 = p + L[2], *c1 = p + L[3] - 1;
+                ok = c1 > c0 && !ws((unsigned char)*c0) && one_token(p + L[3], p + L[4] - 1, &ql);
+            }
+            if (!ok) { size_t cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} return; }
+            if ((int)sl > mrl) { sl = (uint32_t)mrl; if (lpr == 4 && (int)ql > mrl) ql = (uint32_t)mrl; }
+            vn[i] = bsx_view{h0 + 1, nl};
+            vs[i] = bsx_view{p + L[1], sl};
+            vq[i] = lpr == 4 ? bsx_view{p + L[3], ql} : bsx_view{qfill, sl};
+            put_seq(seqs, lens, stride, base + i, p + L[1], sl);
+        }
+    });
+    const size_t took = first_bad.load();
+    r->pos = (size_t)std::min<uint64_t>(ln[took * lpr], r->n);
+    r->n_fast += took;
+    if (took) r->rec_bytes = (double)(ln[took * lpr] - ln[0]) / (double)took;
+    *bad = took < nrec || !short_window;
+    return (uint32_t)took;
+}
+
+// after token-reader records: may the line cutter resume?  (only blanks up to the end of the line)
+bool resume_at_line_start(bsx_reads *r) {
+    size_t q = r->pos;
+    while (q < r->n && r->p[q] != '\n') { if (!ws((unsigned char)r->p[q])) return false; q++; }
+    r->pos = q < r->n ? q + 1 : r->n;
+    return true;
+}
+
+}  // namespace
+
+int bsx_host_threads(int requested) {
+    if (requested > 0) return requested > 64 ? 64 : requested;
+    if (const char *e = getenv("BSX_THREADS")) { int v = atoi(e); if (v > 0) return v > 64 ? 64 : v; }
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    return hc > 32 ? 32 : (int)hc;
+}
+
+extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, bsx_reads **out) {
+    if (!path || !out) { bsx_set_error("bsx_reads_open: bad argument"); return BSX_ERR_ARG; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { bsx_set_error("failed to open read file: %s", path); return BSX_ERR_IO; }
+    bsx_reads *r = new bsx_reads();
+    r->fd = fd; r->zero_qual = zero_qual; r->max_readlen = max_readlen;
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+        r->n = (size_t)st.st_size;
+        if (r->n) {
+            void *m = mmap(nullptr, r->n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { close(fd); delete r; bsx_set_error("mmap failed: %s", path); return BSX_ERR_IO; }
+            madvise(m, r->n, MADV_SEQUENTIAL); madvise(m, r->n, MADV_WILLNEED);
+            r->p = (const char *)m; r->mapped = true;
+        }
+    } else {   // pipe: slurp
+        char buf[1 << 16]; ssize_t g;
+        while ((g = read(fd, buf, sizeof buf)) > 0) r->owned.insert(r->owned.end(), buf, buf + g);
+        r->p = r->owned.data(); r->n = r->owned.size();
+    }
+    // CheckFile (reads.cpp:19-50): the first non-blank character decides
+    size_t q = 0; while (q < r->n && ws((unsigned char)r->p[q])) q++;
+    const int c = q < r->n ? r->p[q] : -1;
+    if (c == '>') r->kind = 1; else if (c == '@') r->kind = 0;
+    else { bsx_reads_close(r); bsx_set_error("fatal error: unrecognizable format of reads file."); return BSX_ERR_ARG; }
+    r->qual_fill.assign((size_t)std::max(max_readlen, 1), (char)(zero_qual + 40));
+    *out = r;
+    return BSX_OK;
+}
+
+extern "C" void bsx_reads_close(bsx_reads *r) {
+    if (!r) return;
+    if (r->mapped) munmap((void *)r->p, r->n);
+    if (r->fd >= 0) close(r->fd);
+    delete r;
+}
+
+extern "C" int bsx_reads_kind(const bsx_reads *r) { return r ? r->kind : -1; }
+extern "C" void bsx_reads_force_token_reader(bsx_reads *r, int on) { if (r) r->force_slow = on != 0; }
+
+extern "C" void bsx_reads_skip(bsx_reads *r, uint64_t n_reads) {
+    if (!r) return;
+    Tok t{r->p, r->n, r->pos};
+    const uint64_t nl = n_reads * (r->kind == 0 ? 4u : 2u);
+    for (uint64_t i = 0; i < nl && t.pos < t.n; i++) t.skipline();
+    r->pos = t.pos;
+}
+
+extern "C" uint32_t bsx_reads_next(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, uint16_t *lens, int threads) {
+    if (!r || want == 0) return 0;
+    threads = bsx_host_threads(threads);
+    r->name.resize(want); r->seq.resize(want); r->qual.resize(want);
+    r->slow_store.clear();
+    uint32_t got = 0;
+    bool line_start = r->pos == 0 || r->p[r->pos - 1] == '\n';
+    std::vector<size_t> slow_slots;
+    std::string nm, sq, ql;
+    while (got < want) {
+        if (!r->force_slow && !line_start) line_start = resume_at_line_start(r);
+        if (!r->force_slow && line_start) {
+            bool bad = true;
+            got += fast_batch(r, want - got, stride, seqs, lens, got, threads, &bad);
+            if (got == want) break;
+            if (!bad) continue;   // the scan window was short: cut some more
+        }
+        // the record at pos is irregular (or the input is exhausted): token reader, a few records at a time
+        uint32_t k = 0;
+        const uint32_t burst = r->force_slow ? want - got : std::min<uint32_t>(want - got, 16);
+        for (; k < burst; k++) {
+            if (!slow_record(r, nm, sq, ql)) break;
+            r->slow_store.push_back(nm); r->slow_store.push_back(sq); r->slow_store.push_back(ql);
+            slow_slots.push_back(got + k);
+            r->n_slow++;
+        }
+        got += k;
+        if (k < burst) break;   // end of input
+        line_start = false;
+    }
+    for (size_t j = 0; j < slow_slots.size(); j++) {   // strings no longer move: take the views now
+        const size_t i = slow_slots[j];
+        const std::string &a = r->slow_store[3 * j], &b = r->slow_store[3 * j + 1], &c = r->slow_store[3 * j + 2];
+        r->name[i] = bsx_view{a.data(), (uint32_t)a.size()};
+        r->seq[i] = bsx_view{b.data(), (uint32_t)b.size()};
+        r->qual[i] = bsx_view{c.data(), (uint32_t)c.size()};
+        put_seq(seqs, lens, stride, i, b.data(), (uint32_t)b.size());
+    }
+    r->name.resize(got); r->seq.resize(got); r->qual.resize(got);
+    return got;
+}
+
+extern "C" int bsx_reads_get(const bsx_reads *r, uint32_t i, const char **name, uint32_t *name_len,
+                             const char **seq, uint32_t *seq_len, const char **qual, uint32_t *qual_len) {
+    if (!r || i >= r->name.size()) { bsx_set_error("bsx_reads_get: index out of range"); return BSX_ERR_ARG; }
+    if (name) *name = r->name[i].p; if (name_len) *name_len = r->name[i].n;
+    if (seq) *seq = r->seq[i].p; if (seq_len) *seq_len = r->seq[i].n;
+    if (qual) *qual = r->qual[i].p; if (qual_len) *qual_len = r->qual[i].n;
+    return BSX_OK;
+}
+
+// Reference FASTA (RefSeq::LoadNextSeq, dbseq.cpp:18-54).  A '>' outside a header line opens a record;
+// its name is the first blank-delimited token of that line; the sequence is every non-blank byte up
+// to the next '>'.  One memchr pass finds the records, then the bodies are compacted in parallel.
+int bsx_load_fasta(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { bsx_set_error("fatal error: failed to open ref file %s", path); return BSX_ERR_IO; }
+    struct stat st;
+    const char *p = nullptr; size_t n = 0; bool mapped = false; std::vector<char> owned;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+        n = (size_t)st.st_size;
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); bsx_set_error("mmap failed: %s", path); return BSX_ERR_IO; }
+        madvise(m, n, MADV_SEQUENTIAL); madvise(m, n, MADV_WILLNEED);
+        p = (const char *)m; mapped = true;
+    } else {
+        char buf[1 << 16]; ssize_t g;
+        while ((g = read(fd, buf, sizeof buf)) > 0) owned.insert(owned.end(), buf, buf + g);
+        p = owned.data(); n = owned.size();
+    }
+    struct Body { size_t b, e; };
+    std::vector<Body> body;
+    names.clear(); seqs.clear();
+    size_t q = 0;
+    while (q < n) {
+        const void *g = memchr(p + q, '>', n - q);
+        if (!g) break;
+        const size_t gt = (size_t)((const char *)g - p);
+        if (!body.empty()) body.back().e = gt;
+        const void *nl = memchr(p + gt, '\n', n - gt);
+        const size_t he = nl ? (size_t)((const char *)nl - p) : n;
+        size_t a = gt + 1;
+        while (a < he && (p[a] == ' ' || p[a] == '\t' || p[a] == '\r')) a++;
+        size_t b = a;
+        while (b < he && !(p[b] == ' ' || p[b] == '\t' || p[b] == '\r')) b++;
+        names.emplace_back(p + a, b - a);
+        q = he < n ? he + 1 : n;
+        body.push_back(Body{q, n});
+    }
+    if (body.empty()) { if (mapped) munmap((void *)p, n); close(fd); bsx_set_error("no sequences in %s", path); return BSX_ERR_IO; }
+    // pieces of at most 4 MB: count the bases, then copy them to their final offsets
+    struct Piece { size_t seq, b, e, off, cnt; };
+    std::vector<Piece> piece;
+    const size_t PIECE = (size_t)4 << 20;
+    for (size_t k = 0; k < body.size(); k++) {
+        size_t b = body[k].b;
+        do { piece.push_back(Piece{k, b, std::min(b + PIECE, body[k].e), 0, 0}); b += PIECE; } while (b < body[k].e);
+    }
+    const int threads = bsx_host_threads(0);
+    std::atomic<size_t> next_piece(0);
+    bsx_parallel(threads, (size_t)threads, [&](int, size_t, size_t) {
+        for (size_t i; (i = next_piece.fetch_add(1)) < piece.size();) {
+            size_t c = 0;
+            for (size_t a = piece[i].b; a < piece[i].e; a++) c += !ws((unsigned char)p[a]);
+            piece[i].cnt = c;
+        }
+    });
+    seqs.resize(body.size());
+    { size_t off = 0, cur = 0; for (Piece &pc : piece) { if (pc.seq != cur) { seqs[cur].resize(off); cur = pc.seq; off = 0; } pc.off = off; off += pc.cnt; } seqs[cur].resize(off); }
+    next_piece = 0;
+    bsx_parallel(threads, (size_t)threads, [&](int, size_t, size_t) {
+        for (size_t i; (i = next_piece.fetch_add(1)) < piece.size();) {
+            char *d = &seqs[piece[i].seq][0] + piece[i].off;
+            for (size_t a = piece[i].b; a < piece[i].e; a++) { const char c = p[a]; if (!ws((unsigned char)c)) *d++ = c; }
+        }
+    });
+    if (mapped) munmap((void *)p, n);
+    close(fd);
+    return BSX_OK;
+}

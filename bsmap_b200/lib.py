@@ -50,12 +50,14 @@ PAIR_REC = np.dtype([("a_loc", "<u4"), ("a_chr", "<u4"), ("b_loc", "<u4"), ("b_c
 
 EXPORTS = [
     "bsx_last_error", "bsx_device_count", "bsx_params_default", "bsx_index_create", "bsx_index_create_from_fasta",
-    "bsx_index_create_text_only", "bsx_index_destroy", "bsx_index_get_info", "bsx_index_seq_name", "bsx_index_seq_size", "bsx_index_download",
+    "bsx_index_create_text_only", "bsx_index_create_text_only_from_fasta", "bsx_index_destroy", "bsx_index_get_info", "bsx_index_seq_name", "bsx_index_seq_size", "bsx_index_download",
     "bsx_index_device_buffers", "bsx_index_replicate", "bsx_index_meta_size", "bsx_index_meta_export",
     "bsx_index_create_shell", "bsx_mapper_create", "bsx_mapper_destroy", "bsx_map_se", "bsx_map_pe",
     "bsx_batch_upload", "bsx_batch_run_se", "bsx_batch_run_pe", "bsx_batch_download_se", "bsx_batch_download_pe",
     "bsx_mapper_sync", "bsx_mapper_stats", "bsx_mapper_launches", "bsx_format_header", "bsx_format_se",
     "bsx_format_pe", "bsx_cli_main",
+    "bsx_reads_open", "bsx_reads_close", "bsx_reads_kind", "bsx_reads_skip", "bsx_reads_force_token_reader",
+    "bsx_reads_next", "bsx_reads_get", "bsx_emit_se", "bsx_emit_pe",
 ]
 
 _lib = None
@@ -77,6 +79,7 @@ def load():
     L.bsx_index_create.argtypes = [C.POINTER(Params), i32, pp, pp, vp, i32, C.POINTER(vp)]
     L.bsx_index_create_from_fasta.argtypes = [C.POINTER(Params), C.c_char_p, i32, C.POINTER(vp)]
     L.bsx_index_create_text_only.argtypes = [C.POINTER(Params), i32, pp, pp, vp, C.POINTER(vp)]
+    L.bsx_index_create_text_only_from_fasta.argtypes = [C.POINTER(Params), C.c_char_p, C.POINTER(vp)]
     L.bsx_index_destroy.argtypes = [vp]
     L.bsx_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.bsx_index_seq_name.restype = C.c_char_p
@@ -110,6 +113,17 @@ def load():
     L.bsx_format_pe.restype = sz
     L.bsx_format_pe.argtypes = [vp, C.POINTER(Params), u32] + [pp] * 6 + [vp] * 5 + [
         C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz), C.POINTER(u32)]
+    L.bsx_reads_open.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.bsx_reads_close.argtypes = [vp]; L.bsx_reads_close.restype = None
+    L.bsx_reads_kind.argtypes = [vp]
+    L.bsx_reads_skip.argtypes = [vp, C.c_uint64]; L.bsx_reads_skip.restype = None
+    L.bsx_reads_force_token_reader.argtypes = [vp, i32]; L.bsx_reads_force_token_reader.restype = None
+    L.bsx_reads_next.argtypes = [vp, u32, u32, vp, vp, i32]; L.bsx_reads_next.restype = u32
+    L.bsx_reads_get.argtypes = [vp, u32] + [C.POINTER(vp), C.POINTER(u32)] * 3
+    L.bsx_emit_se.restype = sz
+    L.bsx_emit_se.argtypes = [vp, C.POINTER(Params), vp, u32, i32, vp, vp, i32, i32, C.POINTER(u32)]
+    L.bsx_emit_pe.restype = sz
+    L.bsx_emit_pe.argtypes = [vp, C.POINTER(Params), vp, vp, u32] + [vp] * 5 + [i32, i32, i32, C.POINTER(u32)]
     if hasattr(L, "bsx_mapper_debug_seeds"):
         L.bsx_mapper_debug_seeds.argtypes = [vp, u32, vp]
     _lib = L

@@ -104,6 +104,7 @@ typedef struct bsx_stats {
 
 typedef struct bsx_index bsx_index;     /* device-resident 2-bit reference + seed table (RefSeq) */
 typedef struct bsx_mapper bsx_mapper;   /* per-device working set: batch buffers, scratch, streams */
+typedef struct bsx_reads bsx_reads;     /* one FASTA / FASTQ read file (ReadClass, reads.h:26-48) */
 
 const char *bsx_last_error(void);
 int bsx_device_count(void);
@@ -115,6 +116,7 @@ int bsx_index_create_from_fasta(const bsx_params *p, const char *fasta_path, int
 /* host-only index for the text layer (bsx_format_*): no device arrays, cannot map */
 int bsx_index_create_text_only(const bsx_params *p, int n_seq, const char *const *names,
                                const char *const *seqs, const uint32_t *lens, bsx_index **out);
+int bsx_index_create_text_only_from_fasta(const bsx_params *p, const char *fasta_path, bsx_index **out);
 int bsx_index_destroy(bsx_index *ix);
 int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info);
 /* name/size of sequence k (RefTitle, dbseq.h:24-30) */
@@ -176,6 +178,30 @@ size_t bsx_format_pe(const bsx_index *ix, const bsx_params *p, uint32_t n,
                      const uint16_t *counts_a, const uint16_t *counts_b,
                      char *out, size_t cap, char *out_unpair, size_t cap_unpair, size_t *n_unpair,
                      uint32_t *n_stats /* pairs, single a, single b */);
+
+/* --- read files: ReadClass::CheckFile / LoadBatchReads (reads.cpp:13-119), FASTA and FASTQ ---- */
+/* The file is memory-mapped; regular 2- / 4-line records are cut on `threads` host threads, anything
+ * irregular (blank lines, indented headers, trailing tokens) goes through a token reader with the
+ * reference's ifstream `>>` / getline semantics, so both give what the reference would load.
+ * Errors: BSX_ERR_IO when the file cannot be opened, BSX_ERR_ARG for an unrecognisable format. */
+int bsx_reads_open(const char *path, int zero_qual, int max_readlen, bsx_reads **out);
+void bsx_reads_close(bsx_reads *r);
+int bsx_reads_kind(const bsx_reads *r);                       /* 0 FASTQ, 1 FASTA (_file_format) */
+void bsx_reads_skip(bsx_reads *r, uint64_t n_reads);          /* -B: 4 (fq) / 2 (fa) lines per read (reads.cpp:56-66) */
+void bsx_reads_force_token_reader(bsx_reads *r, int on);      /* tests: disable the line cutter */
+/* load up to `want` reads; bases go to seqs[i*stride ..] (zero padded) and lens[i]; returns the count.
+ * Names / bases / qualities of the batch stay addressable through bsx_reads_get until the next call. */
+uint32_t bsx_reads_next(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, uint16_t *lens, int threads);
+int bsx_reads_get(const bsx_reads *r, uint32_t i, const char **name, uint32_t *name_len,
+                  const char **seq, uint32_t *seq_len, const char **qual, uint32_t *qual_len);
+/* format the current batch of `a` (and `b`) on `threads` host threads and write it, in input order,
+ * to file descriptor fd (fd_unpair: the BSP -2 file, or -1).  Returns bytes written to fd. */
+size_t bsx_emit_se(const bsx_index *ix, const bsx_params *p, const bsx_reads *a, uint32_t n, int readset,
+                   const bsx_rec *recs, const uint16_t *counts, int threads, int fd, uint32_t *n_aligned);
+size_t bsx_emit_pe(const bsx_index *ix, const bsx_params *p, const bsx_reads *a, const bsx_reads *b, uint32_t n,
+                   const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb,
+                   const uint16_t *counts_a, const uint16_t *counts_b, int threads, int fd, int fd_unpair,
+                   uint32_t *n_stats /* pairs, single a, single b */);
 
 /* --- the bsmap command line (main.cpp:441-476): same options, same output files -------------- */
 int bsx_cli_main(int argc, char **argv);

@@ -1,0 +1,232 @@
+"""Host ingest (bsx_reads_*) and multi-threaded emit (bsx_emit_*) -- no GPU needed.
+
+The record cutter must load exactly what the reference's ifstream token reader loads
+(reads.cpp:83-119); the chunked emit must write the bytes of the unmodified reference (golden files).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+
+import cases as CS
+import runners as R
+
+import bsmap_b200 as B
+from bsmap_b200 import lib as BL
+
+pytestmark = pytest.mark.skipif(not os.path.exists(BL.LIB_PATH), reason="library not built")
+
+
+def load_all(path, want=7, threads=3, token=False, stride=64, max_readlen=144):
+    r = B.Reads(path, max_readlen=max_readlen)
+    if token:
+        r.force_token_reader()
+    out = []
+    while True:
+        n, buf, lens = r.next(want, stride=stride, threads=threads)
+        if n == 0:
+            break
+        for i in range(n):
+            name, seq, qual = r.get(i)
+            assert bytes(buf[i, :lens[i]]) == seq[:stride]
+            assert not buf[i, lens[i]:].any()
+            out.append((name, seq, qual))
+        if n < want:
+            break
+    kind = r.kind
+    r.close()
+    return kind, out
+
+
+def python_token_reader(data: bytes, fastq: bool, max_readlen=144, zero_qual=ord("!")):
+    """reads.cpp:90-113 restated with str.split semantics: `>>` = next whitespace-delimited token"""
+    pos, n, out = 0, len(data), []
+    WS = b" \t\n\r\f\v"
+
+    def skip_ws():
+        nonlocal pos
+        while pos < n and data[pos] in WS:
+            pos += 1
+
+    def token():
+        nonlocal pos
+        skip_ws()
+        s = pos
+        while pos < n and data[pos] not in WS:
+            pos += 1
+        return data[s:pos] if pos > s else None
+
+    def getline():
+        nonlocal pos
+        e = data.find(b"\n", pos)
+        pos = n if e < 0 else e + 1
+
+    while True:
+        skip_ws()
+        if pos >= n:
+            break
+        pos += 1                      # fin >> c
+        name = token()
+        if name is None:
+            break
+        getline()
+        seq = token() or b""
+        if fastq:
+            token(); getline()
+            qual = token() or b""
+        else:
+            qual = bytes([zero_qual + 40]) * len(seq)
+        if len(seq) > max_readlen:
+            seq, qual = seq[:max_readlen], qual[:max_readlen]
+        out.append((name, seq, qual))
+    return out
+
+
+REGULAR_FQ = b"".join(b"@r%d extra words\nACGTNACGT%s\n+\nIIIIIIIII%s\n" % (i, b"A" * (i % 5), b"#" * (i % 5)) for i in range(53))
+IRREGULAR = {
+    "crlf": REGULAR_FQ.replace(b"\n", b"\r\n"),
+    "no_final_newline": REGULAR_FQ[:-1],
+    "blank_lines": REGULAR_FQ.replace(b"@r7 ", b"\n\n@r7 ").replace(b"@r30 ", b"\n@r30 "),
+    "indented_header": REGULAR_FQ.replace(b"@r11 ", b"  @r11 "),
+    "space_after_at": REGULAR_FQ.replace(b"@r5 ", b"@ r5 "),
+    "trailing_blanks": REGULAR_FQ.replace(b"ACGTNACGTAA\n", b"ACGTNACGTAA  \t\n"),
+    "junk_after_seq": REGULAR_FQ.replace(b"ACGTNACGTAAA\n", b"ACGTNACGTAAA junk\n", 1),
+    "plus_with_name": REGULAR_FQ.replace(b"\n+\n", b"\n+again here\n"),
+    "truncated_record": REGULAR_FQ + b"@tail\nACGT\n",
+    "only_header": REGULAR_FQ + b"@tail",
+    "long_reads": b"".join(b"@L%d\n%s\n+\n%s\n" % (i, b"ACGT" * 50, b"I" * 200) for i in range(9)),
+}
+REGULAR_FA = b"".join(b">s%d desc\nACGTTGCA%s\n" % (i, b"C" * (i % 3)) for i in range(41))
+IRREGULAR_FA = {
+    "fa_regular": REGULAR_FA,
+    "fa_blank": REGULAR_FA.replace(b">s9 ", b"\n>s9 "),
+    "fa_wrapped": REGULAR_FA.replace(b"ACGTTGCAC\n", b"ACGT\nTGCAC\n", 2),
+    "fa_no_newline": REGULAR_FA[:-1],
+}
+
+
+@pytest.mark.parametrize("name", ["regular"] + sorted(IRREGULAR) + sorted(IRREGULAR_FA))
+def test_record_cutter_equals_token_reader(tmp_path, name):
+    data = REGULAR_FQ if name == "regular" else IRREGULAR.get(name, IRREGULAR_FA.get(name))
+    fastq = not name.startswith("fa_")
+    path = tmp_path / "reads.txt"
+    path.write_bytes(data)
+    exp = python_token_reader(data, fastq)
+    for want, threads in ((7, 3), (1000, 1), (1, 2), (16, 8)):
+        kind, fast = load_all(str(path), want=want, threads=threads)
+        assert kind == ("fastq" if fastq else "fasta")
+        assert fast == exp, (name, want, threads)
+    _, slow = load_all(str(path), token=True)
+    assert slow == exp
+
+
+def test_regular_input_takes_the_line_cutter(tmp_path):
+    """the fast path must actually be the one that runs on ordinary files"""
+    path = tmp_path / "r.fq"
+    path.write_bytes(REGULAR_FQ)
+    r = B.Reads(str(path))
+    n, buf, lens = r.next(1000, stride=32, threads=4)
+    assert n == 53 and lens[0] == 9 and bytes(buf[1, :10]) == b"ACGTNACGTA"
+    r.close()
+
+
+@pytest.mark.parametrize("empty_lines", [False, True])
+def test_growing_records_span_several_scan_windows(tmp_path, empty_lines):
+    """records that keep getting longer defeat the window estimate: the cutter must come back for more;
+    with every other sequence line empty the file is irregular throughout and the two readers interleave"""
+    path = tmp_path / "grow.fq"
+    n_rec = 60_000
+    with open(path, "wb") as f:
+        for i in range(n_rec):
+            l = 10 + i // 450
+            base = b"" if (empty_lines and i % 4 == 1) else b"ACGT"[(i & 3):(i & 3) + 1]
+            f.write(b"@g%d\n%s\n+\n%s\n" % (i, base * l, b"F" * l))
+    for want in (25_000, n_rec + 1):
+        _, fast = load_all(str(path), want=want, threads=8, stride=160)
+        _, slow = load_all(str(path), want=want, token=True, stride=160)
+        assert fast == slow
+        assert empty_lines or len(fast) == n_rec
+
+
+def test_skip_and_errors(tmp_path):
+    path = tmp_path / "r.fq"
+    path.write_bytes(REGULAR_FQ)
+    r = B.Reads(str(path))
+    r.skip(50)                                     # -B 51
+    n, _, _ = r.next(100)
+    assert n == 3 and r.get(0)[0] == b"r50"
+    with pytest.raises(B.BsxError):
+        r.get(3)
+    r.close()
+    with pytest.raises(B.BsxError, match="failed to open"):
+        B.Reads(str(tmp_path / "missing.fq"))
+    bad = tmp_path / "bad.txt"
+    bad.write_bytes(b"hello\n")
+    with pytest.raises(B.BsxError, match="unrecognizable"):
+        B.Reads(str(bad))
+
+
+def test_reference_fasta_loader(tmp_path):
+    """RefSeq::LoadNextSeq (dbseq.cpp:18-54): names = first token, sequence = all non-blank bytes"""
+    fa = tmp_path / "g.fa"
+    rng = np.random.default_rng(3)
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), size=n)) for n in (9_000_001, 17, 0, 123_457)]
+    names = ["chr%d" % k for k in range(len(seqs))]
+    with open(fa, "wb") as f:
+        for k, s in enumerate(seqs):
+            f.write(b">  chr%d some description\r\n" % k if k == 1 else b">chr%d some description\n" % k)
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + (b" \r\n" if k & 1 else b"\n"))
+    p = B.make_params()
+    got = B.Index.text_only_from_fasta(p, str(fa))
+    exp = B.Index.text_only(p, names, seqs)
+    assert got.header() == exp.header()
+    assert np.array_equal(got.download("refcat"), exp.download("refcat"))
+    with pytest.raises(B.BsxError, match="no CUDA device"):
+        B.Index.from_fasta(p, str(fa))             # the mapping index needs the GPU: no CPU fallback
+    with pytest.raises(B.BsxError, match="failed to open"):
+        B.Index.text_only_from_fasta(p, str(tmp_path / "missing.fa"))
+
+
+@pytest.mark.parametrize("case", [c for c in CS.CASES if not c.fasta_reads or not c.paired], ids=lambda c: c.name)
+@pytest.mark.parametrize("threads", [1, 5])
+def test_emit_reproduces_reference_text(tmp_path, case, threads):
+    """read files -> Reads -> oracle records -> bsx_emit_* (threads) == bytes of the unmodified reference"""
+    d = case.data()
+    got = R.oracle_run(case)
+    p = B.make_params(**case.param_kwargs())
+    ix = B.Index.text_only(p, d["gnames"], d["gseqs"])
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    L = case.opts.get("L", 144)
+    ra = B.Reads(a, max_readlen=L)
+    n = len(d["names"])
+    assert ra.next(n + 5, threads=threads)[0] == n
+    out = tmp_path / "out.txt"
+    out2 = tmp_path / "out2.txt"
+    head = ix.header() if p.out_sam else b""
+    exp_main, exp_un = R.golden_load(case)
+    fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    try:
+        if not case.paired:
+            w, na = B.emit_se(ix, p, ra, n, got["recs"].astype(BL.REC), got["counts"], fd, threads=threads)
+            assert na == got["n_aligned"]
+            un = b""
+        else:
+            rb = B.Reads(b, max_readlen=L)
+            assert rb.next(n + 5, threads=threads)[0] == n
+            fd2 = os.open(out2, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+            w, st = B.emit_pe(ix, p, ra, rb, n, got["pr"].astype(BL.PAIR_REC), got["ra"].astype(BL.REC), got["rb"].astype(BL.REC),
+                              got["ca"], got["cb"], fd, fd2, threads=threads)
+            os.close(fd2)
+            assert st == got["n_aligned"]
+            un = out2.read_bytes()
+            rb.close()
+    finally:
+        os.close(fd)
+    txt = out.read_bytes()
+    assert w == len(txt)
+    assert head + txt == exp_main, R.first_diff(head + txt, exp_main)
+    assert un == exp_un, R.first_diff(un, exp_un)
+    ra.close()
