@@ -234,44 +234,45 @@ __device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R,
     const int cso = (BSX_RRBS(A) && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
     const int lim = I - 1 + mo;
     // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset]
-    //    (profile.a - i lies in [n*s, n*s+I-1]); its list header is read ONCE, coalesced across lanes
+    //    (profile.a - i lies in [n*s, n*s+I-1]); its list header is read ONCE, coalesced across lanes.
+    //    The union of those ranges is enumerated directly: w offsets per segment, the last one takes the tail
+    //    (when the ranges overlap, w = s and the union is one interval).  idx / w by a float reciprocal (idx < 4096).
     int np = 0;
-    #pragma unroll 1
-    for (int p = lane; p + s <= len; p += 32) {
-        bool nd;
-        if (!BSX_RRBS(A)) {
-            const int n = K->segof[p], r = K->remof[p];
-            nd = false;
-#pragma unroll
-            for (int d = 0; d < 4; d++) nd |= (n - d >= 0 && n - d < seg && r + d * s <= lim);
-        } else {
-            nd = p >= cso && K->remof[p - cso] == 0 && (int)K->segof[p - cso] < seg;
-        }
-        if (nd) {
-            const uint32_t key = seed_key(A, R, chain, p);
-            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
-            const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
-            const uint32_t n = e - a.x;
-            X->st[p] = a.x; X->md[p] = a.y;
-            X->sz[p] = BSX_RRBS(A) ? n : (n ? n + 2 : 0u);    // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
-            np++;
+    {
+        const int w = min(lim + 1, s);
+        const int total = BSX_RRBS(A) ? seg : (seg > 0 ? seg * w + (lim + 1 - w) : 0);
+        const float rw = __frcp_rn((float)w);
+        #pragma unroll 1
+        for (int idx = lane; idx < total; idx += 32) {
+            int p;
+            if (BSX_RRBS(A)) p = cso + idx * s;
+            else { const int n = min((int)(((float)idx + 0.5f) * rw), seg - 1); p = n * s + (idx - n * w); }
+            if (p + s <= len) {
+                const uint32_t key = seed_key(A, R, chain, p);
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
+                const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
+                const uint32_t n = e - a.x;
+                X->st[p] = a.x; X->md[p] = a.y;
+                X->sz[p] = BSX_RRBS(A) ? n : (n ? n + 2 : 0u);    // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
+                np++;
+            }
         }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
     CTR_ADD(C, CT_PROBE, np);
     __syncwarp();
-    // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset, in parallel
+    // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset o <= max_offset, in parallel
     if (!BSX_RRBS(A)) {
+        const int mo1 = mo + 1;
+        const float rm = __frcp_rn((float)mo1);
         #pragma unroll 1
-        for (int idx = lane; idx < seg * 16; idx += 32) {
-            const int n = idx >> 4, o = idx & 15;
-            if (o <= mo) {
-                uint32_t tt = 0;
-                #pragma unroll 1
-                for (int k = 0; k < I; k++) tt += X->sz[(int)K->profA[n * 16 + k] + o - k];
-                X->T[idx] = tt;
-            }
+        for (int idx = lane; idx < seg * mo1; idx += 32) {
+            const int n = (int)(((float)idx + 0.5f) * rm), o = idx - n * mo1;
+            uint32_t tt = 0;
+            #pragma unroll 1
+            for (int k = 0; k < I; k++) tt += X->sz[(int)K->profA[n * 16 + k] + o - k];
+            X->T[n * 16 + o] = tt;
         }
         __syncwarp();
     }
@@ -742,7 +743,12 @@ __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr *C, int lan
 __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_SE_MIN_CTAS)
 BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
+#ifdef BSX_OPAQUE_LANE
+    int lane, wid;   // opaque to the optimiser: held in registers instead of re-read from %tid at every use
+    asm volatile("{ .reg .u32 t; mov.u32 t, %%tid.x; and.b32 %0, t, 31; shr.u32 %1, t, 5; }" : "=r"(lane), "=r"(wid));
+#else
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#endif
     const size_t per_warp = bsx_read_smem_bytes(A.plan_cap, A.nslot) + sizeof(SelSm);
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
