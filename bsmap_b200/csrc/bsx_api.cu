@@ -370,6 +370,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     a.site_len = (int)strnlen(p->digest_site, sizeof p->digest_site); a.digest_pos = p->digest_pos;
     a.seed_bits = (p->seed_size == 16) ? 0xffffffffu : ((1u << (2 * p->seed_size)) - 1);
     a.plan_cap = m->plan_cap; a.nslot = m->nslot;
+    bsx_map_args_derive(a);
     for (int i = 0; i < p->n_adapter; i++) { a.adapter_len[i] = (int)strnlen(p->adapter[i], 63); memcpy(a.adapter[i], p->adapter[i], 64); }
     memcpy(a.digest_site, p->digest_site, sizeof a.digest_site);
     a.stride = stride; a.stats = m->d_stats; a.debug = m->d_debug;

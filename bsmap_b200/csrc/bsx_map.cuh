@@ -18,6 +18,7 @@ struct MapArgs {
     uint32_t seed_bits;
     int plan_cap;                 // plan entries per chain = max segments * I
     int nslot;                    // chains a read can use at once: 2 with -n 1, else 1 (plan storage per read)
+    uint32_t read_smem, warp_smem_se, chain_stride, flank_off;   // derived from the two above on the host (bsx_map_args_derive)
     int adapter_len[BSX_MAX_ADAPTERS];
     char adapter[BSX_MAX_ADAPTERS][64];
     char digest_site[32];
@@ -74,7 +75,9 @@ struct CtaSm {
     uint8_t profA[16 * 16];           // Param::InitMapping profile[n][i].a (param.cpp:85-93)
     uint8_t segof[160], remof[160];   // p / seed_size, p % seed_size
     uint8_t divI[256], modI[256];     // t / per, t % per  (per = sub-seeds per segment)
+    uint16_t chr_lut[264];            // int2hit: sequence that holds position g << 24 of the concatenated reference (257 used)
 };
+static_assert(sizeof(CtaSm) % 16 == 0, "per-warp shared memory follows CtaSm and holds uint4");
 
 static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int nslot) {
     return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * 2u * sizeof(uint4);
@@ -84,6 +87,13 @@ static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int n
 }
 static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
     return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot) * BSX_WARPS_PER_CTA;
+}
+
+static inline void bsx_map_args_derive(MapArgs &a) {
+    a.read_smem = (uint32_t)bsx_read_smem_bytes(a.plan_cap, a.nslot);
+    a.warp_smem_se = (uint32_t)bsx_warp_smem_bytes(1, a.plan_cap, a.nslot);
+    a.chain_stride = a.nslot == 2 ? (uint32_t)a.plan_cap : 0u;
+    a.flank_off = (uint32_t)(a.nslot * a.plan_cap);
 }
 
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st);

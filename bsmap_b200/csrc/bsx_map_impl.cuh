@@ -55,7 +55,7 @@
 #define BSX_PIPE 1              // software-pipeline the inline-context loads one step ahead
 #endif
 #ifndef BSX_SE_MIN_CTAS
-#define BSX_SE_MIN_CTAS 6
+#define BSX_SE_MIN_CTAS 5
 #endif
 
 namespace {
@@ -68,10 +68,15 @@ typedef uint32_t Ctr;
 #define CTR_ADD(C, k, v) do { const uint32_t v_ = (uint32_t)(v); if (lane == 0) (C)[k] += v_; } while (0)   // v may hold warp collectives
 
 __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, const MapArgs &A) {
-    return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + (A.nslot == 2 ? chain : 0) * A.plan_cap;
+    return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * A.chain_stride;
 }
 __device__ __forceinline__ uint4 *flank_of(ReadSm *R, int chain, const MapArgs &A) {
-    return plan_of(R, chain, A) + A.nslot * A.plan_cap;
+    return plan_of(R, chain, A) + A.flank_off;
+}
+
+__device__ __forceinline__ const CtaSm *cta_tables() {   // the CTA's tables sit at the start of dynamic shared memory
+    extern __shared__ __align__(16) uint8_t bsx_dyn_smem_[];
+    return reinterpret_cast<const CtaSm *>(bsx_dyn_smem_);
 }
 
 // per-CTA tables: seed profile and p -> (segment, remainder), so per-read code never divides
@@ -83,6 +88,17 @@ __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
     const int per = BSX_RRBS(A) ? 1 : A.I;
     #pragma unroll 1
     for (int t = threadIdx.x; t < 256; t += blockDim.x) { K->divI[t] = (uint8_t)(t / per); K->modI[t] = (uint8_t)(t % per); }
+    // chr_lut[g] = largest k with anchor[k] <= g << 24 (0 when none): int2hit then searches [chr_lut[g], chr_lut[g+1]]
+    #pragma unroll 1
+    for (int t = threadIdx.x; t < 258; t += blockDim.x) {
+        int left = 0;
+        if (t < 256 && A.n_seq < 65536u) {
+            const uint32_t x = (uint32_t)t << 24;
+            int right = (int)A.n_seq;
+            while (left < right - 1) { const int mid = (left + right) / 2; if (x >= A.seqinfo[mid]) left = mid; else right = mid; }
+        } else if (A.n_seq < 65536u) left = (int)A.n_seq - 1;
+        K->chr_lut[t] = (uint16_t)left;
+    }
     __syncthreads();
 }
 
@@ -538,8 +554,10 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
         const uint32_t strand_s = __shfl_sync(BSX_FULL, strand, src);
         uint32_t chr_s;
         if (!BSX_RRBS(A)) {
-            // RefSeq::int2hit (dbseq.cpp:585-595)
+            // RefSeq::int2hit (dbseq.cpp:585-595); the per-CTA table narrows the search to the sequences
+            // that overlap the position's 16 Mb granule (almost always one)
             int left = 0, right = (int)A.n_seq;
+            if (A.n_seq < 65536u) { const CtaSm *K = cta_tables(); left = K->chr_lut[loc_s >> 24]; right = K->chr_lut[(loc_s >> 24) + 1] + 1; }
             while (left < right - 1) { int mid = (left + right) / 2; if (loc_s >= anchor[mid]) left = mid; else right = mid; }
             chr_s = (uint32_t)left * 2u + strand_s;
             loc_s -= anchor[left];
@@ -749,12 +767,11 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
 #else
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #endif
-    const size_t per_warp = bsx_read_smem_bytes(A.plan_cap, A.nslot) + sizeof(SelSm);
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
-    uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
+    uint8_t *base = smem + sizeof(CtaSm) + A.warp_smem_se * wid;
     ReadSm *R = reinterpret_cast<ReadSm *>(base);
-    SelSm *X = reinterpret_cast<SelSm *>(base + bsx_read_smem_bytes(A.plan_cap, A.nslot));
+    SelSm *X = reinterpret_cast<SelSm *>(base + A.read_smem);
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
