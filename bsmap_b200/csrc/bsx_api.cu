@@ -250,6 +250,7 @@ struct bsx_slot {
     uint16_t *d_cnt_a = nullptr, *d_cnt_b = nullptr;
     uint32_t *d_counter = nullptr;
     uint2 *d_hits = nullptr; uint32_t *d_dd = nullptr; uint4 *d_pairs = nullptr;
+    uint8_t *d_prep = nullptr;   // prepared-read images of one chunk (bsx_prep.cu)
 };
 
 struct bsx_mapper {
@@ -274,7 +275,7 @@ int bsx_map_occupancy_pe(size_t smem);   // bsx_map_pe.cu
 
 static void slot_free(bsx_slot &s) {
     cudaFree(s.d_seq_a); cudaFree(s.d_seq_b); cudaFree(s.d_len_a); cudaFree(s.d_len_b); cudaFree(s.d_out_a); cudaFree(s.d_out_b);
-    cudaFree(s.d_out_pair); cudaFree(s.d_cnt_a); cudaFree(s.d_cnt_b); cudaFree(s.d_counter); cudaFree(s.d_hits); cudaFree(s.d_dd); cudaFree(s.d_pairs);
+    cudaFree(s.d_out_pair); cudaFree(s.d_cnt_a); cudaFree(s.d_cnt_b); cudaFree(s.d_counter); cudaFree(s.d_hits); cudaFree(s.d_dd); cudaFree(s.d_pairs); cudaFree(s.d_prep);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = bsx_slot();
 }
@@ -343,6 +344,8 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     m->dd_stride = lv * (uint32_t)p->max_num_hits + 32;
     m->pair_stride = (2 * (uint32_t)p->max_snp_num + 1) * W1 * 2;   // uint4 units (32-byte PairHit)
     const size_t se_warps = (size_t)m->n_ctas_se * BSX_WARPS_PER_CTA;
+    // prepared-unit images: 32 per resident warp (phase A of the align kernels, bsx_prep.cuh)
+    const size_t prep_bytes = std::max(se_warps, (size_t)m->n_ctas_pe * BSX_WARPS_PER_CTA) * 32u * bsx_read_smem_bytes(m->plan_cap, m->nslot);
     for (int i = 0; i < 2; i++) {
         bsx_slot &s = m->slot[i];
         BSX_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -353,6 +356,8 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
         BSX_CUDA_CHECK(cudaMalloc(&s.d_counter, 64));
         BSX_CUDA_CHECK(cudaMalloc(&s.d_hits, se_warps * (size_t)m->hit_stride * sizeof(uint2)));
         BSX_CUDA_CHECK(cudaMalloc(&s.d_dd, se_warps * (size_t)m->dd_stride * 4));
+        BSX_CUDA_CHECK(cudaMalloc(&s.d_prep, prep_bytes));
+        BSX_CUDA_CHECK(cudaMemset(s.d_prep, 0, prep_bytes));
     }
     BSX_CUDA_CHECK(cudaMalloc(&m->d_stats, 8 * sizeof(unsigned long long)));
     BSX_CUDA_CHECK(cudaMemset(m->d_stats, 0, 8 * sizeof(unsigned long long)));
@@ -403,6 +408,7 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     a.n = n; a.first_index = first_index; a.readset = readset;
     a.out_a = s.d_out_a; a.out_b = s.d_out_b; a.out_pair = s.d_out_pair; a.cnt_a = s.d_cnt_a; a.cnt_b = s.d_cnt_b;
     a.work_counter = s.d_counter; a.hit_scratch = s.d_hits; a.dd_scratch = s.d_dd; a.pair_scratch = s.d_pairs;
+    a.prep = s.d_prep; a.mates = pe ? 2 : 1;
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;

@@ -38,15 +38,19 @@ struct MapArgs {
     uint4 *pair_scratch;          // per warp: PE pair buckets
     uint32_t hit_stride, dd_stride, pair_stride;
     uint32_t *debug;              // optional: per read 40 u32 of seed-selection state (tests)
+    uint8_t *prep;                // prepared-unit images: [warp][32] x read_smem bytes (bsx_prep.cuh)
+    int mates;                    // units per read: 1 (SE) or 2 (PE)
 };
 
-// shared memory, per read handled by a warp (SE: 1, PE: 2)
+// One prepared read: written to global memory in the prepare phase (one THREAD per read: trim, filter, pack,
+// choose seeds -- bsx_prep.cuh), copied into shared memory by the warp when it aligns it.  The image is this struct
+// followed by uint4 plan[nslot][plan_cap]: {list start, rc start, list end, read offset | segment << 16}
+// and uint4 flank[nslot][plan_cap]: read bases / mask facing the inline context before (x,y) and after (z,w) the seed.
 struct ReadSm {
     uint32_t rw[2][BSX_FIXWORDS];     // 2-bit read, chain 0 = as is, 1 = reverse complement (bseq/cbseq)
     uint32_t m5[2][BSX_FIXWORDS];     // 01 per ACGT base (reg/creg & 0x5555...)
     uint16_t nh[16], nc[16];          // _cur_n_hit / _cur_n_chit
-    // per-read state (SingleAlign members), warp-uniform; kept in shared memory so the big device functions can be
-    // real calls (one copy of the code: the kernels used to be I-cache bound) instead of inlined register structs
+    // per-read state (SingleAlign members), warp-uniform
     int raw, seedseg, readset, filtered;
     uint32_t index;
     int len, rmsn, nw;                // read length after trimming, read_max_snp_num, packed words
@@ -55,17 +59,11 @@ struct ReadSm {
     uint32_t dn;                      // dedupe entries
     int best;                         // lowest mismatch level that holds a hit
     uint32_t pad_[3];
-    uint8_t ascii[160];
-    // followed by uint4 plan[nslot][plan_cap]: {list start, rc start, list end, read offset | segment << 16}
-    // and uint4 flank[nslot][plan_cap]: read bases / mask facing the inline context before (x,y) and after (z,w) the seed
 };
+static_assert(sizeof(ReadSm) % 16 == 0, "images are copied as uint4");
 
-// transient per-warp scratch used while choosing seeds
+// per-warp scratch of the align kernels
 struct SelSm {
-    uint32_t st[BSX_MAX_KEYS], md[BSX_MAX_KEYS], sz[BSX_MAX_KEYS];   // per read offset: list start, rc start, list "size" (index2[key][0])
-    uint32_t T[16 * 16];              // T[n][o] = CountSeeds(segment n, start offset o)
-    int arr[16];                      // seed_start_array
-    int sidx[16][2];                  // seedindex (sum, segment)
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
     uint32_t ctr[8];                  // work counters of this warp (bsx_stats order), flushed to global rarely
 };
@@ -74,7 +72,6 @@ struct SelSm {
 struct CtaSm {
     uint8_t profA[16 * 16];           // Param::InitMapping profile[n][i].a (param.cpp:85-93)
     uint8_t segof[160], remof[160];   // p / seed_size, p % seed_size
-    uint8_t divI[256], modI[256];     // t / per, t % per  (per = sub-seeds per segment)
     uint16_t chr_lut[264];            // int2hit: sequence that holds position g << 24 of the concatenated reference (257 used)
 };
 static_assert(sizeof(CtaSm) % 16 == 0, "per-warp shared memory follows CtaSm and holds uint4");

@@ -58,6 +58,8 @@
 #define BSX_SE_MIN_CTAS 5
 #endif
 
+#include "bsx_prep.cuh"
+
 namespace {
 
 // work counters live in shared memory (SelSm::ctr, bsx_stats order); lane 0 updates them
@@ -79,15 +81,12 @@ __device__ __forceinline__ const CtaSm *cta_tables() {   // the CTA's tables sit
     return reinterpret_cast<const CtaSm *>(bsx_dyn_smem_);
 }
 
-// per-CTA tables: seed profile and p -> (segment, remainder), so per-read code never divides
+// per-CTA tables: seed profile and p -> (segment, remainder) for the prepare phase, the granule table for int2hit
 __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
     #pragma unroll 1
     for (int t = threadIdx.x; t < 256; t += blockDim.x) K->profA[t] = (uint8_t)bsx_profile_a(A.s, A.I, t >> 4, t & 15);
     #pragma unroll 1
     for (int t = threadIdx.x; t < 160; t += blockDim.x) { K->segof[t] = (uint8_t)(t / A.s); K->remof[t] = (uint8_t)(t % A.s); }
-    const int per = BSX_RRBS(A) ? 1 : A.I;
-    #pragma unroll 1
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) { K->divI[t] = (uint8_t)(t / per); K->modI[t] = (uint8_t)(t % per); }
     // chr_lut[g] = largest k with anchor[k] <= g << 24 (0 when none): int2hit then searches [chr_lut[g], chr_lut[g+1]]
     #pragma unroll 1
     for (int t = threadIdx.x; t < 258; t += blockDim.x) {
@@ -102,278 +101,25 @@ __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
     __syncthreads();
 }
 
-// ------------------------------------------------------------------ K2: load, trim, filter, pack
-__device__ __forceinline__ void load_read(const MapArgs &A, ReadSm *R, const uint8_t *seqs,
-                                          const uint16_t *lens, uint32_t r, int readset, int lane) {
-    int len = lens[r];
-    if (len > A.max_readlen) len = A.max_readlen;          // reads.cpp:115-117
-    if (len > BSX_MAX_READLEN) len = BSX_MAX_READLEN;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(seqs + (size_t)r * A.stride);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(R->ascii);
+// A prepared image (bsx_prep.cuh) -> this warp's shared memory: a few coalesced 16-byte loads per lane.
+// ld.cg: the image was written by another lane of this warp moments ago, so the read-only path is not allowed.
+__device__ __forceinline__ void load_image(const MapArgs &A, ReadSm *R, const uint8_t *img, int lane) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(img);
+    uint4 *dst = reinterpret_cast<uint4 *>(R);
+    const int n16 = (int)(A.read_smem >> 4);
+    __syncwarp();
     #pragma unroll 1
-    for (int t = lane; t < 40; t += 32) dst[t] = (t * 4 < (int)A.stride) ? __ldg(src + t) : 0u;
-    __syncwarp();
-    __syncwarp();
-    if (lane == 0) { R->len = len; R->raw = len; R->readset = readset; R->index = A.first_index + r; }
+    for (int t = lane; t < n16; t += 32) dst[t] = __ldcg(src + t);
     __syncwarp();
 }
 
-// TrimAdapter (align.cpp:371-425): adapters in -A order, positions ascending, first success wins
-__device__ BSX_FN void trim_adapter(const MapArgs &A, ReadSm *R, int lane) {
-    WSET(R->raw, R->len);
-    const int len = R->len, s = A.s;
-    const uint8_t *sq = R->ascii;
-    const int tail = BSX_RRBS(A) ? 5 : 4;
-    #pragma unroll 1
-    for (int a = 0; a < A.n_adapter; a++) {
-        const int al = A.adapter_len[a];
-        #pragma unroll 1
-        for (int pos0 = s; pos0 < len - tail; pos0 += 32) {
-            const int pos = pos0 + lane;
-            bool ok = false;
-            if (pos < len - tail) {
-                int m0 = 0, k = 0;
-                #pragma unroll 1
-                for (; k < al && k < 15 && pos + k < len; k++) {
-                    m0 += (A.adapter[a][k] != (char)sq[pos + k]);
-                    if (m0 > 4) break;
-                }
-                if (!BSX_RRBS(A)) ok = (k >= m0 * 5 && k > 3);
-                else if (k >= m0 * 5) {
-                    // digestion-site remnant just before the adapter (align.cpp:383-404)
-                    const int sl = A.site_len, dp = A.digest_pos;
-                    int m = m0, m2 = m0;
-                    #pragma unroll 1
-                    for (int t = 0; t < sl - dp; t++) {
-                        char x = A.digest_site[t], y = (char)sq[pos - sl + dp + t];
-                        m += (x != y) && (x != 'C' || y != 'T');
-                        m2 += (x != y) && (x != 'G' || y != 'A');
-                    }
-                    ok = (k >= m * 5) || (A.pairend && k >= m2 * 5);
-                }
-            }
-            unsigned b = __ballot_sync(BSX_FULL, ok);
-            if (b) { WSET(R->len, pos0 + __ffs(b) - 1); return; }
-        }
-    }
-}
-
-// FilterReads (align.cpp:579-589); returns 1 when the read is rejected.  The chains the read will be
-// aligned with are packed here (ConvertBinaySeq), because the valid-base mask also gives CountNs.
-__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, int chain, int lane);
-__device__ __forceinline__ int filter_read(const MapArgs &A, ReadSm *R, int lane) {
-    trim_adapter(A, R,  lane);
-    {   // flag_chain / cflag_chain (align.cpp:93-94)
-        const int fc = A.chains || (R->readset < 2), cc = A.chains || (R->readset == 2);
-        __syncwarp();
-        if (lane == 0) { R->fc = fc; R->cc = cc; }
-        __syncwarp();
-    }
-    if (R->len < A.s) return 1;
-    if (R->fc) pack_chain(A, R,  0, lane);
-    if (R->cc) pack_chain(A, R,  1, lane);
-    int nv = lane < BSX_FIXWORDS ? __popc(R->m5[R->fc ? 0 : 1][lane]) : 0;
-#pragma unroll
-    for (int d = 8; d; d >>= 1) nv += __shfl_xor_sync(BSX_FULL, nv, d);
-    nv = __shfl_sync(BSX_FULL, nv, 0);
-    if (R->len - nv > A.max_ns) return 1;            // CountNs (align.cpp:48-55)
-    // read_max_snp_num = (v+1)*(len-1)/raw_readlen (align.cpp:586); equals v for an untrimmed read longer than v
-    WSET(R->rmsn, (R->len == R->raw && A.v + 1 <= R->len) ? A.v : (int)((unsigned)(A.v + 1) * (unsigned)(R->len - 1) / (unsigned)R->raw));
-    return 0;
-}
-
-// four ASCII bases in a u32 (first base in the low byte) -> their 2-bit codes and validity, byte-wise
-__device__ __forceinline__ void codes4(uint32_t w, int rev, uint32_t &code, uint32_t &valid) {
-    const uint32_t v = w | 0x20202020u;
-    valid = __vcmpeq4(v, 0x61616161u) | __vcmpeq4(v, 0x63636363u) | __vcmpeq4(v, 0x67676767u) | __vcmpeq4(v, 0x74747474u);
-    uint32_t c = (w >> 1) & 0x03030303u;          // A 0, C 1, G 3, T 2
-    c ^= (c >> 1) & 0x01010101u;                   // A 0, C 1, G 2, T 3
-    c &= valid;                                    // everything else -> 0 (alphabet[], param.cpp:210)
-    if (rev) c = (~c) & 0x03030303u;               // complement; everything else -> 3 (rev_alphabet[], param.cpp:215)
-    code = c;
-    valid &= 0x01010101u;
-}
-// byte-wise 2-bit fields (first base in the low byte) -> 8 bits, first base most significant
-__device__ __forceinline__ uint32_t squeeze4(uint32_t c) {
-    return ((c & 0x3u) << 6) | ((c >> 4) & 0x30u) | ((c >> 14) & 0xCu) | (c >> 24);
-}
-
-// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask.
-// Lane t < 20 converts bases [8t, 8t+8) with byte-SIMD ops; lane pairs are merged by shuffle.
-__device__ __forceinline__ void pack_chain(const MapArgs &A, ReadSm *R, int chain, int lane) {
-    const int len = R->len;
-    uint32_t half = 0, mhalf = 0;
-    if (lane < 2 * BSX_FIXWORDS) {
-        uint32_t w0, w1;
-        if (!chain) {
-            const uint32_t *a32 = reinterpret_cast<const uint32_t *>(R->ascii);
-            w0 = a32[2 * lane]; w1 = a32[2 * lane + 1];
-        } else {                                    // reversed read: base i is ascii[len-1-i]
-            w0 = 0; w1 = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i0 = len - 1 - (8 * lane + k), i1 = i0 - 4;
-                w0 |= (i0 >= 0 ? (uint32_t)R->ascii[i0] : 0u) << (8 * k);
-                w1 |= (i1 >= 0 ? (uint32_t)R->ascii[i1] : 0u) << (8 * k);
-            }
-        }
-        // bases beyond the read count as invalid code 0
-        const int rem = len - 8 * lane;             // valid bases in this lane's 8
-        uint32_t keep0 = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : (0xffffffffu >> (8 * (4 - rem))));
-        uint32_t keep1 = rem >= 8 ? 0xffffffffu : (rem <= 4 ? 0u : (0xffffffffu >> (8 * (8 - rem))));
-        uint32_t c0, v0, c1, v1;
-        codes4(w0, chain, c0, v0); codes4(w1, chain, c1, v1);
-        c0 &= keep0; v0 &= keep0; c1 &= keep1; v1 &= keep1;
-        half = (squeeze4(c0) << 8) | squeeze4(c1);
-        mhalf = (squeeze4(v0) << 8) | squeeze4(v1);
-    }
-    const uint32_t ohalf = __shfl_down_sync(BSX_FULL, half, 1), omhalf = __shfl_down_sync(BSX_FULL, mhalf, 1);
-    if (lane < 2 * BSX_FIXWORDS && !(lane & 1)) {
-        R->rw[chain][lane >> 1] = (half << 16) | ohalf;
-        R->m5[chain][lane >> 1] = (mhalf << 16) | omhalf;
-    }
-    __syncwarp();
-}
-
-// seed_array[p] (align.cpp:101-105): 3-letter key of the seed starting at read offset p
-__device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const ReadSm *R, int chain, int p) {
-    const int j = p >> 4, sh = (p & 15) * 2;
-    const uint32_t hi = R->rw[chain][j], lo = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u;
-    const uint32_t v = __funnelshift_l(lo, hi, sh) >> (32 - 2 * A.s);
-    return bsx_xt(v & A.seed_bits, A.s);
-}
-
-// ------------------------------------------------------------------ K3: probe + choose seeds
-__device__ BSX_FN void select_seeds(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int chain, int lane, Ctr *C) {
-    const int s = A.s, I = A.I, len = R->len, seg = R->seedseg;
-    const int mo = (BSX_RRBS(A) || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
-    const int cso = (BSX_RRBS(A) && chain) ? (int)K->remof[len] : 0;    // cseed_offset (RRBS rc chain)
-    const int lim = I - 1 + mo;
-    // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset]
-    //    (profile.a - i lies in [n*s, n*s+I-1]); its list header is read ONCE, coalesced across lanes.
-    //    The union of those ranges is enumerated directly: w offsets per segment, the last one takes the tail
-    //    (when the ranges overlap, w = s and the union is one interval).  idx / w by a float reciprocal (idx < 4096).
+// Phase A for a block of `cnt` units starting at unit u0: lane i prepares unit u0 + i into image i of the warp's scratch
+__device__ __forceinline__ void prepare_block(const MapArgs &A, const CtaSm *K, uint8_t *scratch, uint32_t u0, uint32_t cnt, int lane, Ctr *C) {
     int np = 0;
-    {
-        const int w = min(lim + 1, s);
-        const int total = BSX_RRBS(A) ? seg : (seg > 0 ? seg * w + (lim + 1 - w) : 0);
-        const float rw = __frcp_rn((float)w);
-        #pragma unroll 1
-        for (int idx = lane; idx < total; idx += 32) {
-            int p;
-            if (BSX_RRBS(A)) p = cso + idx * s;
-            else { const int n = min((int)(((float)idx + 0.5f) * rw), seg - 1); p = n * s + (idx - n * w); }
-            if (p + s <= len) {
-                const uint32_t key = seed_key(A, R, chain, p);
-                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
-                const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
-                const uint32_t n = e - a.x;
-                X->st[p] = a.x; X->md[p] = a.y;
-                X->sz[p] = BSX_RRBS(A) ? n : (n ? n + 2 : 0u);    // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
-                np++;
-            }
-        }
-    }
+    if ((uint32_t)lane < cnt) np = bsx_prep_unit(A, K, u0 + (uint32_t)lane, scratch + (size_t)lane * A.read_smem);
 #pragma unroll
     for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
     CTR_ADD(C, CT_PROBE, np);
-    __syncwarp();
-    // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset o <= max_offset, in parallel
-    if (!BSX_RRBS(A)) {
-        const int mo1 = mo + 1;
-        const float rm = __frcp_rn((float)mo1);
-        #pragma unroll 1
-        for (int idx = lane; idx < seg * mo1; idx += 32) {
-            const int n = (int)(((float)idx + 0.5f) * rm), o = idx - n * mo1;
-            uint32_t tt = 0;
-            #pragma unroll 1
-            for (int k = 0; k < I; k++) tt += X->sz[(int)K->profA[n * 16 + k] + o - k];
-            X->T[n * 16 + o] = tt;
-        }
-        __syncwarp();
-    }
-    // 3. ReorderSeed (align.cpp:454-468): global offset = FIRST minimum of GetTotalSeedLoc over [0, max_offset)
-    int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
-    if (!BSX_RRBS(A) && mo > 1) {                 // with a single candidate (max_offset == 1) the answer is 0
-        unsigned long long best = ~0ull;
-        if (lane < mo) {
-            uint32_t tt = 0;
-            #pragma unroll 1
-            for (int n = 0; n < seg; n++) tt += X->T[n * 16 + lane];
-            best = ((unsigned long long)tt << 8) | (unsigned)lane;
-        }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) { unsigned long long o2 = __shfl_xor_sync(BSX_FULL, best, d); best = o2 < best ? o2 : best; }
-        og = (int)(best & 0xff);
-    }
-    uint4 *plan = plan_of(R, chain, A), *flank = flank_of(R, chain, A);
-    if (lane == 0) {
-        // AdjustSeedStartArray (align.cpp:506-528)
-        #pragma unroll 1
-        for (int n = 0; n < seg; n++) X->arr[n] = og;
-        if (!BSX_RRBS(A)) {
-            #pragma unroll 1
-            for (int i = 0; i < seg; i++) {
-                const int ptr = (i & 1) == 0 ? i / 2 : seg - 1 - i / 2;
-                uint32_t total = 0xffffffffu;
-                const int start = (ptr == 0) ? 0 : X->arr[ptr - 1];
-                const int end = (ptr == seg - 1) ? mo : X->arr[ptr + 1];
-                int bi = start;
-                #pragma unroll 1
-                for (int ii = start; ii <= end; ii++) {
-                    const uint32_t tt = X->T[ptr * 16 + ii];
-                    if (tt < total) { total = tt; bi = ii; }
-                }
-                X->arr[ptr] = bi;
-            }
-        }
-    }
-    __syncwarp();
-    // seedindex: (sum of list sizes, segment) ascending (align.cpp:474-485): rank sort, one segment per lane
-    int mine = 0;
-    if (lane < seg) {
-        mine = (int)(BSX_RRBS(A) ? X->sz[lane * s + cso] : X->T[lane * 16 + X->arr[lane]]);
-        X->sidx[lane][0] = mine;
-    }
-    __syncwarp();
-    int rank = 0;
-    if (lane < seg) {
-        #pragma unroll 1
-        for (int m = 0; m < seg; m++) {
-            const int other = X->sidx[m][0];
-            rank += (other < mine) || (other == mine && m < lane);
-        }
-    }
-    __syncwarp();
-    if (lane < seg) X->sidx[rank][1] = lane;
-    __syncwarp();
-    // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
-    const int per = BSX_RRBS(A) ? 1 : I;
-    #pragma unroll 1
-    for (int t = lane; t < seg * per; t += 32) {
-        const int m = K->divI[t], k = K->modI[t];
-        const int sg = X->sidx[m][1];
-        const int p = BSX_RRBS(A) ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + X->arr[sg] - k);
-        const uint32_t st0 = X->st[p], sz0 = X->sz[p];
-        const uint32_t en0 = st0 + (BSX_RRBS(A) ? sz0 : (sz0 ? sz0 - 2u : 0u));
-        plan[t] = make_uint4(st0, X->md[p], en0, (uint32_t)p | ((uint32_t)sg << 16));
-        if (!BSX_RRBS(A)) {
-            // read bases / valid mask facing an entry's inline context: [p-16, p) and [p+s, p+s+16)
-            const int xb = p - 16, xa = p + s;
-            uint32_t rb = 0, mb = 0;
-            if (xb >= 0) {
-                const int j = xb >> 4, sh = (xb & 15) * 2;
-                rb = __funnelshift_l(R->rw[chain][j + 1], R->rw[chain][j], sh);      // j + 1 <= 9 because p <= 144
-                mb = __funnelshift_l(R->m5[chain][j + 1], R->m5[chain][j], sh);
-            } else if (xb > -16) {                                                   // fewer than 16 bases before the seed
-                rb = R->rw[chain][0] >> (2 * (-xb)); mb = R->m5[chain][0] >> (2 * (-xb));
-            }
-            const int j = xa >> 4, sh = (xa & 15) * 2;
-            const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
-            const uint32_t r0 = (j < BSX_FIXWORDS) ? R->rw[chain][j] : 0u, m0 = (j < BSX_FIXWORDS) ? R->m5[chain][j] : 0u;
-            flank[t] = make_uint4(rb, mb, __funnelshift_l(r1, r0, sh), __funnelshift_l(m1, m0, sh));
-        }
-    }
     __syncwarp();
 }
 
@@ -577,7 +323,7 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
 // rc entries, sub-seed 1's, ...), 64 table entries per step (two per lane).  Everything that depends on
 // the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
 // work is one 8-byte load, two masked XOR/popcount words and a compare.
-__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
+__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
     const int per = BSX_RRBS(A) ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
@@ -694,35 +440,11 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, SelSm *X, uint2 *hi
     return 0;
 }
 
-// everything RunAlign does before the mode loop (align.cpp:435-444)
-__device__ BSX_FN void prepare_read(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, int lane, Ctr *C, uint32_t *dbg) {
-    {
-        const int q = R->len - A.I + 1;
-        int seg = q > 0 ? min((int)K->segof[q], R->rmsn + 1) : 0;
-        const int rmsn = R->rmsn, nw = (R->len + 15) >> 4;
-        __syncwarp();
-        if (lane == 0) { R->seedseg = seg; R->thres = (uint32_t)rmsn; R->nw = nw; R->dn = 0; R->best = 99; }
-        __syncwarp();
-    }
-    if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
-    __syncwarp();
-    for (int chain = 0; chain < 2; chain++) {
-        if (chain == 0 ? !R->fc : !R->cc) continue;
-        select_seeds(A, K, R, X,  chain, lane, C);
-        if (dbg && lane == 0) {
-            dbg[chain * 20 + 0] = (uint32_t)R->seedseg;
-            for (int n = 0; n < R->seedseg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)X->arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)X->sidx[n][1]; }
-        }
-        __syncwarp();
-    }
-}
-
-// SingleAlign::RunAlign (align.cpp:435-452)
-__device__ BSX_FN void run_align(const MapArgs &A, const CtaSm *K, ReadSm *R, SelSm *X, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint32_t *dbg) {
-    prepare_read(A, K, R, X,  lane, C, dbg);
+// SingleAlign::RunAlign (align.cpp:435-452): the mode loop (everything before it happened in the prepare kernel)
+__device__ BSX_FN void run_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C) {
     #pragma unroll 1
     for (int m = 0; m < R->seedseg; m++) {
-        snp_align(A, R, X,  hits, dd, store_all, m, lane, C);
+        snp_align(A, R, hits, dd, store_all, m, lane, C);
         if (!BSX_RRBS(A) && R->best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
     }
 }
@@ -778,28 +500,25 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     Ctr *C = X->ctr;
     if (lane < 8) C[lane] = 0;
     __syncwarp();
-    uint32_t r = 0, r_end = 0;
+    uint8_t *scratch = A.prep + (size_t)gw * 32u * A.read_smem;
     for (;;) {
-        if (r == r_end) {                       // one atomic hands this warp BSX_READ_BLOCK consecutive reads
-            if (lane == 0) r = atomicAdd(A.work_counter, (uint32_t)BSX_READ_BLOCK);
-            r = __shfl_sync(BSX_FULL, r, 0);
-            if (r >= A.n) break;
-            r_end = min(r + (uint32_t)BSX_READ_BLOCK, A.n);
+        uint32_t r0 = 0;                        // one atomic hands this warp 32 consecutive reads
+        if (lane == 0) r0 = atomicAdd(A.work_counter, 32u);
+        r0 = __shfl_sync(BSX_FULL, r0, 0);
+        if (r0 >= A.n) break;
+        const uint32_t cnt = min(32u, A.n - r0);
+        prepare_block(A, K, scratch, r0, cnt, lane, C);                       // phase A: one lane per read
+        #pragma unroll 1
+        for (uint32_t i = 0; i < cnt; i++) {                                  // phase B: the warp aligns them one by one
+            const uint32_t r = r0 + i;
+            if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
+            load_image(A, R, scratch + (size_t)i * A.read_smem, lane);
+            if (!R->filtered) run_align(A, R, hits, dd, 0, lane, C);
+            __syncwarp();
+            write_record(A, R,  hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
+            if (!R->filtered && R->best <= R->rmsn) CTR_ADD(C, CT_MAPPED, 1);
+            __syncwarp();
         }
-        if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
-        __syncwarp();
-        if (lane == 0) { R->rmsn = 0; R->seedseg = 0; R->nw = 0; R->thres = 0; R->fc = R->cc = 0; R->dn = 0; R->best = 99; }
-        __syncwarp();
-        load_read(A, R,  A.seq_a, A.len_a, r, A.readset, lane);
-        WSET(R->filtered, filter_read(A, R, lane));
-        uint32_t *dbg = A.debug ? A.debug + (size_t)r * 40 : nullptr;
-        if (!R->filtered) run_align(A, K, R, X,  hits, dd, 0, lane, C, dbg);
-        else if (lane < 16) { R->nh[lane] = 0; R->nc[lane] = 0; }
-        __syncwarp();
-        write_record(A, R,  hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
-        if (!R->filtered && R->best <= R->rmsn) CTR_ADD(C, CT_MAPPED, 1);
-        __syncwarp();
-        r++;
     }
     flush_counters(A, C, lane);
 }
@@ -918,11 +637,14 @@ __device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, uint2 *hits) {
     }
 }
 
-__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, 4)
+#ifndef BSX_PE_MIN_CTAS
+#define BSX_PE_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_PE_MIN_CTAS)
 bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t read_sm = bsx_read_smem_bytes(A.plan_cap, A.nslot);
+    const size_t read_sm = A.read_smem;
     const size_t per_warp = 2 * read_sm + sizeof(SelSm);
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
@@ -939,38 +661,32 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     if (lane < 8) C[lane] = 0;
     __syncwarp();
     const size_t W1 = (size_t)A.W + 1;
+    uint8_t *scratch = A.prep + (size_t)gw * 32u * A.read_smem;
     for (;;) {
-        uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(A.work_counter, 1u);
-        r = __shfl_sync(BSX_FULL, r, 0);
-        if (r >= A.n) break;
+        uint32_t r0 = 0;                        // one atomic hands this warp 16 consecutive pairs = 32 units
+        if (lane == 0) r0 = atomicAdd(A.work_counter, 16u);
+        r0 = __shfl_sync(BSX_FULL, r0, 0);
+        if (r0 >= A.n) break;
+        const uint32_t cnt = min(16u, A.n - r0);
+        prepare_block(A, K, scratch, r0 * 2u, cnt * 2u, lane, C);             // phase A: one lane per mate
+      #pragma unroll 1
+      for (uint32_t pi = 0; pi < cnt; pi++) {                                 // phase B: the warp aligns the pairs one by one
+        const uint32_t r = r0 + pi;
         if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
-        __syncwarp();
-        if (lane == 0) {
-            Ra->rmsn = Rb->rmsn = 0; Ra->seedseg = Rb->seedseg = 0; Ra->dn = Rb->dn = 0; Ra->best = Rb->best = 99;
-            Ra->nw = Rb->nw = 0; Ra->thres = Rb->thres = 0; Ra->fc = Ra->cc = Rb->fc = Rb->cc = 0;
-        }
-        __syncwarp();
-        load_read(A, Ra,  A.seq_a, A.len_a, r, 1, lane);
-        load_read(A, Rb,  A.seq_b, A.len_b, r, 2, lane);
-        WSET(Ra->filtered, filter_read(A, Ra, lane));
-        WSET(Rb->filtered, filter_read(A, Rb, lane));
-        if (lane < 16) { Ra->nh[lane] = Ra->nc[lane] = 0; Rb->nh[lane] = Rb->nc[lane] = 0; }
-        __syncwarp();
+        load_image(A, Ra, scratch + (size_t)(2u * pi) * A.read_smem, lane);
+        load_image(A, Rb, scratch + (size_t)(2u * pi + 1u) * A.read_smem, lane);
         int paired = 0;
         bsx_pair_rec po;
         po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
         if (!Ra->filtered && !Rb->filtered) {
             // PairAlign::RunAlign (pairs.cpp:137-190)
-            prepare_read(A, K, Ra, X,  lane, C, nullptr);
-            prepare_read(A, K, Rb, X,  lane, C, nullptr);
             if (lane < 31) npairs[lane] = 0;
             __syncwarp();
             const int maxi = max(Ra->rmsn, Rb->rmsn);
             #pragma unroll 1
             for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Ra->seedseg) snp_align(A, Ra, X,  hits_a, dd_a, 1, i, lane, C);
-                if (i < Rb->seedseg) snp_align(A, Rb, X,  hits_b, dd_b, 1, i, lane, C);
+                if (i < Ra->seedseg) snp_align(A, Ra, hits_a, dd_a, 1, i, lane, C);
+                if (i < Rb->seedseg) snp_align(A, Rb, hits_b, dd_b, 1, i, lane, C);
                 if (i <= Ra->rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
                 if (i <= Rb->rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
                 __syncwarp();
@@ -1003,8 +719,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                 }
             }
         } else {
-            if (!Ra->filtered) run_align(A, K, Ra, X,  hits_a, dd_a, 1, lane, C, nullptr);
-            if (!Rb->filtered) run_align(A, K, Rb, X,  hits_b, dd_b, 1, lane, C, nullptr);
+            if (!Ra->filtered) run_align(A, Ra, hits_a, dd_a, 1, lane, C);
+            if (!Rb->filtered) run_align(A, Rb, hits_b, dd_b, 1, lane, C);
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
         if (!out_paired && BSX_RRBS(A)) {
@@ -1016,6 +732,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
         write_unpaired(A, Rb,  hits_b, A.out_b + r, A.cnt_b ? A.cnt_b + (size_t)r * 16 : nullptr, lane);
         if (out_paired) CTR_ADD(C, CT_MAPPED, 1);
         __syncwarp();
+      }
     }
     flush_counters(A, C, lane);
 }

@@ -1,0 +1,302 @@
+// bsx_prep.cuh -- the prepare phase: everything SingleAlign does to a read before the first SnpAlign call,
+// one THREAD per read.
+//
+//   TrimAdapter (align.cpp:371-425) -> FilterReads / CountNs (579-589, 48-55) -> ConvertBinaySeq (90-162)
+//   -> seed probing + ReorderSeed / AdjustSeedStartArray / seedindex (454-528, 549-571)
+//
+// These steps are short, branchy and sequential per read; run by a whole warp (the first design) they cost
+// ~1000 warp instructions per read with most lanes idle -- a third of the align kernel, which is issue-bound.
+// One thread per read executes the same work in ~1/10 of the warp instructions, because reads of one length
+// take identical trip counts and the lanes stay converged.  A warp therefore takes 32 units (reads / mates) at
+// a time: phase A, each lane prepares one unit into a self-contained image (ReadSm + seed plan + context
+// flanks, bsx_map.cuh) in the warp's global scratch; phase B, the warp aligns the 32 units one after the
+// other, copying each image into shared memory with a few coalesced loads.  Phase A is latency-bound
+// (~30 dependent-free but serial table probes per lane) and hides behind the other warps' phase B.
+// (A separate prepare KERNEL was measured first: 209 M reads/s against 268 M -- alone on the GPU it is bound by
+// DRAM random accesses, 30 ms per 20 M reads, that the fused form overlaps with issue-bound alignment.)
+#pragma once
+#include "bsx_map.cuh"
+
+namespace {
+
+typedef CtaSm PrepSm;   // profA / segof / remof live in the CTA's table block
+
+// four ASCII bases in a u32 (first base in the low byte) -> their 2-bit codes and validity, byte-wise
+__device__ __forceinline__ void codes4(uint32_t w, uint32_t &code, uint32_t &valid) {
+    const uint32_t v = w | 0x20202020u;
+    valid = __vcmpeq4(v, 0x61616161u) | __vcmpeq4(v, 0x63636363u) | __vcmpeq4(v, 0x67676767u) | __vcmpeq4(v, 0x74747474u);
+    uint32_t c = (w >> 1) & 0x03030303u;          // A 0, C 1, G 3, T 2
+    c ^= (c >> 1) & 0x01010101u;                   // A 0, C 1, G 2, T 3
+    code = c & valid;                              // everything else -> 0 (alphabet[], param.cpp:210)
+    valid &= 0x01010101u;
+}
+// byte-wise 2-bit fields (first base in the low byte) -> 8 bits, first base most significant
+__device__ __forceinline__ uint32_t squeeze4(uint32_t c) {
+    return ((c & 0x3u) << 6) | ((c >> 4) & 0x30u) | ((c >> 14) & 0xCu) | (c >> 24);
+}
+
+// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask (01 per ACGT base)
+__device__ void pack_chain(const uint8_t *sq, uint32_t stride, int len, int chain, uint32_t *rw, uint32_t *m5) {
+    if (!chain) {
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(sq);          // rows are 16-byte aligned (stride % 16 == 0)
+        #pragma unroll 1
+        for (int j = 0; j < BSX_FIXWORDS; j++) {
+            uint32_t w = 0, m = 0;
+            const int nb = len - 16 * j;                                 // bases of the read in this word
+            if (nb > 0 && (uint32_t)(16 * j) < stride) {
+                const uint4 q = __ldg(q4 + j);
+                uint32_t c, v;
+                codes4(q.x, c, v); w = squeeze4(c) << 24; m = squeeze4(v) << 24;
+                codes4(q.y, c, v); w |= squeeze4(c) << 16; m |= squeeze4(v) << 16;
+                codes4(q.z, c, v); w |= squeeze4(c) << 8; m |= squeeze4(v) << 8;
+                codes4(q.w, c, v); w |= squeeze4(c); m |= squeeze4(v);
+                if (nb < 16) { const uint32_t keep = ~(0xffffffffu >> (2 * nb)); w &= keep; m &= keep; }   // beyond the read: code 0, invalid
+            }
+            rw[j] = w; m5[j] = m;
+        }
+    } else {
+        // reversed read through rev_alphabet (param.cpp:215-218): complement; every non-ACGT byte -> 3
+        #pragma unroll 1
+        for (int j = 0; j < BSX_FIXWORDS; j++) {
+            uint32_t w = 0, m = 0;
+            #pragma unroll 1
+            for (int b = 0; b < 16; b++) {
+                const int i = 16 * j + b;
+                uint32_t code = 0, v = 0;
+                if (i < len) {
+                    const uint32_t ch = sq[len - 1 - i], lc = ch | 0x20u;
+                    v = (lc == 'a') | (lc == 'c') | (lc == 'g') | (lc == 't');
+                    uint32_t x = (ch >> 1) & 3u; x ^= x >> 1;
+                    code = v ? 3u - x : 3u;
+                }
+                w = (w << 2) | code; m = (m << 2) | v;
+            }
+            rw[j] = w; m5[j] = m;
+        }
+    }
+}
+
+// TrimAdapter (align.cpp:371-425): adapters in -A order, positions ascending, first success wins
+__device__ int trim_adapter(const MapArgs &A, const uint8_t *sq, int len) {
+    const int s = A.s, tail = A.rrbs ? 5 : 4;
+    #pragma unroll 1
+    for (int a = 0; a < A.n_adapter; a++) {
+        const int al = A.adapter_len[a];
+        #pragma unroll 1
+        for (int pos = s; pos < len - tail; pos++) {
+            int m0 = 0, k = 0;
+            #pragma unroll 1
+            for (; k < al && k < 15 && pos + k < len; k++) {
+                m0 += (A.adapter[a][k] != (char)sq[pos + k]);
+                if (m0 > 4) break;
+            }
+            bool ok = false;
+            if (!A.rrbs) ok = (k >= m0 * 5 && k > 3);
+            else if (k >= m0 * 5) {
+                // digestion-site remnant just before the adapter (align.cpp:383-404)
+                const int sl = A.site_len, dp = A.digest_pos;
+                int m = m0, m2 = m0;
+                #pragma unroll 1
+                for (int t = 0; t < sl - dp; t++) {
+                    const char x = A.digest_site[t], y = (char)sq[pos - sl + dp + t];
+                    m += (x != y) && (x != 'C' || y != 'T');
+                    m2 += (x != y) && (x != 'G' || y != 'A');
+                }
+                ok = (k >= m * 5) || (A.pairend && k >= m2 * 5);
+            }
+            if (ok) return pos;
+        }
+    }
+    return len;
+}
+
+// seed_array[p] (align.cpp:101-105): 3-letter key of the seed starting at read offset p
+__device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const uint32_t *rw, int p) {
+    const int j = p >> 4, sh = (p & 15) * 2;
+    const uint32_t hi = rw[j], lo = (j + 1 < BSX_FIXWORDS) ? rw[j + 1] : 0u;
+    const uint32_t v = __funnelshift_l(lo, hi, sh) >> (32 - 2 * A.s);
+    return bsx_xt(v & A.seed_bits, A.s);
+}
+
+// Seed probing and selection for one chain; writes plan[] / flank[] of the image, returns the number of probes.
+__device__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *rw, const uint32_t *m5, int len, int seg, int chain,
+                            uint4 *plan, uint4 *flank, uint32_t *dbg) {
+    const int s = A.s, I = A.I;
+    const bool rrbs = A.rrbs != 0;
+    const int mo = (rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
+    const int cso = (rrbs && chain) ? (int)K->remof[len] : 0;                     // cseed_offset (RRBS rc chain)
+    const int lim = I - 1 + mo;
+    const int w = min(lim + 1, s);                                                // probed offsets per segment (the last one takes the tail)
+    // per probed offset, indexed n*w + (p - n*s): list start, rc start, list "size" (index2[key][0])
+    uint32_t st[BSX_MAX_KEYS + 16], md[BSX_MAX_KEYS + 16], sz[BSX_MAX_KEYS + 16];
+    uint32_t T[16 * 16];
+    int arr[16], order[16];
+    int np = 0;
+    // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset] (profile.a - i lies
+    //    in [n*s, n*s+I-1]).  The union of those ranges is probed once.
+    #pragma unroll 1
+    for (int n = 0; n < seg; n++) {
+        const int rmax = rrbs ? 0 : (n == seg - 1 ? lim : w - 1);
+        #pragma unroll 1
+        for (int r = 0; r <= rmax; r++) {
+            const int p = rrbs ? cso + n * s : n * s + r, idx = rrbs ? n : n * w + r;
+            uint32_t a0 = 0, a1 = 0, zz = 0;
+            if (p + s <= len) {
+                const uint32_t key = seed_key(A, rw, p);
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
+                const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
+                const uint32_t cnt = e - a.x;
+                a0 = a.x; a1 = a.y;
+                zz = rrbs ? cnt : (cnt ? cnt + 2 : 0u);        // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
+                np++;
+            }
+            st[idx] = a0; md[idx] = a1; sz[idx] = zz;
+        }
+    }
+    // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset o <= max_offset
+    if (!rrbs) {
+        #pragma unroll 1
+        for (int n = 0; n < seg; n++)
+            #pragma unroll 1
+            for (int o = 0; o <= mo; o++) {
+                uint32_t tt = 0;
+                #pragma unroll 1
+                for (int k = 0; k < I; k++) tt += sz[n * w + ((int)K->profA[n * 16 + k] + o - k - n * s)];
+                T[n * 16 + o] = tt;
+            }
+    }
+    // 3. ReorderSeed (align.cpp:454-468): global offset = FIRST minimum of GetTotalSeedLoc over [0, max_offset)
+    int og = 0;                                  // App. B Q4: defined as 0 when the loop is empty
+    if (!rrbs && mo > 1) {
+        uint32_t best = 0xffffffffu;
+        #pragma unroll 1
+        for (int o = 0; o < mo; o++) {
+            uint32_t tt = 0;
+            #pragma unroll 1
+            for (int n = 0; n < seg; n++) tt += T[n * 16 + o];
+            if (tt < best) { best = tt; og = o; }
+        }
+    }
+    // AdjustSeedStartArray (align.cpp:506-528)
+    #pragma unroll 1
+    for (int n = 0; n < seg; n++) arr[n] = og;
+    if (!rrbs) {
+        #pragma unroll 1
+        for (int i = 0; i < seg; i++) {
+            const int ptr = (i & 1) == 0 ? i / 2 : seg - 1 - i / 2;
+            uint32_t total = 0xffffffffu;
+            const int start = (ptr == 0) ? 0 : arr[ptr - 1];
+            const int end = (ptr == seg - 1) ? mo : arr[ptr + 1];
+            int bi = start;
+            #pragma unroll 1
+            for (int ii = start; ii <= end; ii++) {
+                const uint32_t tt = T[ptr * 16 + ii];
+                if (tt < total) { total = tt; bi = ii; }
+            }
+            arr[ptr] = bi;
+        }
+    }
+    // seedindex: (sum of list sizes, segment) ascending (align.cpp:474-485)
+    #pragma unroll 1
+    for (int n = 0; n < seg; n++) {
+        const uint32_t mine = rrbs ? sz[n] : T[n * 16 + arr[n]];
+        int rank = 0;
+        #pragma unroll 1
+        for (int m = 0; m < seg; m++) {
+            const uint32_t other = rrbs ? sz[m] : T[m * 16 + arr[m]];
+            rank += (other < mine) || (other == mine && m < n);
+        }
+        order[rank] = n;
+    }
+    if (dbg) {
+        dbg[chain * 20] = (uint32_t)seg;
+        for (int n = 0; n < seg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)order[n]; }
+    }
+    // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode;
+    // flank: the read bases / valid mask that face an entry's inline context, [p-16, p) and [p+s, p+s+16)
+    const int per = rrbs ? 1 : I;
+    #pragma unroll 1
+    for (int m = 0; m < seg; m++) {
+        const int sg = order[m];
+        #pragma unroll 1
+        for (int k = 0; k < per; k++) {
+            const int p = rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + arr[sg] - k);
+            const int idx = rrbs ? sg : sg * w + (p - sg * s);
+            const uint32_t st0 = st[idx], sz0 = sz[idx];
+            const uint32_t en0 = st0 + (rrbs ? sz0 : (sz0 ? sz0 - 2u : 0u));
+            plan[m * per + k] = make_uint4(st0, md[idx], en0, (uint32_t)p | ((uint32_t)sg << 16));
+            if (!rrbs) {
+                const int xb = p - 16, xa = p + s;
+                uint32_t rb = 0, mb = 0;
+                if (xb >= 0) {
+                    const int j = xb >> 4, sh = (xb & 15) * 2;
+                    rb = __funnelshift_l(rw[j + 1], rw[j], sh);      // j + 1 <= 9 because p <= 144
+                    mb = __funnelshift_l(m5[j + 1], m5[j], sh);
+                } else if (xb > -16) {                                // fewer than 16 bases before the seed
+                    rb = rw[0] >> (2 * (-xb)); mb = m5[0] >> (2 * (-xb));
+                }
+                const int j = xa >> 4, sh = (xa & 15) * 2;
+                const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? rw[j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? m5[j + 1] : 0u;
+                const uint32_t r0 = (j < BSX_FIXWORDS) ? rw[j] : 0u, m0 = (j < BSX_FIXWORDS) ? m5[j] : 0u;
+                flank[m * per + k] = make_uint4(rb, mb, __funnelshift_l(r1, r0, sh), __funnelshift_l(m1, m0, sh));
+            }
+        }
+    }
+    return np;
+}
+
+// Prepare unit `u` (read r, mate) into the image at `img`; returns the number of table probes.
+// noinline on purpose: called once per 32 units, with its own register allocation.
+__device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, uint32_t u, uint8_t *img) {
+    const PrepSm &K = *Kp;
+    int np = 0;
+    {
+        const uint32_t r = A.mates == 2 ? u >> 1 : u;
+        const int mate = A.mates == 2 ? (int)(u & 1u) : 0;
+        const uint8_t *sq = (mate ? A.seq_b : A.seq_a) + (size_t)r * A.stride;
+        int len = (mate ? A.len_b : A.len_a)[r];
+        if (len > A.max_readlen) len = A.max_readlen;                       // reads.cpp:115-117
+        if (len > BSX_MAX_READLEN) len = BSX_MAX_READLEN;
+        if (len > (int)A.stride) len = (int)A.stride;
+        const int readset = A.mates == 2 ? mate + 1 : A.readset;
+        ReadSm *G = reinterpret_cast<ReadSm *>(img);
+        uint4 *plan0 = reinterpret_cast<uint4 *>(img + sizeof(ReadSm));
+        const int raw = len;
+        len = trim_adapter(A, sq, len);
+        const int fc = A.chains || (readset < 2), cc = A.chains || (readset == 2);   // flag_chain / cflag_chain (align.cpp:93-94)
+        int filtered = len < A.s, rmsn = 0, seg = 0;
+        uint32_t rw[2][BSX_FIXWORDS], m5[2][BSX_FIXWORDS];
+        if (!filtered) {
+            if (fc) pack_chain(sq, A.stride, len, 0, rw[0], m5[0]);
+            if (cc) pack_chain(sq, A.stride, len, 1, rw[1], m5[1]);
+            int nv = 0;
+            #pragma unroll 1
+            for (int j = 0; j < BSX_FIXWORDS; j++) nv += __popc(m5[fc ? 0 : 1][j]);
+            if (len - nv > A.max_ns) filtered = 1;                           // CountNs (align.cpp:48-55)
+        }
+        if (!filtered) {
+            // read_max_snp_num = (v+1)*(len-1)/raw_readlen (align.cpp:586); equals v for an untrimmed read longer than v
+            rmsn = (len == raw && A.v + 1 <= len) ? A.v : (int)((unsigned)(A.v + 1) * (unsigned)(len - 1) / (unsigned)raw);
+            const int q = len - A.I + 1;
+            seg = q > 0 ? min((int)K.segof[q], rmsn + 1) : 0;               // seedseg_num (align.cpp:440)
+            uint32_t *dbg = A.debug ? A.debug + (size_t)r * 40 : nullptr;
+            #pragma unroll 1
+            for (int chain = 0; chain < 2; chain++) {
+                if (chain == 0 ? !fc : !cc) continue;
+                uint4 *plan = plan0 + chain * A.chain_stride;
+                np += select_seeds(A, &K, rw[chain], m5[chain], len, seg, chain, plan, plan + A.flank_off, dbg);
+                #pragma unroll 1
+                for (int j = 0; j < BSX_FIXWORDS; j++) { G->rw[chain][j] = rw[chain][j]; G->m5[chain][j] = m5[chain][j]; }
+            }
+        }
+        uint4 *z = reinterpret_cast<uint4 *>(G->nh);                        // nh[16], nc[16] = 0
+        z[0] = z[1] = z[2] = z[3] = make_uint4(0, 0, 0, 0);
+        G->raw = raw; G->seedseg = seg; G->readset = readset; G->filtered = filtered;
+        G->index = A.first_index + r;
+        G->len = len; G->rmsn = rmsn; G->nw = (len + 15) >> 4;
+        G->thres = (uint32_t)rmsn; G->fc = fc; G->cc = cc; G->dn = 0; G->best = 99;
+    }
+    return np;
+}
+
+}  // namespace
