@@ -54,6 +54,18 @@
 #ifndef BSX_PIPE
 #define BSX_PIPE 1              // software-pipeline the inline-context loads one step ahead
 #endif
+#ifndef BSX_STREAM_NOALLOC
+#define BSX_STREAM_NOALLOC 1    // list entries bypass L1 (measured +2 %: L1 keeps the prepare phase's local arrays)
+#endif
+#ifndef BSX_LIST_PIPE
+#define BSX_LIST_PIPE 0         // 1 (WGBS-only kernels): request the next step's inline context before evaluating the current one
+#endif
+#ifndef BSX_COOP_FULL
+#define BSX_COOP_FULL 4         // n > 0: up to n phase-0/1 survivors of a step are counted cooperatively, two per round trip
+#endif
+#ifndef BSX_PF_NEXT
+#define BSX_PF_NEXT 0           // 1: L2-prefetch the head of the next list of the mode, 2: also across modes
+#endif
 #ifndef BSX_SE_MIN_CTAS
 #define BSX_SE_MIN_CTAS 5
 #endif
@@ -74,6 +86,17 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, const MapArgs &A
 }
 __device__ __forceinline__ uint4 *flank_of(ReadSm *R, int chain, const MapArgs &A) {
     return plan_of(R, chain, A) + A.flank_off;
+}
+
+// list entries are read once: keep them out of L1, which holds the prepare phase's per-lane arrays (local memory)
+__device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
+#if BSX_STREAM_NOALLOC
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
 }
 
 __device__ __forceinline__ const CtaSm *cta_tables() {   // the CTA's tables sit at the start of dynamic shared memory
@@ -283,6 +306,34 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
     const unsigned pm1 = __ballot_sync(BSX_FULL, pass);
     unsigned pm = 0;
     if (pm1) {
+#if BSX_COOP_FULL
+        if (__popc(pm1) <= BSX_COOP_FULL) {
+            // few survivors (the usual case): the warp counts them two at a time, lanes 16g + j taking word j of
+            // survivor g -- one memory round trip per pair instead of a serial walk over the window per lane
+            const int nw = R->nw, j = lane & 15, g = lane >> 4;
+            unsigned left = pm1;
+            #pragma unroll 1
+            while (left) {
+                const int s0 = __ffs(left) - 1; left &= left - 1;
+                const int s1 = left ? __ffs(left) - 1 : -1; if (left) left &= left - 1;
+                const int src = g ? s1 : s0;
+                const uint32_t loc_g = __shfl_sync(BSX_FULL, loc, src < 0 ? 0 : src);
+                const uint32_t strand_g = __shfl_sync(BSX_FULL, strand, src < 0 ? 0 : src);
+                uint32_t wj = 0;
+                if (src >= 0 && j < nw) {
+                    const uint32_t *rp = (strand_g ? A.crefcat : A.refcat) + (loc_g >> 4) + j;
+                    const uint32_t a = __ldg(rp), b = __ldg(rp + 1);
+                    wj = __popc(bsx_mm_word_bits(R->rw[chain][j], R->m5[chain][j], __funnelshift_l(b, a, (loc_g & 15u) * 2u)));
+                }
+#pragma unroll
+                for (int d = 8; d; d >>= 1) wj += __shfl_xor_sync(BSX_FULL, wj, d);
+                const uint32_t w0 = __shfl_sync(BSX_FULL, wj, 0), w1 = __shfl_sync(BSX_FULL, wj, 16);
+                if (lane == s0) w = w0;
+                if (lane == s1) w = w1;
+            }
+            if (pass) pass = w <= R->thres;
+        } else
+#endif
         if (pass) {
             w = full_mismatch(R, chain, R->nw, refbase, loc, R->thres);
             pass = w <= R->thres;
@@ -331,9 +382,87 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
         uint32_t tbl = 0; bool have_tbl = false;
         uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
         int ret = 0;
+#if BSX_LIST_PIPE
+        // WGBS, software-pipelined over the (list, 64-entry step) pairs of the mode: the inline context of the NEXT
+        // step -- usually the head of the next list, lists being ~1.4 steps long -- is requested before the current
+        // step is evaluated, so the warp waits for one memory round trip per mode rather than one per list.
+        {
+            int ni = 0; uint32_t nex = 0, nez = 0;                        // next step: list index, its bounds, offset
+            #pragma unroll 1
+            for (; ni < per; ni++) { const uint4 t = plan[ni]; nex = t.x; nez = t.z; if (nex != nez) break; }
+            uint32_t nc0 = nex;
+            uint2 nx0 = make_uint2(0, 0), nx1 = make_uint2(0, 0);
+            if (ni < per) {
+                const uint32_t j0 = nc0 + (uint32_t)lane;
+                if (j0 < nez) nx0 = ld_stream(A.ctx + j0);
+                if (j0 + 32u < nez) nx1 = ld_stream(A.ctx + j0 + 32u);
+            }
+            int li = -1;
+            uint4 e = make_uint4(0, 0, 0, 0);
+            uint32_t rb = 0, mb = 0, ra = 0, ma = 0, thres = R->thres;
+            #pragma unroll 1
+            while (ni < per) {
+                if (ni != li) {                                          // first step of a list: its bounds and flanks
+                    li = ni; e = plan[li];
+                    const uint4 f = flank[li];
+                    rb = f.x; mb = f.y; ra = f.z; ma = f.w;
+                }
+                const uint32_t c0 = nc0;
+                const uint2 cx0 = nx0, cx1 = nx1;
+                nc0 = c0 + 64u;
+                if (nc0 >= e.z) {                                        // the next step opens the next non-empty list
+                    #pragma unroll 1
+                    for (ni = li + 1; ni < per; ni++) { const uint4 t = plan[ni]; nex = t.x; nez = t.z; if (nex != nez) break; }
+                    nc0 = nex;
+                }
+                if (ni < per) {
+                    const uint32_t j0 = nc0 + (uint32_t)lane;
+                    if (j0 < nez) nx0 = ld_stream(A.ctx + j0);
+                    if (j0 + 32u < nez) nx1 = ld_stream(A.ctx + j0 + 32u);
+                }
+                const uint32_t i0 = c0 + (uint32_t)lane, i1 = i0 + 32u;
+                bool pass0 = false, pass1 = false;
+                if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
+                if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
+                uint32_t exit_pos = 0;
+                if (__any_sync(BSX_FULL, pass0 || pass1)) {
+                    const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+                    const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
+                    if (use_p1 && !have_tbl) {
+                        int zlo = 1000, zhi = -1;
+                        if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
+#pragma unroll
+                        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+                        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+                        tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
+                        have_tbl = true;
+                    }
+#pragma unroll 1
+                    for (int h = 0; h < 2; h++) {
+                        if (h ? pm1 : pm0) {
+                            const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, e.w & 0xffffu, tbl, use_p1, lane, C);
+                            if (rc & 1) { ret = 1; exit_pos = (c0 - e.x) + 32u * h + (uint32_t)(rc >> 8) + 1u; break; }
+                        }
+                    }
+                    thres = R->thres;
+                }
+                if (ret) { visited += min(c0 + 64u, e.z) - e.x; counted += exit_pos; break; }
+                if (c0 + 64u >= e.z) { visited += e.z - e.x; counted += e.z - e.x; }
+            }
+        }
+#else
         #pragma unroll 1
         for (int i = 0; i < per && !ret; i++) {
             const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
+#if BSX_PF_NEXT
+            // the kernel waits on the first load of every list: start the next list's head on its way to L2 now
+            // (plan[] is contiguous over modes, so plan[i + 1] of the last sub-seed is the next mode's first list)
+            if (!BSX_RRBS(A) && (i + 1 < per || (BSX_PF_NEXT > 1 && mode + 1 < R->seedseg))) {
+                const uint4 en = plan[i + 1];
+                const uint32_t a0 = en.x + 16u * (uint32_t)lane;
+                if (lane < 4 && a0 < en.z) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.ctx + a0));
+            }
+#endif
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
             const uint32_t p = e.w & 0xffffu;
             uint32_t rb = 0, mb = 0, ra = 0, ma = 0, want = 0;
@@ -354,8 +483,8 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                     const uint32_t i0 = c0 + lane, i1 = i0 + 32;
                     bool pass0 = false, pass1 = false;
                     uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0);
-                    if (i0 < e.z) cx0 = __ldg(A.ctx + i0);
-                    if (i1 < e.z) cx1 = __ldg(A.ctx + i1);
+                    if (i0 < e.z) cx0 = ld_stream(A.ctx + i0);
+                    if (i1 < e.z) cx1 = ld_stream(A.ctx + i1);
                     if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
                     if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
                     if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
@@ -428,6 +557,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                 }
             }
         }
+#endif  // BSX_LIST_PIPE
         // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
         // entries evaluated past an exit point count as over-fetch
         if (lane == 0) {
