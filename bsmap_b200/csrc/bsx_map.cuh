@@ -40,6 +40,7 @@ struct MapArgs {
     uint32_t *debug;              // optional: per read 40 u32 of seed-selection state (tests)
     uint8_t *prep;                // prepared-unit images: [warp][32] x read_smem bytes (bsx_prep.cuh)
     int mates;                    // units per read: 1 (SE) or 2 (PE)
+    uint32_t block_units;         // units a warp prepares per work-counter atomic: 32, fewer for small batches (balance)
 };
 
 // One prepared read: written to global memory in the prepare phase (one THREAD per read: trim, filter, pack,

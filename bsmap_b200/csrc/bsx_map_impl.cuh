@@ -632,11 +632,11 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     __syncwarp();
     uint8_t *scratch = A.prep + (size_t)gw * 32u * A.read_smem;
     for (;;) {
-        uint32_t r0 = 0;                        // one atomic hands this warp 32 consecutive reads
-        if (lane == 0) r0 = atomicAdd(A.work_counter, 32u);
+        uint32_t r0 = 0;                        // one atomic hands this warp up to 32 consecutive reads
+        if (lane == 0) r0 = atomicAdd(A.work_counter, A.block_units);
         r0 = __shfl_sync(BSX_FULL, r0, 0);
         if (r0 >= A.n) break;
-        const uint32_t cnt = min(32u, A.n - r0);
+        const uint32_t cnt = min(A.block_units, A.n - r0);
         prepare_block(A, K, scratch, r0, cnt, lane, C);                       // phase A: one lane per read
         #pragma unroll 1
         for (uint32_t i = 0; i < cnt; i++) {                                  // phase B: the warp aligns them one by one
@@ -793,11 +793,11 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     const size_t W1 = (size_t)A.W + 1;
     uint8_t *scratch = A.prep + (size_t)gw * 32u * A.read_smem;
     for (;;) {
-        uint32_t r0 = 0;                        // one atomic hands this warp 16 consecutive pairs = 32 units
-        if (lane == 0) r0 = atomicAdd(A.work_counter, 16u);
+        uint32_t r0 = 0;                        // one atomic hands this warp up to 16 consecutive pairs = 32 units
+        if (lane == 0) r0 = atomicAdd(A.work_counter, A.block_units >> 1);
         r0 = __shfl_sync(BSX_FULL, r0, 0);
         if (r0 >= A.n) break;
-        const uint32_t cnt = min(16u, A.n - r0);
+        const uint32_t cnt = min(A.block_units >> 1, A.n - r0);
         prepare_block(A, K, scratch, r0 * 2u, cnt * 2u, lane, C);             // phase A: one lane per mate
       #pragma unroll 1
       for (uint32_t pi = 0; pi < cnt; pi++) {                                 // phase B: the warp aligns the pairs one by one
