@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from . import lib as _l
-from .lib import PAIR_REC, REC, BsxError, IndexInfo, Params, Stats, check, load, strs
+from .lib import PAIR_REC, REC, BsxError, IndexInfo, MethOpts, Params, Stats, check, load, strs
 
 
 def make_params(s=16, I=4, v=2, w=1000, r=1, m=28, x=500, n=0, pairend=0, S=0, f=5, L=144,
@@ -98,6 +98,15 @@ class Index:
         h = C.c_void_p()
         check(load().bsx_index_create_text_only_from_fasta(C.byref(params), os.fsencode(path), C.byref(h)))
         return cls(params, None, None, -1, _handle=h)
+
+    @classmethod
+    def packed(cls, names, seqs, device: int = 0):
+        """packed reference only (no seed table): enough for Meth, cannot map"""
+        keep = [s if isinstance(s, bytes) else bytes(s) for s in seqs]
+        lens = np.array([len(s) for s in keep], dtype=np.uint32)
+        h = C.c_void_p()
+        check(load().bsx_index_create_packed(len(names), strs(names), strs(keep), lens.ctypes.data, device, C.byref(h)))
+        return cls(make_params(), None, None, device, _handle=h)
 
     def replicate(self, device: int) -> "Index":
         """full replica on another GPU over NVLink (cudaMemcpyPeer): the one-time index broadcast"""
@@ -315,3 +324,56 @@ def emit_pe(index: Index, params: Params, a: Reads, b: Reads, n: int, pr, ra, rb
     w = load().bsx_emit_pe(index.h, C.byref(params), a.h, b.h, n, pr.ctypes.data, ra.ctypes.data, rb.ctypes.data, _ptr(ca), _ptr(cb),
                            threads, fd, fd_unpair, st)
     return w, tuple(st)
+
+
+def meth_opts(unique=False, pair=False, meth0=False, trim_fillin=2, combine_cpg=False, min_depth=1) -> MethOpts:
+    return MethOpts(int(unique), int(pair), int(meth0), int(trim_fillin), int(combine_cpg), int(min_depth))
+
+
+class Meth:
+    """methratio.py's per-position counters on the device (bsx_meth_*)"""
+
+    def __init__(self, index: Index, opts: MethOpts = None):
+        self.index, self.o = index, opts or meth_opts()
+        h = C.c_void_p()
+        check(load().bsx_meth_create(index.h, C.byref(h)))
+        self.h = h
+        self.n_valid = 0
+
+    def add(self, seqs, chr_idx, pos, strand, insert, mate_pos, flags):
+        """seqs: list of bytes (SEQ as printed); strand: bit 0 / 1 = first / second ZS character is '-'"""
+        n = len(seqs)
+        buf, lens = pack_reads(seqs, stride=max(16, (max((len(s) for s in seqs), default=1) + 15) // 16 * 16))
+        arr = lambda a, t: np.ascontiguousarray(np.asarray(a, dtype=t))
+        c, p, st, ins, mt, fl = arr(chr_idx, np.uint32), arr(pos, np.uint32), arr(strand, np.uint8), arr(insert, np.int32), arr(mate_pos, np.int32), arr(flags, np.uint8)
+        nv = C.c_uint64(0)
+        check(load().bsx_meth_add(self.h, C.byref(self.o), n, buf.ctypes.data, buf.shape[1], lens.ctypes.data, c.ctypes.data, p.ctypes.data,
+                                  st.ctypes.data, ins.ctypes.data, mt.ctypes.data, fl.ctypes.data, C.byref(nv)))
+        self.n_valid = nv.value
+        return nv.value
+
+    def counters(self, k: int):
+        """(meth, depth) of reference sequence k"""
+        n = load().bsx_index_seq_size(self.index.h, k)
+        m, d = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        check(load().bsx_meth_download(self.h, C.byref(self.o), k, m.ctypes.data, d.ctypes.data))
+        return m, d
+
+    def write(self, seqs, fd: int, chroms=None, threads=0):
+        keep = [s if isinstance(s, bytes) else bytes(s) for s in seqs]
+        lens = np.array([len(s) for s in keep], dtype=np.uint32)
+        sel = None if chroms is None else np.ascontiguousarray(np.asarray(chroms, dtype=np.uint8))
+        st = (C.c_uint64 * 2)()
+        w = load().bsx_meth_write(self.h, C.byref(self.o), strs(keep), lens.ctypes.data, _ptr(sel), threads, fd, st)
+        return w, (st[0], st[1])
+
+    def close(self):
+        if getattr(self, "h", None) and _l._lib is not None:
+            _l._lib.bsx_meth_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbsmap_b200.so")
 CLI = os.path.join(HERE, "bsmap")
-SOURCES = ["bsx_index.cu", "bsx_map_se.cu", "bsx_map_se_rrbs.cu", "bsx_map_pe.cu", "bsx_api.cu", "bsx_format.cpp", "bsx_reads.cpp", "bsx_cli.cpp"]
+METH_CLI = os.path.join(HERE, "methratio")
+SOURCES = ["bsx_index.cu", "bsx_map_se.cu", "bsx_map_se_rrbs.cu", "bsx_map_pe.cu", "bsx_api.cu", "bsx_meth.cu", "bsx_format.cpp", "bsx_reads.cpp", "bsx_cli.cpp", "bsx_methratio_cli.cpp"]
 HEADERS = ["bsx_common.cuh", "bsx_prep.cuh", "bsx_internal.h", "bsx_map.cuh", "bsx_map_impl.cuh", os.path.join("..", "..", "include", "bsmap_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
@@ -27,11 +28,12 @@ def nvcc() -> str:
 
 
 def stale() -> bool:
-    if not os.path.exists(LIB) or not os.path.exists(CLI):
+    if not os.path.exists(LIB) or not os.path.exists(CLI) or not os.path.exists(METH_CLI):
         return True
     t = min(os.path.getmtime(LIB), os.path.getmtime(CLI))
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, s))]
     deps.append(os.path.join(CSRC, "bsmap_main.cpp"))
+    deps.append(os.path.join(CSRC, "methratio_main.cpp"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -62,13 +64,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    main_cpp = os.path.join(CSRC, "bsmap_main.cpp")
-    if os.path.exists(main_cpp):
-        r = subprocess.run(["g++", "-O2", "-o", CLI, main_cpp, "-L" + HERE, "-lbsmap_b200", "-Wl,-rpath,$ORIGIN"],
-                           capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("bsmap CLI link failed")
+    for exe, src in ((CLI, "bsmap_main.cpp"), (METH_CLI, "methratio_main.cpp")):
+        main_cpp = os.path.join(CSRC, src)
+        if os.path.exists(main_cpp):
+            r = subprocess.run(["g++", "-O2", "-o", exe, main_cpp, "-L" + HERE, "-lbsmap_b200", "-Wl,-rpath,$ORIGIN"],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"{os.path.basename(exe)} CLI link failed")
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

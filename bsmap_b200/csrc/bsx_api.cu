@@ -62,6 +62,21 @@ extern "C" int bsx_index_create(const bsx_params *p, int n_seq, const char *cons
     return BSX_OK;
 }
 
+// Packed reference only (both strands, anchors, sizes) on the device: what bsx_meth needs; no seed table, cannot map.
+extern "C" int bsx_index_create_packed(int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens,
+                                       int device, bsx_index **out) {
+    if (!out || n_seq <= 0 || !names || !seqs || !lens) { bsx_set_error("bsx_index_create_packed: bad argument"); return BSX_ERR_ARG; }
+    int rc = require_device(device); if (rc) return rc;
+    bsx_index *ix = new bsx_index();
+    bsx_params_default(&ix->par);
+    ix->device = device; ix->n_seq = (uint32_t)n_seq; ix->ref_only = true;
+    for (int k = 0; k < n_seq; k++) { ix->names.emplace_back(names[k]); ix->size.push_back(lens[k]); }
+    rc = bsx_index_build_device(ix, seqs);
+    if (rc) { bsx_index_free_device(ix); delete ix; return rc; }
+    *out = ix;
+    return BSX_OK;
+}
+
 // Host-only index for the text layer: names, sizes, anchors, the packed Watson strand (XR:Z / BSP
 // refseq column) and RRBS digestion sites.  It cannot map (device = -1); it exists so that records
 // produced on a GPU node can be formatted elsewhere, and so the formatter is testable without a GPU.
@@ -318,6 +333,7 @@ static int alloc_pe(bsx_mapper *m) {
 extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint32_t max_batch, uint32_t stride, bsx_mapper **out) {
     if (!ix || !p || !out || max_batch == 0) { bsx_set_error("bsx_mapper_create: bad argument"); return BSX_ERR_ARG; }
     if (ix->device < 0) { bsx_set_error("text-only index cannot map: build it with bsx_index_create on a CUDA device"); return BSX_ERR_CUDA; }
+    if (ix->ref_only) { bsx_set_error("packed-reference index (bsx_index_create_packed) has no seed table and cannot map"); return BSX_ERR_ARG; }
     int rc = check_params(p); if (rc) return rc;
     if (stride % 16 != 0 || stride < 16) { bsx_set_error("read stride must be a positive multiple of 16 (got %u)", stride); return BSX_ERR_ARG; }
     if (p->seed_size != ix->par.seed_size || p->index_interval != ix->par.index_interval || p->rrbs != ix->par.rrbs) {

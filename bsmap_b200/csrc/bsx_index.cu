@@ -434,6 +434,12 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs) {
         BSX_CUDA_CHECK(cudaStreamSynchronize(st));   // d_seq is reused
     }
     cudaFree(d_seq);
+    if (ix->ref_only) {   // packed reference only (bsx_index_create_packed): no seed table
+        BSX_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        cudaStreamDestroy(st);
+        return upload_seqinfo(ix);
+    }
 
     // --- blocks (host scan of the ASCII; UnmaskRegion) and RRBS sites (find_CCGG)
     std::vector<bsx_block> blocks;

@@ -21,6 +21,7 @@ struct bsx_index {
     std::vector<uint32_t> anchor;      // ref_anchor, n_seq + 1                  (dbseq.cpp:253-256)
     uint64_t n_words = 0, n_keys = 0, n_entries = 0;
     double build_seconds = 0;
+    bool ref_only = false;             // packed strands only, no seed table (bsx_index_create_packed): cannot map
     // device arrays
     uint32_t *d_refcat = nullptr, *d_crefcat = nullptr;   // 2-bit packed strands, margins zeroed
     uint32_t *d_tab = nullptr;      // 2*n_keys+1: [2k] list start, [2k+1] start of rc part, [2k+2] end

@@ -1,0 +1,245 @@
+// bsx_meth.cu -- methratio.py on the device: per-position methylation counters piled up from
+// the mappings by a warp-per-alignment kernel with global atomics, CpG combining, and the host report writer.
+//
+// Reference: methratio.py.  get_alignment (30-65): filters, fill-in trimming, mate-overlap removal;
+// pile-up (95-118): on a '+' (Watson) hit every reference C under the read counts T as depth and C as
+// meth + depth, on a '-' (Crick) hit every reference G counts A / G; -g (122-131); report (133-154).
+// The reference holds two u32 arrays per chromosome in host memory and walks each read with str.find;
+// here both arrays cover the packed Watson strand of the index in HBM (8 bytes per reference position) and the
+// reference base comes from the 2-bit refcat (non-ACGT packs to A, which is neither C nor G -- same outcome).
+// Not supported: -r (duplicate removal is defined by file order).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <unistd.h>
+#include "bsx_internal.h"
+#include "bsx_common.cuh"
+
+struct bsx_meth {
+    const bsx_index *ix = nullptr;
+    uint32_t *d_meth = nullptr, *d_depth = nullptr;   // n_words * 16 counters each, indexed like refcat bases
+    unsigned long long *d_valid = nullptr;
+    bool combined = false;
+    // staging for bsx_meth_add
+    size_t cap = 0; uint32_t stride = 0;
+    char *d_seq = nullptr; uint16_t *d_len = nullptr; uint32_t *d_chr = nullptr, *d_pos = nullptr;
+    uint8_t *d_strand = nullptr, *d_flags = nullptr; int32_t *d_ins = nullptr, *d_mate = nullptr;
+};
+
+namespace {
+
+__device__ __forceinline__ uint32_t ref_code(const uint32_t *refcat, uint32_t q) { return (refcat[q >> 4] >> (30 - 2 * (q & 15))) & 3u; }
+
+// one warp per alignment
+__global__ void __launch_bounds__(256) meth_pileup_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
+                                                          uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, bsx_meth_opts o, uint32_t n,
+                                                          const char *__restrict__ seqs, uint32_t stride, const uint16_t *__restrict__ lens,
+                                                          const uint32_t *__restrict__ chr, const uint32_t *__restrict__ pos0,
+                                                          const uint8_t *__restrict__ strand, const int32_t *__restrict__ insert,
+                                                          const int32_t *__restrict__ mate_pos, const uint8_t *__restrict__ flags) {
+    const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= n) return;
+    const uint32_t fl = flags[a];
+    if (o.unique && (fl & BSX_METH_SECONDARY)) return;      // methratio.py:35 / 48
+    if (o.pair && !(fl & BSX_METH_PROPER)) return;          // methratio.py:36 / 49
+    const uint32_t k = chr[a];
+    if (k >= n_seq) return;
+    const uint32_t *anchor = seqinfo, *size = seqinfo + n_seq + 1;
+    long long len = lens[a], start = 0, pos = pos0[a];
+    const int st = strand[a], ins = insert[a], N = o.trim_fillin;
+    const bool first_minus = st & 1, second_minus = (st >> 1) & 1;
+    if (N > 0) {                                             // trim fill-in nucleotides (methratio.py:56-63)
+        if (!first_minus && second_minus) len = len - N > 0 ? len - N : 0;                     // '+-': seq[:-N]
+        else if (first_minus && second_minus) { start = N < len ? N : len; len -= start; pos += N; }   // '--': seq[N:], pos + N
+        else if (ins != 0 && len > (long long)abs(ins) - N) {
+            const long long trim = len - ((long long)abs(ins) - N);
+            if (!first_minus) len = len - trim > 0 ? len - trim : 0;                           // '++': seq[:-trim]
+            else { start = trim < len ? trim : len; len -= start; pos += trim; }                // '-+': seq[trim:], pos + trim
+        }
+    }
+    if ((fl & BSX_METH_SAM) && ins > 0) {                    // remove the region overlapped by the mate (methratio.py:64)
+        const long long e = (long long)mate_pos[a] - pos;   // seq[:e] with Python slice semantics
+        if (e < 0) len = len + e > 0 ? len + e : 0; else if (e < len) len = e;
+    }
+    if (pos + len > (long long)size[k]) return;             // methratio.py:105
+    if (lane == 0) atomicAdd(n_valid, 1ull);
+    const uint32_t base = anchor[k] + (uint32_t)pos;
+    const uint32_t match = first_minus ? 2u : 1u;           // '+': C (converted reads show T), '-': G (A)
+    const char cm = first_minus ? 'G' : 'C', cc = first_minus ? 'A' : 'T';
+    const char *sq = seqs + (size_t)a * stride + start;
+    for (int i = lane; i < (int)len; i += 32) {
+        if (ref_code(refcat, base + (uint32_t)i) != match) continue;
+        const char c = sq[i];
+        if (c == cc) atomicAdd(depth + base + i, 1u);
+        else if (c == cm) { atomicAdd(meth + base + i, 1u); atomicAdd(depth + base + i, 1u); }
+    }
+}
+
+// -g: every reference "CG": both counters of the C take the G's, the G's become 0 (methratio.py:122-131)
+__global__ void meth_combine_kernel(const uint32_t *__restrict__ refcat, uint64_t n_pos, uint32_t *meth, uint32_t *depth) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q + 1 >= n_pos) return;
+    if (ref_code(refcat, (uint32_t)q) == 1u && ref_code(refcat, (uint32_t)q + 1u) == 2u) {
+        depth[q] += depth[q + 1]; meth[q] += meth[q + 1];
+        depth[q + 1] = 0; meth[q + 1] = 0;
+    }
+}
+
+int ensure_staging(bsx_meth *m, size_t n, uint32_t stride) {
+    if (n <= m->cap && stride <= m->stride) return BSX_OK;
+    cudaFree(m->d_seq); cudaFree(m->d_len); cudaFree(m->d_chr); cudaFree(m->d_pos); cudaFree(m->d_strand); cudaFree(m->d_flags); cudaFree(m->d_ins); cudaFree(m->d_mate);
+    m->cap = std::max(n, m->cap); m->stride = std::max(stride, m->stride);
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_seq, m->cap * m->stride));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_len, m->cap * 2));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_chr, m->cap * 4));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_pos, m->cap * 4));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_strand, m->cap));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_flags, m->cap));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_ins, m->cap * 4));
+    BSX_CUDA_CHECK(cudaMalloc(&m->d_mate, m->cap * 4));
+    return BSX_OK;
+}
+
+int combine_once(bsx_meth *m, const bsx_meth_opts *o) {
+    if (!o->combine_cpg || m->combined) return BSX_OK;
+    const uint64_t n_pos = m->ix->n_words * 16;
+    meth_combine_kernel<<<(unsigned)((n_pos + 255) / 256), 256>>>(m->ix->d_refcat, n_pos, m->d_meth, m->d_depth);
+    BSX_CUDA_CHECK(cudaGetLastError());
+    BSX_CUDA_CHECK(cudaDeviceSynchronize());
+    m->combined = true;
+    return BSX_OK;
+}
+
+struct Sink {
+    std::string *s;
+    void put(const char *p, size_t n) { s->append(p, n); }
+    void putc(char c) { s->push_back(c); }
+    void putu(unsigned long long v) { char b[24]; char *e = b + 24, *q = e; do { *--q = (char)('0' + v % 10); v /= 10; } while (v); put(q, (size_t)(e - q)); }
+    void putf3(double v) { char b[48]; const int l = snprintf(b, sizeof b, "%.3f", v); put(b, (size_t)l); }
+};
+
+}  // namespace
+
+extern "C" void bsx_meth_opts_default(bsx_meth_opts *o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->trim_fillin = 2; o->min_depth = 1;
+}
+
+extern "C" int bsx_meth_create(const bsx_index *ix, bsx_meth **out) {
+    if (!ix || !out) { bsx_set_error("bsx_meth_create: bad argument"); return BSX_ERR_ARG; }
+    if (ix->device < 0) { bsx_set_error("text-only index has no device arrays: methratio needs the index on a CUDA device"); return BSX_ERR_CUDA; }
+    BSX_CUDA_CHECK(cudaSetDevice(ix->device));
+    bsx_meth *m = new bsx_meth();
+    m->ix = ix;
+    const size_t bytes = ix->n_words * 16 * sizeof(uint32_t);
+    if (cudaMalloc(&m->d_meth, bytes) != cudaSuccess || cudaMalloc(&m->d_depth, bytes) != cudaSuccess || cudaMalloc(&m->d_valid, 8) != cudaSuccess) {
+        cudaGetLastError(); bsx_meth_destroy(m); bsx_set_error("bsx_meth_create: out of device memory (%zu bytes per counter array)", bytes); return BSX_ERR_CUDA; }
+    BSX_CUDA_CHECK(cudaMemset(m->d_meth, 0, bytes));
+    BSX_CUDA_CHECK(cudaMemset(m->d_depth, 0, bytes));
+    BSX_CUDA_CHECK(cudaMemset(m->d_valid, 0, 8));
+    *out = m;
+    return BSX_OK;
+}
+
+extern "C" int bsx_meth_destroy(bsx_meth *m) {
+    if (!m) return BSX_OK;
+    cudaFree(m->d_meth); cudaFree(m->d_depth); cudaFree(m->d_valid);
+    cudaFree(m->d_seq); cudaFree(m->d_len); cudaFree(m->d_chr); cudaFree(m->d_pos); cudaFree(m->d_strand); cudaFree(m->d_flags); cudaFree(m->d_ins); cudaFree(m->d_mate);
+    delete m;
+    return BSX_OK;
+}
+
+extern "C" int bsx_meth_add(bsx_meth *m, const bsx_meth_opts *o, uint32_t n, const char *seqs, uint32_t stride,
+                            const uint16_t *lens, const uint32_t *chr, const uint32_t *pos, const uint8_t *strand,
+                            const int32_t *insert, const int32_t *mate_pos, const uint8_t *flags, uint64_t *n_valid) {
+    if (!m || !o || (n && (!seqs || !lens || !chr || !pos || !strand || !insert || !mate_pos || !flags))) { bsx_set_error("bsx_meth_add: bad argument"); return BSX_ERR_ARG; }
+    if (m->combined) { bsx_set_error("bsx_meth_add: counters were already combined (-g); create a new bsx_meth"); return BSX_ERR_ARG; }
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    if (n) {
+        int rc = ensure_staging(m, n, stride); if (rc) return rc;
+        BSX_CUDA_CHECK(cudaMemcpy2D(m->d_seq, m->stride, seqs, stride, stride, n, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_len, lens, (size_t)n * 2, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_chr, chr, (size_t)n * 4, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_pos, pos, (size_t)n * 4, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_strand, strand, n, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_flags, flags, n, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_ins, insert, (size_t)n * 4, cudaMemcpyHostToDevice));
+        BSX_CUDA_CHECK(cudaMemcpy(m->d_mate, mate_pos, (size_t)n * 4, cudaMemcpyHostToDevice));
+        const unsigned blocks = (unsigned)(((uint64_t)n * 32 + 255) / 256);
+        meth_pileup_kernel<<<blocks, 256>>>(m->ix->d_refcat, m->ix->d_seqinfo, m->ix->n_seq, m->d_meth, m->d_depth, m->d_valid, *o, n,
+                                            m->d_seq, m->stride, m->d_len, m->d_chr, m->d_pos, m->d_strand, m->d_ins, m->d_mate, m->d_flags);
+        BSX_CUDA_CHECK(cudaGetLastError());
+    }
+    if (n_valid) {
+        unsigned long long v = 0;
+        BSX_CUDA_CHECK(cudaMemcpy(&v, m->d_valid, 8, cudaMemcpyDeviceToHost));
+        *n_valid = v;
+    }
+    return BSX_OK;
+}
+
+extern "C" int bsx_meth_download(bsx_meth *m, const bsx_meth_opts *o, uint32_t k, uint32_t *meth, uint32_t *depth) {
+    if (!m || !o || k >= m->ix->n_seq) { bsx_set_error("bsx_meth_download: bad argument"); return BSX_ERR_ARG; }
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    int rc = combine_once(m, o); if (rc) return rc;
+    const size_t off = m->ix->anchor[k], cnt = m->ix->size[k];
+    if (meth) BSX_CUDA_CHECK(cudaMemcpy(meth, m->d_meth + off, cnt * 4, cudaMemcpyDeviceToHost));
+    if (depth) BSX_CUDA_CHECK(cudaMemcpy(depth, m->d_depth + off, cnt * 4, cudaMemcpyDeviceToHost));
+    return BSX_OK;
+}
+
+extern "C" size_t bsx_meth_write(bsx_meth *m, const bsx_meth_opts *o, const char *const *seqs, const uint32_t *lens,
+                                 const uint8_t *chroms, int threads, int fd, uint64_t *stats) {
+    if (!m || !o || !seqs || !lens) { bsx_set_error("bsx_meth_write: bad argument"); return 0; }
+    const bsx_index *ix = m->ix;
+    threads = bsx_host_threads(threads);
+    size_t written = 0;
+    auto out = [&](const std::string &s) { size_t off = 0; while (off < s.size()) { ssize_t w = write(fd, s.data() + off, s.size() - off); if (w <= 0) return; off += (size_t)w; written += (size_t)w; } };
+    out("chr\tpos\tstrand\tcontext\tratio\ttotal_C\tmethy_C\tCI_lower\tCI_upper\n");
+    std::vector<uint32_t> order;
+    for (uint32_t k = 0; k < ix->n_seq; k++) if (!chroms || chroms[k]) order.push_back(k);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ix->names[a] < ix->names[b]; });   // sorted(depth.keys())
+    uint64_t nc = 0, nd = 0;
+    const double z95 = 1.96, z95sq = 1.96 * 1.96;
+    std::vector<uint32_t> hm, hd;
+    for (uint32_t k : order) {
+        const uint32_t L = ix->size[k];
+        if (lens[k] != L) { bsx_set_error("bsx_meth_write: sequence %u has %u bases, the index %u", k, lens[k], L); return written; }
+        hm.resize(L); hd.resize(L);
+        if (bsx_meth_download(m, o, k, hm.data(), hd.data()) != BSX_OK) return written;
+        const char *rs = seqs[k];
+        const std::string &name = ix->names[k];
+        std::vector<std::string> chunk((size_t)threads);
+        std::vector<uint64_t> cnc((size_t)threads, 0), cnd((size_t)threads, 0);
+        bsx_parallel(threads, L, [&](int t, size_t b, size_t e) {
+            Sink s{&chunk[t]};
+            uint64_t lc = 0, ld = 0;
+            for (size_t i = b; i < e; i++) {
+                const uint32_t d = hd[i];
+                if ((long long)d < (long long)o->min_depth || d == 0) continue;
+                lc++; ld += d;
+                const uint32_t mm = hm[i];
+                if (mm == 0 && !o->meth0) continue;
+                const double ratio = (double)mm / d;
+                s.put(name.data(), name.size()); s.putc('\t'); s.putu(i + 1); s.putc('\t');
+                const char rc = (char)(rs[i] >= 'a' && rs[i] <= 'z' ? rs[i] - 32 : rs[i]);
+                s.putc(rc == 'C' ? '+' : '-'); s.putc('\t');
+                if (i >= 2) for (size_t j = i - 2; j < i + 3 && j < L; j++) s.putc((char)(rs[j] >= 'a' && rs[j] <= 'z' ? rs[j] - 32 : rs[j]));   // refcr[i-2:i+3] ('' when i < 2)
+                s.putc('\t'); s.putf3(ratio); s.putc('\t'); s.putu(d); s.putc('\t'); s.putu(mm); s.putc('\t');
+                const double pmid = ratio + z95sq / (2 * (double)d);
+                const double sd = z95 * pow(ratio * (1 - ratio) / d + z95sq / (4 * (double)d * d), 0.5);
+                const double nm = 1 + z95sq / d;
+                s.putf3((pmid - sd) / nm); s.putc('\t'); s.putf3((pmid + sd) / nm); s.putc('\n');
+            }
+            cnc[t] = lc; cnd[t] = ld;
+        });
+        for (int t = 0; t < threads; t++) { out(chunk[t]); nc += cnc[t]; nd += cnd[t]; }
+    }
+    if (stats) { stats[0] = nc; stats[1] = nd; }
+    return written;
+}

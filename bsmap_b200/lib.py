@@ -48,6 +48,11 @@ PAIR_REC = np.dtype([("a_loc", "<u4"), ("a_chr", "<u4"), ("b_loc", "<u4"), ("b_c
                      ("insert", "<i4"), ("npairs", "<u4"), ("na", "u1"), ("nb", "u1"),
                      ("chain", "u1"), ("paired", "u1")])
 
+class MethOpts(C.Structure):
+    """bsx_meth_opts (include/bsmap_b200.h): methratio.py's options"""
+    _fields_ = [(k, C.c_int32) for k in ("unique", "pair", "meth0", "trim_fillin", "combine_cpg", "min_depth")]
+
+
 EXPORTS = [
     "bsx_last_error", "bsx_device_count", "bsx_params_default", "bsx_index_create", "bsx_index_create_from_fasta",
     "bsx_index_create_text_only", "bsx_index_create_text_only_from_fasta", "bsx_index_destroy", "bsx_index_get_info", "bsx_index_seq_name", "bsx_index_seq_size", "bsx_index_download",
@@ -58,6 +63,8 @@ EXPORTS = [
     "bsx_format_pe", "bsx_cli_main",
     "bsx_reads_open", "bsx_reads_close", "bsx_reads_kind", "bsx_reads_skip", "bsx_reads_force_token_reader",
     "bsx_reads_next", "bsx_reads_get", "bsx_emit_se", "bsx_emit_pe",
+    "bsx_index_create_packed", "bsx_meth_opts_default", "bsx_meth_create", "bsx_meth_destroy", "bsx_meth_add", "bsx_meth_download",
+    "bsx_meth_write", "bsx_methratio_main",
 ]
 
 _lib = None
@@ -124,6 +131,14 @@ def load():
     L.bsx_emit_se.argtypes = [vp, C.POINTER(Params), vp, u32, i32, vp, vp, i32, i32, C.POINTER(u32)]
     L.bsx_emit_pe.restype = sz
     L.bsx_emit_pe.argtypes = [vp, C.POINTER(Params), vp, vp, u32] + [vp] * 5 + [i32, i32, i32, C.POINTER(u32)]
+    L.bsx_index_create_packed.argtypes = [i32, pp, pp, vp, i32, C.POINTER(vp)]
+    L.bsx_meth_opts_default.argtypes = [C.POINTER(MethOpts)]; L.bsx_meth_opts_default.restype = None
+    L.bsx_meth_create.argtypes = [vp, C.POINTER(vp)]
+    L.bsx_meth_destroy.argtypes = [vp]
+    L.bsx_meth_add.argtypes = [vp, C.POINTER(MethOpts), u32, vp, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+    L.bsx_meth_download.argtypes = [vp, C.POINTER(MethOpts), u32, vp, vp]
+    L.bsx_meth_write.restype = sz
+    L.bsx_meth_write.argtypes = [vp, C.POINTER(MethOpts), pp, vp, vp, i32, i32, C.POINTER(C.c_uint64)]
     if hasattr(L, "bsx_mapper_debug_seeds"):
         L.bsx_mapper_debug_seeds.argtypes = [vp, u32, vp]
     _lib = L

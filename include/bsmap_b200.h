@@ -105,6 +105,7 @@ typedef struct bsx_stats {
 typedef struct bsx_index bsx_index;     /* device-resident 2-bit reference + seed table (RefSeq) */
 typedef struct bsx_mapper bsx_mapper;   /* per-device working set: batch buffers, scratch, streams */
 typedef struct bsx_reads bsx_reads;     /* one FASTA / FASTQ read file (ReadClass, reads.h:26-48) */
+typedef struct bsx_meth bsx_meth;       /* per-position methylation counters on one device (methratio.py:90-93) */
 
 const char *bsx_last_error(void);
 int bsx_device_count(void);
@@ -116,6 +117,9 @@ int bsx_index_create_from_fasta(const bsx_params *p, const char *fasta_path, int
 /* host-only index for the text layer (bsx_format_*): no device arrays, cannot map */
 int bsx_index_create_text_only(const bsx_params *p, int n_seq, const char *const *names,
                                const char *const *seqs, const uint32_t *lens, bsx_index **out);
+/* packed reference only (no seed table): enough for bsx_meth, cannot map */
+int bsx_index_create_packed(int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens,
+                            int device, bsx_index **out);
 int bsx_index_create_text_only_from_fasta(const bsx_params *p, const char *fasta_path, bsx_index **out);
 int bsx_index_destroy(bsx_index *ix);
 int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info);
@@ -202,6 +206,39 @@ size_t bsx_emit_pe(const bsx_index *ix, const bsx_params *p, const bsx_reads *a,
                    const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb,
                    const uint16_t *counts_a, const uint16_t *counts_b, int threads, int fd, int fd_unpair,
                    uint32_t *n_stats /* pairs, single a, single b */);
+
+/* --- methratio.py (methylation ratios from the mappings) on the device -------------------------- */
+typedef struct bsx_meth_opts {   /* methratio.py:5-16; -r (remove duplicates) is not supported */
+    int32_t unique;        /* -u  process only unique mappings / pairs                         */
+    int32_t pair;          /* -p  process only properly paired mappings                        */
+    int32_t meth0;         /* -z  report loci with zero methylation ratios                     */
+    int32_t trim_fillin;   /* -t  trim N end-repairing fill-in nucleotides (default 2)         */
+    int32_t combine_cpg;   /* -g  combine CpG methylation ratios on both strands               */
+    int32_t min_depth;     /* -m  report loci with sequencing depth >= FOLD (default 1)        */
+} bsx_meth_opts;
+#define BSX_METH_SECONDARY 1u   /* alignment flag: not a unique mapping (SAM 's' / BSP flag != UM)      */
+#define BSX_METH_PROPER    2u   /* alignment flag: properly paired       (SAM 'P' / BSP insert != 0)    */
+#define BSX_METH_SAM       4u   /* alignment came from SAM: mate-overlap removal applies (methratio.py:64) */
+void bsx_meth_opts_default(bsx_meth_opts *o);
+/* zeroed meth / depth counters (u32) for every position of the index's Watson strand */
+int bsx_meth_create(const bsx_index *ix, bsx_meth **out);
+int bsx_meth_destroy(bsx_meth *m);
+/* pile up n alignments (methratio.py:30-118).  seqs: SEQ as printed in the SAM / BSP file, `stride` bytes apart;
+ * chr: 0-based index of the reference sequence; pos: 0-based leftmost position; strand: bit 0 = first ZS
+ * character is '-', bit 1 = second is '-'; insert: TLEN (SAM) / insert size (BSP); mate_pos: PNEXT - 1;
+ * flags: BSX_METH_*.  All host arrays.  *n_valid accumulates the "valid mappings" of the script's summary. */
+int bsx_meth_add(bsx_meth *m, const bsx_meth_opts *o, uint32_t n, const char *seqs, uint32_t stride,
+                 const uint16_t *lens, const uint32_t *chr, const uint32_t *pos, const uint8_t *strand,
+                 const int32_t *insert, const int32_t *mate_pos, const uint8_t *flags, uint64_t *n_valid);
+/* copy the counters of sequence k to the host (after -g combining when o->combine_cpg; idempotent) */
+int bsx_meth_download(bsx_meth *m, const bsx_meth_opts *o, uint32_t k, uint32_t *meth, uint32_t *depth);
+/* write the table of methratio.py:133-152 for the sequences selected by `chroms` (NULL = all), sorted by
+ * name, to fd.  seqs / lens: the reference records as in bsx_index_create (needed for the context column).
+ * stats: covered cytosines, their summed depth.  Returns bytes written. */
+size_t bsx_meth_write(bsx_meth *m, const bsx_meth_opts *o, const char *const *seqs, const uint32_t *lens,
+                      const uint8_t *chroms /* n_seq flags or NULL */, int threads, int fd, uint64_t *stats);
+/* the methratio.py command line: -o -d [-c -u -p -z -q -t -g -m] files... (SAM and BSP; -r, -s, .bam refused) */
+int bsx_methratio_main(int argc, char **argv);
 
 /* --- the bsmap command line (main.cpp:441-476): same options, same output files -------------- */
 int bsx_cli_main(int argc, char **argv);
