@@ -7,6 +7,7 @@
 // suffix like the script does.  The files are memory-mapped and parsed on all host threads; the pile-up runs on
 // the GPU (bsx_meth.cu).  Refused with a message: -r (duplicate removal depends on file order), .bam input
 // (needs a BGZF codec), -s (no samtools involved).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -151,7 +152,10 @@ bool parse_line(const char *b, const char *e, bool sam, const std::unordered_map
 
 }  // namespace
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 extern "C" int bsx_methratio_main(int argc, char **argv) {
+    const double t_start = now_s();
     MOpts m; bsx_meth_opts_default(&m.o);
     parse(argc, argv, m);
     if (m.ref.empty()) usage_error("Missing reference file, use -d or --ref option.");
@@ -163,7 +167,9 @@ extern "C" int bsx_methratio_main(int argc, char **argv) {
     std::thread ctx_thread([] { cudaFree(nullptr); });        // the CUDA context comes up while the FASTA is parsed
     std::vector<std::string> names, seqs;
     const int lrc = bsx_load_fasta(m.ref.c_str(), names, seqs);
+    const double t_fa = now_s();
     ctx_thread.join();
+    const double t_ctx = now_s();
     if (lrc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
     // -c: only these chromosomes (methratio.py:74-79); mappings to any other name are skipped
     std::vector<uint8_t> selected(names.size(), 1);
@@ -186,6 +192,7 @@ extern "C" int bsx_methratio_main(int argc, char **argv) {
     if (bsx_index_create_packed((int)seqs.size(), np.data(), sp.data(), ln.data(), 0, &ix) != BSX_OK || bsx_meth_create(ix, &mh) != BSX_OK) {
         fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
 
+    const double t_ix = now_s();
     uint64_t nmap = 0;
     for (const std::string &path : m.files) {
         disp(m, ("reading " + path + " ...").c_str());
@@ -248,6 +255,7 @@ extern "C" int bsx_methratio_main(int argc, char **argv) {
         }
         munmap((void *)p, n); close(fd);
     }
+    const double t_pile = now_s();
     if (m.o.combine_cpg) disp(m, "combining CpG methylation from both strands ...");
     disp(m, ("writing " + m.out + " ...").c_str());
     const int ofd = open(m.out.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
@@ -255,6 +263,9 @@ extern "C" int bsx_methratio_main(int argc, char **argv) {
     uint64_t stats[2] = {0, 0};
     bsx_meth_write(mh, &m.o, sp.data(), ln.data(), selected.data(), threads, ofd, stats);
     close(ofd);
+    if (getenv("BSX_CLI_TIMING"))
+        fprintf(stderr, "[bsx timing] reference FASTA %.3f s || CUDA context (ready at %.3f s), packed reference + counters %.3f s, parse + pile-up %.3f s, report %.3f s\n",
+                t_fa - t_start, t_ctx - t_start, t_ix - t_ctx, t_pile - t_ix, now_s() - t_pile);
     disp(m, "done.");
     printf("total %llu valid mappings, %llu covered cytosines, average coverage: %.2f fold.\n", (unsigned long long)nmap,
            (unsigned long long)stats[0], stats[0] ? (double)stats[1] / (double)stats[0] : 0.0);
