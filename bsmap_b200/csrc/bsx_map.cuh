@@ -63,6 +63,11 @@ struct ReadSm {
 };
 static_assert(sizeof(ReadSm) % 16 == 0, "images are copied as uint4");
 
+// per-warp scratch of the prepare phase: the packed read of each lane's unit, lane-interleaved (no bank conflicts)
+struct PrepCol {
+    uint32_t rw[BSX_FIXWORDS][32], m5[BSX_FIXWORDS][32];
+};
+
 // per-warp scratch of the align kernels
 struct SelSm {
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]
@@ -81,7 +86,7 @@ static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int n
     return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * 2u * sizeof(uint4);
 }
 static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
-    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot) + sizeof(SelSm);
+    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot) + sizeof(SelSm) + sizeof(PrepCol);
 }
 static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
     return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot) * BSX_WARPS_PER_CTA;

@@ -137,9 +137,9 @@ __device__ __forceinline__ void load_image(const MapArgs &A, ReadSm *R, const ui
 }
 
 // Phase A for a block of `cnt` units starting at unit u0: lane i prepares unit u0 + i into image i of the warp's scratch
-__device__ __forceinline__ void prepare_block(const MapArgs &A, const CtaSm *K, uint8_t *scratch, uint32_t u0, uint32_t cnt, int lane, Ctr *C) {
+__device__ __forceinline__ void prepare_block(const MapArgs &A, const CtaSm *K, PrepCol *P, uint8_t *scratch, uint32_t u0, uint32_t cnt, int lane, Ctr *C) {
     int np = 0;
-    if ((uint32_t)lane < cnt) np = bsx_prep_unit(A, K, u0 + (uint32_t)lane, scratch + (size_t)lane * A.read_smem);
+    if ((uint32_t)lane < cnt) np = bsx_prep_unit(A, K, &P->rw[0][lane], &P->m5[0][lane], u0 + (uint32_t)lane, scratch + (size_t)lane * A.read_smem);
 #pragma unroll
     for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
     CTR_ADD(C, CT_PROBE, np);
@@ -624,6 +624,7 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     uint8_t *base = smem + sizeof(CtaSm) + A.warp_smem_se * wid;
     ReadSm *R = reinterpret_cast<ReadSm *>(base);
     SelSm *X = reinterpret_cast<SelSm *>(base + A.read_smem);
+    PrepCol *P = reinterpret_cast<PrepCol *>(base + A.read_smem + sizeof(SelSm));
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
@@ -637,7 +638,7 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
         r0 = __shfl_sync(BSX_FULL, r0, 0);
         if (r0 >= A.n) break;
         const uint32_t cnt = min(A.block_units, A.n - r0);
-        prepare_block(A, K, scratch, r0, cnt, lane, C);                       // phase A: one lane per read
+        prepare_block(A, K, P, scratch, r0, cnt, lane, C);                       // phase A: one lane per read
         #pragma unroll 1
         for (uint32_t i = 0; i < cnt; i++) {                                  // phase B: the warp aligns them one by one
             const uint32_t r = r0 + i;
@@ -775,13 +776,14 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t read_sm = A.read_smem;
-    const size_t per_warp = 2 * read_sm + sizeof(SelSm);
+    const size_t per_warp = 2 * read_sm + sizeof(SelSm) + sizeof(PrepCol);
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
     uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
     ReadSm *Ra = reinterpret_cast<ReadSm *>(base);
     ReadSm *Rb = reinterpret_cast<ReadSm *>(base + read_sm);
     SelSm *X = reinterpret_cast<SelSm *>(base + 2 * read_sm);
+    PrepCol *P = reinterpret_cast<PrepCol *>(base + 2 * read_sm + sizeof(SelSm));
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits_a = A.hit_scratch + (size_t)gw * 2 * A.hit_stride, *hits_b = hits_a + A.hit_stride;
     uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride, *dd_b = dd_a + A.dd_stride;
@@ -798,7 +800,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
         r0 = __shfl_sync(BSX_FULL, r0, 0);
         if (r0 >= A.n) break;
         const uint32_t cnt = min(A.block_units >> 1, A.n - r0);
-        prepare_block(A, K, scratch, r0 * 2u, cnt * 2u, lane, C);             // phase A: one lane per mate
+        prepare_block(A, K, P, scratch, r0 * 2u, cnt * 2u, lane, C);             // phase A: one lane per mate
       #pragma unroll 1
       for (uint32_t pi = 0; pi < cnt; pi++) {                                 // phase B: the warp aligns the pairs one by one
         const uint32_t r = r0 + pi;

@@ -38,8 +38,9 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t c) {
     return ((c & 0x3u) << 6) | ((c >> 4) & 0x30u) | ((c >> 14) & 0xCu) | (c >> 24);
 }
 
-// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask (01 per ACGT base)
-__device__ void pack_chain(const uint8_t *sq, uint32_t stride, int len, int chain, uint32_t *rw, uint32_t *m5) {
+// ConvertBinaySeq (align.cpp:90-162) for one chain: packed words + valid-base mask (01 per ACGT base).
+// rw / m5 point at this lane's column of the warp's shared scratch: word j lives at [j * 32].
+__device__ __forceinline__ void pack_chain(const uint8_t *sq, uint32_t stride, int len, int chain, uint32_t *rw, uint32_t *m5) {
     if (!chain) {
         const uint4 *q4 = reinterpret_cast<const uint4 *>(sq);          // rows are 16-byte aligned (stride % 16 == 0)
         #pragma unroll 1
@@ -55,7 +56,7 @@ __device__ void pack_chain(const uint8_t *sq, uint32_t stride, int len, int chai
                 codes4(q.w, c, v); w |= squeeze4(c); m |= squeeze4(v);
                 if (nb < 16) { const uint32_t keep = ~(0xffffffffu >> (2 * nb)); w &= keep; m &= keep; }   // beyond the read: code 0, invalid
             }
-            rw[j] = w; m5[j] = m;
+            rw[j * 32] = w; m5[j * 32] = m;
         }
     } else {
         // reversed read through rev_alphabet (param.cpp:215-218): complement; every non-ACGT byte -> 3
@@ -74,7 +75,7 @@ __device__ void pack_chain(const uint8_t *sq, uint32_t stride, int len, int chai
                 }
                 w = (w << 2) | code; m = (m << 2) | v;
             }
-            rw[j] = w; m5[j] = m;
+            rw[j * 32] = w; m5[j * 32] = m;
         }
     }
 }
@@ -116,13 +117,13 @@ __device__ int trim_adapter(const MapArgs &A, const uint8_t *sq, int len) {
 // seed_array[p] (align.cpp:101-105): 3-letter key of the seed starting at read offset p
 __device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const uint32_t *rw, int p) {
     const int j = p >> 4, sh = (p & 15) * 2;
-    const uint32_t hi = rw[j], lo = (j + 1 < BSX_FIXWORDS) ? rw[j + 1] : 0u;
+    const uint32_t hi = rw[j * 32], lo = (j + 1 < BSX_FIXWORDS) ? rw[(j + 1) * 32] : 0u;
     const uint32_t v = __funnelshift_l(lo, hi, sh) >> (32 - 2 * A.s);
     return bsx_xt(v & A.seed_bits, A.s);
 }
 
 // Seed probing and selection for one chain; writes plan[] / flank[] of the image, returns the number of probes.
-__device__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *rw, const uint32_t *m5, int len, int seg, int chain,
+__device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *rw, const uint32_t *m5, int len, int seg, int chain,
                             uint4 *plan, uint4 *flank, uint32_t *dbg) {
     const int s = A.s, I = A.I;
     const bool rrbs = A.rrbs != 0;
@@ -246,14 +247,14 @@ __device__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *r
                 uint32_t rb = 0, mb = 0;
                 if (xb >= 0) {
                     const int j = xb >> 4, sh = (xb & 15) * 2;
-                    rb = __funnelshift_l(rw[j + 1], rw[j], sh);      // j + 1 <= 9 because p <= 144
-                    mb = __funnelshift_l(m5[j + 1], m5[j], sh);
+                    rb = __funnelshift_l(rw[(j + 1) * 32], rw[j * 32], sh);      // j + 1 <= 9 because p <= 144
+                    mb = __funnelshift_l(m5[(j + 1) * 32], m5[j * 32], sh);
                 } else if (xb > -16) {                                // fewer than 16 bases before the seed
                     rb = rw[0] >> (2 * (-xb)); mb = m5[0] >> (2 * (-xb));
                 }
                 const int j = xa >> 4, sh = (xa & 15) * 2;
-                const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? rw[j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? m5[j + 1] : 0u;
-                const uint32_t r0 = (j < BSX_FIXWORDS) ? rw[j] : 0u, m0 = (j < BSX_FIXWORDS) ? m5[j] : 0u;
+                const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? rw[(j + 1) * 32] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? m5[(j + 1) * 32] : 0u;
+                const uint32_t r0 = (j < BSX_FIXWORDS) ? rw[j * 32] : 0u, m0 = (j < BSX_FIXWORDS) ? m5[j * 32] : 0u;
                 flank[m * per + k] = make_uint4(rb, mb, __funnelshift_l(r1, r0, sh), __funnelshift_l(m1, m0, sh));
             }
         }
@@ -263,7 +264,9 @@ __device__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *r
 
 // Prepare unit `u` (read r, mate) into the image at `img`; returns the number of table probes.
 // noinline on purpose: called once per 32 units, with its own register allocation.
-__device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, uint32_t u, uint8_t *img) {
+// rw / m5: this lane's column of the warp's PrepCol (shared memory) -- the packed read is indexed by data-dependent
+// word numbers, which as a thread-local array cost one 32-byte sector per access (130 sectors per read).
+__device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, uint32_t *rw, uint32_t *m5, uint32_t u, uint8_t *img) {
     const PrepSm &K = *Kp;
     int np = 0;
     {
@@ -281,14 +284,13 @@ __device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, ui
         len = trim_adapter(A, sq, len);
         const int fc = A.chains || (readset < 2), cc = A.chains || (readset == 2);   // flag_chain / cflag_chain (align.cpp:93-94)
         int filtered = len < A.s, rmsn = 0, seg = 0;
-        uint32_t rw[2][BSX_FIXWORDS], m5[2][BSX_FIXWORDS];
         if (!filtered) {
-            if (fc) pack_chain(sq, A.stride, len, 0, rw[0], m5[0]);
-            if (cc) pack_chain(sq, A.stride, len, 1, rw[1], m5[1]);
+            // CountNs (align.cpp:48-55) from the valid-base mask of the chain the read uses first
+            pack_chain(sq, A.stride, len, fc ? 0 : 1, rw, m5);
             int nv = 0;
             #pragma unroll 1
-            for (int j = 0; j < BSX_FIXWORDS; j++) nv += __popc(m5[fc ? 0 : 1][j]);
-            if (len - nv > A.max_ns) filtered = 1;                           // CountNs (align.cpp:48-55)
+            for (int j = 0; j < BSX_FIXWORDS; j++) nv += __popc(m5[j * 32]);
+            if (len - nv > A.max_ns) filtered = 1;
         }
         if (!filtered) {
             // read_max_snp_num = (v+1)*(len-1)/raw_readlen (align.cpp:586); equals v for an untrimmed read longer than v
@@ -299,10 +301,11 @@ __device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, ui
             #pragma unroll 1
             for (int chain = 0; chain < 2; chain++) {
                 if (chain == 0 ? !fc : !cc) continue;
+                if (chain == 1 && fc) pack_chain(sq, A.stride, len, 1, rw, m5);   // -n 1: the other orientation, same scratch
                 uint4 *plan = plan0 + chain * A.chain_stride;
-                np += select_seeds(A, &K, rw[chain], m5[chain], len, seg, chain, plan, plan + A.flank_off, dbg);
+                np += select_seeds(A, &K, rw, m5, len, seg, chain, plan, plan + A.flank_off, dbg);
                 #pragma unroll 1
-                for (int j = 0; j < BSX_FIXWORDS; j++) { G->rw[chain][j] = rw[chain][j]; G->m5[chain][j] = m5[chain][j]; }
+                for (int j = 0; j < BSX_FIXWORDS; j++) { G->rw[chain][j] = rw[j * 32]; G->m5[chain][j] = m5[j * 32]; }
             }
         }
         uint4 *z = reinterpret_cast<uint4 *>(G->nh);                        // nh[16], nc[16] = 0
