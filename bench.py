@@ -40,7 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L_READ = 100
-STRIDE = 112
+STRIDE = 104      # bytes per read slot: the 100 bases rounded up to the ABI's 8-byte alignment
 OPTS = dict(s=16, v=5, I=4, S=7)
 
 

@@ -335,7 +335,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     if (ix->device < 0) { bsx_set_error("text-only index cannot map: build it with bsx_index_create on a CUDA device"); return BSX_ERR_CUDA; }
     if (ix->ref_only) { bsx_set_error("packed-reference index (bsx_index_create_packed) has no seed table and cannot map"); return BSX_ERR_ARG; }
     int rc = check_params(p); if (rc) return rc;
-    if (stride % 16 != 0 || stride < 16) { bsx_set_error("read stride must be a positive multiple of 16 (got %u)", stride); return BSX_ERR_ARG; }
+    if (stride % 8 != 0 || stride < 16) { bsx_set_error("read stride must be a multiple of 8, at least 16 (got %u)", stride); return BSX_ERR_ARG; }
     if (p->seed_size != ix->par.seed_size || p->index_interval != ix->par.index_interval || p->rrbs != ix->par.rrbs) {
         bsx_set_error("mapper parameters (-s/-I/-D) differ from the index they were built with"); return BSX_ERR_ARG; }
     if (p->rrbs && (p->pairend || p->chains) != (ix->par.pairend || ix->par.chains)) {

@@ -42,13 +42,15 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t c) {
 // rw / m5 point at this lane's column of the warp's shared scratch: word j lives at [j * 32].
 __device__ __forceinline__ void pack_chain(const uint8_t *sq, uint32_t stride, int len, int chain, uint32_t *rw, uint32_t *m5) {
     if (!chain) {
-        const uint4 *q4 = reinterpret_cast<const uint4 *>(sq);          // rows are 16-byte aligned (stride % 16 == 0)
+        const uint2 *q2 = reinterpret_cast<const uint2 *>(sq);          // rows are 8-byte aligned (stride % 8 == 0)
         #pragma unroll 1
         for (int j = 0; j < BSX_FIXWORDS; j++) {
             uint32_t w = 0, m = 0;
             const int nb = len - 16 * j;                                 // bases of the read in this word
             if (nb > 0 && (uint32_t)(16 * j) < stride) {
-                const uint4 q = __ldg(q4 + j);
+                const uint2 lo = __ldg(q2 + 2 * j);
+                const uint2 hi = (uint32_t)(16 * j + 8) < stride ? __ldg(q2 + 2 * j + 1) : make_uint2(0u, 0u);
+                const uint4 q = make_uint4(lo.x, lo.y, hi.x, hi.y);
                 uint32_t c, v;
                 codes4(q.x, c, v); w = squeeze4(c) << 24; m = squeeze4(v) << 24;
                 codes4(q.y, c, v); w |= squeeze4(c) << 16; m |= squeeze4(v) << 16;

@@ -12,7 +12,7 @@
  * entry point fails with BSX_ERR_CUDA when no CUDA device is usable.
  *
  * Data layout
- *   reads   : ASCII, one read per `stride` bytes (stride % 16 == 0, stride >= longest read), plus
+ *   reads   : ASCII, one read per `stride` bytes (stride % 8 == 0, stride >= 16 and >= longest read), plus
  *             uint16 lengths.  Reads longer than max_readlen are truncated (reads.cpp:115-117).
  *   records : fixed-size bsx_rec / bsx_pair_rec, the decision StringAlign / StringAlignPair makes
  *             before any text is produced; text formatting (s_OutHit & co) is host code in the same

@@ -83,21 +83,21 @@ def test_index_matches_oracle(name):
     ix.close(); oref.close()
 
 
-def _run_gpu(case, max_batch=4096):
+def _run_gpu(case, max_batch=4096, stride=160):
     d = case.data()
     p = B.make_params(**case.param_kwargs())
     ix = B.Index(p, d["gnames"], d["gseqs"])
-    mp = B.Mapper(ix, p, max_batch=max_batch, stride=160)
+    mp = B.Mapper(ix, p, max_batch=max_batch, stride=stride)
     out = {}
     head = ix.header() if p.out_sam else b""
     if not case.paired:
-        buf, lens = B.pack_reads(R.clip(case, d["seqs"]), stride=160)
+        buf, lens = B.pack_reads(R.clip(case, d["seqs"]), stride=stride)
         recs, counts = mp.map_se(buf, lens)
         txt, na = mp.format_se(d["names"], d["seqs"], R.case_quals(case), recs, counts)
         out.update(main=head + txt, unpair=b"", recs=recs, counts=counts, n_aligned=na)
     else:
-        ba, la = B.pack_reads(R.clip(case, d["seqs"]), stride=160)
-        bb, lb = B.pack_reads(R.clip(case, d["seqs_b"]), stride=160)
+        ba, la = B.pack_reads(R.clip(case, d["seqs"]), stride=stride)
+        bb, lb = B.pack_reads(R.clip(case, d["seqs_b"]), stride=stride)
         pr, ra, rb, ca, cb = mp.map_pe(ba, la, bb, lb)
         txt, un, st = mp.format_pe(d["names"], d["seqs"], d["quals"], d["names_b"], d["seqs_b"], d["quals_b"], pr, ra, rb, ca, cb)
         out.update(main=head + txt, unpair=un, pr=pr, ra=ra, rb=rb, ca=ca, cb=cb, n_aligned=st)
@@ -105,6 +105,17 @@ def _run_gpu(case, max_batch=4096):
     out["launches"] = mp.launches
     mp.close(); ix.close()
     return out
+
+
+@pytest.mark.parametrize("name", ["se_cfg2_r0_uR", "pe_sam", "se_n1"])
+def test_read_stride_is_only_8_byte_aligned(name):
+    """100-nt reads in 104-byte slots (the bench layout): same records and text as in 160-byte slots"""
+    case = CS.BY_NAME[name]
+    a, b = _run_gpu(case), _run_gpu(case, stride=104)
+    assert a["main"] == b["main"] and a["unpair"] == b["unpair"]
+    assert a["main"] == R.golden_load(case)[0]
+    with pytest.raises(B.BsxError, match="multiple of 8"):
+        B.Mapper(B.Index(B.make_params(), ["c"], [b"ACGT" * 100]), B.make_params(), max_batch=4, stride=100)
 
 
 def _rec_diff(name, got, exp, reads=None):
