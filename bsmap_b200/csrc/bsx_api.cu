@@ -425,10 +425,13 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     a.out_a = s.d_out_a; a.out_b = s.d_out_b; a.out_pair = s.d_out_pair; a.cnt_a = s.d_cnt_a; a.cnt_b = s.d_cnt_b;
     a.work_counter = s.d_counter; a.hit_scratch = s.d_hits; a.dd_scratch = s.d_dd; a.pair_scratch = s.d_pairs;
     a.prep = s.d_prep; a.mates = pe ? 2 : 1;
-    {   // 32 units per warp and atomic when the batch is large; smaller blocks keep >= 2 blocks per resident warp
+    {   // 32 units per warp and atomic when the batch is large (>= 2 blocks per resident warp: the prepare phase runs
+        // with all lanes busy); small batches take smaller blocks (>= 8 per warp) because there the tail decides --
+        // config 5's 200 k heavy reads: 0.62 M reads/s with blocks of 32, 0.86 M with blocks of 4
         const uint64_t units = (uint64_t)n * (uint64_t)a.mates, warps = (uint64_t)(pe ? m->n_ctas_pe : m->n_ctas_se) * BSX_WARPS_PER_CTA;
+        const uint64_t want = units >= (1u << 19) ? 2 : 8;
         uint32_t b = 32;
-        while (b > 4 && units / b < 2 * warps) b >>= 1;
+        while (b > 4 && units / b < want * warps) b >>= 1;
         a.block_units = b;
     }
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
