@@ -202,6 +202,10 @@ class Mapper:
                                 first_index, pr.ctypes.data, ra.ctypes.data, rb.ctypes.data, ca.ctypes.data, cb.ctypes.data))
         return pr, ra, rb, ca, cb
 
+    def map_pe_ptr(self, n, seq_a_ptr, len_a_ptr, seq_b_ptr, len_b_ptr, pair_ptr, out_a_ptr, out_b_ptr, cnt_a_ptr=None, cnt_b_ptr=None, first_index=0):
+        """raw-address form (pinned host buffers owned by the caller)"""
+        check(load().bsx_map_pe(self.h, n, seq_a_ptr, len_a_ptr, seq_b_ptr, len_b_ptr, first_index, pair_ptr, out_a_ptr, out_b_ptr, cnt_a_ptr, cnt_b_ptr))
+
     # --- staged form: inputs resident in HBM ---
     def upload(self, n, seq_ptr, len_ptr, seq_b_ptr=None, len_b_ptr=None, stream=None):
         check(load().bsx_batch_upload(self.h, n, seq_ptr, len_ptr, seq_b_ptr, len_b_ptr, stream))

@@ -17,6 +17,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 #include "bsx_internal.h"
 
 namespace {
@@ -166,6 +167,21 @@ bool resume_at_line_start(bsx_reads *r) {
 
 }  // namespace
 
+// gzip'ed input (an extension over the reference): inflated into memory, then handled like a map
+static bool is_gzip(const char *p, size_t n) { return n >= 2 && (unsigned char)p[0] == 0x1f && (unsigned char)p[1] == 0x8b; }
+static int gunzip_file(const char *path, std::vector<char> &out) {
+    gzFile g = gzopen(path, "rb");
+    if (!g) return BSX_ERR_IO;
+    gzbuffer(g, 1 << 20);
+    out.clear();
+    std::vector<char> buf((size_t)1 << 22);
+    int got;
+    while ((got = gzread(g, buf.data(), (unsigned)buf.size())) > 0) out.insert(out.end(), buf.begin(), buf.begin() + got);
+    const bool bad = got < 0;
+    gzclose(g);
+    return bad ? BSX_ERR_IO : BSX_OK;
+}
+
 int bsx_host_threads(int requested) {
     if (requested > 0) return requested > 64 ? 64 : requested;
     if (const char *e = getenv("BSX_THREADS")) { int v = atoi(e); if (v > 0) return v > 64 ? 64 : v; }
@@ -192,6 +208,11 @@ extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, 
     } else {   // pipe: slurp
         char buf[1 << 16]; ssize_t g;
         while ((g = read(fd, buf, sizeof buf)) > 0) r->owned.insert(r->owned.end(), buf, buf + g);
+        r->p = r->owned.data(); r->n = r->owned.size();
+    }
+    if (is_gzip(r->p, r->n)) {
+        if (r->mapped) { munmap((void *)r->p, r->n); r->mapped = false; }
+        if (gunzip_file(path, r->owned) != BSX_OK) { close(fd); delete r; bsx_set_error("failed to inflate gzip read file: %s", path); return BSX_ERR_IO; }
         r->p = r->owned.data(); r->n = r->owned.size();
     }
     // CheckFile (reads.cpp:19-50): the first non-blank character decides
@@ -290,6 +311,11 @@ int bsx_load_fasta(const char *path, std::vector<std::string> &names, std::vecto
     } else {
         char buf[1 << 16]; ssize_t g;
         while ((g = read(fd, buf, sizeof buf)) > 0) owned.insert(owned.end(), buf, buf + g);
+        p = owned.data(); n = owned.size();
+    }
+    if (is_gzip(p, n)) {
+        if (mapped) { munmap((void *)p, n); mapped = false; }
+        if (gunzip_file(path, owned) != BSX_OK) { close(fd); bsx_set_error("failed to inflate gzip reference file: %s", path); return BSX_ERR_IO; }
         p = owned.data(); n = owned.size();
     }
     struct Body { size_t b, e; };

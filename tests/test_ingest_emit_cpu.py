@@ -150,6 +150,23 @@ def test_growing_records_span_several_scan_windows(tmp_path, empty_lines):
         assert empty_lines or len(fast) == n_rec
 
 
+def test_gzip_input(tmp_path):
+    """gzip'ed read and reference files are inflated transparently (extension over the reference)"""
+    import gzip
+    plain, gz = tmp_path / "r.fq", tmp_path / "r.fq.gz"
+    plain.write_bytes(REGULAR_FQ)
+    with gzip.open(gz, "wb") as f:
+        f.write(REGULAR_FQ)
+    assert load_all(str(gz)) == load_all(str(plain))
+    fa, fagz = tmp_path / "g.fa", tmp_path / "g.fa.gz"
+    fa.write_bytes(b">chr1 x\nACGTACGTNN\nacgt\n>chr2\nGGGG\n")
+    with gzip.open(fagz, "wb") as f:
+        f.write(fa.read_bytes())
+    p = B.make_params()
+    a, b = B.Index.text_only_from_fasta(p, str(fa)), B.Index.text_only_from_fasta(p, str(fagz))
+    assert a.header() == b.header() and np.array_equal(a.download("refcat"), b.download("refcat"))
+
+
 def test_skip_and_errors(tmp_path):
     path = tmp_path / "r.fq"
     path.write_bytes(REGULAR_FQ)
