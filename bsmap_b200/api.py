@@ -356,6 +356,16 @@ class Meth:
         self.n_valid = nv.value
         return nv.value
 
+    def attach(self, mapper: "Mapper", sam_rules: bool = True):
+        """pile up every batch `mapper` maps from now on, on the device, without SAM text in between"""
+        check(load().bsx_mapper_attach_meth(mapper.h, self.h, C.byref(self.o), int(sam_rules)))
+
+    def valid(self) -> int:
+        nv = C.c_uint64(0)
+        check(load().bsx_meth_valid_count(self.h, C.byref(nv)))
+        self.n_valid = nv.value
+        return nv.value
+
     def counters(self, k: int):
         """(meth, depth) of reference sequence k"""
         n = load().bsx_index_seq_size(self.index.h, k)

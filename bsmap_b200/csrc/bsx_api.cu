@@ -280,6 +280,9 @@ struct bsx_mapper {
     uint32_t *d_debug = nullptr;
     uint64_t launches = 0;
     MapArgs base{};
+    bsx_meth *meth = nullptr;        // attached methylation counters: every mapped batch is piled up on its stream
+    bsx_meth_opts meth_opts{};
+    int meth_sam = 1;
 };
 
 int bsx_map_occupancy_se_wgbs(size_t smem);   // bsx_map_se.cu
@@ -437,8 +440,21 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;
-    if (pe) return bsx_launch_map_pe(a, m->n_ctas_pe, st);
-    return a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st);
+    int rc = pe ? bsx_launch_map_pe(a, m->n_ctas_pe, st)
+                : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st));
+    if (rc == BSX_OK && m->meth) {
+        rc = bsx_meth_pile_mapped(m->meth, &m->meth_opts, m->meth_sam, m->par.report_repeat_hits, n, pe ? 2 : 1, m->stride,
+                                  s.d_seq_a, s.d_seq_b, s.d_out_a, s.d_out_b, s.d_out_pair, st);
+        m->launches++;
+    }
+    return rc;
+}
+
+extern "C" int bsx_mapper_attach_meth(bsx_mapper *m, bsx_meth *meth, const bsx_meth_opts *o, int sam_rules) {
+    if (!m || (meth && !o)) { bsx_set_error("bsx_mapper_attach_meth: bad argument"); return BSX_ERR_ARG; }
+    m->meth = meth; m->meth_sam = sam_rules;
+    if (o) m->meth_opts = *o;
+    return BSX_OK;
 }
 
 static int download_slot(bsx_mapper *m, int si, uint32_t n, bool pe, bsx_pair_rec *op, bsx_rec *oa, bsx_rec *ob,

@@ -23,6 +23,8 @@ struct Opts {
     std::string a, b, d, o, o2;
     unsigned read_start = 1, read_end = ~0u;
     int num_procs = 0, zero_qual = '!', qual_threshold = 0;   // -p: host threads (0 = all cores)
+    std::string meth_out;        // --methratio FILE: methylation ratios straight from the device (no SAM needed)
+    bsx_meth_opts mo;
     unsigned batch = 1u << 17;   // reads per GPU batch: small enough to keep the three host stages overlapped
 };
 
@@ -55,7 +57,12 @@ void usage() {
            "       -m  <int>   minimal insert size allowed, default=28\n"
            "       -x  <int>   maximal insert size allowed, default=500\n"
            "       -2  <str>   output file of unpaired alignment hits\n"
-           "       -h          help\n\n");
+           "       -h          help\n"
+           "\n  Extensions (not in BSMAP 2.6):\n"
+           "       --methratio <str>   also write methratio.py's table, piled up on the GPU from the mapped batches\n"
+           "                           (-o may then be omitted: no alignment text is produced at all)\n"
+           "       --meth-unique --meth-pair --meth-zero --meth-cpg --meth-trim <int> --meth-min-depth <int>\n"
+           "                           methratio.py's -u -p -z -g -t -m\n\n");
     exit(1);
 }
 
@@ -73,6 +80,20 @@ void set_digestion(Opts &o, const char *a) {   // Param::SetDigestionSite (param
 int get_options(int argc, char **argv, Opts &o) {
     for (int i = 1; i < argc; i++) {
         if (argv[i][0] != '-') return i;
+        if (argv[i][1] == '-') {
+            // extensions (the reference's parser stops at any of these): methratio.py's table from the device-side
+            // pile-up, --methratio FILE [--meth-unique --meth-pair --meth-zero --meth-cpg --meth-trim N --meth-min-depth N]
+            const std::string a = argv[i] + 2;
+            if (a == "methratio" && i + 1 < argc) o.meth_out = argv[++i];
+            else if (a == "meth-unique") o.mo.unique = 1;
+            else if (a == "meth-pair") o.mo.pair = 1;
+            else if (a == "meth-zero") o.mo.meth0 = 1;
+            else if (a == "meth-cpg") o.mo.combine_cpg = 1;
+            else if (a == "meth-trim" && i + 1 < argc) o.mo.trim_fillin = atoi(argv[++i]);
+            else if (a == "meth-min-depth" && i + 1 < argc) o.mo.min_depth = atoi(argv[++i]);
+            else return i;
+            continue;
+        }
         const char c = argv[i][1];
         const char *val = nullptr;
         const bool flag = (c == 'R' || c == 'u' || c == 'h');
@@ -148,7 +169,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     printf("\nBSMAP v2.6 (bsmap_b200: B200-native hot path)\n");
     if (argc == 1) usage();
     { time_t t = time(nullptr); printf("Start at:  %s\n", ctime(&t)); }
-    Opts o; bsx_params_default(&o.p);
+    Opts o; bsx_params_default(&o.p); bsx_meth_opts_default(&o.mo);
     if (int bad = get_options(argc, argv, o)) { printf("unknown option: %s\n", argv[bad]); exit(bad); }
     if (o.qual_threshold != 0) { fprintf(stderr, "-q quality trimming is not supported by the GPU path\n"); return 1; }
     if (o.o.size() > 4) {
@@ -169,7 +190,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         for (size_t k = 0; k < ref_seqs.size(); k++) { np.push_back(ref_names[k].c_str()); sp.push_back(ref_seqs[k].data()); ln.push_back((uint32_t)ref_seqs[k].size()); }
         if (bsx_index_create(&o.p, (int)ref_seqs.size(), np.data(), sp.data(), ln.data(), 0, &ix) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
     }
-    std::vector<std::string>().swap(ref_seqs);
+    if (o.meth_out.empty()) std::vector<std::string>().swap(ref_seqs);   // the methratio report prints reference context
     bsx_index_info info; bsx_index_get_info(ix, &info);
     unsigned long long sum_len = 0; for (uint32_t k = 0; k < info.n_seq; k++) sum_len += bsx_index_seq_size(ix, k);
     printf("Load in %u db seqs, total size %llu bp. %ld secs passed\n", info.n_seq, sum_len, (long)(time(nullptr) - t0));
@@ -202,17 +223,24 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     if (rc != BSX_OK) { fprintf(stderr, "fatal error: unrecognizable format of reads file (FASTA/FASTQ only; SAM/BAM input is not supported).\n"); return 1; }
     if (pe) printf("Pair-end alignment(GPU)\nQuery: %s  %s  Reference: %s  Output: %s  %s\n", o.a.c_str(), o.b.c_str(), o.d.c_str(), o.o.c_str(), o.o2.c_str());
     else printf("Single read alignment(GPU)\nQuery: %s  Reference: %s  Output: %s\n", o.a.c_str(), o.d.c_str(), o.o.c_str());
-    FILE *fout = fopen(o.o.c_str(), "wb");
+    const bool no_text = o.o.empty() && !o.meth_out.empty();             // --methratio without -o: no alignment text at all
+    FILE *fout = fopen(no_text ? "/dev/null" : o.o.c_str(), "wb");
     if (!fout) { fprintf(stderr, "failed to open output file (check -o option): %s\n", o.o.c_str()); return 1; }
     FILE *fun = nullptr;
-    if (pe && !p.out_sam) { fun = fopen(o.o2.c_str(), "wb"); if (!fun) { fprintf(stderr, "failed to open output file for unpaired hits (check -2 option): %s\n", o.o2.c_str()); return 1; } }
-    if (p.out_sam) { std::vector<char> text; size_t n = bsx_format_header(ix, nullptr, 0); text.resize(n + 1); bsx_format_header(ix, text.data(), n + 1); fwrite(text.data(), 1, n, fout); fflush(fout); }
+    if (pe && !p.out_sam && !no_text) { fun = fopen(o.o2.c_str(), "wb"); if (!fun) { fprintf(stderr, "failed to open output file for unpaired hits (check -2 option): %s\n", o.o2.c_str()); return 1; } }
+    if (p.out_sam && !no_text) { std::vector<char> text; size_t n = bsx_format_header(ix, nullptr, 0); text.resize(n + 1); bsx_format_header(ix, text.data(), n + 1); fwrite(text.data(), 1, n, fout); fflush(fout); }
 
     const unsigned stride = 160;
     const int threads = bsx_host_threads(o.num_procs);
     if (const char *e = getenv("BSX_CLI_BATCH")) { const int v = atoi(e); if (v > 0) o.batch = (unsigned)v; }
     bsx_mapper *mp = nullptr;
     if (bsx_mapper_create(ix, &p, o.batch, stride, &mp) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    bsx_meth *mh = nullptr;
+    if (!o.meth_out.empty()) {
+        // SAM rules (mate-overlap removal) unless the alignment output is BSP: the table then equals methratio.py run on -o
+        if (bsx_meth_create(ix, &mh) != BSX_OK || bsx_mapper_attach_meth(mp, mh, &o.mo, (p.out_sam || no_text) ? 1 : 0) != BSX_OK) {
+            fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    }
     bsx_reads_skip(ra, o.read_start - 1); if (pe) bsx_reads_skip(rb, o.read_start - 1);
     unsigned index_a = o.read_start - 1;
     // pinned staging: one upload buffer per mate (the map call returns after its copies), three result slots
@@ -236,7 +264,14 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         while (jobs.pop(j)) {
             const double t = now();
             Text tx; tx.done_index = j.done_index;
-            if (!pe) {
+            if (no_text) {   // counts only (the rules of s_OutHit / s_OutHitPair / s_OutHitUnpair for "printed as mapped")
+                auto mapped = [&](const bsx_rec &r) { const int n = r.status ? -1 : (int)r.nhits; return n >= 1 && !(n > 1 && p.report_repeat_hits == 0); };
+                for (uint32_t t = 0; t < j.n; t++) {
+                    if (!pe) n_aligned += mapped(reca[j.slot][t]);
+                    else if (recp[j.slot][t].paired) n_pairs++;
+                    else { n_a += mapped(reca[j.slot][t]); n_b += mapped(recb[j.slot][t]); }
+                }
+            } else if (!pe) {
                 uint32_t na = 0;
                 bsx_format_se_chunks(ix, &p, j.n, j.a.name.data(), j.a.seq.data(), j.a.qual.data(), 0, reca[j.slot], cnta[j.slot], threads, tx.main, &na);
                 n_aligned += na;
@@ -292,6 +327,21 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
                         (unsigned long long)(ra->n_slow + (rb ? rb->n_slow : 0)), threads);
     bsx_reads_close(ra); bsx_reads_close(rb);
     if (fail) return 1;
+    if (mh) {
+        const double t = now();
+        std::vector<const char *> sp; std::vector<uint32_t> ln;
+        for (size_t k = 0; k < ref_seqs.size(); k++) { sp.push_back(ref_seqs[k].data()); ln.push_back((uint32_t)ref_seqs[k].size()); }
+        FILE *fm = fopen(o.meth_out.c_str(), "wb");
+        if (!fm) { fprintf(stderr, "failed to open methratio output file: %s\n", o.meth_out.c_str()); return 1; }
+        uint64_t st[2] = {0, 0}, nv = 0;
+        bsx_meth_valid_count(mh, &nv);
+        bsx_meth_write(mh, &o.mo, sp.data(), ln.data(), nullptr, threads, fileno(fm), st);
+        fclose(fm);
+        printf("total %llu valid mappings, %llu covered cytosines, average coverage: %.2f fold.\n", (unsigned long long)nv, (unsigned long long)st[0],
+               st[0] ? (double)st[1] / (double)st[0] : 0.0);
+        if (timing) fprintf(stderr, "[bsx timing] methratio report %.3f s\n", now() - t);
+        bsx_meth_destroy(mh);
+    }
     const double tot = (double)(index_a - o.read_start + 1);
     if (pe) printf("Total number of aligned reads: \npairs:       %llu (%.2g%%)\nsingle a:    %llu (%.2g%%)\nsingle b:    %llu (%.2g%%)\n",
                    n_pairs, 100.0 * n_pairs / tot, n_a, 100.0 * n_a / tot, n_b, 100.0 * n_b / tot);

@@ -71,6 +71,10 @@ void bsx_format_pe_chunks(const bsx_index *ix, const bsx_params *p, uint32_t n, 
                           const uint16_t *counts_b, int threads, std::vector<std::string> &chunks,
                           std::vector<std::string> &chunks_unpair, uint32_t *n_stats);
 int bsx_load_fasta(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs);   // bsx_reads.cpp
+struct bsx_meth;
+int bsx_meth_pile_mapped(bsx_meth *m, const bsx_meth_opts *o, int sam, int report_repeat_hits, uint32_t n, int mates, uint32_t stride,
+                         const uint8_t *seq_a, const uint8_t *seq_b, const bsx_rec *out_a, const bsx_rec *out_b, const bsx_pair_rec *out_pair,
+                         cudaStream_t st);   // bsx_meth.cu
 int bsx_host_threads(int requested);   // 0 = BSX_THREADS env or hardware concurrency (capped at 32)
 
 int bsx_index_build_device(bsx_index *ix, const char *const *seqs);   // bsx_index.cu

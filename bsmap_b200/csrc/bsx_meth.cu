@@ -33,7 +33,43 @@ namespace {
 
 __device__ __forceinline__ uint32_t ref_code(const uint32_t *refcat, uint32_t q) { return (refcat[q >> 4] >> (30 - 2 * (q & 15))) & 3u; }
 
-// one warp per alignment
+// One alignment, executed by a warp: get_alignment's trimming (methratio.py:56-64), the bounds test (105) and the
+// pile-up (107-118).  getc(i) = i-th character of SEQ as printed.  Filters (-u / -p) were applied by the caller.
+template <class GetC>
+__device__ __forceinline__ void pile_alignment(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
+                                               uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, const bsx_meth_opts &o,
+                                               uint32_t k, long long pos, long long len, int st, int ins, long long mate_pos, bool sam, int lane, GetC getc) {
+    const uint32_t *anchor = seqinfo, *size = seqinfo + n_seq + 1;
+    long long start = 0;
+    const int N = o.trim_fillin;
+    const bool first_minus = st & 1, second_minus = (st >> 1) & 1;
+    if (N > 0) {                                             // trim fill-in nucleotides (methratio.py:56-63)
+        if (!first_minus && second_minus) len = len - N > 0 ? len - N : 0;                     // '+-': seq[:-N]
+        else if (first_minus && second_minus) { start = N < len ? N : len; len -= start; pos += N; }   // '--': seq[N:], pos + N
+        else if (ins != 0 && len > (long long)abs(ins) - N) {
+            const long long trim = len - ((long long)abs(ins) - N);
+            if (!first_minus) len = len - trim > 0 ? len - trim : 0;                           // '++': seq[:-trim]
+            else { start = trim < len ? trim : len; len -= start; pos += trim; }                // '-+': seq[trim:], pos + trim
+        }
+    }
+    if (sam && ins > 0) {                                    // remove the region overlapped by the mate (methratio.py:64)
+        const long long e = mate_pos - pos;                  // seq[:e] with Python slice semantics
+        if (e < 0) len = len + e > 0 ? len + e : 0; else if (e < len) len = e;
+    }
+    if (pos + len > (long long)size[k]) return;             // methratio.py:105
+    if (lane == 0) atomicAdd(n_valid, 1ull);
+    const uint32_t base = anchor[k] + (uint32_t)pos;
+    const uint32_t match = first_minus ? 2u : 1u;           // '+': C (converted reads show T), '-': G (A)
+    const char cm = first_minus ? 'G' : 'C', cc = first_minus ? 'A' : 'T';
+    for (int i = lane; i < (int)len; i += 32) {
+        if (ref_code(refcat, base + (uint32_t)i) != match) continue;
+        const char c = getc((int)start + i);
+        if (c == cc) atomicAdd(depth + base + i, 1u);
+        else if (c == cm) { atomicAdd(meth + base + i, 1u); atomicAdd(depth + base + i, 1u); }
+    }
+}
+
+// alignments parsed from SAM / BSP text on the host: one warp per alignment
 __global__ void __launch_bounds__(256) meth_pileup_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
                                                           uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, bsx_meth_opts o, uint32_t n,
                                                           const char *__restrict__ seqs, uint32_t stride, const uint16_t *__restrict__ lens,
@@ -48,35 +84,60 @@ __global__ void __launch_bounds__(256) meth_pileup_kernel(const uint32_t *__rest
     if (o.pair && !(fl & BSX_METH_PROPER)) return;          // methratio.py:36 / 49
     const uint32_t k = chr[a];
     if (k >= n_seq) return;
-    const uint32_t *anchor = seqinfo, *size = seqinfo + n_seq + 1;
-    long long len = lens[a], start = 0, pos = pos0[a];
-    const int st = strand[a], ins = insert[a], N = o.trim_fillin;
-    const bool first_minus = st & 1, second_minus = (st >> 1) & 1;
-    if (N > 0) {                                             // trim fill-in nucleotides (methratio.py:56-63)
-        if (!first_minus && second_minus) len = len - N > 0 ? len - N : 0;                     // '+-': seq[:-N]
-        else if (first_minus && second_minus) { start = N < len ? N : len; len -= start; pos += N; }   // '--': seq[N:], pos + N
-        else if (ins != 0 && len > (long long)abs(ins) - N) {
-            const long long trim = len - ((long long)abs(ins) - N);
-            if (!first_minus) len = len - trim > 0 ? len - trim : 0;                           // '++': seq[:-trim]
-            else { start = trim < len ? trim : len; len -= start; pos += trim; }                // '-+': seq[trim:], pos + trim
-        }
+    const char *sq = seqs + (size_t)a * stride;
+    pile_alignment(refcat, seqinfo, n_seq, meth, depth, n_valid, o, k, (long long)pos0[a], (long long)lens[a], strand[a], insert[a],
+                   (long long)mate_pos[a], (fl & BSX_METH_SAM) != 0, lane, [sq](int i) { return sq[i]; });
+}
+
+__device__ __forceinline__ char comp_char(char c) {   // rev_char[] (param.cpp:166-177)
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return 'N';
     }
-    if ((fl & BSX_METH_SAM) && ins > 0) {                    // remove the region overlapped by the mate (methratio.py:64)
-        const long long e = (long long)mate_pos[a] - pos;   // seq[:e] with Python slice semantics
-        if (e < 0) len = len + e > 0 ? len + e : 0; else if (e < len) len = e;
+}
+
+// The batch a mapper has just mapped, straight from its device buffers (no SAM text in between): one warp per read
+// (PE: per mate).  Which reads are printed as mapped, with which SEQ orientation / POS / TLEN / PNEXT, restates
+// s_OutHit (align.cpp:631-765), s_OutHitPair (pairs.cpp:288-424) and s_OutHitUnpair (pairs.cpp:426-498).
+__global__ void __launch_bounds__(256) meth_pileup_mapped_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
+                                                                 uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, bsx_meth_opts o,
+                                                                 int sam, int report_repeat_hits, uint32_t n, int mates, uint32_t stride,
+                                                                 const uint8_t *__restrict__ seq_a, const uint8_t *__restrict__ seq_b,
+                                                                 const bsx_rec *__restrict__ out_a, const bsx_rec *__restrict__ out_b,
+                                                                 const bsx_pair_rec *__restrict__ out_pair) {
+    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= n * (uint32_t)mates) return;
+    const uint32_t r = mates == 2 ? u >> 1 : u;
+    const int mate = mates == 2 ? (int)(u & 1u) : 0;
+    const bsx_rec rc = (mate ? out_b : out_a)[r];
+    const uint8_t *rd = (mate ? seq_b : seq_a) + (size_t)r * stride;
+    uint32_t chr, loc; int chain, lp = rc.len, ins = 0; long long mate_pos = -1; bool secondary, proper = false;
+    if (mates == 2 && out_pair[r].paired) {
+        const bsx_pair_rec pp = out_pair[r];
+        const int la = out_a[r].len, lb = out_b[r].len;
+        uint32_t a_loc = pp.a_loc, b_loc = pp.b_loc;
+        // fragment shorter than the read: the adapter part is dropped (pairs.cpp:296-306)
+        if (pp.insert < la && ((int)pp.chain ^ (int)(pp.a_chr & 1u))) a_loc += (uint32_t)(la - pp.insert);
+        if (pp.insert < lb && ((!pp.chain) ^ (int)(pp.b_chr & 1u))) b_loc += (uint32_t)(lb - pp.insert);
+        chr = mate ? pp.b_chr : pp.a_chr; loc = mate ? b_loc : a_loc; chain = mate ? !pp.chain : pp.chain;
+        if (pp.insert < lp) lp = pp.insert;
+        const bool rev = (chain ^ (int)(chr & 1u)) != 0;
+        ins = sam ? (rev ? -pp.insert : pp.insert) : pp.insert;       // TLEN (pairs.cpp:330-340) / BSP insert column
+        mate_pos = mate ? a_loc : b_loc;                             // PNEXT - 1
+        secondary = pp.npairs > 1; proper = true;
+    } else {
+        const int nh = rc.status ? -1 : (int)rc.nhits;
+        if (nh <= 0 || (nh > 1 && report_repeat_hits == 0)) return;  // printed as unmapped ('u') or not at all
+        chr = rc.chr; loc = rc.loc; chain = rc.chain; secondary = nh > 1;
     }
-    if (pos + len > (long long)size[k]) return;             // methratio.py:105
-    if (lane == 0) atomicAdd(n_valid, 1ull);
-    const uint32_t base = anchor[k] + (uint32_t)pos;
-    const uint32_t match = first_minus ? 2u : 1u;           // '+': C (converted reads show T), '-': G (A)
-    const char cm = first_minus ? 'G' : 'C', cc = first_minus ? 'A' : 'T';
-    const char *sq = seqs + (size_t)a * stride + start;
-    for (int i = lane; i < (int)len; i += 32) {
-        if (ref_code(refcat, base + (uint32_t)i) != match) continue;
-        const char c = sq[i];
-        if (c == cc) atomicAdd(depth + base + i, 1u);
-        else if (c == cm) { atomicAdd(meth + base + i, 1u); atomicAdd(depth + base + i, 1u); }
-    }
+    if (o.unique && secondary) return;
+    if (o.pair && !proper) return;
+    const bool rev = (chain ^ (int)(chr & 1u)) != 0;
+    const int st = (int)(chr & 1u) | (chain << 1);
+    pile_alignment(refcat, seqinfo, n_seq, meth, depth, n_valid, o, chr >> 1, (long long)loc, (long long)lp, st, ins, mate_pos, sam != 0, lane,
+                   [rd, rev, lp](int i) { return rev ? comp_char((char)rd[lp - 1 - i]) : (char)rd[i]; });
 }
 
 // -g: every reference "CG": both counters of the C take the G's, the G's become 0 (methratio.py:122-131)
@@ -180,6 +241,29 @@ extern "C" int bsx_meth_add(bsx_meth *m, const bsx_meth_opts *o, uint32_t n, con
         BSX_CUDA_CHECK(cudaMemcpy(&v, m->d_valid, 8, cudaMemcpyDeviceToHost));
         *n_valid = v;
     }
+    return BSX_OK;
+}
+
+// pile up the batch a mapper has just mapped (called by bsx_api.cu::run_slot on the batch's stream)
+int bsx_meth_pile_mapped(bsx_meth *m, const bsx_meth_opts *o, int sam, int report_repeat_hits, uint32_t n, int mates, uint32_t stride,
+                         const uint8_t *seq_a, const uint8_t *seq_b, const bsx_rec *out_a, const bsx_rec *out_b, const bsx_pair_rec *out_pair,
+                         cudaStream_t st) {
+    if (!m || !o || n == 0) return BSX_OK;
+    if (m->combined) { bsx_set_error("bsx_meth: counters were already combined (-g); create a new bsx_meth"); return BSX_ERR_ARG; }
+    const unsigned blocks = (unsigned)(((uint64_t)n * (uint64_t)mates * 32 + 255) / 256);
+    meth_pileup_mapped_kernel<<<blocks, 256, 0, st>>>(m->ix->d_refcat, m->ix->d_seqinfo, m->ix->n_seq, m->d_meth, m->d_depth, m->d_valid, *o,
+                                                       sam, report_repeat_hits, n, mates, stride, seq_a, seq_b, out_a, out_b, out_pair);
+    BSX_CUDA_CHECK(cudaGetLastError());
+    return BSX_OK;
+}
+
+extern "C" int bsx_meth_valid_count(bsx_meth *m, uint64_t *n_valid) {
+    if (!m || !n_valid) return BSX_ERR_ARG;
+    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    BSX_CUDA_CHECK(cudaMemcpy(&v, m->d_valid, 8, cudaMemcpyDeviceToHost));
+    *n_valid = v;
     return BSX_OK;
 }
 

@@ -230,6 +230,12 @@ int bsx_meth_destroy(bsx_meth *m);
 int bsx_meth_add(bsx_meth *m, const bsx_meth_opts *o, uint32_t n, const char *seqs, uint32_t stride,
                  const uint16_t *lens, const uint32_t *chr, const uint32_t *pos, const uint8_t *strand,
                  const int32_t *insert, const int32_t *mate_pos, const uint8_t *flags, uint64_t *n_valid);
+/* In-process form: every batch `mp` maps from now on is piled up on the device right after the align kernel, from
+ * the device-resident reads and records -- no SAM text in between.  Which reads count, with which SEQ orientation,
+ * POS, TLEN and PNEXT, follows s_OutHit / s_OutHitPair / s_OutHitUnpair; sam_rules = 1 applies the script's SAM
+ * branch (mate-overlap removal), 0 its BSP branch.  meth = NULL detaches.  The counters must live on mp's device. */
+int bsx_mapper_attach_meth(bsx_mapper *mp, bsx_meth *meth, const bsx_meth_opts *o, int sam_rules);
+int bsx_meth_valid_count(bsx_meth *m, uint64_t *n_valid);   /* "valid mappings" so far (synchronises the device) */
 /* copy the counters of sequence k to the host (after -g combining when o->combine_cpg; idempotent) */
 int bsx_meth_download(bsx_meth *m, const bsx_meth_opts *o, uint32_t k, uint32_t *meth, uint32_t *depth);
 /* write the table of methratio.py:133-152 for the sequences selected by `chroms` (NULL = all), sorted by

@@ -109,3 +109,65 @@ def test_packed_index_cannot_map():
     with pytest.raises(B.BsxError, match="no seed table"):
         B.Mapper(ix, B.make_params(), max_batch=16, stride=64)
     ix.close()
+
+
+@pytest.mark.parametrize("key", sorted(MANIFEST))
+def test_in_process_pileup_equals_the_reference_table(tmp_path, key):
+    """reads -> Mapper with attached Meth (no SAM text in between) -> table == methratio.py on the reference's own output"""
+    ent = MANIFEST[key]
+    case = CS.BY_NAME[ent["case"]]
+    d = case.data()
+    kw = opts_kwargs(ent["opts"])
+    chroms = kw.pop("chroms", None)
+    p = B.make_params(**case.param_kwargs())
+    ix = B.Index(p, d["gnames"], d["gseqs"])
+    mp = B.Mapper(ix, p, max_batch=1024, stride=160)          # several sub-batches: the hook runs per batch
+    mh = B.Meth(ix, B.meth_opts(**kw))
+    mh.attach(mp, sam_rules=bool(p.out_sam))
+    if not case.paired:
+        buf, lens = B.pack_reads(R.clip(case, d["seqs"]), stride=160)
+        mp.map_se(buf, lens)
+    else:
+        ba, la = B.pack_reads(R.clip(case, d["seqs"]), stride=160)
+        bb, lb = B.pack_reads(R.clip(case, d["seqs_b"]), stride=160)
+        mp.map_pe(ba, la, bb, lb)
+    out = tmp_path / "inproc.txt"
+    fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    sel = None if chroms is None else [1 if n in chroms else 0 for n in d["gnames"]]
+    w, (nc, nd) = mh.write(d["gseqs"], fd, chroms=sel)
+    os.close(fd)
+    exp = gzip.open(os.path.join(GOLD, key + ".txt.gz"), "rb").read()
+    got = out.read_bytes()
+    assert got == exp, R.first_diff(got, exp)
+    if chroms is None:
+        assert ent["stdout"] == "total %d valid mappings, %d covered cytosines, average coverage: %.2f fold." % (mh.valid(), nc, float(nd) / nc)
+    mh.close(); mp.close(); ix.close()
+
+
+@pytest.mark.parametrize("key", ["se_cfg2_r0_uR.default", "pe_sam.p_u", "pe_bsp_r0.default", "se_n1.t_5_g"])
+def test_bsmap_cli_methratio_extension(tmp_path, key):
+    """bsmap --methratio: the table of methratio.py without running it -- next to the alignment file, or instead of it"""
+    ent = MANIFEST[key]
+    case = CS.BY_NAME[ent["case"]]
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    o = str(tmp_path / ("out." + case.out_ext))
+    o2 = str(tmp_path / "out_unpair.bsp") if (case.paired and case.out_ext != "sam") else None
+    flags = {"-u": ["--meth-unique"], "-p": ["--meth-pair"], "-z": ["--meth-zero"], "-g": ["--meth-cpg"]}
+    ext, it = [], iter(ent["opts"])
+    for x in it:
+        ext += flags[x] if x in flags else [{"-t": "--meth-trim", "-m": "--meth-min-depth"}[x], next(it)]
+    exp = gzip.open(os.path.join(GOLD, key + ".txt.gz"), "rb").read()
+    exp_main, exp_un = R.golden_load(case)
+    m1 = str(tmp_path / "m1.txt")
+    r = subprocess.run([exe] + case.cli(a, b, fa, o, o2) + ["--methratio", m1] + ext, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(m1, "rb").read() == exp and open(o, "rb").read() == exp_main
+    assert ent["stdout"] in r.stdout
+    if case.out_ext == "sam":                                   # no alignment text at all
+        m2 = str(tmp_path / "m2.txt")
+        argv = [x for x in case.cli(a, b, fa, o, o2)]
+        k = argv.index("-o"); del argv[k:k + 2]
+        r = subprocess.run([exe] + argv + ["--methratio", m2] + ext, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert open(m2, "rb").read() == exp and ent["stdout"] in r.stdout

@@ -41,6 +41,18 @@ res["methratio_seconds_runs"] = [round(x, 3) for x in runs]
 res["methratio_alignments_per_s"] = a.reads / min(runs)
 res["summary"] = r.stdout.strip()
 res["table_bytes"] = os.path.getsize(out)
+# fused: reads -> methratio table in one process, no alignment text in between (bsmap --methratio without -o)
+fused = []
+for k in range(3):
+    out = os.path.join(td, "fused%d.txt" % k)
+    t0 = time.perf_counter()
+    r2 = subprocess.run([os.path.join(ROOT, "bsmap_b200", "bsmap"), "-a", fq, "-d", fa, "-s", "16", "-v", "5", "-S", "7", "--methratio", out],
+                        capture_output=True, text=True, env=dict(os.environ, BSX_CLI_TIMING="1"))
+    fused.append(time.perf_counter() - t0)
+    assert r2.returncode == 0, r2.stdout[-300:] + r2.stderr[-300:]
+res["fused_fastq_to_table_seconds_runs"] = [round(x, 3) for x in fused]
+res["fused_identical_to_two_step"] = hashlib.md5(open(out, "rb").read()).hexdigest() == hashlib.md5(open(os.path.join(td, "meth2.txt"), "rb").read()).hexdigest()
+res["fused_stages"] = [l for l in r2.stderr.splitlines() if "bsx timing" in l]
 # bounded CPU sample: the first N alignment lines through the numpy restatement of methratio.py
 import methratio_oracle as MO
 small = os.path.join(td, "small.sam")
