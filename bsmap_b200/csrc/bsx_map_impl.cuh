@@ -264,9 +264,9 @@ __device__ int commit_hit(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd
         const int sl = ccgg_seglen(A, chr, loc, R->len);
         if (sl > A.max_insert || sl < A.min_insert) { __syncwarp(); return 0; }
     }
-    const uint32_t cnt = chain ? R->nc[w] : R->nh[w];
     if ((int)w < R->best) WSET(R->best, (int)w);       // lowest level that holds a hit
-    if (lane == 0) {
+    if (lane == 0) {                                    // the bucket counters are lane 0's: nobody else reads them before the fence
+        const uint32_t cnt = chain ? R->nc[w] : R->nh[w];
         if (store_all) hits[((size_t)w * 2 + chain) * (A.W + 1) + cnt] = make_uint2(chr, loc);
         else if ((int)w == R->best) hits[(size_t)chain * (A.W + 1) + cnt] = make_uint2(chr, loc);
         if (chain) R->nc[w] = (uint16_t)(cnt + 1); else R->nh[w] = (uint16_t)(cnt + 1);
