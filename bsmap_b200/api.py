@@ -99,6 +99,16 @@ class Index:
         check(load().bsx_index_create_text_only_from_fasta(C.byref(params), os.fsencode(path), C.byref(h)))
         return cls(params, None, None, -1, _handle=h)
 
+    def save_packed(self, path: str):
+        """packed reference cache: forward strand, blocks, names, sizes (WGBS; independent of -s / -I)"""
+        check(load().bsx_index_save_packed(self.h, os.fsencode(path)))
+
+    @classmethod
+    def from_packed(cls, params: Params, path: str, device: int = 0):
+        h = C.c_void_p()
+        check(load().bsx_index_create_from_packed(C.byref(params), os.fsencode(path), device, C.byref(h)))
+        return cls(params, None, None, device, _handle=h)
+
     @classmethod
     def packed(cls, names, seqs, device: int = 0):
         """packed reference only (no seed table): enough for Meth, cannot map"""

@@ -62,6 +62,67 @@ extern "C" int bsx_index_create(const bsx_params *p, int n_seq, const char *cons
     return BSX_OK;
 }
 
+// ---- packed reference cache.  The seed table takes 0.4 s of kernels to rebuild, so what is worth
+// keeping on disk is what the rebuild needs and the FASTA makes expensive: the packed forward strand (a quarter of
+// the text), the UnmaskRegion blocks, names and sizes.  Parameter-independent (WGBS); the rc strand and the table
+// are derived on the device at load.
+namespace {
+struct PackedHeader { char magic[8]; uint32_t version, n_seq; uint64_t n_words, n_blocks, names_bytes; };
+}
+
+extern "C" int bsx_index_save_packed(const bsx_index *ix, const char *path) {
+    if (!ix || !path || ix->device < 0) { bsx_set_error("bsx_index_save_packed: bad argument"); return BSX_ERR_ARG; }
+    if (ix->par.rrbs) { bsx_set_error("bsx_index_save_packed: RRBS indexes are not cached (digestion sites need the text)"); return BSX_ERR_ARG; }
+    BSX_CUDA_CHECK(cudaSetDevice(ix->device));
+    std::vector<uint32_t> ref(ix->n_words);
+    BSX_CUDA_CHECK(cudaMemcpy(ref.data(), ix->d_refcat, ix->n_words * 4, cudaMemcpyDeviceToHost));
+    std::string names;
+    for (const std::string &n : ix->names) { names += n; names.push_back('\0'); }
+    PackedHeader h; memset(&h, 0, sizeof h);
+    memcpy(h.magic, "BSXPACK", 8); h.version = 1; h.n_seq = ix->n_seq; h.n_words = ix->n_words; h.n_blocks = ix->blocks.size(); h.names_bytes = names.size();
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) { bsx_set_error("bsx_index_save_packed: cannot write %s", tmp.c_str()); return BSX_ERR_IO; }
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(names.data(), 1, names.size(), f) == names.size() &&
+              fwrite(ix->size.data(), 4, ix->n_seq, f) == ix->n_seq &&
+              (ix->blocks.empty() || fwrite(ix->blocks.data(), sizeof(bsx_block), ix->blocks.size(), f) == ix->blocks.size()) &&
+              fwrite(ref.data(), 4, ref.size(), f) == ref.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); bsx_set_error("bsx_index_save_packed: write to %s failed", path); return BSX_ERR_IO; }
+    return BSX_OK;
+}
+
+extern "C" int bsx_index_create_from_packed(const bsx_params *p, const char *path, int device, bsx_index **out) {
+    if (!p || !path || !out) { bsx_set_error("bsx_index_create_from_packed: bad argument"); return BSX_ERR_ARG; }
+    int rc = check_params(p); if (rc) return rc;
+    if (p->rrbs) { bsx_set_error("a packed reference cache cannot seed an RRBS index (digestion sites need the text)"); return BSX_ERR_ARG; }
+    rc = require_device(device); if (rc) return rc;
+    FILE *f = fopen(path, "rb");
+    if (!f) { bsx_set_error("cannot open packed reference %s", path); return BSX_ERR_IO; }
+    PackedHeader h;
+    bsx_index *ix = new bsx_index();
+    auto fail = [&](const char *why) { fclose(f); bsx_index_free_device(ix); delete ix; bsx_set_error("%s: %s", path, why); return BSX_ERR_IO; };
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "BSXPACK", 8) != 0 || h.version != 1) return fail("not a packed reference (BSXPACK v1)");
+    std::string names(h.names_bytes, '\0');
+    ix->device = device; ix->par = *p; ix->n_seq = h.n_seq;
+    ix->size.resize(h.n_seq); ix->blocks.resize(h.n_blocks);
+    uint32_t *ref = nullptr;
+    if (cudaHostAlloc(&ref, h.n_words * 4, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail("out of pinned host memory"); }
+    const bool ok = fread(&names[0], 1, names.size(), f) == names.size() && fread(ix->size.data(), 4, h.n_seq, f) == h.n_seq &&
+                    (h.n_blocks == 0 || fread(ix->blocks.data(), sizeof(bsx_block), h.n_blocks, f) == h.n_blocks) &&
+                    fread(ref, 4, h.n_words, f) == h.n_words;
+    if (!ok) { cudaFreeHost(ref); return fail("truncated file"); }
+    for (size_t q = 0; q < names.size() && ix->names.size() < h.n_seq;) { ix->names.emplace_back(names.c_str() + q); q += ix->names.back().size() + 1; }
+    if (ix->names.size() != h.n_seq) { cudaFreeHost(ref); return fail("corrupt name table"); }
+    fclose(f);
+    rc = bsx_index_build_device(ix, nullptr, ref);
+    if (rc == BSX_OK && ix->n_words != h.n_words) { bsx_set_error("%s: geometry mismatch", path); rc = BSX_ERR_IO; }
+    cudaFreeHost(ref);
+    if (rc) { bsx_index_free_device(ix); delete ix; return rc; }
+    *out = ix;
+    return BSX_OK;
+}
+
 // Packed reference only (both strands, anchors, sizes) on the device: what bsx_meth needs; no seed table, cannot map.
 extern "C" int bsx_index_create_packed(int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens,
                                        int device, bsx_index **out) {

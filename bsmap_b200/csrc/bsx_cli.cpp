@@ -14,6 +14,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "bsx_internal.h"
 
 namespace {
@@ -180,15 +182,34 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     bsx_index *ix = nullptr;
     std::thread ctx_thread([] { cudaFree(nullptr); });
     std::vector<std::string> ref_names, ref_seqs;
-    const int lrc = bsx_load_fasta(o.d.c_str(), ref_names, ref_seqs);
+    // BSX_REF_CACHE=<dir>: keep the packed reference of every FASTA seen there (keyed by name, size and mtime);
+    // the next run skips the FASTA parse and rebuilds the seed table from the packed strand on the device
+    std::string cache_path;
+    if (const char *dir = getenv("BSX_REF_CACHE")) {
+        struct stat st;
+        if (*dir && !o.p.rrbs && o.meth_out.empty() && stat(o.d.c_str(), &st) == 0) {
+            const size_t sl = o.d.find_last_of('/');
+            cache_path = std::string(dir) + "/" + (sl == std::string::npos ? o.d : o.d.substr(sl + 1)) + "." + std::to_string((long long)st.st_size) +
+                         "." + std::to_string((long long)st.st_mtime) + ".bsxpack";
+        }
+    }
+    bool from_cache = !cache_path.empty() && access(cache_path.c_str(), R_OK) == 0;
+    int lrc = BSX_OK;
+    if (!from_cache) lrc = bsx_load_fasta(o.d.c_str(), ref_names, ref_seqs);
     const double t_fa = now();
     ctx_thread.join();
     const double t_ctx = now();
+    if (from_cache && bsx_index_create_from_packed(&o.p, cache_path.c_str(), 0, &ix) != BSX_OK) {
+        fprintf(stderr, "warning: %s -- falling back to %s\n", bsx_last_error(), o.d.c_str());
+        from_cache = false; ix = nullptr;
+        lrc = bsx_load_fasta(o.d.c_str(), ref_names, ref_seqs);
+    }
     if (lrc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
-    {
+    if (!from_cache) {
         std::vector<const char *> np, sp; std::vector<uint32_t> ln;
         for (size_t k = 0; k < ref_seqs.size(); k++) { np.push_back(ref_names[k].c_str()); sp.push_back(ref_seqs[k].data()); ln.push_back((uint32_t)ref_seqs[k].size()); }
         if (bsx_index_create(&o.p, (int)ref_seqs.size(), np.data(), sp.data(), ln.data(), 0, &ix) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+        if (!cache_path.empty() && bsx_index_save_packed(ix, cache_path.c_str()) != BSX_OK) fprintf(stderr, "warning: %s\n", bsx_last_error());
     }
     if (o.meth_out.empty()) std::vector<std::string>().swap(ref_seqs);   // the methratio report prints reference context
     bsx_index_info info; bsx_index_get_info(ix, &info);

@@ -39,6 +39,17 @@ __global__ void pack_strands_kernel(const uint8_t *__restrict__ seq, uint32_t le
     rc[i] = wc;
 }
 
+// The reverse-complement strand from the packed forward strand (used when the reference comes from a packed cache):
+// cBinSeq reads the PADDED forward buffer backwards through rev_alphabet, and both N and padding pack to code 0
+// forward / code 3 reverse, so word i of the rc strand is the 2-bit-wise reversed complement of word nwords-1-i.
+__global__ void rc_from_packed_kernel(const uint32_t *__restrict__ fwd, uint32_t nwords, uint32_t *__restrict__ rc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t x = __brev(fwd[nwords - 1 - i]);                       // fields reversed, bits inside each field swapped
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);        // swap them back
+    rc[i] = ~x;                                                     // complement: code -> 3 - code
+}
+
 // ------------------------------------------------------------------------------------------ K1a
 struct bsx_dev_block {       // one UnmaskRegion block, ready for enumeration
     uint32_t word_base;      // anchor/16 of its sequence
@@ -387,7 +398,9 @@ int bsx_index_alloc_device(bsx_index *ix) {
     return upload_seqinfo(ix);
 }
 
-int bsx_index_build_device(bsx_index *ix, const char *const *seqs) {
+// seqs: the sequences as ASCII, or NULL when `packed` (host copy of the whole packed forward strand, n_words words
+// with margins) and ix->blocks are given instead (bsx_index_create_from_packed; WGBS only)
+int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_t *packed) {
     const bsx_params &p = ix->par;
     const int s = p.seed_size, I = p.index_interval;
     BSX_CUDA_CHECK(cudaSetDevice(ix->device));
@@ -420,20 +433,30 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs) {
     BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_refcat, 0, ix->n_words * 4, st));    // margins defined as zero (App. B Q5)
     BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_crefcat, 0, ix->n_words * 4, st));
 
-    // --- K0: pack every sequence (ASCII staged through one device buffer)
-    uint8_t *d_seq = nullptr;
-    BSX_CUDA_CHECK(cudaMalloc(&d_seq, (size_t)max_len + 64));
+    // --- K0: pack every sequence (ASCII staged through one device buffer), or take the packed forward strand as is
     cudaEventRecord(ev0, st);
     float ms_total = 0;
-    for (uint32_t k = 0; k < ix->n_seq; k++) {
-        BSX_CUDA_CHECK(cudaMemcpyAsync(d_seq, seqs[k], ix->size[k], cudaMemcpyHostToDevice, st));
-        uint32_t nw = ix->nwords[k];
-        pack_strands_kernel<<<(nw + 255) / 256, 256, 0, st>>>(d_seq, ix->size[k], nw, ix->d_refcat + (ix->anchor[k] >> 4),
-                                                             ix->d_crefcat + (ix->anchor[k] >> 4));
+    if (packed) {
+        if (p.rrbs) { bsx_set_error("a packed reference cache cannot seed an RRBS index (digestion sites need the text)"); return BSX_ERR_ARG; }
+        BSX_CUDA_CHECK(cudaMemcpyAsync(ix->d_refcat, packed, ix->n_words * 4, cudaMemcpyHostToDevice, st));
+        for (uint32_t k = 0; k < ix->n_seq; k++) {
+            const uint32_t nw = ix->nwords[k];
+            rc_from_packed_kernel<<<(nw + 255) / 256, 256, 0, st>>>(ix->d_refcat + (ix->anchor[k] >> 4), nw, ix->d_crefcat + (ix->anchor[k] >> 4));
+        }
         BSX_CUDA_CHECK(cudaGetLastError());
-        BSX_CUDA_CHECK(cudaStreamSynchronize(st));   // d_seq is reused
+    } else {
+        uint8_t *d_seq = nullptr;
+        BSX_CUDA_CHECK(cudaMalloc(&d_seq, (size_t)max_len + 64));
+        for (uint32_t k = 0; k < ix->n_seq; k++) {
+            BSX_CUDA_CHECK(cudaMemcpyAsync(d_seq, seqs[k], ix->size[k], cudaMemcpyHostToDevice, st));
+            uint32_t nw = ix->nwords[k];
+            pack_strands_kernel<<<(nw + 255) / 256, 256, 0, st>>>(d_seq, ix->size[k], nw, ix->d_refcat + (ix->anchor[k] >> 4),
+                                                                 ix->d_crefcat + (ix->anchor[k] >> 4));
+            BSX_CUDA_CHECK(cudaGetLastError());
+            BSX_CUDA_CHECK(cudaStreamSynchronize(st));   // d_seq is reused
+        }
+        cudaFree(d_seq);
     }
-    cudaFree(d_seq);
     if (ix->ref_only) {   // packed reference only (bsx_index_create_packed): no seed table
         BSX_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
@@ -442,12 +465,15 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs) {
     }
 
     // --- blocks (host scan of the ASCII; UnmaskRegion) and RRBS sites (find_CCGG)
-    std::vector<bsx_block> blocks;
+    std::vector<bsx_block> &blocks = ix->blocks;
     std::vector<uint32_t> rr_loc, rr_tag;
     if (!p.rrbs) {
-        for (uint32_t k = 0; k < ix->n_seq; k++) unmask_region(seqs[k], ix->size[k], 2 * k, ix->rc_offset[k], blocks);
-        std::stable_sort(blocks.begin(), blocks.end(), [](const bsx_block &a, const bsx_block &b) {
-            return a.id < b.id || (a.id == b.id && a.begin < b.begin); });
+        if (!packed) {
+            blocks.clear();
+            for (uint32_t k = 0; k < ix->n_seq; k++) unmask_region(seqs[k], ix->size[k], 2 * k, ix->rc_offset[k], blocks);
+            std::stable_sort(blocks.begin(), blocks.end(), [](const bsx_block &a, const bsx_block &b) {
+                return a.id < b.id || (a.id == b.id && a.begin < b.begin); });
+        }
     } else {
         const int max_seg = (BSX_FIXWORDS - 1) * 16 / s;      // dbseq.cpp:217
         const int sl = (int)strlen(p.digest_site), dp = p.digest_pos;

@@ -34,6 +34,7 @@ struct bsx_index {
     // host copies used by the text formatter
     std::vector<uint32_t> h_refcat;                 // Watson strands (XR:Z / BSP refseq column)
     std::vector<std::vector<uint32_t>> sites;       // RRBS CCGG_sites (dbseq.cpp:158-163)
+    std::vector<bsx_block> blocks;                  // WGBS: UnmaskRegion blocks, sorted (kept for bsx_index_save_packed)
 };
 
 struct bsx_mapper;
@@ -77,7 +78,7 @@ int bsx_meth_pile_mapped(bsx_meth *m, const bsx_meth_opts *o, int sam, int repor
                          cudaStream_t st);   // bsx_meth.cu
 int bsx_host_threads(int requested);   // 0 = BSX_THREADS env or hardware concurrency (capped at 32)
 
-int bsx_index_build_device(bsx_index *ix, const char *const *seqs);   // bsx_index.cu
+int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_t *packed = nullptr);   // bsx_index.cu
 int bsx_index_alloc_device(bsx_index *ix);                            // shell: allocate device arrays
 void bsx_index_free_device(bsx_index *ix);
 void bsx_set_error(const char *fmt, ...);

@@ -63,7 +63,7 @@ EXPORTS = [
     "bsx_format_pe", "bsx_cli_main",
     "bsx_reads_open", "bsx_reads_close", "bsx_reads_kind", "bsx_reads_skip", "bsx_reads_force_token_reader",
     "bsx_reads_next", "bsx_reads_get", "bsx_emit_se", "bsx_emit_pe",
-    "bsx_index_create_packed", "bsx_meth_opts_default", "bsx_meth_create", "bsx_meth_destroy", "bsx_meth_add", "bsx_meth_download",
+    "bsx_index_create_packed", "bsx_index_save_packed", "bsx_index_create_from_packed", "bsx_meth_opts_default", "bsx_meth_create", "bsx_meth_destroy", "bsx_meth_add", "bsx_meth_download",
     "bsx_meth_write", "bsx_methratio_main", "bsx_mapper_attach_meth", "bsx_meth_valid_count",
 ]
 
@@ -131,6 +131,8 @@ def load():
     L.bsx_emit_se.argtypes = [vp, C.POINTER(Params), vp, u32, i32, vp, vp, i32, i32, C.POINTER(u32)]
     L.bsx_emit_pe.restype = sz
     L.bsx_emit_pe.argtypes = [vp, C.POINTER(Params), vp, vp, u32] + [vp] * 5 + [i32, i32, i32, C.POINTER(u32)]
+    L.bsx_index_save_packed.argtypes = [vp, C.c_char_p]
+    L.bsx_index_create_from_packed.argtypes = [C.POINTER(Params), C.c_char_p, i32, C.POINTER(vp)]
     L.bsx_index_create_packed.argtypes = [i32, pp, pp, vp, i32, C.POINTER(vp)]
     L.bsx_meth_opts_default.argtypes = [C.POINTER(MethOpts)]; L.bsx_meth_opts_default.restype = None
     L.bsx_meth_create.argtypes = [vp, C.POINTER(vp)]

@@ -117,6 +117,10 @@ int bsx_index_create_from_fasta(const bsx_params *p, const char *fasta_path, int
 /* host-only index for the text layer (bsx_format_*): no device arrays, cannot map */
 int bsx_index_create_text_only(const bsx_params *p, int n_seq, const char *const *names,
                                const char *const *seqs, const uint32_t *lens, bsx_index **out);
+/* Packed reference cache (WGBS): the packed forward strand, UnmaskRegion blocks, names and sizes -- everything the
+ * 0.4 s device rebuild of the seed table needs, without parsing the FASTA again.  Independent of -s / -I. */
+int bsx_index_save_packed(const bsx_index *ix, const char *path);
+int bsx_index_create_from_packed(const bsx_params *p, const char *path, int device, bsx_index **out);
 /* packed reference only (no seed table): enough for bsx_meth, cannot map */
 int bsx_index_create_packed(int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens,
                             int device, bsx_index **out);

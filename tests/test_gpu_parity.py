@@ -2,6 +2,7 @@
 against the oracle restatement on the same inputs and against the committed golden outputs of the
 unmodified reference.  Bit-exact: every index word, every record field, every output byte."""
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -226,6 +227,51 @@ def test_larger_random_workload_matches_oracle(L, opts, n_reads):
     assert st["candidates"] == int(ostats[0]) and int(ostats[1]) <= st["probes"] <= 1.35 * int(ostats[1]), (st, ostats)
     assert (recs["nhits"] > 0).mean() > 0.9
     mp.close(); ix.close(); oref.close()
+
+
+def test_packed_reference_cache_rebuilds_the_same_index(tmp_path):
+    """bsx_index_save_packed / bsx_index_create_from_packed: every device array equals the FASTA build, also for
+    other -s / -I than the cache was written with, with N runs (blocks) and lower case in the reference"""
+    rng = np.random.default_rng(5)
+    seqs = []
+    for n in (300_017, 1_234, 90_000):
+        a = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+        a[n // 3:n // 3 + 500] = ord("N"); a[10:40] = ord("n"); a[n // 2:n // 2 + 77] |= 0x20
+        seqs.append(bytes(a))
+    names = ["chrA", "chrB", "chrC"]
+    p0 = B.make_params(s=16, I=4)
+    ix0 = B.Index(p0, names, seqs)
+    path = str(tmp_path / "ref.bsxpack")
+    ix0.save_packed(path)
+    for kw in (dict(s=16, I=4), dict(s=12, I=1), dict(s=10, I=16)):
+        p = B.make_params(**kw)
+        a, b = B.Index(p, names, seqs), B.Index.from_packed(p, path)
+        assert a.header() == b.header() and a.info.n_entries == b.info.n_entries
+        for what in ("refcat", "crefcat", "anchor", "tab", "pos", "ctx"):
+            assert np.array_equal(a.download(what), b.download(what)), (kw, what)
+        a.close(); b.close()
+    with pytest.raises(B.BsxError, match="RRBS"):
+        B.Index.from_packed(B.make_params(D="C-CGG"), path)
+    (tmp_path / "junk").write_bytes(b"hello")
+    with pytest.raises(B.BsxError, match="not a packed reference"):
+        B.Index.from_packed(p0, str(tmp_path / "junk"))
+    ix0.close()
+
+
+def test_cli_reference_cache(tmp_path):
+    """BSX_REF_CACHE: the second run starts from the packed reference and writes the same file"""
+    case = CS.BY_NAME["se_cfg2_r0_uR"]
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    cache = tmp_path / "cache"; cache.mkdir()
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    outs = []
+    for k in range(2):
+        o = str(tmp_path / f"out{k}.sam")
+        r = subprocess.run([exe] + case.cli(a, b, fa, o, None), capture_output=True, text=True, env=dict(os.environ, BSX_REF_CACHE=str(cache), BSX_CLI_TIMING="1"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(open(o, "rb").read())
+        assert len(list(cache.iterdir())) == 1
+    assert outs[0] == outs[1] == R.golden_load(case)[0]
 
 
 def test_index_replica_over_nvlink_or_same_device():
