@@ -196,6 +196,11 @@ def main():
         sim = synth.simulate_reads(genome, m, L_READ, seed=2024, subs="cfg2", first_index=first_index + s0)
         seq_dev[s0:s0 + m, :L_READ] = sim["seq"]
         del sim
+    if os.environ.get("BSX_BENCH_REPEAT_READS"):
+        # diagnostic only (never a bench value): the first K reads repeated, so that every table / list / image access
+        # hits cache -- same instruction stream, no DRAM; tells how far the memory system holds the kernel back
+        k = int(os.environ["BSX_BENCH_REPEAT_READS"])
+        seq_dev[:] = seq_dev[:k].repeat((n + k - 1) // k, 1)[:n]
     del genome
     torch.cuda.empty_cache()
     len_dev = torch.full((n,), L_READ, dtype=torch.int16, device=dev)
