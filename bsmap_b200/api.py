@@ -292,7 +292,11 @@ class Reads:
 
     @property
     def kind(self) -> str:
-        return ("fastq", "fasta")[load().bsx_reads_kind(self.h)]
+        return {0: "fastq", 1: "fasta", 3: "bam"}[load().bsx_reads_kind(self.h)]
+
+    def set_readset(self, readset: int):
+        """BAM input: 0 single-end, 1 / 2 = file a / b of a pair interleaved in one BAM"""
+        load().bsx_reads_set_readset(self.h, readset)
 
     def skip(self, n_reads: int):
         load().bsx_reads_skip(self.h, n_reads)

@@ -4,7 +4,8 @@
 // (SAM when -o ends in .sam, BSP otherwise; -2 for unpaired BSP hits).  Reads are parsed with the
 // reference's token semantics (reads.cpp:83-146), mapped in large batches on the GPU, formatted on
 // the host and written in input order (= the reference with -p 1).
-// Out of scope (errors out): BAM/SAM input, .bam output, -q quality trimming, -M other than TC.
+// Out of scope (errors out): SAM text input (broken in the reference too: it is opened as BAM), .bam output,
+// -q quality trimming, -M other than TC.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -241,7 +242,8 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         rc = bsx_reads_open(o.b.c_str(), o.zero_qual, p.max_readlen, &rb);
         if (rc == BSX_ERR_IO) { fprintf(stderr, "failed to open read file #2 (check -b option): %s\n", o.b.c_str()); return 1; }
     }
-    if (rc != BSX_OK) { fprintf(stderr, "fatal error: unrecognizable format of reads file (FASTA/FASTQ only; SAM/BAM input is not supported).\n"); return 1; }
+    if (rc != BSX_OK) { fprintf(stderr, "fatal error: unrecognizable format of reads file (FASTA, FASTQ, gzip of either, or BAM).\n"); return 1; }
+    if (pe) { bsx_reads_set_readset(ra, 1); bsx_reads_set_readset(rb, 2); }
     if (pe) printf("Pair-end alignment(GPU)\nQuery: %s  %s  Reference: %s  Output: %s  %s\n", o.a.c_str(), o.b.c_str(), o.d.c_str(), o.o.c_str(), o.o2.c_str());
     else printf("Single read alignment(GPU)\nQuery: %s  Reference: %s  Output: %s\n", o.a.c_str(), o.d.c_str(), o.o.c_str());
     const bool no_text = o.o.empty() && !o.meth_out.empty();             // --methratio without -o: no alignment text at all

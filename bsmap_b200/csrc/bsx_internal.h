@@ -48,7 +48,8 @@ struct bsx_reads {
     const char *p = nullptr; size_t n = 0; bool mapped = false;
     std::vector<char> owned;               // non-mappable inputs (pipes) are slurped
     size_t pos = 0;
-    int kind = 0;                          // _file_format: 0 FASTQ, 1 FASTA
+    int kind = 0;                          // _file_format: 0 FASTQ, 1 FASTA, 3 BAM
+    int readset = 0;                       // BAM: 0 single-end, 1 / 2 = file a / b of a pair (interleaved mates)
     int zero_qual = '!', max_readlen = BSX_MAX_READLEN;
     bool force_slow = false;
     std::vector<bsx_view> name, seq, qual; // the current batch

@@ -215,10 +215,23 @@ extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, 
         if (gunzip_file(path, r->owned) != BSX_OK) { close(fd); delete r; bsx_set_error("failed to inflate gzip read file: %s", path); return BSX_ERR_IO; }
         r->p = r->owned.data(); r->n = r->owned.size();
     }
-    // CheckFile (reads.cpp:19-50): the first non-blank character decides
+    // CheckFile (reads.cpp:19-50): the first non-blank character decides; anything else is tried as BAM
     size_t q = 0; while (q < r->n && ws((unsigned char)r->p[q])) q++;
     const int c = q < r->n ? r->p[q] : -1;
-    if (c == '>') r->kind = 1; else if (c == '@') r->kind = 0;
+    if (r->n >= 12 && memcmp(r->p, "BAM\1", 4) == 0) {
+        // BAM (BGZF members are gzip members, inflated above): skip the header text and the reference dictionary
+        r->kind = 3;
+        auto i32 = [&](size_t at) { int32_t v; memcpy(&v, r->p + at, 4); return v; };
+        size_t at = 4;
+        const int32_t l_text = i32(at); at += 4 + (size_t)std::max(l_text, 0);
+        bool ok = at + 4 <= r->n;
+        if (ok) {
+            const int32_t n_ref = i32(at); at += 4;
+            for (int32_t k = 0; ok && k < n_ref; k++) { ok = at + 4 <= r->n; if (ok) { const int32_t l_name = i32(at); at += 4 + (size_t)std::max(l_name, 0) + 4; ok = at <= r->n; } }
+        }
+        if (!ok) { bsx_reads_close(r); bsx_set_error("truncated BAM header: %s", path); return BSX_ERR_IO; }
+        r->pos = at;
+    } else if (c == '>') r->kind = 1; else if (c == '@') r->kind = 0;
     else { bsx_reads_close(r); bsx_set_error("fatal error: unrecognizable format of reads file."); return BSX_ERR_ARG; }
     r->qual_fill.assign((size_t)std::max(max_readlen, 1), (char)(zero_qual + 40));
     *out = r;
@@ -237,11 +250,55 @@ extern "C" void bsx_reads_force_token_reader(bsx_reads *r, int on) { if (r) r->f
 
 extern "C" void bsx_reads_skip(bsx_reads *r, uint64_t n_reads) {
     if (!r) return;
+    if (r->kind == 3) return;   // reference quirk: CheckFile's -B skip covers _file_format 0..2 only, BAM is 3 (reads.cpp:54-75)
     Tok t{r->p, r->n, r->pos};
     const uint64_t nl = n_reads * (r->kind == 0 ? 4u : 2u);
     for (uint64_t i = 0; i < nl && t.pos < t.n; i++) t.skipline();
     r->pos = t.pos;
 }
+
+// BAM records (reads.cpp:120-143): name = qname, bases through bam_nt16_rev_table, qualities + 33, truncated to
+// max_readlen.  readset 1 (file a of a pair) takes a record and skips its mate, readset 2 skips one and takes the next.
+static uint32_t bam_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, uint16_t *lens) {
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    auto record = [&](size_t &pos, const unsigned char *&body, uint32_t &bytes) {   // false at the end of the file
+        if (pos + 4 > r->n) return false;
+        int32_t bs; memcpy(&bs, r->p + pos, 4);
+        if (bs < 32 || pos + 4 + (size_t)bs > r->n) return false;
+        body = (const unsigned char *)r->p + pos + 4; bytes = (uint32_t)bs; pos += 4 + (size_t)bs;
+        return true;
+    };
+    std::vector<std::string> &st = r->slow_store;
+    st.clear(); st.reserve((size_t)want * 3);
+    uint32_t got = 0;
+    const unsigned char *b; uint32_t nb;
+    while (got < want) {
+        if (r->readset == 2 && !record(r->pos, b, nb)) break;
+        if (!record(r->pos, b, nb)) break;
+        const uint32_t l_name = b[8], n_cig = (uint32_t)b[12] | ((uint32_t)b[13] << 8);
+        int32_t l_seq; memcpy(&l_seq, b + 16, 4);
+        const size_t off_seq = 32 + (size_t)l_name + 4 * (size_t)n_cig, off_qual = off_seq + ((size_t)std::max(l_seq, 0) + 1) / 2;
+        if (l_seq < 0 || off_qual + (size_t)l_seq > nb) break;
+        const uint32_t l = (uint32_t)std::min<int64_t>(l_seq, r->max_readlen);
+        std::string nm((const char *)b + 32), sq(l, 'N'), ql(l, '!');
+        for (uint32_t i = 0; i < l; i++) { sq[i] = nt16[(b[off_seq + (i >> 1)] >> ((~i & 1) << 2)) & 15]; ql[i] = (char)(b[off_qual + i] + 33); }
+        st.push_back(std::move(nm)); st.push_back(std::move(sq)); st.push_back(std::move(ql));
+        if (r->readset == 1 && !record(r->pos, b, nb)) { st.resize(st.size() - 3); break; }   // the reference drops a last read without a mate
+        got++;
+    }
+    for (uint32_t i = 0; i < got; i++) {
+        const std::string &a = st[3 * i], &s = st[3 * i + 1], &q = st[3 * i + 2];
+        r->name[i] = bsx_view{a.data(), (uint32_t)a.size()};
+        r->seq[i] = bsx_view{s.data(), (uint32_t)s.size()};
+        r->qual[i] = bsx_view{q.data(), (uint32_t)q.size()};
+        put_seq(seqs, lens, stride, i, s.data(), (uint32_t)s.size());
+    }
+    r->n_slow += got;
+    r->name.resize(got); r->seq.resize(got); r->qual.resize(got);
+    return got;
+}
+
+extern "C" void bsx_reads_set_readset(bsx_reads *r, int readset) { if (r) r->readset = readset; }
 
 extern "C" uint32_t bsx_reads_next(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, uint16_t *lens, int threads) {
     if (!r || want == 0) return 0;
@@ -249,6 +306,7 @@ extern "C" uint32_t bsx_reads_next(bsx_reads *r, uint32_t want, uint32_t stride,
     r->name.resize(want); r->seq.resize(want); r->qual.resize(want);
     r->slow_store.clear();
     uint32_t got = 0;
+    if (r->kind == 3) return bam_batch(r, want, stride, seqs, lens);
     bool line_start = r->pos == 0 || r->p[r->pos - 1] == '\n';
     std::vector<size_t> slow_slots;
     std::string nm, sq, ql;

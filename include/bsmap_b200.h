@@ -194,7 +194,10 @@ size_t bsx_format_pe(const bsx_index *ix, const bsx_params *p, uint32_t n,
  * Errors: BSX_ERR_IO when the file cannot be opened, BSX_ERR_ARG for an unrecognisable format. */
 int bsx_reads_open(const char *path, int zero_qual, int max_readlen, bsx_reads **out);
 void bsx_reads_close(bsx_reads *r);
-int bsx_reads_kind(const bsx_reads *r);                       /* 0 FASTQ, 1 FASTA (_file_format) */
+int bsx_reads_kind(const bsx_reads *r);                       /* 0 FASTQ, 1 FASTA, 3 BAM (_file_format) */
+/* BAM input (reads.cpp:120-143): 0 single-end; 1 / 2 = this reader is file a / b of a pair whose mates are interleaved
+ * in one BAM (a takes a record and skips the next, b skips one and takes the next) */
+void bsx_reads_set_readset(bsx_reads *r, int readset);
 void bsx_reads_skip(bsx_reads *r, uint64_t n_reads);          /* -B: 4 (fq) / 2 (fa) lines per read (reads.cpp:56-66) */
 void bsx_reads_force_token_reader(bsx_reads *r, int on);      /* tests: disable the line cutter */
 /* load up to `want` reads; bases go to seqs[i*stride ..] (zero padded) and lens[i]; returns the count.

@@ -258,6 +258,20 @@ def test_packed_reference_cache_rebuilds_the_same_index(tmp_path):
     ix0.close()
 
 
+@pytest.mark.parametrize("name", ["bam_se", "bam_se_quirks_B11_E400", "bam_pe_interleaved", "bam_pe_odd_tail"])
+def test_cli_bam_read_input(tmp_path, name):
+    """BAM read files through the command line == the unmodified reference fed the same BAM (tests/golden/bam)"""
+    import gzip
+    import bam_cases as BC
+    argv, out = BC.build(name, str(tmp_path))
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    r = subprocess.run([exe] + argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exp = gzip.open(os.path.join(R.GOLDEN, "bam", name + ".sam.gz"), "rb").read()
+    got = open(out, "rb").read()
+    assert got == exp, R.first_diff(got, exp)
+
+
 def test_cli_reference_cache(tmp_path):
     """BSX_REF_CACHE: the second run starts from the packed reference and writes the same file"""
     case = CS.BY_NAME["se_cfg2_r0_uR"]

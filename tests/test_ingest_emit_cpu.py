@@ -167,6 +167,32 @@ def test_gzip_input(tmp_path):
     assert a.header() == b.header() and np.array_equal(a.download("refcat"), b.download("refcat"))
 
 
+def test_bam_input(tmp_path):
+    """BAM read files (reads.cpp:120-143): 4-bit bases come back upper-cased / as 'N', qualities + 33, over-long reads
+    truncated; file a of an interleaved pair takes every other record and drops a last read without a mate; -B does not skip"""
+    import bamio
+    recs = [("r%d" % i, 4, s, q) for i, (s, q) in enumerate([("ACGTNacgtn", "IIIIIFFFFF"), ("ACRYKM.xTT", None), ("A" * 200, "#" * 200), ("GGG", "!J~")])]
+    bam = str(tmp_path / "r.bam")
+    bamio.write_bam(bam, recs)
+    r = B.Reads(bam, max_readlen=144)
+    assert r.kind == "bam"
+    r.skip(2)                                     # reference quirk: no effect on BAM
+    n, buf, lens = r.next(10, stride=160)
+    got = [r.get(i) for i in range(n)]
+    assert got == [(b"r0", b"ACGTNACGTN", b"IIIIIFFFFF"), (b"r1", b"ACRYKMNNTT", b" " * 10), (b"r2", b"A" * 144, b"#" * 144), (b"r3", b"GGG", b"!J~")]
+    assert list(lens) == [10, 10, 144, 3] and bytes(buf[1, :10]) == b"ACRYKMNNTT"
+    r.close()
+    pe = [("p%d/%d" % (i // 2, i % 2 + 1), 0x4d if i % 2 == 0 else 0x8d, "ACGT" * 5, "F" * 20) for i in range(9)]   # 4 pairs + a lone first mate
+    bam2 = str(tmp_path / "pe.bam")
+    bamio.write_bam(bam2, pe)
+    ra, rb = B.Reads(bam2), B.Reads(bam2)
+    ra.set_readset(1); rb.set_readset(2)
+    na, nb = ra.next(100)[0], rb.next(100)[0]
+    assert (na, nb) == (4, 4)
+    assert [ra.get(i)[0] for i in range(4)] == [b"p%d/1" % i for i in range(4)] and [rb.get(i)[0] for i in range(4)] == [b"p%d/2" % i for i in range(4)]
+    ra.close(); rb.close()
+
+
 def test_skip_and_errors(tmp_path):
     path = tmp_path / "r.fq"
     path.write_bytes(REGULAR_FQ)
