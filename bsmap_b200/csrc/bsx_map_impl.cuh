@@ -1,39 +1,33 @@
 // bsx_map_impl.cuh -- SingleAlign / PairAlign on the device (align.cpp, align.h, pairs.cpp).
-// Included by bsx_map_se.cu (everything inlined: fastest for the single-end kernel) and by bsx_map_pe.cu
-// (big device functions are real calls: the paired-end kernel shrinks from 321 KB to 134 KB of SASS and gains
-// 30 %, it was instruction-cache bound).
+// Included by bsx_map_se.cu / bsx_map_se_rrbs.cu (everything inlined, WGBS resp. RRBS compiled out: the single-end
+// kernels are instruction-cache sensitive) and by bsx_map_pe.cu (big device functions are real calls: the paired-end
+// kernel shrank from 321 KB to 134 KB of SASS and gained 30 %).
 //
-// One warp owns one read (SE) or one read pair (PE) from ASCII to result record; warps are
-// persistent and fetch work with an atomic counter, so heavy-tailed candidate lists balance.
+// Warps are persistent and fetch work with an atomic counter.  A warp takes up to 32 units (reads, or mates of 16
+// pairs) at a time:
 //
-//   K2  load / trim / filter / pack   TrimAdapter, FilterReads, ConvertBinaySeq (align.cpp:371-425,
-//                                     579-589, 90-162): ASCII staged in shared memory, 2-bit words
-//                                     and the N mask built by lanes 0..9, all seed keys by XT.
-//   K3  seed selection                ReorderSeed / AdjustSeedStartArray / CountSeeds
-//                                     (align.cpp:454-577): every DISTINCT read offset that can carry
-//                                     a seed is probed once (coalesced across lanes into 8-byte table
-//                                     loads), then lane 0 replays the reference's argmin / sort logic
-//                                     from shared memory.
-//   K4  probe + extend + commit       SnpAlign + CountMismatch (align.cpp:253-346, align.h:167-200):
-//                                     32 list entries per step, coalesced 128-B list loads; each lane
-//                                     extends one candidate.  Extension is two-phase: first ONE aligned
-//                                     16-byte gather (3 read words = 48 bases away from the seed),
-//                                     XOR + asymmetric C/T mask + popcount; only survivors load the rest
-//                                     of the window.  The partial count is a lower bound, so accept /
-//                                     reject decisions are identical to the reference.  Survivors are
-//                                     committed in lane order (ballot + serial loop) so dedupe, bucket
-//                                     counts, -w threshold lowering and the -r 0 exits fire at exactly
-//                                     the candidate the sequential reference would stop at.
-//   K5  selection                     StringAlign (align.cpp:610-627) + myrand.
-//   K6  pairing                       PairAlign::RunAlign / GetPairs (pairs.cpp:34-190).
+//   phase A  prepare, one THREAD per unit (bsx_prep.cuh)
+//     K2  trim / filter / pack   TrimAdapter, FilterReads, ConvertBinaySeq (align.cpp:371-425, 579-589, 90-162)
+//     K3  seed selection         ReorderSeed / AdjustSeedStartArray / CountSeeds (align.cpp:454-577): every distinct
+//                                read offset that can carry a seed is probed once; the plan of (mode, sub-seed) ->
+//                                list bounds + the read words facing the inline context goes into the unit's image
+//   phase B  align, one WARP per unit (this file): the image is copied into shared memory, then
+//     K4  probe + extend + commit  SnpAlign + CountMismatch (align.cpp:253-346, align.h:167-200): 64 list entries
+//                                per step, two per lane.  Phase 0 rejects a candidate from the 8 bytes of reference
+//                                context stored next to its table entry (no random access); survivors get one aligned
+//                                16-byte gather when a step has many of them, then the exact window count (few
+//                                survivors: cooperatively, two per memory round trip).  Every phase is a lower bound
+//                                of CountMismatch, so accept / reject decisions are the reference's.  Survivors are
+//                                committed in list order (ballot + serial loop) so dedupe, bucket counts, -w threshold
+//                                lowering and the -r 0 exits fire at exactly the candidate the sequential reference
+//                                would stop at.
+//     K5  selection              StringAlign (align.cpp:610-627) + myrand.
+//     K6  pairing                PairAlign::RunAlign / GetPairs (pairs.cpp:34-190).
 //
-// Integer, HBM-latency/bandwidth bound: no tensor cores.
+// Integer work bound by memory latency and issue slots: no tensor cores.
 #include <cstdio>
 #include "bsx_map.cuh"
 
-#ifndef BSX_READ_BLOCK
-#define BSX_READ_BLOCK 4        // consecutive reads a warp takes per work-counter atomic
-#endif
 // RRBS mode (-D) as a compile-time constant where a translation unit fixes it (dead code leaves the binary)
 #ifndef BSX_RRBS
 #define BSX_RRBS(A) ((A).rrbs)
@@ -51,20 +45,11 @@
 #else
 #define BSX_FN __forceinline__
 #endif
-#ifndef BSX_PIPE
-#define BSX_PIPE 1              // software-pipeline the inline-context loads one step ahead
-#endif
 #ifndef BSX_STREAM_NOALLOC
 #define BSX_STREAM_NOALLOC 1    // list entries bypass L1 (measured +2 %: L1 keeps the prepare phase's local arrays)
 #endif
-#ifndef BSX_LIST_PIPE
-#define BSX_LIST_PIPE 0         // 1 (WGBS-only kernels): request the next step's inline context before evaluating the current one
-#endif
 #ifndef BSX_COOP_FULL
 #define BSX_COOP_FULL 4         // n > 0: up to n phase-0/1 survivors of a step are counted cooperatively, two per round trip
-#endif
-#ifndef BSX_PF_NEXT
-#define BSX_PF_NEXT 0           // 1: L2-prefetch the head of the next list of the mode, 2: also across modes
 #endif
 #ifndef BSX_SE_MIN_CTAS
 #define BSX_SE_MIN_CTAS 5
@@ -382,87 +367,9 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
         uint32_t tbl = 0; bool have_tbl = false;
         uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
         int ret = 0;
-#if BSX_LIST_PIPE
-        // WGBS, software-pipelined over the (list, 64-entry step) pairs of the mode: the inline context of the NEXT
-        // step -- usually the head of the next list, lists being ~1.4 steps long -- is requested before the current
-        // step is evaluated, so the warp waits for one memory round trip per mode rather than one per list.
-        {
-            int ni = 0; uint32_t nex = 0, nez = 0;                        // next step: list index, its bounds, offset
-            #pragma unroll 1
-            for (; ni < per; ni++) { const uint4 t = plan[ni]; nex = t.x; nez = t.z; if (nex != nez) break; }
-            uint32_t nc0 = nex;
-            uint2 nx0 = make_uint2(0, 0), nx1 = make_uint2(0, 0);
-            if (ni < per) {
-                const uint32_t j0 = nc0 + (uint32_t)lane;
-                if (j0 < nez) nx0 = ld_stream(A.ctx + j0);
-                if (j0 + 32u < nez) nx1 = ld_stream(A.ctx + j0 + 32u);
-            }
-            int li = -1;
-            uint4 e = make_uint4(0, 0, 0, 0);
-            uint32_t rb = 0, mb = 0, ra = 0, ma = 0, thres = R->thres;
-            #pragma unroll 1
-            while (ni < per) {
-                if (ni != li) {                                          // first step of a list: its bounds and flanks
-                    li = ni; e = plan[li];
-                    const uint4 f = flank[li];
-                    rb = f.x; mb = f.y; ra = f.z; ma = f.w;
-                }
-                const uint32_t c0 = nc0;
-                const uint2 cx0 = nx0, cx1 = nx1;
-                nc0 = c0 + 64u;
-                if (nc0 >= e.z) {                                        // the next step opens the next non-empty list
-                    #pragma unroll 1
-                    for (ni = li + 1; ni < per; ni++) { const uint4 t = plan[ni]; nex = t.x; nez = t.z; if (nex != nez) break; }
-                    nc0 = nex;
-                }
-                if (ni < per) {
-                    const uint32_t j0 = nc0 + (uint32_t)lane;
-                    if (j0 < nez) nx0 = ld_stream(A.ctx + j0);
-                    if (j0 + 32u < nez) nx1 = ld_stream(A.ctx + j0 + 32u);
-                }
-                const uint32_t i0 = c0 + (uint32_t)lane, i1 = i0 + 32u;
-                bool pass0 = false, pass1 = false;
-                if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
-                if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
-                uint32_t exit_pos = 0;
-                if (__any_sync(BSX_FULL, pass0 || pass1)) {
-                    const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
-                    const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
-                    if (use_p1 && !have_tbl) {
-                        int zlo = 1000, zhi = -1;
-                        if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
-#pragma unroll
-                        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-                        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                        tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
-                        have_tbl = true;
-                    }
-#pragma unroll 1
-                    for (int h = 0; h < 2; h++) {
-                        if (h ? pm1 : pm0) {
-                            const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, e.w & 0xffffu, tbl, use_p1, lane, C);
-                            if (rc & 1) { ret = 1; exit_pos = (c0 - e.x) + 32u * h + (uint32_t)(rc >> 8) + 1u; break; }
-                        }
-                    }
-                    thres = R->thres;
-                }
-                if (ret) { visited += min(c0 + 64u, e.z) - e.x; counted += exit_pos; break; }
-                if (c0 + 64u >= e.z) { visited += e.z - e.x; counted += e.z - e.x; }
-            }
-        }
-#else
         #pragma unroll 1
         for (int i = 0; i < per && !ret; i++) {
             const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
-#if BSX_PF_NEXT
-            // the kernel waits on the first load of every list: start the next list's head on its way to L2 now
-            // (plan[] is contiguous over modes, so plan[i + 1] of the last sub-seed is the next mode's first list)
-            if (!BSX_RRBS(A) && (i + 1 < per || (BSX_PF_NEXT > 1 && mode + 1 < R->seedseg))) {
-                const uint4 en = plan[i + 1];
-                const uint32_t a0 = en.x + 16u * (uint32_t)lane;
-                if (lane < 4 && a0 < en.z) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.ctx + a0));
-            }
-#endif
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
             const uint32_t p = e.w & 0xffffu;
             uint32_t rb = 0, mb = 0, ra = 0, ma = 0, want = 0;
@@ -557,7 +464,6 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                 }
             }
         }
-#endif  // BSX_LIST_PIPE
         // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
         // entries evaluated past an exit point count as over-fetch
         if (lane == 0) {
@@ -613,12 +519,7 @@ __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr *C, int lan
 __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_SE_MIN_CTAS)
 BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
-#ifdef BSX_OPAQUE_LANE
-    int lane, wid;   // opaque to the optimiser: held in registers instead of re-read from %tid at every use
-    asm volatile("{ .reg .u32 t; mov.u32 t, %%tid.x; and.b32 %0, t, 31; shr.u32 %1, t, 5; }" : "=r"(lane), "=r"(wid));
-#else
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#endif
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
     uint8_t *base = smem + sizeof(CtaSm) + A.warp_smem_se * wid;

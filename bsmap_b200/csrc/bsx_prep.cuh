@@ -15,9 +15,6 @@
 // (A separate prepare KERNEL was measured first: 209 M reads/s against 268 M -- alone on the GPU it is bound by
 // DRAM random accesses, 30 ms per 20 M reads, that the fused form overlaps with issue-bound alignment.)
 #pragma once
-#ifndef BSX_PREP_PREFETCH
-#define BSX_PREP_PREFETCH 0
-#endif
 #include "bsx_map.cuh"
 
 namespace {
@@ -140,19 +137,6 @@ __device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, c
     int np = 0;
     // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset] (profile.a - i lies
     //    in [n*s, n*s+I-1]).  The union of those ranges is probed once.
-#if BSX_PREP_PREFETCH
-    // the probes below are serial per lane (each result is stored before the next load issues): start all table
-    // lines on their way to L2 first, so the serial pass waits on L2 rather than on DRAM
-    #pragma unroll 1
-    for (int n = 0; n < seg; n++) {
-        const int rmax = rrbs ? 0 : (n == seg - 1 ? lim : w - 1);
-        #pragma unroll 1
-        for (int r = 0; r <= rmax; r++) {
-            const int p = rrbs ? cso + n * s : n * s + r;
-            if (p + s <= len) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.tab + 2 * (size_t)seed_key(A, rw, p)));
-        }
-    }
-#endif
     #pragma unroll 1
     for (int n = 0; n < seg; n++) {
         const int rmax = rrbs ? 0 : (n == seg - 1 ? lim : w - 1);
