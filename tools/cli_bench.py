@@ -16,6 +16,7 @@ ap.add_argument("--reads", type=int, default=2_000_000)
 ap.add_argument("--len", type=int, default=50)
 ap.add_argument("--genome-mb", type=float, default=5.0)
 ap.add_argument("--opts", default="-s 16 -v 2 -I 4 -S 7")
+ap.add_argument("--pairs", action="store_true", help="paired-end: --reads pairs, -a/-b files")
 ap.add_argument("--skip-ref", action="store_true")
 ap.add_argument("--repeat", type=int, default=5, help="timed runs of our CLI after the first (median reported)")
 ap.add_argument("--ref-threads", type=int, default=0, help="reference -p (0 = all host cores)")
@@ -24,14 +25,22 @@ dev = "cuda" if torch.cuda.is_available() else "cpu"
 td = tempfile.mkdtemp(prefix="bsx_cli_")
 n_chr = 5
 g = synth.make_genome(1, [int(a.genome_mb * 1e6 / n_chr)] * n_chr, device=dev)
-sim = synth.simulate_reads(g, a.reads, a.len, seed=11, subs="cfg1" if a.len <= 50 else "cfg2")
-fa, fq = os.path.join(td, "ref.fa"), os.path.join(td, "reads.fq")
+fa, fq, fq2 = os.path.join(td, "ref.fa"), os.path.join(td, "reads.fq"), os.path.join(td, "mates.fq")
 synth.write_fasta(fa, [x.cpu() for x in g])
-synth.write_fastq(fq, sim["seq"].cpu(), synth.read_names({k: v.cpu() for k, v in sim.items() if k != "seq"}))
-res = {"reads": a.reads, "read_len": a.len, "genome_mb": a.genome_mb, "opts": a.opts, "host_cores": os.cpu_count()}
+if not a.pairs:
+    sim = synth.simulate_reads(g, a.reads, a.len, seed=11, subs="cfg1" if a.len <= 50 else "cfg2")
+    synth.write_fastq(fq, sim["seq"].cpu(), synth.read_names({k: v.cpu() for k, v in sim.items() if k != "seq"}))
+    inputs = ["-a", fq]
+else:
+    sim = synth.simulate_pairs(g, a.reads, a.len, seed=33, frag_min=150, frag_max=450, subs="cfg2")
+    meta = {k: v.cpu() for k, v in sim.items() if k not in ("seq1", "seq2")}
+    synth.write_fastq(fq, sim["seq1"].cpu(), synth.read_names(meta, suffix="/1"))
+    synth.write_fastq(fq2, sim["seq2"].cpu(), synth.read_names(meta, suffix="/2"))
+    inputs = ["-a", fq, "-b", fq2]
+res = {"paired": a.pairs, "reads": a.reads, "read_len": a.len, "genome_mb": a.genome_mb, "opts": a.opts, "host_cores": os.cpu_count()}
 def run(exe, out, extra):
     t0 = time.perf_counter()
-    r = subprocess.run([exe, "-a", fq, "-d", fa, "-o", out] + a.opts.split() + extra, capture_output=True, text=True,
+    r = subprocess.run([exe] + inputs + ["-d", fa, "-o", out] + a.opts.split() + extra, capture_output=True, text=True,
                        env=dict(os.environ, BSX_CLI_TIMING="1"))
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
