@@ -137,9 +137,9 @@ class Index:
         return cls(params, None, None, device, _handle=h)
 
     def device_buffers(self):
-        ptrs = (C.c_void_p * 6)()
-        sizes = (C.c_size_t * 6)()
-        n = load().bsx_index_device_buffers(self.h, ptrs, sizes, 6)
+        ptrs = (C.c_void_p * 8)()
+        sizes = (C.c_size_t * 8)()
+        n = load().bsx_index_device_buffers(self.h, ptrs, sizes, 8)
         return [(int(ptrs[i] or 0), int(sizes[i])) for i in range(n)]
 
     @property
@@ -155,7 +155,7 @@ class Index:
         i = self.info
         which = {"refcat": (0, i.n_words), "crefcat": (1, i.n_words), "anchor": (2, i.n_seq + 1),
                  "tab": (3, 2 * i.n_keys + 1), "pos": (4, i.n_entries), "tag": (5, i.n_entries),
-                 "ctx": (6, 2 * i.n_entries)}[what]
+                 "ctx": (6, 2 * i.n_entries), "ctx2": (7, 2 * i.n_entries)}[what]
         out = np.empty(int(which[1]), dtype=np.uint32)
         check(load().bsx_index_download(self.h, which[0], out.ctypes.data, out.nbytes))
         return out

@@ -228,6 +228,7 @@ extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size
         case 4: src = ix->d_pos; have = ix->n_entries * 4; break;
         case 5: src = ix->d_tag; have = ix->d_tag ? ix->n_entries * 4 : 0; break;
         case 6: src = ix->d_ctx; have = ix->d_ctx ? ix->n_entries * 8 : 0; break;
+        case 7: src = ix->d_ctx2; have = ix->d_ctx2 ? ix->n_entries * 8 : 0; break;
         default: bsx_set_error("bsx_index_download: unknown array %d", what); return BSX_ERR_ARG;
     }
     if (bytes > have) { bsx_set_error("bsx_index_download: asked %zu bytes, array has %zu", bytes, have); return BSX_ERR_ARG; }
@@ -236,14 +237,15 @@ extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size
 }
 
 extern "C" int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap) {
-    if (!ix || cap < 6) return 0;
+    if (!ix || cap < 7) return 0;
     ptrs[0] = ix->d_refcat; bytes[0] = ix->n_words * 4;
     ptrs[1] = ix->d_crefcat; bytes[1] = ix->n_words * 4;
     ptrs[2] = ix->d_tab; bytes[2] = (2 * ix->n_keys + 1) * 4;
     ptrs[3] = ix->d_pos; bytes[3] = ix->n_entries * 4;
     ptrs[4] = ix->d_tag; bytes[4] = ix->d_tag ? ix->n_entries * 4 : 0;
     ptrs[5] = ix->d_ctx; bytes[5] = ix->d_ctx ? ix->n_entries * 8 : 0;
-    return 6;
+    ptrs[6] = ix->d_ctx2; bytes[6] = ix->d_ctx2 ? ix->n_entries * 8 : 0;
+    return 7;
 }
 
 // metadata blob: everything a replica needs besides the big device arrays
@@ -305,12 +307,12 @@ extern "C" int bsx_index_replicate(const bsx_index *src, int device, bsx_index *
     std::vector<uint8_t> b = meta_blob(src);
     int rc = bsx_index_create_shell(b.data(), b.size(), device, out);
     if (rc) return rc;
-    void *sp[6], *dp[6]; size_t sb[6], db[6];
-    bsx_index_device_buffers(src, sp, sb, 6); bsx_index_device_buffers(*out, dp, db, 6);
+    void *sp[7], *dp[7]; size_t sb[7], db[7];
+    bsx_index_device_buffers(src, sp, sb, 7); bsx_index_device_buffers(*out, dp, db, 7);
     int can = 0;
     cudaDeviceCanAccessPeer(&can, device, src->device);
     if (can) { cudaSetDevice(device); cudaDeviceEnablePeerAccess(src->device, 0); cudaGetLastError(); }
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 7; i++)
         if (sb[i] && sp[i]) BSX_CUDA_CHECK(cudaMemcpyPeer(dp[i], device, sp[i], src->device, sb[i]));
     BSX_CUDA_CHECK(cudaDeviceSynchronize());
     return BSX_OK;
@@ -350,6 +352,8 @@ int bsx_map_occupancy_se_wgbs(size_t smem);   // bsx_map_se.cu
 int bsx_map_occupancy_se_rrbs(size_t smem);   // bsx_map_se_rrbs.cu
 int bsx_launch_map_se_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_launch_map_se_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
+int bsx_map_occupancy_se_wide(size_t smem);   // bsx_map_se_wide.cu
+int bsx_launch_map_se_wide(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_map_occupancy_pe(size_t smem);   // bsx_map_pe.cu
 
 static void slot_free(bsx_slot &s) {
@@ -415,7 +419,9 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     m->nslot = p->chains ? 2 : 1;
     int sms = 0;
     BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    int occ_se = (p->rrbs ? bsx_map_occupancy_se_rrbs(bsx_cta_smem_bytes(1, m->plan_cap, m->nslot)) : bsx_map_occupancy_se_wgbs(bsx_cta_smem_bytes(1, m->plan_cap, m->nslot)));
+    const size_t smem_se = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot);
+    const bool wide = !p->rrbs && p->max_snp_num >= BSX_WIDE_CTX_V && ix->d_ctx2;
+    int occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem_se) : (wide ? bsx_map_occupancy_se_wide(smem_se) : bsx_map_occupancy_se_wgbs(smem_se));
     int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap, m->nslot));
     if (occ_se < 1 || occ_pe < 1) { delete m; bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
@@ -448,6 +454,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     MapArgs &a = m->base;
     memset(&a, 0, sizeof a);
     a.refcat = ix->d_refcat; a.crefcat = ix->d_crefcat; a.tab = ix->d_tab; a.pos = ix->d_pos; a.tag = ix->d_tag; a.ctx = ix->d_ctx;
+    a.ctx2 = p->max_snp_num >= BSX_WIDE_CTX_V ? ix->d_ctx2 : nullptr;   // an index built for a smaller -v simply has none
     a.seqinfo = ix->d_seqinfo; a.sites = ix->d_sites; a.site_off = ix->d_site_off; a.n_seq = ix->n_seq;
     a.s = p->seed_size; a.I = p->index_interval; a.v = p->max_snp_num; a.W = p->max_num_hits; a.r = p->report_repeat_hits;
     a.min_insert = p->min_insert; a.max_insert = p->max_insert; a.chains = p->chains; a.pairend = p->pairend; a.rrbs = p->rrbs;
@@ -502,7 +509,8 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;
     int rc = pe ? bsx_launch_map_pe(a, m->n_ctas_pe, st)
-                : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st));
+                : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st)
+                          : (a.ctx2 ? bsx_launch_map_se_wide(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st)));
     if (rc == BSX_OK && m->meth) {
         rc = bsx_meth_pile_mapped(m->meth, &m->meth_opts, m->meth_sam, m->par.report_repeat_hits, n, pe ? 2 : 1, m->stride,
                                   s.d_seq_a, s.d_seq_b, s.d_out_a, s.d_out_b, s.d_out_pair, st);

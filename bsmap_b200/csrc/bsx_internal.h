@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include "../../include/bsmap_b200.h"
 
+#define BSX_WIDE_CTX_V 8   // from this many allowed mismatches on, 32 context bases let too many candidates through (config 5)
 struct bsx_block { uint32_t id, begin, end; };   // Block (dbseq.h:31-36)
 
 // RefSeq (dbseq.h:59-114) as resident on one device
@@ -27,6 +28,7 @@ struct bsx_index {
     uint32_t *d_tab = nullptr;      // 2*n_keys+1: [2k] list start, [2k+1] start of rc part, [2k+2] end
     uint32_t *d_pos = nullptr;      // n_entries positions (ref_anchor + p), lists fwd-ascending then rc-ascending
     uint2 *d_ctx = nullptr;         // WGBS: per entry the 16 reference bases before the seed (.x) and the 16 after it (.y)
+    uint2 *d_ctx2 = nullptr;        // WGBS, -v >= BSX_WIDE_CTX_V only: the next 16 bases outwards on either side
     uint32_t *d_tag = nullptr;      // RRBS: Hit.chr tag per entry
     uint32_t *d_seqinfo = nullptr;  // anchor[n_seq+1] | size[n_seq] | rc_offset[n_seq]
     uint32_t *d_sites = nullptr;    // RRBS: all digestion sites, concatenated

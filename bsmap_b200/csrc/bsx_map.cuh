@@ -10,6 +10,7 @@ struct MapArgs {
     // RefSeq
     const uint32_t *refcat, *crefcat, *tab, *pos, *tag, *seqinfo;
     const uint2 *ctx;             // WGBS inline context per entry: 16 bases before / after the seed   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
+    const uint2 *ctx2;            // wide context (the next 16 bases outwards), NULL unless -v >= BSX_WIDE_CTX_V
     const uint32_t *sites, *site_off;
     uint32_t n_seq;
     // Param

@@ -32,6 +32,10 @@
 #ifndef BSX_RRBS
 #define BSX_RRBS(A) ((A).rrbs)
 #endif
+// wide inline context (-v >= 8) likewise: the hot list loop of the standard kernel must not carry its registers
+#ifndef BSX_WIDE
+#define BSX_WIDE(A) ((A).ctx2 != nullptr)
+#endif
 #ifndef BSX_SE_KERNEL
 #define BSX_SE_KERNEL bsx_map_se_kernel
 #define BSX_SE_OCC bsx_map_occupancy_se
@@ -71,6 +75,15 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, const MapArgs &A
 }
 __device__ __forceinline__ uint4 *flank_of(ReadSm *R, int chain, const MapArgs &A) {
     return plan_of(R, chain, A) + A.flank_off;
+}
+
+// 16 bases of the read from offset `off` (may start before the read or run past it): (bases, valid mask)
+__device__ __forceinline__ uint2 read_window(const ReadSm *R, int chain, int off) {
+    if (off <= -16 || off >= 16 * BSX_FIXWORDS) return make_uint2(0u, 0u);
+    if (off < 0) return make_uint2(R->rw[chain][0] >> (2 * -off), R->m5[chain][0] >> (2 * -off));
+    const int j = off >> 4, sh = (off & 15) * 2;
+    const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
+    return make_uint2(__funnelshift_l(r1, R->rw[chain][j], sh), __funnelshift_l(m1, R->m5[chain][j], sh));
 }
 
 // list entries are read once: keep them out of L1, which holds the prepare phase's per-lane arrays (local memory)
@@ -386,6 +399,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                 // `> snp_thres` rejects exactly like the reference; pos[] and the reference are only touched by
                 // survivors.  Every entry of the list is a candidate, so the counters need no per-step work.
                 uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
+                uint32_t rb2 = 0, mb2 = 0, ra2 = 0, ma2 = 0; bool have_f2 = false;     // wide-context flanks of this list, set up on first use
                 for (; c0 < e.z; c0 += 64) {
                     const uint32_t i0 = c0 + lane, i1 = i0 + 32;
                     bool pass0 = false, pass1 = false;
@@ -395,6 +409,26 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                     if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
                     if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
                     if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
+                    if (BSX_WIDE(A)) {
+                        // phase 0b (indexes built for -v >= 8): with many mismatches allowed 32 context bases let a fifth
+                        // of the candidates through; the next 16 bases on either side, stored in a second array that only
+                        // these survivors read, are tested before any of them touches the reference
+                        if (!have_f2) {
+                            const uint2 wb = read_window(R, chain, (int)p - 32), wa = read_window(R, chain, (int)p + A.s + 16);
+                            rb2 = wb.x; mb2 = wb.y; ra2 = wa.x; ma2 = wa.y; have_f2 = true;
+                        }
+                        if (pass0) {
+                            const uint2 c2 = __ldg(A.ctx2 + i0);
+                            pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) +
+                                    __popc(bsx_mm_word_bits(rb2, mb2, c2.x)) + __popc(bsx_mm_word_bits(ra2, ma2, c2.y)) <= thres;
+                        }
+                        if (pass1) {
+                            const uint2 c2 = __ldg(A.ctx2 + i1);
+                            pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) +
+                                    __popc(bsx_mm_word_bits(rb2, mb2, c2.x)) + __popc(bsx_mm_word_bits(ra2, ma2, c2.y)) <= thres;
+                        }
+                        if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
+                    }
                     const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
                     // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
                     // (high -v); otherwise survivors go straight to the exact count

@@ -1,8 +1,10 @@
-// bsx_map_se.cu -- the single-end WGBS mapping kernel (SingleAlign::Do_Batch): everything inlined, RRBS code
-// compiled out (the kernel is instruction-cache sensitive: 90 KB of SASS with it).
+// bsx_map_se.cu -- the single-end WGBS mapping kernel (SingleAlign::Do_Batch): everything inlined, RRBS and
+// wide-context code compiled out (the kernel is instruction-cache and register sensitive: 90 KB of SASS with RRBS,
+// -7 % with the wide-context registers live in the list loop).
 #define BSX_BUILD_SE 1
 #define BSX_CALLS 0
 #define BSX_RRBS(A) 0
+#define BSX_WIDE(A) 0
 #define BSX_SE_KERNEL bsx_map_se_wgbs_kernel
 #define BSX_SE_OCC bsx_map_occupancy_se_wgbs
 #define BSX_SE_LAUNCH bsx_launch_map_se_wgbs

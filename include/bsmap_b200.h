@@ -132,10 +132,11 @@ const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k);
 uint32_t bsx_index_seq_size(const bsx_index *ix, uint32_t k);
 /* copy a device array to the host (parity tests): what = 0 refcat, 1 crefcat, 2 anchors (n_seq+1),
  * 3 tab (2*n_keys+1), 4 pos (n_entries), 5 RRBS tags (n_entries), 6 WGBS inline context (n_entries x 2 u32:
- * the 16 reference bases before and the 16 after each entry's seed) */
+ * the 16 reference bases before and the 16 after each entry's seed), 7 wide context (the next 16 bases outwards on
+ * either side; present when the index was built with -v >= 8) */
 int bsx_index_download(const bsx_index *ix, int what, void *dst, size_t bytes);
 /* device pointers + byte sizes of the arrays a replica needs (one-time NVLink broadcast):
- * order refcat, crefcat, tab, pos, tag, ctx (NULL/0 when absent).  Returns the count written (cap >= 6). */
+ * order refcat, crefcat, tab, pos, tag, ctx, ctx2 (NULL/0 when absent).  Returns the count written (cap >= 7). */
 int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap);
 /* replica on another device: allocates there and copies over NVLink with cudaMemcpyPeer */
 int bsx_index_replicate(const bsx_index *src, int device, bsx_index **out);

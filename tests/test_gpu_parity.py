@@ -81,6 +81,13 @@ def test_index_matches_oracle(name):
         s_ = kw.get("s", 16)
         assert np.array_equal(ctx[:, 0].astype(np.uint64), window(pos - 16)), "ctx.before differs"
         assert np.array_equal(ctx[:, 1].astype(np.uint64), window(pos + s_)), "ctx.after differs"
+        if kw.get("v", 2) >= 8:   # wide context: the next 16 bases outwards, built for high -v only
+            ctx2 = ix.download("ctx2").reshape(-1, 2)
+            assert np.array_equal(ctx2[:, 0].astype(np.uint64), window(pos - 32)), "ctx2.before differs"
+            assert np.array_equal(ctx2[:, 1].astype(np.uint64), window(pos + s_ + 16)), "ctx2.after differs"
+        else:
+            with pytest.raises(B.BsxError):
+                ix.download("ctx2")
     ix.close(); oref.close()
 
 

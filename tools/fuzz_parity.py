@@ -43,7 +43,7 @@ def one_round(rng, k):
     rrbs = rng.random() < 0.2
     paired = rng.random() < 0.35
     L = int(rng.choice([36, 50, 75, 100, 125, 144]))
-    kw = dict(v=int(rng.integers(0, 8)), w=int(rng.choice([1, 2, 3, 20, 100, 1000])), r=int(rng.integers(0, 2)),
+    kw = dict(v=int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15])), w=int(rng.choice([1, 2, 3, 20, 100, 1000])), r=int(rng.integers(0, 2)),
               S=int(rng.integers(1, 1000)), n=int(rng.random() < 0.25), f=int(rng.choice([0, 2, 5])),
               L=int(rng.choice([144, 144, 60, 90])))
     if rrbs:
