@@ -405,3 +405,8 @@ class Meth:
             self.close()
         except Exception:
             pass
+
+
+def sam_to_sorted_bam(sam_path: str, bam_path: str, threads: int = 0):
+    """SAM text -> coordinate-sorted BAM + .bai, the way `samtools view -bS | sort | index` (0.1.7) writes them"""
+    check(load().bsx_sam_to_sorted_bam(os.fsencode(sam_path), os.fsencode(bam_path), threads))

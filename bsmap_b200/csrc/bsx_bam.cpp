@@ -1,0 +1,323 @@
+// bsx_bam.cpp -- `-o out.bam`: SAM text -> coordinate-sorted BAM + BAI index, in process (output half).
+//
+// The reference writes SAM text into the .bam path and shells out to `sam2bam.sh` (main.cpp:466-473), i.e. the vendored
+// samtools 0.1.7: `view -bS` (bam_import.c sam_read1), `sort` (bam_sort.c: stable merge sort on (tid, pos)), `index`
+// (bam_index.c).  This file restates those three steps for BSMAP's own SAM output:
+//   * records are encoded exactly as sam_read1 does (bin from reg2bin / calend, 4-bit bases through bam_nt16_table,
+//     qualities - 33 or 0xff for '*', integer tags in the smallest type, mapped-without-CIGAR -> unmapped),
+//   * sorted stably by ((uint32)tid << 32 | pos + 1) so that unmapped reads (tid -1) go last,
+//   * written as BGZF with bgzf.c's blocking (64 KiB of input per block, header and records flowing through without a
+//     flush, an empty block at the end), the blocks deflated on all host threads,
+//   * indexed with bam_index_core's rules (bin chunks closed at every change of bin, 16 kb linear index that records
+//     windows after the first one a read overlaps -- a 0.1.7 trait -- and chunks merged when they share a block).
+// Decompressed, the BAM equals samtools' output byte for byte; the .bai holds the same bins, chunks and linear index
+// as `samtools index` computes for the file (tests/test_bam_output_cpu.py checks both against oracle/_ref/samtools).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+#include "bsx_internal.h"
+
+namespace {
+
+struct Nt16 { unsigned char t[256]; Nt16() { memset(t, 15, 256); const char *s = "=ACMGRSVTWYHKDBN"; for (int i = 0; s[i]; i++) { t[(unsigned char)s[i]] = (unsigned char)i; t[(unsigned char)tolower(s[i])] = (unsigned char)i; }
+                                              t['0'] = 1; t['1'] = 2; t['2'] = 4; t['3'] = 8; } };   // bam_nt16_table (bam_import.c:24-41), incl. its colour-space digits
+const Nt16 kNt16;
+
+inline int reg2bin(uint32_t beg, uint32_t end) {   // bam.h:648-657
+    --end;
+    if (beg >> 14 == end >> 14) return 4681 + (beg >> 14);
+    if (beg >> 17 == end >> 17) return 585 + (beg >> 17);
+    if (beg >> 20 == end >> 20) return 73 + (beg >> 20);
+    if (beg >> 23 == end >> 23) return 9 + (beg >> 23);
+    if (beg >> 26 == end >> 26) return 1 + (beg >> 26);
+    return 0;
+}
+
+struct Field { const char *p; size_t n; };
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+inline long to_long(const char *p, size_t n) { char b[32]; const size_t k = std::min<size_t>(n, 31); memcpy(b, p, k); b[k] = 0; return atol(b); }
+
+template <class T> inline void put(std::string &o, T v) { o.append(reinterpret_cast<const char *>(&v), sizeof v); }
+
+struct Rec { uint64_t key; uint32_t off, len; int32_t tid, pos, end; uint16_t bin; };   // end = calend (for the linear index)
+
+// one SAM line -> one BAM record appended to `out` (block_size first); false for lines that are not alignments
+bool encode(const char *b, const char *e, const std::unordered_map<std::string, int32_t> &tids, std::string &out, Rec &r) {
+    if (e > b && e[-1] == '\r') e--;
+    Field f[11]; int nf = 0;
+    const char *s = b;
+    while (nf < 11) { const char *t = (const char *)memchr(s, '\t', (size_t)(e - s)); if (!t) { f[nf++] = Field{s, (size_t)(e - s)}; s = e; break; } f[nf++] = Field{s, (size_t)(t - s)}; s = t + 1; }
+    if (nf < 11) return false;
+    const char *aux = s;                                             // rest of the line (may be empty)
+    auto tid_of = [&](Field x) -> int32_t { auto it = tids.find(std::string(x.p, x.n)); return it == tids.end() ? -1 : it->second; };
+    uint32_t flag;
+    { char tmp[32]; const size_t k = std::min<size_t>(f[1].n, 31); memcpy(tmp, f[1].p, k); tmp[k] = 0; char *endp; long v = strtol(tmp, &endp, 0); flag = *endp ? 0u : (uint32_t)v; }
+    const int32_t tid = tid_of(f[2]);
+    const int32_t pos = f[3].n && is_digit(f[3].p[0]) ? (int32_t)to_long(f[3].p, f[3].n) - 1 : -1;
+    const uint32_t mapq = f[4].n && is_digit(f[4].p[0]) ? (uint32_t)to_long(f[4].p, f[4].n) : 0;
+    std::vector<uint32_t> cigar;
+    uint32_t endpos = (uint32_t)pos;
+    int bin;
+    if (f[5].n && f[5].p[0] != '*') {
+        const char *c = f[5].p, *ce = f[5].p + f[5].n;
+        while (c < ce) {
+            long x = 0; while (c < ce && is_digit(*c)) x = x * 10 + (*c++ - '0');
+            if (c >= ce) break;
+            const char opc = (char)toupper((unsigned char)*c++);
+            int op; switch (opc) { case 'M': case '=': case 'X': op = 0; break; case 'I': op = 1; break; case 'D': op = 2; break; case 'N': op = 3; break;
+                                   case 'S': op = 4; break; case 'H': op = 5; break; case 'P': op = 6; break; default: return false; }
+            cigar.push_back((uint32_t)x << 4 | (uint32_t)op);
+            if (op == 0 || op == 2 || op == 3) endpos += (uint32_t)x;
+        }
+        bin = reg2bin((uint32_t)pos, endpos);
+    } else {
+        flag |= 0x4;                                                 // mapped sequence without CIGAR (bam_import.c:297-300)
+        bin = reg2bin((uint32_t)pos, (uint32_t)pos + 1);
+    }
+    const int32_t mtid = (f[6].n == 1 && f[6].p[0] == '=') ? tid : tid_of(f[6]);
+    const int32_t mpos = f[7].n && is_digit(f[7].p[0]) ? (int32_t)to_long(f[7].p, f[7].n) - 1 : -1;
+    const int32_t isize = f[8].n && (f[8].p[0] == '-' || is_digit(f[8].p[0])) ? (int32_t)to_long(f[8].p, f[8].n) : 0;
+    const bool has_seq = !(f[9].n == 1 && f[9].p[0] == '*');
+    const int32_t l_seq = has_seq ? (int32_t)f[9].n : 0;
+    const size_t start = out.size();
+    put<int32_t>(out, 0);                                            // block_size, patched below
+    put<int32_t>(out, tid); put<int32_t>(out, pos);
+    put<uint32_t>(out, (uint32_t)bin << 16 | (mapq & 0xff) << 8 | (uint32_t)((f[0].n + 1) & 0xff));
+    put<uint32_t>(out, (flag & 0xffff) << 16 | (uint32_t)(cigar.size() & 0xffff));
+    put<int32_t>(out, l_seq); put<int32_t>(out, mtid); put<int32_t>(out, mpos); put<int32_t>(out, isize);
+    out.append(f[0].p, f[0].n); out.push_back('\0');
+    for (uint32_t c : cigar) put<uint32_t>(out, c);
+    if (has_seq) {
+        for (int32_t i = 0; i < l_seq; i += 2) {
+            const unsigned hi = kNt16.t[(unsigned char)f[9].p[i]], lo = i + 1 < l_seq ? kNt16.t[(unsigned char)f[9].p[i + 1]] : 0u;
+            out.push_back((char)(hi << 4 | lo));
+        }
+        if (f[10].n == 1 && f[10].p[0] == '*') out.append((size_t)l_seq, (char)0xff);
+        else for (int32_t i = 0; i < l_seq; i++) out.push_back((char)((i < (int32_t)f[10].n ? f[10].p[i] : '!') - 33));
+    }
+    // auxiliary fields (bam_import.c:336-395)
+    for (const char *a = aux; a < e;) {
+        const char *t = (const char *)memchr(a, '\t', (size_t)(e - a)); if (!t) t = e;
+        const size_t n = (size_t)(t - a);
+        if (n >= 5 && a[2] == ':' && a[4] == ':') {
+            out.push_back(a[0]); out.push_back(a[1]);
+            const char type = a[3]; const char *v = a + 5; const size_t vn = n - 5;
+            if (type == 'A' || type == 'a' || type == 'c' || type == 'C') { out.push_back('A'); out.push_back(vn ? v[0] : '\0'); }
+            else if (type == 'I' || type == 'i') {
+                char tmp[32]; const size_t k = std::min<size_t>(vn, 31); memcpy(tmp, v, k); tmp[k] = 0;
+                const long long x = atoll(tmp);
+                if (x < 0) {
+                    if (x >= -127) { out.push_back('c'); put<int8_t>(out, (int8_t)x); }
+                    else if (x >= -32767) { out.push_back('s'); put<int16_t>(out, (int16_t)x); }
+                    else { out.push_back('i'); put<int32_t>(out, (int32_t)x); }
+                } else {
+                    if (x <= 255) { out.push_back('C'); put<uint8_t>(out, (uint8_t)x); }
+                    else if (x <= 65535) { out.push_back('S'); put<uint16_t>(out, (uint16_t)x); }
+                    else { out.push_back('I'); put<uint32_t>(out, (uint32_t)x); }
+                }
+            } else if (type == 'f') { char tmp[64]; const size_t k = std::min<size_t>(vn, 63); memcpy(tmp, v, k); tmp[k] = 0; out.push_back('f'); put<float>(out, (float)atof(tmp)); }
+            else if (type == 'd') { char tmp[64]; const size_t k = std::min<size_t>(vn, 63); memcpy(tmp, v, k); tmp[k] = 0; out.push_back('d'); put<double>(out, atof(tmp)); }
+            else if (type == 'Z' || type == 'H') { out.push_back(type); out.append(v, vn); out.push_back('\0'); }
+            else { out.resize(out.size() - 2); }
+        }
+        a = t < e ? t + 1 : e;
+    }
+    const int32_t block_size = (int32_t)(out.size() - start - 4);
+    memcpy(&out[start], &block_size, 4);
+    r.key = (uint64_t)(uint32_t)tid << 32 | (uint32_t)(pos + 1);
+    r.off = (uint32_t)start; r.len = (uint32_t)(out.size() - start);
+    r.tid = tid; r.pos = pos; r.end = (int32_t)endpos; r.bin = (uint16_t)bin;
+    return true;
+}
+
+// one BGZF block (bgzf.c deflate_block): header, raw deflate at the default level, CRC32, ISIZE
+bool bgzf_block(const unsigned char *in, size_t n, std::string &out) {
+    unsigned char buf[65536];
+    z_stream zs; memset(&zs, 0, sizeof zs);
+    zs.next_in = const_cast<unsigned char *>(in); zs.avail_in = (uInt)n;
+    zs.next_out = buf + 18; zs.avail_out = sizeof buf - 18 - 8;
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    const int st = deflate(&zs, Z_FINISH);
+    deflateEnd(&zs);
+    if (st != Z_STREAM_END) return false;                            // would not fit: the caller falls back to smaller input
+    const size_t clen = zs.total_out + 26;
+    static const unsigned char head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(buf, head, 16);
+    buf[16] = (unsigned char)((clen - 1) & 0xff); buf[17] = (unsigned char)((clen - 1) >> 8);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), in, (uInt)n), isz = (uint32_t)n;
+    memcpy(buf + clen - 8, &crc, 4); memcpy(buf + clen - 4, &isz, 4);
+    out.assign(reinterpret_cast<char *>(buf), clen);
+    return true;
+}
+
+}  // namespace
+
+extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path, int threads) {
+    if (!sam_path || !bam_path) { bsx_set_error("bsx_sam_to_sorted_bam: bad argument"); return BSX_ERR_ARG; }
+    threads = bsx_host_threads(threads);
+    const int fd = open(sam_path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) { bsx_set_error("cannot open %s", sam_path); return BSX_ERR_IO; }
+    const size_t n = (size_t)st.st_size;
+    const char *p = n ? (const char *)mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0) : "";
+    if (n && p == MAP_FAILED) { close(fd); bsx_set_error("mmap failed: %s", sam_path); return BSX_ERR_IO; }
+    // header: every leading '@' line verbatim (sam_header_read); @SQ lines define the reference dictionary
+    size_t q = 0;
+    std::vector<std::string> ref_names; std::vector<int32_t> ref_lens;
+    while (q < n && p[q] == '@') {
+        const void *nl = memchr(p + q, '\n', n - q);
+        const size_t le = nl ? (size_t)((const char *)nl - p) : n;
+        if (le - q >= 3 && memcmp(p + q, "@SQ", 3) == 0) {
+            std::string name; long len = 0;
+            for (size_t a = q; a < le;) {
+                const void *t = memchr(p + a, '\t', le - a); const size_t te = t ? (size_t)((const char *)t - p) : le;
+                if (te - a > 3 && memcmp(p + a, "SN:", 3) == 0) name.assign(p + a + 3, te - a - 3);
+                if (te - a > 3 && memcmp(p + a, "LN:", 3) == 0) len = to_long(p + a + 3, te - a - 3);
+                a = te + 1;
+            }
+            ref_names.push_back(name); ref_lens.push_back((int32_t)len);
+        }
+        q = nl ? le + 1 : n;
+    }
+    const size_t header_end = q;
+    std::unordered_map<std::string, int32_t> tids;
+    for (size_t k = 0; k < ref_names.size(); k++) tids.emplace(ref_names[k], (int32_t)k);   // first definition wins, like the hash in bam_aux.c
+
+    // records: byte ranges cut at line starts, one per thread
+    std::vector<std::string> enc((size_t)threads); std::vector<std::vector<Rec>> recs((size_t)threads);
+    const int tn = (n - header_end) < ((size_t)1 << 20) ? 1 : threads;
+    bsx_parallel(tn, (size_t)tn, [&](int t, size_t, size_t) {
+        size_t b = header_end + (n - header_end) * (size_t)t / tn, e = header_end + (n - header_end) * (size_t)(t + 1) / tn;
+        if (t > 0) { const void *x = memchr(p + b - 1, '\n', n - (b - 1)); b = x ? (size_t)((const char *)x - p) + 1 : n; }
+        if (t + 1 < tn) { const void *x = memchr(p + e - 1, '\n', n - (e - 1)); e = x ? (size_t)((const char *)x - p) + 1 : n; }
+        enc[t].reserve((e > b ? e - b : 0) + 1024);
+        while (b < e) {
+            const void *x = memchr(p + b, '\n', n - b);
+            const size_t le = x ? (size_t)((const char *)x - p) : n;
+            Rec r;
+            if (le > b && encode(p + b, p + le, tids, enc[t], r)) recs[t].push_back(r);
+            b = le + 1;
+        }
+    });
+    // stable sort by (tid, pos + 1): (key, thread, index) order = input order for equal keys
+    struct Ord { uint64_t key; uint32_t t, i; };
+    std::vector<Ord> ord;
+    { size_t tot = 0; for (auto &v : recs) tot += v.size(); ord.reserve(tot); }
+    for (int t = 0; t < threads; t++) for (uint32_t i = 0; i < recs[t].size(); i++) ord.push_back(Ord{recs[t][i].key, (uint32_t)t, i});
+    std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.key < b.key; });
+
+    // the uncompressed stream: header, then records; remember where every record starts
+    std::string raw;
+    raw.append("BAM\1", 4);
+    put<int32_t>(raw, (int32_t)header_end); raw.append(p, header_end);
+    put<int32_t>(raw, (int32_t)ref_names.size());
+    for (size_t k = 0; k < ref_names.size(); k++) { put<int32_t>(raw, (int32_t)ref_names[k].size() + 1); raw.append(ref_names[k]); raw.push_back('\0'); put<int32_t>(raw, ref_lens[k]); }
+    std::vector<uint64_t> at(ord.size() + 1);
+    { size_t tot = raw.size(); for (const Ord &o : ord) tot += recs[o.t][o.i].len; raw.reserve(tot); }
+    for (size_t k = 0; k < ord.size(); k++) { const Rec &r = recs[ord[k].t][ord[k].i]; at[k] = raw.size(); raw.append(enc[ord[k].t], r.off, r.len); }
+    at[ord.size()] = raw.size();
+    if (n) munmap((void *)p, n);
+    close(fd);
+
+    // BGZF: 64 KiB of input per block, deflated in parallel; a block that does not fit is redone serially the way
+    // bgzf.c does (1 KiB less input at a time), which shifts every later boundary -- never seen on BAM data
+    const size_t BLK = 65536;
+    size_t nblk = (raw.size() + BLK - 1) / BLK;
+    std::vector<std::string> comp(nblk);
+    std::vector<size_t> blk_in_start(nblk + 1);
+    std::vector<char> okv(nblk, 1);
+    bsx_parallel(threads, nblk, [&](int, size_t b, size_t e) {
+        for (size_t k = b; k < e; k++) okv[k] = bgzf_block((const unsigned char *)raw.data() + k * BLK, std::min(BLK, raw.size() - k * BLK), comp[k]) ? 1 : 0;
+    });
+    bool regular = true; for (char c : okv) regular = regular && c;
+    if (regular) { for (size_t k = 0; k <= nblk; k++) blk_in_start[k] = std::min(k * BLK, raw.size()); }
+    else {
+        comp.clear(); blk_in_start.clear();
+        for (size_t pos = 0; pos < raw.size();) {
+            size_t len = std::min(BLK, raw.size() - pos); std::string c;
+            while (!bgzf_block((const unsigned char *)raw.data() + pos, len, c)) { if (len <= 1024) { bsx_set_error("BGZF: input reduction failed"); return BSX_ERR_IO; } len -= 1024; }
+            blk_in_start.push_back(pos); comp.push_back(c); pos += len;
+        }
+        blk_in_start.push_back(raw.size()); nblk = comp.size();
+    }
+    std::vector<uint64_t> blk_file_start(nblk + 1, 0);
+    for (size_t k = 0; k < nblk; k++) blk_file_start[k + 1] = blk_file_start[k] + comp[k].size();
+    std::string eof_block; bgzf_block((const unsigned char *)"", 0, eof_block);
+    FILE *fo = fopen(bam_path, "wb");
+    if (!fo) { bsx_set_error("cannot write %s", bam_path); return BSX_ERR_IO; }
+    for (const std::string &c : comp) fwrite(c.data(), 1, c.size(), fo);
+    fwrite(eof_block.data(), 1, eof_block.size(), fo);
+    if (fclose(fo) != 0) { bsx_set_error("write to %s failed", bam_path); return BSX_ERR_IO; }
+
+    // ---- index (bam_index_core, bam_index.c:133-190)
+    struct Chunk { uint64_t u, v; };
+    const size_t nref = ref_names.size();
+    std::vector<std::map<uint32_t, std::vector<Chunk>>> bins(nref);
+    std::vector<std::vector<uint64_t>> lidx(nref);
+    std::vector<int32_t> lidx_n(nref, 0);
+    {
+        uint32_t last_bin = 0xffffffffu, save_bin = 0xffffffffu; int32_t last_tid = -2 /* 0xffffffff in the source */, save_tid = -2;
+        bool first = true;
+        uint64_t save_off, last_off;
+        // reader-side tell(): the offset of a record start as the *reader* sees it (start of the next block when the
+        // previous one is exhausted), which is what bam_index_core records
+        auto rtell = [&](uint64_t x) -> uint64_t {
+            size_t k = (size_t)(std::upper_bound(blk_in_start.begin(), blk_in_start.end(), x) - blk_in_start.begin()) - 1;
+            if (k >= nblk) return blk_file_start[nblk] << 16;
+            return blk_file_start[k] << 16 | (x - blk_in_start[k]);
+        };
+        save_off = last_off = rtell(at.empty() ? raw.size() : at[0]);
+        for (size_t k = 0; k < ord.size(); k++) {
+            const Rec &r = recs[ord[k].t][ord[k].i];
+            if (first || last_tid != r.tid) { last_tid = r.tid; last_bin = 0xffffffffu; first = false; }
+            if (r.tid >= 0 && r.bin < 4681) {                          // insert_offset2 (bam_index.c:89-104)
+                const int beg = r.pos >> 14, end = (int)(((uint32_t)r.end - 1) >> 14);
+                std::vector<uint64_t> &lx = lidx[r.tid];
+                if ((int)lx.size() < end + 1) lx.resize((size_t)end + 1, 0);
+                for (int i = beg + 1; i <= end; i++) if (lx[i] == 0) lx[i] = last_off;
+                lidx_n[r.tid] = end + 1;
+            }
+            if (r.bin != last_bin) {
+                if (save_bin != 0xffffffffu) bins[save_tid][save_bin].push_back(Chunk{save_off, last_off});
+                save_off = last_off; save_bin = last_bin = r.bin; save_tid = r.tid;
+                if (save_tid < 0) break;
+            }
+            last_off = rtell(at[k + 1]);
+        }
+        // the loop ran into the end of the file: the reader has swallowed the empty EOF block too (bgzf_read), so its tell()
+        // is the file size
+        if (save_tid >= 0 && save_bin != 0xffffffffu)
+            bins[save_tid][save_bin].push_back(Chunk{save_off, (blk_file_start[nblk] + eof_block.size()) << 16});
+    }
+    const std::string bai_path = std::string(bam_path) + ".bai";
+    FILE *fi = fopen(bai_path.c_str(), "wb");
+    if (!fi) { bsx_set_error("cannot write %s", bai_path.c_str()); return BSX_ERR_IO; }
+    fwrite("BAI\1", 1, 4, fi);
+    { const int32_t x = (int32_t)nref; fwrite(&x, 4, 1, fi); }
+    for (size_t t = 0; t < nref; t++) {
+        const int32_t nb = (int32_t)bins[t].size(); fwrite(&nb, 4, 1, fi);
+        for (auto &kv : bins[t]) {
+            std::vector<Chunk> &l = kv.second;                        // merge_chunks, BAM_VIRTUAL_OFFSET16: same block -> one chunk
+            size_t m = 0;
+            for (size_t i = 1; i < l.size(); i++) { if (l[m].v >> 16 == l[i].u >> 16) l[m].v = l[i].v; else l[++m] = l[i]; }
+            l.resize(l.empty() ? 0 : m + 1);
+            const uint32_t bin = kv.first; const int32_t nc = (int32_t)l.size();
+            fwrite(&bin, 4, 1, fi); fwrite(&nc, 4, 1, fi);
+            for (const Chunk &c : l) { fwrite(&c.u, 8, 1, fi); fwrite(&c.v, 8, 1, fi); }
+        }
+        const int32_t nl = lidx_n[t]; fwrite(&nl, 4, 1, fi);
+        for (int32_t i = 0; i < nl; i++) { const uint64_t v = i < (int32_t)lidx[t].size() ? lidx[t][i] : 0; fwrite(&v, 8, 1, fi); }
+    }
+    if (fclose(fi) != 0) { bsx_set_error("write to %s failed", bai_path.c_str()); return BSX_ERR_IO; }
+    return BSX_OK;
+}

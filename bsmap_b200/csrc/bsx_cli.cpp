@@ -4,8 +4,9 @@
 // (SAM when -o ends in .sam, BSP otherwise; -2 for unpaired BSP hits).  Reads are parsed with the
 // reference's token semantics (reads.cpp:83-146), mapped in large batches on the GPU, formatted on
 // the host and written in input order (= the reference with -p 1).
-// Out of scope (errors out): SAM text input (broken in the reference too: it is opened as BAM), .bam output,
-// -q quality trimming, -M other than TC.
+// `-o x.bam` writes a coordinate-sorted BAM and its .bai in process (bsx_bam.cpp).
+// Out of scope (errors out): SAM text input (broken in the reference too: it is opened as BAM), -q quality
+// trimming, -M other than TC.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,7 @@ struct Opts {
     std::string a, b, d, o, o2;
     unsigned read_start = 1, read_end = ~0u;
     int num_procs = 0, zero_qual = '!', qual_threshold = 0;   // -p: host threads (0 = all cores)
+    std::string bam_out;         // -o x.bam: SAM text goes to a temporary file, then bsx_sam_to_sorted_bam (the reference: sam2bam.sh)
     std::string meth_out;        // --methratio FILE: methylation ratios straight from the device (no SAM needed)
     bsx_meth_opts mo;
     unsigned batch = 1u << 17;   // reads per GPU batch: small enough to keep the three host stages overlapped
@@ -177,7 +179,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     if (o.qual_threshold != 0) { fprintf(stderr, "-q quality trimming is not supported by the GPU path\n"); return 1; }
     if (o.o.size() > 4) {
         if (o.o.compare(o.o.size() - 4, 4, ".sam") == 0) o.p.out_sam = 1;
-        else if (o.o.compare(o.o.size() - 4, 4, ".bam") == 0) { fprintf(stderr, ".bam output is not supported; write .sam and convert\n"); return 1; }
+        else if (o.o.compare(o.o.size() - 4, 4, ".bam") == 0) { o.p.out_sam = 1; o.bam_out = o.o; o.o += ".sam.tmp"; }   // param.out_sam = 2 (main.cpp:295)
     }
     // the CUDA context comes up on its own thread while this one parses the reference FASTA
     bsx_index *ix = nullptr;
@@ -371,6 +373,13 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     else printf("Total number of aligned reads: %llu (%.2g%%)\n", n_aligned, 100.0 * n_aligned / tot);
     printf("Done.\n");
     { time_t t = time(nullptr); printf("Finished at %s", ctime(&t)); }
+    if (!o.bam_out.empty()) {   // main.cpp:466-473: convert, sort by coordinate, index
+        const double t = now();
+        printf("Converting SAM to BAM ...\nSorting BAM ...\nIndexing BAM ...\n");
+        if (bsx_sam_to_sorted_bam(o.o.c_str(), o.bam_out.c_str(), threads) != BSX_OK) { fprintf(stderr, "%s\n%s remains in SAM format.\n", bsx_last_error(), o.o.c_str()); return 1; }
+        remove(o.o.c_str());
+        if (timing) fprintf(stderr, "[bsx timing] SAM -> sorted BAM + BAI %.3f s\n", now() - t);
+    }
     printf("Total time consumed:  %ld secs\n", (long)(time(nullptr) - t0));
     const double t_fin = now();
     bsx_mapper_destroy(mp); bsx_index_destroy(ix);

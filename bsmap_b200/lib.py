@@ -64,7 +64,7 @@ EXPORTS = [
     "bsx_reads_open", "bsx_reads_close", "bsx_reads_kind", "bsx_reads_skip", "bsx_reads_force_token_reader", "bsx_reads_set_readset",
     "bsx_reads_next", "bsx_reads_get", "bsx_emit_se", "bsx_emit_pe",
     "bsx_index_create_packed", "bsx_index_save_packed", "bsx_index_create_from_packed", "bsx_meth_opts_default", "bsx_meth_create", "bsx_meth_destroy", "bsx_meth_add", "bsx_meth_download",
-    "bsx_meth_write", "bsx_methratio_main", "bsx_mapper_attach_meth", "bsx_meth_valid_count",
+    "bsx_meth_write", "bsx_methratio_main", "bsx_sam_to_sorted_bam", "bsx_mapper_attach_meth", "bsx_meth_valid_count",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load():
     L.bsx_meth_destroy.argtypes = [vp]
     L.bsx_meth_add.argtypes = [vp, C.POINTER(MethOpts), u32, vp, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
     L.bsx_meth_download.argtypes = [vp, C.POINTER(MethOpts), u32, vp, vp]
+    L.bsx_sam_to_sorted_bam.argtypes = [C.c_char_p, C.c_char_p, i32]
     L.bsx_mapper_attach_meth.argtypes = [vp, vp, C.POINTER(MethOpts), i32]
     L.bsx_meth_valid_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.bsx_meth_write.restype = sz

@@ -215,6 +215,11 @@ size_t bsx_emit_pe(const bsx_index *ix, const bsx_params *p, const bsx_reads *a,
                    const uint16_t *counts_a, const uint16_t *counts_b, int threads, int fd, int fd_unpair,
                    uint32_t *n_stats /* pairs, single a, single b */);
 
+/* --- `-o out.bam` (main.cpp:466-473: the reference shells out to sam2bam.sh = samtools view -bS | sort | index) ---- */
+/* SAM text (BSMAP's own output) -> coordinate-sorted BAM at bam_path plus bam_path.bai, encoded, ordered, blocked and
+ * indexed the way samtools 0.1.7 does it; the BGZF blocks are deflated on `threads` host threads. */
+int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path, int threads);
+
 /* --- methratio.py (methylation ratios from the mappings) on the device -------------------------- */
 typedef struct bsx_meth_opts {   /* methratio.py:5-16; -r (remove duplicates) is not supported */
     int32_t unique;        /* -u  process only unique mappings / pairs                         */

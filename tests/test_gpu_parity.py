@@ -279,6 +279,21 @@ def test_cli_bam_read_input(tmp_path, name):
     assert got == exp, R.first_diff(got, exp)
 
 
+def test_cli_bam_output(tmp_path):
+    """-o out.bam: coordinate-sorted BAM + .bai in process; decompressed it equals what samtools 0.1.7 (the reference's
+    sam2bam.sh) makes of the reference's SAM for the same run (digest committed by tests/test_bam_output_cpu.py)"""
+    import gzip, hashlib, json
+    case = CS.BY_NAME["pe_sam"]
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    out = str(tmp_path / "out.bam")
+    r = subprocess.run([exe] + case.cli(a, b, fa, out, None), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    digests = json.load(open(os.path.join(R.GOLDEN, "bam_output_sha256.json")))
+    assert hashlib.sha256(gzip.open(out, "rb").read()).hexdigest() == digests["pe_sam"]
+    assert os.path.exists(out + ".bai") and not os.path.exists(out + ".sam.tmp")
+
+
 def test_cli_reference_cache(tmp_path):
     """BSX_REF_CACHE: the second run starts from the packed reference and writes the same file"""
     case = CS.BY_NAME["se_cfg2_r0_uR"]
