@@ -49,7 +49,7 @@ inline long to_long(const char *p, size_t n) { char b[32]; const size_t k = std:
 
 template <class T> inline void put(std::string &o, T v) { o.append(reinterpret_cast<const char *>(&v), sizeof v); }
 
-struct Rec { uint64_t key; uint32_t off, len; int32_t tid, pos, end; uint16_t bin; };   // end = calend (for the linear index)
+struct Rec { uint64_t key, off; uint32_t len; int32_t tid, pos, end; uint16_t bin; };   // end = calend (for the linear index)
 
 // one SAM line -> one BAM record appended to `out` (block_size first); false for lines that are not alignments
 bool encode(const char *b, const char *e, const std::unordered_map<std::string, int32_t> &tids, std::string &out, Rec &r) {
@@ -135,7 +135,7 @@ bool encode(const char *b, const char *e, const std::unordered_map<std::string, 
     const int32_t block_size = (int32_t)(out.size() - start - 4);
     memcpy(&out[start], &block_size, 4);
     r.key = (uint64_t)(uint32_t)tid << 32 | (uint32_t)(pos + 1);
-    r.off = (uint32_t)start; r.len = (uint32_t)(out.size() - start);
+    r.off = start; r.len = (uint32_t)(out.size() - start);
     r.tid = tid; r.pos = pos; r.end = (int32_t)endpos; r.bin = (uint16_t)bin;
     return true;
 }
