@@ -3,10 +3,10 @@
 the unmodified reference binary (oracle/_ref/bsmap -p <cores>) vs the bsmap_b200 drop-in CLI, same FASTA /
 FASTQ files, wall clock of the whole process, outputs compared byte for byte (reference at -p 1 for order).
 
-    python tools/cli_bench.py [--reads 2000000] [--len 50] [--genome-mb 5]
+    python tests/cli_bench.py [--reads 2000000] [--len 50] [--genome-mb 5]
 """
 import argparse, hashlib, json, os, subprocess, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this script lives in tests/)
 sys.path.insert(0, ROOT)
 import torch
 from bsmap_b200 import synth

@@ -3,7 +3,7 @@
 adapters, N-rich and trimmed reads, single- and paired-end, WGBS and RRBS.  Records, per-level counts and the
 candidate counter must agree exactly.
 
-    python tools/fuzz_parity.py [--rounds 40] [--seed 1]
+    python tests/fuzz_parity.py [--rounds 40] [--seed 1]
 """
 import argparse
 import os
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this script lives in tests/)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O      # noqa: E402  (test infrastructure: the checker)
 import bsmap_b200 as B      # noqa: E402

@@ -2,10 +2,10 @@
 """Whole-process timing of the `methratio` command line (GPU pile-up) on BSMAP SAM output, next to the numpy
 restatement of the reference's methratio.py (oracle/methratio_oracle.py, one host core, bounded sample).
 
-    python tools/methratio_bench.py [--reads 4000000] [--len 100] [--genome-mb 200]
+    python tests/methratio_bench.py [--reads 4000000] [--len 100] [--genome-mb 200]
 """
 import argparse, hashlib, json, os, subprocess, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this script lives in tests/)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 from bsmap_b200 import synth
