@@ -139,6 +139,26 @@ def cpu_map_parallel(oref, buf, lens, first_index, threads):
     return dt, np.sum(stats, axis=0)
 
 
+def bind_near_gpu(torch, local):
+    """Host side of the end-to-end path: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA
+    node its GPU hangs off, so that eight ranks do not pull their input through one socket.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(local).pci_bus_id.encode()
+                                                 if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id")
+                                                 else pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -154,6 +174,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_near_gpu(torch, local) if world > 1 else 0
     multi = world > 1 and a.impl == "ours"
     if multi:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -215,6 +236,8 @@ def main():
     cfg = {"workload": f"cfg2: {a.chroms}x{a.chrom_mb:g}Mb synthetic genome, {n} x {L_READ}nt SE reads per GPU per step, -s 16 -v 5 -I 4",
            "l2_policy": "working set larger than L2 (index 21 GB + 2.2 GB reads per step vs 126 MB L2)",
            "reads_per_gpu_per_step": n, "genome_bp": sum(lens)}
+    if numa_cpus:
+        cfg["host_binding"] = f"each rank pinned to the {numa_cpus} CPUs NVML reports as local to its GPU (pinned buffers first-touched there)"
 
     # =====================================================================================
     if a.impl == "reference":
