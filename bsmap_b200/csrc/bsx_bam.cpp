@@ -209,23 +209,39 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
             b = le + 1;
         }
     });
-    // stable sort by (tid, pos + 1): (key, thread, index) order = input order for equal keys
+    // stable sort by (tid, pos + 1).  (key, thread, index) is a total order that equals input order on equal keys, so
+    // the threads sort slices with a plain sort and the slices are merged pairwise, level by level, in parallel.
     struct Ord { uint64_t key; uint32_t t, i; };
+    auto before = [](const Ord &a, const Ord &b) { return a.key != b.key ? a.key < b.key : (a.t != b.t ? a.t < b.t : a.i < b.i); };
     std::vector<Ord> ord;
     { size_t tot = 0; for (auto &v : recs) tot += v.size(); ord.reserve(tot); }
     for (int t = 0; t < threads; t++) for (uint32_t i = 0; i < recs[t].size(); i++) ord.push_back(Ord{recs[t][i].key, (uint32_t)t, i});
-    std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.key < b.key; });
+    {
+        const size_t N = ord.size();
+        const int S = N < ((size_t)1 << 16) ? 1 : threads;
+        std::vector<size_t> cut((size_t)S + 1);
+        for (int k = 0; k <= S; k++) cut[k] = N * (size_t)k / S;
+        bsx_parallel(S, (size_t)S, [&](int k, size_t, size_t) { std::sort(ord.begin() + cut[k], ord.begin() + cut[k + 1], before); });
+        for (int w = 1; w < S; w *= 2) {
+            const int pairs = (S + 2 * w - 1) / (2 * w);
+            bsx_parallel(pairs, (size_t)pairs, [&](int q, size_t, size_t) {
+                const int lo = q * 2 * w, mid = std::min(lo + w, S), hi = std::min(lo + 2 * w, S);
+                if (mid < hi) std::inplace_merge(ord.begin() + cut[lo], ord.begin() + cut[mid], ord.begin() + cut[hi], before);
+            });
+        }
+    }
 
-    // the uncompressed stream: header, then records; remember where every record starts
+    // the uncompressed stream: header, then records (copied to their final offsets in parallel)
     std::string raw;
     raw.append("BAM\1", 4);
     put<int32_t>(raw, (int32_t)header_end); raw.append(p, header_end);
     put<int32_t>(raw, (int32_t)ref_names.size());
     for (size_t k = 0; k < ref_names.size(); k++) { put<int32_t>(raw, (int32_t)ref_names[k].size() + 1); raw.append(ref_names[k]); raw.push_back('\0'); put<int32_t>(raw, ref_lens[k]); }
     std::vector<uint64_t> at(ord.size() + 1);
-    { size_t tot = raw.size(); for (const Ord &o : ord) tot += recs[o.t][o.i].len; raw.reserve(tot); }
-    for (size_t k = 0; k < ord.size(); k++) { const Rec &r = recs[ord[k].t][ord[k].i]; at[k] = raw.size(); raw.append(enc[ord[k].t], r.off, r.len); }
-    at[ord.size()] = raw.size();
+    { uint64_t off = raw.size(); for (size_t k = 0; k < ord.size(); k++) { at[k] = off; off += recs[ord[k].t][ord[k].i].len; } at[ord.size()] = off; raw.resize((size_t)off); }
+    bsx_parallel(threads, ord.size(), [&](int, size_t b, size_t e) {
+        for (size_t k = b; k < e; k++) { const Rec &r = recs[ord[k].t][ord[k].i]; memcpy(&raw[(size_t)at[k]], enc[ord[k].t].data() + r.off, r.len); }
+    });
     if (n) munmap((void *)p, n);
     close(fd);
 
