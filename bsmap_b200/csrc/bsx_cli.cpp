@@ -271,8 +271,12 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     // pinned staging: one upload buffer per mate (the map call returns after its copies), three result slots
     // (slot k is read by the formatter while k+1 waits in the channel and k+2 is being mapped)
     const int NSLOT = 3;
-    char *sa = pinned<char>((size_t)o.batch * stride), *sb = pe ? pinned<char>((size_t)o.batch * stride) : nullptr;
-    uint16_t *la = pinned<uint16_t>(o.batch), *lb = pe ? pinned<uint16_t>(o.batch) : nullptr;
+    // three upload buffers per mate as well: batch k is cut while k-1 waits for the mapper thread and k-2 is being mapped
+    char *sa[NSLOT], *sb[NSLOT]; uint16_t *la[NSLOT], *lb[NSLOT];
+    for (int k = 0; k < NSLOT; k++) {
+        sa[k] = pinned<char>((size_t)o.batch * stride); la[k] = pinned<uint16_t>(o.batch);
+        sb[k] = pe ? pinned<char>((size_t)o.batch * stride) : nullptr; lb[k] = pe ? pinned<uint16_t>(o.batch) : nullptr;
+    }
     bsx_rec *reca[NSLOT], *recb[NSLOT]; bsx_pair_rec *recp[NSLOT]; uint16_t *cnta[NSLOT], *cntb[NSLOT];
     const bool want_counts = !p.out_sam;   // per-level hit counts are a BSP column
     for (int k = 0; k < NSLOT; k++) {
@@ -321,29 +325,45 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
             printf("%u reads finished. %ld secs passed\n", tx.done_index, (long)(time(nullptr) - t0));
         }
     });
+    // cut (this thread) || map (mapper thread) || format || write
+    struct CutJob { uint32_t n = 0; unsigned first = 0, done_index = 0; int slot = 0; Views a, b; };
+    Chan<CutJob> cuts(1);
     int fail = 0;
-    for (unsigned k = 0;; k++) {
+    std::thread mapper([&] {
+        CutJob c;
+        while (cuts.pop(c)) {
+            if (fail) continue;                                     // drain so that the cutter never blocks
+            const double t = now();
+            const int s = c.slot;
+            int mrc;
+            if (!pe) mrc = bsx_map_se(mp, c.n, sa[s], la[s], c.first, 0, reca[s], cnta[s]);
+            else mrc = bsx_map_pe(mp, c.n, sa[s], la[s], sb[s], lb[s], c.first, recp[s], reca[s], recb[s], cnta[s], cntb[s]);
+            t_map += now() - t;
+            if (mrc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); fail = 1; continue; }
+            Job j; j.n = c.n; j.slot = s; j.done_index = c.done_index;
+            j.a = std::move(c.a); j.b = std::move(c.b);
+            jobs.push(std::move(j));
+        }
+        jobs.close();
+    });
+    for (unsigned k = 0; !fail; k++) {
         const unsigned first = index_a;
         const unsigned want = (unsigned)std::min<unsigned long long>(o.batch, index_a < o.read_end ? (unsigned long long)o.read_end - index_a : 0);
         if (!want) break;
-        double t = now();
-        const unsigned n1 = bsx_reads_next(ra, want, stride, sa, la, threads);
-        const unsigned n2 = pe ? bsx_reads_next(rb, want, stride, sb, lb, threads) : n1;
+        const int slot = (int)(k % NSLOT);
+        const double t = now();
+        const unsigned n1 = bsx_reads_next(ra, want, stride, sa[slot], la[slot], threads);
+        const unsigned n2 = pe ? bsx_reads_next(rb, want, stride, sb[slot], lb[slot], threads) : n1;
         t_parse += now() - t;
         if (!n1 || n1 != n2) break;
         index_a += n1;
-        const int slot = (int)(k % NSLOT);
-        t = now();
-        if (!pe) rc = bsx_map_se(mp, n1, sa, la, first, 0, reca[slot], cnta[slot]);
-        else rc = bsx_map_pe(mp, n1, sa, la, sb, lb, first, recp[slot], reca[slot], recb[slot], cnta[slot], cntb[slot]);
-        t_map += now() - t;
-        if (rc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); fail = 1; break; }
-        Job j; j.n = n1; j.slot = slot; j.done_index = index_a - o.read_start + 1;
-        take_views(ra, j.a); if (pe) take_views(rb, j.b);
-        jobs.push(std::move(j));
+        CutJob c; c.n = n1; c.first = first; c.slot = slot; c.done_index = index_a - o.read_start + 1;
+        take_views(ra, c.a); if (pe) take_views(rb, c.b);
+        cuts.push(std::move(c));
     }
+    cuts.close();
+    mapper.join();
     const double t_loop = now();
-    jobs.close();
     formatter.join(); writer.join();
     fclose(fout); if (fun) fclose(fun);
     const double t_drain = now();
