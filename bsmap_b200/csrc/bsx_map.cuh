@@ -69,6 +69,8 @@ struct PrepCol {
     uint32_t rw[BSX_FIXWORDS][32], m5[BSX_FIXWORDS][32];
 };
 
+static_assert(sizeof(PrepCol) >= 4 * 32 * 16, "the align phase stages list heads (4 lists x 32 uint4) in the idle PrepCol");
+
 // per-warp scratch of the align kernels
 struct SelSm {
     uint16_t npairs[32];              // PE: _cur_n_hits[2*MAXSNPS+1]

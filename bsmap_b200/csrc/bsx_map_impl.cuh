@@ -58,6 +58,10 @@
 #ifndef BSX_SE_MIN_CTAS
 #define BSX_SE_MIN_CTAS 5
 #endif
+#ifndef BSX_STAGE
+#define BSX_STAGE 1             // the heads of up to BSX_STAGE_LISTS position lists are fetched together (cp.async -> shared memory)
+#endif
+#define BSX_STAGE_LISTS 4       // 4 x 64 entries x 8 B = 2 KB per warp: aliases the prepare phase's PrepCol
 
 #include "bsx_prep.cuh"
 
@@ -95,6 +99,15 @@ __device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
 #else
     return __ldg(p);
 #endif
+}
+
+// Asynchronous 16-byte copy global -> shared (LDGSTS, bypasses L1 and the register file): the warp requests the heads
+// of all lists of a group back to back and waits once, instead of one DRAM round trip per list.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ const CtaSm *cta_tables() {   // the CTA's tables sit at the start of dynamic shared memory
@@ -372,7 +385,7 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
 // rc entries, sub-seed 1's, ...), 64 table entries per step (two per lane).  Everything that depends on
 // the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
 // work is one 8-byte load, two masked XOR/popcount words and a compare.
-__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C) {
+__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, uint4 *stage) {
     const int per = BSX_RRBS(A) ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
@@ -382,6 +395,21 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
         int ret = 0;
         #pragma unroll 1
         for (int i = 0; i < per && !ret; i++) {
+#if BSX_STAGE
+            if (!BSX_RRBS(A) && !BSX_WIDE(A) && (i & (BSX_STAGE_LISTS - 1)) == 0) {
+                // the first 64 entries (from an even index: 16-byte copies, two entries per lane) of this list and the
+                // next three: one DRAM round trip for the group instead of one per list
+                __syncwarp();
+                #pragma unroll 1
+                for (int k = 0; k < BSX_STAGE_LISTS && i + k < per; k++) {
+                    const uint4 ek = plan[i + k];
+                    const uint32_t g = (ek.x & ~1u) + 2u * (uint32_t)lane;
+                    if (g < ek.z) cp_async16(stage + k * 32 + lane, A.ctx + g);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+            }
+#endif
             const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
             const uint32_t p = e.w & 0xffffu;
@@ -399,6 +427,10 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                 // `> snp_thres` rejects exactly like the reference; pos[] and the reference are only touched by
                 // survivors.  Every entry of the list is a candidate, so the counters need no per-step work.
                 uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
+#if BSX_STAGE
+                if (!BSX_WIDE(A)) c0 &= ~1u;                              // steps start at the even index the staged head starts at
+                const uint2 *head = reinterpret_cast<const uint2 *>(stage + (i & (BSX_STAGE_LISTS - 1)) * 32);
+#endif
                 uint32_t rb2 = 0, mb2 = 0, ra2 = 0, ma2 = 0; bool have_f2 = false;     // wide-context flanks of this list, set up on first use
                 // high -v workloads walk lists of thousands of entries: there the next step's context is requested before
                 // this step is evaluated (on config 2's ~1.4-step lists the same pipelining measured -7 %)
@@ -416,10 +448,16 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                         if (i0 + 64 < e.z) nx0 = ld_stream(A.ctx + i0 + 64);
                         if (i1 + 64 < e.z) nx1 = ld_stream(A.ctx + i1 + 64);
                     } else {
-                        if (i0 < e.z) cx0 = ld_stream(A.ctx + i0);
-                        if (i1 < e.z) cx1 = ld_stream(A.ctx + i1);
+#if BSX_STAGE
+                        if (c0 <= e.x) { cx0 = head[lane]; cx1 = head[lane + 32]; }         // first step: staged (entries past the end are stale, masked below)
+                        else
+#endif
+                        {
+                            if (i0 < e.z) cx0 = ld_stream(A.ctx + i0);
+                            if (i1 < e.z) cx1 = ld_stream(A.ctx + i1);
+                        }
                     }
-                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
+                    if (i0 >= e.x && i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
                     if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
                     if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
                     if (BSX_WIDE(A)) {
@@ -524,10 +562,10 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
 }
 
 // SingleAlign::RunAlign (align.cpp:435-452): the mode loop (everything before it happened in the prepare kernel)
-__device__ BSX_FN void run_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C) {
+__device__ BSX_FN void run_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint4 *stage) {
     #pragma unroll 1
     for (int m = 0; m < R->seedseg; m++) {
-        snp_align(A, R, hits, dd, store_all, m, lane, C);
+        snp_align(A, R, hits, dd, store_all, m, lane, C, stage);
         if (!BSX_RRBS(A) && R->best <= m) return;       // a bucket <= m is non-empty (align.cpp:448)
     }
 }
@@ -592,7 +630,7 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
             const uint32_t r = r0 + i;
             if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
             load_image(A, R, scratch + (size_t)i * A.read_smem, lane);
-            if (!R->filtered) run_align(A, R, hits, dd, 0, lane, C);
+            if (!R->filtered) run_align(A, R, hits, dd, 0, lane, C, reinterpret_cast<uint4 *>(P));
             __syncwarp();
             write_record(A, R,  hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
             if (!R->filtered && R->best <= R->rmsn) CTR_ADD(C, CT_MAPPED, 1);
@@ -765,8 +803,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             const int maxi = max(Ra->rmsn, Rb->rmsn);
             #pragma unroll 1
             for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Ra->seedseg) snp_align(A, Ra, hits_a, dd_a, 1, i, lane, C);
-                if (i < Rb->seedseg) snp_align(A, Rb, hits_b, dd_b, 1, i, lane, C);
+                if (i < Ra->seedseg) snp_align(A, Ra, hits_a, dd_a, 1, i, lane, C, reinterpret_cast<uint4 *>(P));
+                if (i < Rb->seedseg) snp_align(A, Rb, hits_b, dd_b, 1, i, lane, C, reinterpret_cast<uint4 *>(P));
                 if (i <= Ra->rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
                 if (i <= Rb->rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
                 __syncwarp();
@@ -799,8 +837,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                 }
             }
         } else {
-            if (!Ra->filtered) run_align(A, Ra, hits_a, dd_a, 1, lane, C);
-            if (!Rb->filtered) run_align(A, Rb, hits_b, dd_b, 1, lane, C);
+            if (!Ra->filtered) run_align(A, Ra, hits_a, dd_a, 1, lane, C, reinterpret_cast<uint4 *>(P));
+            if (!Rb->filtered) run_align(A, Rb, hits_b, dd_b, 1, lane, C, reinterpret_cast<uint4 *>(P));
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
         if (!out_paired && BSX_RRBS(A)) {
