@@ -431,7 +431,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     m->pair_stride = (2 * (uint32_t)p->max_snp_num + 1) * W1 * 2;   // uint4 units (32-byte PairHit)
     const size_t se_warps = (size_t)m->n_ctas_se * BSX_WARPS_PER_CTA;
     // prepared-unit images: 32 per resident warp (phase A of the align kernels, bsx_prep.cuh)
-    const size_t prep_bytes = std::max(se_warps, (size_t)m->n_ctas_pe * BSX_WARPS_PER_CTA) * 32u * bsx_read_smem_bytes(m->plan_cap, m->nslot);
+    const size_t prep_bytes = std::max(se_warps, (size_t)m->n_ctas_pe * BSX_WARPS_PER_CTA) * 32u * bsx_image_bytes(m->plan_cap, m->nslot);
     for (int i = 0; i < 2; i++) {
         bsx_slot &s = m->slot[i];
         BSX_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));

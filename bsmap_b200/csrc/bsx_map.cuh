@@ -20,6 +20,7 @@ struct MapArgs {
     int plan_cap;                 // plan entries per chain = max segments * I
     int nslot;                    // chains a read can use at once: 2 with -n 1, else 1 (plan storage per read)
     uint32_t read_smem, warp_smem_se, chain_stride, flank_off;   // derived from the two above on the host (bsx_map_args_derive)
+    uint32_t img_slot, img_bytes; // prepared image in global scratch: ImgHdr + nslot x img_slot bytes
     int adapter_len[BSX_MAX_ADAPTERS];
     char adapter[BSX_MAX_ADAPTERS][64];
     char digest_site[32];
@@ -39,15 +40,26 @@ struct MapArgs {
     uint4 *pair_scratch;          // per warp: PE pair buckets
     uint32_t hit_stride, dd_stride, pair_stride;
     uint32_t *debug;              // optional: per read 40 u32 of seed-selection state (tests)
-    uint8_t *prep;                // prepared-unit images: [warp][32] x read_smem bytes (bsx_prep.cuh)
+    uint8_t *prep;                // prepared-unit images: [warp][32] x img_bytes (bsx_prep.cuh)
     int mates;                    // units per read: 1 (SE) or 2 (PE)
     uint32_t block_units;         // units a warp prepares per work-counter atomic: 32, fewer for small batches (balance)
 };
 
-// One prepared read: written to global memory in the prepare phase (one THREAD per read: trim, filter, pack,
-// choose seeds -- bsx_prep.cuh), copied into shared memory by the warp when it aligns it.  The image is this struct
-// followed by uint4 plan[nslot][plan_cap]: {list start, rc start, list end, read offset | segment << 16}
-// and uint4 flank[nslot][plan_cap]: read bases / mask facing the inline context before (x,y) and after (z,w) the seed.
+// One prepared read as the prepare phase (one THREAD per read: trim, filter, pack, choose seeds -- bsx_prep.cuh) leaves
+// it in global scratch: this header, then per chain slot the packed read rw[10] | m5[10] and uint4 plan[plan_cap]:
+// {list start, rc start, list end, read offset | segment << 16}.  480 bytes at config 2 (the first design wrote the
+// whole ReadSm + plan + flanks: 1 056 bytes, all of which went to HBM and back).
+struct ImgHdr {
+    uint32_t index;                   // read index (myrand)
+    uint32_t geom;                    // len | rmsn << 8 | seedseg << 16 | (filtered | fc << 1 | cc << 2) << 24
+    uint32_t aux;                     // raw length | readset << 8
+    uint32_t pad;
+};
+static_assert(sizeof(ImgHdr) == 16, "image header is one uint4");
+
+// The read a warp is aligning, in shared memory: expanded from the image by load_image.  Followed by
+// uint4 plan[nslot][plan_cap] and uint4 flank[nslot][plan_cap]: read bases / mask facing the inline context before
+// (x,y) and after (z,w) the seed of each plan entry.
 struct ReadSm {
     uint32_t rw[2][BSX_FIXWORDS];     // 2-bit read, chain 0 = as is, 1 = reverse complement (bseq/cbseq)
     uint32_t m5[2][BSX_FIXWORDS];     // 01 per ACGT base (reg/creg & 0x5555...)
@@ -100,6 +112,11 @@ static inline void bsx_map_args_derive(MapArgs &a) {
     a.warp_smem_se = (uint32_t)bsx_warp_smem_bytes(1, a.plan_cap, a.nslot);
     a.chain_stride = a.nslot == 2 ? (uint32_t)a.plan_cap : 0u;
     a.flank_off = (uint32_t)(a.nslot * a.plan_cap);
+    a.img_slot = (uint32_t)(2 * BSX_FIXWORDS * 4 + a.plan_cap * sizeof(uint4));
+    a.img_bytes = (uint32_t)(sizeof(ImgHdr) + a.nslot * a.img_slot);
+}
+static inline size_t bsx_image_bytes(int plan_cap, int nslot) {
+    return sizeof(ImgHdr) + (size_t)nslot * (2 * BSX_FIXWORDS * 4 + (size_t)plan_cap * sizeof(uint4));
 }
 
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st);

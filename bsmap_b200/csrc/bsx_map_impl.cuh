@@ -58,10 +58,10 @@
 #ifndef BSX_SE_MIN_CTAS
 #define BSX_SE_MIN_CTAS 5
 #endif
-#ifndef BSX_STAGE
-#define BSX_STAGE 1             // the heads of up to BSX_STAGE_LISTS position lists are fetched together (cp.async -> shared memory)
+#define BSX_ROUND_HS 8           // half-steps (32 list entries each) per staging round: 2 KB of list entries per warp
+#ifndef BSX_PACKED
+#define BSX_PACKED 1            // WGBS list walk over a packed half-step schedule staged through shared memory (snp_align_packed)
 #endif
-#define BSX_STAGE_LISTS 4       // 4 x 64 entries x 8 B = 2 KB per warp: aliases the prepare phase's PrepCol
 
 #include "bsx_prep.cuh"
 
@@ -106,9 +106,8 @@ __device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 __device__ __forceinline__ const CtaSm *cta_tables() {   // the CTA's tables sit at the start of dynamic shared memory
     extern __shared__ __align__(16) uint8_t bsx_dyn_smem_[];
@@ -135,22 +134,58 @@ __device__ __forceinline__ void init_cta_tables(const MapArgs &A, CtaSm *K) {
     __syncthreads();
 }
 
-// A prepared image (bsx_prep.cuh) -> this warp's shared memory: a few coalesced 16-byte loads per lane.
+// A prepared image (bsx_prep.cuh) -> this warp's shared memory: one or two coalesced loads per lane, then the per-read
+// state and the context flanks (the read bases that face an entry's inline context, one plan entry per lane).
 // ld.cg: the image was written by another lane of this warp moments ago, so the read-only path is not allowed.
 __device__ __forceinline__ void load_image(const MapArgs &A, ReadSm *R, const uint8_t *img, int lane) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(img);
-    uint4 *dst = reinterpret_cast<uint4 *>(R);
-    const int n16 = (int)(A.read_smem >> 4);
     __syncwarp();
-    #pragma unroll 1
-    for (int t = lane; t < n16; t += 32) dst[t] = __ldcg(src + t);
+    const uint4 hd = __ldcg(reinterpret_cast<const uint4 *>(img));
+    const int len = (int)(hd.y & 0xffu), rmsn = (int)((hd.y >> 8) & 0xffu), seg = (int)((hd.y >> 16) & 0xffu);
+    const int filtered = (int)((hd.y >> 24) & 1u), fc = (int)((hd.y >> 25) & 1u), cc = (int)((hd.y >> 26) & 1u);
+    const int per = BSX_RRBS(A) ? 1 : A.I, used = seg * per;
+    if (!filtered) {
+        #pragma unroll 1
+        for (int c = 0; c < A.nslot; c++) {
+            const int chain = A.nslot == 2 ? c : (fc ? 0 : 1);
+            const uint8_t *sp = img + sizeof(ImgHdr) + (size_t)c * A.img_slot;
+            if (lane < 2 * BSX_FIXWORDS) {
+                const uint32_t v = __ldcg(reinterpret_cast<const uint32_t *>(sp) + lane);
+                if (lane < BSX_FIXWORDS) R->rw[chain][lane] = v; else R->m5[chain][lane - BSX_FIXWORDS] = v;
+            }
+            uint4 *pl = plan_of(R, chain, A);
+            const uint4 *src = reinterpret_cast<const uint4 *>(sp + 2 * BSX_FIXWORDS * 4);
+            #pragma unroll 1
+            for (int t = lane; t < used; t += 32) pl[t] = __ldcg(src + t);
+        }
+    }
+    if (lane < 16) reinterpret_cast<uint32_t *>(R->nh)[lane] = 0u;      // nh[16], nc[16]
+    if (lane == 0) {
+        R->raw = (int)(hd.z & 0xffu); R->readset = (int)((hd.z >> 8) & 0xffu); R->seedseg = seg; R->filtered = filtered;
+        R->index = hd.x; R->len = len; R->rmsn = rmsn; R->nw = (len + 15) >> 4;
+        R->thres = (uint32_t)rmsn; R->fc = fc; R->cc = cc; R->dn = 0; R->best = 99;
+    }
+    __syncwarp();
+    if (!filtered && !BSX_RRBS(A)) {
+        #pragma unroll 1
+        for (int c = 0; c < A.nslot; c++) {
+            const int chain = A.nslot == 2 ? c : (fc ? 0 : 1);
+            const uint4 *pl = plan_of(R, chain, A);
+            uint4 *fl = flank_of(R, chain, A);
+            #pragma unroll 1
+            for (int t = lane; t < used; t += 32) {
+                const int p = (int)(pl[t].w & 0xffffu);
+                const uint2 wb = read_window(R, chain, p - 16), wa = read_window(R, chain, p + A.s);
+                fl[t] = make_uint4(wb.x, wb.y, wa.x, wa.y);
+            }
+        }
+    }
     __syncwarp();
 }
 
 // Phase A for a block of `cnt` units starting at unit u0: lane i prepares unit u0 + i into image i of the warp's scratch
 __device__ __forceinline__ void prepare_block(const MapArgs &A, const CtaSm *K, PrepCol *P, uint8_t *scratch, uint32_t u0, uint32_t cnt, int lane, Ctr *C) {
     int np = 0;
-    if ((uint32_t)lane < cnt) np = bsx_prep_unit(A, K, &P->rw[0][lane], &P->m5[0][lane], u0 + (uint32_t)lane, scratch + (size_t)lane * A.read_smem);
+    if ((uint32_t)lane < cnt) np = bsx_prep_unit(A, K, &P->rw[0][lane], &P->m5[0][lane], u0 + (uint32_t)lane, scratch + (size_t)lane * A.img_bytes);
 #pragma unroll
     for (int d = 16; d; d >>= 1) np += __shfl_xor_sync(BSX_FULL, np, d);
     CTR_ADD(C, CT_PROBE, np);
@@ -380,12 +415,165 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
     return ret | (last << 8);        // bit 0: SnpAlign returns; bits 8..: exiting lane
 }
 
+// Per-warp staging area of the packed list walk; aliases the prepare phase's PrepCol (idle while the warp aligns).
+struct HalfStep {                       // 32 consecutive entries of one position list
+    uint32_t src, lo, cnt, k;           // first entry index (even), list start, list length, list number within the mode
+    uint32_t rb, mb, ra, ma;            // the read bases / valid mask that face the list's inline context before / after the seed
+};
+struct StageSm {
+    uint2 slot[BSX_ROUND_HS * 32];      // one round of BSX_ROUND_HS half-steps x 32 entries {16 bases before, 16 after the seed}
+    HalfStep sched[BSX_ROUND_HS];
+};
+static_assert(sizeof(StageSm) <= sizeof(PrepCol), "the staging area must fit in the idle PrepCol");
+static_assert(sizeof(HalfStep) == 32, "two uint4");
+
+// SnpAlign for one mode of a WGBS read (align.cpp:168-347), lists staged through shared memory.
+// The I position lists of the mode are cut into half-steps of 32 entries (a list starts a new half-step, at the even
+// entry index at or before its first entry, so that every copy is a 16-byte cp.async); the half-steps of all lists
+// form one schedule that is fetched in rounds of BSX_ROUND_HS and evaluated two half-steps = 64 candidates at a time.
+// Versus walking list after list with direct loads: one DRAM round trip per round instead of one per list, and ~3.5
+// instead of 5.6 steps per mode at config 2 (lists average 43 entries and used to occupy one or two 64-wide steps
+// each).  Within a half-step the list is warp-uniform, so the per-candidate work is still one 8-byte shared-memory
+// load, two masked XOR/popcount words and a compare.  Candidates are visited in the reference's order, so commits, -w
+// threshold lowering and the early returns fire exactly where the sequential reference stops.
+// The owners (lane k < I owns list k of the mode) write the half-steps of round [h0, h0 + BSX_ROUND_HS) into the schedule;
+// returns the number of half-steps of the whole mode.  Out of line: it runs once per mode, the evaluation loop must stay small.
+__device__ __noinline__ uint32_t packed_schedule(const MapArgs &A, ReadSm *R, StageSm *S, int chain, int mode, uint32_t h0, int lane, Ctr *C) {
+    const int per = A.I;
+    const uint4 *plan = plan_of(R, chain, A) + mode * per;
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);                                 // {list start, rc start, list end, p | segment << 16}
+    if (lane < per) e = plan[lane];
+    const uint32_t n = e.z - e.x;
+    const uint32_t nhs = n ? (n + (e.x & 1u) + 31u) >> 5 : 0u;           // half-steps of my list
+    uint32_t cum = nhs;                                                   // inclusive scan over the (<= 16) lists
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(BSX_FULL, cum, d); if (lane >= d) cum += t; }
+    const uint32_t total_hs = __shfl_sync(BSX_FULL, cum, 15);
+    if (h0 == 0) {
+        const uint32_t total_n = __reduce_add_sync(BSX_FULL, n);
+        if (lane == 0) { C[CT_LIST] += total_n; C[CT_CAND] += total_n; }  // corrected by packed_exit when SnpAlign returns early
+    }
+    __syncwarp();
+    if (nhs) {
+        const uint4 f = (flank_of(R, chain, A) + mode * per)[lane];      // read bases facing the list's inline context (load_image)
+        const int first = (int)(cum - nhs) - (int)h0;
+        #pragma unroll 1
+        for (int o = max(0, -first); o < (int)nhs && first + o < BSX_ROUND_HS; o++) {
+            uint4 *d4 = reinterpret_cast<uint4 *>(&S->sched[first + o]);
+            d4[0] = make_uint4((e.x & ~1u) + 32u * (uint32_t)o, e.x, n, (uint32_t)lane);
+            d4[1] = f;
+        }
+    }
+    __syncwarp();
+    return total_hs;
+}
+
+// SnpAlign returned at lane `xl` of half-step `cur` of the current round (nst half-steps): the candidates the sequential
+// reference has visited are the lists before this one and this list up to the exiting entry; everything else that was
+// requested is over-fetch.
+__device__ __noinline__ void packed_exit(const MapArgs &A, ReadSm *R, StageSm *S, int chain, int mode, uint32_t cur, uint32_t nst, uint32_t xl, int lane, Ctr *C) {
+    const int per = A.I;
+    const uint4 *plan = plan_of(R, chain, A) + mode * per;
+    const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[cur]);
+    uint32_t nk = 0;
+    if (lane < per) { const uint4 el = plan[lane]; nk = el.z - el.x; }
+    const uint32_t all = __reduce_add_sync(BSX_FULL, nk);
+    const uint32_t before = __reduce_add_sync(BSX_FULL, (uint32_t)lane < sc.w ? nk : 0u);
+    const uint32_t counted = before + (sc.x + xl - sc.y) + 1u;
+    uint32_t extra = 0;                                                   // entries of this round behind the exiting one
+    if ((uint32_t)lane < nst && (uint32_t)lane >= cur) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(&S->sched[lane]);
+        uint32_t lo_i = max(t.x, t.y);
+        const uint32_t hi_i = min(t.x + 32u, t.y + t.z);
+        if ((uint32_t)lane == cur) lo_i = max(lo_i, t.x + xl + 1u);
+        extra = hi_i > lo_i ? hi_i - lo_i : 0u;
+    }
+    const uint32_t req = counted + __reduce_add_sync(BSX_FULL, extra);
+    if (lane == 0) { C[CT_CAND] -= all - counted; C[CT_LIST] -= all - req; C[CT_OVER] += req - counted; }
+}
+
+// phase-1 chunk choice for a mode: keep away from its seed zone (all sub-seeds)
+__device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm *R, int chain, int mode, int lane) {
+    const int per = A.I;
+    const uint4 *plan = plan_of(const_cast<ReadSm *>(R), chain, A) + mode * per;
+    int zlo = 1000, zhi = -1;
+    if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
+#pragma unroll
+    for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
+    zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
+    return chunk_table(R, chain, R->nw, zlo, zhi, lane);
+}
+
+__device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *S) {
+    #pragma unroll 1
+    for (int chain = 0; chain < 2; chain++) {
+        if (chain == 0 ? !R->fc : !R->cc) continue;
+        uint32_t total_hs = 1;
+        uint32_t thres = R->thres;
+        #pragma unroll 1
+        for (uint32_t h0 = 0; h0 < total_hs; h0 += BSX_ROUND_HS) {
+            total_hs = packed_schedule(A, R, S, chain, mode, h0, lane, C);
+            if (total_hs == 0) break;
+            const uint32_t nst = min((uint32_t)BSX_ROUND_HS, total_hs - h0);
+            {   // every lane copies one 16-byte pair of entries per step of the round
+                const uint32_t half = (uint32_t)lane >> 4, pr = 2u * ((uint32_t)lane & 15u);
+                const uint2 *ctx = A.ctx;
+#pragma unroll
+                for (uint32_t q = 0; q < BSX_ROUND_HS / 2; q++) {
+                    const uint32_t hs = 2u * q + half;
+                    const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
+                    const uint32_t g = sc.x + pr;
+                    if (hs < nst && g < sc.y + sc.z) cp_async16(&S->slot[hs * 32u + pr], ctx + g);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            #pragma unroll 1
+            for (uint32_t hs = 0; hs < nst; hs += 2) {
+                // branch-free: a half-step past the end of the round reads stale shared memory and is masked out
+                const uint4 s0 = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
+                const uint4 f0 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 1);
+                const uint4 s1 = *reinterpret_cast<const uint4 *>(&S->sched[hs + 1]);
+                const uint4 f1 = *(reinterpret_cast<const uint4 *>(&S->sched[hs + 1]) + 1);
+                const uint2 cx0 = S->slot[hs * 32u + lane], cx1 = S->slot[hs * 32u + 32u + lane];
+                const bool in0 = (s0.x + (uint32_t)lane - s0.y) < s0.z;                          // inside the list (unsigned)
+                const bool in1 = ((s1.x + (uint32_t)lane - s1.y) < s1.z) & (hs + 1 < nst);
+                const bool pass0 = in0 & (__popc(bsx_mm_word_bits(f0.x, f0.y, cx0.x)) + __popc(bsx_mm_word_bits(f0.z, f0.w, cx0.y)) <= thres);
+                const bool pass1 = in1 & (__popc(bsx_mm_word_bits(f1.x, f1.y, cx1.x)) + __popc(bsx_mm_word_bits(f1.z, f1.w, cx1.y)) <= thres);
+                if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
+                // ---- slow path: some candidate passed the inline-context filter
+                const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+                // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
+                const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
+                const uint32_t tbl = use_p1 ? mode_chunk_table(A, R, chain, mode, lane) : 0u;
+                int ret = 0;
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {                            // one call site: the slow path exists once in the binary
+                    if (h ? pm1 : pm0) {
+                        const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs + h]);
+                        const uint4 ek = (plan_of(R, chain, A) + mode * A.I)[sc.w];
+                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, sc.x, ek.y, ek.w & 0xffffu, tbl, use_p1, lane, C);
+                        if (rc & 1) { packed_exit(A, R, S, chain, mode, hs + (uint32_t)h, nst, (uint32_t)(rc >> 8), lane, C); ret = 1; break; }
+                    }
+                }
+                if (ret) return 1;
+                thres = R->thres;
+            }
+        }
+    }
+    return 0;
+}
+
 // SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
 // The I position lists of the mode are walked in the reference's order (sub-seed 0's forward entries, its
 // rc entries, sub-seed 1's, ...), 64 table entries per step (two per lane).  Everything that depends on
 // the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
 // work is one 8-byte load, two masked XOR/popcount words and a compare.
-__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, uint4 *stage) {
+__device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *stage) {
+#if BSX_PACKED
+    if (!BSX_RRBS(A) && !BSX_WIDE(A)) return snp_align_packed(A, R, hits, dd, store_all, mode, lane, C, stage);
+#endif
     const int per = BSX_RRBS(A) ? 1 : A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
@@ -395,21 +583,6 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
         int ret = 0;
         #pragma unroll 1
         for (int i = 0; i < per && !ret; i++) {
-#if BSX_STAGE
-            if (!BSX_RRBS(A) && !BSX_WIDE(A) && (i & (BSX_STAGE_LISTS - 1)) == 0) {
-                // the first 64 entries (from an even index: 16-byte copies, two entries per lane) of this list and the
-                // next three: one DRAM round trip for the group instead of one per list
-                __syncwarp();
-                #pragma unroll 1
-                for (int k = 0; k < BSX_STAGE_LISTS && i + k < per; k++) {
-                    const uint4 ek = plan[i + k];
-                    const uint32_t g = (ek.x & ~1u) + 2u * (uint32_t)lane;
-                    if (g < ek.z) cp_async16(stage + k * 32 + lane, A.ctx + g);
-                }
-                cp_async_wait_all();
-                __syncwarp();
-            }
-#endif
             const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
             const uint32_t p = e.w & 0xffffu;
@@ -427,10 +600,6 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                 // `> snp_thres` rejects exactly like the reference; pos[] and the reference are only touched by
                 // survivors.  Every entry of the list is a candidate, so the counters need no per-step work.
                 uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
-#if BSX_STAGE
-                if (!BSX_WIDE(A)) c0 &= ~1u;                              // steps start at the even index the staged head starts at
-                const uint2 *head = reinterpret_cast<const uint2 *>(stage + (i & (BSX_STAGE_LISTS - 1)) * 32);
-#endif
                 uint32_t rb2 = 0, mb2 = 0, ra2 = 0, ma2 = 0; bool have_f2 = false;     // wide-context flanks of this list, set up on first use
                 // high -v workloads walk lists of thousands of entries: there the next step's context is requested before
                 // this step is evaluated (on config 2's ~1.4-step lists the same pipelining measured -7 %)
@@ -448,16 +617,10 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
                         if (i0 + 64 < e.z) nx0 = ld_stream(A.ctx + i0 + 64);
                         if (i1 + 64 < e.z) nx1 = ld_stream(A.ctx + i1 + 64);
                     } else {
-#if BSX_STAGE
-                        if (c0 <= e.x) { cx0 = head[lane]; cx1 = head[lane + 32]; }         // first step: staged (entries past the end are stale, masked below)
-                        else
-#endif
-                        {
-                            if (i0 < e.z) cx0 = ld_stream(A.ctx + i0);
-                            if (i1 < e.z) cx1 = ld_stream(A.ctx + i1);
-                        }
+                        if (i0 < e.z) cx0 = ld_stream(A.ctx + i0);
+                        if (i1 < e.z) cx1 = ld_stream(A.ctx + i1);
                     }
-                    if (i0 >= e.x && i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
+                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
                     if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
                     if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
                     if (BSX_WIDE(A)) {
@@ -562,7 +725,7 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
 }
 
 // SingleAlign::RunAlign (align.cpp:435-452): the mode loop (everything before it happened in the prepare kernel)
-__device__ BSX_FN void run_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, uint4 *stage) {
+__device__ BSX_FN void run_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int lane, Ctr *C, StageSm *stage) {
     #pragma unroll 1
     for (int m = 0; m < R->seedseg; m++) {
         snp_align(A, R, hits, dd, store_all, m, lane, C, stage);
@@ -617,7 +780,7 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     Ctr *C = X->ctr;
     if (lane < 8) C[lane] = 0;
     __syncwarp();
-    uint8_t *scratch = A.prep + (size_t)gw * 32u * A.read_smem;
+    uint8_t *scratch = A.prep + (size_t)gw * 32u * A.img_bytes;
     for (;;) {
         uint32_t r0 = 0;                        // one atomic hands this warp up to 32 consecutive reads
         if (lane == 0) r0 = atomicAdd(A.work_counter, A.block_units);
@@ -629,8 +792,8 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
         for (uint32_t i = 0; i < cnt; i++) {                                  // phase B: the warp aligns them one by one
             const uint32_t r = r0 + i;
             if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
-            load_image(A, R, scratch + (size_t)i * A.read_smem, lane);
-            if (!R->filtered) run_align(A, R, hits, dd, 0, lane, C, reinterpret_cast<uint4 *>(P));
+            load_image(A, R, scratch + (size_t)i * A.img_bytes, lane);
+            if (!R->filtered) run_align(A, R, hits, dd, 0, lane, C, reinterpret_cast<StageSm *>(P));
             __syncwarp();
             write_record(A, R,  hits, 0, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
             if (!R->filtered && R->best <= R->rmsn) CTR_ADD(C, CT_MAPPED, 1);
@@ -779,7 +942,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     if (lane < 8) C[lane] = 0;
     __syncwarp();
     const size_t W1 = (size_t)A.W + 1;
-    uint8_t *scratch = A.prep + (size_t)gw * 32u * A.read_smem;
+    uint8_t *scratch = A.prep + (size_t)gw * 32u * A.img_bytes;
     for (;;) {
         uint32_t r0 = 0;                        // one atomic hands this warp up to 16 consecutive pairs = 32 units
         if (lane == 0) r0 = atomicAdd(A.work_counter, A.block_units >> 1);
@@ -791,8 +954,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
       for (uint32_t pi = 0; pi < cnt; pi++) {                                 // phase B: the warp aligns the pairs one by one
         const uint32_t r = r0 + pi;
         if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
-        load_image(A, Ra, scratch + (size_t)(2u * pi) * A.read_smem, lane);
-        load_image(A, Rb, scratch + (size_t)(2u * pi + 1u) * A.read_smem, lane);
+        load_image(A, Ra, scratch + (size_t)(2u * pi) * A.img_bytes, lane);
+        load_image(A, Rb, scratch + (size_t)(2u * pi + 1u) * A.img_bytes, lane);
         int paired = 0;
         bsx_pair_rec po;
         po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
@@ -803,8 +966,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
             const int maxi = max(Ra->rmsn, Rb->rmsn);
             #pragma unroll 1
             for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Ra->seedseg) snp_align(A, Ra, hits_a, dd_a, 1, i, lane, C, reinterpret_cast<uint4 *>(P));
-                if (i < Rb->seedseg) snp_align(A, Rb, hits_b, dd_b, 1, i, lane, C, reinterpret_cast<uint4 *>(P));
+                if (i < Ra->seedseg) snp_align(A, Ra, hits_a, dd_a, 1, i, lane, C, reinterpret_cast<StageSm *>(P));
+                if (i < Rb->seedseg) snp_align(A, Rb, hits_b, dd_b, 1, i, lane, C, reinterpret_cast<StageSm *>(P));
                 if (i <= Ra->rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
                 if (i <= Rb->rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
                 __syncwarp();
@@ -837,8 +1000,8 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
                 }
             }
         } else {
-            if (!Ra->filtered) run_align(A, Ra, hits_a, dd_a, 1, lane, C, reinterpret_cast<uint4 *>(P));
-            if (!Rb->filtered) run_align(A, Rb, hits_b, dd_b, 1, lane, C, reinterpret_cast<uint4 *>(P));
+            if (!Ra->filtered) run_align(A, Ra, hits_a, dd_a, 1, lane, C, reinterpret_cast<StageSm *>(P));
+            if (!Rb->filtered) run_align(A, Rb, hits_b, dd_b, 1, lane, C, reinterpret_cast<StageSm *>(P));
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
         if (!out_paired && BSX_RRBS(A)) {

@@ -8,9 +8,9 @@
 // ~1000 warp instructions per read with most lanes idle -- a third of the align kernel, which is issue-bound.
 // One thread per read executes the same work in ~1/10 of the warp instructions, because reads of one length
 // take identical trip counts and the lanes stay converged.  A warp therefore takes 32 units (reads / mates) at
-// a time: phase A, each lane prepares one unit into a self-contained image (ReadSm + seed plan + context
-// flanks, bsx_map.cuh) in the warp's global scratch; phase B, the warp aligns the 32 units one after the
-// other, copying each image into shared memory with a few coalesced loads.  Phase A is latency-bound
+// a time: phase A, each lane prepares one unit into a compact image (header, packed read, seed plan: bsx_map.cuh)
+// in the warp's global scratch; phase B, the warp aligns the 32 units one after the other, expanding each image into
+// shared memory (one or two coalesced loads per lane; the context flanks are derived there, one plan entry per lane).  Phase A is latency-bound
 // (~30 dependent-free but serial table probes per lane) and hides behind the other warps' phase B.
 // (A separate prepare KERNEL was measured first: 209 M reads/s against 268 M -- alone on the GPU it is bound by
 // DRAM random accesses, 30 ms per 20 M reads, that the fused form overlaps with issue-bound alignment.)
@@ -121,39 +121,53 @@ __device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const uint32_t *r
     return bsx_xt(v & A.seed_bits, A.s);
 }
 
-// Seed probing and selection for one chain; writes plan[] / flank[] of the image, returns the number of probes.
-__device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *rw, const uint32_t *m5, int len, int seg, int chain,
-                            uint4 *plan, uint4 *flank, uint32_t *dbg) {
+// list header of seed key `key`: {list start, reverse-strand start, list end} (tab is the CSR of the seed table)
+__device__ __forceinline__ uint3 probe_tab(const MapArgs &A, uint32_t key) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
+    return make_uint3(a.x, a.y, __ldg(A.tab + 2 * (size_t)key + 2));
+}
+
+// Seed probing and selection for one chain; writes plan[] of the image, returns the number of probes.
+// Only the list SIZES are kept per probed offset (a thread-local array goes through L1/L2 to HBM for 5 920 resident
+// warps); the bounds of the lists that end up in the plan are read again -- the lines were fetched moments ago.
+__device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *rw, int len, int seg, int chain,
+                            uint4 *plan, uint32_t *dbg) {
     const int s = A.s, I = A.I;
     const bool rrbs = A.rrbs != 0;
     const int mo = (rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
     const int cso = (rrbs && chain) ? (int)K->remof[len] : 0;                     // cseed_offset (RRBS rc chain)
     const int lim = I - 1 + mo;
     const int w = min(lim + 1, s);                                                // probed offsets per segment (the last one takes the tail)
-    // per probed offset, indexed n*w + (p - n*s): list start, rc start, list "size" (index2[key][0])
-    uint32_t st[BSX_MAX_KEYS + 16], md[BSX_MAX_KEYS + 16], sz[BSX_MAX_KEYS + 16];
+    // per probed offset, indexed n*w + (p - n*s): list "size" (index2[key][0])
+    uint32_t sz[BSX_MAX_KEYS + 16];
     uint32_t T[16 * 16];
     int arr[16], order[16];
     int np = 0;
     // 1. every read offset that can carry a seed: segment n owns [n*s, n*s + I-1 + max_offset] (profile.a - i lies
-    //    in [n*s, n*s+I-1]).  The union of those ranges is probed once.
-    #pragma unroll 1
-    for (int n = 0; n < seg; n++) {
-        const int rmax = rrbs ? 0 : (n == seg - 1 ? lim : w - 1);
+    //    in [n*s, n*s+I-1]).  The union of those ranges is probed once, four probes in flight per lane.
+    {
+        const int total = rrbs ? seg : (seg > 0 ? (seg - 1) * w + lim + 1 : 0);
+        int n = 0, r = 0;                                                 // (segment, offset) of flat probe q
         #pragma unroll 1
-        for (int r = 0; r <= rmax; r++) {
-            const int p = rrbs ? cso + n * s : n * s + r, idx = rrbs ? n : n * w + r;
-            uint32_t a0 = 0, a1 = 0, zz = 0;
-            if (p + s <= len) {
-                const uint32_t key = seed_key(A, rw, p);
-                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(A.tab) + key);
-                const uint32_t e = __ldg(A.tab + 2 * (size_t)key + 2);
-                const uint32_t cnt = e - a.x;
-                a0 = a.x; a1 = a.y;
-                zz = rrbs ? cnt : (cnt ? cnt + 2 : 0u);        // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
-                np++;
+        for (int q0 = 0; q0 < total; q0 += 4) {
+            uint32_t key[4]; uint3 h[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int pofs = rrbs ? cso + n * s : n * s + r;
+                ok[u] = (q0 + u < total) && (pofs + s <= len);
+                key[u] = ok[u] ? seed_key(A, rw, pofs) : 0u;
+                if (rrbs || (r + 1 >= w && n < seg - 1)) { n++; r = 0; } else r++;
             }
-            st[idx] = a0; md[idx] = a1; sz[idx] = zz;
+#pragma unroll
+            for (int u = 0; u < 4; u++) h[u] = ok[u] ? probe_tab(A, key[u]) : make_uint3(0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (q0 + u < total) {
+                    const uint32_t cnt = h[u].z - h[u].x;
+                    sz[q0 + u] = rrbs ? cnt : (cnt ? cnt + 2 : 0u);      // index2[key][0] = n + 2 (App. B Q7); RRBS: n1
+                    np += ok[u];
+                }
+            }
         }
     }
     // 2. T[n][o] = CountSeeds(n, o) (align.cpp:549-556) for every segment and start offset o <= max_offset
@@ -215,8 +229,7 @@ __device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, c
         dbg[chain * 20] = (uint32_t)seg;
         for (int n = 0; n < seg && n < 9; n++) { dbg[chain * 20 + 1 + n] = (uint32_t)arr[n]; dbg[chain * 20 + 10 + n] = (uint32_t)order[n]; }
     }
-    // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode;
-    // flank: the read bases / valid mask that face an entry's inline context, [p-16, p) and [p+s, p+s+16)
+    // plan[mode][k]: list bounds and read offset of sub-seed k of the segment processed in that mode
     const int per = rrbs ? 1 : I;
     #pragma unroll 1
     for (int m = 0; m < seg; m++) {
@@ -224,31 +237,15 @@ __device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, c
         #pragma unroll 1
         for (int k = 0; k < per; k++) {
             const int p = rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + arr[sg] - k);
-            const int idx = rrbs ? sg : sg * w + (p - sg * s);
-            const uint32_t st0 = st[idx], sz0 = sz[idx];
-            const uint32_t en0 = st0 + (rrbs ? sz0 : (sz0 ? sz0 - 2u : 0u));
-            plan[m * per + k] = make_uint4(st0, md[idx], en0, (uint32_t)p | ((uint32_t)sg << 16));
-            if (!rrbs) {
-                const int xb = p - 16, xa = p + s;
-                uint32_t rb = 0, mb = 0;
-                if (xb >= 0) {
-                    const int j = xb >> 4, sh = (xb & 15) * 2;
-                    rb = __funnelshift_l(rw[(j + 1) * 32], rw[j * 32], sh);      // j + 1 <= 9 because p <= 144
-                    mb = __funnelshift_l(m5[(j + 1) * 32], m5[j * 32], sh);
-                } else if (xb > -16) {                                // fewer than 16 bases before the seed
-                    rb = rw[0] >> (2 * (-xb)); mb = m5[0] >> (2 * (-xb));
-                }
-                const int j = xa >> 4, sh = (xa & 15) * 2;
-                const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? rw[(j + 1) * 32] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? m5[(j + 1) * 32] : 0u;
-                const uint32_t r0 = (j < BSX_FIXWORDS) ? rw[j * 32] : 0u, m0 = (j < BSX_FIXWORDS) ? m5[j * 32] : 0u;
-                flank[m * per + k] = make_uint4(rb, mb, __funnelshift_l(r1, r0, sh), __funnelshift_l(m1, m0, sh));
-            }
+            uint3 h = make_uint3(0u, 0u, 0u);
+            if (p + s <= len) h = probe_tab(A, seed_key(A, rw, p));
+            plan[m * per + k] = make_uint4(h.x, h.y, h.z, (uint32_t)p | ((uint32_t)sg << 16));
         }
     }
     return np;
 }
 
-// Prepare unit `u` (read r, mate) into the image at `img`; returns the number of table probes.
+// Prepare unit `u` (read r, mate) into the image at `img` (layout: bsx_map.cuh); returns the number of table probes.
 // noinline on purpose: called once per 32 units, with its own register allocation.
 // rw / m5: this lane's column of the warp's PrepCol (shared memory) -- the packed read is indexed by data-dependent
 // word numbers, which as a thread-local array cost one 32-byte sector per access (130 sectors per read).
@@ -264,8 +261,6 @@ __device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, ui
         if (len > BSX_MAX_READLEN) len = BSX_MAX_READLEN;
         if (len > (int)A.stride) len = (int)A.stride;
         const int readset = A.mates == 2 ? mate + 1 : A.readset;
-        ReadSm *G = reinterpret_cast<ReadSm *>(img);
-        uint4 *plan0 = reinterpret_cast<uint4 *>(img + sizeof(ReadSm));
         const int raw = len;
         len = trim_adapter(A, sq, len);
         const int fc = A.chains || (readset < 2), cc = A.chains || (readset == 2);   // flag_chain / cflag_chain (align.cpp:93-94)
@@ -288,18 +283,18 @@ __device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, ui
             for (int chain = 0; chain < 2; chain++) {
                 if (chain == 0 ? !fc : !cc) continue;
                 if (chain == 1 && fc) pack_chain(sq, A.stride, len, 1, rw, m5);   // -n 1: the other orientation, same scratch
-                uint4 *plan = plan0 + chain * A.chain_stride;
-                np += select_seeds(A, &K, rw, m5, len, seg, chain, plan, plan + A.flank_off, dbg);
+                uint32_t *slot = reinterpret_cast<uint32_t *>(img + sizeof(ImgHdr) + (A.nslot == 2 ? chain : 0) * A.img_slot);
+                np += select_seeds(A, &K, rw, len, seg, chain, reinterpret_cast<uint4 *>(slot + 2 * BSX_FIXWORDS), dbg);
                 #pragma unroll 1
-                for (int j = 0; j < BSX_FIXWORDS; j++) { G->rw[chain][j] = rw[j * 32]; G->m5[chain][j] = m5[j * 32]; }
+                for (int j = 0; j < BSX_FIXWORDS; j++) { slot[j] = rw[j * 32]; slot[BSX_FIXWORDS + j] = m5[j * 32]; }
             }
         }
-        uint4 *z = reinterpret_cast<uint4 *>(G->nh);                        // nh[16], nc[16] = 0
-        z[0] = z[1] = z[2] = z[3] = make_uint4(0, 0, 0, 0);
-        G->raw = raw; G->seedseg = seg; G->readset = readset; G->filtered = filtered;
-        G->index = A.first_index + r;
-        G->len = len; G->rmsn = rmsn; G->nw = (len + 15) >> 4;
-        G->thres = (uint32_t)rmsn; G->fc = fc; G->cc = cc; G->dn = 0; G->best = 99;
+        ImgHdr h;
+        h.index = A.first_index + r;
+        h.geom = (uint32_t)len | ((uint32_t)rmsn << 8) | ((uint32_t)seg << 16) | ((uint32_t)(filtered | (fc << 1) | (cc << 2)) << 24);
+        h.aux = (uint32_t)raw | ((uint32_t)readset << 8);
+        h.pad = 0;
+        *reinterpret_cast<uint4 *>(img) = *reinterpret_cast<const uint4 *>(&h);
     }
     return np;
 }
