@@ -46,6 +46,16 @@ def pack_reads(seqs, stride=None):
     return buf, lens
 
 
+def pack_reads_2bit(buf: np.ndarray, lens: np.ndarray, threads: int = 0):
+    """ASCII read slots -> packed slots (2-bit bases + valid mask, bsx_packed_stride bytes each) -> (packed, lower-case bases met)"""
+    n, stride = buf.shape
+    ps = int(load().bsx_packed_stride(stride))
+    out = np.empty((n, ps), dtype=np.uint8)
+    low = C.c_uint64(0)
+    check(load().bsx_pack_reads(n, buf.ctypes.data, stride, lens.ctypes.data, out.ctypes.data, C.byref(low), threads))
+    return out, int(low.value)
+
+
 def _ptr(a):
     return a.ctypes.data if a is not None else None
 
@@ -197,6 +207,30 @@ class Mapper:
         counts = np.zeros((n, 16), dtype=np.uint16) if want_counts else None
         check(load().bsx_map_se(self.h, n, buf.ctypes.data, lens.ctypes.data, first_index, readset, out.ctypes.data, _ptr(counts)))
         return out, counts
+
+    def map_se_packed(self, packed: np.ndarray, lens: np.ndarray, first_index=0, readset=0, want_counts=True):
+        """Do_Batch on packed read slots (pack_reads_2bit of slots with this mapper's stride)"""
+        n = len(lens)
+        assert packed.dtype == np.uint8 and packed.flags.c_contiguous and packed.shape[1] == load().bsx_packed_stride(self.stride)
+        out = np.zeros(n, dtype=REC)
+        counts = np.zeros((n, 16), dtype=np.uint16) if want_counts else None
+        check(load().bsx_map_se_packed(self.h, n, packed.ctypes.data, lens.ctypes.data, first_index, readset, out.ctypes.data, _ptr(counts)))
+        return out, counts
+
+    def map_se_packed_ptr(self, n, packed_ptr, len_ptr, out_ptr, counts_ptr=None, first_index=0, readset=0):
+        check(load().bsx_map_se_packed(self.h, n, packed_ptr, len_ptr, first_index, readset, out_ptr, counts_ptr))
+
+    def map_pe_packed(self, pk_a, lens_a, pk_b, lens_b, first_index=0):
+        n = len(lens_a)
+        pr = np.zeros(n, dtype=PAIR_REC)
+        ra, rb = np.zeros(n, dtype=REC), np.zeros(n, dtype=REC)
+        ca, cb = np.zeros((n, 16), dtype=np.uint16), np.zeros((n, 16), dtype=np.uint16)
+        check(load().bsx_map_pe_packed(self.h, n, pk_a.ctypes.data, lens_a.ctypes.data, pk_b.ctypes.data, lens_b.ctypes.data,
+                                       first_index, pr.ctypes.data, ra.ctypes.data, rb.ctypes.data, ca.ctypes.data, cb.ctypes.data))
+        return pr, ra, rb, ca, cb
+
+    def upload_packed(self, n, packed_ptr, len_ptr, packed_b_ptr=None, len_b_ptr=None, stream=None):
+        check(load().bsx_batch_upload_packed(self.h, n, packed_ptr, len_ptr, packed_b_ptr, len_b_ptr, stream))
 
     def map_se_ptr(self, n, seq_ptr, len_ptr, out_ptr, counts_ptr=None, first_index=0, readset=0):
         """raw-address form (pinned host buffers owned by the caller)"""

@@ -329,10 +329,12 @@ struct bsx_slot {
     uint32_t *d_counter = nullptr;
     uint2 *d_hits = nullptr; uint32_t *d_dd = nullptr; uint4 *d_pairs = nullptr;
     uint8_t *d_prep = nullptr;   // prepared-read images of one chunk (bsx_prep.cu)
+    bool packed = false;         // the slot's read buffers hold packed slots (bsx_packed_stride) instead of ASCII
 };
 
 struct bsx_mapper {
     const bsx_index *ix = nullptr;
+    int device = 0;                  // kept here too: a mapper may be destroyed after its index (garbage-collected bindings)
     bsx_params par{};
     uint32_t max_batch = 0, stride = 0;
     int n_ctas_se = 0, n_ctas_pe = 0, plan_cap = 0, nslot = 1;
@@ -365,7 +367,7 @@ static void slot_free(bsx_slot &s) {
 
 extern "C" int bsx_mapper_destroy(bsx_mapper *m) {
     if (!m) return BSX_OK;
-    cudaSetDevice(m->ix->device);
+    cudaSetDevice(m->device);
     cudaDeviceSynchronize();
     slot_free(m->slot[0]); slot_free(m->slot[1]);
     cudaFree(m->d_stats); cudaFree(m->d_debug);
@@ -398,6 +400,8 @@ static int alloc_pe(bsx_mapper *m) {
     return BSX_OK;
 }
 
+static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, uint32_t max_batch, uint32_t stride);
+
 extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint32_t max_batch, uint32_t stride, bsx_mapper **out) {
     if (!ix || !p || !out || max_batch == 0) { bsx_set_error("bsx_mapper_create: bad argument"); return BSX_ERR_ARG; }
     if (ix->device < 0) { bsx_set_error("text-only index cannot map: build it with bsx_index_create on a CUDA device"); return BSX_ERR_CUDA; }
@@ -411,7 +415,15 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     rc = require_device(ix->device); if (rc) return rc;
     BSX_CUDA_CHECK(cudaSetDevice(ix->device));
     bsx_mapper *m = new bsx_mapper();
-    m->ix = ix; m->par = *p; m->max_batch = max_batch; m->stride = stride;
+    m->ix = ix; m->device = ix->device;
+    rc = mapper_init(m, ix, p, max_batch, stride);
+    if (rc != BSX_OK) { bsx_mapper_destroy(m); return rc; }     // frees whatever was allocated before the failure
+    *out = m;
+    return BSX_OK;
+}
+
+static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, uint32_t max_batch, uint32_t stride) {
+    m->ix = ix; m->device = ix->device; m->par = *p; m->max_batch = max_batch; m->stride = stride;
     int readlen = std::min(p->max_readlen, BSX_MAX_READLEN);
     int maxseg = std::min((readlen - p->index_interval + 1) / p->seed_size, p->max_snp_num + 1);
     if (maxseg < 1) maxseg = 1;
@@ -423,7 +435,7 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     const bool wide = !p->rrbs && p->max_snp_num >= BSX_WIDE_CTX_V && ix->d_ctx2;
     int occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem_se) : (wide ? bsx_map_occupancy_se_wide(smem_se) : bsx_map_occupancy_se_wgbs(smem_se));
     int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap, m->nslot));
-    if (occ_se < 1 || occ_pe < 1) { delete m; bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
+    if (occ_se < 1 || occ_pe < 1) { bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
     const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;
     m->hit_stride = 2 * W1;                        // SE: only the best level is kept
@@ -467,20 +479,32 @@ extern "C" int bsx_mapper_create(const bsx_index *ix, const bsx_params *p, uint3
     memcpy(a.digest_site, p->digest_site, sizeof a.digest_site);
     a.stride = stride; a.stats = m->d_stats; a.debug = m->d_debug;
     a.hit_stride = m->hit_stride; a.dd_stride = m->dd_stride; a.pair_stride = m->pair_stride;
-    *out = m;
     return BSX_OK;
 }
 
 static cudaStream_t pick_stream(bsx_mapper *m, int slot, void *stream) { return stream ? (cudaStream_t)stream : m->slot[slot].stream; }
 
-static int upload_slot(bsx_mapper *m, int si, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb, cudaStream_t st) {
+// packed input needs what the device compares against to be upper-case ACGT (include/bsmap_b200.h)
+static int check_packed_ok(const bsx_mapper *m) {
+    auto acgt = [](const char *t, size_t cap) { for (size_t i = 0; i < cap && t[i]; i++) if (!strchr("ACGT", t[i])) return false; return true; };
+    for (int i = 0; i < m->par.n_adapter; i++)
+        if (!acgt(m->par.adapter[i], 63)) { bsx_set_error("packed read input needs upper-case ACGT adapters (got %s)", m->par.adapter[i]); return BSX_ERR_UNSUPPORTED; }
+    if (m->par.rrbs && !acgt(m->par.digest_site, sizeof m->par.digest_site)) { bsx_set_error("packed read input needs an upper-case ACGT digestion site"); return BSX_ERR_UNSUPPORTED; }
+    if (m->meth) { bsx_set_error("packed read input cannot feed the attached methylation pile-up (it reads the ASCII bases)"); return BSX_ERR_UNSUPPORTED; }
+    return BSX_OK;
+}
+
+static int upload_slot(bsx_mapper *m, int si, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb, cudaStream_t st,
+                       bool packed = false) {
     bsx_slot &s = m->slot[si];
     if (n > m->max_batch) { bsx_set_error("batch of %u reads exceeds max_batch %u", n, m->max_batch); return BSX_ERR_ARG; }
-    BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_seq_a, sa, (size_t)n * m->stride, cudaMemcpyHostToDevice, st));
+    const size_t slot_bytes = packed ? bsx_packed_stride(m->stride) : (size_t)m->stride;
+    s.packed = packed;
+    BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_seq_a, sa, (size_t)n * slot_bytes, cudaMemcpyHostToDevice, st));
     BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_len_a, la, (size_t)n * 2, cudaMemcpyHostToDevice, st));
     if (sb) {
         int rc = alloc_pe(m); if (rc) return rc;
-        BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_seq_b, sb, (size_t)n * m->stride, cudaMemcpyHostToDevice, st));
+        BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_seq_b, sb, (size_t)n * slot_bytes, cudaMemcpyHostToDevice, st));
         BSX_CUDA_CHECK(cudaMemcpyAsync(s.d_len_b, lb, (size_t)n * 2, cudaMemcpyHostToDevice, st));
     }
     return BSX_OK;
@@ -496,6 +520,7 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     a.out_a = s.d_out_a; a.out_b = s.d_out_b; a.out_pair = s.d_out_pair; a.cnt_a = s.d_cnt_a; a.cnt_b = s.d_cnt_b;
     a.work_counter = s.d_counter; a.hit_scratch = s.d_hits; a.dd_scratch = s.d_dd; a.pair_scratch = s.d_pairs;
     a.prep = s.d_prep; a.mates = pe ? 2 : 1;
+    if (s.packed) { a.packed = 1; a.pk_maxlen = m->stride; a.pk_mask_off = (m->stride + 3) / 4; a.stride = (uint32_t)bsx_packed_stride(m->stride); }
     {   // 32 units per warp and atomic when the batch is large (>= 2 blocks per resident warp: the prepare phase runs
         // with all lanes busy); small batches take smaller blocks (>= 8 per warp) because there the tail decides --
         // config 5's 200 k heavy reads: 0.62 M reads/s with blocks of 32, 0.86 M with blocks of 4
@@ -511,7 +536,7 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     int rc = pe ? bsx_launch_map_pe(a, m->n_ctas_pe, st)
                 : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st)
                           : (a.ctx2 ? bsx_launch_map_se_wide(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st)));
-    if (rc == BSX_OK && m->meth) {
+    if (rc == BSX_OK && m->meth && !s.packed) {
         rc = bsx_meth_pile_mapped(m->meth, &m->meth_opts, m->meth_sam, m->par.report_repeat_hits, n, pe ? 2 : 1, m->stride,
                                   s.d_seq_a, s.d_seq_b, s.d_out_a, s.d_out_b, s.d_out_pair, st);
         m->launches++;
@@ -542,22 +567,28 @@ static int download_slot(bsx_mapper *m, int si, uint32_t n, bool pe, bsx_pair_re
 
 extern "C" int bsx_batch_upload(bsx_mapper *m, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb, void *stream) {
     if (!m || !sa || !la) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     return upload_slot(m, 0, n, sa, la, sb, lb, pick_stream(m, 0, stream));
+}
+extern "C" int bsx_batch_upload_packed(bsx_mapper *m, uint32_t n, const uint8_t *sa, const uint16_t *la, const uint8_t *sb, const uint16_t *lb, void *stream) {
+    if (!m || !sa || !la) return BSX_ERR_ARG;
+    int rc = check_packed_ok(m); if (rc) return rc;
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
+    return upload_slot(m, 0, n, (const char *)sa, la, (const char *)sb, lb, pick_stream(m, 0, stream), true);
 }
 extern "C" int bsx_batch_run_se(bsx_mapper *m, uint32_t n, uint32_t first_index, int readset, void *stream) {
     if (!m) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     return run_slot(m, 0, n, first_index, readset, false, pick_stream(m, 0, stream));
 }
 extern "C" int bsx_batch_run_pe(bsx_mapper *m, uint32_t n, uint32_t first_index, void *stream) {
     if (!m) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     return run_slot(m, 0, n, first_index, 0, true, pick_stream(m, 0, stream));
 }
 extern "C" int bsx_batch_download_se(bsx_mapper *m, uint32_t n, bsx_rec *out, uint16_t *counts, void *stream) {
     if (!m) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     cudaStream_t st = pick_stream(m, 0, stream);
     int rc = download_slot(m, 0, n, false, nullptr, out, nullptr, counts, nullptr, st); if (rc) return rc;
     BSX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -565,7 +596,7 @@ extern "C" int bsx_batch_download_se(bsx_mapper *m, uint32_t n, bsx_rec *out, ui
 }
 extern "C" int bsx_batch_download_pe(bsx_mapper *m, uint32_t n, bsx_pair_rec *out, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb, void *stream) {
     if (!m) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     cudaStream_t st = pick_stream(m, 0, stream);
     int rc = download_slot(m, 0, n, true, out, oa, ob, ca, cb, st); if (rc) return rc;
     BSX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -573,7 +604,7 @@ extern "C" int bsx_batch_download_pe(bsx_mapper *m, uint32_t n, bsx_pair_rec *ou
 }
 extern "C" int bsx_mapper_sync(bsx_mapper *m) {
     if (!m) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     BSX_CUDA_CHECK(cudaStreamSynchronize(m->slot[0].stream));
     BSX_CUDA_CHECK(cudaStreamSynchronize(m->slot[1].stream));
     return BSX_OK;
@@ -583,16 +614,18 @@ extern "C" int bsx_mapper_sync(bsx_mapper *m) {
 // batch k+1 and the D2H copy of batch k-1 overlap the kernel of batch k (host buffers should be
 // pinned for the overlap to be real).
 static int map_host(bsx_mapper *m, bool pe, uint32_t n, const char *sa, const uint16_t *la, const char *sb, const uint16_t *lb,
-                    uint32_t first_index, int readset, bsx_pair_rec *op, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb) {
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+                    uint32_t first_index, int readset, bsx_pair_rec *op, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb,
+                    bool packed = false) {
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
+    const size_t slot_bytes = packed ? bsx_packed_stride(m->stride) : (size_t)m->stride;
     uint32_t done = 0; int k = 0;
     while (done < n) {
         const int si = k & 1;
         cudaStream_t st = m->slot[si].stream;
         const uint32_t nb = std::min(m->max_batch, n - done);
         BSX_CUDA_CHECK(cudaStreamSynchronize(st));    // slot free again
-        int rc = upload_slot(m, si, nb, sa + (size_t)done * m->stride, la + done, sb ? sb + (size_t)done * m->stride : nullptr,
-                             lb ? lb + done : nullptr, st);
+        int rc = upload_slot(m, si, nb, sa + (size_t)done * slot_bytes, la + done, sb ? sb + (size_t)done * slot_bytes : nullptr,
+                             lb ? lb + done : nullptr, st, packed);
         if (rc) return rc;
         rc = run_slot(m, si, nb, first_index + done, readset, pe, st); if (rc) return rc;
         rc = download_slot(m, si, nb, pe, op ? op + done : nullptr, oa ? oa + done : nullptr, ob ? ob + done : nullptr,
@@ -618,9 +651,24 @@ extern "C" int bsx_map_pe(bsx_mapper *m, uint32_t n, const char *sa, const uint1
     return map_host(m, true, n, sa, la, sb, lb, first_index, 0, out, oa, ob, ca, cb);
 }
 
+extern "C" int bsx_map_se_packed(bsx_mapper *m, uint32_t n, const uint8_t *packed, const uint16_t *lens, uint32_t first_index, int readset,
+                                 bsx_rec *out, uint16_t *counts) {
+    if (m && n == 0) return BSX_OK;
+    if (!m || !packed || !lens || !out) { bsx_set_error("bsx_map_se_packed: bad argument"); return BSX_ERR_ARG; }
+    int rc = check_packed_ok(m); if (rc) return rc;
+    return map_host(m, false, n, (const char *)packed, lens, nullptr, nullptr, first_index, readset, nullptr, out, nullptr, counts, nullptr, true);
+}
+extern "C" int bsx_map_pe_packed(bsx_mapper *m, uint32_t n, const uint8_t *pa, const uint16_t *la, const uint8_t *pb, const uint16_t *lb,
+                                 uint32_t first_index, bsx_pair_rec *out, bsx_rec *oa, bsx_rec *ob, uint16_t *ca, uint16_t *cb) {
+    if (m && n == 0) return BSX_OK;
+    if (!m || !pa || !la || !pb || !lb || !out || !oa || !ob) { bsx_set_error("bsx_map_pe_packed: bad argument"); return BSX_ERR_ARG; }
+    int rc = check_packed_ok(m); if (rc) return rc;
+    return map_host(m, true, n, (const char *)pa, la, (const char *)pb, lb, first_index, 0, out, oa, ob, ca, cb, true);
+}
+
 extern "C" int bsx_mapper_stats(bsx_mapper *m, bsx_stats *out, int reset) {
     if (!m || !out) return BSX_ERR_ARG;
-    BSX_CUDA_CHECK(cudaSetDevice(m->ix->device));
+    BSX_CUDA_CHECK(cudaSetDevice(m->device));
     BSX_CUDA_CHECK(cudaDeviceSynchronize());
     BSX_CUDA_CHECK(cudaMemcpy(out, m->d_stats, sizeof(bsx_stats), cudaMemcpyDeviceToHost));
     if (reset) BSX_CUDA_CHECK(cudaMemset(m->d_stats, 0, sizeof(bsx_stats)));

@@ -11,8 +11,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -31,6 +33,7 @@ struct Opts {
     std::string meth_out;        // --methratio FILE: methylation ratios straight from the device (no SAM needed)
     bsx_meth_opts mo;
     unsigned batch = 1u << 17;   // reads per GPU batch: small enough to keep the three host stages overlapped
+    std::string gpus;            // -g: number of devices (default: all visible) or a comma list of device ids; output stays in input order
 };
 
 void usage() {
@@ -64,6 +67,8 @@ void usage() {
            "       -2  <str>   output file of unpaired alignment hits\n"
            "       -h          help\n"
            "\n  Extensions (not in BSMAP 2.6):\n"
+           "       -g  <int|list>  number of GPUs to map on (default: all visible) or a comma list of device ids; the index is\n"
+           "                   replicated over NVLink, batches are dealt to the devices and written in input order\n"
            "       --methratio <str>   also write methratio.py's table, piled up on the GPU from the mapped batches\n"
            "                           (-o may then be omitted: no alignment text is produced at all)\n"
            "       --meth-unique --meth-pair --meth-zero --meth-cpg --meth-trim <int> --meth-min-depth <int>\n"
@@ -102,7 +107,7 @@ int get_options(int argc, char **argv, Opts &o) {
         const char c = argv[i][1];
         const char *val = nullptr;
         const bool flag = (c == 'R' || c == 'u' || c == 'h');
-        if (c == 0 || !strchr("abdo2smxnrIvwqfzpARuBEDMLSh", c)) return i;   // default: return i (main.cpp:283)
+        if (c == 0 || !strchr("abdo2smxnrIvwqfzpARuBEDMLShg", c)) return i;   // default: return i (main.cpp:283)
         if (!flag) {
             if (argv[i][2] == 0) { if (i + 1 >= argc) return i; val = argv[++i]; }
             else if (argv[i][2] == '=') val = argv[i] + 3;
@@ -136,6 +141,7 @@ int get_options(int argc, char **argv, Opts &o) {
             case 'M': if (!((val[0] == 'T' || val[0] == 't') && (val[1] == 'C' || val[1] == 'c'))) { fprintf(stderr, "-M %s: only the TC transition is supported by the GPU path\n", val); exit(1); } break;
             case 'L': o.p.max_readlen = atoi(val); break;
             case 'S': o.p.randseed = atoi(val); break;
+            case 'g': o.gpus = val; break;
             case 'h': usage(); break;
             default: return i;
         }
@@ -152,6 +158,26 @@ template <class T> struct Chan {
     void close() { std::unique_lock<std::mutex> l(m); closed = true; cv.notify_all(); }
 };
 
+// hand-off that releases items in sequence order whatever order they arrive in (several mapper threads, one formatter)
+template <class T> struct Ordered {
+    std::mutex m; std::condition_variable cv; std::map<unsigned, T> q; unsigned next = 0; bool closed = false;
+    void push(unsigned seq, T &&v) { std::unique_lock<std::mutex> l(m); q.emplace(seq, std::move(v)); cv.notify_all(); }
+    bool pop(T &v) {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return (!q.empty() && q.begin()->first == next) || closed; });
+        if (q.empty() || q.begin()->first != next) return false;
+        v = std::move(q.begin()->second); q.erase(q.begin()); next++;
+        return true;
+    }
+    void close() { std::unique_lock<std::mutex> l(m); closed = true; cv.notify_all(); }
+};
+// free list of pinned staging slots: taken by the cutter, returned by the formatter
+struct SlotPool {
+    std::mutex m; std::condition_variable cv; std::vector<int> free_;
+    void put(int s) { std::unique_lock<std::mutex> l(m); free_.push_back(s); cv.notify_all(); }
+    int take() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !free_.empty(); }); const int s = free_.back(); free_.pop_back(); return s; }
+};
+
 struct Views { std::vector<bsx_view> name, seq, qual; std::vector<std::string> store; };
 void take_views(bsx_reads *r, Views &v) { v.name.swap(r->name); v.seq.swap(r->seq); v.qual.swap(r->qual); v.store.swap(r->slow_store); }
 
@@ -165,6 +191,28 @@ template <class T> T *pinned(size_t count) {
 }
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// -g: "" = every visible device, "N" = the first N, "a,b,c" = these device ids (an id may repeat: several mappers on one GPU)
+std::vector<int> device_list(const std::string &g) {
+    const int have = std::max(1, bsx_device_count());
+    std::vector<int> d;
+    if (g.find(',') != std::string::npos) {
+        size_t q = 0;
+        while (q <= g.size()) {
+            const size_t e = g.find(',', q);
+            const std::string t = g.substr(q, e == std::string::npos ? std::string::npos : e - q);
+            if (!t.empty()) { const int v = atoi(t.c_str()); if (v < 0 || v >= have) { fprintf(stderr, "-g: no device %d (have %d)\n", v, have); exit(1); } d.push_back(v); }
+            if (e == std::string::npos) break;
+            q = e + 1;
+        }
+    } else {
+        int n = g.empty() ? have : atoi(g.c_str());
+        if (n < 1 || n > have) n = have;
+        for (int i = 0; i < n; i++) d.push_back(i);
+    }
+    if (d.empty()) d.push_back(0);
+    return d;
+}
 
 }  // namespace
 
@@ -183,7 +231,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     }
     // the CUDA context comes up on its own thread while this one parses the reference FASTA
     bsx_index *ix = nullptr;
-    std::thread ctx_thread([] { cudaFree(nullptr); });
+    std::thread ctx_thread([&o] { cudaSetDevice(device_list(o.gpus)[0]); cudaFree(nullptr); });
     std::vector<std::string> ref_names, ref_seqs;
     // BSX_REF_CACHE=<dir>: keep the packed reference of every FASTA seen there (keyed by name, size and mtime);
     // the next run skips the FASTA parse and rebuilds the seed table from the packed strand on the device
@@ -202,7 +250,8 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     const double t_fa = now();
     ctx_thread.join();
     const double t_ctx = now();
-    if (from_cache && bsx_index_create_from_packed(&o.p, cache_path.c_str(), 0, &ix) != BSX_OK) {
+    const int dev0 = device_list(o.gpus)[0];
+    if (from_cache && bsx_index_create_from_packed(&o.p, cache_path.c_str(), dev0, &ix) != BSX_OK) {
         fprintf(stderr, "warning: %s -- falling back to %s\n", bsx_last_error(), o.d.c_str());
         from_cache = false; ix = nullptr;
         lrc = bsx_load_fasta(o.d.c_str(), ref_names, ref_seqs);
@@ -211,7 +260,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     if (!from_cache) {
         std::vector<const char *> np, sp; std::vector<uint32_t> ln;
         for (size_t k = 0; k < ref_seqs.size(); k++) { np.push_back(ref_names[k].c_str()); sp.push_back(ref_seqs[k].data()); ln.push_back((uint32_t)ref_seqs[k].size()); }
-        if (bsx_index_create(&o.p, (int)ref_seqs.size(), np.data(), sp.data(), ln.data(), 0, &ix) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+        if (bsx_index_create(&o.p, (int)ref_seqs.size(), np.data(), sp.data(), ln.data(), dev0, &ix) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
         if (!cache_path.empty() && bsx_index_save_packed(ix, cache_path.c_str()) != BSX_OK) fprintf(stderr, "warning: %s\n", bsx_last_error());
     }
     if (o.meth_out.empty()) std::vector<std::string>().swap(ref_seqs);   // the methratio report prints reference context
@@ -258,8 +307,17 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     const unsigned stride = 160;
     const int threads = bsx_host_threads(o.num_procs);
     if (const char *e = getenv("BSX_CLI_BATCH")) { const int v = atoi(e); if (v > 0) o.batch = (unsigned)v; }
-    bsx_mapper *mp = nullptr;
-    if (bsx_mapper_create(ix, &p, o.batch, stride, &mp) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    // devices: -g N (default all visible).  Device 0 holds the index and starts mapping at once; the others come up on
+    // their own threads (context, replica of the index over NVLink, mapper) and join the pool when ready, so a small
+    // input never waits for them.  --methratio piles up on one device.
+    std::vector<int> devs = device_list(o.gpus);
+    if (!o.meth_out.empty()) devs.resize(1);
+    const int n_dev = (int)devs.size();
+    std::vector<bsx_mapper *> mps((size_t)n_dev, nullptr);
+    std::vector<bsx_index *> ixs((size_t)n_dev, nullptr);
+    ixs[0] = ix;
+    if (bsx_mapper_create(ix, &p, o.batch, stride, &mps[0]) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+    bsx_mapper *mp = mps[0];
     bsx_meth *mh = nullptr;
     if (!o.meth_out.empty()) {
         // SAM rules (mate-overlap removal) unless the alignment output is BSP: the table then equals methratio.py run on -o
@@ -268,25 +326,26 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     }
     bsx_reads_skip(ra, o.read_start - 1); if (pe) bsx_reads_skip(rb, o.read_start - 1);
     unsigned index_a = o.read_start - 1;
-    // pinned staging: one upload buffer per mate (the map call returns after its copies), three result slots
-    // (slot k is read by the formatter while k+1 waits in the channel and k+2 is being mapped)
-    const int NSLOT = 3;
-    // three upload buffers per mate as well: batch k is cut while k-1 waits for the mapper thread and k-2 is being mapped
-    char *sa[NSLOT], *sb[NSLOT]; uint16_t *la[NSLOT], *lb[NSLOT];
+    // pinned staging slots (upload buffers + result records), handed round by a free list: a slot is taken by the cutter,
+    // travels with its batch through a mapper thread and the formatter, and comes back when its text exists
+    const int NSLOT = 2 * n_dev + 2;
+    std::vector<char *> sa(NSLOT), sb(NSLOT); std::vector<uint16_t *> la(NSLOT), lb(NSLOT);
+    std::vector<bsx_rec *> reca(NSLOT), recb(NSLOT); std::vector<bsx_pair_rec *> recp(NSLOT); std::vector<uint16_t *> cnta(NSLOT), cntb(NSLOT);
+    const bool want_counts = !p.out_sam;   // per-level hit counts are a BSP column
+    SlotPool pool;
     for (int k = 0; k < NSLOT; k++) {
         sa[k] = pinned<char>((size_t)o.batch * stride); la[k] = pinned<uint16_t>(o.batch);
         sb[k] = pe ? pinned<char>((size_t)o.batch * stride) : nullptr; lb[k] = pe ? pinned<uint16_t>(o.batch) : nullptr;
-    }
-    bsx_rec *reca[NSLOT], *recb[NSLOT]; bsx_pair_rec *recp[NSLOT]; uint16_t *cnta[NSLOT], *cntb[NSLOT];
-    const bool want_counts = !p.out_sam;   // per-level hit counts are a BSP column
-    for (int k = 0; k < NSLOT; k++) {
         reca[k] = pinned<bsx_rec>(o.batch); cnta[k] = want_counts ? pinned<uint16_t>((size_t)o.batch * 16) : nullptr;
         recb[k] = pe ? pinned<bsx_rec>(o.batch) : nullptr; recp[k] = pe ? pinned<bsx_pair_rec>(o.batch) : nullptr;
         cntb[k] = pe && want_counts ? pinned<uint16_t>((size_t)o.batch * 16) : nullptr;
+        pool.put(k);
     }
     unsigned long long n_aligned = 0, n_pairs = 0, n_a = 0, n_b = 0;
-    double t_parse = 0, t_map = 0, t_fmt = 0, t_write = 0;
-    Chan<Job> jobs(1); Chan<Text> texts(2);
+    double t_parse = 0, t_fmt = 0, t_write = 0;
+    std::vector<double> t_map((size_t)n_dev, 0.0); std::vector<unsigned long long> n_map((size_t)n_dev, 0);
+    Ordered<Job> jobs; Chan<Text> texts(2);
+    std::atomic<int> fail{0};
     const double t_alloc = now();
     std::thread formatter([&] {
         Job j;
@@ -310,6 +369,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
                                      recp[j.slot], reca[j.slot], recb[j.slot], cnta[j.slot], cntb[j.slot], threads, tx.main, tx.unpair, st);
                 n_pairs += st[0]; n_a += st[1]; n_b += st[2];
             }
+            pool.put(j.slot);
             t_fmt += now() - t;
             texts.push(std::move(tx));
         }
@@ -319,57 +379,73 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         Text tx;
         while (texts.pop(tx)) {
             const double t = now();
-            for (const std::string &c : tx.main) fwrite(c.data(), 1, c.size(), fout);
-            if (fun) for (const std::string &c : tx.unpair) fwrite(c.data(), 1, c.size(), fun);
+            for (const std::string &c : tx.main) if (fwrite(c.data(), 1, c.size(), fout) != c.size()) fail = 2;
+            if (fun) for (const std::string &c : tx.unpair) if (fwrite(c.data(), 1, c.size(), fun) != c.size()) fail = 2;
             t_write += now() - t;
             printf("%u reads finished. %ld secs passed\n", tx.done_index, (long)(time(nullptr) - t0));
         }
     });
-    // cut (this thread) || map (mapper thread) || format || write
-    struct CutJob { uint32_t n = 0; unsigned first = 0, done_index = 0; int slot = 0; Views a, b; };
-    Chan<CutJob> cuts(1);
-    int fail = 0;
-    std::thread mapper([&] {
+    // cut (this thread) || map (one thread per device) || format || write
+    struct CutJob { uint32_t n = 0; unsigned first = 0, done_index = 0, seq = 0; int slot = 0; Views a, b; };
+    Chan<CutJob> cuts((size_t)n_dev);
+    std::vector<std::thread> mappers;
+    std::atomic<int> dev_up{0};
+    for (int g = 0; g < n_dev; g++) mappers.emplace_back([&, g] {
+        if (g > 0) {   // bring the device up: context, replica of the index (cudaMemcpyPeer over NVLink), mapper
+            if (bsx_index_replicate(ix, devs[g], &ixs[g]) != BSX_OK || bsx_mapper_create(ixs[g], &p, o.batch, stride, &mps[g]) != BSX_OK) {
+                fprintf(stderr, "warning: device %d not used: %s\n", devs[g], bsx_last_error());
+                dev_up++;
+                return;                                             // the other devices carry on
+            }
+        }
+        dev_up++;
         CutJob c;
         while (cuts.pop(c)) {
-            if (fail) continue;                                     // drain so that the cutter never blocks
-            const double t = now();
-            const int s = c.slot;
-            int mrc;
-            if (!pe) mrc = bsx_map_se(mp, c.n, sa[s], la[s], c.first, 0, reca[s], cnta[s]);
-            else mrc = bsx_map_pe(mp, c.n, sa[s], la[s], sb[s], lb[s], c.first, recp[s], reca[s], recb[s], cnta[s], cntb[s]);
-            t_map += now() - t;
-            if (mrc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); fail = 1; continue; }
-            Job j; j.n = c.n; j.slot = s; j.done_index = c.done_index;
+            Job j; j.n = c.n; j.slot = c.slot; j.done_index = c.done_index;
+            if (!fail) {
+                const double t = now();
+                const int s = c.slot;
+                int mrc;
+                if (!pe) mrc = bsx_map_se(mps[g], c.n, sa[s], la[s], c.first, 0, reca[s], cnta[s]);
+                else mrc = bsx_map_pe(mps[g], c.n, sa[s], la[s], sb[s], lb[s], c.first, recp[s], reca[s], recb[s], cnta[s], cntb[s]);
+                t_map[g] += now() - t; n_map[g] += c.n;
+                if (mrc != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); fail = 1; }
+            }
+            if (fail) j.n = 0;                                      // keep the sequence flowing so that nobody blocks
             j.a = std::move(c.a); j.b = std::move(c.b);
-            jobs.push(std::move(j));
+            jobs.push(c.seq, std::move(j));
         }
-        jobs.close();
     });
+    // BSX_CLI_WAIT_DEVICES=1: do not start before every device is up (reproducible multi-GPU timings and tests)
+    if (getenv("BSX_CLI_WAIT_DEVICES")) while (dev_up.load() < n_dev) usleep(200);
     for (unsigned k = 0; !fail; k++) {
         const unsigned first = index_a;
         const unsigned want = (unsigned)std::min<unsigned long long>(o.batch, index_a < o.read_end ? (unsigned long long)o.read_end - index_a : 0);
         if (!want) break;
-        const int slot = (int)(k % NSLOT);
+        const int slot = pool.take();
         const double t = now();
         const unsigned n1 = bsx_reads_next(ra, want, stride, sa[slot], la[slot], threads);
         const unsigned n2 = pe ? bsx_reads_next(rb, want, stride, sb[slot], lb[slot], threads) : n1;
         t_parse += now() - t;
         if (!n1 || n1 != n2) break;
         index_a += n1;
-        CutJob c; c.n = n1; c.first = first; c.slot = slot; c.done_index = index_a - o.read_start + 1;
+        CutJob c; c.n = n1; c.first = first; c.slot = slot; c.seq = k; c.done_index = index_a - o.read_start + 1;
         take_views(ra, c.a); if (pe) take_views(rb, c.b);
         cuts.push(std::move(c));
     }
     cuts.close();
-    mapper.join();
+    for (auto &t : mappers) t.join();
+    jobs.close();
     const double t_loop = now();
     formatter.join(); writer.join();
-    fclose(fout); if (fun) fclose(fun);
+    if (fclose(fout) != 0) fail = 2;
+    if (fun && fclose(fun) != 0) fail = 2;
+    if (fail == 2) fprintf(stderr, "error: writing the alignment output failed (disk full?)%s\n", o.bam_out.empty() ? "" : "; the BAM conversion is skipped");
     const double t_drain = now();
     if (timing) fprintf(stderr, "[bsx timing] wall: reference FASTA %.3f s || CUDA context (ready at %.3f s), index %.3f s, buffers+mapper %.3f s, map loop %.3f s, drain %.3f s | stage busy time: cut %.3f s, map %.3f s, format %.3f s, write %.3f s | reads cut by line %llu, by token reader %llu | %d host threads\n",
-                        t_fa - t_start, t_ctx - t_start, t_idx - t_ctx, t_alloc - t_idx, t_loop - t_alloc, t_drain - t_loop, t_parse, t_map, t_fmt, t_write, (unsigned long long)(ra->n_fast + (rb ? rb->n_fast : 0)),
+                        t_fa - t_start, t_ctx - t_start, t_idx - t_ctx, t_alloc - t_idx, t_loop - t_alloc, t_drain - t_loop, t_parse, t_map[0], t_fmt, t_write, (unsigned long long)(ra->n_fast + (rb ? rb->n_fast : 0)),
                         (unsigned long long)(ra->n_slow + (rb ? rb->n_slow : 0)), threads);
+    if (timing && n_dev > 1) for (int g = 0; g < n_dev; g++) fprintf(stderr, "[bsx timing] device %d: %llu reads in %.3f s of map calls\n", devs[g], n_map[g], t_map[g]);
     bsx_reads_close(ra); bsx_reads_close(rb);
     if (fail) return 1;
     if (mh) {
@@ -402,7 +478,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     }
     printf("Total time consumed:  %ld secs\n", (long)(time(nullptr) - t0));
     const double t_fin = now();
-    bsx_mapper_destroy(mp); bsx_index_destroy(ix);
+    for (int g = n_dev - 1; g >= 0; g--) { bsx_mapper_destroy(mps[g]); bsx_index_destroy(ixs[g]); }
     if (timing) fprintf(stderr, "[bsx timing] teardown %.3f s, total in main %.3f s\n", now() - t_fin, now() - t_start);
     return 0;
 }

@@ -29,6 +29,8 @@ struct MapArgs {
     const uint16_t *len_a, *len_b;
     uint32_t stride, n, first_index;
     int readset;
+    int packed;                   // 1: read slots hold 2-bit bases + valid mask (bsx_packed_stride), `stride` is the packed slot size
+    uint32_t pk_mask_off, pk_maxlen;   // byte offset of the mask inside a packed slot; bases a slot can hold
     bsx_rec *out_a, *out_b;
     bsx_pair_rec *out_pair;
     uint16_t *cnt_a, *cnt_b;

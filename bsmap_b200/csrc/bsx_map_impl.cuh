@@ -25,8 +25,10 @@
 //     K6  pairing                PairAlign::RunAlign / GetPairs (pairs.cpp:34-190).
 //
 // Integer work bound by memory latency and issue slots: no tensor cores.
+#include <atomic>
 #include <cstdio>
 #include "bsx_map.cuh"
+#define BSX_MAX_DEVICES 64
 
 // RRBS mode (-D) as a compile-time constant where a translation unit fixes it (dead code leaves the binary)
 #ifndef BSX_RRBS
@@ -1033,10 +1035,13 @@ int BSX_SE_OCC(size_t smem) {
 }
 int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
     const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot);
-    static size_t configured = 0;
-    if (smem > configured) {
+    // the attribute belongs to (function, device): one cache slot per device, several mappers / host threads may launch
+    static std::atomic<size_t> configured[BSX_MAX_DEVICES];
+    int dev = 0;
+    BSX_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= BSX_MAX_DEVICES || smem > configured[dev].load(std::memory_order_relaxed)) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(BSX_SE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        if (dev >= 0 && dev < BSX_MAX_DEVICES) configured[dev].store(smem, std::memory_order_relaxed);
     }
     BSX_SE_KERNEL<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
     BSX_CUDA_CHECK(cudaGetLastError());
@@ -1054,10 +1059,12 @@ int bsx_map_occupancy_pe(size_t smem) {
 }
 int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
     const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static std::atomic<size_t> configured[BSX_MAX_DEVICES];
+    int dev = 0;
+    BSX_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= BSX_MAX_DEVICES || smem > configured[dev].load(std::memory_order_relaxed)) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        if (dev >= 0 && dev < BSX_MAX_DEVICES) configured[dev].store(smem, std::memory_order_relaxed);
     }
     bsx_map_pe_kernel<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
     BSX_CUDA_CHECK(cudaGetLastError());

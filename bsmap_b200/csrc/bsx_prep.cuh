@@ -113,6 +113,89 @@ __device__ int trim_adapter(const MapArgs &A, const uint8_t *sq, int len) {
     return len;
 }
 
+// ---- packed read slots (include/bsmap_b200.h): 2-bit bases, four per byte, then a 1-bit valid mask, eight per byte
+// base i of a packed slot: 2-bit code | valid << 2
+__device__ __forceinline__ uint32_t pk_base(const uint8_t *pk, uint32_t mask_off, int i) {
+    const uint32_t c = (pk[i >> 2] >> (6 - 2 * (i & 3))) & 3u, v = (pk[mask_off + (i >> 3)] >> (7 - (i & 7))) & 1u;
+    return c | (v << 2);
+}
+// 16 mask bits (first base in bit 15) -> 01 per valid base, first base in bits 31:30
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u; return (x | (x << 1)) & 0x55555555u;
+}
+
+// ConvertBinaySeq from a packed slot: chain 0 is a byte swap and a bit spread, chain 1 walks the read backwards
+__device__ __forceinline__ void pack_chain_packed(const uint8_t *pk, uint32_t mask_off, int len, int chain, uint32_t *rw, uint32_t *m5) {
+    if (!chain) {
+        const uint32_t *w4 = reinterpret_cast<const uint32_t *>(pk);       // slots are 4-byte aligned
+        #pragma unroll 1
+        for (int j = 0; j < BSX_FIXWORDS; j++) {
+            uint32_t w = 0, m = 0;
+            const int nb = len - 16 * j;
+            if (nb > 0) {
+                w = __byte_perm(__ldg(w4 + j), 0u, 0x0123);                 // first base of the word into bits 31:30
+                m = spread16(((uint32_t)__ldg(pk + mask_off + 2 * j) << 8) | (uint32_t)__ldg(pk + mask_off + 2 * j + 1));
+                if (nb < 16) { const uint32_t keep = ~(0xffffffffu >> (2 * nb)); w &= keep; m &= keep; }
+                w &= m | (m << 1);                                          // invalid bases carry code 0 (alphabet[], param.cpp:210)
+            }
+            rw[j * 32] = w; m5[j * 32] = m;
+        }
+    } else {
+        #pragma unroll 1
+        for (int j = 0; j < BSX_FIXWORDS; j++) {
+            uint32_t w = 0, m = 0;
+            #pragma unroll 1
+            for (int b = 0; b < 16; b++) {
+                const int i = 16 * j + b;
+                uint32_t code = 0, v = 0;
+                if (i < len) {
+                    const uint32_t x = pk_base(pk, mask_off, len - 1 - i);
+                    v = x >> 2;
+                    code = v ? 3u - (x & 3u) : 3u;                          // rev_alphabet (param.cpp:215-218)
+                }
+                w = (w << 2) | code; m = (m << 2) | v;
+            }
+            rw[j * 32] = w; m5[j * 32] = m;
+        }
+    }
+}
+
+// TrimAdapter on a packed slot.  Adapters and the digestion site are upper-case ACGT (checked on the host), so
+// "characters differ" is "invalid base or different code".
+__device__ int trim_adapter_packed(const MapArgs &A, const uint8_t *pk, int len) {
+    const int s = A.s, tail = A.rrbs ? 5 : 4;
+    const uint32_t mo = A.pk_mask_off;
+    #pragma unroll 1
+    for (int a = 0; a < A.n_adapter; a++) {
+        const int al = A.adapter_len[a];
+        #pragma unroll 1
+        for (int pos = s; pos < len - tail; pos++) {
+            int m0 = 0, k = 0;
+            #pragma unroll 1
+            for (; k < al && k < 15 && pos + k < len; k++) {
+                m0 += (pk_base(pk, mo, pos + k) != (bsx_code_fwd((uint8_t)A.adapter[a][k]) | 4u));
+                if (m0 > 4) break;
+            }
+            bool ok = false;
+            if (!A.rrbs) ok = (k >= m0 * 5 && k > 3);
+            else if (k >= m0 * 5) {
+                const int sl = A.site_len, dp = A.digest_pos;
+                int m = m0, m2 = m0;
+                #pragma unroll 1
+                for (int t = 0; t < sl - dp; t++) {
+                    const uint32_t x = bsx_code_fwd((uint8_t)A.digest_site[t]) | 4u, y = pk_base(pk, mo, pos - sl + dp + t);
+                    m += (x != y) && (x != 5u || y != 7u);                  // 'C' vs 'T'
+                    m2 += (x != y) && (x != 6u || y != 4u);                 // 'G' vs 'A'
+                }
+                ok = (k >= m * 5) || (A.pairend && k >= m2 * 5);
+            }
+            if (ok) return pos;
+        }
+    }
+    return len;
+}
+
 // seed_array[p] (align.cpp:101-105): 3-letter key of the seed starting at read offset p
 __device__ __forceinline__ uint32_t seed_key(const MapArgs &A, const uint32_t *rw, int p) {
     const int j = p >> 4, sh = (p & 15) * 2;
@@ -259,15 +342,15 @@ __device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, ui
         int len = (mate ? A.len_b : A.len_a)[r];
         if (len > A.max_readlen) len = A.max_readlen;                       // reads.cpp:115-117
         if (len > BSX_MAX_READLEN) len = BSX_MAX_READLEN;
-        if (len > (int)A.stride) len = (int)A.stride;
+        if (len > (int)(A.packed ? A.pk_maxlen : A.stride)) len = (int)(A.packed ? A.pk_maxlen : A.stride);
         const int readset = A.mates == 2 ? mate + 1 : A.readset;
         const int raw = len;
-        len = trim_adapter(A, sq, len);
+        len = A.packed ? trim_adapter_packed(A, sq, len) : trim_adapter(A, sq, len);
         const int fc = A.chains || (readset < 2), cc = A.chains || (readset == 2);   // flag_chain / cflag_chain (align.cpp:93-94)
         int filtered = len < A.s, rmsn = 0, seg = 0;
         if (!filtered) {
             // CountNs (align.cpp:48-55) from the valid-base mask of the chain the read uses first
-            pack_chain(sq, A.stride, len, fc ? 0 : 1, rw, m5);
+            if (A.packed) pack_chain_packed(sq, A.pk_mask_off, len, fc ? 0 : 1, rw, m5); else pack_chain(sq, A.stride, len, fc ? 0 : 1, rw, m5);
             int nv = 0;
             #pragma unroll 1
             for (int j = 0; j < BSX_FIXWORDS; j++) nv += __popc(m5[j * 32]);
@@ -282,7 +365,9 @@ __device__ __noinline__ int bsx_prep_unit(const MapArgs &A, const PrepSm *Kp, ui
             #pragma unroll 1
             for (int chain = 0; chain < 2; chain++) {
                 if (chain == 0 ? !fc : !cc) continue;
-                if (chain == 1 && fc) pack_chain(sq, A.stride, len, 1, rw, m5);   // -n 1: the other orientation, same scratch
+                if (chain == 1 && fc) {                                          // -n 1: the other orientation, same scratch
+                    if (A.packed) pack_chain_packed(sq, A.pk_mask_off, len, 1, rw, m5); else pack_chain(sq, A.stride, len, 1, rw, m5);
+                }
                 uint32_t *slot = reinterpret_cast<uint32_t *>(img + sizeof(ImgHdr) + (A.nslot == 2 ? chain : 0) * A.img_slot);
                 np += select_seeds(A, &K, rw, len, seg, chain, reinterpret_cast<uint4 *>(slot + 2 * BSX_FIXWORDS), dbg);
                 #pragma unroll 1

@@ -360,6 +360,39 @@ extern "C" int bsx_reads_get(const bsx_reads *r, uint32_t i, const char **name, 
 // Reference FASTA (RefSeq::LoadNextSeq, dbseq.cpp:18-54).  A '>' outside a header line opens a record;
 // its name is the first blank-delimited token of that line; the sequence is every non-blank byte up
 // to the next '>'.  One memchr pass finds the records, then the bodies are compacted in parallel.
+// ---- packed read slots (include/bsmap_b200.h): what ConvertBinaySeq (align.cpp:90-162) derives from the text, on the host
+extern "C" size_t bsx_packed_stride(uint32_t stride) { return (((size_t)stride + 3) / 4 + ((size_t)stride + 7) / 8 + 3) & ~(size_t)3; }
+
+extern "C" int bsx_pack_reads(uint32_t n, const char *seqs, uint32_t stride, const uint16_t *lens, uint8_t *packed,
+                              uint64_t *n_lowercase, int threads) {
+    if ((n && (!seqs || !lens || !packed)) || stride < 16) { bsx_set_error("bsx_pack_reads: bad argument"); return BSX_ERR_ARG; }
+    const size_t ps = bsx_packed_stride(stride), moff = ((size_t)stride + 3) / 4;
+    // per ASCII byte: 2-bit code | valid << 2 | lower-case base << 3
+    uint8_t lut[256];
+    memset(lut, 0, sizeof lut);
+    lut['A'] = 4; lut['C'] = 5; lut['G'] = 6; lut['T'] = 7; lut['a'] = 12; lut['c'] = 13; lut['g'] = 14; lut['t'] = 15;
+    threads = bsx_host_threads(threads);
+    std::vector<uint64_t> low((size_t)threads, 0);
+    bsx_parallel(threads, n, [&](int tid, size_t b, size_t e) {
+        uint64_t lc = 0;
+        for (size_t r = b; r < e; r++) {
+            const uint8_t *sq = (const uint8_t *)seqs + r * stride;
+            uint8_t *o = packed + r * ps;
+            memset(o, 0, ps);
+            const uint32_t len = std::min<uint32_t>(lens[r], stride);
+            for (uint32_t i = 0; i < len; i++) {
+                const uint8_t c = lut[sq[i]];
+                o[i >> 2] |= (uint8_t)((c & 3u) << (6 - 2 * (i & 3u)));
+                o[moff + (i >> 3)] |= (uint8_t)(((c >> 2) & 1u) << (7 - (i & 7u)));
+                lc += c >> 3;
+            }
+        }
+        low[tid] = lc;
+    });
+    if (n_lowercase) { uint64_t t = 0; for (uint64_t x : low) t += x; *n_lowercase = t; }
+    return BSX_OK;
+}
+
 int bsx_load_fasta(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs) {
     const int fd = open(path, O_RDONLY);
     if (fd < 0) { bsx_set_error("fatal error: failed to open ref file %s", path); return BSX_ERR_IO; }

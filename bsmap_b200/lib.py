@@ -65,6 +65,7 @@ EXPORTS = [
     "bsx_reads_next", "bsx_reads_get", "bsx_emit_se", "bsx_emit_pe",
     "bsx_index_create_packed", "bsx_index_save_packed", "bsx_index_create_from_packed", "bsx_meth_opts_default", "bsx_meth_create", "bsx_meth_destroy", "bsx_meth_add", "bsx_meth_download",
     "bsx_meth_write", "bsx_methratio_main", "bsx_sam_to_sorted_bam", "bsx_mapper_attach_meth", "bsx_meth_valid_count",
+    "bsx_packed_stride", "bsx_pack_reads", "bsx_map_se_packed", "bsx_map_pe_packed", "bsx_batch_upload_packed",
 ]
 
 _lib = None
@@ -145,6 +146,12 @@ def load():
     L.bsx_meth_valid_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.bsx_meth_write.restype = sz
     L.bsx_meth_write.argtypes = [vp, C.POINTER(MethOpts), pp, vp, vp, i32, i32, C.POINTER(C.c_uint64)]
+    L.bsx_packed_stride.restype = sz
+    L.bsx_packed_stride.argtypes = [u32]
+    L.bsx_pack_reads.argtypes = [u32, vp, u32, vp, vp, C.POINTER(C.c_uint64), i32]
+    L.bsx_map_se_packed.argtypes = [vp, u32, vp, vp, u32, i32, vp, vp]
+    L.bsx_map_pe_packed.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.bsx_batch_upload_packed.argtypes = [vp, u32, vp, vp, vp, vp, vp]
     if hasattr(L, "bsx_mapper_debug_seeds"):
         L.bsx_mapper_debug_seeds.argtypes = [vp, u32, vp]
     _lib = L

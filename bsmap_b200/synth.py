@@ -207,6 +207,63 @@ def simulate_pairs(genome, n_pairs: int, read_len: int, seed: int, frag_min=150,
     return dict(seq1=m1, seq2=m2, chrom=ch, pos=pos, strand=strand, flen=flen)
 
 
+def rrbs_fragments(genome, site=b"CCGG", digest_pos=1, frag_min=40, frag_max=400):
+    """Digestion fragments of every chromosome between adjacent sites (torch, on the genome's device):
+    int64 tensors (chrom, start, end) of the fragments whose length lies in [frag_min, frag_max]."""
+    dev = genome[0].device
+    st = torch.tensor(list(site), dtype=torch.uint8, device=dev)
+    cs, a_, e_ = [], [], []
+    for c, g in enumerate(genome):
+        n = int(g.numel())
+        hit = torch.ones(n - len(site) + 1, dtype=torch.bool, device=dev)
+        for t in range(len(site)):
+            hit &= g[t:n - len(site) + 1 + t] == st[t]
+        sites = hit.nonzero().squeeze(1) + digest_pos
+        a, e = sites[:-1], sites[1:] + len(site) - 2 * digest_pos
+        ok = ((e - a) >= frag_min) & ((e - a) <= frag_max)
+        a_.append(a[ok]); e_.append(e[ok]); cs.append(torch.full((int(ok.sum()),), c, dtype=torch.int64, device=dev))
+    return torch.cat(cs), torch.cat(a_), torch.cat(e_)
+
+
+def simulate_rrbs_reads(genome, frags, n_reads: int, read_len: int, seed: int, adapter: bytes, conv=0.97, nsub_max=2, first_index: int = 0):
+    """RRBS single-end reads on the device: a random digestion fragment, Watson or Crick (reverse complement), bisulfite
+    converted, read through into `adapter` and then A's when the fragment is shorter than the read; up to nsub_max
+    substitutions.  Read r depends only on (seed, first_index + r).  -> uint8[n, L]"""
+    dev = genome[0].device
+    L = read_len
+    fc, fa, fe = frags
+    lens = torch.tensor([int(g.numel()) for g in genome], dtype=torch.int64, device=dev)
+    off = torch.cumsum(lens, 0) - lens
+    flat = torch.cat(list(genome))
+    r = torch.arange(first_index, first_index + n_reads, dtype=torch.int64, device=dev)
+    base = splitmix64(r * 0x100000 + _s64(seed * 0x2545F4914F6CDD1D) + 11)
+    k = _u(splitmix64(base + 1), 48) % int(fc.numel())
+    strand = _u(splitmix64(base + 2), 1)
+    a, e = off[fc[k]] + fa[k], off[fc[k]] + fe[k]
+    flen = e - a
+    j = torch.arange(L, dtype=torch.int64, device=dev)
+    inside = j[None, :] < flen[:, None]
+    idx = torch.where(strand[:, None] == 0, a[:, None] + j[None, :], e[:, None] - 1 - j[None, :])
+    idx = torch.where(inside, idx, torch.zeros_like(idx))
+    seq = flat[idx]
+    seq = torch.where(strand[:, None] == 1, _COMP.to(dev)[seq.long()], seq)
+    hb = splitmix64(base[:, None] * 0x3 + j[None, :] + 0x1000)
+    keep = (_u(hb, 20).double() / (1 << 20)) >= conv
+    seq = torch.where((seq == 67) & ~keep, torch.full_like(seq, 84), seq)
+    ad = torch.full((L + len(adapter) + 1,), 65, dtype=torch.uint8, device=dev)
+    ad[:len(adapter)] = torch.tensor(list(adapter), dtype=torch.uint8, device=dev)
+    tail = ad[(j[None, :] - flen[:, None]).clamp(min=0, max=L + len(adapter))]
+    seq = torch.where(inside, seq, tail)
+    nsub = _u(splitmix64(base + 3), 32) % (nsub_max + 1)
+    for s_ in range(nsub_max):
+        hs = splitmix64(base + 0x40 + s_)
+        pp = _u(hs, 32) % L
+        nb = _ACGT.to(dev)[_u(splitmix64(hs), 2)]
+        rows = (nsub > s_).nonzero().squeeze(1)
+        seq[rows, pp[rows]] = nb[rows]
+    return seq
+
+
 # ---------------------------------------------------------------------------------------------
 # file writers (numpy; used to feed the reference binary and the bsmap CLI)
 # ---------------------------------------------------------------------------------------------

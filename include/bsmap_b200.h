@@ -160,10 +160,31 @@ int bsx_map_pe(bsx_mapper *m, uint32_t n, const char *seqs_a, const uint16_t *le
                const char *seqs_b, const uint16_t *lens_b, uint32_t first_index,
                bsx_pair_rec *out, bsx_rec *out_a, bsx_rec *out_b, uint16_t *counts_a, uint16_t *counts_b);
 
+/* Packed read input: the same calls with 2-bit bases + a 1-bit valid mask instead of ASCII -- 40 bytes per 100-nt read
+ * slot instead of 104, for callers whose host->device link is the limit (eight GPUs fed from one host).  What the
+ * reference's ConvertBinaySeq (align.cpp:90-162) derives from the text is derived here on the host, once.
+ * Slot layout (bsx_packed_stride(stride) bytes, `stride` = the mapper's ASCII slot size): ceil(stride/4) bytes of bases,
+ * four per byte, first base in bits 7:6, codes A0 C1 G2 T3, 0 for anything else; then ceil(stride/8) bytes of mask,
+ * eight bases per byte, first base in bit 7, set for ACGT/acgt; zero padded to a multiple of 4.
+ * Exactness: identical records to the ASCII entry points, except that letter case is lost -- with adapter trimming
+ * (-A / -D), whose comparison is case sensitive in the reference (align.cpp:376), reads holding lower-case bases must
+ * go through the ASCII call; bsx_pack_reads reports how many such bases it met.  Adapters and the digestion site
+ * must be upper-case ACGT for the packed calls (BSX_ERR_UNSUPPORTED otherwise). */
+size_t bsx_packed_stride(uint32_t stride);
+int bsx_pack_reads(uint32_t n, const char *seqs, uint32_t stride, const uint16_t *lens, uint8_t *packed,
+                   uint64_t *n_lowercase, int threads);
+int bsx_map_se_packed(bsx_mapper *m, uint32_t n, const uint8_t *packed, const uint16_t *lens,
+                      uint32_t first_index, int readset, bsx_rec *out, uint16_t *counts);
+int bsx_map_pe_packed(bsx_mapper *m, uint32_t n, const uint8_t *packed_a, const uint16_t *lens_a,
+                      const uint8_t *packed_b, const uint16_t *lens_b, uint32_t first_index,
+                      bsx_pair_rec *out, bsx_rec *out_a, bsx_rec *out_b, uint16_t *counts_a, uint16_t *counts_b);
+
 /* Staged form (inputs resident in HBM; used for kernel-only timing and by pipelined callers).
  * n <= max_batch.  `stream` is a cudaStream_t (NULL = the mapper's own stream). */
 int bsx_batch_upload(bsx_mapper *m, uint32_t n, const char *seqs_a, const uint16_t *lens_a,
                      const char *seqs_b, const uint16_t *lens_b, void *stream);
+int bsx_batch_upload_packed(bsx_mapper *m, uint32_t n, const uint8_t *packed_a, const uint16_t *lens_a,
+                            const uint8_t *packed_b, const uint16_t *lens_b, void *stream);
 int bsx_batch_run_se(bsx_mapper *m, uint32_t n, uint32_t first_index, int readset, void *stream);
 int bsx_batch_run_pe(bsx_mapper *m, uint32_t n, uint32_t first_index, void *stream);
 int bsx_batch_download_se(bsx_mapper *m, uint32_t n, bsx_rec *out, uint16_t *counts, void *stream);

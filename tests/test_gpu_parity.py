@@ -126,6 +126,47 @@ def test_read_stride_is_only_8_byte_aligned(name):
         B.Mapper(B.Index(B.make_params(), ["c"], [b"ACGT" * 100]), B.make_params(), max_batch=4, stride=100)
 
 
+@pytest.mark.parametrize("name", [c.name for c in CS.CASES])
+def test_packed_read_input_gives_the_same_records(name):
+    """bsx_map_se_packed / bsx_map_pe_packed (2-bit bases + valid mask, 40 bytes per 100-nt slot) == the ASCII entry
+    points on every parity case: adapters, RRBS remnants, N-rich and short reads, -n 1, paired ends.  Cases whose reads
+    hold lower-case bases while adapters are trimmed are the documented exception (the reference compares case-sensitively)."""
+    case = CS.BY_NAME[name]
+    d = case.data()
+    p = B.make_params(**case.param_kwargs())
+    ix = B.Index(p, d["gnames"], d["gseqs"])
+    mp = B.Mapper(ix, p, max_batch=1024, stride=152)
+    bufs = [B.pack_reads(R.clip(case, d[k]), stride=152) for k in (("seqs", "seqs_b") if case.paired else ("seqs",))]
+    packed = [B.pack_reads_2bit(b, l) for b, l in bufs]
+    assert packed[0][0].shape[1] == 60      # 38 + 19 bytes rounded up to a multiple of 4
+    lower = sum(x[1] for x in packed)
+    if lower and p.n_adapter:
+        mp.close(); ix.close()
+        pytest.skip(f"{lower} lower-case bases with adapter trimming: the ASCII entry point is the exact one")
+    if not case.paired:
+        a = mp.map_se(*bufs[0])
+        b = mp.map_se_packed(packed[0][0], bufs[0][1])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    else:
+        a = mp.map_pe(bufs[0][0], bufs[0][1], bufs[1][0], bufs[1][1])
+        b = mp.map_pe_packed(packed[0][0], bufs[0][1], packed[1][0], bufs[1][1])
+        for nm, x, y in zip(("pairs", "recs_a", "recs_b", "counts_a", "counts_b"), a, b):
+            bad = np.nonzero(x != y)[0]
+            assert bad.size == 0, f"{nm}: {bad.size} differ; first idx {bad[0]}: ascii {x[bad[0]]} packed {y[bad[0]]}"
+    mp.close(); ix.close()
+
+
+def test_packed_input_refuses_what_it_cannot_compare():
+    p = B.make_params(A=["AGATCGGAAGAGCNNN"])
+    ix = B.Index(p, ["c"], [b"ACGTTGCA" * 200])
+    mp = B.Mapper(ix, p, max_batch=8, stride=64)
+    buf, lens = B.pack_reads([b"ACGTTGCA" * 6], stride=64)
+    pk, _ = B.pack_reads_2bit(buf, lens)
+    with pytest.raises(B.BsxError, match="upper-case ACGT adapters"):
+        mp.map_se_packed(pk, lens)
+    mp.close(); ix.close()
+
+
 def _rec_diff(name, got, exp, reads=None):
     for f in exp.dtype.names:
         bad = np.nonzero(got[f] != exp[f])[0]
@@ -351,6 +392,32 @@ def test_cli_writes_the_reference_files(name, tmp_path):
         got_un = open(o2, "rb").read()
         assert got_un == exp_un, R.first_diff(got_un, exp_un)
     assert "Total number of aligned reads" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["se_cfg1", "pe_sam", "rrbs_se_A", "se_cfg2_bsp"])
+def test_cli_maps_on_several_devices_in_input_order(name, tmp_path):
+    """`bsmap -g`: one mapper thread per listed device, each with its own replica of the index (cudaMemcpyPeer), small
+    batches dealt to whichever is free, text written in input order -> the same bytes as the one-device run and the
+    reference.  On a one-GPU box the list names device 0 three times (three replicas, three mapper threads); with more
+    devices visible it is every device."""
+    import subprocess
+    case = CS.BY_NAME[name]
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    o = str(tmp_path / ("out." + case.out_ext))
+    o2 = str(tmp_path / "out_unpair.bsp") if (case.paired and case.out_ext != "sam") else None
+    n = BL.load().bsx_device_count()
+    devs = ",".join(str(i) for i in range(n)) if n > 1 else "0,0,0"
+    r = subprocess.run([exe] + case.cli(a, b, fa, o, o2) + ["-p", "4", "-g", devs], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, BSX_CLI_BATCH="257", BSX_CLI_TIMING="1", BSX_CLI_WAIT_DEVICES="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    exp_main, exp_un = R.golden_load(case)
+    got = open(o, "rb").read()
+    assert got == exp_main, R.first_diff(got, exp_main)
+    if o2:
+        assert open(o2, "rb").read() == exp_un
+    used = [ln for ln in r.stderr.splitlines() if "[bsx timing] device" in ln and " 0 reads" not in ln]
+    assert len(used) >= 2, r.stderr[-1500:]     # more than one mapper thread took batches
 
 
 def test_cli_option_grammar(tmp_path):

@@ -81,3 +81,20 @@ def test_formatter_reproduces_reference_text(L, case):
         assert head + txt == exp_main, R.first_diff(head + txt, exp_main)
         assert un == exp_un, R.first_diff(un, exp_un)
         assert st == got["n_aligned"]
+
+
+def test_pack_reads_2bit_layout():
+    """bsx_pack_reads: four bases per byte (first in bits 7:6, A0 C1 G2 T3, 0 otherwise), then one valid bit per base"""
+    import bsmap_b200 as B
+    reads = [b"ACGTNacgtn.X", b"T" * 37, b"", b"GATTACA" * 14]
+    buf, lens = B.pack_reads(reads, stride=104)
+    pk, low = B.pack_reads_2bit(buf, lens, threads=2)
+    assert pk.shape == (4, 40) and low == 4
+    code = {65: 0, 67: 1, 71: 2, 84: 3, 97: 0, 99: 1, 103: 2, 116: 3}
+    for r, rd in enumerate(reads):
+        for i, ch in enumerate(rd[:104]):
+            got = (pk[r, i >> 2] >> (6 - 2 * (i & 3))) & 3
+            valid = (pk[r, 26 + (i >> 3)] >> (7 - (i & 7))) & 1
+            assert valid == (ch in code) and got == code.get(ch, 0), (r, i, ch)
+        tail = np.unpackbits(pk[r, 26:39])[len(rd):]
+        assert not tail.any()
