@@ -105,8 +105,15 @@ __device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
 
 // Asynchronous 16-byte copy global -> shared (LDGSTS, bypasses L1 and the register file): the warp requests the heads
 // of all lists of a group back to back and waits once, instead of one DRAM round trip per list.
+#ifndef BSX_STAGE_64B
+#define BSX_STAGE_64B 1         // list heads and tails: fetch 64-byte granules from HBM, not 128-byte lines
+#endif
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+#if BSX_STAGE_64B
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -338,7 +345,8 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
     uint32_t strand = 0, loc = anchor[0], chr = 0;
     if (pass) {
         const uint32_t idx = idx0 + lane;
-        const uint32_t entry = __ldg(A.pos + idx);
+        uint32_t entry;                                                   // a random 4-byte read: 64-byte HBM fetch
+        asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(entry) : "l"(A.pos + idx));
         if (!BSX_RRBS(A)) { strand = idx >= md; loc = entry - p; }           // h = -profile.a + i - seed_start_array
         else { chr = __ldg(A.tag + idx) & 0xffffu; strand = chr & 1u; loc = entry - p + anchor[chr >> 1]; }
     }

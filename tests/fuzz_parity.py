@@ -89,6 +89,12 @@ def one_round(rng, k):
             bad = "SE per-level counts differ"
         if bad is None and mp.stats()["candidates"] != int(ostats[0]):
             bad = f"candidate counter {mp.stats()['candidates']} != oracle {int(ostats[0])}"
+        if bad is None:                                       # the packed entry point on the same batch, where it is exact
+            pk, low = B.pack_reads_2bit(buf, lens_)
+            if not (low and "A" in kw):
+                precs, pcnt = mp.map_se_packed(pk, lens_)
+                if not (np.array_equal(precs, recs) and np.array_equal(pcnt, counts)):
+                    bad = "packed read input gives different records"
     else:
         sim = synth.simulate_pairs(g, n, L, seed=int(rng.integers(1, 1000)), frag_min=int(rng.choice([40, 150])), frag_max=450, subs="cfg2")
         ra = mutate_reads(rng, [bytes(r) for r in sim["seq1"].numpy()], L, 0.1 if "A" in kw else 0.0, 0.05)
