@@ -164,7 +164,7 @@ class Index:
     def download(self, what: str) -> np.ndarray:
         i = self.info
         which = {"refcat": (0, i.n_words), "crefcat": (1, i.n_words), "anchor": (2, i.n_seq + 1),
-                 "tab": (3, 2 * i.n_keys + 1), "pos": (4, i.n_entries), "tag": (5, i.n_entries),
+                 "tab": (3, i.n_tab), "pos": (4, i.n_entries), "tag": (5, i.n_entries),
                  "ctx": (6, 2 * i.n_entries), "ctx2": (7, 2 * i.n_entries)}[what]
         out = np.empty(int(which[1]), dtype=np.uint32)
         check(load().bsx_index_download(self.h, which[0], out.ctypes.data, out.nbytes))

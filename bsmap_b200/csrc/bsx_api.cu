@@ -206,6 +206,7 @@ extern "C" int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info) {
     if (!ix || !info) return BSX_ERR_ARG;
     info->n_words = ix->n_words; info->n_keys = ix->n_keys; info->n_entries = ix->n_entries;
     info->n_seq = ix->n_seq; info->device = ix->device; info->build_seconds = ix->build_seconds;
+    info->n_tab = ix->ref_only ? 0 : bsx_tab_len(ix);
     return BSX_OK;
 }
 extern "C" const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k) { return (ix && k < ix->n_seq) ? ix->names[k].c_str() : ""; }
@@ -224,7 +225,7 @@ extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size
         case 0: src = ix->d_refcat; have = ix->n_words * 4; break;
         case 1: src = ix->d_crefcat; have = ix->n_words * 4; break;
         case 2: src = ix->d_seqinfo; have = ((size_t)ix->n_seq + 1) * 4; break;
-        case 3: src = ix->d_tab; have = (2 * ix->n_keys + 1) * 4; break;
+        case 3: src = ix->d_tab; have = bsx_tab_len(ix) * 4; break;
         case 4: src = ix->d_pos; have = ix->n_entries * 4; break;
         case 5: src = ix->d_tag; have = ix->d_tag ? ix->n_entries * 4 : 0; break;
         case 6: src = ix->d_ctx; have = ix->d_ctx ? ix->n_entries * 8 : 0; break;
@@ -240,7 +241,7 @@ extern "C" int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t
     if (!ix || cap < 7) return 0;
     ptrs[0] = ix->d_refcat; bytes[0] = ix->n_words * 4;
     ptrs[1] = ix->d_crefcat; bytes[1] = ix->n_words * 4;
-    ptrs[2] = ix->d_tab; bytes[2] = (2 * ix->n_keys + 1) * 4;
+    ptrs[2] = ix->d_tab; bytes[2] = bsx_tab_len(ix) * 4;
     ptrs[3] = ix->d_pos; bytes[3] = ix->n_entries * 4;
     ptrs[4] = ix->d_tag; bytes[4] = ix->d_tag ? ix->n_entries * 4 : 0;
     ptrs[5] = ix->d_ctx; bytes[5] = ix->d_ctx ? ix->n_entries * 8 : 0;
@@ -473,6 +474,7 @@ static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, 
     a.randseed = p->randseed; a.max_ns = p->max_ns; a.max_readlen = p->max_readlen; a.n_adapter = p->n_adapter;
     a.site_len = (int)strnlen(p->digest_site, sizeof p->digest_site); a.digest_pos = p->digest_pos;
     a.seed_bits = (p->seed_size == 16) ? 0xffffffffu : ((1u << (2 * p->seed_size)) - 1);
+    a.rrbs_groups = bsx_rrbs_groups(p->seed_size);
     a.plan_cap = m->plan_cap; a.nslot = m->nslot;
     bsx_map_args_derive(a);
     for (int i = 0; i < p->n_adapter; i++) { a.adapter_len[i] = (int)strnlen(p->adapter[i], 63); memcpy(a.adapter[i], p->adapter[i], 64); }

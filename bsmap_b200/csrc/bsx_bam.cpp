@@ -12,11 +12,19 @@
 //     windows after the first one a read overlaps -- a 0.1.7 trait -- and chunks merged when they share a block).
 // Decompressed, the BAM equals samtools' output byte for byte; the .bai holds the same bins, chunks and linear index
 // as `samtools index` computes for the file (tests/test_bam_output_cpu.py checks both against oracle/_ref/samtools).
+//
+// Memory is bounded the way `samtools sort` bounds it: the SAM text is taken in chunks (BSX_BAM_CHUNK_MB of text, 1 GiB
+// by default); a file that fits one chunk is sorted in memory, a larger one leaves one sorted run per chunk on disk
+// (<out>.runNNNN.tmp) and the runs are merged -- ties go to the earlier chunk, i.e. input order, exactly bam_sort.c's
+// heap rule.  Either way the sorted records stream through a window of 1 024 BGZF blocks that is deflated on all host
+// threads and written as soon as it is full, and the index is built behind it; nothing holds the whole BAM.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <queue>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -160,6 +168,119 @@ bool bgzf_block(const unsigned char *in, size_t n, std::string &out) {
     return true;
 }
 
+// what the index needs to know about a record, and where its bytes are
+struct Meta { uint64_t key; uint32_t len; int32_t tid, pos, end; uint16_t bin; uint16_t pad; };
+
+// a sorted run on disk: Meta, then `len` bytes of BAM record, repeated
+struct RunReader {
+    FILE *f = nullptr; std::vector<char> rec; Meta m{}; bool live = false;
+    bool open(const std::string &path) { f = fopen(path.c_str(), "rb"); if (f) setvbuf(f, nullptr, _IOFBF, 4 << 20); return f != nullptr; }
+    bool advance() {
+        live = fread(&m, sizeof m, 1, f) == 1;
+        if (live) { rec.resize(m.len); live = fread(rec.data(), 1, m.len, f) == m.len; }
+        return live;
+    }
+    void close() { if (f) fclose(f); f = nullptr; }
+};
+
+// BGZF writer + bam_index_core behind it.  Records arrive in sorted order; raw bytes collect in a window that is cut
+// into 64 KiB blocks (bgzf.c's blocking: records flow through block boundaries), deflated in parallel and written.
+struct BamSink {
+    static const size_t BLK = 65536;
+    size_t WINDOW = 1024;                             // blocks per flush (BSX_BAM_WINDOW_BLOCKS: tests shrink it)
+    int threads; FILE *fo = nullptr;
+    std::string win;                                  // raw bytes not yet written, starting at raw offset `flushed`
+    uint64_t flushed = 0, total = 0, file_pos = 0;    // raw bytes written / appended so far; compressed bytes written
+    std::vector<uint64_t> blk_in_start, blk_file_start;   // per written block (sentinel at the end)
+    bool fail = false;
+    // index state (bam_index.c:133-190)
+    struct Chunk { uint64_t u, v; };
+    std::vector<std::map<uint32_t, std::vector<Chunk>>> bins;
+    std::vector<std::vector<uint64_t>> lidx; std::vector<int32_t> lidx_n;
+    uint32_t last_bin = 0xffffffffu, save_bin = 0xffffffffu; int32_t last_tid = -2 /* 0xffffffff in the source */, save_tid = -2;
+    bool first = true, stopped = false, have_off = false;
+    uint64_t save_off = 0, last_off = 0;
+    struct Pending { Meta m; uint64_t at, next; };
+    std::deque<Pending> pend;                         // records whose end lies in a block that is not written yet
+
+    BamSink(int t, size_t nref) : threads(t), bins(nref), lidx(nref), lidx_n(nref, 0) {
+        if (const char *e = getenv("BSX_BAM_WINDOW_BLOCKS")) { const long w = atol(e); if (w > 0) WINDOW = (size_t)w; }
+        blk_in_start.push_back(0); blk_file_start.push_back(0); win.reserve((WINDOW + 2) * BLK);
+    }
+    void append(const char *p, size_t n) { win.append(p, n); total += n; }
+    void add_record(const Meta &m, const char *bytes) {
+        pend.push_back(Pending{m, total, total + m.len});
+        append(bytes, m.len);
+        if (win.size() >= WINDOW * BLK) flush(false);
+    }
+    // reader-side tell() of raw offset x: the offset of a record start as the *reader* sees it (start of the next block
+    // when the previous one is exhausted), which is what bam_index_core records
+    uint64_t rtell(uint64_t x) const {
+        const size_t nblk = blk_in_start.size() - 1;
+        const size_t k = (size_t)(std::upper_bound(blk_in_start.begin(), blk_in_start.end(), x) - blk_in_start.begin()) - 1;
+        if (k >= nblk) return blk_file_start[nblk] << 16;
+        return blk_file_start[k] << 16 | (x - blk_in_start[k]);
+    }
+    void index_ready(bool final) {
+        while (!pend.empty() && !stopped) {
+            const Pending &q = pend.front();
+            if (!final && q.next >= flushed) break;                   // its end is in a block still in the window
+            if (!have_off) { save_off = last_off = rtell(q.at); have_off = true; }
+            const Meta &r = q.m;
+            if (first || last_tid != r.tid) { last_tid = r.tid; last_bin = 0xffffffffu; first = false; }
+            if (r.tid >= 0 && r.bin < 4681) {                          // insert_offset2 (bam_index.c:89-104)
+                const int beg = r.pos >> 14, end = (int)(((uint32_t)r.end - 1) >> 14);
+                std::vector<uint64_t> &lx = lidx[r.tid];
+                if ((int)lx.size() < end + 1) lx.resize((size_t)end + 1, 0);
+                for (int i = beg + 1; i <= end; i++) if (lx[i] == 0) lx[i] = last_off;
+                lidx_n[r.tid] = end + 1;
+            }
+            if (r.bin != last_bin) {
+                if (save_bin != 0xffffffffu) bins[save_tid][save_bin].push_back(Chunk{save_off, last_off});
+                save_off = last_off; save_bin = last_bin = r.bin; save_tid = r.tid;
+                if (save_tid < 0) { stopped = true; break; }
+            }
+            last_off = rtell(q.next);
+            pend.pop_front();
+        }
+        if (stopped) pend.clear();
+    }
+    // deflate and write every full block of the window (everything when final)
+    void flush(bool final) {
+        size_t nblk = final ? (win.size() + BLK - 1) / BLK : win.size() / BLK;
+        if (nblk && !fail) {
+            std::vector<std::string> comp(nblk); std::vector<char> okv(nblk, 1);
+            bsx_parallel(threads, nblk, [&](int, size_t b, size_t e) {
+                for (size_t k = b; k < e; k++) okv[k] = bgzf_block((const unsigned char *)win.data() + k * BLK, std::min(BLK, win.size() - k * BLK), comp[k]) ? 1 : 0;
+            });
+            size_t good = 0; while (good < nblk && okv[good]) good++;
+            size_t used = 0;
+            for (size_t k = 0; k < good; k++) {
+                const size_t len = std::min(BLK, win.size() - k * BLK);
+                if (fwrite(comp[k].data(), 1, comp[k].size(), fo) != comp[k].size()) fail = true;
+                file_pos += comp[k].size(); used += len;
+                blk_in_start.push_back(flushed + used); blk_file_start.push_back(file_pos);
+            }
+            if (good < nblk) {
+                // a block that does not fit is redone the way bgzf.c does it (1 KiB less input at a time), which shifts
+                // every later boundary of the window -- never seen on BAM data
+                const size_t stop = final ? win.size() : nblk * BLK;
+                while (used < stop && !fail) {
+                    size_t len = std::min(BLK, win.size() - used); std::string c;
+                    if (!final && used + len > stop) break;
+                    while (!bgzf_block((const unsigned char *)win.data() + used, len, c)) { if (len <= 1024) { fail = true; break; } len -= 1024; }
+                    if (fail) break;
+                    if (fwrite(c.data(), 1, c.size(), fo) != c.size()) fail = true;
+                    file_pos += c.size(); used += len;
+                    blk_in_start.push_back(flushed + used); blk_file_start.push_back(file_pos);
+                }
+            }
+            win.erase(0, used); flushed += used;
+        }
+        index_ready(final);
+    }
+};
+
 }  // namespace
 
 extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path, int threads) {
@@ -193,128 +314,126 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
     std::unordered_map<std::string, int32_t> tids;
     for (size_t k = 0; k < ref_names.size(); k++) tids.emplace(ref_names[k], (int32_t)k);   // first definition wins, like the hash in bam_aux.c
 
-    // records: byte ranges cut at line starts, one per thread
+    // ---- sorted runs: the text in chunks cut at line starts
+    size_t chunk_bytes = (size_t)1 << 30;
+    if (const char *e = getenv("BSX_BAM_CHUNK_MB")) { const double mb = atof(e); if (mb > 0) chunk_bytes = (size_t)(mb * 1048576.0); }
+    if (chunk_bytes < 4096) chunk_bytes = 4096;
     std::vector<std::string> enc((size_t)threads); std::vector<std::vector<Rec>> recs((size_t)threads);
-    const int tn = (n - header_end) < ((size_t)1 << 20) ? 1 : threads;
-    bsx_parallel(tn, (size_t)tn, [&](int t, size_t, size_t) {
-        size_t b = header_end + (n - header_end) * (size_t)t / tn, e = header_end + (n - header_end) * (size_t)(t + 1) / tn;
-        if (t > 0) { const void *x = memchr(p + b - 1, '\n', n - (b - 1)); b = x ? (size_t)((const char *)x - p) + 1 : n; }
-        if (t + 1 < tn) { const void *x = memchr(p + e - 1, '\n', n - (e - 1)); e = x ? (size_t)((const char *)x - p) + 1 : n; }
-        enc[t].reserve((e > b ? e - b : 0) + 1024);
-        while (b < e) {
-            const void *x = memchr(p + b, '\n', n - b);
-            const size_t le = x ? (size_t)((const char *)x - p) : n;
-            Rec r;
-            if (le > b && encode(p + b, p + le, tids, enc[t], r)) recs[t].push_back(r);
-            b = le + 1;
-        }
-    });
-    // stable sort by (tid, pos + 1).  (key, thread, index) is a total order that equals input order on equal keys, so
-    // the threads sort slices with a plain sort and the slices are merged pairwise, level by level, in parallel.
     struct Ord { uint64_t key; uint32_t t, i; };
-    auto before = [](const Ord &a, const Ord &b) { return a.key != b.key ? a.key < b.key : (a.t != b.t ? a.t < b.t : a.i < b.i); };
     std::vector<Ord> ord;
-    { size_t tot = 0; for (auto &v : recs) tot += v.size(); ord.reserve(tot); }
-    for (int t = 0; t < threads; t++) for (uint32_t i = 0; i < recs[t].size(); i++) ord.push_back(Ord{recs[t][i].key, (uint32_t)t, i});
+    std::vector<std::string> run_paths;
+    bool io_fail = false;
+    auto cleanup = [&]() { for (const std::string &r : run_paths) remove(r.c_str()); if (n) munmap((void *)p, n); close(fd); };
+    size_t cb = header_end;
+    bool in_memory = false;
+    while (cb < n || (cb == header_end && !in_memory && run_paths.empty())) {
+        size_t ce = std::min(n, cb + chunk_bytes);
+        if (ce < n) { const void *x = memchr(p + ce - 1, '\n', n - (ce - 1)); ce = x ? (size_t)((const char *)x - p) + 1 : n; }
+        // records: byte ranges cut at line starts, one per thread
+        const int tn = (ce - cb) < ((size_t)1 << 20) ? 1 : threads;
+        for (auto &v : enc) v.clear();
+        for (auto &v : recs) v.clear();
+        bsx_parallel(tn, (size_t)tn, [&](int t, size_t, size_t) {
+            size_t b = cb + (ce - cb) * (size_t)t / tn, e = cb + (ce - cb) * (size_t)(t + 1) / tn;
+            if (t > 0) { const void *x = memchr(p + b - 1, '\n', ce - (b - 1)); b = x ? (size_t)((const char *)x - p) + 1 : ce; }
+            if (t + 1 < tn) { const void *x = memchr(p + e - 1, '\n', ce - (e - 1)); e = x ? (size_t)((const char *)x - p) + 1 : ce; }
+            enc[t].reserve((e > b ? e - b : 0) + 1024);
+            while (b < e) {
+                const void *x = memchr(p + b, '\n', ce - b);
+                const size_t le = x ? (size_t)((const char *)x - p) : ce;
+                Rec r;
+                if (le > b && encode(p + b, p + le, tids, enc[t], r)) recs[t].push_back(r);
+                b = le + 1;
+            }
+        });
+        // stable sort by (tid, pos + 1).  (key, thread, index) is a total order that equals input order on equal keys, so
+        // the threads sort slices with a plain sort and the slices are merged pairwise, level by level, in parallel.
+        auto before = [](const Ord &a, const Ord &b) { return a.key != b.key ? a.key < b.key : (a.t != b.t ? a.t < b.t : a.i < b.i); };
+        ord.clear();
+        { size_t tot = 0; for (auto &v : recs) tot += v.size(); ord.reserve(tot); }
+        for (int t = 0; t < threads; t++) for (uint32_t i = 0; i < recs[t].size(); i++) ord.push_back(Ord{recs[t][i].key, (uint32_t)t, i});
+        {
+            const size_t N = ord.size();
+            const int S = N < ((size_t)1 << 16) ? 1 : threads;
+            std::vector<size_t> cut((size_t)S + 1);
+            for (int k = 0; k <= S; k++) cut[k] = N * (size_t)k / S;
+            bsx_parallel(S, (size_t)S, [&](int k, size_t, size_t) { std::sort(ord.begin() + cut[k], ord.begin() + cut[k + 1], before); });
+            for (int w = 1; w < S; w *= 2) {
+                const int pairs = (S + 2 * w - 1) / (2 * w);
+                bsx_parallel(pairs, (size_t)pairs, [&](int q, size_t, size_t) {
+                    const int lo = q * 2 * w, mid = std::min(lo + w, S), hi = std::min(lo + 2 * w, S);
+                    if (mid < hi) std::inplace_merge(ord.begin() + cut[lo], ord.begin() + cut[mid], ord.begin() + cut[hi], before);
+                });
+            }
+        }
+        if (cb == header_end && ce >= n) { in_memory = true; break; }    // the whole file is one chunk: no run files
+        char name[32]; snprintf(name, sizeof name, ".run%04zu.tmp", run_paths.size());
+        run_paths.push_back(std::string(bam_path) + name);
+        FILE *fr = fopen(run_paths.back().c_str(), "wb");
+        if (!fr) { cleanup(); bsx_set_error("cannot write %s", run_paths.back().c_str()); return BSX_ERR_IO; }
+        setvbuf(fr, nullptr, _IOFBF, 4 << 20);
+        for (const Ord &o : ord) {
+            const Rec &r = recs[o.t][o.i];
+            const Meta m{r.key, r.len, r.tid, r.pos, r.end, r.bin, 0};
+            if (fwrite(&m, sizeof m, 1, fr) != 1 || fwrite(enc[o.t].data() + r.off, 1, r.len, fr) != r.len) { io_fail = true; break; }
+        }
+        if (fclose(fr) != 0) io_fail = true;
+        if (io_fail) { cleanup(); bsx_set_error("write to %s failed", run_paths.back().c_str()); return BSX_ERR_IO; }
+        cb = ce;
+    }
+    if (!in_memory) {                                                     // the runs are on disk: give the chunk's memory back
+        for (auto &v : enc) std::string().swap(v);
+        for (auto &v : recs) std::vector<Rec>().swap(v);
+        std::vector<Ord>().swap(ord);
+    }
+
+    // ---- the BAM: header, then the sorted records through the BGZF window
+    BamSink sink(threads, ref_names.size());
+    sink.fo = fopen(bam_path, "wb");
+    if (!sink.fo) { cleanup(); bsx_set_error("cannot write %s", bam_path); return BSX_ERR_IO; }
     {
-        const size_t N = ord.size();
-        const int S = N < ((size_t)1 << 16) ? 1 : threads;
-        std::vector<size_t> cut((size_t)S + 1);
-        for (int k = 0; k <= S; k++) cut[k] = N * (size_t)k / S;
-        bsx_parallel(S, (size_t)S, [&](int k, size_t, size_t) { std::sort(ord.begin() + cut[k], ord.begin() + cut[k + 1], before); });
-        for (int w = 1; w < S; w *= 2) {
-            const int pairs = (S + 2 * w - 1) / (2 * w);
-            bsx_parallel(pairs, (size_t)pairs, [&](int q, size_t, size_t) {
-                const int lo = q * 2 * w, mid = std::min(lo + w, S), hi = std::min(lo + 2 * w, S);
-                if (mid < hi) std::inplace_merge(ord.begin() + cut[lo], ord.begin() + cut[mid], ord.begin() + cut[hi], before);
-            });
-        }
+        std::string hd;
+        hd.append("BAM\1", 4);
+        put<int32_t>(hd, (int32_t)header_end); hd.append(p, header_end);
+        put<int32_t>(hd, (int32_t)ref_names.size());
+        for (size_t k = 0; k < ref_names.size(); k++) { put<int32_t>(hd, (int32_t)ref_names[k].size() + 1); hd.append(ref_names[k]); hd.push_back('\0'); put<int32_t>(hd, ref_lens[k]); }
+        sink.append(hd.data(), hd.size());
     }
-
-    // the uncompressed stream: header, then records (copied to their final offsets in parallel)
-    std::string raw;
-    raw.append("BAM\1", 4);
-    put<int32_t>(raw, (int32_t)header_end); raw.append(p, header_end);
-    put<int32_t>(raw, (int32_t)ref_names.size());
-    for (size_t k = 0; k < ref_names.size(); k++) { put<int32_t>(raw, (int32_t)ref_names[k].size() + 1); raw.append(ref_names[k]); raw.push_back('\0'); put<int32_t>(raw, ref_lens[k]); }
-    std::vector<uint64_t> at(ord.size() + 1);
-    { uint64_t off = raw.size(); for (size_t k = 0; k < ord.size(); k++) { at[k] = off; off += recs[ord[k].t][ord[k].i].len; } at[ord.size()] = off; raw.resize((size_t)off); }
-    bsx_parallel(threads, ord.size(), [&](int, size_t b, size_t e) {
-        for (size_t k = b; k < e; k++) { const Rec &r = recs[ord[k].t][ord[k].i]; memcpy(&raw[(size_t)at[k]], enc[ord[k].t].data() + r.off, r.len); }
-    });
-    if (n) munmap((void *)p, n);
-    close(fd);
-
-    // BGZF: 64 KiB of input per block, deflated in parallel; a block that does not fit is redone serially the way
-    // bgzf.c does (1 KiB less input at a time), which shifts every later boundary -- never seen on BAM data
-    const size_t BLK = 65536;
-    size_t nblk = (raw.size() + BLK - 1) / BLK;
-    std::vector<std::string> comp(nblk);
-    std::vector<size_t> blk_in_start(nblk + 1);
-    std::vector<char> okv(nblk, 1);
-    bsx_parallel(threads, nblk, [&](int, size_t b, size_t e) {
-        for (size_t k = b; k < e; k++) okv[k] = bgzf_block((const unsigned char *)raw.data() + k * BLK, std::min(BLK, raw.size() - k * BLK), comp[k]) ? 1 : 0;
-    });
-    bool regular = true; for (char c : okv) regular = regular && c;
-    if (regular) { for (size_t k = 0; k <= nblk; k++) blk_in_start[k] = std::min(k * BLK, raw.size()); }
-    else {
-        comp.clear(); blk_in_start.clear();
-        for (size_t pos = 0; pos < raw.size();) {
-            size_t len = std::min(BLK, raw.size() - pos); std::string c;
-            while (!bgzf_block((const unsigned char *)raw.data() + pos, len, c)) { if (len <= 1024) { bsx_set_error("BGZF: input reduction failed"); return BSX_ERR_IO; } len -= 1024; }
-            blk_in_start.push_back(pos); comp.push_back(c); pos += len;
+    if (in_memory) {
+        for (const Ord &o : ord) {
+            const Rec &r = recs[o.t][o.i];
+            sink.add_record(Meta{r.key, r.len, r.tid, r.pos, r.end, r.bin, 0}, enc[o.t].data() + r.off);
         }
-        blk_in_start.push_back(raw.size()); nblk = comp.size();
+    } else {
+        std::vector<RunReader> rd(run_paths.size());
+        typedef std::pair<uint64_t, size_t> HeapKey;                      // (key, run): ties go to the earlier chunk = input order
+        std::priority_queue<HeapKey, std::vector<HeapKey>, std::greater<HeapKey>> heap;
+        for (size_t k = 0; k < rd.size(); k++) {
+            if (!rd[k].open(run_paths[k])) { io_fail = true; break; }
+            if (rd[k].advance()) heap.push(HeapKey(rd[k].m.key, k));
+        }
+        while (!io_fail && !heap.empty()) {
+            const size_t k = heap.top().second; heap.pop();
+            sink.add_record(rd[k].m, rd[k].rec.data());
+            if (rd[k].advance()) heap.push(HeapKey(rd[k].m.key, k));
+        }
+        for (RunReader &r : rd) r.close();
     }
-    std::vector<uint64_t> blk_file_start(nblk + 1, 0);
-    for (size_t k = 0; k < nblk; k++) blk_file_start[k + 1] = blk_file_start[k] + comp[k].size();
+    sink.flush(true);
     std::string eof_block; bgzf_block((const unsigned char *)"", 0, eof_block);
-    FILE *fo = fopen(bam_path, "wb");
-    if (!fo) { bsx_set_error("cannot write %s", bam_path); return BSX_ERR_IO; }
-    for (const std::string &c : comp) fwrite(c.data(), 1, c.size(), fo);
-    fwrite(eof_block.data(), 1, eof_block.size(), fo);
-    if (fclose(fo) != 0) { bsx_set_error("write to %s failed", bam_path); return BSX_ERR_IO; }
+    if (fwrite(eof_block.data(), 1, eof_block.size(), sink.fo) != eof_block.size()) sink.fail = true;
+    if (fclose(sink.fo) != 0) sink.fail = true;
+    cleanup();
+    if (io_fail || sink.fail) { bsx_set_error("write to %s failed", bam_path); return BSX_ERR_IO; }
+    // the index loop ran into the end of the file: the reader has swallowed the empty EOF block too (bgzf_read), so its
+    // tell() is the file size
+    if (sink.save_tid >= 0 && sink.save_bin != 0xffffffffu && !sink.stopped)
+        sink.bins[sink.save_tid][sink.save_bin].push_back(BamSink::Chunk{sink.save_off, (sink.file_pos + eof_block.size()) << 16});
 
-    // ---- index (bam_index_core, bam_index.c:133-190)
-    struct Chunk { uint64_t u, v; };
     const size_t nref = ref_names.size();
-    std::vector<std::map<uint32_t, std::vector<Chunk>>> bins(nref);
-    std::vector<std::vector<uint64_t>> lidx(nref);
-    std::vector<int32_t> lidx_n(nref, 0);
-    {
-        uint32_t last_bin = 0xffffffffu, save_bin = 0xffffffffu; int32_t last_tid = -2 /* 0xffffffff in the source */, save_tid = -2;
-        bool first = true;
-        uint64_t save_off, last_off;
-        // reader-side tell(): the offset of a record start as the *reader* sees it (start of the next block when the
-        // previous one is exhausted), which is what bam_index_core records
-        auto rtell = [&](uint64_t x) -> uint64_t {
-            size_t k = (size_t)(std::upper_bound(blk_in_start.begin(), blk_in_start.end(), x) - blk_in_start.begin()) - 1;
-            if (k >= nblk) return blk_file_start[nblk] << 16;
-            return blk_file_start[k] << 16 | (x - blk_in_start[k]);
-        };
-        save_off = last_off = rtell(at.empty() ? raw.size() : at[0]);
-        for (size_t k = 0; k < ord.size(); k++) {
-            const Rec &r = recs[ord[k].t][ord[k].i];
-            if (first || last_tid != r.tid) { last_tid = r.tid; last_bin = 0xffffffffu; first = false; }
-            if (r.tid >= 0 && r.bin < 4681) {                          // insert_offset2 (bam_index.c:89-104)
-                const int beg = r.pos >> 14, end = (int)(((uint32_t)r.end - 1) >> 14);
-                std::vector<uint64_t> &lx = lidx[r.tid];
-                if ((int)lx.size() < end + 1) lx.resize((size_t)end + 1, 0);
-                for (int i = beg + 1; i <= end; i++) if (lx[i] == 0) lx[i] = last_off;
-                lidx_n[r.tid] = end + 1;
-            }
-            if (r.bin != last_bin) {
-                if (save_bin != 0xffffffffu) bins[save_tid][save_bin].push_back(Chunk{save_off, last_off});
-                save_off = last_off; save_bin = last_bin = r.bin; save_tid = r.tid;
-                if (save_tid < 0) break;
-            }
-            last_off = rtell(at[k + 1]);
-        }
-        // the loop ran into the end of the file: the reader has swallowed the empty EOF block too (bgzf_read), so its tell()
-        // is the file size
-        if (save_tid >= 0 && save_bin != 0xffffffffu)
-            bins[save_tid][save_bin].push_back(Chunk{save_off, (blk_file_start[nblk] + eof_block.size()) << 16});
-    }
+    std::vector<std::map<uint32_t, std::vector<BamSink::Chunk>>> &bins = sink.bins;
+    std::vector<std::vector<uint64_t>> &lidx = sink.lidx; std::vector<int32_t> &lidx_n = sink.lidx_n;
+    typedef BamSink::Chunk Chunk;
     const std::string bai_path = std::string(bam_path) + ".bai";
     FILE *fi = fopen(bai_path.c_str(), "wb");
     if (!fi) { bsx_set_error("cannot write %s", bai_path.c_str()); return BSX_ERR_IO; }

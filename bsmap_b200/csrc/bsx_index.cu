@@ -83,35 +83,41 @@ __global__ void seed_items_kernel(const uint32_t *__restrict__ refcat, const uin
     atomicAdd(&hist[2 * key + b.strand], 1u);
 }
 
-// RRBS: entries are enumerated on the host (find_CCGG order, dbseq.cpp:144-211,418-438); the device
-// computes their keys.  items = (key << 32) | entry index.
+// RRBS: entries are enumerated on the host; the device computes their keys.  items = (key << 32) | entry index.
+// The reference appends to a key's list segment by segment, sequence by sequence, plain entries before mirrored ones
+// (dbseq.cpp:418-438), and SnpAlign walks the whole list skipping every entry whose (segment, mirror) tag is not the
+// one the mode wants (align.cpp:187, 229).  Here the host enumerates group-major -- (segment, mirror), then sequence,
+// then site -- so the stable sort by key leaves every list partitioned into its groups, each in the reference's
+// order, and the table is a CSR over (key, group): a mode reads exactly the entries the reference would not skip.
 __global__ void rrbs_items_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ crefcat,
                                   const uint32_t *__restrict__ seqinfo, const uint32_t *__restrict__ loc,
                                   const uint32_t *__restrict__ tag, uint64_t n_items, int s, uint32_t seed_bits,
-                                  uint64_t *__restrict__ items, uint32_t *__restrict__ hist) {
+                                  uint32_t groups, uint64_t *__restrict__ items, uint32_t *__restrict__ hist) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_items) return;
-    uint32_t chr = tag[e] & 0xffffu;
+    const uint32_t t = tag[e], chr = t & 0xffffu;
     const uint32_t *m = ((chr & 1u) ? crefcat : refcat) + (seqinfo[chr >> 1] >> 4);
     uint32_t key = seed_key_at(m, loc[e], s, seed_bits);
     items[e] = ((uint64_t)key << 32) | e;
-    atomicAdd(&hist[2 * key], 1u);
+    atomicAdd(&hist[(uint64_t)key * groups + (2u * ((t >> 16) & 0xffu) + (t >> 24))], 1u);
 }
 
+// sorted order -> pos / tag, plus the inline context of every entry (the 16 bases before and the 16 after the seed on
+// the entry's strand), exactly as the WGBS table carries it
 __global__ void rrbs_gather_kernel(const uint32_t *__restrict__ order, const uint32_t *__restrict__ loc,
-                                   const uint32_t *__restrict__ tag, uint64_t n, uint32_t *__restrict__ out_loc,
-                                   uint32_t *__restrict__ out_tag) {
+                                   const uint32_t *__restrict__ tag, uint64_t n, const uint32_t *__restrict__ refcat,
+                                   const uint32_t *__restrict__ crefcat, const uint32_t *__restrict__ seqinfo, int seed_size,
+                                   uint32_t *__restrict__ out_loc, uint32_t *__restrict__ out_tag, uint2 *__restrict__ out_ctx) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     uint32_t src = order[e];
-    out_loc[e] = loc[src];
-    out_tag[e] = tag[src];
-}
-
-// RRBS tab has no rc split: tab[2k+1] := tab[2k+2]
-__global__ void rrbs_fix_tab_kernel(uint32_t *tab, uint64_t n_keys) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n_keys) tab[2 * k + 1] = tab[2 * k + 2];
+    const uint32_t l = loc[src], t = tag[src], chr = t & 0xffffu;
+    out_loc[e] = l;
+    out_tag[e] = t;
+    const uint32_t *m = (chr & 1u) ? crefcat : refcat;
+    const uint32_t c = seqinfo[chr >> 1] + l, bb = c - 16u, aa = c + (uint32_t)seed_size;
+    out_ctx[e] = make_uint2(__funnelshift_l(m[(bb >> 4) + 1], m[bb >> 4], (bb & 15u) * 2u),
+                            __funnelshift_l(m[(aa >> 4) + 1], m[aa >> 4], (aa & 15u) * 2u));
 }
 
 // ------------------------------------------------------------------------------------------ scan
@@ -396,13 +402,11 @@ int bsx_index_alloc_device(bsx_index *ix) {
     BSX_CUDA_CHECK(cudaSetDevice(ix->device));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_refcat, ix->n_words * 4));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_crefcat, ix->n_words * 4));
-    BSX_CUDA_CHECK(cudaMalloc(&ix->d_tab, (2 * ix->n_keys + 1) * 4));
+    BSX_CUDA_CHECK(cudaMalloc(&ix->d_tab, bsx_tab_len(ix) * 4));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_pos, (ix->n_entries + 64) * 4));
+    BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (ix->n_entries + 64) * sizeof(uint2)));
     if (ix->par.rrbs) BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, (ix->n_entries + 64) * 4));
-    else {
-        BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (ix->n_entries + 64) * sizeof(uint2)));
-        if (ix->par.max_snp_num >= BSX_WIDE_CTX_V) BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx2, (ix->n_entries + 64) * sizeof(uint2)));
-    }
+    else if (ix->par.max_snp_num >= BSX_WIDE_CTX_V) BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx2, (ix->n_entries + 64) * sizeof(uint2)));
     return upload_seqinfo(ix);
 }
 
@@ -508,14 +512,17 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
                     for (int i = 0; i < max_seg && seedloc >= 0; i++, seedloc -= s) cidx[(size_t)i * 2 * ix->n_seq + 2 * k + 1].push_back(tmp_offset - (uint32_t)seedloc);
                 }
         }
+        // group-major enumeration (see rrbs_items_kernel): the reference's order is j, chr, {plain, mirrored}
         for (int j = 0; j < max_seg; j++)
-            for (uint32_t chr = 0; chr < 2 * ix->n_seq; chr++) {
-                for (uint32_t v : cidx[(size_t)j * 2 * ix->n_seq + chr]) { rr_loc.push_back(v); rr_tag.push_back(chr | ((uint32_t)j << 16)); }
-                if (mirror) {
-                    const uint32_t tmp_offset = ix->rc_offset[chr >> 1] - s;
-                    for (uint32_t v : cidx[(size_t)j * 2 * ix->n_seq + (chr ^ 1)]) { rr_loc.push_back(tmp_offset - v); rr_tag.push_back(chr | ((uint32_t)j << 16) | 0x1000000u); }
+            for (int flag = 0; flag < (mirror ? 2 : 1); flag++)
+                for (uint32_t chr = 0; chr < 2 * ix->n_seq; chr++) {
+                    if (!flag) {
+                        for (uint32_t v : cidx[(size_t)j * 2 * ix->n_seq + chr]) { rr_loc.push_back(v); rr_tag.push_back(chr | ((uint32_t)j << 16)); }
+                    } else {
+                        const uint32_t tmp_offset = ix->rc_offset[chr >> 1] - s;
+                        for (uint32_t v : cidx[(size_t)j * 2 * ix->n_seq + (chr ^ 1)]) { rr_loc.push_back(tmp_offset - v); rr_tag.push_back(chr | ((uint32_t)j << 16) | 0x1000000u); }
+                    }
                 }
-            }
     }
     if (upload_seqinfo(ix)) return BSX_ERR_CUDA;
 
@@ -536,8 +543,8 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
     if (n_items >= (1ull << 32)) { bsx_set_error("seed table exceeds 2^32 entries"); return BSX_ERR_ARG; }
     ix->n_entries = n_items;
 
-    BSX_CUDA_CHECK(cudaMalloc(&ix->d_tab, (2 * ix->n_keys + 1) * 4));
-    BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_tab, 0, (2 * ix->n_keys + 1) * 4, st));
+    BSX_CUDA_CHECK(cudaMalloc(&ix->d_tab, bsx_tab_len(ix) * 4));
+    BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_tab, 0, bsx_tab_len(ix) * 4, st));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_pos, (n_items + 64) * 4));
     BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_pos, 0, (n_items + 64) * 4, st));
 
@@ -563,11 +570,12 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
             BSX_CUDA_CHECK(cudaMalloc(&d_rt, n_items * 4));
             BSX_CUDA_CHECK(cudaMemcpyAsync(d_rl, rr_loc.data(), n_items * 4, cudaMemcpyHostToDevice, st));
             BSX_CUDA_CHECK(cudaMemcpyAsync(d_rt, rr_tag.data(), n_items * 4, cudaMemcpyHostToDevice, st));
-            rrbs_items_kernel<<<grid, 256, 0, st>>>(ix->d_refcat, ix->d_crefcat, ix->d_seqinfo, d_rl, d_rt, n_items, s, seed_bits, d_a, ix->d_tab);
+            rrbs_items_kernel<<<grid, 256, 0, st>>>(ix->d_refcat, ix->d_crefcat, ix->d_seqinfo, d_rl, d_rt, n_items, s, seed_bits,
+                                                    bsx_rrbs_groups(s), d_a, ix->d_tab);
             BSX_CUDA_CHECK(cudaGetLastError());
         }
         // histogram -> CSR offsets (in place; the last slot becomes the total)
-        int rc = exclusive_scan_u32(ix->d_tab, ix->d_tab, 2 * ix->n_keys + 1, st);
+        int rc = exclusive_scan_u32(ix->d_tab, ix->d_tab, bsx_tab_len(ix), st);
         if (rc) return rc;
         int key_bits = 1; while ((1ull << key_bits) < ix->n_keys) key_bits++;
         if (!p.rrbs) {
@@ -586,17 +594,20 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
             rc = radix_sort_items(d_a, d_b, n_items, key_bits, d_order, st);
             if (rc) return rc;
             BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, (n_items + 64) * 4));
-            rrbs_gather_kernel<<<grid, 256, 0, st>>>(d_order, d_rl, d_rt, n_items, ix->d_pos, ix->d_tag);
-            rrbs_fix_tab_kernel<<<(unsigned)((ix->n_keys + 255) / 256), 256, 0, st>>>(ix->d_tab, ix->n_keys);
+            BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_tag, 0, (n_items + 64) * 4, st));
+            BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (n_items + 64) * sizeof(uint2)));
+            BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, (n_items + 64) * sizeof(uint2), st));
+            rrbs_gather_kernel<<<grid, 256, 0, st>>>(d_order, d_rl, d_rt, n_items, ix->d_refcat, ix->d_crefcat, ix->d_seqinfo, s,
+                                                     ix->d_pos, ix->d_tag, ix->d_ctx);
             BSX_CUDA_CHECK(cudaGetLastError());
             BSX_CUDA_CHECK(cudaStreamSynchronize(st));
             cudaFree(d_order); cudaFree(d_rl); cudaFree(d_rt);
         }
         cudaFree(d_a); cudaFree(d_b);
-    } else if (p.rrbs) {
-        BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, 64 * 4));
     } else {
+        if (p.rrbs) { BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, 64 * 4)); BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_tag, 0, 64 * 4, st)); }
         BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, 64 * sizeof(uint2)));
+        BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, 64 * sizeof(uint2), st));
     }
     cudaEventRecord(ev1, st);
     BSX_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -25,9 +25,9 @@ struct bsx_index {
     bool ref_only = false;             // packed strands only, no seed table (bsx_index_create_packed): cannot map
     // device arrays
     uint32_t *d_refcat = nullptr, *d_crefcat = nullptr;   // 2-bit packed strands, margins zeroed
-    uint32_t *d_tab = nullptr;      // 2*n_keys+1: [2k] list start, [2k+1] start of rc part, [2k+2] end
+    uint32_t *d_tab = nullptr;      // bsx_tab_len(): WGBS [2k] list start, [2k+1] start of rc part, [2k+2] end; RRBS CSR over (key, group)
     uint32_t *d_pos = nullptr;      // n_entries positions (ref_anchor + p), lists fwd-ascending then rc-ascending
-    uint2 *d_ctx = nullptr;         // WGBS: per entry the 16 reference bases before the seed (.x) and the 16 after it (.y)
+    uint2 *d_ctx = nullptr;         // per entry the 16 reference bases before the seed (.x) and the 16 after it (.y)
     uint2 *d_ctx2 = nullptr;        // WGBS, -v >= BSX_WIDE_CTX_V only: the next 16 bases outwards on either side
     uint32_t *d_tag = nullptr;      // RRBS: Hit.chr tag per entry
     uint32_t *d_seqinfo = nullptr;  // anchor[n_seq+1] | size[n_seq] | rc_offset[n_seq]
@@ -38,6 +38,13 @@ struct bsx_index {
     std::vector<std::vector<uint32_t>> sites;       // RRBS CCGG_sites (dbseq.cpp:158-163)
     std::vector<bsx_block> blocks;                  // WGBS: UnmaskRegion blocks, sorted (kept for bsx_index_save_packed)
 };
+
+// RRBS seed table: one CSR slot per (key, group), group = 2 * segment + mirrored (bsx_index.cu); dbseq.cpp:217 max_seedseg_num
+static inline uint32_t bsx_rrbs_groups(int seed_size) { return 2u * (uint32_t)((10 - 1) * 16 / seed_size); }
+// u32 entries of the table: WGBS [2k] list start, [2k+1] start of the rc half, [2k+2] end; RRBS [k * groups + g] group start
+static inline uint64_t bsx_tab_len(const bsx_index *ix) {
+    return ix->par.rrbs ? ix->n_keys * bsx_rrbs_groups(ix->par.seed_size) + 1 : 2 * ix->n_keys + 1;
+}
 
 struct bsx_mapper;
 

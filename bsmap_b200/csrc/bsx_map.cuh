@@ -9,7 +9,7 @@
 struct MapArgs {
     // RefSeq
     const uint32_t *refcat, *crefcat, *tab, *pos, *tag, *seqinfo;
-    const uint2 *ctx;             // WGBS inline context per entry: 16 bases before / after the seed   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
+    const uint2 *ctx;             // inline context per entry: 16 bases before / after the seed   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
     const uint2 *ctx2;            // wide context (the next 16 bases outwards), NULL unless -v >= BSX_WIDE_CTX_V
     const uint32_t *sites, *site_off;
     uint32_t n_seq;
@@ -17,6 +17,7 @@ struct MapArgs {
     int s, I, v, W, r, min_insert, max_insert, chains, pairend, rrbs, randseed, max_ns, max_readlen;
     int n_adapter, site_len, digest_pos;
     uint32_t seed_bits;
+    uint32_t rrbs_groups;         // RRBS: CSR slots per key of the seed table (bsx_rrbs_groups)
     int plan_cap;                 // plan entries per chain = max segments * I
     int nslot;                    // chains a read can use at once: 2 with -n 1, else 1 (plan storage per read)
     uint32_t read_smem, warp_smem_se, chain_stride, flank_off;   // derived from the two above on the host (bsx_map_args_derive)

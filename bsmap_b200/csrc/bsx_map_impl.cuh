@@ -61,9 +61,6 @@
 #define BSX_SE_MIN_CTAS 5
 #endif
 #define BSX_ROUND_HS 8           // half-steps (32 list entries each) per staging round: 2 KB of list entries per warp
-#ifndef BSX_PACKED
-#define BSX_PACKED 1            // WGBS list walk over a packed half-step schedule staged through shared memory (snp_align_packed)
-#endif
 
 #include "bsx_prep.cuh"
 
@@ -90,6 +87,22 @@ __device__ __forceinline__ uint2 read_window(const ReadSm *R, int chain, int off
     const int j = off >> 4, sh = (off & 15) * 2;
     const uint32_t r1 = (j + 1 < BSX_FIXWORDS) ? R->rw[chain][j + 1] : 0u, m1 = (j + 1 < BSX_FIXWORDS) ? R->m5[chain][j + 1] : 0u;
     return make_uint2(__funnelshift_l(r1, R->rw[chain][j], sh), __funnelshift_l(m1, R->m5[chain][j], sh));
+}
+
+// The read bases that face an entry's inline context are fixed per list, the context word varies per candidate.  With
+// M = one bit per valid base (low) plus the high bit of every valid base that is not T, a base mismatches iff
+// ((q ^ s) & M) has a bit in its field: read T (11) matches reference T and C (low bit equal), everything else must be
+// equal -- the same decision as XM((q & XC(s)) ^ s) & r (param.h:126,139-147, bsx_mm_word_bits) in four instead of six
+// operations per word, and the two words of a candidate share one popcount.
+__device__ __forceinline__ uint32_t flank_mask(uint32_t q, uint32_t m5) { return m5 | ((m5 & ~(q & (q >> 1))) << 1); }
+__device__ __forceinline__ uint32_t ctx_mm(uint32_t q, uint32_t M, uint32_t s) {
+    const uint32_t u = (q ^ s) & M;
+    return (uint32_t)__popc((u | (u >> 1)) & 0x55555555u);
+}
+// f = {q before, M before, q after, M after}, c = {16 bases before the seed, 16 after}
+__device__ __forceinline__ uint32_t ctx_mm2(const uint4 f, const uint2 c) {
+    const uint32_t ub = (f.x ^ c.x) & f.y, ua = (f.z ^ c.y) & f.w;
+    return (uint32_t)__popc(((ub | (ub >> 1)) & 0x55555555u) | ((ua | (ua << 1)) & 0xAAAAAAAAu));
 }
 
 // list entries are read once: keep them out of L1, which holds the prepare phase's per-lane arrays (local memory)
@@ -174,7 +187,7 @@ __device__ __forceinline__ void load_image(const MapArgs &A, ReadSm *R, const ui
         R->thres = (uint32_t)rmsn; R->fc = fc; R->cc = cc; R->dn = 0; R->best = 99;
     }
     __syncwarp();
-    if (!filtered && !BSX_RRBS(A)) {
+    if (!filtered) {
         #pragma unroll 1
         for (int c = 0; c < A.nslot; c++) {
             const int chain = A.nslot == 2 ? c : (fc ? 0 : 1);
@@ -184,7 +197,7 @@ __device__ __forceinline__ void load_image(const MapArgs &A, ReadSm *R, const ui
             for (int t = lane; t < used; t += 32) {
                 const int p = (int)(pl[t].w & 0xffffu);
                 const uint2 wb = read_window(R, chain, p - 16), wa = read_window(R, chain, p + A.s);
-                fl[t] = make_uint4(wb.x, wb.y, wa.x, wa.y);
+                fl[t] = make_uint4(wb.x, flank_mask(wb.x, wb.y), wa.x, flank_mask(wa.x, wa.y));
             }
         }
     }
@@ -348,7 +361,10 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
         uint32_t entry;                                                   // a random 4-byte read: 64-byte HBM fetch
         asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(entry) : "l"(A.pos + idx));
         if (!BSX_RRBS(A)) { strand = idx >= md; loc = entry - p; }           // h = -profile.a + i - seed_start_array
-        else { chr = __ldg(A.tag + idx) & 0xffffu; strand = chr & 1u; loc = entry - p + anchor[chr >> 1]; }
+        else {
+            chr = __ldg(A.tag + idx) & 0xffffu; strand = chr & 1u; loc = entry - p + anchor[chr >> 1];
+            if (entry < p) pass = false;                                      // underflow the start of refseq (align.cpp:194, 236)
+        }
     }
     const uint32_t *refbase = strand ? A.crefcat : A.refcat;
     uint32_t w = 0xffffu;
@@ -427,8 +443,8 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
 
 // Per-warp staging area of the packed list walk; aliases the prepare phase's PrepCol (idle while the warp aligns).
 struct HalfStep {                       // 32 consecutive entries of one position list
-    uint32_t src, lo, cnt, k;           // first entry index (even), list start, list length, list number within the mode
-    uint32_t rb, mb, ra, ma;            // the read bases / valid mask that face the list's inline context before / after the seed
+    uint32_t src, lo, cnt, k;           // first entry index (even), list start, list length (0: padding), list number within the mode
+    uint32_t qb, Mb, qa, Ma;            // the read bases / flank_mask that face the list's inline context before / after the seed
 };
 struct StageSm {
     uint2 slot[BSX_ROUND_HS * 32];      // one round of BSX_ROUND_HS half-steps x 32 entries {16 bases before, 16 after the seed}
@@ -436,54 +452,12 @@ struct StageSm {
 };
 static_assert(sizeof(StageSm) <= sizeof(PrepCol), "the staging area must fit in the idle PrepCol");
 static_assert(sizeof(HalfStep) == 32, "two uint4");
+static_assert(BSX_ROUND_HS % 2 == 0 && BSX_ROUND_HS <= 32, "half-steps are evaluated in pairs; one lane describes one half-step");
 
-// SnpAlign for one mode of a WGBS read (align.cpp:168-347), lists staged through shared memory.
-// The I position lists of the mode are cut into half-steps of 32 entries (a list starts a new half-step, at the even
-// entry index at or before its first entry, so that every copy is a 16-byte cp.async); the half-steps of all lists
-// form one schedule that is fetched in rounds of BSX_ROUND_HS and evaluated two half-steps = 64 candidates at a time.
-// Versus walking list after list with direct loads: one DRAM round trip per round instead of one per list, and ~3.5
-// instead of 5.6 steps per mode at config 2 (lists average 43 entries and used to occupy one or two 64-wide steps
-// each).  Within a half-step the list is warp-uniform, so the per-candidate work is still one 8-byte shared-memory
-// load, two masked XOR/popcount words and a compare.  Candidates are visited in the reference's order, so commits, -w
-// threshold lowering and the early returns fire exactly where the sequential reference stops.
-// The owners (lane k < I owns list k of the mode) write the half-steps of round [h0, h0 + BSX_ROUND_HS) into the schedule;
-// returns the number of half-steps of the whole mode.  Out of line: it runs once per mode, the evaluation loop must stay small.
-__device__ __noinline__ uint32_t packed_schedule(const MapArgs &A, ReadSm *R, StageSm *S, int chain, int mode, uint32_t h0, int lane, Ctr *C) {
-    const int per = A.I;
-    const uint4 *plan = plan_of(R, chain, A) + mode * per;
-    uint4 e = make_uint4(0u, 0u, 0u, 0u);                                 // {list start, rc start, list end, p | segment << 16}
-    if (lane < per) e = plan[lane];
-    const uint32_t n = e.z - e.x;
-    const uint32_t nhs = n ? (n + (e.x & 1u) + 31u) >> 5 : 0u;           // half-steps of my list
-    uint32_t cum = nhs;                                                   // inclusive scan over the (<= 16) lists
-#pragma unroll
-    for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(BSX_FULL, cum, d); if (lane >= d) cum += t; }
-    const uint32_t total_hs = __shfl_sync(BSX_FULL, cum, 15);
-    if (h0 == 0) {
-        const uint32_t total_n = __reduce_add_sync(BSX_FULL, n);
-        if (lane == 0) { C[CT_LIST] += total_n; C[CT_CAND] += total_n; }  // corrected by packed_exit when SnpAlign returns early
-    }
-    __syncwarp();
-    if (nhs) {
-        const uint4 f = (flank_of(R, chain, A) + mode * per)[lane];      // read bases facing the list's inline context (load_image)
-        const int first = (int)(cum - nhs) - (int)h0;
-        #pragma unroll 1
-        for (int o = max(0, -first); o < (int)nhs && first + o < BSX_ROUND_HS; o++) {
-            uint4 *d4 = reinterpret_cast<uint4 *>(&S->sched[first + o]);
-            d4[0] = make_uint4((e.x & ~1u) + 32u * (uint32_t)o, e.x, n, (uint32_t)lane);
-            d4[1] = f;
-        }
-    }
-    __syncwarp();
-    return total_hs;
-}
-
-// SnpAlign returned at lane `xl` of half-step `cur` of the current round (nst half-steps): the candidates the sequential
-// reference has visited are the lists before this one and this list up to the exiting entry; everything else that was
-// requested is over-fetch.
-__device__ __noinline__ void packed_exit(const MapArgs &A, ReadSm *R, StageSm *S, int chain, int mode, uint32_t cur, uint32_t nst, uint32_t xl, int lane, Ctr *C) {
-    const int per = A.I;
-    const uint4 *plan = plan_of(R, chain, A) + mode * per;
+// SnpAlign returned at lane `xl` of half-step `cur` of the current round: the candidates the sequential reference has
+// visited are the lists before this one and this list up to the exiting entry; everything else that was requested
+// in this round is over-fetch, the rounds that were never requested do not count at all.
+__device__ __noinline__ void packed_exit(const uint4 *plan, int per, StageSm *S, uint32_t cur, uint32_t xl, int lane, Ctr *C) {
     const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[cur]);
     uint32_t nk = 0;
     if (lane < per) { const uint4 el = plan[lane]; nk = el.z - el.x; }
@@ -491,7 +465,7 @@ __device__ __noinline__ void packed_exit(const MapArgs &A, ReadSm *R, StageSm *S
     const uint32_t before = __reduce_add_sync(BSX_FULL, (uint32_t)lane < sc.w ? nk : 0u);
     const uint32_t counted = before + (sc.x + xl - sc.y) + 1u;
     uint32_t extra = 0;                                                   // entries of this round behind the exiting one
-    if ((uint32_t)lane < nst && (uint32_t)lane >= cur) {
+    if (lane < BSX_ROUND_HS && (uint32_t)lane >= cur) {
         const uint4 t = *reinterpret_cast<const uint4 *>(&S->sched[lane]);
         uint32_t lo_i = max(t.x, t.y);
         const uint32_t hi_i = min(t.x + 32u, t.y + t.z);
@@ -499,13 +473,11 @@ __device__ __noinline__ void packed_exit(const MapArgs &A, ReadSm *R, StageSm *S
         extra = hi_i > lo_i ? hi_i - lo_i : 0u;
     }
     const uint32_t req = counted + __reduce_add_sync(BSX_FULL, extra);
-    if (lane == 0) { C[CT_CAND] -= all - counted; C[CT_LIST] -= all - req; C[CT_OVER] += req - counted; }
+    if (lane == 0) { C[CT_LIST] -= all - req; C[CT_OVER] += req - counted; }
 }
 
 // phase-1 chunk choice for a mode: keep away from its seed zone (all sub-seeds)
-__device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm *R, int chain, int mode, int lane) {
-    const int per = A.I;
-    const uint4 *plan = plan_of(const_cast<ReadSm *>(R), chain, A) + mode * per;
+__device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm *R, int chain, const uint4 *plan, int per, int lane) {
     int zlo = 1000, zhi = -1;
     if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
 #pragma unroll
@@ -514,18 +486,54 @@ __device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm
     return chunk_table(R, chain, R->nw, zlo, zhi, lane);
 }
 
+// SnpAlign for one mode (align.cpp:168-347), lists staged through shared memory.
+// The position lists of the mode (WGBS: its I sub-seeds; RRBS: the one (segment, mirror) group of its key) are cut into
+// half-steps of 32 entries -- a list starts a new half-step, at the even entry index at or before its first entry, so
+// that every copy is a 16-byte cp.async -- and the half-steps of all lists form one schedule that is fetched in rounds
+// of BSX_ROUND_HS and evaluated two half-steps = 64 candidates at a time: one DRAM round trip per round instead of one per
+// list.  Lane t of the warp describes half-step t of the round (which list, where it starts, the read bases that face
+// its context); within a half-step the list is warp-uniform, so a candidate costs one 8-byte shared-memory load, eight
+// logic operations, one popcount and a compare.  The fast path does not even test whether a staged entry belongs to
+// the list: stale or foreign entries can only raise a false alarm, which the slow path masks out.  Candidates are
+// visited in the reference's order, so commits, -w threshold lowering and the early returns fire exactly where the
+// sequential reference stops.
 __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *S) {
+    const int per = BSX_RRBS(A) ? 1 : A.I;
     #pragma unroll 1
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
-        uint32_t total_hs = 1;
+        const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per;
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);                             // lane k < per owns list k: {start, rc start, end, p | segment << 16}
+        if (lane < per) e = plan[lane];
+        const uint32_t n = e.z - e.x;
+        uint32_t cum = n ? (n + (e.x & 1u) + 31u) >> 5 : 0u;             // half-steps of my list -> inclusive scan over the lists
+        #pragma unroll 1
+        for (int d = 1; d < per; d <<= 1) { const uint32_t t = __shfl_up_sync(BSX_FULL, cum, d); if (lane >= d) cum += t; }
+        const uint32_t total_hs = __shfl_sync(BSX_FULL, cum, per - 1);
+        if (total_hs == 0) continue;
+        CTR_ADD(C, CT_LIST, __reduce_add_sync(BSX_FULL, n));              // corrected by packed_exit when SnpAlign returns early
         uint32_t thres = R->thres;
         #pragma unroll 1
         for (uint32_t h0 = 0; h0 < total_hs; h0 += BSX_ROUND_HS) {
-            total_hs = packed_schedule(A, R, S, chain, mode, h0, lane, C);
-            if (total_hs == 0) break;
-            const uint32_t nst = min((uint32_t)BSX_ROUND_HS, total_hs - h0);
-            {   // every lane copies one 16-byte pair of entries per step of the round
+            {   // lane t describes half-step h0 + t: its list is the first one whose running total exceeds h0 + t
+                const uint32_t target = h0 + (uint32_t)lane;
+                int k = 0; uint32_t first = 0;
+                #pragma unroll 1
+                for (int j = 0; j < per; j++) { const uint32_t c = __shfl_sync(BSX_FULL, cum, j); if (c <= target) { k = j + 1; first = c; } }
+                __syncwarp();                                             // the previous round's slow path may still read the schedule
+                if (lane < BSX_ROUND_HS) {
+                    uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;       // padding: no entry of it is ever inside a list
+                    if (k < per) {
+                        const uint4 ek = plan[k];
+                        d0 = make_uint4((ek.x & ~1u) + 32u * (target - first), ek.x, ek.z - ek.x, (uint32_t)k);
+                        d1 = flank[k];
+                    }
+                    uint4 *d4 = reinterpret_cast<uint4 *>(&S->sched[lane]);
+                    d4[0] = d0; d4[1] = d1;
+                }
+                __syncwarp();
+            }
+            {   // every lane copies one 16-byte pair of entries per pair of half-steps
                 const uint32_t half = (uint32_t)lane >> 4, pr = 2u * ((uint32_t)lane & 15u);
                 const uint2 *ctx = A.ctx;
 #pragma unroll
@@ -533,38 +541,38 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
                     const uint32_t hs = 2u * q + half;
                     const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
                     const uint32_t g = sc.x + pr;
-                    if (hs < nst && g < sc.y + sc.z) cp_async16(&S->slot[hs * 32u + pr], ctx + g);
+                    if (g < sc.y + sc.z) cp_async16(&S->slot[hs * 32u + pr], ctx + g);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
             }
             __syncwarp();
+            const uint32_t nst = min((uint32_t)BSX_ROUND_HS, total_hs - h0);
             #pragma unroll 1
             for (uint32_t hs = 0; hs < nst; hs += 2) {
-                // branch-free: a half-step past the end of the round reads stale shared memory and is masked out
-                const uint4 s0 = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
                 const uint4 f0 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 1);
-                const uint4 s1 = *reinterpret_cast<const uint4 *>(&S->sched[hs + 1]);
-                const uint4 f1 = *(reinterpret_cast<const uint4 *>(&S->sched[hs + 1]) + 1);
+                const uint4 f1 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 3);
                 const uint2 cx0 = S->slot[hs * 32u + lane], cx1 = S->slot[hs * 32u + 32u + lane];
-                const bool in0 = (s0.x + (uint32_t)lane - s0.y) < s0.z;                          // inside the list (unsigned)
-                const bool in1 = ((s1.x + (uint32_t)lane - s1.y) < s1.z) & (hs + 1 < nst);
-                const bool pass0 = in0 & (__popc(bsx_mm_word_bits(f0.x, f0.y, cx0.x)) + __popc(bsx_mm_word_bits(f0.z, f0.w, cx0.y)) <= thres);
-                const bool pass1 = in1 & (__popc(bsx_mm_word_bits(f1.x, f1.y, cx1.x)) + __popc(bsx_mm_word_bits(f1.z, f1.w, cx1.y)) <= thres);
+                bool pass0 = ctx_mm2(f0, cx0) <= thres, pass1 = ctx_mm2(f1, cx1) <= thres;
                 if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
-                // ---- slow path: some candidate passed the inline-context filter
+                // ---- slow path: some staged entry passed the inline-context filter; is it a candidate at all?
+                const uint4 s0 = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
+                const uint4 s1 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 2);
+                pass0 &= (s0.x + (uint32_t)lane - s0.y) < s0.z;                                  // inside the list (unsigned; padding has length 0)
+                pass1 &= (s1.x + (uint32_t)lane - s1.y) < s1.z;
                 const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+                if (!(pm0 | pm1)) continue;
                 // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
                 const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
-                const uint32_t tbl = use_p1 ? mode_chunk_table(A, R, chain, mode, lane) : 0u;
+                const uint32_t tbl = use_p1 ? mode_chunk_table(A, R, chain, plan, per, lane) : 0u;
                 int ret = 0;
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {                            // one call site: the slow path exists once in the binary
                     if (h ? pm1 : pm0) {
-                        const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs + h]);
-                        const uint4 ek = (plan_of(R, chain, A) + mode * A.I)[sc.w];
+                        const uint4 sc = h ? s1 : s0;
+                        const uint4 ek = plan[sc.w];
                         const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, sc.x, ek.y, ek.w & 0xffffu, tbl, use_p1, lane, C);
-                        if (rc & 1) { packed_exit(A, R, S, chain, mode, hs + (uint32_t)h, nst, (uint32_t)(rc >> 8), lane, C); ret = 1; break; }
+                        if (rc & 1) { packed_exit(plan, per, S, hs + (uint32_t)h, (uint32_t)(rc >> 8), lane, C); ret = 1; break; }
                     }
                 }
                 if (ret) return 1;
@@ -576,15 +584,12 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
 }
 
 // SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
-// The I position lists of the mode are walked in the reference's order (sub-seed 0's forward entries, its
-// rc entries, sub-seed 1's, ...), 64 table entries per step (two per lane).  Everything that depends on
-// the list (its bounds, the read bases that face the inline context) is warp-uniform, so the per-candidate
-// work is one 8-byte load, two masked XOR/popcount words and a compare.
+// Indexes built for -v >= 8 (wide context) walk the I position lists of the mode one by one with direct loads, in the
+// reference's order (sub-seed 0's forward entries, its rc entries, sub-seed 1's, ...), 64 table entries per step; their
+// lists run to thousands of entries, so the next step's context is requested before this one is evaluated.
 __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *stage) {
-#if BSX_PACKED
-    if (!BSX_RRBS(A) && !BSX_WIDE(A)) return snp_align_packed(A, R, hits, dd, store_all, mode, lane, C, stage);
-#endif
-    const int per = BSX_RRBS(A) ? 1 : A.I;
+    if (!BSX_WIDE(A)) return snp_align_packed(A, R, hits, dd, store_all, mode, lane, C, stage);
+    const int per = A.I;
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
         const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per;
@@ -596,139 +601,57 @@ __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32
             const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
             if (e.x == e.z) continue;                                    // index2[_seed] == NULL
             const uint32_t p = e.w & 0xffffu;
-            uint32_t rb = 0, mb = 0, ra = 0, ma = 0, want = 0;
-            if (!BSX_RRBS(A)) {
-                const uint4 f = flank[i];                                // prepared with the plan (select_seeds)
-                rb = f.x; mb = f.y; ra = f.z; ma = f.w;
-            } else {
-                const int sg = (int)(e.w >> 16);
-                want = chain ? (uint32_t)(R->len / A.s - 1 - sg) : (uint32_t)sg;     // RRBS segment tag
-            }
-            if (!BSX_RRBS(A)) {
-                // ---- WGBS: phase 0 = mismatches among the <= 32 read bases that face the entry's inline context
-                // (8 bytes that arrive with the list stream).  It is a lower bound of CountMismatch, so
-                // `> snp_thres` rejects exactly like the reference; pos[] and the reference are only touched by
-                // survivors.  Every entry of the list is a candidate, so the counters need no per-step work.
-                uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
-                uint32_t rb2 = 0, mb2 = 0, ra2 = 0, ma2 = 0; bool have_f2 = false;     // wide-context flanks of this list, set up on first use
-                // high -v workloads walk lists of thousands of entries: there the next step's context is requested before
-                // this step is evaluated (on config 2's ~1.4-step lists the same pipelining measured -7 %)
-                uint2 nx0 = make_uint2(0, 0), nx1 = make_uint2(0, 0);
-                if (BSX_WIDE(A)) {
-                    if (c0 + lane < e.z) nx0 = ld_stream(A.ctx + c0 + lane);
-                    if (c0 + lane + 32 < e.z) nx1 = ld_stream(A.ctx + c0 + lane + 32);
+            const uint4 f = flank[i];                                    // read bases / masks facing the inline context (load_image)
+            // phase 0 = mismatches among the <= 32 read bases that face the entry's inline context (8 bytes that arrive
+            // with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the
+            // reference; pos[] and the reference are only touched by survivors.
+            uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
+            uint32_t rb2 = 0, Mb2 = 0, ra2 = 0, Ma2 = 0; bool have_f2 = false;     // wide-context flanks of this list, set up on first use
+            uint2 nx0 = make_uint2(0, 0), nx1 = make_uint2(0, 0);
+            if (c0 + lane < e.z) nx0 = ld_stream(A.ctx + c0 + lane);
+            if (c0 + lane + 32 < e.z) nx1 = ld_stream(A.ctx + c0 + lane + 32);
+            for (; c0 < e.z; c0 += 64) {
+                const uint32_t i0 = c0 + lane, i1 = i0 + 32;
+                const uint2 cx0 = nx0, cx1 = nx1;
+                if (i0 + 64 < e.z) nx0 = ld_stream(A.ctx + i0 + 64);
+                if (i1 + 64 < e.z) nx1 = ld_stream(A.ctx + i1 + 64);
+                bool pass0 = i0 < e.z && ctx_mm2(f, cx0) <= thres, pass1 = i1 < e.z && ctx_mm2(f, cx1) <= thres;
+                if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
+                // phase 0b: with many mismatches allowed 32 context bases let a fifth of the candidates through; the
+                // next 16 bases on either side, stored in a second array that only these survivors read, are tested
+                // before any of them touches the reference
+                if (!have_f2) {
+                    const uint2 wb = read_window(R, chain, (int)p - 32), wa = read_window(R, chain, (int)p + A.s + 16);
+                    rb2 = wb.x; Mb2 = flank_mask(wb.x, wb.y); ra2 = wa.x; Ma2 = flank_mask(wa.x, wa.y); have_f2 = true;
                 }
-                for (; c0 < e.z; c0 += 64) {
-                    const uint32_t i0 = c0 + lane, i1 = i0 + 32;
-                    bool pass0 = false, pass1 = false;
-                    uint2 cx0 = make_uint2(0, 0), cx1 = make_uint2(0, 0);
-                    if (BSX_WIDE(A)) {
-                        cx0 = nx0; cx1 = nx1;
-                        if (i0 + 64 < e.z) nx0 = ld_stream(A.ctx + i0 + 64);
-                        if (i1 + 64 < e.z) nx1 = ld_stream(A.ctx + i1 + 64);
-                    } else {
-                        if (i0 < e.z) cx0 = ld_stream(A.ctx + i0);
-                        if (i1 < e.z) cx1 = ld_stream(A.ctx + i1);
-                    }
-                    if (i0 < e.z) pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) <= thres;
-                    if (i1 < e.z) pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) <= thres;
-                    if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
-                    if (BSX_WIDE(A)) {
-                        // phase 0b (indexes built for -v >= 8): with many mismatches allowed 32 context bases let a fifth
-                        // of the candidates through; the next 16 bases on either side, stored in a second array that only
-                        // these survivors read, are tested before any of them touches the reference
-                        if (!have_f2) {
-                            const uint2 wb = read_window(R, chain, (int)p - 32), wa = read_window(R, chain, (int)p + A.s + 16);
-                            rb2 = wb.x; mb2 = wb.y; ra2 = wa.x; ma2 = wa.y; have_f2 = true;
-                        }
-                        if (pass0) {
-                            const uint2 c2 = __ldg(A.ctx2 + i0);
-                            pass0 = __popc(bsx_mm_word_bits(rb, mb, cx0.x)) + __popc(bsx_mm_word_bits(ra, ma, cx0.y)) +
-                                    __popc(bsx_mm_word_bits(rb2, mb2, c2.x)) + __popc(bsx_mm_word_bits(ra2, ma2, c2.y)) <= thres;
-                        }
-                        if (pass1) {
-                            const uint2 c2 = __ldg(A.ctx2 + i1);
-                            pass1 = __popc(bsx_mm_word_bits(rb, mb, cx1.x)) + __popc(bsx_mm_word_bits(ra, ma, cx1.y)) +
-                                    __popc(bsx_mm_word_bits(rb2, mb2, c2.x)) + __popc(bsx_mm_word_bits(ra2, ma2, c2.y)) <= thres;
-                        }
-                        if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
-                    }
-                    const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
-                    // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
-                    // (high -v); otherwise survivors go straight to the exact count
-                    const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
-                    if (use_p1 && !have_tbl) {
-                        // phase-1 chunk choice: keep away from the seed zone of this mode (all sub-seeds)
-                        int zlo = 1000, zhi = -1;
-                        if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
-#pragma unroll
-                        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-                        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                        tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
-                        have_tbl = true;
-                    }
+                if (pass0) {
+                    const uint2 c2 = __ldg(A.ctx2 + i0);
+                    pass0 = ctx_mm2(f, cx0) + ctx_mm(rb2, Mb2, c2.x) + ctx_mm(ra2, Ma2, c2.y) <= thres;
+                }
+                if (pass1) {
+                    const uint2 c2 = __ldg(A.ctx2 + i1);
+                    pass1 = ctx_mm2(f, cx1) + ctx_mm(rb2, Mb2, c2.x) + ctx_mm(ra2, Ma2, c2.y) <= thres;
+                }
+                if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
+                const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
+                // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
+                const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
+                if (use_p1 && !have_tbl) { tbl = mode_chunk_table(A, R, chain, plan, per, lane); have_tbl = true; }
 #pragma unroll 1
-                    for (int h = 0; h < 2; h++) {                        // one call site: the slow path exists once in the binary
-                        if (h ? pm1 : pm0) {
-                            const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, use_p1, lane, C);
-                            if (rc & 1) { ret = 1; exit_pos = (c0 - e.x) + 32u * h + (uint32_t)(rc >> 8) + 1u; break; }
-                        }
+                for (int h = 0; h < 2; h++) {                        // one call site: the slow path exists once in the binary
+                    if (h ? pm1 : pm0) {
+                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, use_p1, lane, C);
+                        if (rc & 1) { ret = 1; exit_pos = (c0 - e.x) + 32u * h + (uint32_t)(rc >> 8) + 1u; break; }
                     }
-                    if (ret) break;
-                    thres = R->thres;
                 }
-                if (!ret) { visited += e.z - e.x; counted += e.z - e.x; }
-                else { visited += min(c0 + 64u, e.z) - e.x; counted += exit_pos; }
-            } else {
-                // ---- RRBS: tagged Hit{chr, loc}: segment/strand filter, then underflow test (align.cpp:187-194,
-                // 229-236); survivors of the filter are the reference's candidates
-                for (uint32_t c0 = e.x; c0 < e.z; c0 += 64) {
-                    const uint32_t i0 = c0 + lane, i1 = i0 + 32;
-                    bool pass0 = false, pass1 = false;
-                    unsigned vm0 = 0, vm1 = 0;
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t idx = h ? i1 : i0;
-                        bool valid = idx < e.z;
-                        if (valid) {
-                            const uint32_t tag = __ldg(A.tag + idx);
-                            if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) valid = false;
-                            if (__ldg(A.pos + idx) < p) valid = false;
-                        }
-                        if (h == 0) { pass0 = valid; vm0 = __ballot_sync(BSX_FULL, valid); }
-                        else { pass1 = valid; vm1 = __ballot_sync(BSX_FULL, valid); }
-                    }
-                    visited += min(64u, e.z - c0);
-                    if ((vm0 | vm1) == 0) continue;
-                    if (!have_tbl) {
-                        int zlo = 1000, zhi = -1;
-                        if (lane < per) { zlo = zhi = (int)(plan[lane].w & 0xffffu); }
-#pragma unroll
-                        for (int d = 8; d; d >>= 1) { zlo = min(zlo, __shfl_xor_sync(BSX_FULL, zlo, d)); zhi = max(zhi, __shfl_xor_sync(BSX_FULL, zhi, d)); }
-                        zlo = __shfl_sync(BSX_FULL, zlo, 0); zhi = __shfl_sync(BSX_FULL, zhi, 0) + A.s;
-                        tbl = chunk_table(R, chain, R->nw, zlo, zhi, lane);
-                        have_tbl = true;
-                    }
-#pragma unroll 1
-                    for (int h = 0; h < 2; h++) {
-                        const unsigned vmh = h ? vm1 : vm0;
-                        if (vmh) {
-                            const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, 1, lane, C);
-                            if (rc & 1) { ret = 1; counted += __popc(vmh & ((2u << (rc >> 8)) - 1u)); break; }
-                        }
-                        counted += __popc(vmh);
-                    }
-                    if (ret) break;
-                }
+                if (ret) break;
+                thres = R->thres;
             }
+            if (!ret) { visited += e.z - e.x; counted += e.z - e.x; }
+            else { visited += min(c0 + 64u, e.z) - e.x; counted += exit_pos; }
         }
-        // C = candidates the sequential reference visits (RRBS: tag-filtered entries are not counted);
-        // entries evaluated past an exit point count as over-fetch
-        if (lane == 0) {
-            C[CT_LIST] += visited;
-            C[CT_CAND] += counted;
-            if (ret) C[CT_OVER] += (BSX_RRBS(A) ? 0u : visited - counted);
-        }
+        // candidates the sequential reference visits = list entries - over-fetch (entries evaluated past an exit point)
+        if (lane == 0) { C[CT_LIST] += visited; if (ret) C[CT_OVER] += visited - counted; }
         if (ret) return 1;
     }
     return 0;
@@ -768,7 +691,10 @@ __device__ void write_record(const MapArgs &A, const ReadSm *R, const uint2 *hit
 
 __device__ __forceinline__ void flush_counters(const MapArgs &A, Ctr *C, int lane) {
     __syncwarp();
-    if (lane < 8) { atomicAdd(A.stats + lane, (unsigned long long)C[lane]); C[lane] = 0; }
+    // candidates the reference semantics visit = list entries requested - entries evaluated past an exit point
+    if (lane < 8) { atomicAdd(A.stats + lane, (unsigned long long)(lane == CT_CAND ? C[CT_LIST] - C[CT_OVER] : C[lane])); }
+    __syncwarp();
+    if (lane < 8) C[lane] = 0;
     __syncwarp();
 }
 
@@ -801,7 +727,7 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
         #pragma unroll 1
         for (uint32_t i = 0; i < cnt; i++) {                                  // phase B: the warp aligns them one by one
             const uint32_t r = r0 + i;
-            if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
+            if (C[CT_LIST] & 0x80000000u) flush_counters(A, C, lane);
             load_image(A, R, scratch + (size_t)i * A.img_bytes, lane);
             if (!R->filtered) run_align(A, R, hits, dd, 0, lane, C, reinterpret_cast<StageSm *>(P));
             __syncwarp();
@@ -963,7 +889,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
       #pragma unroll 1
       for (uint32_t pi = 0; pi < cnt; pi++) {                                 // phase B: the warp aligns the pairs one by one
         const uint32_t r = r0 + pi;
-        if ((C[CT_CAND] | C[CT_LIST]) & 0x80000000u) flush_counters(A, C, lane);
+        if (C[CT_LIST] & 0x80000000u) flush_counters(A, C, lane);
         load_image(A, Ra, scratch + (size_t)(2u * pi) * A.img_bytes, lane);
         load_image(A, Rb, scratch + (size_t)(2u * pi + 1u) * A.img_bytes, lane);
         int paired = 0;

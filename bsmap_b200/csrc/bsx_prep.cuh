@@ -223,6 +223,13 @@ __device__ __forceinline__ uint3 probe_tab(const MapArgs &A, uint32_t key) {
 #endif
 }
 
+// RRBS: the table is a CSR over (key, group) (bsx_index.cu); the whole list of a key -- ref.index[key].n1, what
+// ReorderSeed ranks the segments by (align.cpp:474-485) -- spans its `groups` consecutive slots
+__device__ __forceinline__ uint32_t probe_rrbs_size(const MapArgs &A, uint32_t key) {
+    const uint32_t *p = A.tab + (size_t)key * A.rrbs_groups;
+    return __ldg(p + A.rrbs_groups) - __ldg(p);
+}
+
 // Seed probing and selection for one chain; writes plan[] of the image, returns the number of probes.
 // Only the list SIZES are kept per probed offset (a thread-local array goes through L1/L2 to HBM for 5 920 resident
 // warps); the bounds of the lists that end up in the plan are read again -- the lines were fetched moments ago.
@@ -255,7 +262,7 @@ __device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, c
                 if (rrbs || (r + 1 >= w && n < seg - 1)) { n++; r = 0; } else r++;
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) h[u] = ok[u] ? probe_tab(A, key[u]) : make_uint3(0u, 0u, 0u);
+            for (int u = 0; u < 4; u++) h[u] = !ok[u] ? make_uint3(0u, 0u, 0u) : (rrbs ? make_uint3(0u, 0u, probe_rrbs_size(A, key[u])) : probe_tab(A, key[u]));
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (q0 + u < total) {
@@ -334,7 +341,18 @@ __device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, c
         for (int k = 0; k < per; k++) {
             const int p = rrbs ? (sg * s + cso) : ((int)K->profA[sg * 16 + k] + arr[sg] - k);
             uint3 h = make_uint3(0u, 0u, 0u);
-            if (p + s <= len) h = probe_tab(A, seed_key(A, rw, p));
+            if (p + s <= len) {
+                if (!rrbs) h = probe_tab(A, seed_key(A, rw, p));
+                else {
+                    // the entries SnpAlign does not skip: segment sg of plain entries for the read as is, segment
+                    // len/s - 1 - sg of mirrored entries for its reverse complement (align.cpp:187, 222-229)
+                    const uint32_t g = chain ? 2u * (uint32_t)((int)K->segof[len] - 1 - sg) + 1u : 2u * (uint32_t)sg;
+                    if (g < A.rrbs_groups) {
+                        const uint32_t *t = A.tab + (size_t)seed_key(A, rw, p) * A.rrbs_groups + g;
+                        h.x = __ldg(t); h.z = __ldg(t + 1); h.y = h.z;
+                    }
+                }
+            }
             plan[m * per + k] = make_uint4(h.x, h.y, h.z, (uint32_t)p | ((uint32_t)sg << 16));
         }
     }

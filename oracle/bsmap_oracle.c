@@ -644,7 +644,9 @@ static void snp_align(sa_t *a, int mode) {
                 uint32_t tag = r->tag[j], loc = r->pos[j];
                 if (((chain ? (tag ^ 0x1000000u) : tag) >> 16) != want) continue;
                 uint32_t chr = tag & 0xffff;
-                if (loc < h) continue;
+                /* n_cand counts the entries that pass the tag test: those the reference goes on to examine.  The few
+                   whose window would start before the sequence are dropped here without a CountMismatch call. */
+                if (loc < h) { a->n_cand++; continue; }
                 loc -= h;
                 const uint32_t *m = ((chr & 1) ? r->crefcat : r->refcat) + r->anchor[chr >> 1] / SEGLEN;
                 uint32_t w = count_mismatch(a, bs[loc % SEGLEN], rg[loc % SEGLEN], m + loc / SEGLEN);

@@ -65,6 +65,22 @@ def test_sorted_bam_equals_samtools(tmp_path, name):
     assert parse_bai(ours + ".bai") == mine
 
 
+@pytest.mark.parametrize("name", ["pe_sam", "se_cfg5", "rrbs_se_A"])
+def test_bounded_memory_path_writes_the_same_files(tmp_path, monkeypatch, name):
+    """text taken in 20 KB chunks (sorted runs on disk + merge) and BGZF windows of two blocks (the index trails the
+    writer): same .bam and .bai bytes as the one-chunk, one-window conversion"""
+    case = CS.BY_NAME[name]
+    sam = str(tmp_path / "in.sam")
+    open(sam, "wb").write(R.golden_load(case)[0])
+    assert os.path.getsize(sam) > 200_000
+    B.sam_to_sorted_bam(sam, str(tmp_path / "a.bam"), threads=3)
+    monkeypatch.setenv("BSX_BAM_CHUNK_MB", "0.02"); monkeypatch.setenv("BSX_BAM_WINDOW_BLOCKS", "2")
+    B.sam_to_sorted_bam(sam, str(tmp_path / "b.bam"), threads=3)
+    assert open(tmp_path / "a.bam", "rb").read() == open(tmp_path / "b.bam", "rb").read()
+    assert open(tmp_path / "a.bam.bai", "rb").read() == open(tmp_path / "b.bam.bai", "rb").read()
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".tmp")], "run files must be removed"
+
+
 def test_bam_writer_errors(tmp_path):
     with pytest.raises(B.BsxError, match="cannot open"):
         B.sam_to_sorted_bam(str(tmp_path / "missing.sam"), str(tmp_path / "x.bam"))

@@ -54,40 +54,53 @@ def test_index_matches_oracle(name):
     ix = B.Index(pb, d["gnames"], d["gseqs"])
     info = ix.info
     assert (info.n_words, info.n_keys, info.n_entries) == (oref.n_words, oref.n_keys, oref.n_entries)
-    for what in ("refcat", "crefcat", "anchor", "tab", "pos"):
+    f, c = np.array(oref.refcat).astype(np.uint64), np.array(oref.crefcat).astype(np.uint64)
+
+    def window(coord, strand):
+        w, sh = coord >> 4, ((coord & 15) * 2).astype(np.uint64)
+        lo_f, hi_f = f[w + 1], f[w]; lo_c, hi_c = c[w + 1], c[w]
+        hi, lo = np.where(strand, hi_c, hi_f), np.where(strand, lo_c, lo_f)
+        return ((((hi << np.uint64(32)) | lo) << sh) >> np.uint64(32)) & np.uint64(0xffffffff)
+
+    s_ = 12 if kw.get("D") else kw.get("s", 16)   # -D forces seed 12 (param.cpp:95-106)
+    for what in ("refcat", "crefcat", "anchor"):
         msg = _diff_arrays(what, ix.download(what), np.array(getattr(oref, what)))
         assert msg is None, msg
+    tab, pos = np.array(oref.tab).astype(np.int64), np.array(oref.pos).astype(np.int64)
     if kw.get("D"):
-        msg = _diff_arrays("tag", ix.download("tag"), np.array(oref.pos_tag))
-        assert msg is None, msg
+        # RRBS: every list of the reference, stably partitioned by its (segment, mirrored) tag -- the entries one
+        # SnpAlign call does not skip become contiguous, in the reference's order -- and a CSR over (key, group)
+        tag = np.array(oref.pos_tag).astype(np.int64)
+        G = 2 * (144 // s_)
+        key = np.repeat(np.arange(info.n_keys, dtype=np.int64), tab[2::2] - tab[0:-1:2])
+        comp = key * G + 2 * ((tag >> 16) & 0xff) + (tag >> 24)
+        order = np.argsort(comp, kind="stable")
+        exp_tab = np.concatenate([[0], np.cumsum(np.bincount(comp, minlength=int(info.n_keys) * G))])
+        assert info.n_tab == len(exp_tab)
+        for what, exp in (("tab", exp_tab), ("pos", pos[order]), ("tag", tag[order])):
+            msg = _diff_arrays(what, ix.download(what), exp.astype(np.uint32))
+            assert msg is None, msg
+        chr_ = tag[order] & 0xffff
+        coord, strand = np.array(oref.anchor).astype(np.int64)[chr_ >> 1] + pos[order], (chr_ & 1).astype(bool)
     else:
-        # inline context: the 16 reference bases before / after every entry's seed, on the entry's strand
-        tab, pos = np.array(oref.tab).astype(np.int64), np.array(oref.pos).astype(np.int64)
-        ctx = ix.download("ctx").reshape(-1, 2)
-        strand = np.zeros(len(pos), dtype=bool)
-        starts, mids, ends = tab[0:-1:2], tab[1::2], tab[2::2]
-        nz = np.nonzero(ends > mids)[0]
-        for k in nz[:200000]:
-            strand[mids[k]:ends[k]] = True
-        if len(nz) > 200000:   # vectorised fallback for big tables
-            strand = np.zeros(len(pos) + 1, dtype=np.int64); np.add.at(strand, mids, 1); np.add.at(strand, ends, -1)
-            strand = np.cumsum(strand)[:-1] > 0
-        f, c = np.array(oref.refcat).astype(np.uint64), np.array(oref.crefcat).astype(np.uint64)
-        def window(coord):
-            w, sh = coord >> 4, ((coord & 15) * 2).astype(np.uint64)
-            lo_f, hi_f = f[w + 1], f[w]; lo_c, hi_c = c[w + 1], c[w]
-            hi, lo = np.where(strand, hi_c, hi_f), np.where(strand, lo_c, lo_f)
-            return ((((hi << np.uint64(32)) | lo) << sh) >> np.uint64(32)) & np.uint64(0xffffffff)
-        s_ = kw.get("s", 16)
-        assert np.array_equal(ctx[:, 0].astype(np.uint64), window(pos - 16)), "ctx.before differs"
-        assert np.array_equal(ctx[:, 1].astype(np.uint64), window(pos + s_)), "ctx.after differs"
-        if kw.get("v", 2) >= 8:   # wide context: the next 16 bases outwards, built for high -v only
-            ctx2 = ix.download("ctx2").reshape(-1, 2)
-            assert np.array_equal(ctx2[:, 0].astype(np.uint64), window(pos - 32)), "ctx2.before differs"
-            assert np.array_equal(ctx2[:, 1].astype(np.uint64), window(pos + s_ + 16)), "ctx2.after differs"
-        else:
-            with pytest.raises(B.BsxError):
-                ix.download("ctx2")
+        for what in ("tab", "pos"):
+            msg = _diff_arrays(what, ix.download(what), np.array(getattr(oref, what)))
+            assert msg is None, msg
+        strand = np.zeros(len(pos) + 1, dtype=np.int64)
+        np.add.at(strand, tab[1::2], 1); np.add.at(strand, tab[2::2], -1)
+        strand = np.cumsum(strand)[:-1] > 0
+        coord = pos
+    # inline context: the 16 reference bases before / after every entry's seed, on the entry's strand
+    ctx = ix.download("ctx").reshape(-1, 2)
+    assert np.array_equal(ctx[:, 0].astype(np.uint64), window(coord - 16, strand)), "ctx.before differs"
+    assert np.array_equal(ctx[:, 1].astype(np.uint64), window(coord + s_, strand)), "ctx.after differs"
+    if not kw.get("D") and kw.get("v", 2) >= 8:   # wide context: the next 16 bases outwards, built for high -v only
+        ctx2 = ix.download("ctx2").reshape(-1, 2)
+        assert np.array_equal(ctx2[:, 0].astype(np.uint64), window(coord - 32, strand)), "ctx2.before differs"
+        assert np.array_equal(ctx2[:, 1].astype(np.uint64), window(coord + s_ + 16, strand)), "ctx2.after differs"
+    else:
+        with pytest.raises(B.BsxError):
+            ix.download("ctx2")
     ix.close(); oref.close()
 
 
