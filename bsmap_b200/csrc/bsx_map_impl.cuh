@@ -60,6 +60,18 @@
 #ifndef BSX_SE_MIN_CTAS
 #define BSX_SE_MIN_CTAS 5
 #endif
+#ifndef BSX_KSEARCH
+#define BSX_KSEARCH 0           // schedule lookup: 0 = one shuffle per list (independent, pipelined), 1 = binary search over the lanes
+                                // holding the running totals (fewer instructions but a dependent chain: measured -9 % on paired-end)
+#endif
+#ifndef BSX_KUNROLL
+#define BSX_KUNROLL 1
+#endif
+#define BSX_PRAGMA_(x) _Pragma(#x)
+#define BSX_UNROLL(n) BSX_PRAGMA_(unroll n)
+#ifndef BSX_STAGE_MAP
+#define BSX_STAGE_MAP 0         // lanes per staged half-step: 0 = sixteen (256 contiguous bytes per half-warp), 1 = four
+#endif
 #define BSX_ROUND_HS 8           // half-steps (32 list entries each) per staging round: 2 KB of list entries per warp
 
 #include "bsx_prep.cuh"
@@ -126,6 +138,13 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 #else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void *gsrc) {   // destination as a shared-window address
+#if BSX_STAGE_64B
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(smem_addr), "l"(gsrc) : "memory");
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gsrc) : "memory");
 #endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -499,6 +518,7 @@ __device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm
 // sequential reference stops.
 __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *S) {
     const int per = BSX_RRBS(A) ? 1 : A.I;
+    const int top = 1 << (31 - __clz(per));                               // largest power of two <= per
     #pragma unroll 1
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
@@ -518,8 +538,20 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
             {   // lane t describes half-step h0 + t: its list is the first one whose running total exceeds h0 + t
                 const uint32_t target = h0 + (uint32_t)lane;
                 int k = 0; uint32_t first = 0;
+#if BSX_KSEARCH
+                // k = number of lists whose running total is <= h0 + t: binary search over the lanes that hold the totals
                 #pragma unroll 1
+                for (int st = top; st; st >>= 1) {
+                    const int idx = k + st;
+                    const uint32_t c = __shfl_sync(BSX_FULL, cum, (idx - 1) & 15);
+                    if (idx <= per && c <= target) k = idx;
+                }
+                first = __shfl_sync(BSX_FULL, cum, (k - 1) & 15);
+                if (k == 0) first = 0;
+#else
+                BSX_UNROLL(BSX_KUNROLL)
                 for (int j = 0; j < per; j++) { const uint32_t c = __shfl_sync(BSX_FULL, cum, j); if (c <= target) { k = j + 1; first = c; } }
+#endif
                 __syncwarp();                                             // the previous round's slow path may still read the schedule
                 if (lane < BSX_ROUND_HS) {
                     uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;       // padding: no entry of it is ever inside a list
@@ -533,19 +565,37 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
                 }
                 __syncwarp();
             }
-            {   // every lane copies one 16-byte pair of entries per pair of half-steps
+#if BSX_STAGE_MAP == 0
+            {   // sixteen lanes stage one half-step: 256 contiguous bytes per half-warp and copy
                 const uint32_t half = (uint32_t)lane >> 4, pr = 2u * ((uint32_t)lane & 15u);
-                const uint2 *ctx = A.ctx;
+                const char *ctx = reinterpret_cast<const char *>(A.ctx + pr);
+                uint32_t sp = (uint32_t)__cvta_generic_to_shared(&S->slot[half * 32u + pr]);
+                asm volatile("" : "+r"(sp), "+l"(ctx));                   // opaque: computed once, not rematerialised under each predicate
+                const uint4 *sc4 = reinterpret_cast<const uint4 *>(&S->sched[half]);
 #pragma unroll
                 for (uint32_t q = 0; q < BSX_ROUND_HS / 2; q++) {
-                    const uint32_t hs = 2u * q + half;
-                    const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
-                    const uint32_t g = sc.x + pr;
-                    if (g < sc.y + sc.z) cp_async16(&S->slot[hs * 32u + pr], ctx + g);
+                    const uint4 sc = sc4[4u * q];                         // sched[2q + half]
+                    if (sc.x + pr < sc.y + sc.z) cp_async16s(sp + 512u * q, ctx + (size_t)sc.x * 8u);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
             }
+#else
+            {   // four lanes stage one half-step: lane L copies the 16-byte entry pairs (L & 3) + 4j, j = 0..3, of half-step
+                // L >> 2 -- one schedule read and one address per lane, the copies differ by constants
+                static_assert(BSX_ROUND_HS == 8, "32 lanes = 8 half-steps x 4 lanes");
+                const uint32_t hs = (uint32_t)lane >> 2, e0 = 2u * ((uint32_t)lane & 3u);
+                const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
+                const uint32_t g = sc.x + e0, end = sc.y + sc.z;
+                const uint2 *gp = A.ctx + g;
+                const uint32_t sp = (uint32_t)__cvta_generic_to_shared(&S->slot[hs * 32u + e0]);
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++)
+                    if (g + 8u * j < end) cp_async16s(sp + 64u * j, gp + 8u * j);
+                cp_async_commit();
+                cp_async_wait<0>();
+            }
+#endif
             __syncwarp();
             const uint32_t nst = min((uint32_t)BSX_ROUND_HS, total_hs - h0);
             #pragma unroll 1
@@ -871,7 +921,7 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
     PrepCol *P = reinterpret_cast<PrepCol *>(base + 2 * read_sm + sizeof(SelSm));
     const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
     uint2 *hits_a = A.hit_scratch + (size_t)gw * 2 * A.hit_stride, *hits_b = hits_a + A.hit_stride;
-    uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride, *dd_b = dd_a + A.dd_stride;
+    uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride;                       // mate b: + dd_stride
     PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
     uint16_t *npairs = X->npairs;
     Ctr *C = X->ctr;
@@ -890,63 +940,84 @@ bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
       for (uint32_t pi = 0; pi < cnt; pi++) {                                 // phase B: the warp aligns the pairs one by one
         const uint32_t r = r0 + pi;
         if (C[CT_LIST] & 0x80000000u) flush_counters(A, C, lane);
-        load_image(A, Ra, scratch + (size_t)(2u * pi) * A.img_bytes, lane);
-        load_image(A, Rb, scratch + (size_t)(2u * pi + 1u) * A.img_bytes, lane);
+        // every big device function has exactly one call site (loops over the mate instead of two calls), so the
+        // kernel can be inlined whole without holding several copies of the list walk: instruction fetch was the top
+        // stall of the version that called them as functions
+        #pragma unroll 1
+        for (uint32_t mate = 0; mate < 2; mate++)
+            load_image(A, reinterpret_cast<ReadSm *>(base + mate * read_sm), scratch + (size_t)(2u * pi + mate) * A.img_bytes, lane);
         int paired = 0;
         bsx_pair_rec po;
         po.a_loc = po.a_chr = po.b_loc = po.b_chr = 0; po.insert = 0; po.npairs = 0; po.na = po.nb = po.chain = po.paired = 0;
-        if (!Ra->filtered && !Rb->filtered) {
-            // PairAlign::RunAlign (pairs.cpp:137-190)
-            if (lane < 31) npairs[lane] = 0;
-            __syncwarp();
-            const int maxi = max(Ra->rmsn, Rb->rmsn);
+        const bool both = !Ra->filtered && !Rb->filtered;
+        // both mates usable: PairAlign::RunAlign (pairs.cpp:137-190), level by level until a level pairs.  Otherwise the
+        // usable mate runs SingleAlign::RunAlign (align.cpp:435-452): its modes in turn, stopping at the first mode m
+        // that leaves a hit at level <= m
+        const int maxi = both ? max(Ra->rmsn, Rb->rmsn) : max(Ra->filtered ? -1 : Ra->seedseg - 1, Rb->filtered ? -1 : Rb->seedseg - 1);
+        uint32_t done = (Ra->filtered ? 1u : 0u) | (Rb->filtered ? 2u : 0u);      // mates that take no further SnpAlign call
+        if (lane < 31) npairs[lane] = 0;
+        __syncwarp();
+        #pragma unroll 1
+        for (int i = 0; i <= maxi && !paired; i++) {
             #pragma unroll 1
-            for (int i = 0; i <= maxi && !paired; i++) {
-                if (i < Ra->seedseg) snp_align(A, Ra, hits_a, dd_a, 1, i, lane, C, reinterpret_cast<StageSm *>(P));
-                if (i < Rb->seedseg) snp_align(A, Rb, hits_b, dd_b, 1, i, lane, C, reinterpret_cast<StageSm *>(P));
-                if (i <= Ra->rmsn) { sort_hits(hits_a + ((size_t)i * 2) * W1, Ra->nh[i], lane); sort_hits(hits_a + ((size_t)i * 2 + 1) * W1, Ra->nc[i], lane); }
-                if (i <= Rb->rmsn) { sort_hits(hits_b + ((size_t)i * 2) * W1, Rb->nh[i], lane); sort_hits(hits_b + ((size_t)i * 2 + 1) * W1, Rb->nc[i], lane); }
-                __syncwarp();
-                int n = 0;
-                if (lane == 0) {
-                    n = get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, i, i);
-                    for (int j = 0; j < i; j++) { n += get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, i, j);
-                                                  n += get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, j, i); }
+            for (uint32_t mate = 0; mate < 2; mate++) {
+                if ((done >> mate) & 1u) continue;
+                ReadSm *R = reinterpret_cast<ReadSm *>(base + mate * read_sm);
+                if (i < R->seedseg) {
+                    snp_align(A, R, hits_a + mate * A.hit_stride, dd_a + mate * A.dd_stride, 1, i, lane, C, reinterpret_cast<StageSm *>(P));
+                    if (!both && !BSX_RRBS(A) && R->best <= i) done |= 1u << mate;   // a bucket <= i is non-empty (align.cpp:448)
                 }
-                n = __shfl_sync(BSX_FULL, n, 0);
-                if (n > 0) paired = i + 1;
+            }
+            if (!both) continue;
+            #pragma unroll 1
+            for (uint32_t q = 0; q < 4; q++) {                               // SortHits4PE: level i of both mates, both chains
+                const ReadSm *R = reinterpret_cast<const ReadSm *>(base + (q >> 1) * read_sm);
+                if (i <= R->rmsn) sort_hits(hits_a + (q >> 1) * A.hit_stride + ((size_t)i * 2 + (q & 1u)) * W1, (q & 1u) ? R->nc[i] : R->nh[i], lane);
             }
             __syncwarp();
-            if (paired && lane == 0) {
-                // StringAlignPair (pairs.cpp:222-242)
+            int n = 0;
+            if (lane == 0) {
                 #pragma unroll 1
-                for (int i = 0; i <= A.v * 2; i++) {
-                    const int np = npairs[i];
-                    if (!np) continue;
-                    int j = -1;
-                    if (np == 1) j = 0;
-                    else if (A.r == 1) j = (int)(bsx_myrand(Ra->index, A.randseed) % (uint32_t)np);
-                    if (j >= 0) {
-                        const PairHitDev ph = pairs[(size_t)i * W1 + j];
-                        po.a_chr = ph.a_chr; po.a_loc = ph.a_loc; po.b_chr = ph.b_chr; po.b_loc = ph.b_loc; po.insert = ph.insert;
-                        po.npairs = (uint32_t)np; po.chain = (uint8_t)(ph.meta & 0xff); po.na = (uint8_t)((ph.meta >> 8) & 0xff);
-                        po.nb = (uint8_t)((ph.meta >> 16) & 0xff); po.paired = 1;
-                    }
-                    break;
+                for (int t = 0; t <= 2 * i; t++) {                           // (i,i), then (i,j), (j,i) for j < i
+                    const int j = (t - 1) >> 1;
+                    n += get_pairs(A, Ra, Rb, hits_a, hits_b, pairs, npairs, (t == 0 || (t & 1)) ? i : j, (t == 0 || !(t & 1)) ? i : j);
                 }
             }
-        } else {
-            if (!Ra->filtered) run_align(A, Ra, hits_a, dd_a, 1, lane, C, reinterpret_cast<StageSm *>(P));
-            if (!Rb->filtered) run_align(A, Rb, hits_b, dd_b, 1, lane, C, reinterpret_cast<StageSm *>(P));
+            n = __shfl_sync(BSX_FULL, n, 0);
+            if (n > 0) paired = i + 1;
+        }
+        __syncwarp();
+        if (paired && lane == 0) {
+            // StringAlignPair (pairs.cpp:222-242)
+            #pragma unroll 1
+            for (int i = 0; i <= A.v * 2; i++) {
+                const int np = npairs[i];
+                if (!np) continue;
+                int j = -1;
+                if (np == 1) j = 0;
+                else if (A.r == 1) j = (int)(bsx_myrand(Ra->index, A.randseed) % (uint32_t)np);
+                if (j >= 0) {
+                    const PairHitDev ph = pairs[(size_t)i * W1 + j];
+                    po.a_chr = ph.a_chr; po.a_loc = ph.a_loc; po.b_chr = ph.b_chr; po.b_loc = ph.b_loc; po.insert = ph.insert;
+                    po.npairs = (uint32_t)np; po.chain = (uint8_t)(ph.meta & 0xff); po.na = (uint8_t)((ph.meta >> 8) & 0xff);
+                    po.nb = (uint8_t)((ph.meta >> 16) & 0xff); po.paired = 1;
+                }
+                break;
+            }
         }
         const int out_paired = __shfl_sync(BSX_FULL, (int)po.paired, 0);
-        if (!out_paired && BSX_RRBS(A)) {
-            if (lane == 0) { if (!Ra->filtered) fix_unpaired_short(A, Ra,  hits_a); if (!Rb->filtered) fix_unpaired_short(A, Rb,  hits_b); }
-            __syncwarp();
-        }
         if (lane == 0) A.out_pair[r] = po;
-        write_unpaired(A, Ra,  hits_a, A.out_a + r, A.cnt_a ? A.cnt_a + (size_t)r * 16 : nullptr, lane);
-        write_unpaired(A, Rb,  hits_b, A.out_b + r, A.cnt_b ? A.cnt_b + (size_t)r * 16 : nullptr, lane);
+        #pragma unroll 1
+        for (uint32_t mate = 0; mate < 2; mate++) {
+            ReadSm *R = reinterpret_cast<ReadSm *>(base + mate * read_sm);
+            uint2 *hits = hits_a + mate * A.hit_stride;
+            if (!out_paired && BSX_RRBS(A)) {
+                if (lane == 0 && !R->filtered) fix_unpaired_short(A, R, hits);
+                __syncwarp();
+            }
+            uint16_t *cnt16 = mate ? A.cnt_b : A.cnt_a;
+            write_unpaired(A, R, hits, (mate ? A.out_b : A.out_a) + r, cnt16 ? cnt16 + (size_t)r * 16 : nullptr, lane);
+        }
         if (out_paired) CTR_ADD(C, CT_MAPPED, 1);
         __syncwarp();
       }
