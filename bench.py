@@ -543,7 +543,7 @@ def main():
     bytes_per_unit = mates * 2 * ((L + 3) // 4) + 12 * p_per + c_per * (4 + L / 4) + 32
     kernel_s = (ms * 1e-3) / a.steps
     achieved = bytes_per_unit * n / kernel_s / 1e9
-    kname = "bsx_map_pe_kernel" if pe else ("bsx_map_se_rrbs_kernel" if kind == "rrbs" else
+    kname = ("bsx_map_pe_rrbs_kernel" if kind == "rrbs" else "bsx_map_pe_wgbs_kernel") if pe else ("bsx_map_se_rrbs_kernel" if kind == "rrbs" else
                                             ("bsx_map_se_wide_kernel" if cfg["opts"].get("v", 2) >= 8 else "bsx_map_se_wgbs_kernel"))
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_unit": bytes_per_unit,

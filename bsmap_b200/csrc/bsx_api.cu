@@ -357,7 +357,10 @@ int bsx_launch_map_se_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_launch_map_se_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_map_occupancy_se_wide(size_t smem);   // bsx_map_se_wide.cu
 int bsx_launch_map_se_wide(const MapArgs &a, int n_ctas, cudaStream_t st);
-int bsx_map_occupancy_pe(size_t smem);   // bsx_map_pe.cu
+int bsx_map_occupancy_pe_wgbs(size_t smem);   // bsx_map_pe.cu
+int bsx_map_occupancy_pe_rrbs(size_t smem);   // bsx_map_pe_rrbs.cu
+int bsx_launch_map_pe_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
+int bsx_launch_map_pe_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 
 static void slot_free(bsx_slot &s) {
     cudaFree(s.d_seq_a); cudaFree(s.d_seq_b); cudaFree(s.d_len_a); cudaFree(s.d_len_b); cudaFree(s.d_out_a); cudaFree(s.d_out_b);
@@ -435,7 +438,8 @@ static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, 
     const size_t smem_se = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot);
     const bool wide = !p->rrbs && p->max_snp_num >= BSX_WIDE_CTX_V && ix->d_ctx2;
     int occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem_se) : (wide ? bsx_map_occupancy_se_wide(smem_se) : bsx_map_occupancy_se_wgbs(smem_se));
-    int occ_pe = bsx_map_occupancy_pe(bsx_cta_smem_bytes(2, m->plan_cap, m->nslot));
+    const size_t smem_pe = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot);
+    int occ_pe = p->rrbs ? bsx_map_occupancy_pe_rrbs(smem_pe) : bsx_map_occupancy_pe_wgbs(smem_pe);
     if (occ_se < 1 || occ_pe < 1) { bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
     const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;
@@ -535,7 +539,7 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;
-    int rc = pe ? bsx_launch_map_pe(a, m->n_ctas_pe, st)
+    int rc = pe ? (a.rrbs ? bsx_launch_map_pe_rrbs(a, m->n_ctas_pe, st) : bsx_launch_map_pe_wgbs(a, m->n_ctas_pe, st))
                 : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st)
                           : (a.ctx2 ? bsx_launch_map_se_wide(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st)));
     if (rc == BSX_OK && m->meth && !s.packed) {

@@ -122,4 +122,3 @@ static inline size_t bsx_image_bytes(int plan_cap, int nslot) {
     return sizeof(ImgHdr) + (size_t)nslot * (2 * BSX_FIXWORDS * 4 + (size_t)plan_cap * sizeof(uint4));
 }
 
-int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st);

@@ -43,6 +43,11 @@
 #define BSX_SE_OCC bsx_map_occupancy_se
 #define BSX_SE_LAUNCH bsx_launch_map_se
 #endif
+#ifndef BSX_PE_KERNEL
+#define BSX_PE_KERNEL bsx_map_pe_kernel
+#define BSX_PE_OCC bsx_map_occupancy_pe
+#define BSX_PE_LAUNCH bsx_launch_map_pe
+#endif
 #ifndef BSX_CALLS
 #define BSX_CALLS 1             // 1: big device functions are real calls (small binary), 0: everything inlined
 #endif
@@ -907,7 +912,7 @@ __device__ void fix_unpaired_short(const MapArgs &A, ReadSm *R, uint2 *hits) {
 #define BSX_PE_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(BSX_WARPS_PER_CTA * 32, BSX_PE_MIN_CTAS)
-bsx_map_pe_kernel(const __grid_constant__ MapArgs A) {
+BSX_PE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t read_sm = A.read_smem;
@@ -1055,23 +1060,23 @@ int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
 #endif
 
 #ifdef BSX_BUILD_PE
-int bsx_map_occupancy_pe(size_t smem) {
+int BSX_PE_OCC(size_t smem) {
     int occ = 0;
-    cudaError_t e = cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsx_map_pe_kernel, BSX_WARPS_PER_CTA * 32, smem);
+    cudaError_t e = cudaFuncSetAttribute(BSX_PE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, BSX_PE_KERNEL, BSX_WARPS_PER_CTA * 32, smem);
     if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
     return occ;
 }
-int bsx_launch_map_pe(const MapArgs &a, int n_ctas, cudaStream_t st) {
+int BSX_PE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
     const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot);
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
     BSX_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= BSX_MAX_DEVICES || smem > configured[dev].load(std::memory_order_relaxed)) {
-        BSX_CUDA_CHECK(cudaFuncSetAttribute(bsx_map_pe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BSX_CUDA_CHECK(cudaFuncSetAttribute(BSX_PE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < BSX_MAX_DEVICES) configured[dev].store(smem, std::memory_order_relaxed);
     }
-    bsx_map_pe_kernel<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
+    BSX_PE_KERNEL<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
     BSX_CUDA_CHECK(cudaGetLastError());
     return BSX_OK;
 }

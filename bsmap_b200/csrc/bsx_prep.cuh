@@ -81,7 +81,7 @@ __device__ __forceinline__ void pack_chain(const uint8_t *sq, uint32_t stride, i
 
 // TrimAdapter (align.cpp:371-425): adapters in -A order, positions ascending, first success wins
 __device__ int trim_adapter(const MapArgs &A, const uint8_t *sq, int len) {
-    const int s = A.s, tail = A.rrbs ? 5 : 4;
+    const int s = A.s, tail = BSX_RRBS(A) ? 5 : 4;
     #pragma unroll 1
     for (int a = 0; a < A.n_adapter; a++) {
         const int al = A.adapter_len[a];
@@ -94,7 +94,7 @@ __device__ int trim_adapter(const MapArgs &A, const uint8_t *sq, int len) {
                 if (m0 > 4) break;
             }
             bool ok = false;
-            if (!A.rrbs) ok = (k >= m0 * 5 && k > 3);
+            if (!BSX_RRBS(A)) ok = (k >= m0 * 5 && k > 3);
             else if (k >= m0 * 5) {
                 // digestion-site remnant just before the adapter (align.cpp:383-404)
                 const int sl = A.site_len, dp = A.digest_pos;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void pack_chain_packed(const uint8_t *pk, uint32_t ma
 // TrimAdapter on a packed slot.  Adapters and the digestion site are upper-case ACGT (checked on the host), so
 // "characters differ" is "invalid base or different code".
 __device__ int trim_adapter_packed(const MapArgs &A, const uint8_t *pk, int len) {
-    const int s = A.s, tail = A.rrbs ? 5 : 4;
+    const int s = A.s, tail = BSX_RRBS(A) ? 5 : 4;
     const uint32_t mo = A.pk_mask_off;
     #pragma unroll 1
     for (int a = 0; a < A.n_adapter; a++) {
@@ -178,7 +178,7 @@ __device__ int trim_adapter_packed(const MapArgs &A, const uint8_t *pk, int len)
                 if (m0 > 4) break;
             }
             bool ok = false;
-            if (!A.rrbs) ok = (k >= m0 * 5 && k > 3);
+            if (!BSX_RRBS(A)) ok = (k >= m0 * 5 && k > 3);
             else if (k >= m0 * 5) {
                 const int sl = A.site_len, dp = A.digest_pos;
                 int m = m0, m2 = m0;
@@ -236,7 +236,7 @@ __device__ __forceinline__ uint32_t probe_rrbs_size(const MapArgs &A, uint32_t k
 __device__ __forceinline__ int select_seeds(const MapArgs &A, const PrepSm *K, const uint32_t *rw, int len, int seg, int chain,
                             uint4 *plan, uint32_t *dbg) {
     const int s = A.s, I = A.I;
-    const bool rrbs = A.rrbs != 0;
+    const bool rrbs = BSX_RRBS(A) != 0;                                           // fixed at compile time in the specialised kernels
     const int mo = (rrbs || len - I + 1 < 0) ? 0 : (int)K->remof[len - I + 1];   // max_offset = (len-I+1) % s
     const int cso = (rrbs && chain) ? (int)K->remof[len] : 0;                     // cseed_offset (RRBS rc chain)
     const int lim = I - 1 + mo;
