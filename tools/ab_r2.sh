@@ -1,3 +1,4 @@
-CFG=cfg3 bash tools/ab_bench.sh pe_ku4 2>&1 | grep -v "^$"
-CFG=cfg2 bash tools/ab_bench.sh se_ku4 2>&1 | grep -v "^$"
-bash tools/ncu_kernel.sh r2d_pe cfg3 bsx_map_pe 2000000
+CFG=cfg2 bash tools/ab_bench.sh se_pf1 se_pf2 2>&1 | grep -v "^$"
+grep -o '"value_ascii_resident": [0-9.]*' gpurun_out/b_main.log
+CFG=cfg3 bash tools/ab_bench.sh pe_pf2 2>&1 | grep -v "^$"
+bash tools/ncu_se.sh r2e
