@@ -628,7 +628,8 @@ static int map_host(bsx_mapper *m, bool pe, uint32_t n, const char *sa, const ui
     while (done < n) {
         const int si = k & 1;
         cudaStream_t st = m->slot[si].stream;
-        const uint32_t nb = std::min(m->max_batch, n - done);
+        // the first sub-batch is small: its upload is the one copy no kernel hides
+        const uint32_t nb = std::min(k == 0 && n > m->max_batch ? std::max(m->max_batch / 8u, 1u) : m->max_batch, n - done);
         BSX_CUDA_CHECK(cudaStreamSynchronize(st));    // slot free again
         int rc = upload_slot(m, si, nb, sa + (size_t)done * slot_bytes, la + done, sb ? sb + (size_t)done * slot_bytes : nullptr,
                              lb ? lb + done : nullptr, st, packed);

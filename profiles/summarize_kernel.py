@@ -13,6 +13,9 @@ for i, n in enumerate(h):
     except ValueError:
         val[n] = v[i]; continue
     val[n] = x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "Tbyte": 1e12, "Gbyte/s": 1e9, "Tbyte/s": 1e12, "Mbyte/s": 1e6}.get(u[i], 1)
+    if n == "gpu__time_duration.sum":   # keep the table in the report's unit, the rate in seconds
+        dur_s = x * {"s": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "second": 1.0, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9}.get(u[i], 1e-9)
+        dur_unit = u[i]
 W = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
      "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
      "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
@@ -29,14 +32,15 @@ per = {"dram_bytes_per_unit": (val.get("dram__bytes_read.sum", 0) + val.get("dra
        "dram_read_bytes_per_unit": val.get("dram__bytes_read.sum", 0) / units, "dram_write_bytes_per_unit": val.get("dram__bytes_write.sum", 0) / units,
        "warp_instructions_per_unit": val.get("smsp__inst_executed.sum", 0) / units, "l2_read_sectors_per_unit": val.get("lts__t_sectors_srcunit_tex_op_read.sum", 0) / units,
        "global_load_sectors_per_request": ld_s / ld_r if ld_r else None,
-       "units_per_second_under_ncu": units / (val.get("gpu__time_duration.sum", 1) * 1e-9) if val.get("gpu__time_duration.sum") else None}
+       "units_per_second_under_ncu": units / dur_s if val.get("gpu__time_duration.sum") else None}
 json.dump({"kernel": kname, "units_in_capture": units, "metrics": out, "derived": per}, open(os.path.join(HERE, tag + ".json"), "w"), indent=1)
 with open(os.path.join(HERE, tag + ".md"), "w") as f:
     f.write(f"# ncu --set full: {title}\n\nkernel `{kname}`, {units:.0f} units in the captured launch (`--clock-control none`; cold-cache, serialised: shares, not absolutes)\n\n| metric | value |\n|---|---|\n")
     for k in W:
         if k in val:
             x = val[k]
-            f.write(f"| {k} | {x:,.3f} |\n" if isinstance(x, float) else f"| {k} | {x} |\n")
+            label = f"{k} ({dur_unit})" if k == "gpu__time_duration.sum" else k
+            f.write(f"| {label} | {x:,.3f} |\n" if isinstance(x, float) else f"| {label} | {x} |\n")
     f.write("\n| derived | value |\n|---|---|\n")
     for k, x in per.items():
         f.write(f"| {k} | {x:,.2f} |\n" if x is not None else f"| {k} | n/a |\n")
