@@ -165,7 +165,7 @@ class Index:
         i = self.info
         which = {"refcat": (0, i.n_words), "crefcat": (1, i.n_words), "anchor": (2, i.n_seq + 1),
                  "tab": (3, i.n_tab), "pos": (4, i.n_entries), "tag": (5, i.n_entries),
-                 "ctx": (6, 2 * i.n_entries), "ctx2": (7, 2 * i.n_entries)}[what]
+                 "ctx": (6, i.ctx_words * i.n_entries)}[what]
         out = np.empty(int(which[1]), dtype=np.uint32)
         check(load().bsx_index_download(self.h, which[0], out.ctypes.data, out.nbytes))
         return out

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbsmap_b200.so")
 CLI = os.path.join(HERE, "bsmap")
 METH_CLI = os.path.join(HERE, "methratio")
-SOURCES = ["bsx_index.cu", "bsx_map_se.cu", "bsx_map_se_wide.cu", "bsx_map_se_rrbs.cu", "bsx_map_pe.cu", "bsx_map_pe_rrbs.cu", "bsx_api.cu", "bsx_meth.cu", "bsx_format.cpp", "bsx_reads.cpp", "bsx_bam.cpp", "bsx_cli.cpp", "bsx_methratio_cli.cpp"]
+SOURCES = ["bsx_index.cu", "bsx_map_se.cu", "bsx_map_se_wide.cu", "bsx_map_se_rrbs.cu", "bsx_map_pe.cu", "bsx_map_pe_rrbs.cu", "bsx_map_pe_wide.cu", "bsx_api.cu", "bsx_meth.cu", "bsx_format.cpp", "bsx_reads.cpp", "bsx_bam.cpp", "bsx_cli.cpp", "bsx_methratio_cli.cpp"]
 HEADERS = ["bsx_common.cuh", "bsx_prep.cuh", "bsx_internal.h", "bsx_map.cuh", "bsx_map_impl.cuh", os.path.join("..", "..", "include", "bsmap_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

@@ -207,6 +207,7 @@ extern "C" int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info) {
     info->n_words = ix->n_words; info->n_keys = ix->n_keys; info->n_entries = ix->n_entries;
     info->n_seq = ix->n_seq; info->device = ix->device; info->build_seconds = ix->build_seconds;
     info->n_tab = ix->ref_only ? 0 : bsx_tab_len(ix);
+    info->ctx_words = ix->ref_only ? 0u : (uint32_t)(bsx_ctx_entry_bytes(ix) / 4);
     return BSX_OK;
 }
 extern "C" const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k) { return (ix && k < ix->n_seq) ? ix->names[k].c_str() : ""; }
@@ -228,8 +229,7 @@ extern "C" int bsx_index_download(const bsx_index *ix, int what, void *dst, size
         case 3: src = ix->d_tab; have = bsx_tab_len(ix) * 4; break;
         case 4: src = ix->d_pos; have = ix->n_entries * 4; break;
         case 5: src = ix->d_tag; have = ix->d_tag ? ix->n_entries * 4 : 0; break;
-        case 6: src = ix->d_ctx; have = ix->d_ctx ? ix->n_entries * 8 : 0; break;
-        case 7: src = ix->d_ctx2; have = ix->d_ctx2 ? ix->n_entries * 8 : 0; break;
+        case 6: src = ix->d_ctx; have = ix->d_ctx ? ix->n_entries * bsx_ctx_entry_bytes(ix) : 0; break;
         default: bsx_set_error("bsx_index_download: unknown array %d", what); return BSX_ERR_ARG;
     }
     if (bytes > have) { bsx_set_error("bsx_index_download: asked %zu bytes, array has %zu", bytes, have); return BSX_ERR_ARG; }
@@ -244,8 +244,8 @@ extern "C" int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t
     ptrs[2] = ix->d_tab; bytes[2] = bsx_tab_len(ix) * 4;
     ptrs[3] = ix->d_pos; bytes[3] = ix->n_entries * 4;
     ptrs[4] = ix->d_tag; bytes[4] = ix->d_tag ? ix->n_entries * 4 : 0;
-    ptrs[5] = ix->d_ctx; bytes[5] = ix->d_ctx ? ix->n_entries * 8 : 0;
-    ptrs[6] = ix->d_ctx2; bytes[6] = ix->d_ctx2 ? ix->n_entries * 8 : 0;
+    ptrs[5] = ix->d_ctx; bytes[5] = ix->d_ctx ? ix->n_entries * bsx_ctx_entry_bytes(ix) : 0;
+    ptrs[6] = nullptr; bytes[6] = 0;    // (round 1 kept the outer context bases in a second array)
     return 7;
 }
 
@@ -358,6 +358,8 @@ int bsx_launch_map_se_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_map_occupancy_se_wide(size_t smem);   // bsx_map_se_wide.cu
 int bsx_launch_map_se_wide(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_map_occupancy_pe_wgbs(size_t smem);   // bsx_map_pe.cu
+int bsx_map_occupancy_pe_wide(size_t smem);   // bsx_map_pe_wide.cu
+int bsx_launch_map_pe_wide(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_map_occupancy_pe_rrbs(size_t smem);   // bsx_map_pe_rrbs.cu
 int bsx_launch_map_pe_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
 int bsx_launch_map_pe_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
@@ -435,11 +437,12 @@ static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, 
     m->nslot = p->chains ? 2 : 1;
     int sms = 0;
     BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    const size_t smem_se = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot);
-    const bool wide = !p->rrbs && p->max_snp_num >= BSX_WIDE_CTX_V && ix->d_ctx2;
+    // the kernel follows the index layout: an index built with -v >= 8 holds 16-byte context entries whatever -v the mapper uses
+    const bool wide = !p->rrbs && ix->ctx_wide;
+    const size_t smem_se = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot, wide);
     int occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem_se) : (wide ? bsx_map_occupancy_se_wide(smem_se) : bsx_map_occupancy_se_wgbs(smem_se));
-    const size_t smem_pe = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot);
-    int occ_pe = p->rrbs ? bsx_map_occupancy_pe_rrbs(smem_pe) : bsx_map_occupancy_pe_wgbs(smem_pe);
+    const size_t smem_pe = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot, wide);
+    int occ_pe = p->rrbs ? bsx_map_occupancy_pe_rrbs(smem_pe) : (wide ? bsx_map_occupancy_pe_wide(smem_pe) : bsx_map_occupancy_pe_wgbs(smem_pe));
     if (occ_se < 1 || occ_pe < 1) { bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
     const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;
@@ -471,7 +474,7 @@ static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, 
     MapArgs &a = m->base;
     memset(&a, 0, sizeof a);
     a.refcat = ix->d_refcat; a.crefcat = ix->d_crefcat; a.tab = ix->d_tab; a.pos = ix->d_pos; a.tag = ix->d_tag; a.ctx = ix->d_ctx;
-    a.ctx2 = p->max_snp_num >= BSX_WIDE_CTX_V ? ix->d_ctx2 : nullptr;   // an index built for a smaller -v simply has none
+    a.ctx_wide = ix->ctx_wide ? 1 : 0;
     a.seqinfo = ix->d_seqinfo; a.sites = ix->d_sites; a.site_off = ix->d_site_off; a.n_seq = ix->n_seq;
     a.s = p->seed_size; a.I = p->index_interval; a.v = p->max_snp_num; a.W = p->max_num_hits; a.r = p->report_repeat_hits;
     a.min_insert = p->min_insert; a.max_insert = p->max_insert; a.chains = p->chains; a.pairend = p->pairend; a.rrbs = p->rrbs;
@@ -539,9 +542,10 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;
-    int rc = pe ? (a.rrbs ? bsx_launch_map_pe_rrbs(a, m->n_ctas_pe, st) : bsx_launch_map_pe_wgbs(a, m->n_ctas_pe, st))
+    int rc = pe ? (a.rrbs ? bsx_launch_map_pe_rrbs(a, m->n_ctas_pe, st)
+                          : (a.ctx_wide ? bsx_launch_map_pe_wide(a, m->n_ctas_pe, st) : bsx_launch_map_pe_wgbs(a, m->n_ctas_pe, st)))
                 : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st)
-                          : (a.ctx2 ? bsx_launch_map_se_wide(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st)));
+                          : (a.ctx_wide ? bsx_launch_map_se_wide(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st)));
     if (rc == BSX_OK && m->meth && !s.packed) {
         rc = bsx_meth_pile_mapped(m->meth, &m->meth_opts, m->meth_sam, m->par.report_repeat_hits, n, pe ? 2 : 1, m->stride,
                                   s.d_seq_a, s.d_seq_b, s.d_out_a, s.d_out_b, s.d_out_pair, st);

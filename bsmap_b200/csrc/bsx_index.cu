@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32)
 radix_scatter_ctx_kernel(const uint64_t *__restrict__ in, uint64_t n, int shift, int bits, uint32_t n_sub,
                          const uint32_t *__restrict__ offs, const uint32_t *__restrict__ refcat,
                          const uint32_t *__restrict__ crefcat, int seed_size, uint32_t *__restrict__ out_pos,
-                         uint2 *__restrict__ out_ctx, uint2 *__restrict__ out_ctx2) {
+                         uint2 *__restrict__ out_ctx, uint4 *__restrict__ out_ctx16) {
     __shared__ uint32_t sh[RS_WARPS][1 << RS_MAX_BITS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t sub = blockIdx.x * RS_WARPS + wid;
@@ -294,17 +294,17 @@ radix_scatter_ctx_kernel(const uint64_t *__restrict__ in, uint64_t n, int shift,
             const uint32_t before = __funnelshift_l(m[(bb >> 4) + 1], m[bb >> 4], (bb & 15u) * 2u);
             const uint32_t after = __funnelshift_l(m[(aa >> 4) + 1], m[aa >> 4], (aa & 15u) * 2u);
             out_pos[dst] = c;
-            out_ctx[dst] = make_uint2(before, after);
-            if (out_ctx2) {   // the next 16 bases outwards: [c-32, c-16) and [c+s+16, c+s+32)
+            if (!out_ctx16) out_ctx[dst] = make_uint2(before, after);
+            else {            // indexes built for -v >= 8: the next 16 bases outwards as well, [c-32, c-16) and [c+s+16, c+s+32)
                 const uint32_t b2 = c - 32u, a2 = aa + 16u;
-                out_ctx2[dst] = make_uint2(__funnelshift_l(m[(b2 >> 4) + 1], m[b2 >> 4], (b2 & 15u) * 2u),
-                                           __funnelshift_l(m[(a2 >> 4) + 1], m[a2 >> 4], (a2 & 15u) * 2u));
+                out_ctx16[dst] = make_uint4(__funnelshift_l(m[(b2 >> 4) + 1], m[b2 >> 4], (b2 & 15u) * 2u), before, after,
+                                            __funnelshift_l(m[(a2 >> 4) + 1], m[a2 >> 4], (a2 & 15u) * 2u));
             }
         }
     }
 }
 
-struct bsx_ctx_out { const uint32_t *refcat, *crefcat; int seed_size; uint2 *ctx, *ctx2; };
+struct bsx_ctx_out { const uint32_t *refcat, *crefcat; int seed_size; uint2 *ctx; uint4 *ctx16; };
 
 static int radix_sort_items(uint64_t *d_a, uint64_t *d_b, uint64_t n, int key_bits, uint32_t *d_out32, cudaStream_t st,
                             const bsx_ctx_out *cx = nullptr) {
@@ -327,7 +327,7 @@ static int radix_sort_items(uint64_t *d_a, uint64_t *d_b, uint64_t n, int key_bi
         if (rc) { cudaFree(d_hist); return rc; }
         if (p == passes - 1 && cx)
             radix_scatter_ctx_kernel<<<grid, RS_WARPS * 32, 0, st>>>(src, n, shift, bits, n_sub, d_hist, cx->refcat, cx->crefcat,
-                                                                      cx->seed_size, d_out32, cx->ctx, cx->ctx2);
+                                                                      cx->seed_size, d_out32, cx->ctx, cx->ctx16);
         else if (p == passes - 1)
             radix_scatter_kernel<uint32_t><<<grid, RS_WARPS * 32, 0, st>>>(src, n, shift, bits, n_sub, d_hist, d_out32);
         else
@@ -375,9 +375,9 @@ static void unmask_region(const char *seq, uint32_t len, uint32_t id, uint32_t T
 void bsx_index_free_device(bsx_index *ix) {
     if (ix->device >= 0) cudaSetDevice(ix->device);
     cudaFree(ix->d_refcat); cudaFree(ix->d_crefcat); cudaFree(ix->d_tab); cudaFree(ix->d_pos);
-    cudaFree(ix->d_tag); cudaFree(ix->d_seqinfo); cudaFree(ix->d_sites); cudaFree(ix->d_site_off); cudaFree(ix->d_ctx); cudaFree(ix->d_ctx2);
+    cudaFree(ix->d_tag); cudaFree(ix->d_seqinfo); cudaFree(ix->d_sites); cudaFree(ix->d_site_off); cudaFree(ix->d_ctx);
     ix->d_refcat = ix->d_crefcat = ix->d_tab = ix->d_pos = ix->d_tag = ix->d_seqinfo = ix->d_sites = ix->d_site_off = nullptr;
-    ix->d_ctx = ix->d_ctx2 = nullptr;
+    ix->d_ctx = nullptr;
 }
 
 static int upload_seqinfo(bsx_index *ix) {
@@ -404,9 +404,9 @@ int bsx_index_alloc_device(bsx_index *ix) {
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_crefcat, ix->n_words * 4));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_tab, bsx_tab_len(ix) * 4));
     BSX_CUDA_CHECK(cudaMalloc(&ix->d_pos, (ix->n_entries + 64) * 4));
-    BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (ix->n_entries + 64) * sizeof(uint2)));
+    ix->ctx_wide = !ix->par.rrbs && ix->par.max_snp_num >= BSX_WIDE_CTX_V;
+    BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (ix->n_entries + 64) * bsx_ctx_entry_bytes(ix)));
     if (ix->par.rrbs) BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, (ix->n_entries + 64) * 4));
-    else if (ix->par.max_snp_num >= BSX_WIDE_CTX_V) BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx2, (ix->n_entries + 64) * sizeof(uint2)));
     return upload_seqinfo(ix);
 }
 
@@ -579,13 +579,10 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
         if (rc) return rc;
         int key_bits = 1; while ((1ull << key_bits) < ix->n_keys) key_bits++;
         if (!p.rrbs) {
-            BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (n_items + 64) * sizeof(uint2)));
-            BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, (n_items + 64) * sizeof(uint2), st));
-            if (p.max_snp_num >= BSX_WIDE_CTX_V) {
-                BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx2, (n_items + 64) * sizeof(uint2)));
-                BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx2, 0, (n_items + 64) * sizeof(uint2), st));
-            }
-            bsx_ctx_out cx = {ix->d_refcat, ix->d_crefcat, s, ix->d_ctx, ix->d_ctx2};
+            ix->ctx_wide = p.max_snp_num >= BSX_WIDE_CTX_V;
+            BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (n_items + 64) * bsx_ctx_entry_bytes(ix)));
+            BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, (n_items + 64) * bsx_ctx_entry_bytes(ix), st));
+            bsx_ctx_out cx = {ix->d_refcat, ix->d_crefcat, s, ix->ctx_wide ? nullptr : (uint2 *)ix->d_ctx, ix->ctx_wide ? (uint4 *)ix->d_ctx : nullptr};
             rc = radix_sort_items(d_a, d_b, n_items, key_bits, ix->d_pos, st, &cx);
             if (rc) return rc;
         } else {
@@ -598,7 +595,7 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
             BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, (n_items + 64) * sizeof(uint2)));
             BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, (n_items + 64) * sizeof(uint2), st));
             rrbs_gather_kernel<<<grid, 256, 0, st>>>(d_order, d_rl, d_rt, n_items, ix->d_refcat, ix->d_crefcat, ix->d_seqinfo, s,
-                                                     ix->d_pos, ix->d_tag, ix->d_ctx);
+                                                     ix->d_pos, ix->d_tag, (uint2 *)ix->d_ctx);
             BSX_CUDA_CHECK(cudaGetLastError());
             BSX_CUDA_CHECK(cudaStreamSynchronize(st));
             cudaFree(d_order); cudaFree(d_rl); cudaFree(d_rt);
@@ -606,8 +603,9 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
         cudaFree(d_a); cudaFree(d_b);
     } else {
         if (p.rrbs) { BSX_CUDA_CHECK(cudaMalloc(&ix->d_tag, 64 * 4)); BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_tag, 0, 64 * 4, st)); }
-        BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, 64 * sizeof(uint2)));
-        BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, 64 * sizeof(uint2), st));
+        ix->ctx_wide = !p.rrbs && p.max_snp_num >= BSX_WIDE_CTX_V;
+        BSX_CUDA_CHECK(cudaMalloc(&ix->d_ctx, 64 * 16));
+        BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_ctx, 0, 64 * 16, st));
     }
     cudaEventRecord(ev1, st);
     BSX_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -27,8 +27,9 @@ struct bsx_index {
     uint32_t *d_refcat = nullptr, *d_crefcat = nullptr;   // 2-bit packed strands, margins zeroed
     uint32_t *d_tab = nullptr;      // bsx_tab_len(): WGBS [2k] list start, [2k+1] start of rc part, [2k+2] end; RRBS CSR over (key, group)
     uint32_t *d_pos = nullptr;      // n_entries positions (ref_anchor + p), lists fwd-ascending then rc-ascending
-    uint2 *d_ctx = nullptr;         // per entry the 16 reference bases before the seed (.x) and the 16 after it (.y)
-    uint2 *d_ctx2 = nullptr;        // WGBS, -v >= BSX_WIDE_CTX_V only: the next 16 bases outwards on either side
+    void *d_ctx = nullptr;          // inline context per entry: uint2 {the 16 reference bases before the seed, the 16 after it}, or,
+                                    // when ctx_wide, uint4 {bases -32..-17, -16..-1, +s..+s+15, +s+16..+s+31}
+    bool ctx_wide = false;          // WGBS index built with -v >= BSX_WIDE_CTX_V: 16-byte context entries
     uint32_t *d_tag = nullptr;      // RRBS: Hit.chr tag per entry
     uint32_t *d_seqinfo = nullptr;  // anchor[n_seq+1] | size[n_seq] | rc_offset[n_seq]
     uint32_t *d_sites = nullptr;    // RRBS: all digestion sites, concatenated
@@ -45,6 +46,8 @@ static inline uint32_t bsx_rrbs_groups(int seed_size) { return 2u * (uint32_t)((
 static inline uint64_t bsx_tab_len(const bsx_index *ix) {
     return ix->par.rrbs ? ix->n_keys * bsx_rrbs_groups(ix->par.seed_size) + 1 : 2 * ix->n_keys + 1;
 }
+
+static inline size_t bsx_ctx_entry_bytes(const bsx_index *ix) { return ix->ctx_wide ? 16 : 8; }
 
 struct bsx_mapper;
 

@@ -9,8 +9,9 @@
 struct MapArgs {
     // RefSeq
     const uint32_t *refcat, *crefcat, *tab, *pos, *tag, *seqinfo;
-    const uint2 *ctx;             // inline context per entry: 16 bases before / after the seed   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
-    const uint2 *ctx2;            // wide context (the next 16 bases outwards), NULL unless -v >= BSX_WIDE_CTX_V
+    const void *ctx;              // inline context per entry: uint2 {16 bases before, 16 after the seed}; wide indexes (-v >= BSX_WIDE_CTX_V):
+                                  // uint4 {bases -32..-17, -16..-1, +s..+s+15, +s+16..+s+31}   // seqinfo: anchor[n+1] | size[n] | rc_offset[n]
+    int ctx_wide;                 // 1: 16-byte context entries (the wide kernels)
     const uint32_t *sites, *site_off;
     uint32_t n_seq;
     // Param
@@ -61,8 +62,8 @@ struct ImgHdr {
 static_assert(sizeof(ImgHdr) == 16, "image header is one uint4");
 
 // The read a warp is aligning, in shared memory: expanded from the image by load_image.  Followed by
-// uint4 plan[nslot][plan_cap] and uint4 flank[nslot][plan_cap]: read bases / mask facing the inline context before
-// (x,y) and after (z,w) the seed of each plan entry.
+// uint4 plan[nslot][plan_cap] and uint4 flank[nslot][plan_cap][FW]: read bases / mask facing the inline context before
+// (x,y) and after (z,w) the seed of each plan entry (FW = 1; wide indexes FW = 2: the inner 16+16 bases, then the outer).
 struct ReadSm {
     uint32_t rw[2][BSX_FIXWORDS];     // 2-bit read, chain 0 = as is, 1 = reverse complement (bseq/cbseq)
     uint32_t m5[2][BSX_FIXWORDS];     // 01 per ACGT base (reg/creg & 0x5555...)
@@ -100,19 +101,19 @@ struct CtaSm {
 };
 static_assert(sizeof(CtaSm) % 16 == 0, "per-warp shared memory follows CtaSm and holds uint4");
 
-static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int nslot) {
-    return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * 2u * sizeof(uint4);
+static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int nslot, int wide) {
+    return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * (wide ? 3u : 2u) * sizeof(uint4);
 }
-static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
-    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot) + sizeof(SelSm) + sizeof(PrepCol);
+static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide) {
+    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot, wide) + sizeof(SelSm) + sizeof(PrepCol);
 }
-static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot) {
-    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot) * BSX_WARPS_PER_CTA;
+static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide) {
+    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot, wide) * BSX_WARPS_PER_CTA;
 }
 
 static inline void bsx_map_args_derive(MapArgs &a) {
-    a.read_smem = (uint32_t)bsx_read_smem_bytes(a.plan_cap, a.nslot);
-    a.warp_smem_se = (uint32_t)bsx_warp_smem_bytes(1, a.plan_cap, a.nslot);
+    a.read_smem = (uint32_t)bsx_read_smem_bytes(a.plan_cap, a.nslot, a.ctx_wide);
+    a.warp_smem_se = (uint32_t)bsx_warp_smem_bytes(1, a.plan_cap, a.nslot, a.ctx_wide);
     a.chain_stride = a.nslot == 2 ? (uint32_t)a.plan_cap : 0u;
     a.flank_off = (uint32_t)(a.nslot * a.plan_cap);
     a.img_slot = (uint32_t)(2 * BSX_FIXWORDS * 4 + a.plan_cap * sizeof(uint4));

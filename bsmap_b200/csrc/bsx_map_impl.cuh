@@ -34,9 +34,15 @@
 #ifndef BSX_RRBS
 #define BSX_RRBS(A) ((A).rrbs)
 #endif
-// wide inline context (-v >= 8) likewise: the hot list loop of the standard kernel must not carry its registers
+// wide inline context (indexes built for -v >= 8: 16-byte entries with 32 + 32 context bases): a compile-time constant of
+// the translation unit
 #ifndef BSX_WIDE
-#define BSX_WIDE(A) ((A).ctx2 != nullptr)
+#error "the translation unit fixes BSX_WIDE(A) to 0 or 1"
+#endif
+#if BSX_WIDE(0)
+#define BSX_FW 2                // uint4 per plan entry in the flank array
+#else
+#define BSX_FW 1
 #endif
 #ifndef BSX_SE_KERNEL
 #define BSX_SE_KERNEL bsx_map_se_kernel
@@ -56,9 +62,6 @@
 #else
 #define BSX_FN __forceinline__
 #endif
-#ifndef BSX_STREAM_NOALLOC
-#define BSX_STREAM_NOALLOC 1    // list entries bypass L1 (measured +2 %: L1 keeps the prepare phase's local arrays)
-#endif
 #ifndef BSX_COOP_FULL
 #define BSX_COOP_FULL 4         // n > 0: up to n phase-0/1 survivors of a step are counted cooperatively, two per round trip
 #endif
@@ -77,7 +80,11 @@
 #ifndef BSX_STAGE_MAP
 #define BSX_STAGE_MAP 0         // lanes per staged half-step: 0 = sixteen (256 contiguous bytes per half-warp), 1 = four
 #endif
+#if BSX_WIDE(0)
+#define BSX_ROUND_HS 4           // 16-byte entries: the same 2 KB of list entries per warp and round
+#else
 #define BSX_ROUND_HS 8           // half-steps (32 list entries each) per staging round: 2 KB of list entries per warp
+#endif
 
 #include "bsx_prep.cuh"
 
@@ -94,7 +101,7 @@ __device__ __forceinline__ uint4 *plan_of(ReadSm *R, int chain, const MapArgs &A
     return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + chain * A.chain_stride;
 }
 __device__ __forceinline__ uint4 *flank_of(ReadSm *R, int chain, const MapArgs &A) {
-    return plan_of(R, chain, A) + A.flank_off;
+    return reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(R) + sizeof(ReadSm)) + A.flank_off + chain * A.chain_stride * BSX_FW;
 }
 
 // 16 bases of the read from offset `off` (may start before the read or run past it): (bases, valid mask)
@@ -112,25 +119,10 @@ __device__ __forceinline__ uint2 read_window(const ReadSm *R, int chain, int off
 // equal -- the same decision as XM((q & XC(s)) ^ s) & r (param.h:126,139-147, bsx_mm_word_bits) in four instead of six
 // operations per word, and the two words of a candidate share one popcount.
 __device__ __forceinline__ uint32_t flank_mask(uint32_t q, uint32_t m5) { return m5 | ((m5 & ~(q & (q >> 1))) << 1); }
-__device__ __forceinline__ uint32_t ctx_mm(uint32_t q, uint32_t M, uint32_t s) {
-    const uint32_t u = (q ^ s) & M;
-    return (uint32_t)__popc((u | (u >> 1)) & 0x55555555u);
-}
 // f = {q before, M before, q after, M after}, c = {16 bases before the seed, 16 after}
 __device__ __forceinline__ uint32_t ctx_mm2(const uint4 f, const uint2 c) {
     const uint32_t ub = (f.x ^ c.x) & f.y, ua = (f.z ^ c.y) & f.w;
     return (uint32_t)__popc(((ub | (ub >> 1)) & 0x55555555u) | ((ua | (ua << 1)) & 0xAAAAAAAAu));
-}
-
-// list entries are read once: keep them out of L1, which holds the prepare phase's per-lane arrays (local memory)
-__device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
-#if BSX_STREAM_NOALLOC
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
 }
 
 // Asynchronous 16-byte copy global -> shared (LDGSTS, bypasses L1 and the register file): the warp requests the heads
@@ -221,7 +213,11 @@ __device__ __forceinline__ void load_image(const MapArgs &A, ReadSm *R, const ui
             for (int t = lane; t < used; t += 32) {
                 const int p = (int)(pl[t].w & 0xffffu);
                 const uint2 wb = read_window(R, chain, p - 16), wa = read_window(R, chain, p + A.s);
-                fl[t] = make_uint4(wb.x, flank_mask(wb.x, wb.y), wa.x, flank_mask(wa.x, wa.y));
+                fl[t * BSX_FW] = make_uint4(wb.x, flank_mask(wb.x, wb.y), wa.x, flank_mask(wa.x, wa.y));
+#if BSX_WIDE(0)
+                const uint2 wb2 = read_window(R, chain, p - 32), wa2 = read_window(R, chain, p + A.s + 16);
+                fl[t * BSX_FW + 1] = make_uint4(wb2.x, flank_mask(wb2.x, wb2.y), wa2.x, flank_mask(wa2.x, wa2.y));
+#endif
             }
         }
     }
@@ -466,23 +462,39 @@ __device__ BSX_FN int extend_and_commit(const MapArgs &A, ReadSm *R, uint2 *hits
 }
 
 // Per-warp staging area of the packed list walk; aliases the prepare phase's PrepCol (idle while the warp aligns).
+#if BSX_WIDE(0)
+typedef uint4 CtxEntry;                 // {bases -32..-17, -16..-1 before the seed, +0..+15, +16..+31 after it}
+#else
+typedef uint2 CtxEntry;                 // {16 bases before the seed, 16 after it}
+#endif
 struct HalfStep {                       // 32 consecutive entries of one position list
-    uint32_t src, lo, cnt, k;           // first entry index (even), list start, list length (0: padding), list number within the mode
-    uint32_t qb, Mb, qa, Ma;            // the read bases / flank_mask that face the list's inline context before / after the seed
+    uint4 d;                            // first entry index, list start, list length (0: padding), list number within the mode
+    uint4 f;                            // the read bases / flank_mask that face the list's inline context before / after the seed
+#if BSX_WIDE(0)
+    uint4 f2;                           // the same for the outer 16 + 16 bases
+#endif
 };
 struct StageSm {
-    uint2 slot[BSX_ROUND_HS * 32];      // one round of BSX_ROUND_HS half-steps x 32 entries {16 bases before, 16 after the seed}
+    CtxEntry slot[BSX_ROUND_HS * 32];   // one round of BSX_ROUND_HS half-steps x 32 entries
     HalfStep sched[BSX_ROUND_HS];
 };
 static_assert(sizeof(StageSm) <= sizeof(PrepCol), "the staging area must fit in the idle PrepCol");
-static_assert(sizeof(HalfStep) == 32, "two uint4");
 static_assert(BSX_ROUND_HS % 2 == 0 && BSX_ROUND_HS <= 32, "half-steps are evaluated in pairs; one lane describes one half-step");
+
+// mismatches among the read bases that face one entry's inline context: a lower bound of CountMismatch
+__device__ __forceinline__ uint32_t ctx_count(const HalfStep &h, const CtxEntry c) {
+#if BSX_WIDE(0)
+    return ctx_mm2(h.f, make_uint2(c.y, c.z)) + ctx_mm2(h.f2, make_uint2(c.x, c.w));
+#else
+    return ctx_mm2(h.f, c);
+#endif
+}
 
 // SnpAlign returned at lane `xl` of half-step `cur` of the current round: the candidates the sequential reference has
 // visited are the lists before this one and this list up to the exiting entry; everything else that was requested
 // in this round is over-fetch, the rounds that were never requested do not count at all.
 __device__ __noinline__ void packed_exit(const uint4 *plan, int per, StageSm *S, uint32_t cur, uint32_t xl, int lane, Ctr *C) {
-    const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[cur]);
+    const uint4 sc = S->sched[cur].d;
     uint32_t nk = 0;
     if (lane < per) { const uint4 el = plan[lane]; nk = el.z - el.x; }
     const uint32_t all = __reduce_add_sync(BSX_FULL, nk);
@@ -490,7 +502,7 @@ __device__ __noinline__ void packed_exit(const uint4 *plan, int per, StageSm *S,
     const uint32_t counted = before + (sc.x + xl - sc.y) + 1u;
     uint32_t extra = 0;                                                   // entries of this round behind the exiting one
     if (lane < BSX_ROUND_HS && (uint32_t)lane >= cur) {
-        const uint4 t = *reinterpret_cast<const uint4 *>(&S->sched[lane]);
+        const uint4 t = S->sched[lane].d;
         uint32_t lo_i = max(t.x, t.y);
         const uint32_t hi_i = min(t.x + 32u, t.y + t.z);
         if ((uint32_t)lane == cur) lo_i = max(lo_i, t.x + xl + 1u);
@@ -512,10 +524,12 @@ __device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm
 
 // SnpAlign for one mode (align.cpp:168-347), lists staged through shared memory.
 // The position lists of the mode (WGBS: its I sub-seeds; RRBS: the one (segment, mirror) group of its key) are cut into
-// half-steps of 32 entries -- a list starts a new half-step, at the even entry index at or before its first entry, so
-// that every copy is a 16-byte cp.async -- and the half-steps of all lists form one schedule that is fetched in rounds
-// of BSX_ROUND_HS and evaluated two half-steps = 64 candidates at a time: one DRAM round trip per round instead of one per
-// list.  Lane t of the warp describes half-step t of the round (which list, where it starts, the read bases that face
+// half-steps of 32 entries -- a list starts a new half-step (8-byte entries: at the even entry index at or before its
+// first entry, so that every copy is a 16-byte cp.async) -- and the half-steps of all lists form one schedule that is
+// fetched in rounds of BSX_ROUND_HS and evaluated two half-steps = 64 candidates at a time: one DRAM round trip per round
+// instead of one per list.  Indexes built for -v >= 8 carry 16-byte entries (32 + 32 context bases): 32 bases let a fifth
+// of config 5's candidates through; the first design kept the outer bases in a second array read by survivors only,
+// which cost one dependent random access per 64-candidate step.  Lane t of the warp describes half-step t of the round (which list, where it starts, the read bases that face
 // its context); within a half-step the list is warp-uniform, so a candidate costs one 8-byte shared-memory load, eight
 // logic operations, one popcount and a compare.  The fast path does not even test whether a staged entry belongs to
 // the list: stale or foreign entries can only raise a false alarm, which the slow path masks out.  Candidates are
@@ -527,11 +541,11 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
     #pragma unroll 1
     for (int chain = 0; chain < 2; chain++) {
         if (chain == 0 ? !R->fc : !R->cc) continue;
-        const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per;
+        const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per * BSX_FW;
         uint4 e = make_uint4(0u, 0u, 0u, 0u);                             // lane k < per owns list k: {start, rc start, end, p | segment << 16}
         if (lane < per) e = plan[lane];
         const uint32_t n = e.z - e.x;
-        uint32_t cum = n ? (n + (e.x & 1u) + 31u) >> 5 : 0u;             // half-steps of my list -> inclusive scan over the lists
+        uint32_t cum = n ? (n + (BSX_WIDE(A) ? 0u : (e.x & 1u)) + 31u) >> 5 : 0u;   // half-steps of my list -> inclusive scan over the lists
         #pragma unroll 1
         for (int d = 1; d < per; d <<= 1) { const uint32_t t = __shfl_up_sync(BSX_FULL, cum, d); if (lane >= d) cum += t; }
         const uint32_t total_hs = __shfl_sync(BSX_FULL, cum, per - 1);
@@ -559,27 +573,45 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
 #endif
                 __syncwarp();                                             // the previous round's slow path may still read the schedule
                 if (lane < BSX_ROUND_HS) {
-                    uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;       // padding: no entry of it is ever inside a list
+                    HalfStep h;                                           // padding: no entry of it is ever inside a list
+                    h.d = h.f = make_uint4(0u, 0u, 0u, 0u);
+#if BSX_WIDE(0)
+                    h.f2 = h.d;
+#endif
                     if (k < per) {
                         const uint4 ek = plan[k];
-                        d0 = make_uint4((ek.x & ~1u) + 32u * (target - first), ek.x, ek.z - ek.x, (uint32_t)k);
-                        d1 = flank[k];
+                        h.d = make_uint4((BSX_WIDE(A) ? ek.x : (ek.x & ~1u)) + 32u * (target - first), ek.x, ek.z - ek.x, (uint32_t)k);
+                        h.f = flank[k * BSX_FW];
+#if BSX_WIDE(0)
+                        h.f2 = flank[k * BSX_FW + 1];
+#endif
                     }
-                    uint4 *d4 = reinterpret_cast<uint4 *>(&S->sched[lane]);
-                    d4[0] = d0; d4[1] = d1;
+                    S->sched[lane] = h;
                 }
                 __syncwarp();
             }
-#if BSX_STAGE_MAP == 0
+#if BSX_WIDE(0)
+            {   // 16-byte entries: lane L stages entry L of every half-step of the round (512 contiguous bytes per copy)
+                const char *ctx = reinterpret_cast<const char *>(A.ctx) + 16u * (uint32_t)lane;
+                uint32_t sp = (uint32_t)__cvta_generic_to_shared(&S->slot[lane]);
+                asm volatile("" : "+r"(sp), "+l"(ctx));                   // opaque: computed once, not rematerialised under each predicate
+#pragma unroll
+                for (uint32_t q = 0; q < BSX_ROUND_HS; q++) {
+                    const uint4 sc = S->sched[q].d;
+                    if (sc.x + (uint32_t)lane < sc.y + sc.z) cp_async16s(sp + 512u * q, ctx + (size_t)sc.x * 16u);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+            }
+#elif BSX_STAGE_MAP == 0
             {   // sixteen lanes stage one half-step: 256 contiguous bytes per half-warp and copy
                 const uint32_t half = (uint32_t)lane >> 4, pr = 2u * ((uint32_t)lane & 15u);
-                const char *ctx = reinterpret_cast<const char *>(A.ctx + pr);
+                const char *ctx = reinterpret_cast<const char *>(A.ctx) + 8u * pr;
                 uint32_t sp = (uint32_t)__cvta_generic_to_shared(&S->slot[half * 32u + pr]);
                 asm volatile("" : "+r"(sp), "+l"(ctx));                   // opaque: computed once, not rematerialised under each predicate
-                const uint4 *sc4 = reinterpret_cast<const uint4 *>(&S->sched[half]);
 #pragma unroll
                 for (uint32_t q = 0; q < BSX_ROUND_HS / 2; q++) {
-                    const uint4 sc = sc4[4u * q];                         // sched[2q + half]
+                    const uint4 sc = S->sched[2u * q + half].d;
                     if (sc.x + pr < sc.y + sc.z) cp_async16s(sp + 512u * q, ctx + (size_t)sc.x * 8u);
                 }
                 cp_async_commit();
@@ -590,9 +622,9 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
                 // L >> 2 -- one schedule read and one address per lane, the copies differ by constants
                 static_assert(BSX_ROUND_HS == 8, "32 lanes = 8 half-steps x 4 lanes");
                 const uint32_t hs = (uint32_t)lane >> 2, e0 = 2u * ((uint32_t)lane & 3u);
-                const uint4 sc = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
+                const uint4 sc = S->sched[hs].d;
                 const uint32_t g = sc.x + e0, end = sc.y + sc.z;
-                const uint2 *gp = A.ctx + g;
+                const uint2 *gp = reinterpret_cast<const uint2 *>(A.ctx) + g;
                 const uint32_t sp = (uint32_t)__cvta_generic_to_shared(&S->slot[hs * 32u + e0]);
 #pragma unroll
                 for (uint32_t j = 0; j < 4; j++)
@@ -605,14 +637,11 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
             const uint32_t nst = min((uint32_t)BSX_ROUND_HS, total_hs - h0);
             #pragma unroll 1
             for (uint32_t hs = 0; hs < nst; hs += 2) {
-                const uint4 f0 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 1);
-                const uint4 f1 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 3);
-                const uint2 cx0 = S->slot[hs * 32u + lane], cx1 = S->slot[hs * 32u + 32u + lane];
-                bool pass0 = ctx_mm2(f0, cx0) <= thres, pass1 = ctx_mm2(f1, cx1) <= thres;
+                bool pass0 = ctx_count(S->sched[hs], S->slot[hs * 32u + lane]) <= thres;
+                bool pass1 = ctx_count(S->sched[hs + 1], S->slot[hs * 32u + 32u + lane]) <= thres;
                 if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
                 // ---- slow path: some staged entry passed the inline-context filter; is it a candidate at all?
-                const uint4 s0 = *reinterpret_cast<const uint4 *>(&S->sched[hs]);
-                const uint4 s1 = *(reinterpret_cast<const uint4 *>(&S->sched[hs]) + 2);
+                const uint4 s0 = S->sched[hs].d, s1 = S->sched[hs + 1].d;
                 pass0 &= (s0.x + (uint32_t)lane - s0.y) < s0.z;                                  // inside the list (unsigned; padding has length 0)
                 pass1 &= (s1.x + (uint32_t)lane - s1.y) < s1.z;
                 const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
@@ -638,78 +667,9 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
     return 0;
 }
 
-// SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early.
-// Indexes built for -v >= 8 (wide context) walk the I position lists of the mode one by one with direct loads, in the
-// reference's order (sub-seed 0's forward entries, its rc entries, sub-seed 1's, ...), 64 table entries per step; their
-// lists run to thousands of entries, so the next step's context is requested before this one is evaluated.
+// SnpAlign (align.cpp:168-347) for one mode; returns 1 if it `return`ed early
 __device__ BSX_FN int snp_align(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *stage) {
-    if (!BSX_WIDE(A)) return snp_align_packed(A, R, hits, dd, store_all, mode, lane, C, stage);
-    const int per = A.I;
-    for (int chain = 0; chain < 2; chain++) {
-        if (chain == 0 ? !R->fc : !R->cc) continue;
-        const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per;
-        uint32_t tbl = 0; bool have_tbl = false;
-        uint32_t visited = 0, counted = 0;                               // list entries loaded / reference-visible candidates
-        int ret = 0;
-        #pragma unroll 1
-        for (int i = 0; i < per && !ret; i++) {
-            const uint4 e = plan[i];                                     // {list start, rc start, list end, p | segment << 16}
-            if (e.x == e.z) continue;                                    // index2[_seed] == NULL
-            const uint32_t p = e.w & 0xffffu;
-            const uint4 f = flank[i];                                    // read bases / masks facing the inline context (load_image)
-            // phase 0 = mismatches among the <= 32 read bases that face the entry's inline context (8 bytes that arrive
-            // with the list stream).  It is a lower bound of CountMismatch, so `> snp_thres` rejects exactly like the
-            // reference; pos[] and the reference are only touched by survivors.
-            uint32_t thres = R->thres, c0 = e.x, exit_pos = 0;
-            uint32_t rb2 = 0, Mb2 = 0, ra2 = 0, Ma2 = 0; bool have_f2 = false;     // wide-context flanks of this list, set up on first use
-            uint2 nx0 = make_uint2(0, 0), nx1 = make_uint2(0, 0);
-            if (c0 + lane < e.z) nx0 = ld_stream(A.ctx + c0 + lane);
-            if (c0 + lane + 32 < e.z) nx1 = ld_stream(A.ctx + c0 + lane + 32);
-            for (; c0 < e.z; c0 += 64) {
-                const uint32_t i0 = c0 + lane, i1 = i0 + 32;
-                const uint2 cx0 = nx0, cx1 = nx1;
-                if (i0 + 64 < e.z) nx0 = ld_stream(A.ctx + i0 + 64);
-                if (i1 + 64 < e.z) nx1 = ld_stream(A.ctx + i1 + 64);
-                bool pass0 = i0 < e.z && ctx_mm2(f, cx0) <= thres, pass1 = i1 < e.z && ctx_mm2(f, cx1) <= thres;
-                if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
-                // phase 0b: with many mismatches allowed 32 context bases let a fifth of the candidates through; the
-                // next 16 bases on either side, stored in a second array that only these survivors read, are tested
-                // before any of them touches the reference
-                if (!have_f2) {
-                    const uint2 wb = read_window(R, chain, (int)p - 32), wa = read_window(R, chain, (int)p + A.s + 16);
-                    rb2 = wb.x; Mb2 = flank_mask(wb.x, wb.y); ra2 = wa.x; Ma2 = flank_mask(wa.x, wa.y); have_f2 = true;
-                }
-                if (pass0) {
-                    const uint2 c2 = __ldg(A.ctx2 + i0);
-                    pass0 = ctx_mm2(f, cx0) + ctx_mm(rb2, Mb2, c2.x) + ctx_mm(ra2, Ma2, c2.y) <= thres;
-                }
-                if (pass1) {
-                    const uint2 c2 = __ldg(A.ctx2 + i1);
-                    pass1 = ctx_mm2(f, cx1) + ctx_mm(rb2, Mb2, c2.x) + ctx_mm(ra2, Ma2, c2.y) <= thres;
-                }
-                if (!__any_sync(BSX_FULL, pass0 || pass1)) continue;
-                const unsigned pm0 = __ballot_sync(BSX_FULL, pass0), pm1 = __ballot_sync(BSX_FULL, pass1);
-                // phase 1 (one aligned 16-byte gather per survivor) only pays when phase 0 lets many through
-                const int use_p1 = __popc(pm0) + __popc(pm1) > 2;
-                if (use_p1 && !have_tbl) { tbl = mode_chunk_table(A, R, chain, plan, per, lane); have_tbl = true; }
-#pragma unroll 1
-                for (int h = 0; h < 2; h++) {                        // one call site: the slow path exists once in the binary
-                    if (h ? pm1 : pm0) {
-                        const int rc = extend_and_commit(A, R, hits, dd, store_all, chain, mode, h ? pass1 : pass0, c0 + 32u * h, e.y, p, tbl, use_p1, lane, C);
-                        if (rc & 1) { ret = 1; exit_pos = (c0 - e.x) + 32u * h + (uint32_t)(rc >> 8) + 1u; break; }
-                    }
-                }
-                if (ret) break;
-                thres = R->thres;
-            }
-            if (!ret) { visited += e.z - e.x; counted += e.z - e.x; }
-            else { visited += min(c0 + 64u, e.z) - e.x; counted += exit_pos; }
-        }
-        // candidates the sequential reference visits = list entries - over-fetch (entries evaluated past an exit point)
-        if (lane == 0) { C[CT_LIST] += visited; if (ret) C[CT_OVER] += visited - counted; }
-        if (ret) return 1;
-    }
-    return 0;
+    return snp_align_packed(A, R, hits, dd, store_all, mode, lane, C, stage);
 }
 
 // SingleAlign::RunAlign (align.cpp:435-452): the mode loop (everything before it happened in the prepare kernel)
@@ -1044,7 +1004,7 @@ int BSX_SE_OCC(size_t smem) {
     return occ;
 }
 int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot);
+    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot, BSX_WIDE(a));
     // the attribute belongs to (function, device): one cache slot per device, several mappers / host threads may launch
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
@@ -1068,7 +1028,7 @@ int BSX_PE_OCC(size_t smem) {
     return occ;
 }
 int BSX_PE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot);
+    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot, BSX_WIDE(a));
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
     BSX_CUDA_CHECK(cudaGetDevice(&dev));

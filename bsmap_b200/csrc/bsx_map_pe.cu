@@ -4,7 +4,7 @@
 #define BSX_BUILD_PE 1
 #define BSX_CALLS 0
 #define BSX_RRBS(A) 0
-#define BSX_WIDE(A) 0          // the wide-context phase costs the pairing kernel 10 % in registers; pairs at -v >= 8 use 32 bases
+#define BSX_WIDE(A) 0          // 8-byte context entries; indexes built for -v >= 8 take bsx_map_pe_wide.cu
 #define BSX_PE_KERNEL bsx_map_pe_wgbs_kernel
 #define BSX_PE_OCC bsx_map_occupancy_pe_wgbs
 #define BSX_PE_LAUNCH bsx_launch_map_pe_wgbs

@@ -1,5 +1,5 @@
-// bsx_map_se_wide.cu -- the single-end WGBS kernel for -v >= 8: candidates that pass the 32-base inline context are
-// tested against the next 16 bases on either side (bsx_index::d_ctx2) before they touch the reference.
+// bsx_map_se_wide.cu -- the single-end WGBS kernel for indexes built with -v >= 8: 16-byte context entries (32 + 32 bases
+// around the seed) staged and tested in one go, where 32 bases would let a fifth of config 5's candidates through.
 #define BSX_BUILD_SE 1
 #define BSX_CALLS 0
 #define BSX_RRBS(A) 0

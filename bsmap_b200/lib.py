@@ -31,7 +31,7 @@ class Params(C.Structure):
 
 class IndexInfo(C.Structure):
     _fields_ = [("n_words", C.c_uint64), ("n_keys", C.c_uint64), ("n_entries", C.c_uint64),
-                ("n_seq", C.c_uint32), ("device", C.c_int32), ("build_seconds", C.c_double), ("n_tab", C.c_uint64)]
+                ("n_seq", C.c_uint32), ("device", C.c_int32), ("build_seconds", C.c_double), ("n_tab", C.c_uint64), ("ctx_words", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -89,6 +89,8 @@ typedef struct bsx_index_info {
     int32_t  device;
     double   build_seconds;   /* device time of pack + key + sort + table kernels */
     uint64_t n_tab;      /* u32 entries of the seed table: 2*n_keys+1 (WGBS), n_keys*groups+1 (RRBS, see below) */
+    uint32_t ctx_words;  /* u32 per inline-context entry: 2, or 4 for a WGBS index built with -v >= 8             */
+    uint32_t pad_;
 } bsx_index_info;
 
 /* work counters accumulated by the mapping kernels */
@@ -132,16 +134,16 @@ int bsx_index_get_info(const bsx_index *ix, bsx_index_info *info);
 const char *bsx_index_seq_name(const bsx_index *ix, uint32_t k);
 uint32_t bsx_index_seq_size(const bsx_index *ix, uint32_t k);
 /* copy a device array to the host (parity tests): what = 0 refcat, 1 crefcat, 2 anchors (n_seq+1),
- * 3 tab (info.n_tab), 4 pos (n_entries), 5 RRBS tags (n_entries), 6 inline context (n_entries x 2 u32:
- * the 16 reference bases before and the 16 after each entry's seed), 7 wide context (the next 16 bases outwards on
- * either side; WGBS indexes built with -v >= 8).
+ * 3 tab (info.n_tab), 4 pos (n_entries), 5 RRBS tags (n_entries), 6 inline context (n_entries x info.ctx_words u32:
+ * the 16 reference bases before and the 16 after each entry's seed; WGBS indexes built with -v >= 8 hold four words per
+ * entry -- bases -32..-17, -16..-1 before the seed, +0..+15, +16..+31 after it).
  * RRBS (-D): the reference keeps one list per key and SnpAlign skips the entries whose (segment, mirrored) tag is not
  * the mode's (dbseq.cpp:418-438, align.cpp:187,229).  Here every list is stored partitioned by that tag -- group g =
  * 2*segment + mirrored, each group in the reference's order -- and tab is the CSR over (key, group):
  * tab[key*groups + g] .. tab[key*groups + g + 1], groups = 2 * (144 / seed_size). */
 int bsx_index_download(const bsx_index *ix, int what, void *dst, size_t bytes);
 /* device pointers + byte sizes of the arrays a replica needs (one-time NVLink broadcast):
- * order refcat, crefcat, tab, pos, tag, ctx, ctx2 (NULL/0 when absent).  Returns the count written (cap >= 7). */
+ * order refcat, crefcat, tab, pos, tag, ctx, (unused: NULL/0).  Returns the count written (cap >= 7). */
 int bsx_index_device_buffers(const bsx_index *ix, void **ptrs, size_t *bytes, int cap);
 /* replica on another device: allocates there and copies over NVLink with cudaMemcpyPeer */
 int bsx_index_replicate(const bsx_index *src, int device, bsx_index **out);

@@ -67,10 +67,10 @@ def test_index_equals_the_oracles_own_build(world, golden):
     info = ix.info
     assert (info.n_words, info.n_keys, info.n_entries) == (golden["n_words"], golden["n_keys"], golden["n_entries"])
     exp = golden["arrays"]
-    bufs = ix.device_buffers()      # refcat, crefcat, tab, pos, tag, ctx, ctx2
+    bufs = ix.device_buffers()      # refcat, crefcat, tab, pos, tag, ctx
     assert SC.sha(ix.download("anchor")) == exp["anchor"]
     with ThreadPoolExecutor(8) as pool:
-        for name, k, per_entry in (("refcat", 0, 0), ("crefcat", 1, 0), ("tab", 2, 0), ("pos", 3, 4), ("ctx", 5, 8), ("ctx2", 6, 8)):
+        for name, k, per_entry in (("refcat", 0, 0), ("crefcat", 1, 0), ("tab", 2, 0), ("pos", 3, 4)):
             ptr, nbytes = bufs[k]
             assert ptr and nbytes, name
             if per_entry:
@@ -80,6 +80,19 @@ def test_index_equals_the_oracles_own_build(world, golden):
             else:
                 got = _digest_device_array(torch, dev, ptr, nbytes, nbytes, pool)[0]
                 assert got == exp[name], f"{name} differs from the oracle's build"
+        # the index is built with -v >= 8: 16-byte context entries {outer before, before, after, outer after}.  The oracle's
+        # digests are of the inner pair ("ctx") and the outer pair ("ctx2") as separate arrays: split on the host.
+        assert info.ctx_words == 4
+        ptr, nbytes = bufs[5]
+        view = torch.as_tensor(_DevBuf(ptr, nbytes), device=dev).view(torch.int32).view(-1, 4)
+        step = golden["chunk"]
+        futs = []
+        for lo in range(0, view.shape[0], step):
+            c = view[lo:lo + step].cpu().numpy().view(np.uint32)
+            futs.append((pool.submit(SC.sha, np.ascontiguousarray(c[:, 1:3])), pool.submit(SC.sha, np.ascontiguousarray(c[:, [0, 3]]))))
+        got_in, got_out = [a.result() for a, _ in futs], [b.result() for _, b in futs]
+        assert got_in == exp["ctx"], "inner context differs from the oracle's build"
+        assert got_out == exp["ctx2"], "outer context differs from the oracle's build"
 
 
 def _map_se(world, w, want_counts=True):
