@@ -339,6 +339,7 @@ struct bsx_mapper {
     bsx_params par{};
     uint32_t max_batch = 0, stride = 0;
     int n_ctas_se = 0, n_ctas_pe = 0, plan_cap = 0, nslot = 1;
+    int warps_se = BSX_WARPS_PER_CTA, warps_pe = BSX_WARPS_PER_CTA;   // warps per CTA (fewer when the plan of a read is large)
     uint32_t hit_stride = 0, dd_stride = 0, pair_stride = 0;
     bool pe_ready = false;
     bsx_slot slot[2];
@@ -351,18 +352,18 @@ struct bsx_mapper {
     int meth_sam = 1;
 };
 
-int bsx_map_occupancy_se_wgbs(size_t smem);   // bsx_map_se.cu
-int bsx_map_occupancy_se_rrbs(size_t smem);   // bsx_map_se_rrbs.cu
-int bsx_launch_map_se_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
-int bsx_launch_map_se_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
-int bsx_map_occupancy_se_wide(size_t smem);   // bsx_map_se_wide.cu
-int bsx_launch_map_se_wide(const MapArgs &a, int n_ctas, cudaStream_t st);
-int bsx_map_occupancy_pe_wgbs(size_t smem);   // bsx_map_pe.cu
-int bsx_map_occupancy_pe_wide(size_t smem);   // bsx_map_pe_wide.cu
-int bsx_launch_map_pe_wide(const MapArgs &a, int n_ctas, cudaStream_t st);
-int bsx_map_occupancy_pe_rrbs(size_t smem);   // bsx_map_pe_rrbs.cu
-int bsx_launch_map_pe_wgbs(const MapArgs &a, int n_ctas, cudaStream_t st);
-int bsx_launch_map_pe_rrbs(const MapArgs &a, int n_ctas, cudaStream_t st);
+int bsx_map_occupancy_se_wgbs(size_t smem, int warps);   // bsx_map_se.cu
+int bsx_map_occupancy_se_rrbs(size_t smem, int warps);   // bsx_map_se_rrbs.cu
+int bsx_launch_map_se_wgbs(const MapArgs &a, int n_ctas, int warps, cudaStream_t st);
+int bsx_launch_map_se_rrbs(const MapArgs &a, int n_ctas, int warps, cudaStream_t st);
+int bsx_map_occupancy_se_wide(size_t smem, int warps);   // bsx_map_se_wide.cu
+int bsx_launch_map_se_wide(const MapArgs &a, int n_ctas, int warps, cudaStream_t st);
+int bsx_map_occupancy_pe_wgbs(size_t smem, int warps);   // bsx_map_pe.cu
+int bsx_map_occupancy_pe_wide(size_t smem, int warps);   // bsx_map_pe_wide.cu
+int bsx_launch_map_pe_wide(const MapArgs &a, int n_ctas, int warps, cudaStream_t st);
+int bsx_map_occupancy_pe_rrbs(size_t smem, int warps);   // bsx_map_pe_rrbs.cu
+int bsx_launch_map_pe_wgbs(const MapArgs &a, int n_ctas, int warps, cudaStream_t st);
+int bsx_launch_map_pe_rrbs(const MapArgs &a, int n_ctas, int warps, cudaStream_t st);
 
 static void slot_free(bsx_slot &s) {
     cudaFree(s.d_seq_a); cudaFree(s.d_seq_b); cudaFree(s.d_len_a); cudaFree(s.d_len_b); cudaFree(s.d_out_a); cudaFree(s.d_out_b);
@@ -384,7 +385,7 @@ extern "C" int bsx_mapper_destroy(bsx_mapper *m) {
 static int alloc_pe(bsx_mapper *m) {
     // second mate + pair buckets: allocated on first paired-end use
     if (m->pe_ready) return BSX_OK;
-    const size_t warps = (size_t)m->n_ctas_pe * BSX_WARPS_PER_CTA;
+    const size_t warps = (size_t)m->n_ctas_pe * m->warps_pe;
     const uint32_t W1 = (uint32_t)m->par.max_num_hits + 1, lv = (uint32_t)m->par.max_snp_num + 1;
     for (int i = 0; i < 2; i++) {
         bsx_slot &s = m->slot[i];
@@ -395,7 +396,7 @@ static int alloc_pe(bsx_mapper *m) {
         BSX_CUDA_CHECK(cudaMalloc(&s.d_out_pair, (size_t)m->max_batch * sizeof(bsx_pair_rec)));
         // all-level hit storage for both mates replaces the SE scratch
         cudaFree(s.d_hits); cudaFree(s.d_dd); s.d_hits = nullptr; s.d_dd = nullptr;
-        const size_t se_warps = (size_t)m->n_ctas_se * BSX_WARPS_PER_CTA;
+        const size_t se_warps = (size_t)m->n_ctas_se * m->warps_se;
         const size_t hit_elems = std::max(warps * 2 * (size_t)(lv * 2 * W1), se_warps * (size_t)(2 * W1));
         const size_t dd_elems = std::max(warps * 2, se_warps) * (size_t)m->dd_stride;
         BSX_CUDA_CHECK(cudaMalloc(&s.d_hits, hit_elems * sizeof(uint2)));
@@ -439,19 +440,29 @@ static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, 
     BSX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
     // the kernel follows the index layout: an index built with -v >= 8 holds 16-byte context entries whatever -v the mapper uses
     const bool wide = !p->rrbs && ix->ctx_wide;
-    const size_t smem_se = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot, wide);
-    int occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem_se) : (wide ? bsx_map_occupancy_se_wide(smem_se) : bsx_map_occupancy_se_wgbs(smem_se));
-    const size_t smem_pe = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot, wide);
-    int occ_pe = p->rrbs ? bsx_map_occupancy_pe_rrbs(smem_pe) : (wide ? bsx_map_occupancy_pe_wide(smem_pe) : bsx_map_occupancy_pe_wgbs(smem_pe));
-    if (occ_se < 1 || occ_pe < 1) { bsx_set_error("mapping kernel does not fit on an SM (shared memory): %s", bsx_last_error()); return BSX_ERR_CUDA; }
+    // eight warps per CTA; a parameter set whose per-read plan is large (many segments x -I, -n 1, wide context) runs with fewer
+    int occ_se = 0, occ_pe = 0;
+    for (int w = BSX_WARPS_PER_CTA; w >= 1 && occ_se < 1; w >>= 1) {
+        const size_t smem = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot, wide, w);
+        if (smem > BSX_MAX_CTA_SMEM) continue;
+        m->warps_se = w;
+        occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem, w) : (wide ? bsx_map_occupancy_se_wide(smem, w) : bsx_map_occupancy_se_wgbs(smem, w));
+    }
+    for (int w = BSX_WARPS_PER_CTA; w >= 1 && occ_pe < 1; w >>= 1) {
+        const size_t smem = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot, wide, w);
+        if (smem > BSX_MAX_CTA_SMEM) continue;
+        m->warps_pe = w;
+        occ_pe = p->rrbs ? bsx_map_occupancy_pe_rrbs(smem, w) : (wide ? bsx_map_occupancy_pe_wide(smem, w) : bsx_map_occupancy_pe_wgbs(smem, w));
+    }
+    if (occ_se < 1 || occ_pe < 1) { bsx_set_error("mapping kernel does not fit on an SM (shared memory: plan of %d entries x %d chains)", m->plan_cap, m->nslot); return BSX_ERR_CUDA; }
     m->n_ctas_se = sms * occ_se; m->n_ctas_pe = sms * occ_pe;
     const uint32_t W1 = (uint32_t)p->max_num_hits + 1, lv = (uint32_t)p->max_snp_num + 1;
     m->hit_stride = 2 * W1;                        // SE: only the best level is kept
     m->dd_stride = lv * (uint32_t)p->max_num_hits + 32;
     m->pair_stride = (2 * (uint32_t)p->max_snp_num + 1) * W1 * 2;   // uint4 units (32-byte PairHit)
-    const size_t se_warps = (size_t)m->n_ctas_se * BSX_WARPS_PER_CTA;
+    const size_t se_warps = (size_t)m->n_ctas_se * m->warps_se;
     // prepared-unit images: 32 per resident warp (phase A of the align kernels, bsx_prep.cuh)
-    const size_t prep_bytes = std::max(se_warps, (size_t)m->n_ctas_pe * BSX_WARPS_PER_CTA) * 32u * bsx_image_bytes(m->plan_cap, m->nslot);
+    const size_t prep_bytes = std::max(se_warps, (size_t)m->n_ctas_pe * m->warps_pe) * 32u * bsx_image_bytes(m->plan_cap, m->nslot);
     for (int i = 0; i < 2; i++) {
         bsx_slot &s = m->slot[i];
         BSX_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -533,7 +544,7 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     {   // 32 units per warp and atomic when the batch is large (>= 2 blocks per resident warp: the prepare phase runs
         // with all lanes busy); small batches take smaller blocks (>= 8 per warp) because there the tail decides --
         // config 5's 200 k heavy reads: 0.62 M reads/s with blocks of 32, 0.86 M with blocks of 4
-        const uint64_t units = (uint64_t)n * (uint64_t)a.mates, warps = (uint64_t)(pe ? m->n_ctas_pe : m->n_ctas_se) * BSX_WARPS_PER_CTA;
+        const uint64_t units = (uint64_t)n * (uint64_t)a.mates, warps = (uint64_t)(pe ? m->n_ctas_pe * m->warps_pe : m->n_ctas_se * m->warps_se);
         const uint64_t want = units >= (1u << 19) ? 2 : 8;
         uint32_t b = 32;
         while (b > 4 && units / b < want * warps) b >>= 1;
@@ -542,10 +553,10 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
     if (pe) a.hit_stride = ((uint32_t)m->par.max_snp_num + 1) * 2 * ((uint32_t)m->par.max_num_hits + 1);
     BSX_CUDA_CHECK(cudaMemsetAsync(s.d_counter, 0, 4, st));
     m->launches++;
-    int rc = pe ? (a.rrbs ? bsx_launch_map_pe_rrbs(a, m->n_ctas_pe, st)
-                          : (a.ctx_wide ? bsx_launch_map_pe_wide(a, m->n_ctas_pe, st) : bsx_launch_map_pe_wgbs(a, m->n_ctas_pe, st)))
-                : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, st)
-                          : (a.ctx_wide ? bsx_launch_map_se_wide(a, m->n_ctas_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, st)));
+    int rc = pe ? (a.rrbs ? bsx_launch_map_pe_rrbs(a, m->n_ctas_pe, m->warps_pe, st)
+                          : (a.ctx_wide ? bsx_launch_map_pe_wide(a, m->n_ctas_pe, m->warps_pe, st) : bsx_launch_map_pe_wgbs(a, m->n_ctas_pe, m->warps_pe, st)))
+                : (a.rrbs ? bsx_launch_map_se_rrbs(a, m->n_ctas_se, m->warps_se, st)
+                          : (a.ctx_wide ? bsx_launch_map_se_wide(a, m->n_ctas_se, m->warps_se, st) : bsx_launch_map_se_wgbs(a, m->n_ctas_se, m->warps_se, st)));
     if (rc == BSX_OK && m->meth && !s.packed) {
         rc = bsx_meth_pile_mapped(m->meth, &m->meth_opts, m->meth_sam, m->par.report_repeat_hits, n, pe ? 2 : 1, m->stride,
                                   s.d_seq_a, s.d_seq_b, s.d_out_a, s.d_out_b, s.d_out_pair, st);

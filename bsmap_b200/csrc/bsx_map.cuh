@@ -4,7 +4,8 @@
 #include "../../include/bsmap_b200.h"
 
 #define BSX_MAX_KEYS 144          // seed_array[144] (align.h:84)
-#define BSX_WARPS_PER_CTA 8
+#define BSX_WARPS_PER_CTA 8       // warps of a mapping CTA; parameter sets whose per-warp shared memory is too large for eight run with 4, 2 or 1
+#define BSX_MAX_CTA_SMEM (227u * 1024u)
 
 struct MapArgs {
     // RefSeq
@@ -101,14 +102,24 @@ struct CtaSm {
 };
 static_assert(sizeof(CtaSm) % 16 == 0, "per-warp shared memory follows CtaSm and holds uint4");
 
+// half-steps (32 list entries) per staging round: 2 KB of 8-byte entries; wide indexes stage 16-byte entries
+#ifndef BSX_WIDE_ROUND_HS
+#define BSX_WIDE_ROUND_HS 8
+#endif
+#define BSX_NARROW_ROUND_HS 8
+// bytes of the per-warp staging area beyond the PrepCol it aliases (slot[HS*32] entries + HS schedule entries of 48 bytes)
+static inline __host__ __device__ size_t bsx_stage_extra_bytes(int wide) {
+    const size_t need = wide ? (size_t)BSX_WIDE_ROUND_HS * (32u * 16u + 48u) : (size_t)BSX_NARROW_ROUND_HS * (32u * 8u + 32u);
+    return need > sizeof(PrepCol) ? ((need - sizeof(PrepCol) + 15u) & ~(size_t)15u) : 0u;
+}
 static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int nslot, int wide) {
     return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * (wide ? 3u : 2u) * sizeof(uint4);
 }
 static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide) {
-    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot, wide) + sizeof(SelSm) + sizeof(PrepCol);
+    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot, wide) + sizeof(SelSm) + sizeof(PrepCol) + bsx_stage_extra_bytes(wide);
 }
-static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide) {
-    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot, wide) * BSX_WARPS_PER_CTA;
+static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide, int warps) {
+    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot, wide) * (size_t)warps;
 }
 
 static inline void bsx_map_args_derive(MapArgs &a) {

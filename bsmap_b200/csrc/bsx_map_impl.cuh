@@ -32,7 +32,7 @@
 
 // RRBS mode (-D) as a compile-time constant where a translation unit fixes it (dead code leaves the binary)
 #ifndef BSX_RRBS
-#define BSX_RRBS(A) ((A).rrbs)
+#error "the translation unit fixes BSX_RRBS(A) to 0 or 1"
 #endif
 // wide inline context (indexes built for -v >= 8: 16-byte entries with 32 + 32 context bases): a compile-time constant of
 // the translation unit
@@ -72,6 +72,9 @@
 #define BSX_KSEARCH 0           // schedule lookup: 0 = one shuffle per list (independent, pipelined), 1 = binary search over the lanes
                                 // holding the running totals (fewer instructions but a dependent chain: measured -9 % on paired-end)
 #endif
+#ifndef BSX_RUN_ADVANCE          // rounds that stay inside one long list advance the previous schedule instead of rebuilding it:
+#define BSX_RUN_ADVANCE (BSX_RRBS(0) || BSX_WIDE(0))   // pays where lists run to thousands of entries (cfg4 +2 %, cfg5 +9 %), costs 1-3 % on cfg2 / cfg3
+#endif
 #ifndef BSX_KUNROLL
 #define BSX_KUNROLL 1
 #endif
@@ -81,9 +84,9 @@
 #define BSX_STAGE_MAP 0         // lanes per staged half-step: 0 = sixteen (256 contiguous bytes per half-warp), 1 = four
 #endif
 #if BSX_WIDE(0)
-#define BSX_ROUND_HS 4           // 16-byte entries: the same 2 KB of list entries per warp and round
+#define BSX_ROUND_HS BSX_WIDE_ROUND_HS     // half-steps (32 list entries each) per staging round (bsx_map.cuh)
 #else
-#define BSX_ROUND_HS 8           // half-steps (32 list entries each) per staging round: 2 KB of list entries per warp
+#define BSX_ROUND_HS BSX_NARROW_ROUND_HS
 #endif
 
 #include "bsx_prep.cuh"
@@ -478,7 +481,7 @@ struct StageSm {
     CtxEntry slot[BSX_ROUND_HS * 32];   // one round of BSX_ROUND_HS half-steps x 32 entries
     HalfStep sched[BSX_ROUND_HS];
 };
-static_assert(sizeof(StageSm) <= sizeof(PrepCol), "the staging area must fit in the idle PrepCol");
+// the staging area aliases the idle PrepCol plus bsx_stage_extra_bytes() behind it (bsx_warp_smem_bytes)
 static_assert(BSX_ROUND_HS % 2 == 0 && BSX_ROUND_HS <= 32, "half-steps are evaluated in pairs; one lane describes one half-step");
 
 // mismatches among the read bases that face one entry's inline context: a lower bound of CountMismatch
@@ -552,8 +555,21 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
         if (total_hs == 0) continue;
         CTR_ADD(C, CT_LIST, __reduce_add_sync(BSX_FULL, n));              // corrected by packed_exit when SnpAlign returns early
         uint32_t thres = R->thres;
+#if BSX_RUN_ADVANCE
+        uint32_t run_end = 0;                                             // running total of the list the previous round ended in
+#endif
         #pragma unroll 1
         for (uint32_t h0 = 0; h0 < total_hs; h0 += BSX_ROUND_HS) {
+#if BSX_RUN_ADVANCE
+            if (h0 + BSX_ROUND_HS <= run_end) {
+                // a long list: every half-step of this round continues the list the previous round ended in, so the
+                // schedule is that round's last entry moved on by 32 entries per half-step
+                HalfStep h = S->sched[BSX_ROUND_HS - 1];
+                __syncwarp();
+                if (lane < BSX_ROUND_HS) { h.d.x += 32u * ((uint32_t)lane + 1u); S->sched[lane] = h; }
+                __syncwarp();
+            } else
+#endif
             {   // lane t describes half-step h0 + t: its list is the first one whose running total exceeds h0 + t
                 const uint32_t target = h0 + (uint32_t)lane;
                 int k = 0; uint32_t first = 0;
@@ -570,6 +586,13 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
 #else
                 BSX_UNROLL(BSX_KUNROLL)
                 for (int j = 0; j < per; j++) { const uint32_t c = __shfl_sync(BSX_FULL, cum, j); if (c <= target) { k = j + 1; first = c; } }
+#endif
+#if BSX_RUN_ADVANCE
+                {   // where the list of this round's last half-step ends
+                    const int kk = __shfl_sync(BSX_FULL, k, BSX_ROUND_HS - 1);
+                    const uint32_t ce = __shfl_sync(BSX_FULL, cum, kk & 15);
+                    run_end = kk < per ? ce : 0u;
+                }
 #endif
                 __syncwarp();                                             // the previous round's slow path may still read the schedule
                 if (lane < BSX_ROUND_HS) {
@@ -725,7 +748,7 @@ BSX_SE_KERNEL(const __grid_constant__ MapArgs A) {
     ReadSm *R = reinterpret_cast<ReadSm *>(base);
     SelSm *X = reinterpret_cast<SelSm *>(base + A.read_smem);
     PrepCol *P = reinterpret_cast<PrepCol *>(base + A.read_smem + sizeof(SelSm));
-    const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + wid;
     uint2 *hits = A.hit_scratch + (size_t)gw * A.hit_stride;
     uint32_t *dd = A.dd_scratch + (size_t)gw * A.dd_stride;
     Ctr *C = X->ctr;
@@ -876,7 +899,7 @@ BSX_PE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t read_sm = A.read_smem;
-    const size_t per_warp = 2 * read_sm + sizeof(SelSm) + sizeof(PrepCol);
+    const size_t per_warp = 2 * read_sm + sizeof(SelSm) + sizeof(PrepCol) + bsx_stage_extra_bytes(BSX_WIDE(0));
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
     uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
@@ -884,7 +907,7 @@ BSX_PE_KERNEL(const __grid_constant__ MapArgs A) {
     ReadSm *Rb = reinterpret_cast<ReadSm *>(base + read_sm);
     SelSm *X = reinterpret_cast<SelSm *>(base + 2 * read_sm);
     PrepCol *P = reinterpret_cast<PrepCol *>(base + 2 * read_sm + sizeof(SelSm));
-    const uint32_t gw = blockIdx.x * BSX_WARPS_PER_CTA + wid;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + wid;
     uint2 *hits_a = A.hit_scratch + (size_t)gw * 2 * A.hit_stride, *hits_b = hits_a + A.hit_stride;
     uint32_t *dd_a = A.dd_scratch + (size_t)gw * 2 * A.dd_stride;                       // mate b: + dd_stride
     PairHitDev *pairs = reinterpret_cast<PairHitDev *>(A.pair_scratch + (size_t)gw * A.pair_stride);
@@ -996,15 +1019,15 @@ BSX_PE_KERNEL(const __grid_constant__ MapArgs A) {
 
 // resident CTAs per SM for the persistent grid (0 when the kernel cannot launch with `smem`), and the launchers
 #ifdef BSX_BUILD_SE
-int BSX_SE_OCC(size_t smem) {
+int BSX_SE_OCC(size_t smem, int warps) {
     int occ = 0;
     cudaError_t e = cudaFuncSetAttribute(BSX_SE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, BSX_SE_KERNEL, BSX_WARPS_PER_CTA * 32, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, BSX_SE_KERNEL, warps * 32, smem);
     if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
     return occ;
 }
-int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot, BSX_WIDE(a));
+int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, int warps, cudaStream_t st) {
+    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot, BSX_WIDE(a), warps);
     // the attribute belongs to (function, device): one cache slot per device, several mappers / host threads may launch
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
@@ -1013,22 +1036,22 @@ int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(BSX_SE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < BSX_MAX_DEVICES) configured[dev].store(smem, std::memory_order_relaxed);
     }
-    BSX_SE_KERNEL<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
+    BSX_SE_KERNEL<<<n_ctas, warps * 32, smem, st>>>(a);
     BSX_CUDA_CHECK(cudaGetLastError());
     return BSX_OK;
 }
 #endif
 
 #ifdef BSX_BUILD_PE
-int BSX_PE_OCC(size_t smem) {
+int BSX_PE_OCC(size_t smem, int warps) {
     int occ = 0;
     cudaError_t e = cudaFuncSetAttribute(BSX_PE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, BSX_PE_KERNEL, BSX_WARPS_PER_CTA * 32, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, BSX_PE_KERNEL, warps * 32, smem);
     if (e != cudaSuccess) { bsx_set_error("occupancy query failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 0; }
     return occ;
 }
-int BSX_PE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot, BSX_WIDE(a));
+int BSX_PE_LAUNCH(const MapArgs &a, int n_ctas, int warps, cudaStream_t st) {
+    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot, BSX_WIDE(a), warps);
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
     BSX_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1036,7 +1059,7 @@ int BSX_PE_LAUNCH(const MapArgs &a, int n_ctas, cudaStream_t st) {
         BSX_CUDA_CHECK(cudaFuncSetAttribute(BSX_PE_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < BSX_MAX_DEVICES) configured[dev].store(smem, std::memory_order_relaxed);
     }
-    BSX_PE_KERNEL<<<n_ctas, BSX_WARPS_PER_CTA * 32, smem, st>>>(a);
+    BSX_PE_KERNEL<<<n_ctas, warps * 32, smem, st>>>(a);
     BSX_CUDA_CHECK(cudaGetLastError());
     return BSX_OK;
 }
