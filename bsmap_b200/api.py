@@ -378,8 +378,8 @@ def emit_pe(index: Index, params: Params, a: Reads, b: Reads, n: int, pr, ra, rb
     return w, tuple(st)
 
 
-def meth_opts(unique=False, pair=False, meth0=False, trim_fillin=2, combine_cpg=False, min_depth=1) -> MethOpts:
-    return MethOpts(int(unique), int(pair), int(meth0), int(trim_fillin), int(combine_cpg), int(min_depth))
+def meth_opts(unique=False, pair=False, meth0=False, trim_fillin=2, combine_cpg=False, min_depth=1, rm_dup=False) -> MethOpts:
+    return MethOpts(int(unique), int(pair), int(meth0), int(trim_fillin), int(combine_cpg), int(min_depth), int(rm_dup))
 
 
 class Meth:

@@ -567,6 +567,11 @@ static int run_slot(bsx_mapper *m, int si, uint32_t n, uint32_t first_index, int
 
 extern "C" int bsx_mapper_attach_meth(bsx_mapper *m, bsx_meth *meth, const bsx_meth_opts *o, int sam_rules) {
     if (!m || (meth && !o)) { bsx_set_error("bsx_mapper_attach_meth: bad argument"); return BSX_ERR_ARG; }
+    if (meth && o->rm_dup && m->par.pairend && !sam_rules) {
+        // methratio.py reads the paired file, then the unpaired one: its -r order is not the order the batches are mapped in
+        bsx_set_error("-r (remove duplicates) with paired-end BSP output follows the order of two files: run methratio on them instead");
+        return BSX_ERR_UNSUPPORTED;
+    }
     m->meth = meth; m->meth_sam = sam_rules;
     if (o) m->meth_opts = *o;
     return BSX_OK;

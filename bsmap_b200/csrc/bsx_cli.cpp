@@ -72,8 +72,8 @@ void usage() {
            "                   replicated over NVLink, batches are dealt to the devices and written in input order\n"
            "       --methratio <str>   also write methratio.py's table, piled up on the GPU from the mapped batches\n"
            "                           (-o may then be omitted: no alignment text is produced at all)\n"
-           "       --meth-unique --meth-pair --meth-zero --meth-cpg --meth-trim <int> --meth-min-depth <int>\n"
-           "                           methratio.py's -u -p -z -g -t -m\n\n");
+           "       --meth-unique --meth-pair --meth-zero --meth-cpg --meth-rmdup --meth-trim <int> --meth-min-depth <int>\n"
+           "                           methratio.py's -u -p -z -g -r -t -m\n\n");
     exit(1);
 }
 
@@ -100,6 +100,7 @@ int get_options(int argc, char **argv, Opts &o) {
             else if (a == "meth-pair") o.mo.pair = 1;
             else if (a == "meth-zero") o.mo.meth0 = 1;
             else if (a == "meth-cpg") o.mo.combine_cpg = 1;
+            else if (a == "meth-rmdup") o.mo.rm_dup = 1;
             else if (a == "meth-trim" && i + 1 < argc) o.mo.trim_fillin = atoi(argv[++i]);
             else if (a == "meth-min-depth" && i + 1 < argc) o.mo.min_depth = atoi(argv[++i]);
             else return i;

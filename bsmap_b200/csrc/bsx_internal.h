@@ -89,6 +89,7 @@ struct bsx_meth;
 int bsx_meth_pile_mapped(bsx_meth *m, const bsx_meth_opts *o, int sam, int report_repeat_hits, uint32_t n, int mates, uint32_t stride,
                          const uint8_t *seq_a, const uint8_t *seq_b, const bsx_rec *out_a, const bsx_rec *out_b, const bsx_pair_rec *out_pair,
                          cudaStream_t st);   // bsx_meth.cu
+int bsx_inflate_file(const char *path, std::vector<char> &out);   // gzip / BGZF members -> bytes (bsx_reads.cpp)
 int bsx_host_threads(int requested);   // 0 = BSX_THREADS env or hardware concurrency (capped at 32)
 
 int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_t *packed = nullptr);   // bsx_index.cu

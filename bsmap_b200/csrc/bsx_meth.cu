@@ -7,7 +7,11 @@
 // The reference holds two u32 arrays per chromosome in host memory and walks each read with str.find;
 // here both arrays cover the packed Watson strand of the index in HBM (8 bytes per reference position) and the
 // reference base comes from the 2-bit refcat (non-ACGT packs to A, which is neither C nor G -- same outcome).
-// Not supported: -r (duplicate removal is defined by file order).
+// -r (methratio.py:52-55: of the alignments that pass the filters, the first in file order per (chromosome, fragment
+// end, direction) counts) is a two-kernel min-reduction: every alignment of a batch claims its key with
+// atomicMin(first[key], order + 1), then the pile-up kernel lets the alignment through whose claim stands and marks
+// the key 0 = taken for good, so later batches lose against earlier ones.  8 bytes per reference position, allocated
+// on first use.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -22,6 +26,8 @@ struct bsx_meth {
     const bsx_index *ix = nullptr;
     uint32_t *d_meth = nullptr, *d_depth = nullptr;   // n_words * 16 counters each, indexed like refcat bases
     unsigned long long *d_valid = nullptr;
+    uint32_t *d_first = nullptr;                      // -r: per (position, direction) the order + 1 of the claiming alignment; 0 = taken
+    cudaEvent_t dup_order = nullptr;                  // -r, in-process: the pile-up of batch k+1 waits for that of batch k
     bool combined = false;
     // staging for bsx_meth_add
     size_t cap = 0; uint32_t stride = 0;
@@ -69,9 +75,58 @@ __device__ __forceinline__ void pile_alignment(const uint32_t *__restrict__ refc
     }
 }
 
+// what get_alignment hands on (before trimming): sequence index, 0-based position, printed length, strand bits, ...
+struct AlnView { uint32_t k; long long pos, len; int st, ins; long long mate_pos; bool sam; };
+
+// -r key of an alignment (methratio.py:52-53): '+-' / '-+' hits are identified by where they end (direction 2), the
+// others by where they start (direction 1).  A fragment end outside [0, size) makes the script raise IndexError (or
+// wrap to the chromosome's last entry for -1); BSMAP never prints such a record, and here it skips the duplicate test.
+__device__ __forceinline__ bool dup_key(const uint32_t *__restrict__ seqinfo, uint32_t n_seq, const AlnView &v, uint64_t &key) {
+    const uint32_t *anchor = seqinfo, *size = seqinfo + n_seq + 1;
+    const bool dir2 = ((v.st ^ (v.st >> 1)) & 1) != 0;
+    const long long fe = dir2 ? v.pos + v.len : v.pos;
+    if (fe < 0 || fe >= (long long)size[v.k]) return false;
+    key = ((uint64_t)anchor[v.k] + (uint64_t)fe) * 2u + (dir2 ? 1u : 0u);
+    return true;
+}
+// resolve (warp-uniform): does alignment `order` hold its key?  The holder marks it taken for every later batch.  A
+// loser reads either the holder's claim or the 0 the holder has just written: both differ from its own claim.
+__device__ __forceinline__ bool dup_holds(uint32_t *first, const uint32_t *__restrict__ seqinfo, uint32_t n_seq, const AlnView &v, uint32_t order, int lane) {
+    uint64_t key;
+    if (!dup_key(seqinfo, n_seq, v, key)) return true;
+    uint32_t w = 0;
+    if (lane == 0) { w = first[key]; if (w == order + 1u) first[key] = 0u; }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    return w == order + 1u;
+}
+
+// alignment a of a batch parsed from SAM / BSP text on the host, after the -u / -p filters (methratio.py:35-36, 48-49)
+__device__ __forceinline__ bool parsed_alignment(const bsx_meth_opts &o, uint32_t n_seq, uint32_t a, const uint16_t *__restrict__ lens,
+                                                 const uint32_t *__restrict__ chr, const uint32_t *__restrict__ pos0, const uint8_t *__restrict__ strand,
+                                                 const int32_t *__restrict__ insert, const int32_t *__restrict__ mate_pos, const uint8_t *__restrict__ flags, AlnView &v) {
+    const uint32_t fl = flags[a];
+    if (o.unique && (fl & BSX_METH_SECONDARY)) return false;
+    if (o.pair && !(fl & BSX_METH_PROPER)) return false;
+    v.k = chr[a];
+    if (v.k >= n_seq) return false;
+    v.pos = (long long)pos0[a]; v.len = (long long)lens[a]; v.st = strand[a]; v.ins = insert[a]; v.mate_pos = (long long)mate_pos[a];
+    v.sam = (fl & BSX_METH_SAM) != 0;
+    return true;
+}
+
+// -r, first kernel: one thread per alignment claims its key
+__global__ void __launch_bounds__(256) meth_claim_kernel(const uint32_t *__restrict__ seqinfo, uint32_t n_seq, uint32_t *first, bsx_meth_opts o, uint32_t n,
+                                                         const uint16_t *__restrict__ lens, const uint32_t *__restrict__ chr, const uint32_t *__restrict__ pos0,
+                                                         const uint8_t *__restrict__ strand, const int32_t *__restrict__ insert,
+                                                         const int32_t *__restrict__ mate_pos, const uint8_t *__restrict__ flags) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    AlnView v; uint64_t key;
+    if (a < n && parsed_alignment(o, n_seq, a, lens, chr, pos0, strand, insert, mate_pos, flags, v) && dup_key(seqinfo, n_seq, v, key)) atomicMin(first + key, a + 1u);
+}
+
 // alignments parsed from SAM / BSP text on the host: one warp per alignment
 __global__ void __launch_bounds__(256) meth_pileup_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
-                                                          uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, bsx_meth_opts o, uint32_t n,
+                                                          uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, uint32_t *first, bsx_meth_opts o, uint32_t n,
                                                           const char *__restrict__ seqs, uint32_t stride, const uint16_t *__restrict__ lens,
                                                           const uint32_t *__restrict__ chr, const uint32_t *__restrict__ pos0,
                                                           const uint8_t *__restrict__ strand, const int32_t *__restrict__ insert,
@@ -79,14 +134,11 @@ __global__ void __launch_bounds__(256) meth_pileup_kernel(const uint32_t *__rest
     const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (a >= n) return;
-    const uint32_t fl = flags[a];
-    if (o.unique && (fl & BSX_METH_SECONDARY)) return;      // methratio.py:35 / 48
-    if (o.pair && !(fl & BSX_METH_PROPER)) return;          // methratio.py:36 / 49
-    const uint32_t k = chr[a];
-    if (k >= n_seq) return;
+    AlnView v;
+    if (!parsed_alignment(o, n_seq, a, lens, chr, pos0, strand, insert, mate_pos, flags, v)) return;
+    if (first && !dup_holds(first, seqinfo, n_seq, v, a, lane)) return;
     const char *sq = seqs + (size_t)a * stride;
-    pile_alignment(refcat, seqinfo, n_seq, meth, depth, n_valid, o, k, (long long)pos0[a], (long long)lens[a], strand[a], insert[a],
-                   (long long)mate_pos[a], (fl & BSX_METH_SAM) != 0, lane, [sq](int i) { return sq[i]; });
+    pile_alignment(refcat, seqinfo, n_seq, meth, depth, n_valid, o, v.k, v.pos, v.len, v.st, v.ins, v.mate_pos, v.sam, lane, [sq](int i) { return sq[i]; });
 }
 
 __device__ __forceinline__ char comp_char(char c) {   // rev_char[] (param.cpp:166-177)
@@ -97,22 +149,15 @@ __device__ __forceinline__ char comp_char(char c) {   // rev_char[] (param.cpp:1
     }
 }
 
-// The batch a mapper has just mapped, straight from its device buffers (no SAM text in between): one warp per read
-// (PE: per mate).  Which reads are printed as mapped, with which SEQ orientation / POS / TLEN / PNEXT, restates
-// s_OutHit (align.cpp:631-765), s_OutHitPair (pairs.cpp:288-424) and s_OutHitUnpair (pairs.cpp:426-498).
-__global__ void __launch_bounds__(256) meth_pileup_mapped_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
-                                                                 uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, bsx_meth_opts o,
-                                                                 int sam, int report_repeat_hits, uint32_t n, int mates, uint32_t stride,
-                                                                 const uint8_t *__restrict__ seq_a, const uint8_t *__restrict__ seq_b,
-                                                                 const bsx_rec *__restrict__ out_a, const bsx_rec *__restrict__ out_b,
-                                                                 const bsx_pair_rec *__restrict__ out_pair) {
-    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (u >= n * (uint32_t)mates) return;
+// Unit u of the batch a mapper has just mapped (one read; PE: one mate), straight from its device buffers.  Which reads
+// are printed as mapped, with which SEQ orientation / POS / TLEN / PNEXT, restates s_OutHit (align.cpp:631-765),
+// s_OutHitPair (pairs.cpp:288-424) and s_OutHitUnpair (pairs.cpp:426-498); then the -u / -p filters.
+__device__ __forceinline__ bool mapped_alignment(const bsx_meth_opts &o, int sam, int report_repeat_hits, uint32_t u, int mates,
+                                                 const bsx_rec *__restrict__ out_a, const bsx_rec *__restrict__ out_b,
+                                                 const bsx_pair_rec *__restrict__ out_pair, AlnView &v, bool &rev) {
     const uint32_t r = mates == 2 ? u >> 1 : u;
     const int mate = mates == 2 ? (int)(u & 1u) : 0;
     const bsx_rec rc = (mate ? out_b : out_a)[r];
-    const uint8_t *rd = (mate ? seq_b : seq_a) + (size_t)r * stride;
     uint32_t chr, loc; int chain, lp = rc.len, ins = 0; long long mate_pos = -1; bool secondary, proper = false;
     if (mates == 2 && out_pair[r].paired) {
         const bsx_pair_rec pp = out_pair[r];
@@ -123,20 +168,50 @@ __global__ void __launch_bounds__(256) meth_pileup_mapped_kernel(const uint32_t 
         if (pp.insert < lb && ((!pp.chain) ^ (int)(pp.b_chr & 1u))) b_loc += (uint32_t)(lb - pp.insert);
         chr = mate ? pp.b_chr : pp.a_chr; loc = mate ? b_loc : a_loc; chain = mate ? !pp.chain : pp.chain;
         if (pp.insert < lp) lp = pp.insert;
-        const bool rev = (chain ^ (int)(chr & 1u)) != 0;
-        ins = sam ? (rev ? -pp.insert : pp.insert) : pp.insert;       // TLEN (pairs.cpp:330-340) / BSP insert column
+        const bool rv = (chain ^ (int)(chr & 1u)) != 0;
+        ins = sam ? (rv ? -pp.insert : pp.insert) : pp.insert;       // TLEN (pairs.cpp:330-340) / BSP insert column
         mate_pos = mate ? a_loc : b_loc;                             // PNEXT - 1
         secondary = pp.npairs > 1; proper = true;
     } else {
         const int nh = rc.status ? -1 : (int)rc.nhits;
-        if (nh <= 0 || (nh > 1 && report_repeat_hits == 0)) return;  // printed as unmapped ('u') or not at all
+        if (nh <= 0 || (nh > 1 && report_repeat_hits == 0)) return false;   // printed as unmapped ('u') or not at all
         chr = rc.chr; loc = rc.loc; chain = rc.chain; secondary = nh > 1;
     }
-    if (o.unique && secondary) return;
-    if (o.pair && !proper) return;
-    const bool rev = (chain ^ (int)(chr & 1u)) != 0;
-    const int st = (int)(chr & 1u) | (chain << 1);
-    pile_alignment(refcat, seqinfo, n_seq, meth, depth, n_valid, o, chr >> 1, (long long)loc, (long long)lp, st, ins, mate_pos, sam != 0, lane,
+    if (o.unique && secondary) return false;
+    if (o.pair && !proper) return false;
+    rev = (chain ^ (int)(chr & 1u)) != 0;
+    v.k = chr >> 1; v.pos = (long long)loc; v.len = (long long)lp; v.st = (int)(chr & 1u) | (chain << 1); v.ins = ins; v.mate_pos = mate_pos; v.sam = sam != 0;
+    return true;
+}
+
+// -r, first kernel of the in-process form: one thread per unit claims its key (the order of the SAM lines: read by read, mate a before mate b)
+__global__ void __launch_bounds__(256) meth_claim_mapped_kernel(const uint32_t *__restrict__ seqinfo, uint32_t n_seq, uint32_t *first, bsx_meth_opts o,
+                                                                int sam, int report_repeat_hits, uint32_t n, int mates,
+                                                                const bsx_rec *__restrict__ out_a, const bsx_rec *__restrict__ out_b,
+                                                                const bsx_pair_rec *__restrict__ out_pair) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    AlnView v; bool rev; uint64_t key;
+    if (u < n * (uint32_t)mates && mapped_alignment(o, sam, report_repeat_hits, u, mates, out_a, out_b, out_pair, v, rev) && dup_key(seqinfo, n_seq, v, key))
+        atomicMin(first + key, u + 1u);
+}
+
+// pile-up of the mapped batch: one warp per read (PE: per mate)
+__global__ void __launch_bounds__(256) meth_pileup_mapped_kernel(const uint32_t *__restrict__ refcat, const uint32_t *__restrict__ seqinfo, uint32_t n_seq,
+                                                                 uint32_t *meth, uint32_t *depth, unsigned long long *n_valid, uint32_t *first, bsx_meth_opts o,
+                                                                 int sam, int report_repeat_hits, uint32_t n, int mates, uint32_t stride,
+                                                                 const uint8_t *__restrict__ seq_a, const uint8_t *__restrict__ seq_b,
+                                                                 const bsx_rec *__restrict__ out_a, const bsx_rec *__restrict__ out_b,
+                                                                 const bsx_pair_rec *__restrict__ out_pair) {
+    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= n * (uint32_t)mates) return;
+    AlnView v; bool rev;
+    if (!mapped_alignment(o, sam, report_repeat_hits, u, mates, out_a, out_b, out_pair, v, rev)) return;
+    if (first && !dup_holds(first, seqinfo, n_seq, v, u, lane)) return;
+    const uint32_t r = mates == 2 ? u >> 1 : u;
+    const uint8_t *rd = ((mates == 2 && (u & 1u)) ? seq_b : seq_a) + (size_t)r * stride;
+    const int lp = (int)v.len;
+    pile_alignment(refcat, seqinfo, n_seq, meth, depth, n_valid, o, v.k, v.pos, v.len, v.st, v.ins, v.mate_pos, v.sam, lane,
                    [rd, rev, lp](int i) { return rev ? comp_char((char)rd[lp - 1 - i]) : (char)rd[i]; });
 }
 
@@ -162,6 +237,17 @@ int ensure_staging(bsx_meth *m, size_t n, uint32_t stride) {
     BSX_CUDA_CHECK(cudaMalloc(&m->d_flags, m->cap));
     BSX_CUDA_CHECK(cudaMalloc(&m->d_ins, m->cap * 4));
     BSX_CUDA_CHECK(cudaMalloc(&m->d_mate, m->cap * 4));
+    return BSX_OK;
+}
+
+// -r: the claim table, all keys free
+int ensure_dup_table(bsx_meth *m) {
+    if (m->d_first) return BSX_OK;
+    const size_t bytes = m->ix->n_words * 16 * 2 * sizeof(uint32_t);
+    if (cudaMalloc(&m->d_first, bytes) != cudaSuccess) { cudaGetLastError(); bsx_set_error("-r: out of device memory (%zu bytes for the duplicate table)", bytes); return BSX_ERR_CUDA; }
+    BSX_CUDA_CHECK(cudaMemset(m->d_first, 0xff, bytes));
+    BSX_CUDA_CHECK(cudaEventCreateWithFlags(&m->dup_order, cudaEventDisableTiming));
+    BSX_CUDA_CHECK(cudaDeviceSynchronize());
     return BSX_OK;
 }
 
@@ -209,7 +295,8 @@ extern "C" int bsx_meth_create(const bsx_index *ix, bsx_meth **out) {
 
 extern "C" int bsx_meth_destroy(bsx_meth *m) {
     if (!m) return BSX_OK;
-    cudaFree(m->d_meth); cudaFree(m->d_depth); cudaFree(m->d_valid);
+    cudaFree(m->d_meth); cudaFree(m->d_depth); cudaFree(m->d_valid); cudaFree(m->d_first);
+    if (m->dup_order) cudaEventDestroy(m->dup_order);
     cudaFree(m->d_seq); cudaFree(m->d_len); cudaFree(m->d_chr); cudaFree(m->d_pos); cudaFree(m->d_strand); cudaFree(m->d_flags); cudaFree(m->d_ins); cudaFree(m->d_mate);
     delete m;
     return BSX_OK;
@@ -231,9 +318,15 @@ extern "C" int bsx_meth_add(bsx_meth *m, const bsx_meth_opts *o, uint32_t n, con
         BSX_CUDA_CHECK(cudaMemcpy(m->d_flags, flags, n, cudaMemcpyHostToDevice));
         BSX_CUDA_CHECK(cudaMemcpy(m->d_ins, insert, (size_t)n * 4, cudaMemcpyHostToDevice));
         BSX_CUDA_CHECK(cudaMemcpy(m->d_mate, mate_pos, (size_t)n * 4, cudaMemcpyHostToDevice));
+        if (o->rm_dup) {
+            rc = ensure_dup_table(m); if (rc) return rc;
+            meth_claim_kernel<<<(n + 255) / 256, 256>>>(m->ix->d_seqinfo, m->ix->n_seq, m->d_first, *o, n, m->d_len, m->d_chr, m->d_pos, m->d_strand,
+                                                       m->d_ins, m->d_mate, m->d_flags);
+            BSX_CUDA_CHECK(cudaGetLastError());
+        }
         const unsigned blocks = (unsigned)(((uint64_t)n * 32 + 255) / 256);
-        meth_pileup_kernel<<<blocks, 256>>>(m->ix->d_refcat, m->ix->d_seqinfo, m->ix->n_seq, m->d_meth, m->d_depth, m->d_valid, *o, n,
-                                            m->d_seq, m->stride, m->d_len, m->d_chr, m->d_pos, m->d_strand, m->d_ins, m->d_mate, m->d_flags);
+        meth_pileup_kernel<<<blocks, 256>>>(m->ix->d_refcat, m->ix->d_seqinfo, m->ix->n_seq, m->d_meth, m->d_depth, m->d_valid,
+                                            o->rm_dup ? m->d_first : nullptr, *o, n, m->d_seq, m->stride, m->d_len, m->d_chr, m->d_pos, m->d_strand, m->d_ins, m->d_mate, m->d_flags);
         BSX_CUDA_CHECK(cudaGetLastError());
     }
     if (n_valid) {
@@ -250,10 +343,22 @@ int bsx_meth_pile_mapped(bsx_meth *m, const bsx_meth_opts *o, int sam, int repor
                          cudaStream_t st) {
     if (!m || !o || n == 0) return BSX_OK;
     if (m->combined) { bsx_set_error("bsx_meth: counters were already combined (-g); create a new bsx_meth"); return BSX_ERR_ARG; }
+    if (o->rm_dup) {
+        // file order = batch order: this batch's claims start when the previous batch has resolved its own (the batches
+        // alternate between two streams).  Paired-end BSP output goes to two files, whose concatenation is the script's
+        // order: that case is refused by bsx_mapper_attach_meth.
+        int rc = ensure_dup_table(m); if (rc) return rc;
+        BSX_CUDA_CHECK(cudaStreamWaitEvent(st, m->dup_order, 0));
+        meth_claim_mapped_kernel<<<(unsigned)(((uint64_t)n * (uint64_t)mates + 255) / 256), 256, 0, st>>>(m->ix->d_seqinfo, m->ix->n_seq, m->d_first, *o, sam,
+                                                                                                      report_repeat_hits, n, mates, out_a, out_b, out_pair);
+        BSX_CUDA_CHECK(cudaGetLastError());
+    }
     const unsigned blocks = (unsigned)(((uint64_t)n * (uint64_t)mates * 32 + 255) / 256);
-    meth_pileup_mapped_kernel<<<blocks, 256, 0, st>>>(m->ix->d_refcat, m->ix->d_seqinfo, m->ix->n_seq, m->d_meth, m->d_depth, m->d_valid, *o,
-                                                       sam, report_repeat_hits, n, mates, stride, seq_a, seq_b, out_a, out_b, out_pair);
+    meth_pileup_mapped_kernel<<<blocks, 256, 0, st>>>(m->ix->d_refcat, m->ix->d_seqinfo, m->ix->n_seq, m->d_meth, m->d_depth, m->d_valid,
+                                                       o->rm_dup ? m->d_first : nullptr, *o, sam, report_repeat_hits, n, mates, stride, seq_a, seq_b,
+                                                       out_a, out_b, out_pair);
     BSX_CUDA_CHECK(cudaGetLastError());
+    if (o->rm_dup) BSX_CUDA_CHECK(cudaEventRecord(m->dup_order, st));
     return BSX_OK;
 }
 

@@ -59,11 +59,11 @@ void parse(int argc, char **argv, MOpts &m) {
             case 'p': m.o.pair = 1; break;
             case 'z': m.o.meth0 = 1; break;
             case 'q': m.quiet = true; break;
-            case 'r': usage_error("-r/--remove-duplicate is not supported by the GPU pile-up (it depends on the order of the input lines)"); break;
+            case 'r': m.o.rm_dup = 1; break;
             case 't': { char *e; long x = strtol(v, &e, 10); if (*e || e == v) usage_error("option -t: invalid integer value"); m.o.trim_fillin = (int)x; } break;
             case 'g': m.o.combine_cpg = 1; break;
             case 'm': { char *e; long x = strtol(v, &e, 10); if (*e || e == v) usage_error("option -m: invalid integer value"); m.o.min_depth = (int)x; } break;
-            case 'h': printf("Usage: methratio [options] BSMAP_MAPPING_FILES\n  -o FILE -d FILE [-c CHR] [-u] [-p] [-z] [-q] [-t N] [-g] [-m FOLD]\n"); exit(0);
+            case 'h': printf("Usage: methratio [options] BSMAP_MAPPING_FILES\n  -o FILE -d FILE [-c CHR] [-u] [-p] [-z] [-q] [-r] [-t N] [-g] [-m FOLD]\n"); exit(0);
         }
     };
     for (int i = 1; i < argc; i++) {
@@ -150,6 +150,91 @@ bool parse_line(const char *b, const char *e, bool sam, const std::unordered_map
     return true;
 }
 
+// A BAM file (the script reads it through `samtools view -X`, methratio.py:91): reference names from the file's own
+// dictionary, FLAG bits 0x4 / 0x100 / 0x2 = the letters u / s / P, SEQ through the 4-bit table, ZS:Z from the tags.
+// Records are found with one sequential hop over the block sizes, then decoded in parallel, PIECE records at a time.
+template <class Pile>
+bool pile_bam(const std::string &path, const std::unordered_map<std::string, uint32_t> &chrom, int threads, Pile &pile, std::string &err) {
+    std::vector<char> raw;
+    if (bsx_inflate_file(path.c_str(), raw) != BSX_OK) { err = "failed to read (BGZF inflate)"; return false; }
+    const unsigned char *p = (const unsigned char *)raw.data();
+    const size_t n = raw.size();
+    auto i32 = [&](size_t at) { int32_t v; memcpy(&v, p + at, 4); return v; };
+    if (n < 12 || memcmp(p, "BAM\1", 4) != 0) { err = "not a BAM file"; return false; }
+    size_t at = 8 + (size_t)std::max(i32(4), 0);
+    if (at + 4 > n) { err = "truncated BAM header"; return false; }
+    const int32_t n_ref = i32(at); at += 4;
+    std::vector<int64_t> ref_to_chr((size_t)std::max(n_ref, 0), -1);       // BAM refID -> index of the FASTA record (or not selected)
+    for (int32_t k = 0; k < n_ref; k++) {
+        if (at + 4 > n) { err = "truncated BAM header"; return false; }
+        const int32_t l_name = i32(at);
+        if (l_name < 1 || at + 4 + (size_t)l_name + 4 > n) { err = "truncated BAM header"; return false; }
+        auto it = chrom.find(std::string((const char *)p + at + 4, (size_t)l_name - 1));
+        if (it != chrom.end()) ref_to_chr[(size_t)k] = it->second;
+        at += 4 + (size_t)l_name + 4;
+    }
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    const size_t PIECE = (size_t)4 << 20;
+    while (at + 4 <= n) {
+        std::vector<size_t> recs;                                            // offsets of the records' bodies
+        while (recs.size() < PIECE && at + 4 <= n) {
+            const int32_t bs = i32(at);
+            if (bs < 32 || at + 4 + (size_t)bs > n) { err = "truncated BAM record"; return false; }
+            recs.push_back(at + 4); at += 4 + (size_t)bs;
+        }
+        std::vector<std::vector<Aln>> part((size_t)threads);
+        std::vector<std::vector<char>> bases((size_t)threads);
+        std::vector<std::string> errs((size_t)threads);
+        bsx_parallel(threads, recs.size(), [&](int t, size_t b, size_t e) {
+            size_t need = 0;
+            for (size_t r = b; r < e; r++) need += (size_t)std::max(i32(recs[r] + 16), 0);
+            bases[t].resize(need + 1);                                       // decoded SEQ of this thread's records, never reallocated
+            size_t used = 0;
+            for (size_t r = b; r < e; r++) {
+                const unsigned char *q = p + recs[r];
+                const size_t bytes = (size_t)i32(recs[r] - 4);
+                const int32_t ref_id = i32(recs[r]), pos = i32(recs[r] + 4), l_seq = i32(recs[r] + 16), next_pos = i32(recs[r] + 24), tlen = i32(recs[r] + 28);
+                const uint32_t l_name = q[8], n_cig = (uint32_t)q[12] | ((uint32_t)q[13] << 8), flag = (uint32_t)q[14] | ((uint32_t)q[15] << 8);
+                const size_t off_seq = 32 + (size_t)l_name + 4 * (size_t)n_cig;
+                if (l_seq < 0 || off_seq + ((size_t)l_seq + 1) / 2 + (size_t)l_seq > bytes) { errs[t] = "truncated BAM record"; return; }
+                if (flag & 0x4) continue;                                    // 'u'
+                if (ref_id < 0 || ref_id >= (int32_t)ref_to_chr.size() || ref_to_chr[(size_t)ref_id] < 0) continue;   // cr not in options.chroms
+                Aln a;
+                a.flags = (uint8_t)(BSX_METH_SAM | ((flag & 0x100) ? BSX_METH_SECONDARY : 0u) | ((flag & 0x2) ? BSX_METH_PROPER : 0u));
+                a.chr = (uint32_t)ref_to_chr[(size_t)ref_id]; a.pos = (uint32_t)pos; a.insert = tlen; a.mate = next_pos;
+                char *sq = bases[t].data() + used;
+                for (int32_t i = 0; i < l_seq; i++) sq[i] = nt16[(q[off_seq + ((size_t)i >> 1)] >> ((~i & 1) << 2)) & 15];
+                a.seq = sq; a.len = (uint32_t)l_seq; used += (size_t)l_seq;
+                // tags: two letters, a type, a value
+                int strand = -1;
+                size_t x = off_seq + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+                while (x + 3 <= bytes && strand < 0) {
+                    const char t0 = (char)q[x], t1 = (char)q[x + 1], ty = (char)q[x + 2];
+                    x += 3;
+                    if (ty == 'Z' || ty == 'H') {
+                        const void *z = memchr(q + x, 0, bytes - x);
+                        const size_t l = z ? (size_t)((const unsigned char *)z - (q + x)) : bytes - x;
+                        if (t0 == 'Z' && t1 == 'S' && ty == 'Z' && l >= 2) strand = (q[x] == '-' ? 1 : 0) | (q[x + 1] == '-' ? 2 : 0);
+                        x += l + 1;
+                    } else if (ty == 'A' || ty == 'c' || ty == 'C') x += 1;
+                    else if (ty == 's' || ty == 'S') x += 2;
+                    else if (ty == 'i' || ty == 'I' || ty == 'f') x += 4;
+                    else if (ty == 'B' && x + 5 <= bytes) {
+                        const char sub = (char)q[x]; uint32_t cnt; memcpy(&cnt, q + x + 1, 4);
+                        x += 5 + (size_t)cnt * (sub == 'c' || sub == 'C' ? 1u : (sub == 's' || sub == 'S' ? 2u : 4u));
+                    } else break;
+                }
+                if (strand < 0) { errs[t] = "BAM record without a ZS:Z: tag (not BSMAP output?)"; return; }
+                a.strand = (uint8_t)strand;
+                part[t].push_back(a);
+            }
+        });
+        for (const std::string &e : errs) if (!e.empty()) { err = e; return false; }
+        if (!pile(part)) return false;
+    }
+    return true;
+}
+
 }  // namespace
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -194,12 +279,40 @@ extern "C" int bsx_methratio_main(int argc, char **argv) {
 
     const double t_ix = now_s();
     uint64_t nmap = 0;
+    // one piece of alignments (file order = thread 0's, then thread 1's, ...) -> staging arrays -> the device
+    auto pile = [&](const std::vector<std::vector<Aln>> &part) -> bool {
+        size_t tot = 0; uint32_t maxlen = 16;
+        std::vector<size_t> off((size_t)threads + 1, 0);
+        for (int t = 0; t < threads; t++) { off[t] = tot; tot += part[t].size(); for (const Aln &a : part[t]) maxlen = std::max(maxlen, a.len); }
+        off[threads] = tot;
+        if (tot > 0xffffffffull) { fprintf(stderr, "too many alignments in one piece\n"); return false; }
+        const uint32_t stride = (std::min<uint32_t>(maxlen, 65535u) + 15u) & ~15u;
+        std::vector<char> sq(tot * stride); std::vector<uint16_t> len(tot); std::vector<uint32_t> chr(tot), pos(tot);
+        std::vector<uint8_t> strand(tot), flags(tot); std::vector<int32_t> ins(tot), mate(tot);
+        bsx_parallel(threads, (size_t)threads, [&](int t, size_t, size_t) {
+            size_t i = off[t];
+            for (const Aln &a : part[t]) {
+                const uint32_t l = std::min(a.len, stride);
+                memcpy(&sq[i * stride], a.seq, l);
+                len[i] = (uint16_t)l; chr[i] = a.chr; pos[i] = a.pos; strand[i] = a.strand; flags[i] = a.flags; ins[i] = a.insert; mate[i] = a.mate;
+                i++;
+            }
+        });
+        if (bsx_meth_add(mh, &m.o, (uint32_t)tot, sq.data(), stride, len.data(), chr.data(), pos.data(), strand.data(), ins.data(), mate.data(),
+                         flags.data(), &nmap) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return false; }
+        return true;
+    };
     for (const std::string &path : m.files) {
         disp(m, ("reading " + path + " ...").c_str());
         const size_t pl = path.size();
         std::string suf = pl >= 4 ? path.substr(pl - 4) : "";
         for (char &c : suf) c = (char)toupper((unsigned char)c);
-        if (suf == ".BAM") { fprintf(stderr, "%s: BAM input is not supported; convert with `samtools view -h` first\n", path.c_str()); return 1; }
+        if (suf == ".BAM") {
+            // methratio.py:91 pipes the file through `samtools view -X`; here the records are decoded in place
+            std::string err;
+            if (!pile_bam(path, chrom, threads, pile, err)) { if (!err.empty()) fprintf(stderr, "%s: %s\n", path.c_str(), err.c_str()); return 1; }
+            continue;
+        }
         const bool sam = suf == ".SAM";
         const int fd = open(path.c_str(), O_RDONLY);
         struct stat st;
@@ -232,25 +345,7 @@ extern "C" int bsx_methratio_main(int argc, char **argv) {
                 }
             });
             for (const std::string &e : errs) if (!e.empty()) { fprintf(stderr, "%s: %s\n", path.c_str(), e.c_str()); return 1; }
-            size_t tot = 0; uint32_t maxlen = 16;
-            std::vector<size_t> off((size_t)threads + 1, 0);
-            for (int t = 0; t < threads; t++) { off[t] = tot; tot += part[t].size(); for (const Aln &a : part[t]) maxlen = std::max(maxlen, a.len); }
-            off[threads] = tot;
-            if (tot > 0xffffffffull) { fprintf(stderr, "too many alignments in one piece\n"); return 1; }
-            const uint32_t stride = (std::min<uint32_t>(maxlen, 65535u) + 15u) & ~15u;
-            std::vector<char> sq(tot * stride); std::vector<uint16_t> len(tot); std::vector<uint32_t> chr(tot), pos(tot);
-            std::vector<uint8_t> strand(tot), flags(tot); std::vector<int32_t> ins(tot), mate(tot);
-            bsx_parallel(threads, (size_t)threads, [&](int t, size_t, size_t) {
-                size_t i = off[t];
-                for (const Aln &a : part[t]) {
-                    const uint32_t l = std::min(a.len, stride);
-                    memcpy(&sq[i * stride], a.seq, l);
-                    len[i] = (uint16_t)l; chr[i] = a.chr; pos[i] = a.pos; strand[i] = a.strand; flags[i] = a.flags; ins[i] = a.insert; mate[i] = a.mate;
-                    i++;
-                }
-            });
-            if (bsx_meth_add(mh, &m.o, (uint32_t)tot, sq.data(), stride, len.data(), chr.data(), pos.data(), strand.data(), ins.data(), mate.data(),
-                             flags.data(), &nmap) != BSX_OK) { fprintf(stderr, "%s\n", bsx_last_error()); return 1; }
+            if (!pile(part)) return 1;
             p0 = p1;
         }
         munmap((void *)p, n); close(fd);

@@ -187,6 +187,8 @@ static int gunzip_file(const char *path, std::vector<char> &out) {
     return bad ? BSX_ERR_IO : BSX_OK;
 }
 
+int bsx_inflate_file(const char *path, std::vector<char> &out) { return gunzip_file(path, out); }
+
 int bsx_host_threads(int requested) {
     if (requested > 0) return requested > 64 ? 64 : requested;
     if (const char *e = getenv("BSX_THREADS")) { int v = atoi(e); if (v > 0) return v > 64 ? 64 : v; }

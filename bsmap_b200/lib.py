@@ -50,7 +50,7 @@ PAIR_REC = np.dtype([("a_loc", "<u4"), ("a_chr", "<u4"), ("b_loc", "<u4"), ("b_c
 
 class MethOpts(C.Structure):
     """bsx_meth_opts (include/bsmap_b200.h): methratio.py's options"""
-    _fields_ = [(k, C.c_int32) for k in ("unique", "pair", "meth0", "trim_fillin", "combine_cpg", "min_depth")]
+    _fields_ = [(k, C.c_int32) for k in ("unique", "pair", "meth0", "trim_fillin", "combine_cpg", "min_depth", "rm_dup")]
 
 
 EXPORTS = [

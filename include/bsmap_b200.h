@@ -249,13 +249,15 @@ size_t bsx_emit_pe(const bsx_index *ix, const bsx_params *p, const bsx_reads *a,
 int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path, int threads);
 
 /* --- methratio.py (methylation ratios from the mappings) on the device -------------------------- */
-typedef struct bsx_meth_opts {   /* methratio.py:5-16; -r (remove duplicates) is not supported */
+typedef struct bsx_meth_opts {   /* methratio.py:5-16 */
     int32_t unique;        /* -u  process only unique mappings / pairs                         */
     int32_t pair;          /* -p  process only properly paired mappings                        */
     int32_t meth0;         /* -z  report loci with zero methylation ratios                     */
     int32_t trim_fillin;   /* -t  trim N end-repairing fill-in nucleotides (default 2)         */
     int32_t combine_cpg;   /* -g  combine CpG methylation ratios on both strands               */
     int32_t min_depth;     /* -m  report loci with sequencing depth >= FOLD (default 1)        */
+    int32_t rm_dup;        /* -r  remove duplicated reads: the first alignment (in the order given) per
+                            *     (sequence, fragment end, direction) counts; +8 bytes of HBM per position */
 } bsx_meth_opts;
 #define BSX_METH_SECONDARY 1u   /* alignment flag: not a unique mapping (SAM 's' / BSP flag != UM)      */
 #define BSX_METH_PROPER    2u   /* alignment flag: properly paired       (SAM 'P' / BSP insert != 0)    */
@@ -284,7 +286,7 @@ int bsx_meth_download(bsx_meth *m, const bsx_meth_opts *o, uint32_t k, uint32_t 
  * stats: covered cytosines, their summed depth.  Returns bytes written. */
 size_t bsx_meth_write(bsx_meth *m, const bsx_meth_opts *o, const char *const *seqs, const uint32_t *lens,
                       const uint8_t *chroms /* n_seq flags or NULL */, int threads, int fd, uint64_t *stats);
-/* the methratio.py command line: -o -d [-c -u -p -z -q -t -g -m] files... (SAM and BSP; -r, -s, .bam refused) */
+/* the methratio.py command line: -o -d [-c -u -p -z -q -t -g -m] files... (SAM and BSP; -s, .bam refused) */
 int bsx_methratio_main(int argc, char **argv);
 
 /* --- the bsmap command line (main.cpp:441-476): same options, same output files -------------- */

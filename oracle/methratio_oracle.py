@@ -9,7 +9,8 @@ Follows /root/reference/methratio.py line by line:
   pileup         (methratio.py:95-118)  per reference C (Watson hits) / G (Crick hits): T/A -> depth, C/G -> meth+depth
   combine CpG    (methratio.py:122-131)
   report         (methratio.py:133-154) ratio and Wilson interval, %.3f
-Not restated: -r (remove duplicates; order-dependent) -- out of scope for the device path, see DESIGN.md.
+  -r             (methratio.py:52-55)   of the alignments that pass the filters, the first one in file order per
+                                        (chromosome, fragment end, direction) counts; tested before trimming
 """
 from __future__ import annotations
 
@@ -77,7 +78,7 @@ def trim(seq, strand, pos, insert, mate_pos, sam, trim_fillin):
     return seq, pos
 
 
-def methratio(names, seqs, files, chroms=None, unique=False, pair=False, meth0=False, trim_fillin=2, combine_cpg=False, min_depth=1):
+def methratio(names, seqs, files, chroms=None, unique=False, pair=False, meth0=False, trim_fillin=2, combine_cpg=False, min_depth=1, rm_dup=False):
     """names/seqs: the reference FASTA records (bytes or str).  -> (table text, (nmap, nc, nd))"""
     ref = {}
     for n, s in zip(names, seqs):
@@ -88,9 +89,15 @@ def methratio(names, seqs, files, chroms=None, unique=False, pair=False, meth0=F
     meth = {c: np.zeros(len(s), dtype=np.int64) for c, s in ref.items()}
     depth = {c: np.zeros(len(s), dtype=np.int64) for c, s in ref.items()}
     refarr = {c: np.frombuffer(s.encode(), dtype=np.uint8) for c, s in ref.items()}
+    coverage = {c: np.zeros(len(s), dtype=np.uint8) for c, s in ref.items()} if rm_dup else None
     nmap = 0
     for path in files:
         for seq, strand, cr, pos, insert, mate_pos, sam in parse_alignments(path, chroms, unique, pair):
+            if rm_dup:                                       # methratio.py:52-55
+                frag_end, direction = (pos + len(seq), 2) if strand in ("+-", "-+") else (pos, 1)
+                if coverage[cr][frag_end] & direction:
+                    continue
+                coverage[cr][frag_end] |= direction
             seq, pos = trim(seq, strand, pos, insert, mate_pos, sam, trim_fillin)
             if pos + len(seq) > len(ref[cr]):
                 continue

@@ -27,13 +27,16 @@ REF = "/root/reference/methratio.py"
 OUT = os.path.join(HERE, "methratio")
 FLAG_LETTERS = "pPuUrR12sfd"
 
-# (case, methratio options) -- every option the script has except -r and -s (samtools path)
+# (case, methratio options) -- every option the script has except -s (samtools path)
 RUNS = [
     ("se_cfg2_r0_uR", []), ("se_cfg2_r0_uR", ["-z", "-m", "2"]), ("se_cfg2_bsp", []), ("se_cfg2_bsp", ["-u", "-t", "0"]),
     ("se_cfg1", ["-u"]), ("se_cfg1", ["-g", "-z"]), ("se_n1", []), ("se_n1", ["-t", "5", "-g"]), ("se_mixed_A", ["-z"]),
     ("pe_sam", []), ("pe_sam", ["-p", "-u"]), ("pe_sam_v5_R", ["-t", "3", "-z"]), ("pe_readthrough", []), ("pe_readthrough", ["-p", "-g"]),
     ("pe_bsp_r0", []), ("pe_bsp_r0", ["-p"]), ("pe_n1", ["-c", "chr2,chr1"]), ("rrbs_se_A", ["-z"]), ("rrbs_pe", ["-t", "0"]),
     ("se_cfg5", ["-m", "3"]),
+    # -r: the first alignment (file order) of each (chromosome, fragment end, direction) counts
+    ("se_cfg2_r0_uR", ["-r"]), ("se_cfg2_bsp", ["-r", "-u"]), ("se_cfg5", ["-r", "-z"]), ("se_n1", ["-r", "-t", "0"]), ("pe_sam", ["-r"]),
+    ("pe_sam_v5_R", ["-r", "-p"]), ("pe_readthrough", ["-r", "-g"]), ("pe_bsp_r0", ["-r"]), ("rrbs_se_A", ["-r"]), ("rrbs_pe", ["-r", "-u"]),
 ]
 
 

@@ -53,7 +53,7 @@ def test_methratio_cli_option_grammar(tmp_path):
         assert r.returncode == 0, r.stderr
         assert open(out, "rb").read() == exp
     for argv, msg in ((["-d", fa] + files, "Missing output file"), (["-o", out] + files, "Missing reference file"),
-                      (["-o", out, "-d", fa], "at least one"), (["-o", out, "-d", fa, "-r"] + files, "not supported"),
+                      (["-o", out, "-d", fa], "at least one"),
                       (["-o", out, "-d", fa, "-t", "x"] + files, "invalid integer"), (["-o", out, "-d", fa, "-Q"] + files, "no such option")):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode == 2 and msg in r.stderr, (argv, r.stderr)
@@ -61,7 +61,8 @@ def test_methratio_cli_option_grammar(tmp_path):
     assert r.returncode == 1 and "BAM input is not supported" in r.stderr
 
 
-@pytest.mark.parametrize("name,kw", [("pe_readthrough", dict(pair=True)), ("se_n1", dict(trim_fillin=7, combine_cpg=True)), ("pe_bsp_r0", dict(unique=True))])
+@pytest.mark.parametrize("name,kw", [("pe_readthrough", dict(pair=True)), ("se_n1", dict(trim_fillin=7, combine_cpg=True)), ("pe_bsp_r0", dict(unique=True)),
+                                     ("rrbs_se_A", dict(rm_dup=True)), ("pe_bsp_r0", dict(rm_dup=True, pair=True)), ("pe_sam", dict(rm_dup=True, trim_fillin=0))])
 def test_meth_api_counters_equal_the_oracle(tmp_path, name, kw):
     """bsx_meth_add / bsx_meth_download through the C ABI: counters per position == the restatement's arrays"""
     case = CS.BY_NAME[name]
@@ -93,7 +94,12 @@ def test_meth_api_counters_equal_the_oracle(tmp_path, name, kw):
                 flags[k] |= (0 if col[3][:2] == "UM" else 1) | (0 if col[7] == "0" else 2)
             k += 1
     assert k == len(seqs)
-    mh.add(seqs, chrs, pos, strand, ins, mate, flags)
+    if kw.get("rm_dup"):                                        # several batches: a later batch loses against an earlier one
+        cut = [0, len(seqs) // 3, len(seqs) // 3 + 1, len(seqs)]
+        for b, e in zip(cut, cut[1:]):
+            mh.add(seqs[b:e], chrs[b:e], pos[b:e], strand[b:e], ins[b:e], mate[b:e], flags[b:e])
+    else:
+        mh.add(seqs, chrs, pos, strand, ins, mate, flags)
     txt, (nmap, nc, nd) = MO.methratio(names, d["gseqs"], files, **kw)
     assert mh.n_valid == nmap
     out = tmp_path / "api.txt"
@@ -123,6 +129,11 @@ def test_in_process_pileup_equals_the_reference_table(tmp_path, key):
     ix = B.Index(p, d["gnames"], d["gseqs"])
     mp = B.Mapper(ix, p, max_batch=1024, stride=160)          # several sub-batches: the hook runs per batch
     mh = B.Meth(ix, B.meth_opts(**kw))
+    if kw.get("rm_dup") and case.paired and not p.out_sam:     # two output files: the script's -r order is not the mapping order
+        with pytest.raises(B.BsxError, match="order of two files"):
+            mh.attach(mp, sam_rules=False)
+        mh.close(); mp.close(); ix.close()
+        return
     mh.attach(mp, sam_rules=bool(p.out_sam))
     if not case.paired:
         buf, lens = B.pack_reads(R.clip(case, d["seqs"]), stride=160)
@@ -144,7 +155,7 @@ def test_in_process_pileup_equals_the_reference_table(tmp_path, key):
     mh.close(); mp.close(); ix.close()
 
 
-@pytest.mark.parametrize("key", ["se_cfg2_r0_uR.default", "pe_sam.p_u", "pe_bsp_r0.default", "se_n1.t_5_g"])
+@pytest.mark.parametrize("key", ["se_cfg2_r0_uR.default", "pe_sam.p_u", "pe_bsp_r0.default", "se_n1.t_5_g", "rrbs_se_A.r", "pe_sam_v5_R.r_p"])
 def test_bsmap_cli_methratio_extension(tmp_path, key):
     """bsmap --methratio: the table of methratio.py without running it -- next to the alignment file, or instead of it"""
     ent = MANIFEST[key]
@@ -153,7 +164,7 @@ def test_bsmap_cli_methratio_extension(tmp_path, key):
     fa, a, b = CS.write_inputs(case, str(tmp_path))
     o = str(tmp_path / ("out." + case.out_ext))
     o2 = str(tmp_path / "out_unpair.bsp") if (case.paired and case.out_ext != "sam") else None
-    flags = {"-u": ["--meth-unique"], "-p": ["--meth-pair"], "-z": ["--meth-zero"], "-g": ["--meth-cpg"]}
+    flags = {"-u": ["--meth-unique"], "-p": ["--meth-pair"], "-z": ["--meth-zero"], "-g": ["--meth-cpg"], "-r": ["--meth-rmdup"]}
     ext, it = [], iter(ent["opts"])
     for x in it:
         ext += flags[x] if x in flags else [{"-t": "--meth-trim", "-m": "--meth-min-depth"}[x], next(it)]
