@@ -356,20 +356,30 @@ static const uint8_t *class_table() {
 // UnmaskRegion (dbseq.cpp:114-142): maximal runs that start at the first ACGTacgt, end at the first
 // NXnx (or the sequence end), kept when >= 30 nt; never merged (the merge test is dead code, it
 // compares against the rc block pushed just before).
-static void unmask_region(const char *seq, uint32_t len, uint32_t id, uint32_t T, std::vector<bsx_block> &out) {
+// The scan is a two-state machine driven only by the class-1 (start) and class-2 (end) characters, so a sequence is cut
+// into pieces scanned on all host threads -- each keeps the positions where the class changes -- and the pieces' short
+// event lists are stitched in order.
+static void unmask_region(const char *seq, uint32_t len, uint32_t id, uint32_t T, std::vector<bsx_block> &out, int threads) {
     const uint8_t *cls = class_table();
     const uint8_t *s = (const uint8_t *)seq;
-    uint32_t e = 0;
-    while (e < len) {
-        uint32_t b = e;
-        while (b < len && cls[s[b]] != 1) b++;
-        if (b >= len) break;
-        e = b;
-        while (e < len && cls[s[e]] != 2) e++;
-        if (e - b < 30) continue;
-        out.push_back({id, b, e});
-        out.push_back({id + 1, T - e, T - b});
-    }
+    struct Ev { uint32_t pos; uint8_t c; };
+    const size_t pieces = std::max<size_t>(1, std::min<size_t>((size_t)threads * 4, len / (1u << 20)));
+    std::vector<std::vector<Ev>> ev(pieces);
+    bsx_parallel(threads, pieces, [&](int, size_t pb, size_t pe) {
+        for (size_t pc = pb; pc < pe; pc++) {
+            const uint32_t b = (uint32_t)((uint64_t)len * pc / pieces), e = (uint32_t)((uint64_t)len * (pc + 1) / pieces);
+            uint8_t last = 0;
+            for (uint32_t q = b; q < e; q++) { const uint8_t c = cls[s[q]]; if (c != 0 && c != last) { ev[pc].push_back({q, c}); last = c; } }
+        }
+    });
+    bool inside = false; uint32_t b = 0;
+    auto close = [&](uint32_t e) { if (e - b >= 30) { out.push_back({id, b, e}); out.push_back({id + 1, T - e, T - b}); } };
+    for (const std::vector<Ev> &v : ev)
+        for (const Ev &x : v) {
+            if (x.c == 1 && !inside) { inside = true; b = x.pos; }
+            else if (x.c == 2 && inside) { inside = false; close(x.pos); }
+        }
+    if (inside) close(len);
 }
 
 void bsx_index_free_device(bsx_index *ix) {
@@ -445,6 +455,20 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
     BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_refcat, 0, ix->n_words * 4, st));    // margins defined as zero (App. B Q5)
     BSX_CUDA_CHECK(cudaMemsetAsync(ix->d_crefcat, 0, ix->n_words * 4, st));
 
+    // --- blocks (UnmaskRegion): a host scan of the ASCII on all threads, while the sequences go to the device below
+    std::vector<bsx_block> &blocks = ix->blocks;
+    std::thread block_scan;
+    if (!p.rrbs && !packed && !ix->ref_only) {
+        blocks.clear();
+        block_scan = std::thread([ix, seqs, &blocks] {
+            const int threads = bsx_host_threads(0);
+            for (uint32_t k = 0; k < ix->n_seq; k++) unmask_region(seqs[k], ix->size[k], 2 * k, ix->rc_offset[k], blocks, threads);
+            std::stable_sort(blocks.begin(), blocks.end(), [](const bsx_block &a, const bsx_block &b) {
+                return a.id < b.id || (a.id == b.id && a.begin < b.begin); });
+        });
+    }
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } block_scan_joiner{block_scan};   // error returns below
+
     // --- K0: pack every sequence (ASCII staged through one device buffer), or take the packed forward strand as is
     cudaEventRecord(ev0, st);
     float ms_total = 0;
@@ -476,17 +500,10 @@ int bsx_index_build_device(bsx_index *ix, const char *const *seqs, const uint32_
         return upload_seqinfo(ix);
     }
 
-    // --- blocks (host scan of the ASCII; UnmaskRegion) and RRBS sites (find_CCGG)
-    std::vector<bsx_block> &blocks = ix->blocks;
+    // --- RRBS sites (find_CCGG)
     std::vector<uint32_t> rr_loc, rr_tag;
-    if (!p.rrbs) {
-        if (!packed) {
-            blocks.clear();
-            for (uint32_t k = 0; k < ix->n_seq; k++) unmask_region(seqs[k], ix->size[k], 2 * k, ix->rc_offset[k], blocks);
-            std::stable_sort(blocks.begin(), blocks.end(), [](const bsx_block &a, const bsx_block &b) {
-                return a.id < b.id || (a.id == b.id && a.begin < b.begin); });
-        }
-    } else {
+    if (block_scan.joinable()) block_scan.join();
+    if (p.rrbs) {
         const int max_seg = (BSX_FIXWORDS - 1) * 16 / s;      // dbseq.cpp:217
         const int sl = (int)strlen(p.digest_site), dp = p.digest_pos;
         const bool mirror = p.pairend || p.chains;

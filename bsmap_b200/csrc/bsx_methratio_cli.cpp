@@ -1,12 +1,12 @@
 // bsx_methratio_cli.cpp -- the reference's `methratio.py` command line over the C ABI.
 //
-//   methratio -o OUT -d REF.fa [-c chr1,chr2] [-u] [-p] [-z] [-q] [-t N] [-g] [-m FOLD] MAPPING_FILES...
+//   methratio -o OUT -d REF.fa [-c chr1,chr2] [-u] [-p] [-z] [-q] [-r] [-t N] [-g] [-m FOLD] MAPPING_FILES...
 //
 // Same options and output as methratio.py:5-16 / 133-154.  Mapping files are BSMAP's SAM (text; FLAG numeric as
-// BSMAP writes it, or lettered as `samtools view -X` prints it) or BSP output; the format follows the file
-// suffix like the script does.  The files are memory-mapped and parsed on all host threads; the pile-up runs on
-// the GPU (bsx_meth.cu).  Refused with a message: -r (duplicate removal depends on file order), .bam input
-// (needs a BGZF codec), -s (no samtools involved).
+// BSMAP writes it, or lettered as `samtools view -X` prints it), BAM (decoded here instead of being piped through
+// `samtools view -X`) or BSP output; the format follows the file suffix like the script does.  Text files are
+// memory-mapped and parsed on all host threads; the pile-up, and -r's "first alignment in file order wins", run on the
+// GPU (bsx_meth.cu).  -s (path to samtools) is accepted and ignored: nothing here shells out.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>

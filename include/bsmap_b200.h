@@ -286,7 +286,7 @@ int bsx_meth_download(bsx_meth *m, const bsx_meth_opts *o, uint32_t k, uint32_t 
  * stats: covered cytosines, their summed depth.  Returns bytes written. */
 size_t bsx_meth_write(bsx_meth *m, const bsx_meth_opts *o, const char *const *seqs, const uint32_t *lens,
                       const uint8_t *chroms /* n_seq flags or NULL */, int threads, int fd, uint64_t *stats);
-/* the methratio.py command line: -o -d [-c -u -p -z -q -t -g -m] files... (SAM and BSP; -s, .bam refused) */
+/* the methratio.py command line: -o -d [-c -u -p -z -q -r -t -g -m -s] files... (SAM, BAM and BSP; -s is ignored) */
 int bsx_methratio_main(int argc, char **argv);
 
 /* --- the bsmap command line (main.cpp:441-476): same options, same output files -------------- */

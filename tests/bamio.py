@@ -47,3 +47,42 @@ def write_sam(path, records):
     with open(path, "w") as f:
         for name, flag, seq, qual in records:
             f.write("\t".join([name, str(flag), "*", "0", "0", "*", "*", "0", "0", seq or "*", qual if qual is not None else "*"]) + "\n")
+
+
+def bam_to_sam_text(path) -> str:
+    """an aligned BAM file as headerless SAM text (what `samtools view` prints, numeric FLAG; Z / A / integer tags only):
+    lets the methratio oracle, which reads text, see the records of a BAM file in the file's own order"""
+    import gzip
+    raw = gzip.open(path, "rb").read()
+    assert raw[:4] == b"BAM\1"
+    l_text, = struct.unpack_from("<i", raw, 4)
+    o = 8 + l_text
+    n_ref, = struct.unpack_from("<i", raw, o); o += 4
+    names = []
+    for _ in range(n_ref):
+        ln, = struct.unpack_from("<i", raw, o)
+        names.append(raw[o + 4:o + 4 + ln - 1].decode()); o += 4 + ln + 4
+    out = []
+    while o + 4 <= len(raw):
+        bs, = struct.unpack_from("<i", raw, o)
+        b = raw[o + 4:o + 4 + bs]; o += 4 + bs
+        ref, pos, l_name, mapq, _bin, n_cig, flag, l_seq, nref, npos, tlen = struct.unpack_from("<iiBBHHHiiii", b, 0)
+        x = 32
+        qname = b[x:x + l_name - 1].decode(); x += l_name
+        cig = "".join("%d%s" % (v >> 4, "MIDNSHP=X"[v & 15]) for v in struct.unpack_from("<%dI" % n_cig, b, x)) or "*"; x += 4 * n_cig
+        seq = "".join(NT16[(b[x + (i >> 1)] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq)) or "*"; x += (l_seq + 1) // 2
+        qual = "*" if l_seq == 0 or b[x] == 0xff else "".join(chr(c + 33) for c in b[x:x + l_seq]); x += l_seq
+        tags = []
+        while x + 3 <= len(b):
+            tg, ty = b[x:x + 2].decode(), chr(b[x + 2]); x += 3
+            if ty == "Z":
+                e = b.index(b"\0", x); tags.append("%s:Z:%s" % (tg, b[x:e].decode())); x = e + 1
+            elif ty == "A":
+                tags.append("%s:A:%s" % (tg, chr(b[x]))); x += 1
+            else:
+                fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I"}[ty]
+                tags.append("%s:i:%d" % (tg, struct.unpack_from(fmt, b, x)[0])); x += struct.calcsize(fmt)
+        rn = names[ref] if ref >= 0 else "*"
+        rnext = "*" if nref < 0 else ("=" if nref == ref else names[nref])
+        out.append("\t".join([qname, str(flag), rn, str(pos + 1), str(mapq), cig, rnext, str(npos + 1), str(tlen), seq, qual] + tags))
+    return "\n".join(out) + ("\n" if out else "")

@@ -6,7 +6,10 @@ so the script is run from /root/reference through three MECHANICAL adaptations (
   * `print >> sys.stderr, x` / `print x`  ->  print(...)      * `xrange` -> `range`
   * `os.popen('<samtools> view -XS file')` -> a reader that yields the SAM body with FLAG rendered the way
     samtools 0.1.x `-X` renders it (one letter per set bit: p P u U r R 1 2 s f d for 0x1 ... 0x400).
-Run in the build container:  python tests/golden/make_methratio_golden.py
+BAM input (BAM_RUNS) goes through the REAL vendored samtools built by `make -C oracle ref`: the golden SAM is turned
+into a sorted BAM by `samtools view -bS | samtools sort` (what the reference's sam2bam.sh does) and the script reads it
+through its own `os.popen('samtools view -X file.bam')`, untouched.
+Run in the build container:  make -C oracle ref && python tests/golden/make_methratio_golden.py
 The adapted source is never written to the repo; only its outputs are (as fixtures), with this script.
 """
 import gzip
@@ -40,6 +43,11 @@ RUNS = [
 ]
 
 
+# (case, methratio options) on the case's golden SAM converted to a sorted BAM; -r then follows the sorted order
+BAM_RUNS = [("se_cfg2_r0_uR", []), ("pe_sam", ["-r"]), ("rrbs_se_A", ["-r", "-u"]), ("pe_readthrough", ["-p", "-g"]), ("rrbs_pe", ["-r", "-t", "0"])]
+SAMTOOLS_DIR = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref")
+
+
 def samtools_view_X(path):
     """the SAM body (no header) with the FLAG column as samtools 0.1.x -X prints it"""
     out = io.StringIO()
@@ -60,7 +68,7 @@ def adapted_source():
     src = re.sub(r"print >> sys\.stderr, (.*)$", r"print(\1, file=sys.stderr)", src, flags=re.M)
     src = re.sub(r"^print (.*)$", r"print(\1)", src, flags=re.M)
     src = src.replace("os.popen('%ssamtools view -XS %s' % (options.sam_path, infile))", "samtools_view_X(infile)")
-    src = src.replace("os.popen('%ssamtools view -X %s' % (options.sam_path, infile))", "samtools_view_X(infile)")
+    # the .BAM branch keeps its os.popen('%ssamtools view -X %s'): BAM_RUNS pass -s <oracle/_ref>
     return src
 
 
@@ -103,6 +111,24 @@ def main():
         with gzip.GzipFile(os.path.join(OUT, key + ".txt.gz"), "wb", mtime=0) as f:
             f.write(txt)
         manifest[key] = dict(case=name, opts=opts, lines=txt.count(b"\n"), stdout=stdout.strip())
+        print(key, manifest[key]["lines"], stdout.strip())
+    import subprocess
+    for name, opts in BAM_RUNS:
+        case = CS.BY_NAME[name]
+        with tempfile.TemporaryDirectory() as td:
+            fa, _, _ = CS.write_inputs(case, td)
+            main_txt, _ = R.golden_load(case)
+            sam = os.path.join(td, "aln.sam")
+            open(sam, "wb").write(main_txt)
+            st = os.path.join(SAMTOOLS_DIR, "samtools")
+            subprocess.run(f"{st} view -bS {sam} > {td}/tmp.bam 2>/dev/null && {st} sort {td}/tmp.bam {td}/aln", shell=True, check=True)
+            out = os.path.join(td, "meth.txt")
+            stdout = run_reference(["-o", out, "-d", fa, "-q", "-s", SAMTOOLS_DIR] + opts + [os.path.join(td, "aln.bam")])
+            txt = open(out, "rb").read()
+        key = f"{name}.bam.{tag(opts)}"
+        with gzip.GzipFile(os.path.join(OUT, key + ".txt.gz"), "wb", mtime=0) as f:
+            f.write(txt)
+        manifest[key] = dict(case=name, opts=opts, lines=txt.count(b"\n"), stdout=stdout.strip(), bam=True)
         print(key, manifest[key]["lines"], stdout.strip())
     json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1, sort_keys=True)
 

@@ -103,6 +103,38 @@ def test_index_matches_oracle(name):
     ix.close(); oref.close()
 
 
+def test_index_of_a_long_masked_sequence():
+    """UnmaskRegion on a sequence long enough for the piecewise host scan (bsx_index.cu: pieces of >= 1 Mb stitched in order):
+    N / X runs, IUPAC letters that neither start nor end a block, lower case, islands shorter than 30 nt, runs across
+    piece borders, a block that reaches the sequence end -- table and every list equal the oracle's"""
+    rng = np.random.default_rng(5)
+    L = 5_300_000
+    g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].copy()
+    lower = rng.random(L) < 0.05
+    g[lower] += 32
+    for _ in range(4000):                                    # masked runs of every length, some back to back
+        b, n = int(rng.integers(0, L)), int(rng.choice([1, 2, 5, 29, 30, 31, 200, 5000]))
+        g[b:b + n] = rng.choice(np.frombuffer(b"NXnx", dtype=np.uint8))
+    for _ in range(3000):                                    # letters of class 0: inside a block they continue it, outside they do not start one
+        b, n = int(rng.integers(0, L)), int(rng.integers(1, 40))
+        g[b:b + n] = rng.choice(np.frombuffer(b"RYKMryBD-", dtype=np.uint8))
+    for piece in range(1, 20):                               # runs straddling the borders of the scan pieces (any thread count up to 64)
+        for parts in (4, 8, 16, 20, 32, 64, 128, 256):
+            q = L * piece // parts
+            if 0 < q < L - 50:
+                g[q - 3:q + 4] = ord("N") if piece % 2 else ord("R")
+    g[:40] = ord("N"); g[-100:] = np.frombuffer(b"ACGT" * 25, dtype=np.uint8)
+    names, seqs = ["long", "short"], [g.tobytes(), (b"ACGTTGCA" * 40) + b"N" * 7 + (b"GATTACA" * 30)]
+    kw = dict(s=12, I=4)
+    oref = O.OracleRef(O.make_params(**kw), names, seqs)
+    ix = B.Index(B.make_params(**kw), names, seqs)
+    assert (ix.info.n_words, ix.info.n_entries) == (oref.n_words, oref.n_entries)
+    for what in ("refcat", "crefcat", "anchor", "tab", "pos"):
+        msg = _diff_arrays(what, ix.download(what), np.array(getattr(oref, what)))
+        assert msg is None, msg
+    ix.close(); oref.close()
+
+
 def _run_gpu(case, max_batch=4096, stride=160):
     d = case.data()
     p = B.make_params(**case.param_kwargs())
