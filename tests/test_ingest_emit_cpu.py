@@ -219,7 +219,7 @@ def test_reference_fasta_loader(tmp_path):
     names = ["chr%d" % k for k in range(len(seqs))]
     with open(fa, "wb") as f:
         for k, s in enumerate(seqs):
-            f.write(b">  chr%d some description\r\n" % k if k == 1 else b">chr%d some description\n" % k)
+            f.write(b">  chr%d some description\r\n" % k if k == 1 else b">chr%d some >description with a > inside\n" % k)
             for i in range(0, len(s), 60):
                 f.write(s[i:i + 60] + (b" \r\n" if k & 1 else b"\n"))
     p = B.make_params()
