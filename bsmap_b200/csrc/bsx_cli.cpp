@@ -180,8 +180,9 @@ struct SlotPool {
     int take() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !free_.empty(); }); const int s = free_.back(); free_.pop_back(); return s; }
 };
 
-struct Views { std::vector<bsx_view> name, seq, qual; std::vector<std::string> store; };
-void take_views(bsx_reads *r, Views &v) { v.name.swap(r->name); v.seq.swap(r->seq); v.qual.swap(r->qual); v.store.swap(r->slow_store); }
+struct Views { std::vector<bsx_view> name, seq, qual; std::vector<std::string> store; std::vector<std::shared_ptr<std::vector<char>>> keep; };
+// the batch's views leave the reader: with them the strings and the stream windows they point into
+void take_views(bsx_reads *r, Views &v) { v.name.swap(r->name); v.seq.swap(r->seq); v.qual.swap(r->qual); v.store.swap(r->slow_store); v.keep.swap(r->keep); }
 
 struct Job { uint32_t n = 0; int slot = 0; unsigned done_index = 0; Views a, b; };
 struct Text { std::vector<std::string> main, unpair; unsigned done_index = 0; };

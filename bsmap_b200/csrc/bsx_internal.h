@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <memory>
 #include <vector>
 #include <thread>
 #include <cuda_runtime.h>
@@ -58,7 +59,15 @@ struct bsx_view { const char *p; uint32_t n; };
 struct bsx_reads {
     int fd = -1;
     const char *p = nullptr; size_t n = 0; bool mapped = false;
-    std::vector<char> owned;               // non-mappable inputs (pipes) are slurped
+    // Streamed inputs (gzip'ed text, pipes): p / n / pos describe a WINDOW of the inflated stream, refilled as the
+    // cutter advances (bsx_reads.cpp: stream_ensure); `keep` holds every window the current batch's views point into, so
+    // a pipeline that moves the views on (bsx_cli.cpp: take_views) moves `keep` with them.  Memory stays bounded by the
+    // batches in flight, whatever the size of the file.
+    void *gz = nullptr;                    // gzFile; reads plain data transparently
+    bool stream_eof = true;                // nothing left to inflate (always true for mapped files)
+    bool win_starts_line = true;           // the window's first byte follows a line feed
+    std::shared_ptr<std::vector<char>> win;
+    std::vector<std::shared_ptr<std::vector<char>>> keep;
     size_t pos = 0;
     int kind = 0;                          // _file_format: 0 FASTQ, 1 FASTA, 3 BAM
     int readset = 0;                       // BAM: 0 single-end, 1 / 2 = file a / b of a pair (interleaved mates)

@@ -118,6 +118,7 @@ uint32_t fast_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, ui
     }
     const double wbytes = (double)want * r->rec_bytes * 1.03 + 4096;
     const size_t wend = wbytes >= (double)(r->n - r->pos) ? r->n : r->pos + (size_t)wbytes;
+    if (wend == r->n && !r->stream_eof) { r->rec_bytes *= 2; *bad = false; return 0; }   // streamed input: the caller widens the window first
 #ifdef MADV_POPULATE_READ
     // map the window's pages with one call: faulting them in one by one from all cutter threads serialises on the
     // address-space lock (measured: 8 threads no faster than 1)
@@ -190,6 +191,27 @@ static int gunzip_file(const char *path, std::vector<char> &out) {
 
 int bsx_inflate_file(const char *path, std::vector<char> &out) { return gunzip_file(path, out); }
 
+// Streamed input: make the window hold at least `need` unread bytes, or everything up to the end of the stream.  The unread
+// tail moves to the front of a fresh window; the old one stays alive through r->keep for the views of the current batch.
+static void stream_ensure(bsx_reads *r, size_t need) {
+    if (r->stream_eof || r->n - r->pos >= need) return;
+    const size_t have = r->n - r->pos;
+    need += (size_t)8 << 20;                                 // refills stay rare when the caller advances in small steps
+    auto nw = std::make_shared<std::vector<char>>(need);
+    if (have) memcpy(nw->data(), r->p + r->pos, have);
+    r->win_starts_line = r->pos == 0 ? r->win_starts_line : r->p[r->pos - 1] == '\n';
+    size_t fill = have;
+    while (fill < need) {
+        const int got = gzread((gzFile)r->gz, nw->data() + fill, (unsigned)std::min<size_t>(need - fill, (size_t)1 << 30));
+        if (got <= 0) { r->stream_eof = true; break; }
+        fill += (size_t)got;
+    }
+    nw->resize(fill);
+    r->win = nw; r->keep.push_back(nw);
+    r->p = nw->data(); r->n = fill; r->pos = 0;
+}
+static inline bool at_line_start(const bsx_reads *r) { return r->pos == 0 ? r->win_starts_line : r->p[r->pos - 1] == '\n'; }
+
 int bsx_host_threads(int requested) {
     if (requested > 0) return requested > 64 ? 64 : requested;
     if (const char *e = getenv("BSX_THREADS")) { int v = atoi(e); if (v > 0) return v > 64 ? 64 : v; }
@@ -205,7 +227,8 @@ extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, 
     bsx_reads *r = new bsx_reads();
     r->fd = fd; r->zero_qual = zero_qual; r->max_readlen = max_readlen;
     struct stat st;
-    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+    const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+    if (regular) {
         r->n = (size_t)st.st_size;
         if (r->n) {
             void *m = mmap(nullptr, r->n, PROT_READ, MAP_PRIVATE, fd, 0);
@@ -213,15 +236,21 @@ extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, 
             madvise(m, r->n, MADV_SEQUENTIAL); madvise(m, r->n, MADV_WILLNEED);
             r->p = (const char *)m; r->mapped = true;
         }
-    } else {   // pipe: slurp
-        char buf[1 << 16]; ssize_t g;
-        while ((g = read(fd, buf, sizeof buf)) > 0) r->owned.insert(r->owned.end(), buf, buf + g);
-        r->p = r->owned.data(); r->n = r->owned.size();
     }
-    if (is_gzip(r->p, r->n)) {
+    if (!regular || is_gzip(r->p, r->n)) {
+        // gzip'ed files and pipes are streamed through zlib (which passes plain data through): a window at a time
         if (r->mapped) { munmap((void *)r->p, r->n); r->mapped = false; }
-        if (gunzip_file(path, r->owned) != BSX_OK) { close(fd); delete r; bsx_set_error("failed to inflate gzip read file: %s", path); return BSX_ERR_IO; }
-        r->p = r->owned.data(); r->n = r->owned.size();
+        r->p = nullptr; r->n = 0;
+        r->gz = regular ? (void *)gzopen(path, "rb") : (void *)gzdopen(fd, "rb");
+        if (!r->gz) { close(fd); delete r; bsx_set_error("failed to open read file: %s", path); return BSX_ERR_IO; }
+        if (!regular) r->fd = -1;                              // gzclose closes the descriptor it was given
+        gzbuffer((gzFile)r->gz, 1 << 20);
+        r->stream_eof = false;
+        stream_ensure(r, (size_t)1 << 20);
+        if (r->n >= 4 && memcmp(r->p, "BAM\1", 4) == 0) {      // BAM (BGZF members are gzip members): taken whole, as before
+            size_t want = (size_t)64 << 20;
+            while (!r->stream_eof) { stream_ensure(r, want); want *= 2; }
+        }
     }
     // CheckFile (reads.cpp:19-50): the first non-blank character decides; anything else is tried as BAM
     size_t q = 0; while (q < r->n && ws((unsigned char)r->p[q])) q++;
@@ -249,6 +278,7 @@ extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, 
 extern "C" void bsx_reads_close(bsx_reads *r) {
     if (!r) return;
     if (r->mapped) munmap((void *)r->p, r->n);
+    if (r->gz) gzclose((gzFile)r->gz);
     if (r->fd >= 0) close(r->fd);
     delete r;
 }
@@ -259,10 +289,18 @@ extern "C" void bsx_reads_force_token_reader(bsx_reads *r, int on) { if (r) r->f
 extern "C" void bsx_reads_skip(bsx_reads *r, uint64_t n_reads) {
     if (!r) return;
     if (r->kind == 3) return;   // reference quirk: CheckFile's -B skip covers _file_format 0..2 only, BAM is 3 (reads.cpp:54-75)
-    Tok t{r->p, r->n, r->pos};
     const uint64_t nl = n_reads * (r->kind == 0 ? 4u : 2u);
-    for (uint64_t i = 0; i < nl && t.pos < t.n; i++) t.skipline();
-    r->pos = t.pos;
+    for (uint64_t i = 0; i < nl; i++) {
+        stream_ensure(r, (size_t)4 << 20);
+        r->keep.clear();                                     // no views point into the windows left behind
+        if (r->pos >= r->n) break;
+        for (;;) {   // a line may run past the window of a streamed input
+            const void *q = memchr(r->p + r->pos, '\n', r->n - r->pos);
+            if (q) { r->pos = (size_t)((const char *)q - r->p) + 1; break; }
+            if (r->stream_eof) { r->pos = r->n; break; }
+            stream_ensure(r, (r->n - r->pos) * 2 + ((size_t)4 << 20));
+        }
+    }
 }
 
 // BAM records (reads.cpp:120-143): name = qname, bases through bam_nt16_rev_table, qualities + 33, truncated to
@@ -313,12 +351,16 @@ extern "C" uint32_t bsx_reads_next(bsx_reads *r, uint32_t want, uint32_t stride,
     threads = bsx_host_threads(threads);
     r->name.resize(want); r->seq.resize(want); r->qual.resize(want);
     r->slow_store.clear();
+    r->keep.clear();
+    if (r->win) r->keep.push_back(r->win);
     uint32_t got = 0;
     if (r->kind == 3) return bam_batch(r, want, stride, seqs, lens);
-    bool line_start = r->pos == 0 || r->p[r->pos - 1] == '\n';
+    bool line_start = at_line_start(r);
     std::vector<size_t> slow_slots;
     std::string nm, sq, ql;
     while (got < want) {
+        // streamed input: the records still wanted plus a margin no single record outgrows, or the rest of the stream
+        if (!r->stream_eof) stream_ensure(r, (size_t)((double)(want - got) * std::max(r->rec_bytes, 64.0) * 1.25) + ((size_t)4 << 20));
         if (!r->force_slow && !line_start) line_start = resume_at_line_start(r);
         if (!r->force_slow && line_start) {
             bool bad = true;

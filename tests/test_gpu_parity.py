@@ -466,6 +466,26 @@ def test_cli_maps_on_several_devices_in_input_order(name, tmp_path):
     assert len(used) >= 2, r.stderr[-1500:]     # more than one mapper thread took batches
 
 
+@pytest.mark.parametrize("name", ["se_mixed_A", "pe_sam"])
+def test_cli_streams_gzipped_reads(name, tmp_path):
+    """gzip'ed read files go through the windowed stream reader; with small batches several windows are alive in the cut ->
+    map -> format pipeline at once (the views of a batch keep theirs) -> the reference's bytes all the same"""
+    import gzip, subprocess
+    case = CS.BY_NAME[name]
+    exe = os.path.join(os.path.dirname(BL.LIB_PATH), "bsmap")
+    fa, a, b = CS.write_inputs(case, str(tmp_path))
+    for f in (a, b):
+        if f:
+            with gzip.open(f + ".gz", "wb", compresslevel=1) as g:
+                g.write(open(f, "rb").read())
+    o = str(tmp_path / ("out." + case.out_ext))
+    r = subprocess.run([exe] + case.cli(a + ".gz", b + ".gz" if b else None, fa, o, None) + ["-p", "4"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, BSX_CLI_BATCH="193"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got, exp = open(o, "rb").read(), R.golden_load(case)[0]
+    assert got == exp, R.first_diff(got, exp)
+
+
 def test_cli_option_grammar(tmp_path):
     """-x=val form, unknown option exit code = argv index (main.cpp:452-455)"""
     import subprocess

@@ -273,3 +273,70 @@ def test_emit_reproduces_reference_text(tmp_path, case, threads):
     assert head + txt == exp_main, R.first_diff(head + txt, exp_main)
     assert un == exp_un, R.first_diff(un, exp_un)
     ra.close()
+
+
+def _stream_corpus(n_rec=60_000, seed=9):
+    """a FASTQ text of ~15 MB (several stream windows at small batch sizes): regular records with irregular ones sprinkled in
+    -- CRLF, blank lines, leading blanks, a long wrapped-looking record -- so that both readers work across window borders"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_rec):
+        L = int(rng.integers(30, 145))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=L))
+        qual = bytes(rng.integers(33, 74, size=L).astype(np.uint8)).replace(b"@", b"A")
+        k = int(rng.integers(0, 400))
+        if k == 0:
+            out.append(b"@r%d extra words\r\n%s\r\n+\r\n%s\r\n" % (i, seq, qual))
+        elif k == 1:
+            out.append(b"\n\n@r%d\n%s\n+\n%s\n" % (i, seq, qual))
+        elif k == 2:
+            out.append(b"  @r%d\n %s\n+\n%s  \n" % (i, seq, qual))
+        else:
+            out.append(b"@r%d/1\n%s\n+\n%s\n" % (i, seq, qual))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("want", [1000, 16384])
+def test_streamed_gzip_reads_equal_the_mapped_file(tmp_path, want):
+    """gzip'ed read files are inflated a window at a time (bounded memory): same records, batch by batch, as the memory-mapped
+    plain file -- over many windows, with irregular records and -B style skips in between"""
+    import gzip
+    data = _stream_corpus()
+    plain, gz = tmp_path / "r.fq", tmp_path / "r.fq.gz"
+    plain.write_bytes(data)
+    with gzip.open(gz, "wb", compresslevel=1) as f:
+        f.write(data)
+    a, b = load_all(str(plain), want=want, stride=160), load_all(str(gz), want=want, stride=160)
+    assert a[0] == b[0] == "fastq" and len(a[1]) == 60_000
+    assert a == b
+    assert load_all(str(gz), want=want, stride=160, token=True) == a          # the token reader alone, window after window
+    for skip in (1, 12_345):
+        ra, rb = B.Reads(str(plain)), B.Reads(str(gz))
+        ra.skip(skip); rb.skip(skip)
+        na, _, _ = ra.next(500); nb, _, _ = rb.next(500)
+        assert na == nb == 500 and [ra.get(i) for i in range(500)] == [rb.get(i) for i in range(500)]
+        ra.close(); rb.close()
+
+
+def test_reads_from_a_pipe_are_streamed(tmp_path):
+    """a FIFO (e.g. `zcat x.gz |` or a process substitution): read through the same windows, plain or gzip'ed"""
+    import gzip
+    import threading
+    data = _stream_corpus(20_000, seed=4)
+    plain = tmp_path / "r.fq"
+    plain.write_bytes(data)
+    exp = load_all(str(plain), want=4096, stride=160)
+    for payload in (data, gzip.compress(data, 1)):
+        fifo = str(tmp_path / "fifo")
+        if os.path.exists(fifo):
+            os.unlink(fifo)
+        os.mkfifo(fifo)
+
+        def feed():
+            with open(fifo, "wb") as f:
+                f.write(payload)
+        t = threading.Thread(target=feed)
+        t.start()
+        got = load_all(fifo, want=4096, stride=160)
+        t.join()
+        assert got == exp

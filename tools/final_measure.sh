@@ -1,5 +1,6 @@
 # tools/final_measure.sh: everything the round's single-GPU numbers come from, on one GPU box (writes under gpurun_out/)
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+python -m pytest tests -x -q -m gpu > gpurun_out/t_final.log 2>&1; tail -2 gpurun_out/t_final.log
 python bench.py > gpurun_out/bench_r2_default.log 2>&1; tail -1 gpurun_out/bench_r2_default.log | cut -c1-300
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r2_ref.log 2>&1; tail -1 gpurun_out/bench_r2_ref.log | cut -c1-300
 for c in cfg1 cfg3 cfg4 cfg5; do
@@ -8,3 +9,8 @@ for c in cfg1 cfg3 cfg4 cfg5; do
 done
 # launch list of the default bench command (cold-cache, serialised: the kernel's share of the step, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_final.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/launch_r2_final.log 2>&1; tail -1 gpurun_out/launch_r2_final.log | cut -c1-120
+bash tools/ncu_kernel.sh r2h_se cfg2 bsx_map_se_wgbs 4000000 3
+bash tools/ncu_kernel.sh r2h_pe cfg3 bsx_map_pe 2000000 3
+bash tools/ncu_kernel.sh r2h_rrbs cfg4 bsx_map_se_rrbs 2000000 3
+bash tools/ncu_kernel.sh r2h_wide cfg5 bsx_map_se_wide 200000 3
+bash tools/cli_r2.sh
