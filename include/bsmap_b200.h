@@ -291,6 +291,8 @@ int bsx_methratio_main(int argc, char **argv);
 
 /* --- the bsmap command line (main.cpp:441-476): same options, same output files -------------- */
 int bsx_cli_main(int argc, char **argv);
+/* a stand-alone executable that will _exit() right after bsx_cli_main may skip the device teardown (1.8 s at 3.1 Gb) */
+void bsx_cli_exit_after_main(int on);
 
 #ifdef __cplusplus
 }
