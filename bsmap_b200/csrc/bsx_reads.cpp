@@ -247,24 +247,21 @@ extern "C" int bsx_reads_open(const char *path, int zero_qual, int max_readlen, 
         gzbuffer((gzFile)r->gz, 1 << 20);
         r->stream_eof = false;
         stream_ensure(r, (size_t)1 << 20);
-        if (r->n >= 4 && memcmp(r->p, "BAM\1", 4) == 0) {      // BAM (BGZF members are gzip members): taken whole, as before
-            size_t want = (size_t)64 << 20;
-            while (!r->stream_eof) { stream_ensure(r, want); want *= 2; }
-        }
     }
     // CheckFile (reads.cpp:19-50): the first non-blank character decides; anything else is tried as BAM
     size_t q = 0; while (q < r->n && ws((unsigned char)r->p[q])) q++;
     const int c = q < r->n ? r->p[q] : -1;
     if (r->n >= 12 && memcmp(r->p, "BAM\1", 4) == 0) {
-        // BAM (BGZF members are gzip members, inflated above): skip the header text and the reference dictionary
+        // BAM (BGZF members are gzip members, streamed like any gzip input): skip the header text and the reference dictionary
         r->kind = 3;
+        auto have = [&](size_t upto) { if (upto > r->n) stream_ensure(r, upto); return upto <= r->n; };   // pos is 0: offsets stay valid
         auto i32 = [&](size_t at) { int32_t v; memcpy(&v, r->p + at, 4); return v; };
         size_t at = 4;
         const int32_t l_text = i32(at); at += 4 + (size_t)std::max(l_text, 0);
-        bool ok = at + 4 <= r->n;
+        bool ok = have(at + 4);
         if (ok) {
             const int32_t n_ref = i32(at); at += 4;
-            for (int32_t k = 0; ok && k < n_ref; k++) { ok = at + 4 <= r->n; if (ok) { const int32_t l_name = i32(at); at += 4 + (size_t)std::max(l_name, 0) + 4; ok = at <= r->n; } }
+            for (int32_t k = 0; ok && k < n_ref; k++) { ok = have(at + 4); if (ok) { const int32_t l_name = i32(at); at += 4 + (size_t)std::max(l_name, 0) + 4; ok = have(at); } }
         }
         if (!ok) { bsx_reads_close(r); bsx_set_error("truncated BAM header: %s", path); return BSX_ERR_IO; }
         r->pos = at;
@@ -307,9 +304,11 @@ extern "C" void bsx_reads_skip(bsx_reads *r, uint64_t n_reads) {
 // max_readlen.  readset 1 (file a of a pair) takes a record and skips its mate, readset 2 skips one and takes the next.
 static uint32_t bam_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, uint16_t *lens) {
     static const char nt16[] = "=ACMGRSVTWYHKDBN";
-    auto record = [&](size_t &pos, const unsigned char *&body, uint32_t &bytes) {   // false at the end of the file
+    auto record = [&](size_t &pos, const unsigned char *&body, uint32_t &bytes) {   // false at the end of the file; pos is r->pos
+        if (!r->stream_eof && r->n - pos < 4 + 65536) stream_ensure(r, (size_t)16 << 20);   // streamed: the records are copied out, no window is kept
         if (pos + 4 > r->n) return false;
         int32_t bs; memcpy(&bs, r->p + pos, 4);
+        if (bs >= 32 && pos + 4 + (size_t)bs > r->n) stream_ensure(r, 4 + (size_t)bs);
         if (bs < 32 || pos + 4 + (size_t)bs > r->n) return false;
         body = (const unsigned char *)r->p + pos + 4; bytes = (uint32_t)bs; pos += 4 + (size_t)bs;
         return true;

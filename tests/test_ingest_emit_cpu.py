@@ -193,6 +193,45 @@ def test_bam_input(tmp_path):
     ra.close(); rb.close()
 
 
+def test_bam_input_is_streamed_over_many_windows(tmp_path):
+    """a BAM of ~45 MB inflated (the reader's windows are 16-24 MB): every record comes back, single-end and as the two files
+    of an interleaved pair, also through a FIFO"""
+    import bamio
+    import threading
+    rng = np.random.default_rng(8)
+    n = 300_000
+    seqs = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(L))) for L in rng.integers(60, 145, 2000)]
+    recs = [("read_%07d" % i, 0x4d if i % 2 == 0 else 0x8d, seqs[i % 2000], "F" * len(seqs[i % 2000])) for i in range(n)]
+    bam = str(tmp_path / "big.bam")
+    bamio.write_bam(bam, recs)
+
+    def names_of(path, readset, want):
+        r = B.Reads(path)
+        r.set_readset(readset)
+        out = []
+        while True:
+            k, buf, lens = r.next(want, stride=160)
+            for i in (0, k // 2, k - 1) if k else ():
+                nm, sq, ql = r.get(i)
+                j = len(out) + i
+                src = recs[j] if readset == 0 else recs[2 * j + (readset - 1)]
+                assert (nm.decode(), sq.decode(), ql.decode()) == (src[0], src[2], src[3]) and bytes(buf[i, :lens[i]]) == sq
+            out += [None] * k
+            if k < want:
+                break
+        r.close()
+        return len(out)
+
+    assert names_of(bam, 0, 70_000) == n
+    assert names_of(bam, 1, 50_000) == n // 2 and names_of(bam, 2, 50_000) == n // 2
+    fifo = str(tmp_path / "fifo.bam")
+    os.mkfifo(fifo)
+    t = threading.Thread(target=lambda: open(fifo, "wb").write(open(bam, "rb").read()))
+    t.start()
+    assert names_of(fifo, 0, 65_536) == n
+    t.join()
+
+
 def test_skip_and_errors(tmp_path):
     path = tmp_path / "r.fq"
     path.write_bytes(REGULAR_FQ)
