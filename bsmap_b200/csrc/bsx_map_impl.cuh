@@ -78,6 +78,9 @@
 #ifndef BSX_KUNROLL
 #define BSX_KUNROLL 1
 #endif
+#ifndef BSX_OWNER_SCHED
+#define BSX_OWNER_SCHED 0       // schedule of a round: 0 = lane t looks up the list of half-step t (one shuffle per list), 1 = the lane that owns a
+#endif                          // list writes the descriptors of its own half-steps (no lookup, no plan reload) -- A/B switch
 #define BSX_PRAGMA_(x) _Pragma(#x)
 #define BSX_UNROLL(n) BSX_PRAGMA_(unroll n)
 #ifndef BSX_STAGE_MAP
@@ -541,14 +544,17 @@ __device__ __noinline__ uint32_t mode_chunk_table(const MapArgs &A, const ReadSm
 __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uint2 *hits, uint32_t *dd, int store_all, int mode, int lane, Ctr *C, StageSm *S) {
     const int per = BSX_RRBS(A) ? 1 : A.I;
     const int top = 1 << (31 - __clz(per));                               // largest power of two <= per
+    const int chain_lo = R->fc ? 0 : 1, chain_hi = R->cc ? 2 : 1;          // the chains this read is searched on (fixed per read)
     #pragma unroll 1
-    for (int chain = 0; chain < 2; chain++) {
-        if (chain == 0 ? !R->fc : !R->cc) continue;
+    for (int chain = chain_lo; chain < chain_hi; chain++) {
         const uint4 *plan = plan_of(R, chain, A) + mode * per, *flank = flank_of(R, chain, A) + mode * per * BSX_FW;
         uint4 e = make_uint4(0u, 0u, 0u, 0u);                             // lane k < per owns list k: {start, rc start, end, p | segment << 16}
         if (lane < per) e = plan[lane];
         const uint32_t n = e.z - e.x;
         uint32_t cum = n ? (n + (BSX_WIDE(A) ? 0u : (e.x & 1u)) + 31u) >> 5 : 0u;   // half-steps of my list -> inclusive scan over the lists
+#if BSX_OWNER_SCHED
+        const uint32_t my_hs = cum;
+#endif
         #pragma unroll 1
         for (int d = 1; d < per; d <<= 1) { const uint32_t t = __shfl_up_sync(BSX_FULL, cum, d); if (lane >= d) cum += t; }
         const uint32_t total_hs = __shfl_sync(BSX_FULL, cum, per - 1);
@@ -570,6 +576,43 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
                 __syncwarp();
             } else
 #endif
+#if BSX_OWNER_SCHED
+            {   // the lane that owns list j writes the descriptors of the list's half-steps that fall into this round; the
+                // tail of the round (past the mode's last half-step) is padding: no entry of it is ever inside a list
+                const uint32_t first = cum - my_hs;                       // my list's first half-step in the mode's sequence
+#if BSX_RUN_ADVANCE
+                {   // where the list of this round's last half-step ends
+                    const uint32_t idx = h0 + BSX_ROUND_HS - 1u;
+                    const unsigned own = __ballot_sync(BSX_FULL, lane < per && first <= idx && idx < cum);
+                    const uint32_t ce = __shfl_sync(BSX_FULL, cum, own ? __ffs(own) - 1 : 0);
+                    run_end = own ? ce : 0u;
+                }
+#endif
+                __syncwarp();                                             // the previous round's slow path may still read the schedule
+                if (lane < BSX_ROUND_HS && h0 + (uint32_t)lane >= total_hs) {
+                    HalfStep z;
+                    z.d = z.f = make_uint4(0u, 0u, 0u, 0u);
+#if BSX_WIDE(0)
+                    z.f2 = z.d;
+#endif
+                    S->sched[lane] = z;
+                }
+                if (lane < per && my_hs) {
+                    const uint32_t lo = max(first, h0), hi = min(cum, h0 + (uint32_t)BSX_ROUND_HS);
+                    if (lo < hi) {
+                        HalfStep h;
+                        h.f = flank[lane * BSX_FW];
+#if BSX_WIDE(0)
+                        h.f2 = flank[lane * BSX_FW + 1];
+#endif
+                        h.d = make_uint4((BSX_WIDE(A) ? e.x : (e.x & ~1u)) + 32u * (lo - first), e.x, n, (uint32_t)lane);
+                        #pragma unroll 1
+                        for (uint32_t t = lo; t < hi; t++) { S->sched[t - h0] = h; h.d.x += 32u; }
+                    }
+                }
+                __syncwarp();
+            }
+#else
             {   // lane t describes half-step h0 + t: its list is the first one whose running total exceeds h0 + t
                 const uint32_t target = h0 + (uint32_t)lane;
                 int k = 0; uint32_t first = 0;
@@ -613,6 +656,7 @@ __device__ __forceinline__ int snp_align_packed(const MapArgs &A, ReadSm *R, uin
                 }
                 __syncwarp();
             }
+#endif  // BSX_OWNER_SCHED
 #if BSX_WIDE(0)
             {   // 16-byte entries: lane L stages entry L of every half-step of the round (512 contiguous bytes per copy)
                 const char *ctx = reinterpret_cast<const char *>(A.ctx) + 16u * (uint32_t)lane;
@@ -716,7 +760,7 @@ __device__ void write_record(const MapArgs &A, const ReadSm *R, const uint2 *hit
         const int sum = ii <= R->rmsn ? R->nh[ii] + R->nc[ii] : 0;
         o.nm = (uint8_t)ii;
         if (sum > 0) {
-            const int j = (int)(bsx_myrand(R->index, A.randseed) % (uint32_t)sum);
+            const int j = sum > 1 ? (int)(bsx_myrand(R->index, A.randseed) % (uint32_t)sum) : 0;   // a unique hit needs no draw (and no division)
             const int nh = R->nh[ii];
             const int chain = j >= nh;
             const size_t lvl = store_all ? (size_t)ii * 2 : 0;

@@ -1,3 +1,5 @@
-nvidia-smi -L | wc -l
-N=${NG:-8}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_r2_${N}gpu.log 2>&1; tail -1 gpurun_out/bench_r2_${N}gpu.log | cut -c1-300
+BSMAP_B200_LIB=variants/v2.so python -m pytest tests/test_gpu_parity.py tests/test_fuzz_gpu.py -x -q -m gpu -k "not cli" > gpurun_out/t_v2.log 2>&1; tail -2 gpurun_out/t_v2.log
+bash tools/ab_bench.sh v2
+CFG=cfg3 bash tools/ab_bench.sh v2
+CFG=cfg4 bash tools/ab_bench.sh v2
+CFG=cfg5 bash tools/ab_bench.sh v2
