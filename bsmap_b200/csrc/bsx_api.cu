@@ -443,13 +443,13 @@ static int mapper_init(bsx_mapper *m, const bsx_index *ix, const bsx_params *p, 
     // eight warps per CTA; a parameter set whose per-read plan is large (many segments x -I, -n 1, wide context) runs with fewer
     int occ_se = 0, occ_pe = 0;
     for (int w = BSX_WARPS_PER_CTA; w >= 1 && occ_se < 1; w >>= 1) {
-        const size_t smem = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot, wide, w);
+        const size_t smem = bsx_cta_smem_bytes(1, m->plan_cap, m->nslot, wide, p->rrbs, w);
         if (smem > BSX_MAX_CTA_SMEM) continue;
         m->warps_se = w;
         occ_se = p->rrbs ? bsx_map_occupancy_se_rrbs(smem, w) : (wide ? bsx_map_occupancy_se_wide(smem, w) : bsx_map_occupancy_se_wgbs(smem, w));
     }
     for (int w = BSX_WARPS_PER_CTA; w >= 1 && occ_pe < 1; w >>= 1) {
-        const size_t smem = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot, wide, w);
+        const size_t smem = bsx_cta_smem_bytes(2, m->plan_cap, m->nslot, wide, p->rrbs, w);
         if (smem > BSX_MAX_CTA_SMEM) continue;
         m->warps_pe = w;
         occ_pe = p->rrbs ? bsx_map_occupancy_pe_rrbs(smem, w) : (wide ? bsx_map_occupancy_pe_wide(smem, w) : bsx_map_occupancy_pe_wgbs(smem, w));

@@ -102,29 +102,42 @@ struct CtaSm {
 };
 static_assert(sizeof(CtaSm) % 16 == 0, "per-warp shared memory follows CtaSm and holds uint4");
 
-// half-steps (32 list entries) per staging round: 2 KB of 8-byte entries; wide indexes stage 16-byte entries
+// half-steps (32 list entries) per staging round: 2 KB of 8-byte entries at 8; wide indexes stage 16-byte entries.  Longer
+// rounds spread the per-round work (schedule, staging issue, wait) over more entries but cost shared memory and leave
+// more of a short mode's round empty: measured per kernel family (paired-end, config 3: 8 -> 81.3, 12 -> 84.2, 16 -> 80.3 M pairs/s;
+// single-end WGBS, config 2: 8 -> 356.3, 12 -> 355.4 M reads/s; single-end RRBS, config 4: 12 and 16 gain 2 % resident and lose 4-7 %
+// end to end in 1 M-read sub-batches).
 #ifndef BSX_WIDE_ROUND_HS
 #define BSX_WIDE_ROUND_HS 8
 #endif
-#define BSX_NARROW_ROUND_HS 8
-// bytes of the per-warp staging area beyond the PrepCol it aliases (slot[HS*32] entries + HS schedule entries of 48 bytes)
-static inline __host__ __device__ size_t bsx_stage_extra_bytes(int wide) {
-    const size_t need = wide ? (size_t)BSX_WIDE_ROUND_HS * (32u * 16u + 48u) : (size_t)BSX_NARROW_ROUND_HS * (32u * 8u + 32u);
+#ifndef BSX_NARROW_ROUND_HS
+#define BSX_NARROW_ROUND_HS 8          // single-end WGBS
+#endif
+#ifndef BSX_NARROW_ROUND_HS_PE
+#define BSX_NARROW_ROUND_HS_PE 12      // paired-end (WGBS and RRBS)
+#endif
+#ifndef BSX_NARROW_ROUND_HS_RRBS
+#define BSX_NARROW_ROUND_HS_RRBS 8     // single-end RRBS
+#endif
+// bytes of the per-warp staging area beyond the PrepCol it aliases (slot[HS*32] entries + HS schedule entries of 32 / 48 bytes)
+static inline __host__ __device__ size_t bsx_stage_extra_bytes(int wide, int pe, int rrbs) {
+    const size_t need = wide ? (size_t)BSX_WIDE_ROUND_HS * (32u * 16u + 48u)
+                             : (size_t)(pe ? BSX_NARROW_ROUND_HS_PE : (rrbs ? BSX_NARROW_ROUND_HS_RRBS : BSX_NARROW_ROUND_HS)) * (32u * 8u + 32u);
     return need > sizeof(PrepCol) ? ((need - sizeof(PrepCol) + 15u) & ~(size_t)15u) : 0u;
 }
 static inline __host__ __device__ size_t bsx_read_smem_bytes(int plan_cap, int nslot, int wide) {
     return sizeof(ReadSm) + (size_t)nslot * (size_t)plan_cap * (wide ? 3u : 2u) * sizeof(uint4);
 }
-static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide) {
-    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot, wide) + sizeof(SelSm) + sizeof(PrepCol) + bsx_stage_extra_bytes(wide);
+static inline size_t bsx_warp_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide, int rrbs) {
+    return (size_t)reads_per_warp * bsx_read_smem_bytes(plan_cap, nslot, wide) + sizeof(SelSm) + sizeof(PrepCol) + bsx_stage_extra_bytes(wide, reads_per_warp == 2, rrbs);
 }
-static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide, int warps) {
-    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot, wide) * (size_t)warps;
+static inline size_t bsx_cta_smem_bytes(int reads_per_warp, int plan_cap, int nslot, int wide, int rrbs, int warps) {
+    return sizeof(CtaSm) + bsx_warp_smem_bytes(reads_per_warp, plan_cap, nslot, wide, rrbs) * (size_t)warps;
 }
 
 static inline void bsx_map_args_derive(MapArgs &a) {
     a.read_smem = (uint32_t)bsx_read_smem_bytes(a.plan_cap, a.nslot, a.ctx_wide);
-    a.warp_smem_se = (uint32_t)bsx_warp_smem_bytes(1, a.plan_cap, a.nslot, a.ctx_wide);
+    a.warp_smem_se = (uint32_t)bsx_warp_smem_bytes(1, a.plan_cap, a.nslot, a.ctx_wide, a.rrbs);
     a.chain_stride = a.nslot == 2 ? (uint32_t)a.plan_cap : 0u;
     a.flank_off = (uint32_t)(a.nslot * a.plan_cap);
     a.img_slot = (uint32_t)(2 * BSX_FIXWORDS * 4 + a.plan_cap * sizeof(uint4));

@@ -88,6 +88,10 @@
 #endif
 #if BSX_WIDE(0)
 #define BSX_ROUND_HS BSX_WIDE_ROUND_HS     // half-steps (32 list entries each) per staging round (bsx_map.cuh)
+#elif defined(BSX_BUILD_PE)
+#define BSX_ROUND_HS BSX_NARROW_ROUND_HS_PE
+#elif BSX_RRBS(0)
+#define BSX_ROUND_HS BSX_NARROW_ROUND_HS_RRBS
 #else
 #define BSX_ROUND_HS BSX_NARROW_ROUND_HS
 #endif
@@ -943,7 +947,7 @@ BSX_PE_KERNEL(const __grid_constant__ MapArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t read_sm = A.read_smem;
-    const size_t per_warp = 2 * read_sm + sizeof(SelSm) + sizeof(PrepCol) + bsx_stage_extra_bytes(BSX_WIDE(0));
+    const size_t per_warp = 2 * read_sm + sizeof(SelSm) + sizeof(PrepCol) + bsx_stage_extra_bytes(BSX_WIDE(0), 1, BSX_RRBS(0));
     CtaSm *K = reinterpret_cast<CtaSm *>(smem);
     init_cta_tables(A, K);
     uint8_t *base = smem + sizeof(CtaSm) + per_warp * wid;
@@ -1071,7 +1075,7 @@ int BSX_SE_OCC(size_t smem, int warps) {
     return occ;
 }
 int BSX_SE_LAUNCH(const MapArgs &a, int n_ctas, int warps, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot, BSX_WIDE(a), warps);
+    const size_t smem = bsx_cta_smem_bytes(1, a.plan_cap, a.nslot, BSX_WIDE(a), BSX_RRBS(a), warps);
     // the attribute belongs to (function, device): one cache slot per device, several mappers / host threads may launch
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
@@ -1095,7 +1099,7 @@ int BSX_PE_OCC(size_t smem, int warps) {
     return occ;
 }
 int BSX_PE_LAUNCH(const MapArgs &a, int n_ctas, int warps, cudaStream_t st) {
-    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot, BSX_WIDE(a), warps);
+    const size_t smem = bsx_cta_smem_bytes(2, a.plan_cap, a.nslot, BSX_WIDE(a), BSX_RRBS(a), warps);
     static std::atomic<size_t> configured[BSX_MAX_DEVICES];
     int dev = 0;
     BSX_CUDA_CHECK(cudaGetDevice(&dev));

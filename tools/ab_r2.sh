@@ -1,5 +1,3 @@
-BSMAP_B200_LIB=variants/v2.so python -m pytest tests/test_gpu_parity.py tests/test_fuzz_gpu.py -x -q -m gpu -k "not cli" > gpurun_out/t_v2.log 2>&1; tail -2 gpurun_out/t_v2.log
-bash tools/ab_bench.sh v2
-CFG=cfg3 bash tools/ab_bench.sh v2
-CFG=cfg4 bash tools/ab_bench.sh v2
-CFG=cfg5 bash tools/ab_bench.sh v2
+bash tools/ab_bench.sh se12
+CFG=cfg4 bash tools/ab_bench.sh rrbs12 rrbs16
+CFG=cfg3 bash tools/ab_bench.sh
