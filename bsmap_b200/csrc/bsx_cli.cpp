@@ -158,6 +158,9 @@ template <class T> struct Chan {
     void push(T &&v) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return q.size() < cap; }); q.push_back(std::move(v)); cv.notify_all(); }
     bool pop(T &v) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return false; v = std::move(q.front()); q.erase(q.begin()); cv.notify_all(); return true; }
     void close() { std::unique_lock<std::mutex> l(m); closed = true; cv.notify_all(); }
+    // non-blocking forms (recycling pools: an empty pool means "make a new one", a full pool "drop it")
+    bool try_push(T &&v) { std::unique_lock<std::mutex> l(m); if (q.size() >= cap) return false; q.push_back(std::move(v)); cv.notify_all(); return true; }
+    bool try_pop(T &v) { std::unique_lock<std::mutex> l(m); if (q.empty()) return false; v = std::move(q.back()); q.pop_back(); return true; }
 };
 
 // hand-off that releases items in sequence order whatever order they arrive in (several mapper threads, one formatter)
@@ -374,13 +377,17 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
     double t_parse = 0, t_fmt = 0, t_write = 0;
     std::vector<double> t_map((size_t)n_dev, 0.0); std::vector<unsigned long long> n_map((size_t)n_dev, 0);
     Ordered<Job> jobs; Chan<Text> texts(2);
+    Chan<Text> spare(4);
+    Chan<Views> spare_views(8);                     // view arrays of formatted batches go back to the cutter with their capacity                            // written texts come back with their buffers: the formatter fills them again (no fresh pages)
     std::atomic<int> fail{0};
     const double t_alloc = now();
     std::thread formatter([&] {
         Job j;
         while (jobs.pop(j)) {
             const double t = now();
-            Text tx; tx.done_index = j.done_index;
+            Text tx;
+            spare.try_pop(tx);
+            tx.done_index = j.done_index;
             if (no_text) {   // counts only (the rules of s_OutHit / s_OutHitPair / s_OutHitUnpair for "printed as mapped")
                 auto mapped = [&](const bsx_rec &r) { const int n = r.status ? -1 : (int)r.nhits; return n >= 1 && !(n > 1 && p.report_repeat_hits == 0); };
                 for (uint32_t t = 0; t < j.n; t++) {
@@ -399,6 +406,8 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
                 n_pairs += st[0]; n_a += st[1]; n_b += st[2];
             }
             pool.put(j.slot);
+            j.a.keep.clear(); j.a.store.clear(); spare_views.try_push(std::move(j.a));   // the stream windows and token strings are released here
+            if (pe) { j.b.keep.clear(); j.b.store.clear(); spare_views.try_push(std::move(j.b)); }
             t_fmt += now() - t;
             texts.push(std::move(tx));
         }
@@ -414,6 +423,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
             if (fun && !of_un.write_chunks(tx.unpair, threads)) fail = 2;
             t_write += now() - t;
             printf("%u reads finished. %ld secs passed\n", tx.done_index, (long)(time(nullptr) - t0));
+            spare.try_push(std::move(tx));
         }
     });
     // cut (this thread) || map (one thread per device) || format || write
@@ -461,6 +471,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         if (!n1 || n1 != n2) break;
         index_a += n1;
         CutJob c; c.n = n1; c.first = first; c.slot = slot; c.seq = k; c.done_index = index_a - o.read_start + 1;
+        spare_views.try_pop(c.a); if (pe) spare_views.try_pop(c.b);          // recycled arrays, swapped into the readers for the next batch
         take_views(ra, c.a); if (pe) take_views(rb, c.b);
         cuts.push(std::move(c));
     }

@@ -14,20 +14,30 @@ namespace {
 
 const char kNt[] = "ACGTacgt";   // useful_nt after SetAlign('T','C') (param.cpp:220-221)
 
-// text sink: a caller-sized buffer (the C ABI's two-call protocol) or a growing string (chunked emit)
+// text sink: a caller-sized buffer (the C ABI's two-call protocol: bytes beyond cap are counted, not written) or a growing
+// string (chunked emit).  The string is grown ahead of the cursor -- ensure() once per record with an upper bound of the
+// record's size -- so that the twenty-odd pieces of a record are plain stores, not twenty capacity checks.
 struct Out {
     char *p; size_t cap, n; std::string *dyn;
+    void ensure(size_t bound) {
+        if (!dyn || n + bound <= cap) return;
+        dyn->resize(std::max(cap * 2, n + bound + (size_t)65536));
+        p = &(*dyn)[0]; cap = dyn->size();
+    }
+    void finish() { if (dyn) { dyn->resize(n); cap = n; } }
     void put(const char *s, size_t len) {
-        if (dyn) dyn->append(s, len);
-        else if (n + len <= cap && p) memcpy(p + n, s, len);
+        if (p && n + len <= cap) memcpy(p + n, s, len);
         n += len;
     }
     void put(const std::string &s) { put(s.data(), s.size()); }
-    void puts(const char *s) { put(s, strlen(s)); }
-    void putc(char c) { put(&c, 1); }
+    template <size_t N> void puts(const char (&s)[N]) { put(s, N - 1); }     // string literals: length known at compile time
+    void putc(char c) { if (p && n < cap) p[n] = c; n++; }
     void putu(unsigned long long v) { char b[24]; char *e = b + 24, *q = e; do { *--q = (char)('0' + v % 10); v /= 10; } while (v); put(q, (size_t)(e - q)); }
     void puti(long long v) { if (v < 0) { putc('-'); putu(0ull - (unsigned long long)v); } else putu((unsigned long long)v); }
 };
+// upper bound of what one read can print (name, bases, qualities, reference name, XR / BSP reference window, BSP counts, fixed text)
+inline size_t record_bound(size_t max_ref_name, const bsx_view &name) { return (size_t)name.n + 4u * (BSX_MAX_READLEN + 16u) + max_ref_name + 384u; }
+inline size_t longest_name(const bsx_index *ix) { size_t m = 0; for (const std::string &n : ix->names) m = std::max(m, n.size()); return m; }
 
 char comp(char c) {   // rev_char[] (param.cpp:166-177)
     switch (c) {
@@ -194,11 +204,12 @@ namespace {
 
 // reads [b, e) of a single-end batch
 void se_range(const bsx_index *ix, const bsx_params *p, uint32_t b, uint32_t e, const bsx_view *names, const bsx_view *seqs,
-              const bsx_view *quals, int readset, const bsx_rec *recs, const uint16_t *counts, Out &o, uint32_t *n_aligned) {
+              const bsx_view *quals, int readset, const bsx_rec *recs, const uint16_t *counts, Out &o, uint32_t *n_aligned, size_t max_ref_name) {
     uint32_t na = 0;
     Read rd;
     for (uint32_t t = b; t < e; t++) {
         const bsx_rec &rc = recs[t];
+        o.ensure(record_bound(max_ref_name, names[t]));
         make_read(rd, p, names[t], seqs[t], quals[t], rc.len);
         if (rc.status == 1) {   // Do_Batch (align.cpp:598-600): filtered reads are printed only when -r != 0
             if (p->report_repeat_hits) out_hit(ix, p, o, rd, readset, 0, -1, 0, 0, 0, 0, nullptr, 0, &na);
@@ -207,6 +218,7 @@ void se_range(const bsx_index *ix, const bsx_params *p, uint32_t b, uint32_t e, 
         out_hit(ix, p, o, rd, readset, rc.chain, (int)rc.nhits, rc.nm, rc.chr, rc.loc, 0, counts ? counts + (size_t)t * 16 : nullptr,
                 rmsn(p, rc.len, rd.raw), &na);
     }
+    o.finish();
     *n_aligned = na;
 }
 
@@ -215,10 +227,11 @@ void pe_range(const bsx_index *ix, const bsx_params *p, uint32_t b, uint32_t e,
               const bsx_view *names_a, const bsx_view *seqs_a, const bsx_view *quals_a,
               const bsx_view *names_b, const bsx_view *seqs_b, const bsx_view *quals_b,
               const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb, const uint16_t *counts_a, const uint16_t *counts_b,
-              Out &o, Out &ou, uint32_t *st) {
+              Out &o, Out &ou, uint32_t *st, size_t max_ref_name) {
     uint32_t n_pairs = 0, n_a = 0, n_b = 0, dummy = 0;
     Read A, B;
     for (uint32_t t = b; t < e; t++) {
+        { const size_t bound = record_bound(max_ref_name, names_a[t]) + record_bound(max_ref_name, names_b[t]); o.ensure(bound); ou.ensure(bound); }
         make_read(A, p, names_a[t], seqs_a[t], quals_a[t], ra[t].len);
         make_read(B, p, names_b[t], seqs_b[t], quals_b[t], rb[t].len);
         if (p->out_sam && !(A.name.n == B.name.n && memcmp(A.name.p, B.name.p, A.name.n) == 0)) {
@@ -271,6 +284,7 @@ void pe_range(const bsx_index *ix, const bsx_params *p, uint32_t b, uint32_t e,
             out_hit(ix, p, ou, B, 2, rb[t].chain, mb, rb[t].nm, rb[t].chr, rb[t].loc, 0, cb, rb[t].status ? 0 : rmsn(p, rb[t].len, B.raw), &dummy);
         }
     }
+    o.finish(); ou.finish();
     st[0] = n_pairs; st[1] = n_a; st[2] = n_b;
 }
 
@@ -278,6 +292,12 @@ std::vector<bsx_view> views_of(const char *const *s, uint32_t n) {
     std::vector<bsx_view> v(n);
     for (uint32_t t = 0; t < n; t++) v[t] = bsx_view{s[t], (uint32_t)strlen(s[t])};
     return v;
+}
+
+// a growing sink over a string that may come back from an earlier batch with its buffer: the text starts at offset 0
+Out sink_of(std::string &s, size_t estimate) {
+    if (s.size() < estimate) s.resize(estimate);
+    return Out{s.empty() ? nullptr : &s[0], s.size(), 0, &s};
 }
 
 bool needs_watson(const bsx_params *p) { return p->out_ref || !p->out_sam; }
@@ -299,7 +319,7 @@ extern "C" size_t bsx_format_se(const bsx_index *ix, const bsx_params *p, uint32
     Out o{out, cap, 0, nullptr};
     uint32_t na = 0;
     const std::vector<bsx_view> vn = views_of(names, n), vs = views_of(seqs, n), vq = views_of(quals, n);
-    se_range(ix, p, 0, n, vn.data(), vs.data(), vq.data(), readset, recs, counts, o, &na);
+    se_range(ix, p, 0, n, vn.data(), vs.data(), vq.data(), readset, recs, counts, o, &na, 0);
     if (n_aligned) *n_aligned = na;
     return o.n;
 }
@@ -314,7 +334,7 @@ extern "C" size_t bsx_format_pe(const bsx_index *ix, const bsx_params *p, uint32
     uint32_t st[3];
     const std::vector<bsx_view> na = views_of(names_a, n), sa = views_of(seqs_a, n), qa = views_of(quals_a, n);
     const std::vector<bsx_view> nb = views_of(names_b, n), sb = views_of(seqs_b, n), qb = views_of(quals_b, n);
-    pe_range(ix, p, 0, n, na.data(), sa.data(), qa.data(), nb.data(), sb.data(), qb.data(), pr, ra, rb, counts_a, counts_b, o, ou, st);
+    pe_range(ix, p, 0, n, na.data(), sa.data(), qa.data(), nb.data(), sb.data(), qb.data(), pr, ra, rb, counts_a, counts_b, o, ou, st, 0);
     if (n_unpair) *n_unpair = ou.n;
     if (n_stats) { n_stats[0] = st[0]; n_stats[1] = st[1]; n_stats[2] = st[2]; }
     return o.n;
@@ -327,12 +347,12 @@ void bsx_format_se_chunks(const bsx_index *ix, const bsx_params *p, uint32_t n, 
                           std::vector<std::string> &chunks, uint32_t *n_aligned) {
     threads = std::max(1, std::min<int>(threads, (int)std::max<uint32_t>(n, 1)));
     if (needs_watson(p)) watson(ix);   // lazily downloaded once, before the workers read it
-    chunks.assign((size_t)threads, std::string());
+    chunks.resize((size_t)threads);                 // strings a caller hands back keep their buffers: no fresh pages, no zero fill
     std::vector<uint32_t> na((size_t)threads, 0);
+    const size_t max_ref_name = longest_name(ix);
     bsx_parallel(threads, n, [&](int t, size_t b, size_t e) {
-        chunks[t].reserve((e - b) * 320);
-        Out o{nullptr, 0, 0, &chunks[t]};
-        se_range(ix, p, (uint32_t)b, (uint32_t)e, names, seqs, quals, readset, recs, counts, o, &na[t]);
+        Out o = sink_of(chunks[t], (e - b) * 320);
+        se_range(ix, p, (uint32_t)b, (uint32_t)e, names, seqs, quals, readset, recs, counts, o, &na[t], max_ref_name);
     });
     if (n_aligned) { uint32_t s = 0; for (uint32_t v : na) s += v; *n_aligned = s; }
 }
@@ -344,12 +364,12 @@ void bsx_format_pe_chunks(const bsx_index *ix, const bsx_params *p, uint32_t n, 
                           std::vector<std::string> &chunks_unpair, uint32_t *n_stats) {
     threads = std::max(1, std::min<int>(threads, (int)std::max<uint32_t>(n, 1)));
     if (needs_watson(p)) watson(ix);
-    chunks.assign((size_t)threads, std::string()); chunks_unpair.assign((size_t)threads, std::string());
+    chunks.resize((size_t)threads); chunks_unpair.resize((size_t)threads);
     std::vector<uint32_t> st((size_t)threads * 3, 0);
+    const size_t max_ref_name = longest_name(ix);
     bsx_parallel(threads, n, [&](int t, size_t b, size_t e) {
-        chunks[t].reserve((e - b) * 640);
-        Out o{nullptr, 0, 0, &chunks[t]}, ou{nullptr, 0, 0, &chunks_unpair[t]};
-        pe_range(ix, p, (uint32_t)b, (uint32_t)e, names_a, seqs_a, quals_a, names_b, seqs_b, quals_b, pr, ra, rb, counts_a, counts_b, o, ou, &st[3 * t]);
+        Out o = sink_of(chunks[t], (e - b) * 640), ou = sink_of(chunks_unpair[t], 0);
+        pe_range(ix, p, (uint32_t)b, (uint32_t)e, names_a, seqs_a, quals_a, names_b, seqs_b, quals_b, pr, ra, rb, counts_a, counts_b, o, ou, &st[3 * t], max_ref_name);
     });
     if (n_stats) { n_stats[0] = n_stats[1] = n_stats[2] = 0; for (int t = 0; t < threads; t++) for (int k = 0; k < 3; k++) n_stats[k] += st[3 * t + k]; }
 }
@@ -357,7 +377,7 @@ void bsx_format_pe_chunks(const bsx_index *ix, const bsx_params *p, uint32_t n, 
 extern "C" size_t bsx_emit_se(const bsx_index *ix, const bsx_params *p, const bsx_reads *a, uint32_t n, int readset,
                               const bsx_rec *recs, const uint16_t *counts, int threads, int fd, uint32_t *n_aligned) {
     if (!ix || !p || !a || !recs || n > a->name.size()) { bsx_set_error("bsx_emit_se: bad argument"); return 0; }
-    std::vector<std::string> chunks;
+    static thread_local std::vector<std::string> chunks;   // buffers reused from call to call
     bsx_format_se_chunks(ix, p, n, a->name.data(), a->seq.data(), a->qual.data(), readset, recs, counts, bsx_host_threads(threads), chunks, n_aligned);
     return write_all(fd, chunks);
 }
@@ -366,7 +386,7 @@ extern "C" size_t bsx_emit_pe(const bsx_index *ix, const bsx_params *p, const bs
                               const bsx_pair_rec *pr, const bsx_rec *ra, const bsx_rec *rb,
                               const uint16_t *counts_a, const uint16_t *counts_b, int threads, int fd, int fd_unpair, uint32_t *n_stats) {
     if (!ix || !p || !a || !b || !pr || !ra || !rb || n > a->name.size() || n > b->name.size()) { bsx_set_error("bsx_emit_pe: bad argument"); return 0; }
-    std::vector<std::string> chunks, chunks2;
+    static thread_local std::vector<std::string> chunks, chunks2;
     bsx_format_pe_chunks(ix, p, n, a->name.data(), a->seq.data(), a->qual.data(), b->name.data(), b->seq.data(), b->qual.data(),
                          pr, ra, rb, counts_a, counts_b, bsx_host_threads(threads), chunks, chunks2, n_stats);
     const size_t w = write_all(fd, chunks);

@@ -77,6 +77,7 @@ struct bsx_reads {
     std::vector<std::string> slow_store;   // backing store of records that took the token reader
     std::string qual_fill;                 // FASTA reads: zero_qual + default_qual (reads.cpp:108)
     std::vector<uint64_t> lines;
+    std::vector<std::vector<uint64_t>> scan_parts;   // per-thread line starts of the current window (kept for their capacity)
     double rec_bytes = 0;                  // running bytes per record: sizes the next scan window
     uint64_t n_fast = 0, n_slow = 0;
 };

@@ -85,7 +85,9 @@ void scan_lines(bsx_reads *r, size_t wend, int threads) {
     const char *p = r->p;
     const size_t pos = r->pos, span = wend - pos;
     if ((size_t)threads > span / 65536 + 1) threads = (int)(span / 65536 + 1);
-    std::vector<std::vector<uint64_t>> part((size_t)threads);
+    std::vector<std::vector<uint64_t>> &part = r->scan_parts;
+    if (part.size() < (size_t)threads) part.resize((size_t)threads);
+    for (auto &v : part) v.clear();
     bsx_parallel(threads, span, [&, p, pos](int t, size_t b, size_t e) {
         std::vector<uint64_t> &v = part[t];
         v.reserve((e - b) / 24 + 16);
