@@ -76,12 +76,31 @@ inline void put_seq(char *seqs, uint16_t *lens, uint32_t stride, size_t slot, co
     lens[slot] = (uint16_t)m;
 }
 
-// Line starts of a window of the file, found by `threads` memchr scanners.  ln = starts of the lines
-// in [pos, wend) plus one sentinel (one past the last complete line's '\n'; n + 1 when the file's last
-// line has none), so line i is [ln[i], ln[i+1] - 1).
-void scan_lines(bsx_reads *r, size_t wend, int threads) {
-    std::vector<uint64_t> &ln = r->lines;
-    ln.clear();
+// Line starts of a window of the file, found by `threads` memchr scanners.  The starts stay where the scanners put them --
+// one array per scanner, r->scan_parts -- and are addressed as one sequence: entry 0 is the window's first byte, then the
+// parts in order, then (when the file's last line has no line feed) one sentinel n + 1; line i is [at(i), at(i + 1) - 1).
+// (Merging them into one array was a 4 MB serial copy per batch: a third of the cutter's time on sixteen threads.)
+struct LineIndex {
+    const std::vector<std::vector<uint64_t>> *part; std::vector<size_t> first;   // first[t] = global index of part t's entry 0
+    uint64_t head, tail; bool has_tail; size_t total;
+    uint64_t at(size_t g) const {
+        if (g == 0) return head;
+        if (has_tail && g == total - 1) return tail;
+        size_t t = (size_t)(std::upper_bound(first.begin(), first.end(), g) - first.begin()) - 1;
+        return (*part)[t][g - first[t]];
+    }
+    // entries g .. g + k of the sequence, k <= 4 (a record's line starts and the start of the next record)
+    void get(size_t g, int k, uint64_t *L) const {
+        if (g == 0 || (has_tail && g + (size_t)k >= total - 1)) { for (int i = 0; i <= k; i++) L[i] = at(g + (size_t)i); return; }
+        size_t t = (size_t)(std::upper_bound(first.begin(), first.end(), g) - first.begin()) - 1, o = g - first[t];
+        for (int i = 0; i <= k; i++) {
+            while (o >= (*part)[t].size()) { t++; o = 0; }
+            L[i] = (*part)[t][o++];
+        }
+    }
+};
+
+LineIndex scan_lines(bsx_reads *r, size_t wend, int threads) {
     const char *p = r->p;
     const size_t pos = r->pos, span = wend - pos;
     if ((size_t)threads > span / 65536 + 1) threads = (int)(span / 65536 + 1);
@@ -98,11 +117,14 @@ void scan_lines(bsx_reads *r, size_t wend, int threads) {
             v.push_back(q);
         }
     });
-    size_t tot = 2; for (auto &v : part) tot += v.size();
-    ln.reserve(tot);
-    ln.push_back(pos);
-    for (auto &v : part) ln.insert(ln.end(), v.begin(), v.end());
-    if (wend == r->n && ln.back() != r->n) ln.push_back(r->n + 1);   // last line without '\n'
+    LineIndex li;
+    li.part = &part; li.head = pos; li.first.resize(part.size());
+    size_t tot = 1; uint64_t last = pos;
+    for (size_t t = 0; t < part.size(); t++) { li.first[t] = tot; tot += part[t].size(); if (!part[t].empty()) last = part[t].back(); }
+    li.has_tail = wend == r->n && last != r->n;          // last line without a line feed
+    li.tail = r->n + 1;
+    li.total = tot + (li.has_tail ? 1 : 0);
+    return li;
 }
 
 // Cut up to `want` regular records starting at r->pos (which must be a line start); returns how many
@@ -126,11 +148,10 @@ uint32_t fast_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, ui
     // address-space lock (measured: 8 threads no faster than 1)
     if (r->mapped) { const size_t a0 = r->pos & ~(size_t)4095; madvise((void *)(r->p + a0), wend - a0, MADV_POPULATE_READ); }
 #endif
-    scan_lines(r, wend, threads);
-    std::vector<uint64_t> &ln = r->lines;
-    const bool short_window = wend < r->n && (ln.size() - 1) / lpr < want;
-    if (ln.size() - 1 > (size_t)want * lpr) ln.resize((size_t)want * lpr + 1);
-    const size_t nrec = (ln.size() - 1) / lpr;
+    const LineIndex li = scan_lines(r, wend, threads);
+    const size_t n_lines = li.total - 1;
+    const bool short_window = wend < r->n && n_lines / lpr < want;
+    const size_t nrec = std::min<size_t>(n_lines / lpr, want);
     if (nrec == 0) { *bad = !short_window; if (short_window) r->rec_bytes *= 2; return 0; }
     std::atomic<size_t> first_bad(nrec);
     const char *p = r->p;
@@ -138,9 +159,11 @@ uint32_t fast_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, ui
     bsx_view *vn = r->name.data() + base, *vs = r->seq.data() + base, *vq = r->qual.data() + base;
     const char *qfill = r->qual_fill.data();
     bsx_parallel(threads, nrec, [&, p, hdr, lpr, mrl, stride, seqs, lens, base, vn, vs, vq, qfill](int, size_t b, size_t e) {
+        // this thread's records: a cursor over the scanners' arrays (the few records that touch the sequence's ends go through at())
         for (size_t i = b; i < e; i++) {
             if (i >= first_bad.load(std::memory_order_relaxed)) return;
-            const uint64_t *L = &ln[i * lpr];
+            uint64_t L[5];
+            li.get(i * (size_t)lpr, lpr, L);
             const char *h0 = p + L[0], *h1 = p + L[1] - 1;          // header line without its '\n'
             bool ok = h1 - h0 >= 2 && h0[0] == hdr && !ws((unsigned char)h0[1]);
             uint32_t nl = 0, sl = 0, ql = 0;
@@ -159,9 +182,10 @@ uint32_t fast_batch(bsx_reads *r, uint32_t want, uint32_t stride, char *seqs, ui
         }
     });
     const size_t took = first_bad.load();
-    r->pos = (size_t)std::min<uint64_t>(ln[took * lpr], r->n);
+    const uint64_t end_at = li.at(took * (size_t)lpr);
+    r->pos = (size_t)std::min<uint64_t>(end_at, r->n);
     r->n_fast += took;
-    if (took) r->rec_bytes = (double)(ln[took * lpr] - ln[0]) / (double)took;
+    if (took) r->rec_bytes = (double)(end_at - li.head) / (double)took;
     *bad = took < nrec || !short_window;
     return (uint32_t)took;
 }

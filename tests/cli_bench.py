@@ -20,6 +20,7 @@ ap.add_argument("--pairs", action="store_true", help="paired-end: --reads pairs,
 ap.add_argument("--skip-ref", action="store_true")
 ap.add_argument("--repeat", type=int, default=5, help="timed runs of our CLI after the first (median reported)")
 ap.add_argument("--ref-threads", type=int, default=0, help="reference -p (0 = all host cores)")
+ap.add_argument("--env-variants", default="", help="extra timed runs of our CLI under these environments: 'A=1;B=2,C=3' = two variants")
 a = ap.parse_args()
 dev = "cuda" if torch.cuda.is_available() else "cpu"
 td = tempfile.mkdtemp(prefix="bsx_cli_")
@@ -38,10 +39,10 @@ else:
     synth.write_fastq(fq2, sim["seq2"].cpu(), synth.read_names(meta, suffix="/2"))
     inputs = ["-a", fq, "-b", fq2]
 res = {"paired": a.pairs, "reads": a.reads, "read_len": a.len, "genome_mb": a.genome_mb, "opts": a.opts, "host_cores": os.cpu_count()}
-def run(exe, out, extra):
+def run(exe, out, extra, env_extra=None):
     t0 = time.perf_counter()
     r = subprocess.run([exe] + inputs + ["-d", fa, "-o", out] + a.opts.split() + extra, capture_output=True, text=True,
-                       env=dict(os.environ, BSX_CLI_TIMING="1"))
+                       env=dict(os.environ, BSX_CLI_TIMING="1", **(env_extra or {})))
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
     return dt, hashlib.md5(open(out, "rb").read()).hexdigest(), [l for l in r.stderr.splitlines() if "bsx timing" in l]
@@ -57,6 +58,16 @@ runs.sort(key=lambda x: x[0])
 dt, tl = runs[len(runs) // 2]
 res["ours_first_run_seconds"], res["ours_all_runs_seconds"] = dt0, [round(x[0], 3) for x in runs]
 res["ours_seconds"], res["ours_reads_per_s"], res["ours_md5"], res["ours_stages"] = dt, a.reads / dt, md5, tl
+for var in [v for v in a.env_variants.split(";") if v]:
+    env = dict(kv.split("=", 1) for kv in var.split(","))
+    best = None
+    for k in range(2):
+        dtv, md5v, tlv = run(ours, os.path.join(td, "var.sam"), [], env)
+        assert md5v == md5
+        os.unlink(os.path.join(td, "var.sam"))
+        if best is None or dtv < best[0]:
+            best = (dtv, tlv)
+    res.setdefault("variants", {})[var] = {"seconds": best[0], "stages": best[1]}
 refbin = os.path.join(ROOT, "oracle", "_ref", "bsmap")
 if os.path.exists(refbin) and not a.skip_ref:
     p = a.ref_threads or (os.cpu_count() or 1)
