@@ -328,6 +328,11 @@ class Reads:
     def kind(self) -> str:
         return {0: "fastq", 1: "fasta", 3: "bam"}[load().bsx_reads_kind(self.h)]
 
+    @property
+    def failed(self) -> bool:
+        """a streamed input (gzip, pipe) ended in an error: corrupt or truncated data"""
+        return bool(load().bsx_reads_failed(self.h))
+
     def set_readset(self, readset: int):
         """BAM input: 0 single-end, 1 / 2 = file a / b of a pair interleaved in one BAM"""
         load().bsx_reads_set_readset(self.h, readset)

@@ -478,6 +478,11 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
         cuts.push(std::move(c));
     }
     cuts.close();
+    bool input_failed = false;
+    if (bsx_reads_failed(ra) || (pe && bsx_reads_failed(rb))) {   // a corrupt / truncated gzip input: what was read is mapped and written, the run fails
+        fprintf(stderr, "error: %s\n", bsx_last_error());
+        input_failed = true;
+    }
     for (auto &t : mappers) t.join();
     jobs.close();
     const double t_loop = now();
@@ -491,7 +496,7 @@ extern "C" int bsx_cli_main(int argc, char **argv) {
                         (unsigned long long)(ra->n_slow + (rb ? rb->n_slow : 0)), threads);
     if (timing && n_dev > 1) for (int g = 0; g < n_dev; g++) fprintf(stderr, "[bsx timing] device %d: %llu reads in %.3f s of map calls\n", devs[g], n_map[g], t_map[g]);
     bsx_reads_close(ra); bsx_reads_close(rb);
-    if (fail) return 1;
+    if (fail || input_failed) return 1;
     if (mh) {
         const double t = now();
         std::vector<const char *> sp; std::vector<uint32_t> ln;

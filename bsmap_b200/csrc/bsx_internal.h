@@ -65,6 +65,7 @@ struct bsx_reads {
     // batches in flight, whatever the size of the file.
     void *gz = nullptr;                    // gzFile; reads plain data transparently
     bool stream_eof = true;                // nothing left to inflate (always true for mapped files)
+    bool io_error = false;                 // the stream ended in an error (corrupt or truncated gzip): what was read so far is served, the caller asks bsx_reads_failed
     bool win_starts_line = true;           // the window's first byte follows a line feed
     std::shared_ptr<std::vector<char>> win;
     std::vector<std::shared_ptr<std::vector<char>>> keep;

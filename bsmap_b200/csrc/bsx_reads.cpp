@@ -229,7 +229,14 @@ static void stream_ensure(bsx_reads *r, size_t need) {
     size_t fill = have;
     while (fill < need) {
         const int got = gzread((gzFile)r->gz, nw->data() + fill, (unsigned)std::min<size_t>(need - fill, (size_t)1 << 30));
-        if (got <= 0) { r->stream_eof = true; break; }
+        if (got <= 0) {
+            // the end of the stream, or an error: zlib reports a truncated member as Z_BUF_ERROR at this point, damaged data as Z_DATA_ERROR
+            int zerr = 0;
+            const char *msg = gzerror((gzFile)r->gz, &zerr);
+            if (got < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) { r->io_error = true; bsx_set_error("read input: %s", msg && *msg ? msg : "gzip stream ended unexpectedly"); }
+            r->stream_eof = true;
+            break;
+        }
         fill += (size_t)got;
     }
     nw->resize(fill);
@@ -307,6 +314,7 @@ extern "C" void bsx_reads_close(bsx_reads *r) {
 }
 
 extern "C" int bsx_reads_kind(const bsx_reads *r) { return r ? r->kind : -1; }
+extern "C" int bsx_reads_failed(const bsx_reads *r) { return r && r->io_error ? 1 : 0; }
 extern "C" void bsx_reads_force_token_reader(bsx_reads *r, int on) { if (r) r->force_slow = on != 0; }
 
 extern "C" void bsx_reads_skip(bsx_reads *r, uint64_t n_reads) {

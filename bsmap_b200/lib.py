@@ -61,7 +61,7 @@ EXPORTS = [
     "bsx_batch_upload", "bsx_batch_run_se", "bsx_batch_run_pe", "bsx_batch_download_se", "bsx_batch_download_pe",
     "bsx_mapper_sync", "bsx_mapper_stats", "bsx_mapper_launches", "bsx_format_header", "bsx_format_se",
     "bsx_format_pe", "bsx_cli_main",
-    "bsx_reads_open", "bsx_reads_close", "bsx_reads_kind", "bsx_reads_skip", "bsx_reads_force_token_reader", "bsx_reads_set_readset",
+    "bsx_reads_open", "bsx_reads_close", "bsx_reads_kind", "bsx_reads_failed", "bsx_reads_skip", "bsx_reads_force_token_reader", "bsx_reads_set_readset",
     "bsx_reads_next", "bsx_reads_get", "bsx_emit_se", "bsx_emit_pe",
     "bsx_index_create_packed", "bsx_index_save_packed", "bsx_index_create_from_packed", "bsx_meth_opts_default", "bsx_meth_create", "bsx_meth_destroy", "bsx_meth_add", "bsx_meth_download",
     "bsx_meth_write", "bsx_methratio_main", "bsx_sam_to_sorted_bam", "bsx_mapper_attach_meth", "bsx_meth_valid_count",
@@ -124,6 +124,7 @@ def load():
     L.bsx_reads_open.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bsx_reads_close.argtypes = [vp]; L.bsx_reads_close.restype = None
     L.bsx_reads_kind.argtypes = [vp]
+    L.bsx_reads_failed.argtypes = [vp]
     L.bsx_reads_skip.argtypes = [vp, C.c_uint64]; L.bsx_reads_skip.restype = None
     L.bsx_reads_set_readset.argtypes = [vp, i32]; L.bsx_reads_set_readset.restype = None
     L.bsx_reads_force_token_reader.argtypes = [vp, i32]; L.bsx_reads_force_token_reader.restype = None

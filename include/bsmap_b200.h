@@ -224,6 +224,8 @@ size_t bsx_format_pe(const bsx_index *ix, const bsx_params *p, uint32_t n,
 int bsx_reads_open(const char *path, int zero_qual, int max_readlen, bsx_reads **out);
 void bsx_reads_close(bsx_reads *r);
 int bsx_reads_kind(const bsx_reads *r);                       /* 0 FASTQ, 1 FASTA, 3 BAM (_file_format) */
+int bsx_reads_failed(const bsx_reads *r);                     /* 1: a streamed input (gzip, pipe) ended in an error -- corrupt or truncated; the
+                                                               * reads before it were served, bsx_last_error() has the text */
 /* BAM input (reads.cpp:120-143): 0 single-end; 1 / 2 = this reader is file a / b of a pair whose mates are interleaved
  * in one BAM (a takes a record and skips the next, b skips one and takes the next) */
 void bsx_reads_set_readset(bsx_reads *r, int readset);

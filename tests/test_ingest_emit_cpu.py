@@ -379,3 +379,25 @@ def test_reads_from_a_pipe_are_streamed(tmp_path):
         got = load_all(fifo, want=4096, stride=160)
         t.join()
         assert got == exp
+
+
+def test_truncated_gzip_input_is_reported(tmp_path):
+    """a gzip read file cut short (or damaged) still serves the reads before the damage, and says so: the command line then
+    exits non-zero instead of writing a silently shorter output"""
+    import gzip
+    data = _stream_corpus(30_000, seed=5)
+    blob = gzip.compress(data, 1)
+    good, cut = tmp_path / "ok.fq.gz", tmp_path / "cut.fq.gz"
+    good.write_bytes(blob)
+    cut.write_bytes(blob[:len(blob) * 2 // 3])
+    for path, want_fail in ((good, False), (cut, True)):
+        r = B.Reads(str(path))
+        n_tot = 0
+        while True:
+            n, _, _ = r.next(8192, stride=160)
+            n_tot += n
+            if n < 8192:
+                break
+        assert r.failed == want_fail, (path, n_tot)
+        assert (n_tot == 30_000) == (not want_fail) and n_tot > 10_000
+        r.close()
