@@ -401,3 +401,43 @@ def test_truncated_gzip_input_is_reported(tmp_path):
         assert r.failed == want_fail, (path, n_tot)
         assert (n_tot == 30_000) == (not want_fail) and n_tot > 10_000
         r.close()
+
+
+def test_chunked_emit_equals_the_two_call_formatter_on_awkward_records(tmp_path):
+    """the chunked emitter grows its buffers ahead of a raw cursor (one bound per record); the C ABI's two-call formatter counts
+    into a caller-sized buffer: same bytes for read names of 30 KB, unmapped / filtered / repeat records, SAM and BSP, and
+    for a second, smaller batch through the same (reused) buffers"""
+    import ctypes as C
+    from bsmap_b200.lib import load, strs
+    rng = np.random.default_rng(12)
+    gnames, gseqs = ["chrA_with_a_long_name_" + "x" * 200, "c2"], [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)) for n in (50_000, 9_000)]
+    for out_sam in (1, 0):
+        p = B.make_params(v=5, r=1, R=1)
+        p.out_sam = out_sam
+        ix = B.Index.text_only(p, gnames, gseqs)
+        for n in (3000, 17):
+            names = [("read%d_" % i + "n" * int(rng.choice([0, 3, 200, 30_000], p=[0.5, 0.3, 0.19, 0.01]))) for i in range(n)]
+            L = rng.integers(20, 145, n)
+            seqs = ["".join("ACGTN"[c] for c in rng.integers(0, 5, int(l))) for l in L]
+            quals = ["I" * int(l) for l in L]
+            fq = tmp_path / ("r%d_%d.fq" % (out_sam, n))
+            fq.write_text("".join("@%s\n%s\n+\n%s\n" % t for t in zip(names, seqs, quals)))
+            recs = np.zeros(n, dtype=BL.REC)
+            recs["chr"] = rng.integers(0, 4, n); recs["loc"] = rng.integers(2, 8_000, n); recs["nhits"] = rng.choice([0, 1, 1, 1, 5], n)
+            recs["nm"] = rng.integers(0, 6, n); recs["chain"] = rng.integers(0, 2, n); recs["status"] = rng.random(n) < 0.05; recs["len"] = L
+            counts = rng.integers(0, 70000, (n, 16)).astype(np.uint16)
+            r = B.Reads(str(fq))
+            assert r.next(n + 1)[0] == n
+            out = tmp_path / "emit.txt"
+            fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+            w, na = B.emit_se(ix, p, r, n, recs, counts, fd, threads=3)
+            os.close(fd)
+            args = (ix.h, C.byref(p), n, strs([s.encode() for s in names]), strs([s.encode() for s in seqs]), strs([s.encode() for s in quals]), 0,
+                    recs.ctypes.data, counts.ctypes.data)
+            na2 = C.c_uint32(0)
+            need = load().bsx_format_se(*args, None, 0, C.byref(na2))
+            buf = C.create_string_buffer(need + 1)
+            load().bsx_format_se(*args, buf, need + 1, C.byref(na2))
+            assert out.read_bytes() == buf.raw[:need] and w == need and na == na2.value
+            r.close()
+        ix.close()
