@@ -441,3 +441,43 @@ def test_chunked_emit_equals_the_two_call_formatter_on_awkward_records(tmp_path)
             assert out.read_bytes() == buf.raw[:need] and w == need and na == na2.value
             r.close()
         ix.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_read_files_line_cutter_equals_token_reader(tmp_path, seed):
+    """random FASTA / FASTQ texts -- regular records mixed with CRLF, blank lines, leading blanks, trailing tabs, a missing
+    final line feed, a truncated tail -- cut with random batch sizes and thread counts: the line cutter (which addresses the
+    scanners' line starts in place) and the token reader that restates the reference's stream semantics give the same reads"""
+    import random
+    rnd = random.Random(seed)
+
+    def rec(i, fastq):
+        L = rnd.choice([1, 5, 30, 60, 100, 144, 150])
+        seq = "".join(rnd.choice("ACGTN") for _ in range(L)); q = "".join(chr(rnd.randint(35, 73)) for _ in range(L))
+        k, h, nl = rnd.random(), "@" if fastq else ">", rnd.choice(["\n", "\n", "\n", "\r\n"])
+        if k < 0.85: return f"{h}r{i}{nl}{seq}{nl}" + (f"+{nl}{q}{nl}" if fastq else "")
+        if k < 0.90: return f"{nl}{h}r{i} extra{nl}{seq}{nl}" + (f"+r{i}{nl}{q}{nl}" if fastq else "")
+        if k < 0.94: return f" {h}r{i}{nl} {seq} {nl}" + (f"+{nl}{q}{nl}" if fastq else "")
+        if k < 0.97: return f"{h}r{i}{nl}{seq}{nl}{nl}" + (f"+{nl}{q}{nl}{nl}" if fastq else "")
+        return f"{h}r{i}\t{nl}{seq}\t{nl}" + (f"+{nl}{q}{nl}" if fastq else "")
+
+    path = str(tmp_path / "fz.txt")
+    checked = 0
+    for case in range(120):
+        fastq = rnd.random() < 0.7
+        n = rnd.choice([0, 1, 2, 3, 7, 50, 400, 3000])
+        txt = "".join(rec(i, fastq) for i in range(n))
+        if n and rnd.random() < 0.4: txt = txt.rstrip("\r\n")
+        if n and rnd.random() < 0.1: txt = txt[:len(txt) - rnd.randint(1, min(40, len(txt) - 1))]
+        if not txt.strip():
+            continue
+        open(path, "w", newline="").write(txt)
+        want, threads = rnd.choice([1, 2, 3, 7, 64, 1000, 5000]), rnd.choice([1, 2, 3, 8])
+        try:
+            a = load_all(path, want=want, threads=threads, stride=160)
+            b = load_all(path, want=want, threads=threads, stride=160, token=True)
+        except B.BsxError:
+            continue
+        assert a == b, (case, n, want, threads)
+        checked += 1
+    assert checked > 80
