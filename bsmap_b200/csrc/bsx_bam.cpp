@@ -19,6 +19,9 @@
 // heap rule.  Either way the sorted records stream through a window of 1 024 BGZF blocks that is deflated on all host
 // threads and written as soon as it is full, and the index is built behind it; nothing holds the whole BAM.
 #include <algorithm>
+#include <memory>
+#include <future>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +29,7 @@
 #include <map>
 #include <queue>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <vector>
 #include <fcntl.h>
@@ -60,20 +64,21 @@ template <class T> inline void put(std::string &o, T v) { o.append(reinterpret_c
 struct Rec { uint64_t key, off; uint32_t len; int32_t tid, pos, end; uint16_t bin; };   // end = calend (for the linear index)
 
 // one SAM line -> one BAM record appended to `out` (block_size first); false for lines that are not alignments
-bool encode(const char *b, const char *e, const std::unordered_map<std::string, int32_t> &tids, std::string &out, Rec &r) {
+bool encode(const char *b, const char *e, const std::unordered_map<std::string_view, int32_t> &tids, std::string &out, Rec &r) {
     if (e > b && e[-1] == '\r') e--;
     Field f[11]; int nf = 0;
     const char *s = b;
     while (nf < 11) { const char *t = (const char *)memchr(s, '\t', (size_t)(e - s)); if (!t) { f[nf++] = Field{s, (size_t)(e - s)}; s = e; break; } f[nf++] = Field{s, (size_t)(t - s)}; s = t + 1; }
     if (nf < 11) return false;
     const char *aux = s;                                             // rest of the line (may be empty)
-    auto tid_of = [&](Field x) -> int32_t { auto it = tids.find(std::string(x.p, x.n)); return it == tids.end() ? -1 : it->second; };
+    auto tid_of = [&](Field x) -> int32_t { auto it = tids.find(std::string_view(x.p, x.n)); return it == tids.end() ? -1 : it->second; };
     uint32_t flag;
     { char tmp[32]; const size_t k = std::min<size_t>(f[1].n, 31); memcpy(tmp, f[1].p, k); tmp[k] = 0; char *endp; long v = strtol(tmp, &endp, 0); flag = *endp ? 0u : (uint32_t)v; }
     const int32_t tid = tid_of(f[2]);
     const int32_t pos = f[3].n && is_digit(f[3].p[0]) ? (int32_t)to_long(f[3].p, f[3].n) - 1 : -1;
     const uint32_t mapq = f[4].n && is_digit(f[4].p[0]) ? (uint32_t)to_long(f[4].p, f[4].n) : 0;
-    std::vector<uint32_t> cigar;
+    uint32_t cigar_small[8]; std::vector<uint32_t> cigar_big;     // BSMAP writes one operation; anything longer spills to the heap
+    size_t n_cigar = 0;
     uint32_t endpos = (uint32_t)pos;
     int bin;
     if (f[5].n && f[5].p[0] != '*') {
@@ -84,7 +89,9 @@ bool encode(const char *b, const char *e, const std::unordered_map<std::string, 
             const char opc = (char)toupper((unsigned char)*c++);
             int op; switch (opc) { case 'M': case '=': case 'X': op = 0; break; case 'I': op = 1; break; case 'D': op = 2; break; case 'N': op = 3; break;
                                    case 'S': op = 4; break; case 'H': op = 5; break; case 'P': op = 6; break; default: return false; }
-            cigar.push_back((uint32_t)x << 4 | (uint32_t)op);
+            { const uint32_t cv = (uint32_t)x << 4 | (uint32_t)op;
+              if (n_cigar < 8) cigar_small[n_cigar] = cv; else { if (n_cigar == 8) cigar_big.assign(cigar_small, cigar_small + 8); cigar_big.push_back(cv); }
+              n_cigar++; }
             if (op == 0 || op == 2 || op == 3) endpos += (uint32_t)x;
         }
         bin = reg2bin((uint32_t)pos, endpos);
@@ -101,17 +108,21 @@ bool encode(const char *b, const char *e, const std::unordered_map<std::string, 
     put<int32_t>(out, 0);                                            // block_size, patched below
     put<int32_t>(out, tid); put<int32_t>(out, pos);
     put<uint32_t>(out, (uint32_t)bin << 16 | (mapq & 0xff) << 8 | (uint32_t)((f[0].n + 1) & 0xff));
-    put<uint32_t>(out, (flag & 0xffff) << 16 | (uint32_t)(cigar.size() & 0xffff));
+    put<uint32_t>(out, (flag & 0xffff) << 16 | (uint32_t)(n_cigar & 0xffff));
     put<int32_t>(out, l_seq); put<int32_t>(out, mtid); put<int32_t>(out, mpos); put<int32_t>(out, isize);
     out.append(f[0].p, f[0].n); out.push_back('\0');
-    for (uint32_t c : cigar) put<uint32_t>(out, c);
+    { const uint32_t *cg = n_cigar > 8 ? cigar_big.data() : cigar_small; out.append(reinterpret_cast<const char *>(cg), n_cigar * 4); }
     if (has_seq) {
-        for (int32_t i = 0; i < l_seq; i += 2) {
-            const unsigned hi = kNt16.t[(unsigned char)f[9].p[i]], lo = i + 1 < l_seq ? kNt16.t[(unsigned char)f[9].p[i + 1]] : 0u;
-            out.push_back((char)(hi << 4 | lo));
-        }
-        if (f[10].n == 1 && f[10].p[0] == '*') out.append((size_t)l_seq, (char)0xff);
-        else for (int32_t i = 0; i < l_seq; i++) out.push_back((char)((i < (int32_t)f[10].n ? f[10].p[i] : '!') - 33));
+        const size_t at = out.size(), nb = ((size_t)l_seq + 1) / 2;
+        out.resize(at + nb + (size_t)l_seq);                         // packed bases, then qualities: written through a raw cursor
+        unsigned char *w = reinterpret_cast<unsigned char *>(&out[at]);
+        const unsigned char *sq = reinterpret_cast<const unsigned char *>(f[9].p);
+        for (int32_t i = 0; i + 1 < l_seq; i += 2) *w++ = (unsigned char)(kNt16.t[sq[i]] << 4 | kNt16.t[sq[i + 1]]);
+        if (l_seq & 1) *w++ = (unsigned char)(kNt16.t[sq[l_seq - 1]] << 4);
+        if (f[10].n == 1 && f[10].p[0] == '*') memset(w, 0xff, (size_t)l_seq);
+        else { const int32_t nq = (int32_t)std::min<size_t>(f[10].n, (size_t)l_seq);
+               for (int32_t i = 0; i < nq; i++) w[i] = (unsigned char)(f[10].p[i] - 33);
+               for (int32_t i = nq; i < l_seq; i++) w[i] = (unsigned char)('!' - 33); }
     }
     // auxiliary fields (bam_import.c:336-395)
     for (const char *a = aux; a < e;) {
@@ -185,6 +196,7 @@ struct RunReader {
 
 // BGZF writer + bam_index_core behind it.  Records arrive in sorted order; raw bytes collect in a window that is cut
 // into 64 KiB blocks (bgzf.c's blocking: records flow through block boundaries), deflated in parallel and written.
+static double bam_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct BamSink {
     static const size_t BLK = 65536;
     size_t WINDOW = 1024;                             // blocks per flush (BSX_BAM_WINDOW_BLOCKS: tests shrink it)
@@ -193,6 +205,7 @@ struct BamSink {
     uint64_t flushed = 0, total = 0, file_pos = 0;    // raw bytes written / appended so far; compressed bytes written
     std::vector<uint64_t> blk_in_start, blk_file_start;   // per written block (sentinel at the end)
     bool fail = false;
+    double t_deflate = 0, t_write = 0, t_index = 0;   // BSX_CLI_TIMING
     // index state (bam_index.c:133-190)
     struct Chunk { uint64_t u, v; };
     std::vector<std::map<uint32_t, std::vector<Chunk>>> bins;
@@ -245,39 +258,63 @@ struct BamSink {
         }
         if (stopped) pend.clear();
     }
-    // deflate and write every full block of the window (everything when final)
-    void flush(bool final) {
-        size_t nblk = final ? (win.size() + BLK - 1) / BLK : win.size() / BLK;
-        if (nblk && !fail) {
-            std::vector<std::string> comp(nblk); std::vector<char> okv(nblk, 1);
-            bsx_parallel(threads, nblk, [&](int, size_t b, size_t e) {
-                for (size_t k = b; k < e; k++) okv[k] = bgzf_block((const unsigned char *)win.data() + k * BLK, std::min(BLK, win.size() - k * BLK), comp[k]) ? 1 : 0;
-            });
-            size_t good = 0; while (good < nblk && okv[good]) good++;
-            size_t used = 0;
-            for (size_t k = 0; k < good; k++) {
-                const size_t len = std::min(BLK, win.size() - k * BLK);
-                if (fwrite(comp[k].data(), 1, comp[k].size(), fo) != comp[k].size()) fail = true;
-                file_pos += comp[k].size(); used += len;
+    // Deflate and write every full block of the window (everything when final).  The blocks of a window are deflated on all
+    // threads by a background task while the caller goes on filling the next window (the producer -- an in-order walk over
+    // the sorted records or the merge of the runs -- is one thread; the deflate, at zlib's default level because the bytes
+    // must equal samtools', is the bulk of the work).  The index catches up with a window when its task is joined.
+    std::string job;                                  // the bytes the background task is working on
+    std::future<size_t> task;                         // -> bytes of `job` it consumed (all of them unless a block did not fit)
+    size_t deflate_job(bool final) {
+        const size_t nblk = (job.size() + BLK - 1) / BLK;
+        std::vector<std::string> comp(nblk); std::vector<char> okv(nblk, 1);
+        const double td0 = bam_now();
+        bsx_parallel(threads, nblk, [&](int, size_t b, size_t e) {
+            for (size_t k = b; k < e; k++) okv[k] = bgzf_block((const unsigned char *)job.data() + k * BLK, std::min(BLK, job.size() - k * BLK), comp[k]) ? 1 : 0;
+        });
+        const double td1 = bam_now(); t_deflate += td1 - td0;
+        size_t good = 0; while (good < nblk && okv[good]) good++;
+        size_t used = 0;
+        for (size_t k = 0; k < good; k++) {
+            const size_t len = std::min(BLK, job.size() - k * BLK);
+            if (fwrite(comp[k].data(), 1, comp[k].size(), fo) != comp[k].size()) fail = true;
+            file_pos += comp[k].size(); used += len;
+            blk_in_start.push_back(flushed + used); blk_file_start.push_back(file_pos);
+        }
+        if (good < nblk) {
+            // a block that does not fit is redone the way bgzf.c does it (1 KiB less input at a time), which shifts
+            // every later boundary -- never seen on BAM data.  What is left of the job goes back to the window.
+            while (used < job.size() && !fail) {
+                size_t len = std::min(BLK, job.size() - used); std::string c;
+                if (!final && len < BLK) break;
+                while (!bgzf_block((const unsigned char *)job.data() + used, len, c)) { if (len <= 1024) { fail = true; break; } len -= 1024; }
+                if (fail) break;
+                if (fwrite(c.data(), 1, c.size(), fo) != c.size()) fail = true;
+                file_pos += c.size(); used += len;
                 blk_in_start.push_back(flushed + used); blk_file_start.push_back(file_pos);
             }
-            if (good < nblk) {
-                // a block that does not fit is redone the way bgzf.c does it (1 KiB less input at a time), which shifts
-                // every later boundary of the window -- never seen on BAM data
-                const size_t stop = final ? win.size() : nblk * BLK;
-                while (used < stop && !fail) {
-                    size_t len = std::min(BLK, win.size() - used); std::string c;
-                    if (!final && used + len > stop) break;
-                    while (!bgzf_block((const unsigned char *)win.data() + used, len, c)) { if (len <= 1024) { fail = true; break; } len -= 1024; }
-                    if (fail) break;
-                    if (fwrite(c.data(), 1, c.size(), fo) != c.size()) fail = true;
-                    file_pos += c.size(); used += len;
-                    blk_in_start.push_back(flushed + used); blk_file_start.push_back(file_pos);
-                }
-            }
-            win.erase(0, used); flushed += used;
         }
-        index_ready(final);
+        flushed += used;
+        t_write += bam_now() - td1;
+        return used;
+    }
+    void join_task() {
+        if (!task.valid()) return;
+        const size_t used = task.get();
+        if (used < job.size()) win.insert(0, job, used, std::string::npos);   // the rare shifted-boundary case
+        job.clear();
+        const double ti0 = bam_now();
+        index_ready(false);
+        t_index += bam_now() - ti0;
+    }
+    void flush(bool final) {
+        join_task();
+        const size_t take = final ? win.size() : win.size() / BLK * BLK;
+        if (take && !fail) {
+            job.assign(win, 0, take); win.erase(0, take);
+            if (final) { deflate_job(true); if (!win.empty() && !fail) { job.swap(win); win.clear(); deflate_job(true); } job.clear(); }
+            else task = std::async(std::launch::async, [this] { return deflate_job(false); });
+        }
+        if (final) { const double ti0 = bam_now(); index_ready(true); t_index += bam_now() - ti0; }
     }
 };
 
@@ -311,9 +348,12 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
         q = nl ? le + 1 : n;
     }
     const size_t header_end = q;
-    std::unordered_map<std::string, int32_t> tids;
-    for (size_t k = 0; k < ref_names.size(); k++) tids.emplace(ref_names[k], (int32_t)k);   // first definition wins, like the hash in bam_aux.c
+    std::unordered_map<std::string_view, int32_t> tids;               // keys view ref_names (complete by now: no reallocation)
+    for (size_t k = 0; k < ref_names.size(); k++) tids.emplace(std::string_view(ref_names[k]), (int32_t)k);   // first definition wins, like the hash in bam_aux.c
 
+    const bool timing = getenv("BSX_CLI_TIMING") != nullptr;
+    const double t_begin = bam_now();
+    double t_encode = 0, t_sort = 0;
     // ---- sorted runs: the text in chunks cut at line starts
     size_t chunk_bytes = (size_t)1 << 30;
     if (const char *e = getenv("BSX_BAM_CHUNK_MB")) { const double mb = atof(e); if (mb > 0) chunk_bytes = (size_t)(mb * 1048576.0); }
@@ -331,6 +371,7 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
         if (ce < n) { const void *x = memchr(p + ce - 1, '\n', n - (ce - 1)); ce = x ? (size_t)((const char *)x - p) + 1 : n; }
         // records: byte ranges cut at line starts, one per thread
         const int tn = (ce - cb) < ((size_t)1 << 20) ? 1 : threads;
+        const double t_chunk0 = bam_now();
         for (auto &v : enc) v.clear();
         for (auto &v : recs) v.clear();
         bsx_parallel(tn, (size_t)tn, [&](int t, size_t, size_t) {
@@ -346,6 +387,8 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
                 b = le + 1;
             }
         });
+        t_encode += bam_now() - t_chunk0;
+        const double t_sort0 = bam_now();
         // stable sort by (tid, pos + 1).  (key, thread, index) is a total order that equals input order on equal keys, so
         // the threads sort slices with a plain sort and the slices are merged pairwise, level by level, in parallel.
         auto before = [](const Ord &a, const Ord &b) { return a.key != b.key ? a.key < b.key : (a.t != b.t ? a.t < b.t : a.i < b.i); };
@@ -366,16 +409,36 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
                 });
             }
         }
+        t_sort += bam_now() - t_sort0;
         if (cb == header_end && ce >= n) { in_memory = true; break; }    // the whole file is one chunk: no run files
         char name[32]; snprintf(name, sizeof name, ".run%04zu.tmp", run_paths.size());
         run_paths.push_back(std::string(bam_path) + name);
         FILE *fr = fopen(run_paths.back().c_str(), "wb");
         if (!fr) { cleanup(); bsx_set_error("cannot write %s", run_paths.back().c_str()); return BSX_ERR_IO; }
-        setvbuf(fr, nullptr, _IOFBF, 4 << 20);
-        for (const Ord &o : ord) {
-            const Rec &r = recs[o.t][o.i];
-            const Meta m{r.key, r.len, r.tid, r.pos, r.end, r.bin, 0};
-            if (fwrite(&m, sizeof m, 1, fr) != 1 || fwrite(enc[o.t].data() + r.off, 1, r.len, fr) != r.len) { io_fail = true; break; }
+        {
+            // the run = (Meta, record bytes) in sorted order.  Walking the sorted order touches the encoded records at random:
+            // all threads gather them into slabs of ~256 MB, each written with one call.
+            const size_t N = ord.size();
+            std::vector<uint32_t> sz(N);
+            bsx_parallel(threads, N, [&](int, size_t b, size_t e) { for (size_t j = b; j < e; j++) sz[j] = (uint32_t)sizeof(Meta) + recs[ord[j].t][ord[j].i].len; });
+            const size_t SLAB = (size_t)256 << 20;
+            std::unique_ptr<char[]> slab(new char[SLAB + (1 << 20)]);
+            std::vector<size_t> at;
+            for (size_t j0 = 0; j0 < N && !io_fail;) {
+                at.clear();
+                size_t bytes = 0, j1 = j0;
+                while (j1 < N && bytes + sz[j1] <= SLAB + (1 << 20) && (bytes < SLAB || j1 == j0)) { at.push_back(bytes); bytes += sz[j1++]; }
+                bsx_parallel(threads, j1 - j0, [&](int, size_t b, size_t e) {
+                    for (size_t j = j0 + b; j < j0 + e; j++) {
+                        const Rec &r = recs[ord[j].t][ord[j].i];
+                        const Meta m{r.key, r.len, r.tid, r.pos, r.end, r.bin, 0};
+                        char *w = slab.get() + at[j - j0];
+                        memcpy(w, &m, sizeof m); memcpy(w + sizeof m, enc[ord[j].t].data() + r.off, r.len);
+                    }
+                });
+                if (fwrite(slab.get(), 1, bytes, fr) != bytes) io_fail = true;
+                j0 = j1;
+            }
         }
         if (fclose(fr) != 0) io_fail = true;
         if (io_fail) { cleanup(); bsx_set_error("write to %s failed", run_paths.back().c_str()); return BSX_ERR_IO; }
@@ -387,6 +450,7 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
         std::vector<Ord>().swap(ord);
     }
 
+    const double t_phase1 = bam_now();
     // ---- the BAM: header, then the sorted records through the BGZF window
     BamSink sink(threads, ref_names.size());
     sink.fo = fopen(bam_path, "wb");
@@ -420,6 +484,8 @@ extern "C" int bsx_sam_to_sorted_bam(const char *sam_path, const char *bam_path,
         for (RunReader &r : rd) r.close();
     }
     sink.flush(true);
+    if (timing) fprintf(stderr, "[bsx timing] BAM: chunks %.3f s (encode %.3f s, sort %.3f s, the rest sorted runs), merge + BGZF %.3f s (deflate %.3f s in the background, write %.3f s, index %.3f s), total %.3f s (%d threads)\n",
+                        t_phase1 - t_begin, t_encode, t_sort, bam_now() - t_phase1, sink.t_deflate, sink.t_write, sink.t_index, bam_now() - t_begin, threads);
     std::string eof_block; bgzf_block((const unsigned char *)"", 0, eof_block);
     if (fwrite(eof_block.data(), 1, eof_block.size(), sink.fo) != eof_block.size()) sink.fail = true;
     if (fclose(sink.fo) != 0) sink.fail = true;
